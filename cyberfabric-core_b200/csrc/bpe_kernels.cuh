@@ -1,0 +1,517 @@
+// bpe_kernels.cuh -- the encode hot path as CUDA kernels for sm_100a.
+//
+//   K1 pretok_split_kernel   packed prompt bytes -> piece-start bitmask        
+//   K2 bpe_encode_kernel     pieces -> token ids (whole-piece lookup, then the
+//                            min-rank merge loop, one lane per byte)           (a2)
+//   K2b bpe_long_kernel      pieces longer than one warp window               (a2)
+//   K3 flag_count / tile_scan / emit_compact
+//                            token flags -> dense id stream + offsets + counts (a3, a4)
+//
+// Pure integer/indexing work: no tensor cores (north_star).  Bounds: HBM for the byte and id
+// streams, L2 latency for the rank-table lookups.
+//
+// The file compiles for the GPU with nvcc and, unchanged, for the CPU SIMT emulator used by
+// the non-GPU tests (tests/simt/cusim.h defines the CUDA builtins); there is no CPU fallback
+// in the product library.
+#pragma once
+#include <stdint.h>
+
+#include "pretok.cuh"
+#include "tables.h"
+
+namespace cfbpe {
+
+constexpr uint32_t kMaxVocabs = 8;
+constexpr uint32_t kSplitChunk = 64;     // bytes of text per K1 thread
+constexpr uint32_t kEncodeRange = 1024;  // bytes of text per K2 warp
+constexpr uint32_t kScanTileWords = 256;   // flag words per K3 tile (= 8 KiB of text); one word per thread
+
+struct VocabSet {
+    TablesView v[kMaxVocabs];
+};
+
+struct BatchView {
+    const uint8_t* bytes;      // packed prompt bytes (+ >= 16 bytes of readable padding)
+    const uint64_t* offsets;   // n_prompts + 1
+    const uint8_t* vocab_ids;  // n_prompts or nullptr
+    uint32_t n_prompts;
+    uint64_t total_bytes;
+};
+
+// status word written by the kernels
+struct DeviceStatus {
+    uint32_t bad_utf8;     // != 0: some prompt held malformed UTF-8
+    uint32_t n_long;       // number of long pieces queued for K2b
+    uint32_t long_overflow;
+    uint32_t pad;
+    uint64_t n_tokens;     // total ids produced (written by tile_scan)
+};
+
+struct LongPiece { uint64_t start; uint64_t end; uint32_t vocab; uint32_t pad; };
+
+// ---------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------
+// index of the prompt that contains byte position pos (pos < total): largest i with offsets[i] <= pos
+__device__ __forceinline__ uint32_t find_prompt(const uint64_t* __restrict__ offsets, uint32_t n, uint64_t pos) {
+    uint32_t lo = 0, hi = n;  // invariant: offsets[lo] <= pos < offsets[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= pos) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void or_bits(uint32_t* __restrict__ words, uint64_t word, uint32_t bits) {
+    if (bits) atomicOr(&words[word], bits);
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: pre-tokenizer split.  One thread per kSplitChunk bytes.  A thread starts at the first
+// sync point of its chunk (prompt start or is_sync_point) and scans matches until it stands
+// on a sync point at or beyond the end of its chunk -- which is where a later thread started.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict__ piece_bits, DeviceStatus* status) {
+    const uint64_t chunk = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t cs = chunk * kSplitChunk;
+    if (cs >= b.total_bytes) return;
+    const uint64_t ce = (cs + kSplitChunk < b.total_bytes) ? cs + kSplitChunk : b.total_bytes;
+    const uint8_t* __restrict__ s = b.bytes;
+
+    uint32_t pidx = find_prompt(b.offsets, b.n_prompts, cs);
+    uint64_t ps = b.offsets[pidx], pe = b.offsets[pidx + 1];
+
+    // ---- find the first sync point in [cs, ce)
+    uint64_t pos = cs;
+    bool found = false;
+    while (pos < ce) {
+        if (pos == pe) {  // step into the next non-empty prompt
+            do { ++pidx; ps = pe; pe = b.offsets[pidx + 1]; } while (pe == ps);
+        }
+        if (pos == ps || is_sync_point(s, pos, ps, pe, uc)) { found = true; break; }
+        ++pos;
+    }
+    if (!found) return;
+
+    // ---- scan matches
+    uint32_t pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
+    int bad = 0;
+    uint64_t cur_word = pos >> 5;
+    uint32_t cur_bits = 0;
+    for (;;) {
+        // pos is a match start inside prompt [ps, pe)
+        const uint64_t w = pos >> 5;
+        if (w != cur_word) { or_bits(piece_bits, cur_word, cur_bits); cur_word = w; cur_bits = 0; }
+        cur_bits |= 1u << (pos & 31);
+        pos = match_end(s, pos, pe, pat, uc, &bad);
+        if (pos >= b.total_bytes) break;
+        if (pos == pe) {
+            do { ++pidx; ps = pe; pe = b.offsets[pidx + 1]; } while (pe == ps);
+            pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
+            if (pos >= ce) break;  // a prompt start is a sync point: the owner of that chunk takes over
+            continue;
+        }
+        if (pos >= ce && (bad || is_sync_point(s, pos, ps, pe, uc))) break;
+    }
+    or_bits(piece_bits, cur_word, cur_bits);
+    if (bad) atomicOr(&status->bad_utf8, 1u);
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: encode.  One warp owns the pieces that START in its kEncodeRange bytes.  It walks them in
+// windows of up to 32 bytes made of whole pieces, one lane per byte:
+//   1. whole-piece lookup (CoreBPE's `if piece in ranks` shortcut) from the head lane;
+//   2. for the pieces that miss: parts = bytes, rank of each adjacent pair from the tables,
+//      then repeat { per-piece argmin (leftmost) by segmented warp shuffle; merge } until no
+//      pair of the piece is in the vocabulary (tiktoken/_educational.py:95-110);
+//   3. surviving lanes hold the ids: ids_by_pos[byte position] and one flag bit per id.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t lanemask_lt(uint32_t lane) { return (1u << lane) - 1u; }
+
+// 33 piece-start bits for positions ws .. ws+32 (bit i <-> ws+i); words beyond n_words read as 0
+__device__ __forceinline__ uint64_t load_bits33(const uint32_t* __restrict__ bits, uint64_t n_words, uint64_t ws) {
+    const uint64_t w = ws >> 5;
+    const uint32_t sh = static_cast<uint32_t>(ws & 31);
+    const uint64_t lo = bits[w];
+    const uint64_t hi = (w + 1 < n_words) ? bits[w + 1] : 0;
+    const uint64_t v = (lo | (hi << 32)) >> sh;   // 64 - sh >= 33 valid bits
+    return v & 0x1FFFFFFFFull;
+}
+
+// next set bit at position >= from and < limit in the bit array, or limit
+__device__ __forceinline__ uint64_t next_set_bit(const uint32_t* __restrict__ bits, uint64_t from, uint64_t limit) {
+    if (from >= limit) return limit;
+    uint64_t w = from >> 5;
+    uint32_t cur = bits[w] & (kFull << (from & 31));
+    const uint64_t wl = (limit + 31) >> 5;
+    while (!cur) {
+        if (++w >= wl) return limit;
+        cur = bits[w];
+    }
+    const uint64_t p = (w << 5) + (__ffs(cur) - 1);
+    return p < limit ? p : limit;
+}
+
+__global__ void __launch_bounds__(256)
+bpe_encode_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits,
+                  uint32_t* __restrict__ ids_by_pos,    // may be nullptr (count only)
+                  uint32_t* __restrict__ tok_bits, LongPiece* __restrict__ long_list, uint32_t long_cap,
+                  DeviceStatus* status) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t r0 = warp * kEncodeRange;
+    if (r0 >= b.total_bytes) return;   // whole warp exits together
+    const uint64_t r1 = (r0 + kEncodeRange < b.total_bytes) ? r0 + kEncodeRange : b.total_bytes;
+    const uint64_t n_words = (b.total_bytes + 31) >> 5;
+    const uint8_t* __restrict__ text = b.bytes;
+
+    uint64_t ws = next_set_bit(piece_bits, r0, r1);
+    if (ws >= r1) return;
+    uint32_t pidx = find_prompt(b.offsets, b.n_prompts, ws);
+    uint64_t pe = b.offsets[pidx + 1];
+    uint32_t vid = b.vocab_ids ? b.vocab_ids[pidx] : 0;
+    TablesView T = vs.v[vid];
+
+    while (ws < r1) {
+        // ---- window geometry (warp-uniform)
+        if (ws >= pe) {   // first piece of a later prompt (usually the next one)
+            if (pidx + 2 <= b.n_prompts && b.offsets[pidx + 2] > ws) ++pidx;
+            else pidx = find_prompt(b.offsets, b.n_prompts, ws);
+            pe = b.offsets[pidx + 1];
+            const uint32_t nv = b.vocab_ids ? b.vocab_ids[pidx] : 0;
+            if (nv != vid) { vid = nv; T = vs.v[vid]; }
+        }
+        const uint32_t avail = (pe - ws < 32) ? static_cast<uint32_t>(pe - ws) : 32u;
+        uint64_t pb = load_bits33(piece_bits, n_words, ws);          // bit i: a piece starts at ws+i
+        if (pe - ws <= 32) pb |= 1ull << (pe - ws);                  // the prompt end closes the last piece
+        const uint64_t bnd = pb & ~1ull & ((2ull << avail) - 1);     // boundaries at 1..avail
+        uint32_t wlen;
+        if (!bnd) {
+            // ---- piece longer than a window: queue it for K2b
+            uint64_t e = next_set_bit(piece_bits, ws + 32, pe);
+            if (lane == 0) {
+                const uint32_t slot = atomicAdd(&status->n_long, 1u);
+                if (slot < long_cap) { LongPiece lp; lp.start = ws; lp.end = e; lp.vocab = vid; lp.pad = 0; long_list[slot] = lp; }
+                else atomicOr(&status->long_overflow, 1u);
+            }
+            ws = e;   // pieces tile a prompt: e is the next piece start, or the prompt end
+            if (ws >= pe && ws < r1) ws = next_set_bit(piece_bits, ws, r1);
+            continue;
+        }
+        {
+            const uint64_t c = r1 - ws;   // pieces starting at >= r1 belong to the next warp
+            const uint64_t at_or_after = (c <= 32) ? (bnd >> c) << c : 0;
+            if (at_or_after) wlen = static_cast<uint32_t>(__ffsll(static_cast<long long>(at_or_after)) - 1);
+            else wlen = 63u - static_cast<uint32_t>(__clzll(static_cast<long long>(bnd)));
+        }
+        const uint32_t wmask = (wlen >= 32) ? kFull : ((1u << wlen) - 1u);
+        const uint32_t heads = static_cast<uint32_t>(pb) & wmask;            // piece starts inside the window
+        const bool active = lane < wlen;
+
+        // ---- per-lane piece geometry
+        const uint32_t my_byte = active ? text[ws + lane] : 0u;
+        const uint32_t head_lane = 31u - __clz(heads & (lanemask_lt(lane) | (1u << lane)));   // start of my piece
+        const uint32_t above = heads & ~(lanemask_lt(lane) | (1u << lane));
+        const uint32_t piece_end = above ? (__ffs(above) - 1u) : wlen;                        // one past my piece
+        const bool is_head = active && ((heads >> lane) & 1u);
+        const uint32_t plen = piece_end - head_lane;
+
+        // ---- whole-piece lookup: gather up to 12 bytes of key from the lanes to the right
+        uint32_t w4 = my_byte;
+        w4 |= __shfl_down_sync(kFull, my_byte, 1) << 8;
+        w4 |= __shfl_down_sync(kFull, my_byte, 2) << 16;
+        w4 |= __shfl_down_sync(kFull, my_byte, 3) << 24;                   // bytes lane..lane+3 (garbage past wlen is masked below)
+        const uint32_t w4b = __shfl_down_sync(kFull, w4, 4);
+        const uint32_t w4c = __shfl_down_sync(kFull, w4, 8);
+        uint32_t tok = kNone;
+        if (is_head && plen <= T.max_token_len) {
+            uint64_t k0 = static_cast<uint64_t>(w4) | (static_cast<uint64_t>(w4b) << 32);
+            uint32_t k1 = w4c;
+            if (plen < 8) k0 &= (1ull << (8 * plen)) - 1ull;
+            if (plen <= 8) k1 = 0; else if (plen < 12) k1 &= (1u << (8 * (plen - 8))) - 1u;
+            if (plen <= kShortMaxLen) {
+                tok = short_lookup(T, k0, k1, plen);
+            } else {
+                const uint8_t* p = text + ws + lane;
+                tok = long_lookup(T, long_hash(k0, k1, load_le32(p + plen - 4), plen), p, plen);
+            }
+        }
+        const uint32_t hit_heads = __ballot_sync(kFull, tok != kNone);
+        // lanes of pieces that still need the merge loop
+        const bool unresolved = active && !((hit_heads >> head_lane) & 1u);
+        uint32_t alive = __ballot_sync(kFull, unresolved);      // one part per byte
+        uint32_t out_mask = hit_heads;                          // lanes that hold a final id
+
+        if (alive) {
+            uint32_t id = unresolved ? T.byte2id[my_byte] : kNone;
+            // rank of (my part, next part); initial parts are single bytes -> direct byte-pair table
+            const uint32_t nb = __shfl_down_sync(kFull, my_byte, 1);
+            uint32_t rank = kNone;
+            if (unresolved && lane + 1 < piece_end) rank = T.bytepair[(my_byte << 8) | nb];
+            for (;;) {
+                // -- segmented argmin over each piece: key = rank<<5 | lane (rank < 2^21), leftmost wins ties
+                uint32_t key = (rank != kNone) ? ((rank << 5) | lane) : kNone;
+#pragma unroll
+                for (uint32_t d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_down_sync(kFull, key, d);
+                    if (lane + d < piece_end && o < key) key = o;
+                }
+                const uint32_t best = __shfl_sync(kFull, key, head_lane);   // min over my piece
+                if (!__any_sync(kFull, unresolved && best != kNone)) break;
+                const bool winner = unresolved && best != kNone && (best & 31u) == lane;
+                const uint32_t winners = __ballot_sync(kFull, winner);
+                // -- kill the right partner of every winner: I die if the alive lane before me is a winner
+                const uint32_t below = alive & lanemask_lt(lane);
+                const uint32_t prev_alive = below ? (31u - __clz(below)) : 32u;
+                const bool i_am_alive = (alive >> lane) & 1u;
+                const bool die = i_am_alive && prev_alive < 32u && ((winners >> prev_alive) & 1u);
+                const uint32_t dead = __ballot_sync(kFull, die);
+                alive &= ~dead;
+                if (winner) id = best >> 5;                        // rank == id of the merged token
+                // -- refresh the two ranks each merge touches
+                const uint32_t nxt_mask = alive & ~(lanemask_lt(lane) | (1u << lane));
+                const uint32_t nxt = nxt_mask ? (__ffs(nxt_mask) - 1u) : 32u;
+                const uint32_t nid = __shfl_sync(kFull, id, nxt & 31u);
+                const bool alive_now = (alive >> lane) & 1u;
+                const bool nxt_is_winner = nxt < 32u && ((winners >> nxt) & 1u);
+                if (alive_now && unresolved && (winner || nxt_is_winner)) {
+                    rank = (nxt < piece_end) ? pair_lookup(T, id, nid) : kNone;
+                }
+                if (!alive_now) rank = kNone;
+            }
+            if (unresolved && ((alive >> lane) & 1u)) tok = id;
+            out_mask |= alive;
+        }
+
+        // ---- emit
+        if ((out_mask >> lane) & 1u) {
+            if (ids_by_pos) ids_by_pos[ws + lane] = tok;
+        }
+        if (lane == 0) {
+            const uint64_t w = ws >> 5;
+            const uint32_t sh = static_cast<uint32_t>(ws & 31);
+            atomicOr(&tok_bits[w], out_mask << sh);
+            if (sh && (out_mask >> (32 - sh))) atomicOr(&tok_bits[w + 1], out_mask >> (32 - sh));
+        }
+        ws += wlen;
+        if (ws >= pe && ws < r1) ws = next_set_bit(piece_bits, ws, r1);   // skip empty prompts / reach next prompt's first piece
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2b: pieces longer than 32 bytes.  One CTA per piece.  Exact sequential semantics: each
+// round finds the global minimum rank (leftmost) with a block reduction and applies that one
+// merge.  State lives in the piece's own slice of four per-byte arrays: ids (ids_by_pos; kNone
+// marks a dead slot), rank of the pair starting there, and next/prev alive links.
+// ---------------------------------------------------------------------------------------
+struct LongScratch {
+    uint32_t* rank;   // u32 per byte position
+    uint32_t* next;
+    uint32_t* prev;
+};
+
+__global__ void __launch_bounds__(256)
+bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, const DeviceStatus* status,
+                uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
+    __shared__ unsigned long long s_red[8];
+    __shared__ unsigned long long s_best;
+    uint32_t n_long = status->n_long;
+    if (n_long > long_cap) n_long = long_cap;
+    for (uint32_t item = blockIdx.x; item < n_long; item += gridDim.x) {
+        const LongPiece lp = long_list[item];
+        const TablesView T = vs.v[lp.vocab];
+        const uint8_t* __restrict__ p = b.bytes + lp.start;
+        const uint32_t n = static_cast<uint32_t>(lp.end - lp.start);
+        uint32_t* __restrict__ ids = ids_by_pos + lp.start;
+        uint32_t* __restrict__ rk = sc.rank + lp.start;
+        uint32_t* __restrict__ nx = sc.next + lp.start;   // index of the next alive part (n = none)
+        uint32_t* __restrict__ pv = sc.prev + lp.start;   // index of the previous alive part (kNone = none)
+        const uint32_t tid = threadIdx.x, nt = blockDim.x;
+
+        // whole-piece shortcut (CoreBPE: `if piece in ranks`)
+        if (n <= T.max_token_len) {
+            if (tid == 0) s_best = piece_lookup(T, p, n);
+            __syncthreads();
+            const uint32_t t = static_cast<uint32_t>(s_best);
+            __syncthreads();
+            if (t != kNone) {
+                if (tid == 0) {
+                    ids[0] = t;
+                    atomicOr(&tok_bits[lp.start >> 5], 1u << (lp.start & 31));
+                }
+                continue;
+            }
+        }
+        for (uint32_t i = tid; i < n; i += nt) {
+            ids[i] = T.byte2id[p[i]];
+            rk[i] = (i + 1 < n) ? T.bytepair[(static_cast<uint32_t>(p[i]) << 8) | p[i + 1]] : kNone;
+            nx[i] = i + 1;
+            pv[i] = i ? i - 1 : kNone;
+        }
+        __syncthreads();
+        for (;;) {
+            // block argmin of (rank, index): leftmost minimum
+            unsigned long long best = ~0ull;
+            for (uint32_t i = tid; i < n; i += nt) {
+                const uint32_t r = rk[i];
+                if (r != kNone) {
+                    const unsigned long long k = (static_cast<unsigned long long>(r) << 32) | i;
+                    if (k < best) best = k;
+                }
+            }
+#pragma unroll
+            for (uint32_t d = 16; d; d >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(kFull, best, d);
+                if (o < best) best = o;
+            }
+            if ((tid & 31) == 0) s_red[tid >> 5] = best;
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long m = ~0ull;
+                for (uint32_t w = 0; w < (nt + 31) / 32; ++w) if (s_red[w] < m) m = s_red[w];
+                s_best = m;
+                if (m != ~0ull) {
+                    const uint32_t i = static_cast<uint32_t>(m);
+                    const uint32_t merged = static_cast<uint32_t>(m >> 32);   // rank == id of the merged token
+                    const uint32_t j = nx[i];        // right partner
+                    const uint32_t k = nx[j];        // part after the partner, or n
+                    ids[i] = merged;
+                    ids[j] = kNone;                  // partner dies
+                    rk[j] = kNone;
+                    nx[i] = k;
+                    if (k < n) pv[k] = i;
+                    rk[i] = (k < n) ? pair_lookup(T, merged, ids[k]) : kNone;
+                    const uint32_t q = pv[i];
+                    if (q != kNone) rk[q] = pair_lookup(T, ids[q], merged);
+                }
+            }
+            __syncthreads();
+            const bool done = (s_best == ~0ull);
+            __syncthreads();
+            if (done) break;
+        }
+        // one flag per surviving part
+        for (uint32_t i = tid; i < n; i += nt) {
+            if (ids[i] != kNone) {
+                const uint64_t pos = lp.start + i;
+                atomicOr(&tok_bits[pos >> 5], 1u << (pos & 31));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: flags -> dense output.
+//   flag_count:   popcount of each tile of kScanTileWords flag words
+//   tile_scan:    exclusive scan of the tile counts (single CTA), total -> status->n_tokens
+//   emit_compact: out_ids[rank(pos)] = ids_by_pos[pos]; out_offsets[p] = rank(offsets[p]); counts
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_reduce_add_256(uint32_t v, uint32_t* s_tmp) {
+#pragma unroll
+    for (uint32_t d = 16; d; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t t = 0;
+    for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) t += s_tmp[w];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+flag_count_kernel(const uint32_t* __restrict__ tok_bits, uint64_t n_words, uint32_t* __restrict__ tile_counts) {
+    __shared__ uint32_t s_tmp[8];
+    const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanTileWords;
+    uint32_t c = 0;
+    for (uint32_t i = threadIdx.x; i < kScanTileWords; i += blockDim.x) {
+        const uint64_t w = base + i;
+        if (w < n_words) c += __popc(tok_bits[w]);
+    }
+    const uint32_t t = block_reduce_add_256(c, s_tmp);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = t;
+}
+
+// single CTA; n_tiles arbitrary (looped)
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(const uint32_t* __restrict__ tile_counts, uint32_t n_tiles, uint64_t* __restrict__ tile_base,
+                 DeviceStatus* status) {
+    __shared__ uint64_t s_warp[32];
+    __shared__ uint64_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n_tiles; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t v = (i < n_tiles) ? tile_counts[i] : 0;
+        uint64_t x = v;
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const uint64_t o = __shfl_up_sync(kFull, x, d);
+            if (lane >= d) x += o;
+        }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        uint64_t woff = 0;
+        for (uint32_t w = 0; w < wid; ++w) woff += s_warp[w];
+        const uint64_t carry = s_carry;
+        if (i < n_tiles) tile_base[i] = carry + woff + x - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + woff + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) status->n_tokens = s_carry;
+}
+
+__global__ void __launch_bounds__(256)
+emit_compact_kernel(const uint32_t* __restrict__ tok_bits, uint64_t n_words, const uint64_t* __restrict__ tile_base,
+                    const uint32_t* __restrict__ ids_by_pos, uint32_t* __restrict__ out_ids, uint64_t out_cap) {
+    // one CTA per tile of kScanTileWords (= blockDim.x) flag words, one word per thread
+    __shared__ uint32_t s_warp[8];
+    const uint64_t w = static_cast<uint64_t>(blockIdx.x) * kScanTileWords + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t bits = (w < n_words) ? tok_bits[w] : 0u;
+    const uint32_t c = __popc(bits);
+    uint32_t x = c;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(kFull, x, d);
+        if (lane >= d) x += o;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (uint32_t k = 0; k < wid; ++k) woff += s_warp[k];
+    uint64_t r = tile_base[blockIdx.x] + woff + (x - c);
+    uint32_t rest = bits;
+    while (rest) {
+        const uint32_t bit = __ffs(rest) - 1;
+        rest &= rest - 1;
+        if (r < out_cap) out_ids[r] = ids_by_pos[(w << 5) + bit];
+        ++r;
+    }
+}
+
+// out_offsets[p] = number of flags before byte offsets[p]; counts[p] = difference.  One thread per prompt.
+__global__ void __launch_bounds__(256)
+prompt_offsets_kernel(BatchView b, const uint32_t* __restrict__ tok_bits, const uint64_t* __restrict__ tile_base,
+                      uint64_t* __restrict__ out_offsets, uint32_t* __restrict__ out_counts, const DeviceStatus* status) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i > b.n_prompts) return;
+    auto rank_at = [&](uint64_t pos) -> uint64_t {
+        if (pos >= b.total_bytes) return status->n_tokens;
+        const uint64_t w = pos >> 5;
+        const uint64_t tile = w / kScanTileWords;
+        uint64_t r = tile_base[tile];
+        for (uint64_t k = tile * kScanTileWords; k < w; ++k) r += __popc(tok_bits[k]);
+        r += __popc(tok_bits[w] & ((1u << (pos & 31)) - 1u));
+        return r;
+    };
+    const uint64_t r = rank_at(b.offsets[i]);
+    out_offsets[i] = r;
+    if (i < b.n_prompts && out_counts) out_counts[i] = static_cast<uint32_t>(rank_at(b.offsets[i + 1]) - r);
+}
+
+}  // namespace cfbpe

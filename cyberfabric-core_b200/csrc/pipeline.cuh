@@ -1,0 +1,79 @@
+// pipeline.cuh -- the launch sequence of one encode pass (shared by libcfbpe.so and the
+// non-GPU SIMT-emulator tests so that both run the same kernels in the same order).
+//
+// The including translation unit supplies three macros:
+//   CFBPE_LAUNCH(kernel, grid, block, stream, ...)   launch
+//   CFBPE_ZERO(ptr, bytes, stream)                   asynchronous zero fill
+//   CFBPE_MARK(prof, idx, stream, begin)             optional per-kernel event record
+#pragma once
+#include "bpe_kernels.cuh"
+
+namespace cfbpe {
+
+struct Workspace {
+    uint32_t* piece_bits;   // 1 bit per byte: a piece starts here          [n_words + 2]
+    uint32_t* tok_bits;     // 1 bit per byte: a token id lives here        [n_words + 2]
+    uint32_t* ids_by_pos;   // token id at the byte position of its first byte [total]
+    LongScratch lscratch;   // K2b per-byte state                            [total] each
+    LongPiece* long_list;
+    uint32_t long_cap;
+    uint32_t* tile_counts;  // [n_tiles]
+    uint64_t* tile_base;    // [n_tiles]
+    DeviceStatus* status;
+};
+
+enum KernelIdx { K_SPLIT = 0, K_ENCODE = 1, K_LONG = 2, K_COUNT = 3, K_SCAN = 4, K_EMIT = 5 };
+
+inline uint64_t n_flag_words(uint64_t total_bytes) { return (total_bytes + 31) >> 5; }
+inline uint32_t n_scan_tiles(uint64_t total_bytes) {
+    return static_cast<uint32_t>((n_flag_words(total_bytes) + kScanTileWords - 1) / kScanTileWords);
+}
+
+// Enqueue the whole path.  out_ids may be nullptr (count only).  Everything is asynchronous on `stream`.
+template <typename Stream, typename Prof>
+inline void enqueue_encode(const BatchView& b, const VocabSet& vs, const UcTables& uc, const Workspace& w,
+                           uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_counts,
+                           uint32_t long_grid, Stream stream, Prof* prof) {
+    const uint64_t nw = n_flag_words(b.total_bytes);
+    const uint32_t nt = n_scan_tiles(b.total_bytes);
+    CFBPE_ZERO(w.status, sizeof(DeviceStatus), stream);
+    if (b.total_bytes) {
+        CFBPE_ZERO(w.piece_bits, (nw + 2) * sizeof(uint32_t), stream);
+        CFBPE_ZERO(w.tok_bits, (nw + 2) * sizeof(uint32_t), stream);
+
+        const uint64_t n_chunks = (b.total_bytes + kSplitChunk - 1) / kSplitChunk;
+        CFBPE_MARK(prof, K_SPLIT, stream, true);
+        CFBPE_LAUNCH(pretok_split_kernel, static_cast<unsigned>((n_chunks + 255) / 256), 256, stream,
+                     b, vs, uc, w.piece_bits, w.status);
+        CFBPE_MARK(prof, K_SPLIT, stream, false);
+
+        const uint64_t n_warps = (b.total_bytes + kEncodeRange - 1) / kEncodeRange;
+        CFBPE_MARK(prof, K_ENCODE, stream, true);
+        CFBPE_LAUNCH(bpe_encode_kernel, static_cast<unsigned>((n_warps + 7) / 8), 256, stream,
+                     b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
+        CFBPE_MARK(prof, K_ENCODE, stream, false);
+
+        CFBPE_MARK(prof, K_LONG, stream, true);
+        CFBPE_LAUNCH(bpe_long_kernel, long_grid, 256, stream,
+                     b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
+        CFBPE_MARK(prof, K_LONG, stream, false);
+
+        CFBPE_MARK(prof, K_COUNT, stream, true);
+        CFBPE_LAUNCH(flag_count_kernel, nt, 256, stream, w.tok_bits, nw, w.tile_counts);
+        CFBPE_MARK(prof, K_COUNT, stream, false);
+        CFBPE_MARK(prof, K_SCAN, stream, true);
+        CFBPE_LAUNCH(tile_scan_kernel, 1u, 1024, stream, w.tile_counts, nt, w.tile_base, w.status);
+        CFBPE_MARK(prof, K_SCAN, stream, false);
+        CFBPE_MARK(prof, K_EMIT, stream, true);
+        if (out_ids) {
+            CFBPE_LAUNCH(emit_compact_kernel, nt, 256, stream, w.tok_bits, nw, w.tile_base, w.ids_by_pos, out_ids, out_cap);
+        }
+    } else {
+        CFBPE_MARK(prof, K_EMIT, stream, true);
+    }
+    CFBPE_LAUNCH(prompt_offsets_kernel, static_cast<unsigned>((static_cast<uint64_t>(b.n_prompts) + 1 + 255) / 256), 256, stream,
+                 b, w.tok_bits, w.tile_base, out_offsets, out_counts, w.status);
+    CFBPE_MARK(prof, K_EMIT, stream, false);
+}
+
+}  // namespace cfbpe

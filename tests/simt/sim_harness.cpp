@@ -1,0 +1,115 @@
+// sim_harness.cpp -- runs the product's CUDA kernels on the CPU SIMT emulator (tests/simt/cusim.h).
+// TEST INFRASTRUCTURE: built by tests/simt/build.py into tests/simt/_build/libcfbpe_sim.so and
+// loaded only by the non-GPU tests.  The table builder (csrc/vocab.cpp) and the kernels
+// (csrc/bpe_kernels.cuh, csrc/pipeline.cuh) are the product sources, compiled unchanged.
+#include "cusim.h"
+
+#define CFBPE_LAUNCH(kernel, grid, block, stream, ...) cusim::launch((grid), (block), [&] { kernel(__VA_ARGS__); })
+#define CFBPE_ZERO(ptr, bytes, stream) std::memset((ptr), 0, (bytes))
+#define CFBPE_MARK(prof, idx, stream, begin) ((void)0)
+
+#include <string>
+#include <vector>
+
+#include "../../cyberfabric-core_b200/csrc/pipeline.cuh"
+#include "../../cyberfabric-core_b200/csrc/unicode_tables.h"
+#include "../../cyberfabric-core_b200/csrc/vocab.h"
+#include "../../include/cfbpe.h"
+
+using namespace cfbpe;
+
+struct SimVocab {
+    std::vector<uint8_t> blob;
+    TablesHeader hdr;
+};
+
+static UcTables uc_tables() { return UcTables{cfbpe_uc_stage1, cfbpe_uc_stage2}; }
+
+extern "C" {
+
+__attribute__((visibility("default"))) void* sim_vocab_build(const uint8_t* file, size_t len, uint32_t format,
+                                                             uint32_t pattern, uint32_t max_ranks, char* err, size_t errcap) {
+    std::vector<std::string> toks;
+    std::string e;
+    int rc = (format == CFBPE_FORMAT_TEKKEN_JSON) ? parse_tekken_json(file, len, max_ranks, toks, e)
+                                                  : parse_tiktoken(file, len, max_ranks, toks, e);
+    SimVocab* v = nullptr;
+    if (rc == 0) {
+        v = new SimVocab();
+        rc = build_tables(toks, pattern, v->blob, e);
+        if (rc == 0) rc = validate_tables(v->blob.data(), v->blob.size(), e);
+        if (rc != 0) { delete v; v = nullptr; }
+        else std::memcpy(&v->hdr, v->blob.data(), sizeof(TablesHeader));
+    }
+    if (!v && err && errcap) { std::snprintf(err, errcap, "%s", e.c_str()); }
+    return v;
+}
+__attribute__((visibility("default"))) void sim_vocab_free(void* v) { delete static_cast<SimVocab*>(v); }
+__attribute__((visibility("default"))) void sim_vocab_info(void* vp, cfbpe_vocab_info* out) {
+    SimVocab* v = static_cast<SimVocab*>(vp);
+    out->n_ranks = v->hdr.n_ranks; out->pattern_id = v->hdr.pattern_id; out->max_token_len = v->hdr.max_token_len;
+    out->n_pair_entries = v->hdr.n_pair_entries; out->table_bytes = v->hdr.total_bytes;
+}
+// host-side lookups through the packed tables (table-builder tests)
+__attribute__((visibility("default"))) uint32_t sim_piece_lookup(void* vp, const uint8_t* p, uint32_t n) {
+    SimVocab* v = static_cast<SimVocab*>(vp);
+    std::vector<uint8_t> tmp(p, p + n); tmp.resize(n + 16);
+    return piece_lookup(make_view(v->blob.data(), v->hdr), tmp.data(), n);
+}
+__attribute__((visibility("default"))) uint32_t sim_pair_lookup(void* vp, uint32_t l, uint32_t r) {
+    SimVocab* v = static_cast<SimVocab*>(vp);
+    return pair_lookup(make_view(v->blob.data(), v->hdr), l, r);
+}
+
+// K1 only: piece-start bits (n_words+2 words) for a packed batch; patterns[] per vocab id
+__attribute__((visibility("default"))) int sim_split(const uint32_t* patterns, uint32_t n_patterns, uint32_t n_prompts,
+                                                     const uint8_t* bytes, const uint64_t* offsets, const uint8_t* vocab_ids,
+                                                     uint32_t* piece_bits) {
+    const uint64_t total = offsets[n_prompts];
+    std::vector<uint8_t> padded(bytes, bytes + total); padded.resize(total + 64);
+    BatchView b{padded.data(), offsets, vocab_ids, n_prompts, total};
+    VocabSet vs{};
+    for (uint32_t i = 0; i < n_patterns && i < kMaxVocabs; ++i) vs.v[i].pattern_id = patterns[i];
+    DeviceStatus st{};
+    const uint64_t nw = n_flag_words(total);
+    std::memset(piece_bits, 0, (nw + 2) * 4);
+    if (total) {
+        const uint64_t n_chunks = (total + kSplitChunk - 1) / kSplitChunk;
+        UcTables uc = uc_tables();
+        cusim::launch(static_cast<unsigned>((n_chunks + 255) / 256), 256, [&] { pretok_split_kernel(b, vs, uc, piece_bits, &st); });
+    }
+    return st.bad_utf8 ? CFBPE_EILSEQ : 0;
+}
+
+// the whole path (K1..K3) on host memory
+__attribute__((visibility("default"))) int sim_encode_batch(void* const* vocabs, uint32_t n_vocabs, uint32_t n_prompts,
+                                                            const uint8_t* bytes, const uint64_t* offsets, const uint8_t* vocab_ids,
+                                                            uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets,
+                                                            uint32_t* out_counts, uint64_t* n_long_out) {
+    const uint64_t total = offsets[n_prompts];
+    std::vector<uint8_t> padded(bytes, bytes + total); padded.resize(total + 64);
+    BatchView b{padded.data(), offsets, vocab_ids, n_prompts, total};
+    VocabSet vs{};
+    for (uint32_t i = 0; i < n_vocabs && i < kMaxVocabs; ++i) {
+        SimVocab* v = static_cast<SimVocab*>(vocabs[i]);
+        vs.v[i] = make_view(v->blob.data(), v->hdr);
+    }
+    const uint64_t nw = n_flag_words(total);
+    const uint32_t nt = n_scan_tiles(total);
+    std::vector<uint32_t> piece_bits(nw + 2), tok_bits(nw + 2), ids(total + 1, 0xDEADBEEF), rk(total + 1), nx(total + 1), pv(total + 1);
+    std::vector<uint32_t> tile_counts(nt + 1);
+    std::vector<uint64_t> tile_base(nt + 1);
+    std::vector<LongPiece> ll(total / 32 + 1);
+    DeviceStatus st{};
+    Workspace w{piece_bits.data(), tok_bits.data(), ids.data(), LongScratch{rk.data(), nx.data(), pv.data()},
+                ll.data(), static_cast<uint32_t>(ll.size()), tile_counts.data(), tile_base.data(), &st};
+    int* prof = nullptr;
+    enqueue_encode(b, vs, uc_tables(), w, out_ids, out_cap, out_offsets, out_counts, 4u, 0, prof);
+    if (n_long_out) *n_long_out = st.n_long;
+    if (st.bad_utf8) return CFBPE_EILSEQ;
+    if (st.long_overflow) return CFBPE_EIO;
+    if (out_ids && st.n_tokens > out_cap) return CFBPE_ENOSPC;
+    return 0;
+}
+
+}  // extern "C"

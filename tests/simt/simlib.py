@@ -1,0 +1,102 @@
+"""ctypes binding of the SIMT-emulator harness (test infrastructure)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import build as _build  # noqa: E402
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(_build.build())
+        L.sim_vocab_build.restype = C.c_void_p
+        L.sim_vocab_build.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]
+        L.sim_vocab_free.argtypes = [C.c_void_p]
+        L.sim_vocab_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.sim_piece_lookup.restype = C.c_uint32
+        L.sim_piece_lookup.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
+        L.sim_pair_lookup.restype = C.c_uint32
+        L.sim_pair_lookup.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.sim_split.restype = C.c_int
+        L.sim_split.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sim_encode_batch.restype = C.c_int
+        L.sim_encode_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class SimVocab:
+    def __init__(self, file_bytes, fmt, pattern, max_ranks=0):
+        err = C.create_string_buffer(256)
+        self._h = lib().sim_vocab_build(file_bytes, len(file_bytes), fmt, pattern, max_ranks, err, 256)
+        if not self._h:
+            raise ValueError(err.value.decode())
+        info = (C.c_uint32 * 6)()
+        lib().sim_vocab_info(self._h, info)
+        self.n_ranks, self.pattern_id, self.max_token_len, self.n_pair_entries = info[0], info[1], info[2], info[3]
+        self.table_bytes = info[4] | (info[5] << 32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().sim_vocab_free(self._h)
+            self._h = None
+
+    def piece_lookup(self, b: bytes):
+        return lib().sim_piece_lookup(self._h, b, len(b))
+
+    def pair_lookup(self, l, r):
+        return lib().sim_pair_lookup(self._h, l, r)
+
+
+def pack(prompts):
+    """list[bytes] -> (uint8 array, uint64 offsets)"""
+    offs = np.zeros(len(prompts) + 1, dtype=np.uint64)
+    if prompts:
+        offs[1:] = np.cumsum([len(p) for p in prompts], dtype=np.uint64)
+    data = np.frombuffer(b"".join(prompts), dtype=np.uint8).copy() if prompts else np.zeros(0, np.uint8)
+    return data, offs
+
+
+def split(patterns, prompts, vocab_ids=None):
+    """piece END offsets per prompt (relative to the prompt) from the K1 bitmask"""
+    data, offs = pack(prompts)
+    total = int(offs[-1])
+    nw = (total + 31) // 32
+    bits = np.zeros(nw + 2, dtype=np.uint32)
+    pats = np.asarray(patterns, dtype=np.uint32)
+    vid = None if vocab_ids is None else np.ascontiguousarray(vocab_ids, dtype=np.uint8)
+    dbuf = np.concatenate([data, np.zeros(8, np.uint8)])
+    rc = lib().sim_split(pats.ctypes.data, len(pats), len(prompts), dbuf.ctypes.data, offs.ctypes.data,
+                         None if vid is None else vid.ctypes.data, bits.ctypes.data)
+    flags = np.unpackbits(bits.view(np.uint8), bitorder="little")[:total]
+    out = []
+    for i in range(len(prompts)):
+        a, b = int(offs[i]), int(offs[i + 1])
+        starts = np.nonzero(flags[a:b])[0]
+        ends = list(starts[1:]) + ([b - a] if b > a else [])
+        out.append([int(e) for e in ends])
+    return rc, out
+
+
+def encode_batch(vocabs, prompts, vocab_ids=None, out_cap=None):
+    data, offs = pack(prompts)
+    total = int(offs[-1])
+    cap = total + 1 if out_cap is None else out_cap
+    ids = np.zeros(max(cap, 1), dtype=np.uint32)
+    out_off = np.zeros(len(prompts) + 1, dtype=np.uint64)
+    counts = np.zeros(max(len(prompts), 1), dtype=np.uint32)
+    vh = (C.c_void_p * len(vocabs))(*[v._h for v in vocabs])
+    vid = None if vocab_ids is None else np.ascontiguousarray(vocab_ids, dtype=np.uint8)
+    nlong = C.c_uint64(0)
+    dbuf = np.concatenate([data, np.zeros(8, np.uint8)])
+    rc = lib().sim_encode_batch(vh, len(vocabs), len(prompts), dbuf.ctypes.data, offs.ctypes.data,
+                                None if vid is None else vid.ctypes.data, ids.ctypes.data, cap,
+                                out_off.ctypes.data, counts.ctypes.data, C.byref(nlong))
+    return rc, ids, out_off, counts[:len(prompts)], nlong.value
