@@ -1,0 +1,320 @@
+"""Python mirror of the ModKit plugin surface the tokenizer sits behind.
+
+The Rust toolchain is absent from this image, so the host side above the C ABI
+is written here with the names, argument meaning and error behaviour a ModKit plugin has
+(INTEGRATION.md shows the Rust crates a maintainer would add).  Conventions mirrored, with
+the reference file each one follows:
+
+* plugin trait name ends in `PluginClient` (lint DE0503, dylint_lints/README.md:36); methods
+  take the SecurityContext first and return Result<_, XError>
+  (modules/system/tenant-resolver/tenant-resolver-sdk/src/plugin_api.rs:28-47);
+* error enum with NoPluginAvailable / ServiceUnavailable(String) / Internal(String)
+  (modules/system/tenant-resolver/tenant-resolver-sdk/src/error.rs:7-34);
+* a plugin registers a GTS instance {id, vendor, priority, properties}
+  (libs/modkit/src/gts/plugin.rs:12-17) and a client scoped by that instance id
+  (libs/modkit/src/client_hub.rs:142-234); the gateway picks vendor match, lowest priority
+  (libs/modkit/src/plugins/mod.rs:136-191) and resolves lazily, once;
+* token counts feed Usage.input_tokens >= 0
+  (modules/llm-gateway/llm-gateway-sdk/schemas/core/usage.v1.schema.json:8-12) and are the sum over a
+  request's TextContent.text parts (schemas/content/text_content.v1.schema.json,
+  schemas/core/message.v1.schema.json).
+
+Prompt text is never logged (modules/llm-gateway/docs/DESIGN.md:120-124): only sizes and counts.
+"""
+from __future__ import annotations
+
+import threading
+import uuid
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from . import vocabs as V
+
+
+# --------------------------------------------------------------------------- errors
+class TokenizerError(Exception):
+    """base of the SDK error enum (`TokenizerError` in the planned llm-gateway-sdk)"""
+
+
+class NoPluginAvailable(TokenizerError):
+    pass
+
+
+class ServiceUnavailable(TokenizerError):
+    pass
+
+
+class Internal(TokenizerError):
+    pass
+
+
+class InvalidInput(TokenizerError):
+    """bad offsets / malformed UTF-8 / oversize batch (maps to RFC 9457 Problem 400)"""
+
+
+class VocabNotFound(TokenizerError):
+    pass
+
+
+def _map_native(e: N.NativeError) -> TokenizerError:
+    if e.code in (N.EINVAL, N.EILSEQ, N.ENOSPC):
+        return InvalidInput(str(e))
+    if e.code == N.ENOENT:
+        return VocabNotFound(str(e))
+    if e.code in (N.ENODEV, N.ENOMEM):
+        return ServiceUnavailable(str(e))
+    return Internal(str(e))
+
+
+# --------------------------------------------------------------------------- boundary types
+@dataclass(frozen=True)
+class SecurityContext:
+    """libs/modkit-security/src/context.rs:23-39 (tenant identity carried on every plugin call)"""
+    subject_id: uuid.UUID
+    subject_tenant_id: uuid.UUID
+    subject_type: Optional[str] = None
+    token_scopes: Sequence[str] = ()
+
+    @staticmethod
+    def anonymous() -> "SecurityContext":
+        z = uuid.UUID(int=0)
+        return SecurityContext(z, z, "service", ("*",))
+
+
+@dataclass(frozen=True)
+class VocabRef:
+    """names a loaded vocabulary: registry name ("cl100k_base") or canonical model id ("openai::gpt-4")"""
+    name: str
+
+
+@dataclass
+class EncodeBatchRequest:
+    vocab: VocabRef
+    bytes: np.ndarray            # uint8, packed UTF-8 of all prompts
+    offsets: np.ndarray          # uint64, n+1, offsets[0] == 0
+    vocabs_per_prompt: Optional[Sequence[VocabRef]] = None   # multi-tenant batches: one vocab per prompt
+
+
+@dataclass
+class EncodeBatchResponse:
+    ids: np.ndarray              # uint32 dense id stream
+    offsets: np.ndarray          # uint64, n+1
+    counts: np.ndarray           # uint32, n
+
+
+@dataclass
+class CountTokensRequest:
+    vocab: VocabRef
+    bytes: np.ndarray
+    offsets: np.ndarray
+    vocabs_per_prompt: Optional[Sequence[VocabRef]] = None
+
+
+@dataclass
+class Usage:
+    """gts.x.llmgw.core.usage.v1~"""
+    input_tokens: int
+    output_tokens: int = 0
+
+
+# --------------------------------------------------------------------------- plugin trait
+class TokenizerPluginClient:
+    """plugin API (scoped in ClientHub by GTS instance id)"""
+
+    def encode_batch(self, ctx: SecurityContext, req: EncodeBatchRequest) -> EncodeBatchResponse:
+        raise NotImplementedError
+
+    def count_tokens(self, ctx: SecurityContext, req: CountTokensRequest) -> np.ndarray:
+        raise NotImplementedError
+
+
+GTS_PLUGIN_SCHEMA = "gts.x.core.modkit.plugin.v1~x.llmgw.tokenizer.plugin.v1~"
+
+
+@dataclass
+class PluginInstance:
+    """BaseModkitPluginV1 content (libs/modkit/src/gts/plugin.rs:12-17)"""
+    id: str
+    vendor: str
+    priority: int
+    properties: dict = field(default_factory=dict)
+
+
+class ClientHub:
+    """type+scope keyed registry (libs/modkit/src/client_hub.rs:142-234), reduced to what the path needs"""
+
+    def __init__(self):
+        self._lock = threading.RLock()
+        self._scoped: Dict[tuple, object] = {}
+
+    def register_scoped(self, iface: type, scope: str, client: object) -> None:
+        with self._lock:
+            self._scoped[(iface, scope)] = client
+
+    def get_scoped(self, iface: type, scope: str):
+        with self._lock:
+            try:
+                return self._scoped[(iface, scope)]
+            except KeyError:
+                raise KeyError("ScopedNotFound(%s, %s)" % (iface.__name__, scope)) from None
+
+    def try_get_scoped(self, iface: type, scope: str):
+        with self._lock:
+            return self._scoped.get((iface, scope))
+
+
+def choose_plugin_instance(vendor: str, instances: Sequence[PluginInstance]) -> str:
+    """vendor match, lowest priority wins, first wins ties (libs/modkit/src/plugins/mod.rs:136-191)"""
+    best = None
+    for inst in instances:
+        if inst.vendor != vendor:
+            continue
+        if best is None or inst.priority < best.priority:
+            best = inst
+    if best is None:
+        raise NoPluginAvailable("no tokenizer plugin for vendor %r" % vendor)
+    return best.id
+
+
+# --------------------------------------------------------------------------- the GPU plugin
+class GpuBpeTokenizerPlugin(TokenizerPluginClient):
+    """`gpu-bpe-tokenizer-plugin`: owns one device context; init = Module::init of the plugin
+    (cuda context, vocab load -> device tables; multi-GPU broadcast is in cfbpe.dist)."""
+
+    VENDOR = "cyberfabric"
+
+    def __init__(self, device: int = 0, vocab_names: Sequence[str] = ("cl100k_base",), max_batch_bytes: int = 0,
+                 max_prompts: int = 0, priority: int = 10, import_blobs: Optional[Dict[str, np.ndarray]] = None):
+        try:
+            self.ctx = N.Context(device, max_batch_bytes, max_prompts)
+        except N.NativeError as e:
+            raise _map_native(e) from e
+        self._slot: Dict[str, int] = {}
+        self.resolved: Dict[str, V.ResolvedVocab] = {}
+        self._lock = threading.Lock()
+        self.instance = PluginInstance(
+            id=GTS_PLUGIN_SCHEMA + "cyberfabric.gpu_bpe.b200.v1", vendor=self.VENDOR, priority=priority,
+            properties={"device": device})
+        for name in vocab_names:
+            self.load_vocab(name, None if import_blobs is None else import_blobs.get(name))
+
+    # -- vocab management (model-registry vocab loader side)
+    def load_vocab(self, name: str, blob: Optional[np.ndarray] = None) -> int:
+        with self._lock:
+            if name in self._slot:
+                return self._slot[name]
+            slot = len(self._slot)
+            if slot >= N.MAX_VOCABS:
+                raise InvalidInput("too many vocabularies loaded")
+            rv = V.resolve(name)
+            try:
+                if blob is not None:
+                    self.ctx.vocab_import(slot, blob)
+                else:
+                    self.ctx.vocab_load(slot, rv.file_bytes, rv.spec.fmt, rv.pattern_id, rv.max_ranks)
+            except N.NativeError as e:
+                raise _map_native(e) from e
+            self._slot[name] = slot
+            self.resolved[name] = rv
+            return slot
+
+    def export_vocab(self, name: str) -> np.ndarray:
+        return self.ctx.vocab_export(self._slot[name])
+
+    def _resolve_slot(self, ref: VocabRef) -> int:
+        name = ref.name
+        if name not in self._slot and name in V.MODEL_VOCABS:
+            name = V.MODEL_VOCABS[name]
+        if name not in self._slot:
+            raise VocabNotFound("vocab %r is not loaded on this plugin" % ref.name)
+        return self._slot[name]
+
+    def _vocab_ids(self, req) -> Optional[np.ndarray]:
+        n = len(req.offsets) - 1
+        if req.vocabs_per_prompt is None:
+            slot = self._resolve_slot(req.vocab)
+            return None if slot == 0 else np.full(max(n, 1), slot, dtype=np.uint8)
+        if len(req.vocabs_per_prompt) != n:
+            raise InvalidInput("vocabs_per_prompt must name one vocab per prompt")
+        return np.fromiter((self._resolve_slot(r) for r in req.vocabs_per_prompt), dtype=np.uint8, count=n)
+
+    @staticmethod
+    def _check_arrays(req):
+        if req.bytes.dtype != np.uint8 or req.offsets.dtype != np.uint64 or len(req.offsets) < 1:
+            raise InvalidInput("bytes must be uint8 and offsets uint64 with n+1 entries")
+
+    # -- TokenizerPluginClient
+    def encode_batch(self, ctx: SecurityContext, req: EncodeBatchRequest, out: Optional[EncodeBatchResponse] = None) -> EncodeBatchResponse:
+        self._check_arrays(req)
+        vid = self._vocab_ids(req)
+        try:
+            ids, offs, counts = self.ctx.encode_batch(
+                req.bytes, req.offsets, vid,
+                None if out is None else out.ids, None if out is None else out.offsets,
+                None if out is None else out.counts)
+        except N.NativeError as e:
+            raise _map_native(e) from e
+        return EncodeBatchResponse(ids, offs, counts)
+
+    def count_tokens(self, ctx: SecurityContext, req: CountTokensRequest, out_counts: Optional[np.ndarray] = None) -> np.ndarray:
+        self._check_arrays(req)
+        vid = self._vocab_ids(req)
+        try:
+            return self.ctx.count_batch(req.bytes, req.offsets, vid, out_counts)
+        except N.NativeError as e:
+            raise _map_native(e) from e
+
+    def close(self):
+        self.ctx.close()
+
+
+# --------------------------------------------------------------------------- gateway side
+def pack_texts(texts: Sequence[str]):
+    """list[str] -> (uint8 packed bytes, uint64 offsets): the packed multi-tenant prompt buffer"""
+    enc = [t.encode("utf-8") for t in texts]
+    offs = np.zeros(len(enc) + 1, dtype=np.uint64)
+    if enc:
+        offs[1:] = np.cumsum([len(e) for e in enc], dtype=np.uint64)
+    data = np.frombuffer(b"".join(enc), dtype=np.uint8) if enc else np.zeros(0, dtype=np.uint8)
+    return data, offs
+
+
+class LlmGatewayTokenizerService:
+    """`llm-gateway::tokenizer` + `llm-gateway::usage::count_tokens`: the gateway-side domain service.
+    Plugin resolution is lazy and cached (libs/modkit/src/plugins/mod.rs:44-78)."""
+
+    def __init__(self, hub: ClientHub, instances: Sequence[PluginInstance], vendor: str = GpuBpeTokenizerPlugin.VENDOR):
+        self._hub, self._instances, self._vendor = hub, list(instances), vendor
+        self._resolved: Optional[str] = None
+        self._lock = threading.Lock()
+
+    def _plugin(self) -> TokenizerPluginClient:
+        with self._lock:
+            if self._resolved is None:
+                self._resolved = choose_plugin_instance(self._vendor, self._instances)
+        p = self._hub.try_get_scoped(TokenizerPluginClient, self._resolved)
+        if p is None:
+            raise ServiceUnavailable("tokenizer plugin %s is not registered yet" % self._resolved)
+        return p
+
+    def encode(self, ctx: SecurityContext, model: str, texts: Sequence[str]) -> List[np.ndarray]:
+        data, offs = pack_texts(texts)
+        r = self._plugin().encode_batch(ctx, EncodeBatchRequest(VocabRef(model), data, offs))
+        return [r.ids[int(r.offsets[i]):int(r.offsets[i + 1])] for i in range(len(texts))]
+
+    def count_tokens(self, ctx: SecurityContext, model: str, messages: Sequence[dict]) -> Usage:
+        """Usage.input_tokens of one chat request = sum of len(encode_ordinary(text)) over its
+        TextContent parts; chat-template overheads are provider specific and out of scope."""
+        texts = [part["text"] for m in messages for part in m.get("content", []) if part.get("type") == "text"]
+        if not texts:
+            return Usage(0)
+        data, offs = pack_texts(texts)
+        counts = self._plugin().count_tokens(ctx, CountTokensRequest(VocabRef(model), data, offs))
+        return Usage(int(counts.sum()))
+
+    def check_budget(self, ctx: SecurityContext, model: str, messages: Sequence[dict], remaining_tokens: int) -> bool:
+        """pre-call estimate used by check_budget (modules/llm-gateway/docs/DESIGN.md:833-855)"""
+        return self.count_tokens(ctx, model, messages).input_tokens <= remaining_tokens

@@ -1,0 +1,417 @@
+// cfbpe.cu -- libcfbpe.so: device context, vocab upload and the C ABI of include/cfbpe.h.
+//
+// Built for sm_100a only.  There is no CPU path in this library: every entry point that
+// computes runs the kernels of bpe_kernels.cuh on the device or returns an error.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cfbpe.h"
+
+struct ProfEvents;
+#define CFBPE_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define CFBPE_ZERO(ptr, bytes, stream) cudaMemsetAsync((ptr), 0, (bytes), (stream))
+#define CFBPE_MARK(prof, idx, stream, begin) prof_mark((prof), (idx), (stream), (begin))
+static inline void prof_mark(ProfEvents* p, int idx, cudaStream_t s, bool begin);
+
+#include "pipeline.cuh"
+#include "unicode_tables.h"
+#include "vocab.h"
+
+using namespace cfbpe;
+
+struct ProfEvents {
+    cudaEvent_t ev[CFBPE_NUM_KERNELS][2];
+    cudaEvent_t h2d[2], d2h[2], total[2];
+    bool launched[CFBPE_NUM_KERNELS];
+};
+static inline void prof_mark(ProfEvents* p, int idx, cudaStream_t s, bool begin) {
+    if (!p) return;
+    cudaEventRecord(p->ev[idx][begin ? 0 : 1], s);
+    p->launched[idx] = true;
+}
+
+struct VocabSlot {
+    bool loaded = false;
+    uint8_t* d_blob = nullptr;
+    std::vector<uint8_t> h_blob;
+    TablesHeader hdr{};
+};
+
+struct cfbpe_ctx {
+    int device = 0;
+    std::mutex mu;
+    std::string err;
+    uint64_t max_bytes = 0;
+    uint32_t max_prompts = 0;
+    cudaStream_t stream = nullptr;
+    // inputs / outputs of the host API
+    uint8_t* d_bytes = nullptr;
+    uint64_t* d_offsets = nullptr;
+    uint8_t* d_vocab_ids = nullptr;
+    uint32_t* d_out_ids = nullptr;
+    uint64_t* d_out_offsets = nullptr;
+    uint32_t* d_out_counts = nullptr;
+    Workspace ws{};
+    DeviceStatus* h_status = nullptr;  // pinned
+    uint8_t* d_uc1 = nullptr;
+    uint8_t* d_uc2 = nullptr;
+    UcTables uc{};
+    VocabSlot vocabs[CFBPE_MAX_VOCABS];
+    VocabSet vs{};
+    int sm_count = 148;
+    bool profiling = false;
+    ProfEvents prof{};
+    bool prof_ready = false;
+    cfbpe_profile last_profile{};
+};
+
+namespace {
+
+int fail(cfbpe_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            return fail(ctx, CFBPE_EIO, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+        }                                                                                                \
+    } while (0)
+
+template <typename T>
+cudaError_t dmalloc(T** p, uint64_t count) { return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)); }
+
+int validate_batch(cfbpe_ctx* ctx, uint32_t n, const uint64_t* offsets, const uint8_t* vocab_ids, uint64_t* total_out) {
+    if (n > ctx->max_prompts) return fail(ctx, CFBPE_EINVAL, "n_prompts exceeds max_prompts of this context");
+    if (!offsets) return fail(ctx, CFBPE_EINVAL, "offsets is NULL");
+    if (offsets[0] != 0) return fail(ctx, CFBPE_EINVAL, "offsets[0] must be 0");
+    for (uint32_t i = 0; i < n; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, CFBPE_EINVAL, "offsets are not monotonic at prompt " + std::to_string(i));
+    if (offsets[n] > ctx->max_bytes) return fail(ctx, CFBPE_EINVAL, "batch exceeds max_batch_bytes of this context");
+    if (vocab_ids) {
+        for (uint32_t i = 0; i < n; ++i)
+            if (vocab_ids[i] >= CFBPE_MAX_VOCABS || !ctx->vocabs[vocab_ids[i]].loaded)
+                return fail(ctx, CFBPE_ENOENT, "prompt " + std::to_string(i) + " names a vocab that is not loaded");
+    } else if (!ctx->vocabs[0].loaded) {
+        return fail(ctx, CFBPE_ENOENT, "vocab 0 is not loaded");
+    }
+    *total_out = offsets[n];
+    return CFBPE_OK;
+}
+
+int install_blob(cfbpe_ctx* ctx, uint32_t vocab_id, std::vector<uint8_t>&& blob) {
+    VocabSlot& v = ctx->vocabs[vocab_id];
+    uint8_t* d = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&d), blob.size()));
+    cudaError_t e = cudaMemcpy(d, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return fail(ctx, CFBPE_EIO, std::string("table upload: ") + cudaGetErrorString(e)); }
+    if (v.d_blob) { cudaStreamSynchronize(ctx->stream); cudaFree(v.d_blob); }
+    v.d_blob = d;
+    v.h_blob = std::move(blob);
+    std::memcpy(&v.hdr, v.h_blob.data(), sizeof(TablesHeader));
+    v.loaded = true;
+    ctx->vs.v[vocab_id] = make_view(v.d_blob, v.hdr);
+    return CFBPE_OK;
+}
+
+void fill_profile(cfbpe_ctx* ctx, uint64_t n_bytes) {
+    cfbpe_profile& p = ctx->last_profile;
+    std::memset(&p, 0, sizeof p);
+    for (int k = 0; k < CFBPE_NUM_KERNELS; ++k) {
+        if (!ctx->prof.launched[k]) continue;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->prof.ev[k][0], ctx->prof.ev[k][1]) == cudaSuccess) p.kernel_ms[k] = ms;
+        p.kernel_launches[k] = (k == K_EMIT) ? 2 : 1;
+    }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->prof.h2d[0], ctx->prof.h2d[1]) == cudaSuccess) p.h2d_ms = ms;
+    if (cudaEventElapsedTime(&ms, ctx->prof.d2h[0], ctx->prof.d2h[1]) == cudaSuccess) p.d2h_ms = ms;
+    if (cudaEventElapsedTime(&ms, ctx->prof.total[0], ctx->prof.total[1]) == cudaSuccess) p.total_ms = ms;
+    p.n_tokens = ctx->h_status->n_tokens;
+    p.n_long_pieces = ctx->h_status->n_long;
+    p.n_bytes = n_bytes;
+    ctx->prof_ready = true;
+}
+
+// shared body of encode_batch / count_batch (host buffers)
+int run_host(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const uint64_t* offsets, const uint8_t* vocab_ids,
+             uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_counts, bool want_ids) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    uint64_t total = 0;
+    int rc = validate_batch(ctx, n, offsets, vocab_ids, &total);
+    if (rc) return rc;
+    if (total && !bytes) return fail(ctx, CFBPE_EINVAL, "bytes is NULL");
+    if (want_ids && (!out_offsets || (!out_ids && out_cap))) return fail(ctx, CFBPE_EINVAL, "output pointer is NULL");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    ProfEvents* prof = ctx->profiling ? &ctx->prof : nullptr;
+    if (prof) { std::memset(prof->launched, 0, sizeof prof->launched); cudaEventRecord(prof->total[0], s); cudaEventRecord(prof->h2d[0], s); }
+    if (total) CK(cudaMemcpyAsync(ctx->d_bytes, bytes, total, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_offsets, offsets, (static_cast<uint64_t>(n) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    if (vocab_ids && n) CK(cudaMemcpyAsync(ctx->d_vocab_ids, vocab_ids, n, cudaMemcpyHostToDevice, s));
+    if (prof) cudaEventRecord(prof->h2d[1], s);
+
+    BatchView b{ctx->d_bytes, ctx->d_offsets, vocab_ids ? ctx->d_vocab_ids : nullptr, n, total};
+    enqueue_encode(b, ctx->vs, ctx->uc, ctx->ws, want_ids ? ctx->d_out_ids : nullptr, ctx->max_bytes, ctx->d_out_offsets,
+                   ctx->d_out_counts, static_cast<uint32_t>(ctx->sm_count * 4), s, prof);
+    CK(cudaGetLastError());
+    if (prof) cudaEventRecord(prof->d2h[0], s);
+    CK(cudaMemcpyAsync(ctx->h_status, ctx->ws.status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
+    if (out_offsets) CK(cudaMemcpyAsync(out_offsets, ctx->d_out_offsets, (static_cast<uint64_t>(n) + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (out_counts && n) CK(cudaMemcpyAsync(out_counts, ctx->d_out_counts, static_cast<uint64_t>(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const DeviceStatus st = *ctx->h_status;
+    if (st.long_overflow) return fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
+    if (st.bad_utf8) return fail(ctx, CFBPE_EILSEQ, "a prompt holds malformed UTF-8");
+    if (want_ids) {
+        if (st.n_tokens > out_cap) {
+            if (out_offsets) out_offsets[n] = st.n_tokens;
+            return fail(ctx, CFBPE_ENOSPC, "out_cap too small: need " + std::to_string(st.n_tokens) + " ids");
+        }
+        if (st.n_tokens) CK(cudaMemcpyAsync(out_ids, ctx->d_out_ids, st.n_tokens * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
+    if (prof) { cudaEventRecord(prof->d2h[1], s); cudaEventRecord(prof->total[1], s); }
+    CK(cudaStreamSynchronize(s));
+    if (prof) fill_profile(ctx, total);
+    return CFBPE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cfbpe_abi_version(void) { return static_cast<int>(CFBPE_ABI_VERSION); }
+
+int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
+    if (!cfg || !out || cfg->struct_size < sizeof(cfbpe_config)) return CFBPE_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return CFBPE_ENODEV;
+    if (cfg->device < 0 || cfg->device >= ndev) return CFBPE_ENODEV;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return CFBPE_ENODEV;
+    if (prop.major != 10) return CFBPE_ENODEV;  // sm_100a SASS only
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return CFBPE_ENODEV;
+
+    cfbpe_ctx* ctx = new (std::nothrow) cfbpe_ctx();
+    if (!ctx) return CFBPE_ENOMEM;
+    ctx->device = cfg->device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_bytes = cfg->max_batch_bytes ? cfg->max_batch_bytes : (256ull << 20);
+    ctx->max_prompts = cfg->max_prompts ? cfg->max_prompts : (1u << 20);
+    const uint64_t mb = ctx->max_bytes, mp = ctx->max_prompts;
+    const uint64_t nw = n_flag_words(mb) + 2;
+    const uint64_t nt = n_scan_tiles(mb) + 1;
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_bytes, mb + 256) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_offsets, mp + 1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_vocab_ids, mp + 1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_out_ids, mb + 1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_out_offsets, mp + 1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_out_counts, mp + 1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.piece_bits, nw) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.tok_bits, nw) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.ids_by_pos, mb + 1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.lscratch.rank, mb + 1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.lscratch.next, mb + 1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.lscratch.prev, mb + 1) == cudaSuccess;
+    ctx->ws.long_cap = static_cast<uint32_t>(mb / 32 + 1);   // a long piece holds more than 32 bytes
+    ok = ok && dmalloc(&ctx->ws.long_list, ctx->ws.long_cap) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.tile_counts, nt) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.tile_base, nt) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.status, 1) == cudaSuccess;
+    ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status), sizeof(DeviceStatus)) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_uc1, sizeof cfbpe_uc_stage1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_uc2, sizeof cfbpe_uc_stage2) == cudaSuccess;
+    ok = ok && cudaMemcpy(ctx->d_uc1, cfbpe_uc_stage1, sizeof cfbpe_uc_stage1, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(ctx->d_uc2, cfbpe_uc_stage2, sizeof cfbpe_uc_stage2, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_bytes, 0, mb + 256) == cudaSuccess;
+    for (int k = 0; ok && k < CFBPE_NUM_KERNELS; ++k)
+        ok = cudaEventCreate(&ctx->prof.ev[k][0]) == cudaSuccess && cudaEventCreate(&ctx->prof.ev[k][1]) == cudaSuccess;
+    for (int k = 0; ok && k < 2; ++k)
+        ok = cudaEventCreate(&ctx->prof.h2d[k]) == cudaSuccess && cudaEventCreate(&ctx->prof.d2h[k]) == cudaSuccess &&
+             cudaEventCreate(&ctx->prof.total[k]) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        cfbpe_destroy(ctx);
+        return CFBPE_ENOMEM;
+    }
+    ctx->uc = UcTables{ctx->d_uc1, ctx->d_uc2};
+    *out = ctx;
+    return CFBPE_OK;
+}
+
+void cfbpe_destroy(cfbpe_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_bytes); cudaFree(ctx->d_offsets); cudaFree(ctx->d_vocab_ids);
+    cudaFree(ctx->d_out_ids); cudaFree(ctx->d_out_offsets); cudaFree(ctx->d_out_counts);
+    cudaFree(ctx->ws.piece_bits); cudaFree(ctx->ws.tok_bits); cudaFree(ctx->ws.ids_by_pos);
+    cudaFree(ctx->ws.lscratch.rank); cudaFree(ctx->ws.lscratch.next); cudaFree(ctx->ws.lscratch.prev);
+    cudaFree(ctx->ws.long_list); cudaFree(ctx->ws.tile_counts); cudaFree(ctx->ws.tile_base); cudaFree(ctx->ws.status);
+    cudaFree(ctx->d_uc1); cudaFree(ctx->d_uc2);
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    for (auto& v : ctx->vocabs) if (v.d_blob) cudaFree(v.d_blob);
+    for (int k = 0; k < CFBPE_NUM_KERNELS; ++k) for (int j = 0; j < 2; ++j) if (ctx->prof.ev[k][j]) cudaEventDestroy(ctx->prof.ev[k][j]);
+    for (int j = 0; j < 2; ++j) {
+        if (ctx->prof.h2d[j]) cudaEventDestroy(ctx->prof.h2d[j]);
+        if (ctx->prof.d2h[j]) cudaEventDestroy(ctx->prof.d2h[j]);
+        if (ctx->prof.total[j]) cudaEventDestroy(ctx->prof.total[j]);
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* cfbpe_last_error(const cfbpe_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int cfbpe_vocab_load(cfbpe_ctx* ctx, uint32_t vocab_id, const uint8_t* ranks_file, size_t len, uint32_t format,
+                     uint32_t pattern_id, uint32_t max_ranks) {
+    if (!ctx) return CFBPE_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    if (vocab_id >= CFBPE_MAX_VOCABS) return fail(ctx, CFBPE_EINVAL, "vocab_id out of range");
+    if (!ranks_file || !len) return fail(ctx, CFBPE_EINVAL, "empty rank file");
+    if (pattern_id >= CFBPE_PATTERN_COUNT) return fail(ctx, CFBPE_EINVAL, "unknown pattern id");
+    std::vector<std::string> toks;
+    std::string e;
+    int rc;
+    if (format == CFBPE_FORMAT_TIKTOKEN) rc = parse_tiktoken(ranks_file, len, max_ranks, toks, e);
+    else if (format == CFBPE_FORMAT_TEKKEN_JSON) rc = parse_tekken_json(ranks_file, len, max_ranks, toks, e);
+    else return fail(ctx, CFBPE_EINVAL, "unknown rank-file format");
+    if (rc) return fail(ctx, rc, e);
+    std::vector<uint8_t> blob;
+    rc = build_tables(toks, pattern_id, blob, e);
+    if (rc) return fail(ctx, rc, e);
+    CK(cudaSetDevice(ctx->device));
+    return install_blob(ctx, vocab_id, std::move(blob));
+}
+
+int cfbpe_vocab_get_info(const cfbpe_ctx* ctx, uint32_t vocab_id, cfbpe_vocab_info* out) {
+    if (!ctx || !out || vocab_id >= CFBPE_MAX_VOCABS) return CFBPE_EINVAL;
+    const VocabSlot& v = ctx->vocabs[vocab_id];
+    if (!v.loaded) return CFBPE_ENOENT;
+    out->n_ranks = v.hdr.n_ranks;
+    out->pattern_id = v.hdr.pattern_id;
+    out->max_token_len = v.hdr.max_token_len;
+    out->n_pair_entries = v.hdr.n_pair_entries;
+    out->table_bytes = v.hdr.total_bytes;
+    return CFBPE_OK;
+}
+
+int cfbpe_vocab_export(const cfbpe_ctx* ctx, uint32_t vocab_id, uint8_t* buf, uint64_t cap, uint64_t* size) {
+    if (!ctx || vocab_id >= CFBPE_MAX_VOCABS) return CFBPE_EINVAL;
+    const VocabSlot& v = ctx->vocabs[vocab_id];
+    if (!v.loaded) return CFBPE_ENOENT;
+    if (size) *size = v.h_blob.size();
+    if (!buf) return CFBPE_OK;
+    if (cap < v.h_blob.size()) return CFBPE_ENOSPC;
+    std::memcpy(buf, v.h_blob.data(), v.h_blob.size());
+    return CFBPE_OK;
+}
+
+int cfbpe_vocab_import(cfbpe_ctx* ctx, uint32_t vocab_id, const uint8_t* buf, uint64_t size) {
+    if (!ctx) return CFBPE_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    if (vocab_id >= CFBPE_MAX_VOCABS || !buf) return fail(ctx, CFBPE_EINVAL, "bad argument");
+    std::string e;
+    int rc = validate_tables(buf, size, e);
+    if (rc) return fail(ctx, rc, e);
+    CK(cudaSetDevice(ctx->device));
+    return install_blob(ctx, vocab_id, std::vector<uint8_t>(buf, buf + size));
+}
+
+int cfbpe_encode_batch(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t* bytes, const uint64_t* offsets,
+                       const uint8_t* vocab_ids, uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets,
+                       uint32_t* out_counts) {
+    if (!ctx) return CFBPE_EINVAL;
+    return run_host(ctx, n_prompts, bytes, offsets, vocab_ids, out_ids, out_cap, out_offsets, out_counts, true);
+}
+
+int cfbpe_count_batch(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t* bytes, const uint64_t* offsets,
+                      const uint8_t* vocab_ids, uint32_t* out_counts) {
+    if (!ctx) return CFBPE_EINVAL;
+    if (!out_counts && n_prompts) return fail(ctx, CFBPE_EINVAL, "out_counts is NULL");
+    return run_host(ctx, n_prompts, bytes, offsets, vocab_ids, nullptr, 0, nullptr, out_counts, false);
+}
+
+int cfbpe_encode_batch_device(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t* d_bytes, uint64_t total_bytes,
+                              const uint64_t* d_offsets, const uint8_t* d_vocab_ids, uint32_t* d_out_ids,
+                              uint64_t out_cap, uint64_t* d_out_offsets, uint32_t* d_out_counts, uint64_t* n_tokens,
+                              void* stream) {
+    if (!ctx) return CFBPE_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    if (n_prompts > ctx->max_prompts || total_bytes > ctx->max_bytes) return fail(ctx, CFBPE_EINVAL, "batch exceeds the limits of this context");
+    if (!d_offsets || !d_out_offsets || (total_bytes && !d_bytes)) return fail(ctx, CFBPE_EINVAL, "device pointer is NULL");
+    if (!ctx->vocabs[0].loaded && !d_vocab_ids) return fail(ctx, CFBPE_ENOENT, "vocab 0 is not loaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ProfEvents* prof = ctx->profiling ? &ctx->prof : nullptr;
+    if (prof) { std::memset(prof->launched, 0, sizeof prof->launched); cudaEventRecord(prof->total[0], s); cudaEventRecord(prof->h2d[0], s); cudaEventRecord(prof->h2d[1], s); }
+    BatchView b{d_bytes, d_offsets, d_vocab_ids, n_prompts, total_bytes};
+    enqueue_encode(b, ctx->vs, ctx->uc, ctx->ws, d_out_ids, out_cap, d_out_offsets, d_out_counts,
+                   static_cast<uint32_t>(ctx->sm_count * 4), s, prof);
+    CK(cudaGetLastError());
+    if (prof) { cudaEventRecord(prof->d2h[0], s); cudaEventRecord(prof->d2h[1], s); cudaEventRecord(prof->total[1], s); }
+    if (n_tokens || prof) {
+        CK(cudaMemcpyAsync(ctx->h_status, ctx->ws.status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (prof) fill_profile(ctx, total_bytes);
+        const DeviceStatus st = *ctx->h_status;
+        if (n_tokens) *n_tokens = st.n_tokens;
+        if (st.long_overflow) return fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
+        if (st.bad_utf8) return fail(ctx, CFBPE_EILSEQ, "a prompt holds malformed UTF-8");
+        if (d_out_ids && st.n_tokens > out_cap) return fail(ctx, CFBPE_ENOSPC, "out_cap too small: need " + std::to_string(st.n_tokens) + " ids");
+    }
+    return CFBPE_OK;
+}
+
+int cfbpe_device_status(cfbpe_ctx* ctx, void* stream) {
+    if (!ctx) return CFBPE_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CK(cudaMemcpyAsync(ctx->h_status, ctx->ws.status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (ctx->h_status->long_overflow) return fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
+    if (ctx->h_status->bad_utf8) return fail(ctx, CFBPE_EILSEQ, "a prompt holds malformed UTF-8");
+    return CFBPE_OK;
+}
+
+void* cfbpe_host_alloc(cfbpe_ctx* ctx, size_t size) {
+    if (!ctx) return nullptr;
+    void* p = nullptr;
+    cudaSetDevice(ctx->device);
+    if (cudaMallocHost(&p, size ? size : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void cfbpe_host_free(cfbpe_ctx* ctx, void* ptr) {
+    if (!ctx || !ptr) return;
+    cudaSetDevice(ctx->device);
+    cudaFreeHost(ptr);
+}
+
+int cfbpe_profile_enable(cfbpe_ctx* ctx, int on) {
+    if (!ctx) return CFBPE_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->profiling = on != 0;
+    ctx->prof_ready = false;
+    return CFBPE_OK;
+}
+int cfbpe_profile_read(cfbpe_ctx* ctx, cfbpe_profile* out) {
+    if (!ctx || !out) return CFBPE_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ctx->prof_ready) return CFBPE_ENOENT;
+    *out = ctx->last_profile;
+    return CFBPE_OK;
+}
+
+}  // extern "C"

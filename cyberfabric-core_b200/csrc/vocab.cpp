@@ -110,16 +110,21 @@ int parse_tekken_json(const uint8_t* f, size_t len, uint32_t max_ranks, std::vec
         e = i++;
         return true;
     };
-    // find "vocab" key at any depth (it is top-level in the published files)
+    // find the "vocab" key whose value is an array (top-level in the published files)
     const char* key = "\"vocab\"";
-    size_t kpos = std::string_view(reinterpret_cast<const char*>(f), len).find(key);
-    if (kpos == std::string_view::npos) { err = "tekken json: no \"vocab\" array"; return CFBPE_EINVAL; }
-    i = kpos + std::strlen(key);
-    skip_ws();
-    if (i >= len || f[i] != ':') { err = "tekken json: malformed vocab key"; return CFBPE_EINVAL; }
-    ++i; skip_ws();
-    if (i >= len || f[i] != '[') { err = "tekken json: vocab is not an array"; return CFBPE_EINVAL; }
-    ++i;
+    std::string_view all(reinterpret_cast<const char*>(f), len);
+    size_t kpos = 0;
+    bool found = false;
+    while ((kpos = all.find(key, kpos)) != std::string_view::npos) {
+        i = kpos + std::strlen(key);
+        skip_ws();
+        if (i < len && f[i] == ':') {
+            ++i; skip_ws();
+            if (i < len && f[i] == '[') { ++i; found = true; break; }
+        }
+        kpos += 1;
+    }
+    if (!found) { err = "tekken json: no \"vocab\" array"; return CFBPE_EINVAL; }
     std::string tb;
     for (;;) {
         skip_ws();

@@ -46,6 +46,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define CFBPE_API __attribute__((visibility("default")))
+#else
+#define CFBPE_API
+#endif
+
 #define CFBPE_ABI_VERSION 1u
 
 /* error codes (negative errno values) */
@@ -98,32 +104,32 @@ typedef struct cfbpe_profile {
     uint64_t n_tokens, n_bytes, n_long_pieces;
 } cfbpe_profile;
 
-int cfbpe_abi_version(void);
+CFBPE_API int cfbpe_abi_version(void);
 
-int cfbpe_create(const cfbpe_config *cfg, cfbpe_ctx **out);
-void cfbpe_destroy(cfbpe_ctx *ctx);
+CFBPE_API int cfbpe_create(const cfbpe_config *cfg, cfbpe_ctx **out);
+CFBPE_API void cfbpe_destroy(cfbpe_ctx *ctx);
 /* NUL-terminated description of the last failure on this ctx (valid until the next call) */
-const char *cfbpe_last_error(const cfbpe_ctx *ctx);
+CFBPE_API const char *cfbpe_last_error(const cfbpe_ctx *ctx);
 
 /* Parse a rank file, build the lookup tables on the host and upload them.
  * max_ranks: keep only ranks < max_ranks (0 = all). */
-int cfbpe_vocab_load(cfbpe_ctx *ctx, uint32_t vocab_id, const uint8_t *ranks_file, size_t len,
+CFBPE_API int cfbpe_vocab_load(cfbpe_ctx *ctx, uint32_t vocab_id, const uint8_t *ranks_file, size_t len,
                      uint32_t format, uint32_t pattern_id, uint32_t max_ranks);
-int cfbpe_vocab_get_info(const cfbpe_ctx *ctx, uint32_t vocab_id, cfbpe_vocab_info *out);
+CFBPE_API int cfbpe_vocab_get_info(const cfbpe_ctx *ctx, uint32_t vocab_id, cfbpe_vocab_info *out);
 /* Copy the packed tables out (size query: buf = NULL, cap = 0) / install packed tables
  * produced by cfbpe_vocab_export on another rank. */
-int cfbpe_vocab_export(const cfbpe_ctx *ctx, uint32_t vocab_id, uint8_t *buf, uint64_t cap, uint64_t *size);
-int cfbpe_vocab_import(cfbpe_ctx *ctx, uint32_t vocab_id, const uint8_t *buf, uint64_t size);
+CFBPE_API int cfbpe_vocab_export(const cfbpe_ctx *ctx, uint32_t vocab_id, uint8_t *buf, uint64_t cap, uint64_t *size);
+CFBPE_API int cfbpe_vocab_import(cfbpe_ctx *ctx, uint32_t vocab_id, const uint8_t *buf, uint64_t size);
 
 /* Encode n_prompts prompts.  bytes/offsets: packed UTF-8, prompt i = bytes[offsets[i] .. offsets[i+1]),
  * offsets[0] must be 0.  vocab_ids: per-prompt vocab id or NULL (all vocab 0).
  * out_ids: room for out_cap ids; out_offsets: n_prompts+1; out_counts: n_prompts (may be NULL).
  * Host pointers; pinned buffers from cfbpe_host_alloc are DMA'd directly, others are staged. */
-int cfbpe_encode_batch(cfbpe_ctx *ctx, uint32_t n_prompts, const uint8_t *bytes, const uint64_t *offsets,
+CFBPE_API int cfbpe_encode_batch(cfbpe_ctx *ctx, uint32_t n_prompts, const uint8_t *bytes, const uint64_t *offsets,
                        const uint8_t *vocab_ids, uint32_t *out_ids, uint64_t out_cap, uint64_t *out_offsets,
                        uint32_t *out_counts);
 /* Token counts only (no id stream leaves the device). */
-int cfbpe_count_batch(cfbpe_ctx *ctx, uint32_t n_prompts, const uint8_t *bytes, const uint64_t *offsets,
+CFBPE_API int cfbpe_count_batch(cfbpe_ctx *ctx, uint32_t n_prompts, const uint8_t *bytes, const uint64_t *offsets,
                       const uint8_t *vocab_ids, uint32_t *out_counts);
 
 /* Same path on device-resident buffers, enqueued on `stream` (a cudaStream_t; NULL = the legacy
@@ -131,20 +137,20 @@ int cfbpe_count_batch(cfbpe_ctx *ctx, uint32_t n_prompts, const uint8_t *bytes, 
  * after an internal stream sync; with n_tokens == NULL the call is fully asynchronous and
  * d_out_offsets[n_prompts] holds the total.  Malformed UTF-8 is reported by the next call that
  * synchronises (or cfbpe_device_status). */
-int cfbpe_encode_batch_device(cfbpe_ctx *ctx, uint32_t n_prompts, const uint8_t *d_bytes, uint64_t total_bytes,
+CFBPE_API int cfbpe_encode_batch_device(cfbpe_ctx *ctx, uint32_t n_prompts, const uint8_t *d_bytes, uint64_t total_bytes,
                               const uint64_t *d_offsets, const uint8_t *d_vocab_ids, uint32_t *d_out_ids,
                               uint64_t out_cap, uint64_t *d_out_offsets, uint32_t *d_out_counts,
                               uint64_t *n_tokens, void *stream);
 /* Synchronise `stream` and return the status word of the last device call (0, CFBPE_EILSEQ, CFBPE_ENOSPC). */
-int cfbpe_device_status(cfbpe_ctx *ctx, void *stream);
+CFBPE_API int cfbpe_device_status(cfbpe_ctx *ctx, void *stream);
 
 /* page-locked host memory the DMA engines can read without a staging copy */
-void *cfbpe_host_alloc(cfbpe_ctx *ctx, size_t size);
-void cfbpe_host_free(cfbpe_ctx *ctx, void *ptr);
+CFBPE_API void *cfbpe_host_alloc(cfbpe_ctx *ctx, size_t size);
+CFBPE_API void cfbpe_host_free(cfbpe_ctx *ctx, void *ptr);
 
 /* CUDA-event timing of each kernel of the following calls (adds event records, no syncs) */
-int cfbpe_profile_enable(cfbpe_ctx *ctx, int on);
-int cfbpe_profile_read(cfbpe_ctx *ctx, cfbpe_profile *out);
+CFBPE_API int cfbpe_profile_enable(cfbpe_ctx *ctx, int on);
+CFBPE_API int cfbpe_profile_read(cfbpe_ctx *ctx, cfbpe_profile *out);
 
 #ifdef __cplusplus
 }

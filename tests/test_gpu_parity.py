@@ -1,0 +1,213 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libcfbpe.so), against the CPU oracle
+and the committed golden vectors.  Bit-exact (integer work): no tolerance anywhere."""
+import base64
+import os
+
+import numpy as np
+import pytest
+
+import fuzzgen
+from conftest import COMBOS, golden_cases, pack
+
+pytestmark = pytest.mark.gpu
+
+SLOT_NAMES = {0: "cl100k_base", 1: "o200k_base", 2: "llama3", 3: "tekken"}
+
+
+@pytest.fixture(scope="module")
+def plug():
+    from cfbpe import plugin as P
+    p = P.GpuBpeTokenizerPlugin(device=0, vocab_names=("cl100k_base", "o200k_base", "llama3", "tekken"),
+                                max_batch_bytes=160 << 20, max_prompts=1 << 17)
+    yield p
+    p.close()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from cfbpe import plugin as P
+    return P.SecurityContext.anonymous()
+
+
+def encode(plug, ctx, name, data, offs, per_prompt=None):
+    from cfbpe import plugin as P
+    return plug.encode_batch(ctx, P.EncodeBatchRequest(P.VocabRef(name), data, offs, per_prompt))
+
+
+def test_native_library_is_the_cuda_one(plug):
+    """the product path is libcfbpe.so in-tree and nothing else"""
+    from cfbpe import _native
+    assert os.path.samefile(_native.SO_PATH, os.path.join(os.path.dirname(_native.__file__), "libcfbpe.so"))
+    with open("/proc/self/maps") as f:
+        assert any("libcfbpe.so" in line for line in f)
+
+
+@pytest.mark.parametrize("pat,n_ranks", COMBOS)
+def test_golden_vectors(plug, ctx, golden, pat, n_ranks):
+    cases = golden_cases(golden)
+    data, offs = pack(cases)
+    r = encode(plug, ctx, SLOT_NAMES[pat], data, offs)
+    assert np.array_equal(r.offsets, golden["id_offsets_%d" % pat])
+    assert np.array_equal(r.ids, golden["ids_%d" % pat])
+
+
+@pytest.mark.parametrize("pat,n_ranks", COMBOS)
+def test_fuzz_against_oracle(plug, ctx, oracle_vocabs, pat, n_ranks):
+    from oracle import oracle
+    prompts = [s.encode() for s in fuzzgen.fuzz_strings(9000 + pat, 20000, max_atoms=48) + fuzzgen.long_runs(77)]
+    data, offs = pack(prompts)
+    want_ids, want_off, want_counts = oracle.encode_batch([oracle_vocabs[pat]], [pat], data, offs, nthreads=os.cpu_count())
+    r = encode(plug, ctx, SLOT_NAMES[pat], data, offs)
+    assert np.array_equal(r.offsets, want_off)
+    assert np.array_equal(r.ids, want_ids)
+    assert np.array_equal(r.counts, want_counts)
+
+
+@pytest.mark.parametrize("cfg_id,scale", [(2, 1.0), (3, 0.125), (4, 0.25)])
+def test_benchmark_configs_against_oracle(plug, ctx, cfg_id, scale):
+    from cfbpe import workload as W
+    from oracle import oracle
+    data, offs, vid, meta = W.make_config(cfg_id, scale)
+    name = meta["vocabs"][0]
+    rv = plug.resolved[name]
+    ov = oracle.OracleVocab(rv.file_bytes, rv.max_ranks)
+    want_ids, want_off, want_counts = oracle.encode_batch([ov], [rv.pattern_id], data, offs, nthreads=os.cpu_count())
+    r = encode(plug, ctx, name, data, offs)
+    assert np.array_equal(r.offsets, want_off)
+    assert np.array_equal(r.ids, want_ids)
+
+
+def test_multi_tenant_vocab_mix_against_oracle(plug, ctx):
+    from cfbpe import plugin as P
+    from cfbpe import workload as W
+    from oracle import oracle
+    data, offs, vid, meta = W.make_config(5, 0.05)
+    names = meta["vocabs"]
+    ovs, pats = [], []
+    for nm in names:
+        rv = plug.resolved[nm]
+        ovs.append(oracle.OracleVocab(rv.file_bytes, rv.max_ranks))
+        pats.append(rv.pattern_id)
+    want_ids, want_off, _ = oracle.encode_batch(ovs, pats, data, offs, vocab_ids=vid, nthreads=os.cpu_count())
+    refs = [P.VocabRef(names[int(v)]) for v in vid]
+    r = encode(plug, ctx, names[0], data, offs, per_prompt=refs)
+    assert np.array_equal(r.offsets, want_off)
+    assert np.array_equal(r.ids, want_ids)
+
+
+def test_full_size_config3_properties(plug, ctx, tekken_bytes):
+    """BASELINE.json config 3 at full size (65 536 prompts, ~134 MB): size-independent properties --
+    decode(encode(x)) == x byte for byte, offsets monotone and consistent with counts, count_tokens == encode counts,
+    and a sampled subset bit-exact against the oracle."""
+    from cfbpe import plugin as P
+    from cfbpe import workload as W
+    from oracle import oracle
+    data, offs, vid, meta = W.make_config(3, 1.0)
+    r = encode(plug, ctx, "cl100k_base", data, offs)
+    n = len(offs) - 1
+    assert len(r.offsets) == n + 1 and r.offsets[0] == 0 and int(r.offsets[-1]) == len(r.ids)
+    assert np.array_equal(np.diff(r.offsets.astype(np.int64)), r.counts.astype(np.int64))
+    counts = plug.count_tokens(ctx, P.CountTokensRequest(P.VocabRef("cl100k_base"), data, offs))
+    assert np.array_equal(counts, r.counts)
+    # round trip: token byte lengths must re-tile every prompt, and the bytes must match
+    rv = plug.resolved["cl100k_base"]
+    toks = [base64.b64decode(l.split()[0]) for l in tekken_bytes.splitlines()[:rv.max_ranks]]
+    tlen = np.array([len(t) for t in toks], dtype=np.int64)
+    assert r.ids.max() < len(toks)
+    per_prompt_bytes = np.add.reduceat(tlen[r.ids], r.offsets[:-1].astype(np.int64))
+    assert np.array_equal(per_prompt_bytes, np.diff(offs.astype(np.int64)))
+    blob = np.frombuffer(b"".join(toks), dtype=np.uint8)
+    tstart = np.concatenate([[0], np.cumsum(tlen)[:-1]])
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, n, size=300):
+        ids = r.ids[int(r.offsets[i]):int(r.offsets[i + 1])]
+        dec = b"".join(toks[t] for t in ids)
+        assert dec == bytes(data[int(offs[i]):int(offs[i + 1])])
+    ov = oracle.OracleVocab(rv.file_bytes, rv.max_ranks)
+    sel = rng.integers(0, n, size=2000)
+    for i in sel:
+        want = ov.encode(rv.pattern_id, bytes(data[int(offs[i]):int(offs[i + 1])]))
+        assert np.array_equal(r.ids[int(r.offsets[i]):int(r.offsets[i + 1])], want)
+
+
+def test_edge_cases(plug, ctx):
+    from cfbpe import plugin as P
+    for prompts in ([], [b""], [b"", b"", b""], [b"a"], [b"", b"a", b""], [b" " * 5000], [b"\n" * 33, b"", b"x" * 4096]):
+        data, offs = pack(prompts)
+        r = encode(plug, ctx, "cl100k_base", data, offs)
+        assert len(r.offsets) == len(prompts) + 1
+        assert int(r.offsets[-1]) == len(r.ids)
+        for i, p in enumerate(prompts):
+            if not p:
+                assert r.counts[i] == 0
+
+
+def test_error_codes(plug, ctx):
+    from cfbpe import plugin as P
+    data, offs = pack([b"fine", b"bad \xff\xfe", b"ok"])
+    with pytest.raises(P.InvalidInput):
+        encode(plug, ctx, "cl100k_base", data, offs)
+    with pytest.raises(P.VocabNotFound):
+        encode(plug, ctx, "no-such-vocab", data, offs)
+    bad_offs = np.array([0, 5, 3], dtype=np.uint64)
+    with pytest.raises(P.InvalidInput):
+        encode(plug, ctx, "cl100k_base", np.zeros(8, np.uint8), bad_offs)
+    # ENOSPC: out buffer too small reports the needed size
+    from cfbpe import _native as N
+    d, o = pack([b"hello world, hello world, hello world"])
+    out_ids = np.zeros(2, dtype=np.uint32)
+    with pytest.raises(N.NativeError) as ei:
+        plug.ctx.encode_batch(d, o, None, out_ids)
+    assert ei.value.code == N.ENOSPC
+    # the context still works afterwards
+    r = encode(plug, ctx, "cl100k_base", *pack([b"still alive"]))
+    assert len(r.ids) > 0
+
+
+def test_device_resident_api_matches_host_api(plug, ctx):
+    import torch
+    from cfbpe import workload as W
+    data, offs, vid, meta = W.make_config(2, 1.0)
+    r = encode(plug, ctx, "cl100k_base", data, offs)
+    dev = torch.device("cuda:0")
+    d_bytes = torch.from_numpy(np.concatenate([data, np.zeros(64, np.uint8)])).to(dev)
+    d_offs = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    n = len(offs) - 1
+    d_ids = torch.zeros(len(data) + 1, dtype=torch.int32, device=dev)
+    d_out_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    d_counts = torch.zeros(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    nt = plug.ctx.encode_batch_device(n, d_bytes.data_ptr(), int(offs[-1]), d_offs.data_ptr(), None, d_ids.data_ptr(),
+                                      d_ids.numel(), d_out_off.data_ptr(), d_counts.data_ptr(), stream, sync=True)
+    assert nt == len(r.ids)
+    assert np.array_equal(d_ids[:nt].cpu().numpy().view(np.uint32), r.ids)
+    assert np.array_equal(d_out_off.cpu().numpy().astype(np.uint64), r.offsets)
+
+
+def test_vocab_export_import_roundtrip(plug, ctx):
+    from cfbpe import _native as N
+    blob = plug.export_vocab("tekken")
+    c2 = N.Context(0, 4 << 20, 1024)
+    c2.vocab_import(0, blob)
+    data, offs = pack([s.encode() for s in fuzzgen.fuzz_strings(3, 500)])
+    a = plug.ctx.encode_batch(data, offs, np.full(len(offs) - 1, plug._slot["tekken"], dtype=np.uint8))
+    b = c2.encode_batch(data, offs)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    with pytest.raises(N.NativeError):
+        c2.vocab_import(1, blob[:1000])
+    c2.close()
+
+
+def test_usage_count_tokens_service(plug, ctx):
+    from cfbpe import plugin as P
+    hub = P.ClientHub()
+    hub.register_scoped(P.TokenizerPluginClient, plug.instance.id, plug)
+    svc = P.LlmGatewayTokenizerService(hub, [plug.instance])
+    msgs = [{"role": "user", "content": [{"type": "text", "text": "Hello there, how's it going?"},
+                                         {"type": "image", "url": "x"}]},
+            {"role": "assistant", "content": [{"type": "text", "text": "Fine."}]}]
+    u = svc.count_tokens(ctx, "openai::gpt-4", msgs)
+    ids = svc.encode(ctx, "openai::gpt-4", ["Hello there, how's it going?", "Fine."])
+    assert u.input_tokens == sum(len(x) for x in ids) > 0
+    assert svc.check_budget(ctx, "openai::gpt-4", msgs, u.input_tokens)
+    assert not svc.check_budget(ctx, "openai::gpt-4", msgs, u.input_tokens - 1)

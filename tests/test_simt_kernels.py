@@ -1,0 +1,95 @@
+"""The product's CUDA kernels (csrc/bpe_kernels.cuh, unchanged) executed on the CPU SIMT emulator
+and compared with the oracle.  This is how kernel logic is validated in the GPU-less container;
+the same comparisons run on the real device in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import fuzzgen
+import simlib
+from conftest import COMBOS, golden_cases
+from oracle import oracle
+
+
+@pytest.fixture(scope="module")
+def sim_vocabs(tekken_bytes):
+    return {pat: simlib.SimVocab(tekken_bytes, 0, pat, n) for pat, n in COMBOS}
+
+
+def check_batch(sv, ov, pat, prompts, **kw):
+    rc, ids, off, counts, nlong = simlib.encode_batch([sv], prompts, **kw)
+    assert rc == 0
+    for i, p in enumerate(prompts):
+        want = ov.encode(pat, p)
+        got = ids[int(off[i]):int(off[i + 1])]
+        assert np.array_equal(got, want), (pat, p)
+        assert counts[i] == len(want)
+    return nlong
+
+
+@pytest.mark.parametrize("pat", [0, 1, 2, 3])
+def test_split_kernel_matches_oracle(pat):
+    prompts = [s.encode() for s in fuzzgen.fuzz_strings(70 + pat, 1200) + fuzzgen.long_runs(9)]
+    rc, ends = simlib.split([pat], prompts)
+    assert rc == 0
+    for p, e in zip(prompts, ends):
+        assert oracle.split(pat, p).tolist() == e, (pat, p)
+
+
+@pytest.mark.parametrize("pat,n_ranks", COMBOS)
+def test_pipeline_matches_golden(golden, sim_vocabs, pat, n_ranks):
+    cases = golden_cases(golden)
+    rc, ids, off, counts, _ = simlib.encode_batch([sim_vocabs[pat]], cases)
+    assert rc == 0
+    gi, go = golden["ids_%d" % pat], golden["id_offsets_%d" % pat]
+    assert int(off[-1]) == int(go[-1])
+    assert np.array_equal(ids[:int(off[-1])], gi)
+    assert np.array_equal(off, go)
+
+
+@pytest.mark.parametrize("pat", [0, 3])
+def test_pipeline_fuzz_and_long_pieces(sim_vocabs, oracle_vocabs, pat):
+    prompts = [s.encode() for s in fuzzgen.fuzz_strings(500 + pat, 800, max_atoms=60) + fuzzgen.long_runs(13)]
+    nlong = check_batch(sim_vocabs[pat], oracle_vocabs[pat], pat, prompts)
+    assert nlong > 0   # the long-piece kernel was exercised
+
+
+def test_empty_and_tiny_prompts(sim_vocabs, oracle_vocabs):
+    prompts = [b"", b"a", b"", b"", b" ", b"\n", b"ab", b"", b"x" * 40, b""]
+    check_batch(sim_vocabs[0], oracle_vocabs[0], 0, prompts)
+    rc, ids, off, counts, _ = simlib.encode_batch([sim_vocabs[0]], [])
+    assert rc == 0 and int(off[0]) == 0
+    rc, ids, off, counts, _ = simlib.encode_batch([sim_vocabs[0]], [b"", b""])
+    assert rc == 0 and off.tolist() == [0, 0, 0]
+
+
+def test_multi_vocab_batch(sim_vocabs, oracle_vocabs):
+    prompts = [s.encode() for s in fuzzgen.fuzz_strings(31, 300, max_atoms=40)]
+    vid = np.array([i % 3 for i in range(len(prompts))], dtype=np.uint8)
+    vocs = [sim_vocabs[0], sim_vocabs[1], sim_vocabs[2]]
+    rc, ids, off, counts, _ = simlib.encode_batch(vocs, prompts, vocab_ids=vid)
+    assert rc == 0
+    for i, p in enumerate(prompts):
+        pat = int(vid[i])
+        assert np.array_equal(ids[int(off[i]):int(off[i + 1])], oracle_vocabs[pat].encode(pat, p)), (pat, p)
+
+
+def test_bad_utf8_is_reported(sim_vocabs):
+    for bad in [b"ok \xff bad", b"\xc3", b"abc\xe2\x82", b"\xed\xa0\x80", b"x\x80y"]:
+        rc, *_ = simlib.encode_batch([sim_vocabs[0]], [b"fine", bad, b"also fine"])
+        assert rc == -84
+
+
+def test_out_cap_too_small(sim_vocabs):
+    rc, ids, off, counts, _ = simlib.encode_batch([sim_vocabs[0]], [b"hello world, this is a test"], out_cap=2)
+    assert rc == -28
+
+
+def test_roundtrip_decode(sim_vocabs, tekken_bytes):
+    """encode -> concatenate token bytes == input (size-independent property used at full size on the GPU)"""
+    import base64
+    toks = [base64.b64decode(l.split()[0]) for l in tekken_bytes.splitlines()[:100256]]
+    prompts = [s.encode() for s in fuzzgen.fuzz_strings(99, 400)]
+    rc, ids, off, counts, _ = simlib.encode_batch([sim_vocabs[0]], prompts)
+    assert rc == 0
+    for i, p in enumerate(prompts):
+        assert b"".join(toks[t] for t in ids[int(off[i]):int(off[i + 1])]) == p
