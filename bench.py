@@ -1,0 +1,349 @@
+#!/usr/bin/env python3
+"""bench.py -- prompt-bytes/s of the batched BPE encode path (BASELINE.json metric).
+
+  python bench.py [--gpus N --steps K --warmup W]         the CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference [...]                  the CPU implementation timed on the host cores
+
+A "step" is one pass of the hot path over one synthetic batch: BASELINE.json configs[2]
+(65 536 prompts, lengths uniform 8..4096 B, cl100k pattern) -- the config the north_star metric
+is quoted on; it fits one GPU.  Weak scaling: every rank encodes its own 65 536-prompt shard
+(seed 3 + rank), so the global batch is N x 65 536 prompts and there is no data-path collective;
+the per-shard token totals are all_gathered every step (the path's only exchange).
+
+  value     whole-job prompt-bytes/s, inputs resident in HBM (cfbpe_encode_batch_device on torch's stream)
+  e2e       the same metric through the plugin / C ABI with pinned HOST buffers, H2D + D2H inside the timed region
+  roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs the measured HBM copy peak
+  cpu_baseline  the oracle port on the host cores, bounded sample, rank 0 only
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "cyberfabric-core_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "prompt_bytes_per_sec_bpe_encode"
+UNIT = "bytes/s"
+CONFIG_ID = 3
+WORKLOAD = "BASELINE.json configs[2]: 65536 prompts/GPU, lengths uniform 8-4096 B (mix 80% english+code, 10% multilingual, " \
+           "5% digits/whitespace, 5% adversarial), cl100k pattern"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs"""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_encode_rate(data, offs, rv, threads, target_s=12.0):
+    """oracle port on `threads` host threads over a bounded prefix of the batch; returns (bytes/s, sample description)"""
+    from oracle import oracle
+    ov = oracle.OracleVocab(rv.file_bytes, rv.max_ranks)
+    n = len(offs) - 1
+    probe = min(n, 2048)
+
+    def run(k):
+        sub = offs[:k + 1]
+        t0 = time.perf_counter()
+        oracle.encode_batch([ov], [rv.pattern_id], data[:int(sub[-1])], sub, nthreads=threads, want_ids=True)
+        return time.perf_counter() - t0, int(sub[-1])
+    run(min(n, 256))                       # warm the tables
+    t, b = run(probe)
+    k = int(min(n, max(probe, probe * target_s / max(t, 1e-3))))
+    t, b = run(k)
+    return b / t, "first %d prompts (%d bytes) of the same batch, %.1f s wall" % (k, b, t), t, b
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation on the host cores.  The reference tree has no tokenizer to
+    compile, so this is the oracle port (oracle/bpe_oracle.c) on every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from cfbpe import vocabs as V
+    from cfbpe import workload as W
+    data, offs, vid, meta = W.make_config(CONFIG_ID, 1.0)
+    rv = V.resolve("cl100k_base")
+    threads = os.cpu_count() or 1
+    per_step = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+    for _ in range(args.warmup):
+        cpu_encode_rate(data, offs, rv, threads, target_s=per_step / 2)
+    tt = tb = 0.0
+    sample = ""
+    for _ in range(args.steps):
+        rate, sample, t, b = cpu_encode_rate(data, offs, rv, threads, target_s=per_step)
+        tt += t; tb += b
+    value = tb / tt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "vocab": rv.label, "total_bytes_per_gpu": meta["total_bytes"], "seed": 3},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "each step: " + sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cfbpe", choices=["cfbpe", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the batch (debug only; a scaled run is not a bench value)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cfbpe" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from cfbpe import _native as N
+    from cfbpe import dist as D
+    from cfbpe import plugin as P
+    from cfbpe import workload as W
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.stderr.write("bench.py: --gpus %d needs torchrun (one process per GPU)\n" % args.gpus)
+            return 2
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- init: one rank parses the rank file, NCCL broadcasts the packed tables
+    def factory(blobs):
+        return P.GpuBpeTokenizerPlugin(device=local_rank, vocab_names=("cl100k_base",), max_batch_bytes=160 << 20,
+                                       max_prompts=1 << 17, import_blobs=blobs)
+    plug = D.load_vocab_everywhere(factory, ["cl100k_base"], 0, dev) if world > 1 else factory(None)
+    rv = plug.resolved["cl100k_base"]
+    ctx = P.SecurityContext.anonymous()
+
+    # ---- this rank's shard (weak scaling: its own 64K-prompt batch)
+    cfg = dict(W.CONFIGS[CONFIG_ID])
+    n_prompts = max(1, int(round(cfg["n"] * args.scale)))
+    data, offs, meta = W.make_batch(n_prompts, cfg["min_len"], cfg["max_len"], cfg["seed"] + rank)
+    total = int(offs[-1])
+    n = n_prompts
+
+    # pinned host buffers for the e2e leg
+    h_bytes = plug.ctx.pinned(total + 64, np.uint8); h_bytes.array[:total] = data
+    h_offs = plug.ctx.pinned(n + 1, np.uint64); h_offs.array[:] = offs
+    h_ids = plug.ctx.pinned(total + 1, np.uint32)
+    h_out_off = plug.ctx.pinned(n + 1, np.uint64)
+    h_counts = plug.ctx.pinned(n, np.uint32)
+    # device-resident buffers for the kernel-only leg
+    d_bytes = torch.zeros(total + 256, dtype=torch.uint8, device=dev)
+    d_bytes[:total] = torch.from_numpy(data).to(dev)
+    d_offs = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    d_ids = torch.empty(total + 1, dtype=torch.int32, device=dev)
+    d_out_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    d_counts = torch.empty(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    totals = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+
+    def step_device():
+        plug.ctx.encode_batch_device(n, d_bytes.data_ptr(), total, d_offs.data_ptr(), None, d_ids.data_ptr(), d_ids.numel(),
+                                     d_out_off.data_ptr(), d_counts.data_ptr(), stream, sync=False)
+        if world > 1:
+            dist.all_gather(totals, d_out_off[n:n + 1])
+
+    def step_e2e():
+        req = P.EncodeBatchRequest(P.VocabRef("cl100k_base"), h_bytes.array[:total], h_offs.array)
+        return plug.encode_batch(ctx, req, out=P.EncodeBatchResponse(h_ids.array, h_out_off.array, h_counts.array))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- kernel-only leg (inputs resident in HBM)
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    plug.ctx.device_status(stream)          # warm-up result sanity: raises on bad UTF-8
+    n_tokens = int(d_out_off[n].item())
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    total_all = sum_over_ranks(float(total))
+    tokens_all = sum_over_ranks(float(n_tokens))
+    value = total_all * args.steps / (dev_ms * 1e-3)
+
+    # ---- per-kernel device times (CUDA events inside the library, same stream), averaged over the steps
+    plug.ctx.profile_enable(True)
+    kms = {k: 0.0 for k in N.KERNEL_NAMES}
+    for _ in range(args.steps):
+        plug.ctx.encode_batch_device(n, d_bytes.data_ptr(), total, d_offs.data_ptr(), None, d_ids.data_ptr(), d_ids.numel(),
+                                     d_out_off.data_ptr(), d_counts.data_ptr(), stream, sync=True)
+        pr = plug.ctx.profile_read()
+        for k in N.KERNEL_NAMES:
+            kms[k] += pr["kernel_ms"][k] / args.steps
+    n_long = pr["n_long_pieces"]
+    plug.ctx.profile_enable(False)
+
+    # ---- end-to-end leg: pinned host buffers through the plugin / C ABI, H2D and D2H inside the timed region
+    for _ in range(args.warmup):
+        r = step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(args.steps):
+        r = step_e2e()
+    c1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(c0.elapsed_time(c1), (time.perf_counter() - t0) * 1e3))
+    e2e_value = total_all * args.steps / (e2e_ms * 1e-3)
+    assert int(r.offsets[n]) == n_tokens
+    h2d = total + (n + 1) * 8
+    d2h = n_tokens * 4 + (n + 1) * 8 + n * 4 + 24
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel
+    hbm_gbs, peak_src = peaks()
+    alg = {  # algorithmic bytes per launch
+        "pretok_split": total * (1 + 1 / 8) + 8 * (n + 1),
+        "bpe_encode": total * (1 + 1 / 8) + 4 * n_tokens + total / 8,
+        "bpe_long": 0.0,
+        "flag_count": total / 8,
+        "tile_scan": 0.0,
+        "emit_compact": total / 8 + 8 * n_tokens + 12 * (n + 1),
+    }
+    dom = max(kms, key=lambda k: kms[k])
+    achieved = alg[dom] / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    path_alg = total + 4 * n_tokens + 21 * n
+    kernels_ms = sum(kms.values())
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, sample, _, _ = cpu_encode_rate(data, offs, rv, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "vocab": rv.label, "vocab_stand_in": rv.stand_in, "prompts_per_gpu": n,
+                   "total_bytes_per_gpu": total, "tokens_per_gpu": n_tokens, "bytes_per_token": total / max(n_tokens, 1),
+                   "long_pieces_per_gpu": int(n_long), "seed": cfg["seed"], "parallelism": "dp%d (batch-sharded, no data-path collective)" % world,
+                   "l2": "inputs (%.0f MB) and per-byte work arrays (> 1 GB) exceed the 126 MB L2; no flush needed" % (total / 1e6),
+                   "scale": args.scale},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": 7 * args.steps,
+        "kernel_ms": kms,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
+                     "path_algorithmic_bytes": path_alg,
+                     "path_achieved_gbs": path_alg / (kernels_ms * 1e-3) / 1e9 if kernels_ms > 0 else 0.0},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,97 @@
+"""Host-side logic above the C ABI: plugin selection, ClientHub scoping, request packing, vocab registry,
+workload determinism, byte-balanced sharding."""
+import numpy as np
+import pytest
+
+from cfbpe import dist as D
+from cfbpe import plugin as P
+from cfbpe import vocabs as V
+from cfbpe import workload as W
+
+
+def test_choose_plugin_instance_vendor_and_priority():
+    inst = [P.PluginInstance("a", "other", 0), P.PluginInstance("b", "cyberfabric", 20),
+            P.PluginInstance("c", "cyberfabric", 5), P.PluginInstance("d", "cyberfabric", 5)]
+    assert P.choose_plugin_instance("cyberfabric", inst) == "c"      # lowest priority, first wins ties
+    with pytest.raises(P.NoPluginAvailable):
+        P.choose_plugin_instance("nobody", inst)
+
+
+def test_client_hub_scoped():
+    hub = P.ClientHub()
+    a, b = object(), object()
+    hub.register_scoped(P.TokenizerPluginClient, "gts.a", a)
+    hub.register_scoped(P.TokenizerPluginClient, "gts.b", b)
+    assert hub.get_scoped(P.TokenizerPluginClient, "gts.a") is a
+    assert hub.try_get_scoped(P.TokenizerPluginClient, "gts.b") is b
+    assert hub.try_get_scoped(P.TokenizerPluginClient, "gts.c") is None
+    with pytest.raises(KeyError):
+        hub.get_scoped(P.TokenizerPluginClient, "gts.c")
+
+
+def test_service_reports_unavailable_until_plugin_registers():
+    hub = P.ClientHub()
+    svc = P.LlmGatewayTokenizerService(hub, [P.PluginInstance("x", "cyberfabric", 1)])
+    with pytest.raises(P.ServiceUnavailable):
+        svc.encode(P.SecurityContext.anonymous(), "openai::gpt-4", ["hi"])
+
+
+def test_service_with_a_mock_plugin_counts_text_parts_only():
+    class Mock(P.TokenizerPluginClient):
+        def count_tokens(self, ctx, req):
+            return np.diff(req.offsets.astype(np.int64)).astype(np.uint32)   # 1 token per byte
+    hub = P.ClientHub()
+    hub.register_scoped(P.TokenizerPluginClient, "x", Mock())
+    svc = P.LlmGatewayTokenizerService(hub, [P.PluginInstance("x", "cyberfabric", 1)])
+    msgs = [{"role": "user", "content": [{"type": "text", "text": "abcd"}, {"type": "image", "url": "u"}]},
+            {"role": "user", "content": [{"type": "text", "text": "é"}]}]
+    assert svc.count_tokens(P.SecurityContext.anonymous(), "m", msgs).input_tokens == 4 + 2
+    assert svc.count_tokens(P.SecurityContext.anonymous(), "m", []).input_tokens == 0
+
+
+def test_pack_texts():
+    data, offs = P.pack_texts(["ab", "", "é"])
+    assert offs.tolist() == [0, 2, 2, 4] and data.tobytes() == "abé".encode()
+    data, offs = P.pack_texts([])
+    assert offs.tolist() == [0] and data.size == 0
+
+
+def test_vocab_registry_resolution():
+    rv = V.resolve("tekken")
+    assert not rv.stand_in and rv.max_ranks == 130072 and rv.pattern_id == 3
+    for name, pat in (("cl100k_base", 0), ("o200k_base", 1), ("llama3", 2)):
+        rv = V.resolve(name)
+        assert rv.pattern_id == pat
+        assert rv.stand_in and "STAND-IN" in rv.label          # the real rank files are not on this box
+    assert V.for_model("openai::gpt-4o") == "o200k_base"
+    with pytest.raises(KeyError):
+        V.for_model("nobody::nothing")
+
+
+def test_workload_is_deterministic_and_valid_utf8():
+    a = W.make_batch(300, 8, 512, seed=9)
+    b = W.make_batch(300, 8, 512, seed=9)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    data, offs, _ = a
+    lens = np.diff(offs.astype(np.int64))
+    assert lens.min() >= 1 and lens.max() <= 512
+    for i in range(300):
+        bytes(data[int(offs[i]):int(offs[i + 1])]).decode("utf-8")      # raises if a slice cut a character
+    d5, o5, vid, meta = W.make_config(5, 0.02)
+    assert set(np.unique(vid)) <= {0, 1, 2} and len(vid) == len(o5) - 1
+
+
+def test_shard_by_bytes_is_a_balanced_partition():
+    rng = np.random.default_rng(0)
+    lens = rng.integers(0, 5000, size=1000)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    for world in (1, 2, 3, 8):
+        sh = D.shard_by_bytes(offs, world)
+        assert sh[0][0] == 0 and sh[-1][1] == 1000
+        assert all(sh[i][1] == sh[i + 1][0] for i in range(world - 1))
+        sizes = [int(offs[hi] - offs[lo]) for lo, hi in sh]
+        assert max(sizes) - min(sizes) <= 2 * 5000
+    data = rng.integers(0, 255, size=int(offs[-1]), dtype=np.uint8)
+    parts = [D.shard_batch(data, offs, None, r, 4) for r in range(4)]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), data)
+    assert all(p[1][0] == 0 for p in parts)
