@@ -43,7 +43,7 @@ struct DeviceStatus {
     uint32_t bad_utf8;     // != 0: some prompt held malformed UTF-8
     uint32_t n_long;       // number of long pieces queued for K2b
     uint32_t long_overflow;
-    uint32_t pad;
+    uint32_t long_next;    // K2b work ticket
     uint64_t n_tokens;     // total ids produced (written by tile_scan)
 };
 
@@ -302,105 +302,204 @@ bpe_encode_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
 }
 
 // ---------------------------------------------------------------------------------------
-// K2b: pieces longer than 32 bytes.  One CTA per piece.  Exact sequential semantics: each
-// round finds the global minimum rank (leftmost) with a block reduction and applies that one
-// merge.  State lives in the piece's own slice of four per-byte arrays: ids (ids_by_pos; kNone
-// marks a dead slot), rank of the pair starting there, and next/prev alive links.
+// K2b: pieces longer than one window.  One WARP per piece (work list filled by K2, taken with an
+// atomic ticket).  The piece's parts live as a compact array in its own slice of per-byte scratch:
+//   id[i]  token id of part i            (ids_by_pos slice)
+//   rk[i]  rank of the pair (i, i+1), kNone when none / last part
+// Phase A, "batched rounds": every occurrence of the current minimum rank r* merges into the SAME
+// token, so all non-overlapping occurrences (leftmost first, as the sequential loop would take them)
+// are merged in one round -- unless a pair created on the way ranks below r*, which the sequential
+// loop would take first: the round is then cut after the leftmost such merge (exact).
+// Runs of one character or of a short period collapse in O(log n) rounds this way.
+// Phase B, "list rounds": when a batched round no longer merges a useful fraction, the array turns
+// into a linked list; each lane caches the minimum of a contiguous chunk, a round is one warp argmin,
+// one merge, two table lookups and a re-scan of the chunks that changed.
 // ---------------------------------------------------------------------------------------
 struct LongScratch {
     uint32_t* rank;   // u32 per byte position
-    uint32_t* next;
-    uint32_t* prev;
+    uint32_t* aux0;   // phase A: rank of the new left pair  | phase B: next alive part
+    uint32_t* aux1;   // phase A: rank of the new right pair | phase B: previous alive part
 };
 
+__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
+#pragma unroll
+    for (uint32_t d = 16; d; d >>= 1) { const uint32_t o = __shfl_xor_sync(kFull, v, d); v = o < v ? o : v; }
+    return v;
+}
+
+// one 32-element chunk of the selection: which pairs (i, i+1) with rank == rmin merge this round.
+// carry = number (parity matters) of consecutive candidates ending just before this chunk.
+__device__ __forceinline__ bool select_chunk(uint32_t r, uint32_t rmin, uint32_t lane, uint32_t& carry, uint32_t& sel_ballot) {
+    const bool cand = (r == rmin);
+    const uint32_t C = __ballot_sync(kFull, cand);
+    const uint32_t z = ~C & lanemask_lt(lane);
+    const uint32_t s = z ? (32u - __clz(z)) : 0u;             // first lane of the run of candidates ending at me
+    const uint32_t cnt = lane - s + (s == 0 ? carry : 0u);    // consecutive candidates right before me
+    const bool sel = cand && !(cnt & 1u);
+    sel_ballot = __ballot_sync(kFull, sel);
+    const uint32_t nz = ~C;
+    carry = nz ? static_cast<uint32_t>(__clz(nz)) : (carry + 32u);   // leading ones of C = candidates at the top
+    return sel;
+}
+
 __global__ void __launch_bounds__(256)
-bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, const DeviceStatus* status,
+bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
-    __shared__ unsigned long long s_red[8];
-    __shared__ unsigned long long s_best;
+    const uint32_t lane = threadIdx.x & 31;
     uint32_t n_long = status->n_long;
     if (n_long > long_cap) n_long = long_cap;
-    for (uint32_t item = blockIdx.x; item < n_long; item += gridDim.x) {
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(&status->long_next, 1u);
+        item = __shfl_sync(kFull, item, 0);
+        if (item >= n_long) break;
         const LongPiece lp = long_list[item];
         const TablesView T = vs.v[lp.vocab];
         const uint8_t* __restrict__ p = b.bytes + lp.start;
         const uint32_t n = static_cast<uint32_t>(lp.end - lp.start);
-        uint32_t* __restrict__ ids = ids_by_pos + lp.start;
+        uint32_t* __restrict__ id = ids_by_pos + lp.start;
         uint32_t* __restrict__ rk = sc.rank + lp.start;
-        uint32_t* __restrict__ nx = sc.next + lp.start;   // index of the next alive part (n = none)
-        uint32_t* __restrict__ pv = sc.prev + lp.start;   // index of the previous alive part (kNone = none)
-        const uint32_t tid = threadIdx.x, nt = blockDim.x;
+        uint32_t* __restrict__ a0 = sc.aux0 + lp.start;
+        uint32_t* __restrict__ a1 = sc.aux1 + lp.start;
 
-        // whole-piece shortcut (CoreBPE: `if piece in ranks`)
+        // ---- whole-piece shortcut (CoreBPE: `if piece in ranks`)
         if (n <= T.max_token_len) {
-            if (tid == 0) s_best = piece_lookup(T, p, n);
-            __syncthreads();
-            const uint32_t t = static_cast<uint32_t>(s_best);
-            __syncthreads();
+            uint32_t t = kNone;
+            if (lane == 0) t = piece_lookup(T, p, n);
+            t = __shfl_sync(kFull, t, 0);
             if (t != kNone) {
-                if (tid == 0) {
-                    ids[0] = t;
-                    atomicOr(&tok_bits[lp.start >> 5], 1u << (lp.start & 31));
-                }
+                if (lane == 0) { id[0] = t; atomicOr(&tok_bits[lp.start >> 5], 1u << (lp.start & 31)); }
                 continue;
             }
         }
-        for (uint32_t i = tid; i < n; i += nt) {
-            ids[i] = T.byte2id[p[i]];
-            rk[i] = (i + 1 < n) ? T.bytepair[(static_cast<uint32_t>(p[i]) << 8) | p[i + 1]] : kNone;
-            nx[i] = i + 1;
-            pv[i] = i ? i - 1 : kNone;
+        // ---- parts = bytes
+        uint32_t m = n;
+        uint32_t rmin = kNone;
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t c0 = p[i];
+            id[i] = T.byte2id[c0];
+            const uint32_t r = (i + 1 < n) ? T.bytepair[(c0 << 8) | p[i + 1]] : kNone;
+            rk[i] = r;
+            rmin = r < rmin ? r : rmin;
         }
-        __syncthreads();
-        for (;;) {
-            // block argmin of (rank, index): leftmost minimum
-            unsigned long long best = ~0ull;
-            for (uint32_t i = tid; i < n; i += nt) {
-                const uint32_t r = rk[i];
-                if (r != kNone) {
-                    const unsigned long long k = (static_cast<unsigned long long>(r) << 32) | i;
-                    if (k < best) best = k;
+        rmin = warp_min_u32(rmin);
+        __syncwarp();
+
+        // ---- phase A: batched rounds on the compact array
+        bool list_mode = false;
+        while (rmin != kNone) {
+            // A1: select, look up the pairs each merge creates, find the cut
+            uint32_t carry = 0, prevS = 0, cut = kNone;
+            for (uint32_t base = 0; base < m && cut == kNone; base += 32) {
+                const uint32_t i = base + lane;
+                const uint32_t r = (i + 1 < m) ? rk[i] : kNone;
+                uint32_t S;
+                const bool sel = select_chunk(r, rmin, lane, carry, S);
+                bool viol = false;
+                if (sel) {
+                    const bool selm2 = (lane >= 2) ? ((S >> (lane - 2)) & 1u) : ((prevS >> (30 + lane)) & 1u);
+                    uint32_t L = kNone, R = kNone;
+                    if (i > 0) L = pair_lookup(T, selm2 ? rmin : id[i - 1], rmin);
+                    if (i + 2 < m) R = pair_lookup(T, rmin, id[i + 2]);
+                    a0[i] = L;
+                    a1[i] = R;
+                    viol = (L < rmin) || (R < rmin);
+                }
+                const uint32_t V = __ballot_sync(kFull, viol);
+                if (V) cut = base + (__ffs(V) - 1);
+                prevS = S;
+            }
+            __syncwarp();
+            // A2: apply the merges up to the cut, in place (two sub-steps per chunk: right ranks, then left ranks)
+            carry = 0; prevS = 0;
+            for (uint32_t base = 0; base < m && base <= cut; base += 32) {
+                const uint32_t i = base + lane;
+                const uint32_t r = (i + 1 < m) ? rk[i] : kNone;
+                uint32_t S;
+                const bool sel = select_chunk(r, rmin, lane, carry, S);
+                const bool app = sel && i <= cut;
+                const bool selm2 = (lane >= 2) ? ((S >> (lane - 2)) & 1u) : ((prevS >> (30 + lane)) & 1u);
+                uint32_t L = kNone;
+                if (app) {
+                    L = a0[i];
+                    id[i] = rmin;             // rank == id of the merged token
+                    id[i + 1] = kNone;        // partner dies
+                    rk[i] = a1[i];
+                }
+                __syncwarp();
+                if (app && i > 0) rk[selm2 ? i - 2 : i - 1] = L;
+                __syncwarp();
+                prevS = S;
+            }
+            // A3: compact, and take the minimum of the new ranks
+            uint32_t out = 0, nmin = kNone;
+            for (uint32_t base = 0; base < m; base += 32) {
+                const uint32_t i = base + lane;
+                const uint32_t myid = (i < m) ? id[i] : kNone;
+                const uint32_t myrk = (i < m) ? rk[i] : kNone;
+                const bool keep = myid != kNone;
+                const uint32_t K = __ballot_sync(kFull, keep);
+                const uint32_t pos = out + __popc(K & lanemask_lt(lane));
+                __syncwarp();
+                if (keep) { id[pos] = myid; rk[pos] = myrk; nmin = myrk < nmin ? myrk : nmin; }
+                out += __popc(K);
+            }
+            __syncwarp();
+            const uint32_t merged = m - out;
+            m = out;
+            rmin = warp_min_u32(nmin);
+            if (rmin != kNone && merged * 8u < m && m > 32u) { list_mode = true; break; }
+        }
+
+        // ---- phase B: linked list, one merge per round
+        if (list_mode) {
+            uint32_t csh = 0;
+            while ((32u << csh) < m) ++csh;               // chunk = 2^csh parts per lane
+            for (uint32_t i = lane; i < m; i += 32) { a0[i] = i + 1; a1[i] = i ? i - 1 : kNone; }
+            __syncwarp();
+            const uint32_t lo = lane << csh;
+            const uint32_t hi = ((lane + 1) << csh) < m ? ((lane + 1) << csh) : m;
+            uint32_t mymin = kNone, mypos = 0;
+            for (uint32_t x = lo; x < hi; ++x) { const uint32_t r = rk[x]; if (r < mymin) { mymin = r; mypos = x; } }
+            for (;;) {
+                const uint32_t best = warp_min_u32(mymin != kNone ? ((mymin << 5) | lane) : kNone);
+                if (best == kNone) break;
+                const uint32_t r = best >> 5;
+                const uint32_t i = __shfl_sync(kFull, mypos, best & 31u);
+                const uint32_t j = a0[i];
+                const uint32_t k = a0[j];
+                const uint32_t q = a1[i];
+                uint32_t val = kNone;
+                if (lane == 0 && k < m) val = pair_lookup(T, r, id[k]);
+                if (lane == 1 && q != kNone) val = pair_lookup(T, id[q], r);
+                const uint32_t newR = __shfl_sync(kFull, val, 0);
+                const uint32_t newL = __shfl_sync(kFull, val, 1);
+                if (lane == 0) {
+                    id[i] = r; id[j] = kNone; rk[j] = kNone; rk[i] = newR; a0[i] = k;
+                    if (k < m) a1[k] = i;
+                    if (q != kNone) rk[q] = newL;
+                }
+                __syncwarp();
+                const uint32_t oi = i >> csh, oj = j >> csh, oq = (q != kNone) ? (q >> csh) : 32u;
+                if (lane == oi || lane == oj || lane == oq) {
+                    mymin = kNone;
+                    for (uint32_t x = lo; x < hi; ++x) { const uint32_t rr = rk[x]; if (rr < mymin) { mymin = rr; mypos = x; } }
                 }
             }
-#pragma unroll
-            for (uint32_t d = 16; d; d >>= 1) {
-                const unsigned long long o = __shfl_xor_sync(kFull, best, d);
-                if (o < best) best = o;
-            }
-            if ((tid & 31) == 0) s_red[tid >> 5] = best;
-            __syncthreads();
-            if (tid == 0) {
-                unsigned long long m = ~0ull;
-                for (uint32_t w = 0; w < (nt + 31) / 32; ++w) if (s_red[w] < m) m = s_red[w];
-                s_best = m;
-                if (m != ~0ull) {
-                    const uint32_t i = static_cast<uint32_t>(m);
-                    const uint32_t merged = static_cast<uint32_t>(m >> 32);   // rank == id of the merged token
-                    const uint32_t j = nx[i];        // right partner
-                    const uint32_t k = nx[j];        // part after the partner, or n
-                    ids[i] = merged;
-                    ids[j] = kNone;                  // partner dies
-                    rk[j] = kNone;
-                    nx[i] = k;
-                    if (k < n) pv[k] = i;
-                    rk[i] = (k < n) ? pair_lookup(T, merged, ids[k]) : kNone;
-                    const uint32_t q = pv[i];
-                    if (q != kNone) rk[q] = pair_lookup(T, ids[q], merged);
-                }
-            }
-            __syncthreads();
-            const bool done = (s_best == ~0ull);
-            __syncthreads();
-            if (done) break;
         }
-        // one flag per surviving part
-        for (uint32_t i = tid; i < n; i += nt) {
-            if (ids[i] != kNone) {
-                const uint64_t pos = lp.start + i;
-                atomicOr(&tok_bits[pos >> 5], 1u << (pos & 31));
+        // ---- one flag per surviving part (dead slots hold kNone); order along the slice is token order
+        for (uint32_t base = 0; base < m; base += 32) {
+            const uint32_t i = base + lane;
+            const bool alive = (i < m) && id[i] != kNone;
+            const uint32_t A = __ballot_sync(kFull, alive);
+            if (lane == 0 && A) {
+                const uint64_t pos = lp.start + base;
+                const uint32_t sh = static_cast<uint32_t>(pos & 31);
+                atomicOr(&tok_bits[pos >> 5], A << sh);
+                if (sh && (A >> (32 - sh))) atomicOr(&tok_bits[(pos >> 5) + 1], A >> (32 - sh));
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 

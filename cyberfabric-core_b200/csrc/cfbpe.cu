@@ -220,8 +220,8 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     ok = ok && dmalloc(&ctx->ws.tok_bits, nw) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.ids_by_pos, mb + 1) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.lscratch.rank, mb + 1) == cudaSuccess;
-    ok = ok && dmalloc(&ctx->ws.lscratch.next, mb + 1) == cudaSuccess;
-    ok = ok && dmalloc(&ctx->ws.lscratch.prev, mb + 1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.lscratch.aux0, mb + 1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.lscratch.aux1, mb + 1) == cudaSuccess;
     ctx->ws.long_cap = static_cast<uint32_t>(mb / 32 + 1);   // a long piece holds more than 32 bytes
     ok = ok && dmalloc(&ctx->ws.long_list, ctx->ws.long_cap) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.tile_counts, nt) == cudaSuccess;
@@ -255,7 +255,7 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     cudaFree(ctx->d_bytes); cudaFree(ctx->d_offsets); cudaFree(ctx->d_vocab_ids);
     cudaFree(ctx->d_out_ids); cudaFree(ctx->d_out_offsets); cudaFree(ctx->d_out_counts);
     cudaFree(ctx->ws.piece_bits); cudaFree(ctx->ws.tok_bits); cudaFree(ctx->ws.ids_by_pos);
-    cudaFree(ctx->ws.lscratch.rank); cudaFree(ctx->ws.lscratch.next); cudaFree(ctx->ws.lscratch.prev);
+    cudaFree(ctx->ws.lscratch.rank); cudaFree(ctx->ws.lscratch.aux0); cudaFree(ctx->ws.lscratch.aux1);
     cudaFree(ctx->ws.long_list); cudaFree(ctx->ws.tile_counts); cudaFree(ctx->ws.tile_base); cudaFree(ctx->ws.status);
     cudaFree(ctx->d_uc1); cudaFree(ctx->d_uc2);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);

@@ -211,3 +211,41 @@ def test_usage_count_tokens_service(plug, ctx):
     assert u.input_tokens == sum(len(x) for x in ids) > 0
     assert svc.check_budget(ctx, "openai::gpt-4", msgs, u.input_tokens)
     assert not svc.check_budget(ctx, "openai::gpt-4", msgs, u.input_tokens - 1)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_adversarial_rank_orders_on_device(seed):
+    """random rank order (merged tokens may rank below their parts): guard of the batched merge rounds"""
+    import synth_vocab
+    from cfbpe import _native as N
+    from oracle import oracle
+    rf = synth_vocab.make_rank_file(seed, n_extra=40 + 10 * seed, max_len=4 + seed % 3)
+    ov = oracle.OracleVocab(rf)
+    c = N.Context(0, 8 << 20, 1 << 14)
+    c.vocab_load(0, rf, N.FORMAT_TIKTOKEN, seed % 4, 0)
+    prompts = [t.encode() for t in synth_vocab.make_texts(100 + seed, 3000, max_len=700)]
+    data, offs = pack(prompts)
+    want_ids, want_off, _ = oracle.encode_batch([ov], [seed % 4], data, offs, nthreads=os.cpu_count())
+    got_ids, got_off, _ = c.encode_batch(data, offs)
+    assert np.array_equal(got_off, want_off)
+    assert np.array_equal(got_ids, want_ids)
+    c.close()
+
+
+def test_long_pieces_on_device(plug, ctx, oracle_vocabs):
+    import random
+    from oracle import oracle
+    rng = random.Random(5)
+    letters = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
+    prompts = []
+    for n in [33, 40, 64, 65, 100, 257, 600, 1500, 4096, 20000]:
+        for _ in range(8):
+            prompts.append("".join(rng.choice(letters) for _ in range(n)).encode())
+            prompts.append("".join(rng.choice("etaoinshr") for _ in range(n)).encode())
+        prompts += [("xyz" * n)[:n].encode(), (" " * n).encode(), ("=" * n).encode(), ("ab" * n)[:n].encode(), ("\n" * n).encode()]
+    data, offs = pack(prompts)
+    for pat in (0, 1, 3):
+        want_ids, want_off, _ = oracle.encode_batch([oracle_vocabs[pat]], [pat], data, offs, nthreads=os.cpu_count())
+        r = encode(plug, ctx, SLOT_NAMES[pat], data, offs)
+        assert np.array_equal(r.offsets, want_off)
+        assert np.array_equal(r.ids, want_ids)

@@ -93,3 +93,31 @@ def test_roundtrip_decode(sim_vocabs, tekken_bytes):
     assert rc == 0
     for i, p in enumerate(prompts):
         assert b"".join(toks[t] for t in ids[int(off[i]):int(off[i + 1])]) == p
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_adversarial_rank_orders(seed):
+    """random rank order over a 3-letter alphabet: merged tokens may rank below their parts, so the batched
+    rounds of the long-piece kernel must cut exactly where the sequential loop would deviate"""
+    import synth_vocab
+    rf = synth_vocab.make_rank_file(seed, n_extra=40 + 10 * seed, max_len=4 + seed % 3)
+    ov = oracle.OracleVocab(rf)
+    sv = simlib.SimVocab(rf, 0, 0, 0)
+    prompts = [t.encode() for t in synth_vocab.make_texts(100 + seed, 250)]
+    nlong = check_batch(sv, ov, 0, prompts)
+    assert nlong > 50
+
+
+def test_long_random_words_list_mode(sim_vocabs, oracle_vocabs):
+    import random
+    rng = random.Random(5)
+    letters = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
+    prompts = []
+    for n in [33, 40, 64, 65, 100, 257, 600, 1500, 4096]:
+        prompts.append("".join(rng.choice(letters) for _ in range(n)).encode())
+        prompts.append("".join(rng.choice("etaoinshr") for _ in range(n)).encode())
+        prompts.append(("xyz" * n)[:n].encode())
+        prompts.append((" " * n).encode())
+        prompts.append(("=" * n).encode())
+    check_batch(sim_vocabs[0], oracle_vocabs[0], 0, prompts)
+    check_batch(sim_vocabs[3], oracle_vocabs[3], 3, prompts)
