@@ -24,6 +24,7 @@ namespace cfbpe {
 constexpr uint32_t kMaxVocabs = 8;
 constexpr uint32_t kSplitChunk = 64;     // bytes of text per K1 thread
 constexpr uint32_t kEncodeRange = 1024;  // bytes of text per K2 warp
+constexpr uint32_t kBigPiece = 256;      // bytes: K2b serves longer pieces first (tail latency)
 constexpr uint32_t kScanTileWords = 256;   // flag words per K3 tile (= 8 KiB of text); one word per thread
 
 struct VocabSet {
@@ -44,6 +45,8 @@ struct DeviceStatus {
     uint32_t n_long;       // number of long pieces queued for K2b
     uint32_t long_overflow;
     uint32_t long_next;    // K2b work ticket
+    uint32_t n_big;        // pieces longer than kBigPiece (stored from the back of the list)
+    uint32_t pad;
     uint64_t n_tokens;     // total ids produced (written by tile_scan)
 };
 
@@ -192,9 +195,11 @@ bpe_encode_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
         if (!bnd) {
             // ---- piece longer than a window: queue it for K2b
             uint64_t e = next_set_bit(piece_bits, ws + 32, pe);
-            if (lane == 0) {
-                const uint32_t slot = atomicAdd(&status->n_long, 1u);
-                if (slot < long_cap) { LongPiece lp; lp.start = ws; lp.end = e; lp.vocab = vid; lp.pad = 0; long_list[slot] = lp; }
+            if (lane == 0) {   // big pieces fill the list from the back and are served first by K2b
+                const bool big = (e - ws) > kBigPiece;
+                const uint32_t idx = atomicAdd(big ? &status->n_big : &status->n_long, 1u);
+                // a long piece holds > 32 bytes, so both counters together stay below long_cap = total/32 + 1
+                if (idx < long_cap) { LongPiece lp; lp.start = ws; lp.end = e; lp.vocab = vid; lp.pad = 0; long_list[big ? long_cap - 1 - idx : idx] = lp; }
                 else atomicOr(&status->long_overflow, 1u);
             }
             ws = e;   // pieces tile a prompt: e is the next piece start, or the prompt end
@@ -260,15 +265,13 @@ bpe_encode_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
                     if (lane + d < piece_end && o < key) key = o;
                 }
                 const uint32_t best = __shfl_sync(kFull, key, head_lane);   // min over my piece
-                if (!__any_sync(kFull, unresolved && best != kNone)) break;
                 const bool winner = unresolved && best != kNone && (best & 31u) == lane;
                 const uint32_t winners = __ballot_sync(kFull, winner);
-                // -- kill the right partner of every winner: I die if the alive lane before me is a winner
-                const uint32_t below = alive & lanemask_lt(lane);
-                const uint32_t prev_alive = below ? (31u - __clz(below)) : 32u;
-                const bool i_am_alive = (alive >> lane) & 1u;
-                const bool die = i_am_alive && prev_alive < 32u && ((winners >> prev_alive) & 1u);
-                const uint32_t dead = __ballot_sync(kFull, die);
+                if (!winners) break;
+                // -- the right partner of every winner dies: next alive lane above each winner bit.  Adding
+                //    (winners << 1) to the NOT-alive mask ripples each carry up to exactly that lane.
+                const uint32_t not_alive = ~alive;
+                const uint32_t dead = ((not_alive + (winners << 1)) ^ not_alive) & alive;
                 alive &= ~dead;
                 if (winner) id = best >> 5;                        // rank == id of the merged token
                 // -- refresh the two ranks each merge touches
@@ -346,14 +349,14 @@ __global__ void __launch_bounds__(256)
 bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t n_long = status->n_long;
-    if (n_long > long_cap) n_long = long_cap;
+    const uint32_t n_big = status->n_big;
+    const uint32_t n_all = status->long_overflow ? 0u : status->n_long + n_big;
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(&status->long_next, 1u);
         item = __shfl_sync(kFull, item, 0);
-        if (item >= n_long) break;
-        const LongPiece lp = long_list[item];
+        if (item >= n_all) break;
+        const LongPiece lp = long_list[item < n_big ? long_cap - 1 - item : item - n_big];
         const TablesView T = vs.v[lp.vocab];
         const uint8_t* __restrict__ p = b.bytes + lp.start;
         const uint32_t n = static_cast<uint32_t>(lp.end - lp.start);

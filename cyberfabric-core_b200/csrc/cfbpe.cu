@@ -134,7 +134,7 @@ void fill_profile(cfbpe_ctx* ctx, uint64_t n_bytes) {
     if (cudaEventElapsedTime(&ms, ctx->prof.d2h[0], ctx->prof.d2h[1]) == cudaSuccess) p.d2h_ms = ms;
     if (cudaEventElapsedTime(&ms, ctx->prof.total[0], ctx->prof.total[1]) == cudaSuccess) p.total_ms = ms;
     p.n_tokens = ctx->h_status->n_tokens;
-    p.n_long_pieces = ctx->h_status->n_long;
+    p.n_long_pieces = static_cast<uint64_t>(ctx->h_status->n_long) + ctx->h_status->n_big;
     p.n_bytes = n_bytes;
     ctx->prof_ready = true;
 }

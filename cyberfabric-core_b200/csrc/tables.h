@@ -84,15 +84,21 @@ CFBPE_HD uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
     x ^= x >> 31;
     return x;
 }
+CFBPE_HD uint32_t mix32(uint32_t h) {  // 32-bit finaliser (lowbias32)
+    h ^= h >> 16; h *= 0x21f0aaadu;
+    h ^= h >> 15; h *= 0x735a2d97u;
+    h ^= h >> 15;
+    return h;
+}
 CFBPE_HD uint32_t pair_hash(uint32_t left, uint32_t right) {
-    uint64_t k = (static_cast<uint64_t>(left) << kIdBits) | right;
-    return static_cast<uint32_t>(mix64(k) >> 20);
+    return mix32(left * 0x9E3779B1u + right * 0x85EBCA77u + 0x165667B1u);
 }
 CFBPE_HD uint64_t pair_slot(uint32_t left, uint32_t right, uint32_t merged) {
     return (static_cast<uint64_t>(left) << (2 * kIdBits)) | (static_cast<uint64_t>(right) << kIdBits) | merged;
 }
 CFBPE_HD uint32_t short_hash(uint64_t k0, uint32_t k1, uint32_t len) {
-    return static_cast<uint32_t>(mix64(k0 ^ (static_cast<uint64_t>(k1) << 13) ^ (static_cast<uint64_t>(len) << 56)) >> 24);
+    const uint32_t lo = static_cast<uint32_t>(k0), hi = static_cast<uint32_t>(k0 >> 32);
+    return mix32(lo * 0x9E3779B1u + hi * 0x85EBCA77u + k1 * 0xC2B2AE3Du + len * 0x27D4EB2Fu);
 }
 // long tokens: first 12 bytes + last 4 bytes + length (cheap to gather); collisions are
 // resolved by comparing the bytes against the blob.

@@ -105,7 +105,7 @@ __attribute__((visibility("default"))) int sim_encode_batch(void* const* vocabs,
                 ll.data(), static_cast<uint32_t>(ll.size()), tile_counts.data(), tile_base.data(), &st};
     int* prof = nullptr;
     enqueue_encode(b, vs, uc_tables(), w, out_ids, out_cap, out_offsets, out_counts, 4u, 0, prof);
-    if (n_long_out) *n_long_out = st.n_long;
+    if (n_long_out) *n_long_out = static_cast<uint64_t>(st.n_long) + st.n_big;
     if (st.bad_utf8) return CFBPE_EILSEQ;
     if (st.long_overflow) return CFBPE_EIO;
     if (out_ids && st.n_tokens > out_cap) return CFBPE_ENOSPC;
