@@ -17,6 +17,7 @@
 #include <stdint.h>
 
 #include "pretok.cuh"
+#include "pretok_fsm.h"
 #include "tables.h"
 
 namespace cfbpe {
@@ -70,12 +71,21 @@ __device__ __forceinline__ void or_bits(uint32_t* __restrict__ words, uint64_t w
 }
 
 // ---------------------------------------------------------------------------------------
-// K1: pre-tokenizer split.  One thread per kSplitChunk bytes.  A thread starts at the first
-// sync point of its chunk (prompt start or is_sync_point) and scans matches until it stands
-// on a sync point at or beyond the end of its chunk -- which is where a later thread started.
+// K1: pre-tokenizer split.  One thread per kSplitChunk bytes.  A thread starts at the first sync
+// point of its chunk (prompt start or is_sync_point) and runs the table-driven automaton of
+// pretok_fsm.h, ONE CHARACTER PER ITERATION, until it stands on a sync point at or beyond the end
+// of its chunk -- which is where a later thread started.  All lanes execute the same instruction
+// stream whatever match they are in (the first version walked whole matches per thread: 4.3 of 32
+// lanes active, profiles/ncu_lines_pretok_split_r01a.txt).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict__ piece_bits, DeviceStatus* status) {
+    __shared__ uint16_t s_fsm[kNumPatterns * kPretokTableSize];
+    __shared__ uint8_t s_ascii[128];
+    for (uint32_t i = threadIdx.x; i < kNumPatterns * kPretokTableSize; i += blockDim.x) s_fsm[i] = uc.fsm[i];
+    if (threadIdx.x < 128) s_ascii[threadIdx.x] = uc.ascii_x[threadIdx.x];
+    __syncthreads();
+
     const uint64_t chunk = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const uint64_t cs = chunk * kSplitChunk;
     if (cs >= b.total_bytes) return;
@@ -87,35 +97,67 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
 
     // ---- find the first sync point in [cs, ce)
     uint64_t pos = cs;
-    bool found = false;
+    uint32_t state = kNoSync;
+    uint32_t pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
     while (pos < ce) {
         if (pos == pe) {  // step into the next non-empty prompt
             do { ++pidx; ps = pe; pe = b.offsets[pidx + 1]; } while (pe == ps);
+            pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
         }
-        if (pos == ps || is_sync_point(s, pos, ps, pe, uc)) { found = true; break; }
+        state = (pos == ps) ? S_START : sync_state(s, pos, ps, pe, uc, (pat & 1u) != 0);
+        if (state != kNoSync) break;
         ++pos;
     }
-    if (!found) return;
+    if (state == kNoSync) return;
 
-    // ---- scan matches
-    uint32_t pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
+    // ---- run the automaton
+    const uint16_t* tab = s_fsm + pat * kPretokTableSize;
+    uint64_t alc = 0, last = 0, lbe = 0;
     int bad = 0;
     uint64_t cur_word = pos >> 5;
     uint32_t cur_bits = 0;
     for (;;) {
-        // pos is a match start inside prompt [ps, pe)
-        const uint64_t w = pos >> 5;
-        if (w != cur_word) { or_bits(piece_bits, cur_word, cur_bits); cur_word = w; cur_bits = 0; }
-        cur_bits |= 1u << (pos & 31);
-        pos = match_end(s, pos, pe, pat, uc, &bad);
-        if (pos >= b.total_bytes) break;
-        if (pos == pe) {
+        uint32_t x, len;
+        if (pos == pe) { x = X_EOT; len = 0; }
+        else {
+            const uint32_t b0 = s[pos];
+            if (b0 < 0x80) { x = s_ascii[b0]; len = 1; }
+            else { const Ch c = get_char(s, pos, pe, uc, &bad); x = c.cls; len = c.len; }
+        }
+        uint32_t a = tab[state * X_COUNT + x];
+        uint32_t skip = 0;
+        if (a & A_CONTR) {
+            skip = contraction_bytes(s, pos, pe);
+            if (skip && (a & A_CONTR_SUFFIX)) a &= ~A_B_NOW;   // the contraction belongs to the piece that just ended
+        }
+        // retroactive boundaries (all at positions I own)
+        if (a & (A_EMIT_ALC | A_EMIT_LAST | A_EMIT_LBE)) {
+            if (a & A_EMIT_ALC) { if ((alc >> 5) == cur_word) cur_bits |= 1u << (alc & 31); else atomicOr(&piece_bits[alc >> 5], 1u << (alc & 31)); }
+            if (a & A_EMIT_LAST) { if ((last >> 5) == cur_word) cur_bits |= 1u << (last & 31); else atomicOr(&piece_bits[last >> 5], 1u << (last & 31)); }
+            if (a & A_EMIT_LBE) { if ((lbe >> 5) == cur_word) cur_bits |= 1u << (lbe & 31); else atomicOr(&piece_bits[lbe >> 5], 1u << (lbe & 31)); }
+        }
+        if (x == X_EOT) {
+            if (pos >= b.total_bytes) break;
             do { ++pidx; ps = pe; pe = b.offsets[pidx + 1]; } while (pe == ps);
+            if (pos >= ce) break;            // the next prompt's first byte is a sync point of a later chunk
             pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
-            if (pos >= ce) break;  // a prompt start is a sync point: the owner of that chunk takes over
+            tab = s_fsm + pat * kPretokTableSize;
+            state = S_START;
             continue;
         }
-        if (pos >= ce && (bad || is_sync_point(s, pos, ps, pe, uc))) break;
+        // hand over to the thread that started at the first sync point at or beyond the end of my chunk
+        // (after the retroactive boundaries above, which concern positions of mine)
+        if (pos >= ce && (bad || sync_state(s, pos, ps, pe, uc, (pat & 1u) != 0) != kNoSync)) break;
+        if (a & A_B_NOW) {
+            const uint64_t w = pos >> 5;
+            if (w != cur_word) { or_bits(piece_bits, cur_word, cur_bits); cur_word = w; cur_bits = 0; }
+            cur_bits |= 1u << (pos & 31);
+        }
+        if (a & A_SET_ALC) alc = pos + len;
+        if (a & A_SET_LAST) last = pos;
+        if (a & A_SET_LBE) lbe = pos + len;
+        if (skip) { state = S_START; pos += skip; }
+        else { state = a & A_STATE_MASK; pos += len; }
     }
     or_bits(piece_bits, cur_word, cur_bits);
     if (bad) atomicOr(&status->bad_utf8, 1u);

@@ -60,6 +60,8 @@ struct cfbpe_ctx {
     DeviceStatus* h_status = nullptr;  // pinned
     uint8_t* d_uc1 = nullptr;
     uint8_t* d_uc2 = nullptr;
+    uint8_t* d_ascii = nullptr;
+    uint16_t* d_fsm = nullptr;
     UcTables uc{};
     VocabSlot vocabs[CFBPE_MAX_VOCABS];
     VocabSet vs{};
@@ -232,6 +234,16 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     ok = ok && dmalloc(&ctx->d_uc2, sizeof cfbpe_uc_stage2) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_uc1, cfbpe_uc_stage1, sizeof cfbpe_uc_stage1, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_uc2, cfbpe_uc_stage2, sizeof cfbpe_uc_stage2, cudaMemcpyHostToDevice) == cudaSuccess;
+    {
+        std::vector<uint16_t> fsm(kNumPatterns * kPretokTableSize);
+        uint8_t ascii[128];
+        build_pretok_tables(fsm.data());
+        build_ascii_classes(ascii);
+        ok = ok && dmalloc(&ctx->d_ascii, 128) == cudaSuccess;
+        ok = ok && dmalloc(&ctx->d_fsm, fsm.size()) == cudaSuccess;
+        ok = ok && cudaMemcpy(ctx->d_ascii, ascii, 128, cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMemcpy(ctx->d_fsm, fsm.data(), fsm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     ok = ok && cudaMemset(ctx->d_bytes, 0, mb + 256) == cudaSuccess;
     for (int k = 0; ok && k < CFBPE_NUM_KERNELS; ++k)
         ok = cudaEventCreate(&ctx->prof.ev[k][0]) == cudaSuccess && cudaEventCreate(&ctx->prof.ev[k][1]) == cudaSuccess;
@@ -243,7 +255,7 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
         cfbpe_destroy(ctx);
         return CFBPE_ENOMEM;
     }
-    ctx->uc = UcTables{ctx->d_uc1, ctx->d_uc2};
+    ctx->uc = UcTables{ctx->d_uc1, ctx->d_uc2, ctx->d_ascii, ctx->d_fsm};
     *out = ctx;
     return CFBPE_OK;
 }
@@ -257,7 +269,7 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     cudaFree(ctx->ws.piece_bits); cudaFree(ctx->ws.tok_bits); cudaFree(ctx->ws.ids_by_pos);
     cudaFree(ctx->ws.lscratch.rank); cudaFree(ctx->ws.lscratch.aux0); cudaFree(ctx->ws.lscratch.aux1);
     cudaFree(ctx->ws.long_list); cudaFree(ctx->ws.tile_counts); cudaFree(ctx->ws.tile_base); cudaFree(ctx->ws.status);
-    cudaFree(ctx->d_uc1); cudaFree(ctx->d_uc2);
+    cudaFree(ctx->d_uc1); cudaFree(ctx->d_uc2); cudaFree(ctx->d_ascii); cudaFree(ctx->d_fsm);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     for (auto& v : ctx->vocabs) if (v.d_blob) cudaFree(v.d_blob);
     for (int k = 0; k < CFBPE_NUM_KERNELS; ++k) for (int j = 0; j < 2; ++j) if (ctx->prof.ev[k][j]) cudaEventDestroy(ctx->prof.ev[k][j]);

@@ -23,7 +23,13 @@ struct SimVocab {
     TablesHeader hdr;
 };
 
-static UcTables uc_tables() { return UcTables{cfbpe_uc_stage1, cfbpe_uc_stage2}; }
+static UcTables uc_tables() {
+    static uint16_t fsm[kNumPatterns * kPretokTableSize];
+    static uint8_t ascii[128];
+    static bool init = false;
+    if (!init) { build_pretok_tables(fsm); build_ascii_classes(ascii); init = true; }
+    return UcTables{cfbpe_uc_stage1, cfbpe_uc_stage2, ascii, fsm};
+}
 
 extern "C" {
 

@@ -121,3 +121,33 @@ def test_long_random_words_list_mode(sim_vocabs, oracle_vocabs):
         prompts.append(("=" * n).encode())
     check_batch(sim_vocabs[0], oracle_vocabs[0], 0, prompts)
     check_batch(sim_vocabs[3], oracle_vocabs[3], 3, prompts)
+
+
+@pytest.mark.parametrize("pat", [0, 1, 2, 3])
+def test_split_exhaustive_short_strings(pat):
+    """every string of <= 5 characters over 13 representative characters (402 233 prompts packed in one batch:
+    chunk boundaries and sync points fall everywhere)"""
+    import itertools
+    alpha = ["a", "B", "中", "́", "1", " ", "\t", "\n", "'", "/", "!", "s", "l"]
+    strs = ["".join(t).encode() for n in range(1, 6) for t in itertools.product(alpha, repeat=n)]
+    rc, ends = simlib.split([pat], strs)
+    assert rc == 0
+    bad = [(p, e) for p, e in zip(strs, ends) if oracle.split(pat, p).tolist() != e]
+    assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize("pat", [0, 1, 2, 3])
+def test_split_long_runs_across_chunks(pat):
+    """long letter / mark / punctuation runs with contractions sprinkled in: state-sync hand-over between threads"""
+    import random
+    rng = random.Random(40 + pat)
+    alpha = ["a", "b", "B", "C", "'", "s", "l", "t", "中", "文", "é", "́", " ", "!", "/", "\n", "1"]
+    weights = [12, 8, 6, 4, 3, 3, 3, 2, 6, 4, 3, 1, 1, 2, 1, 1, 1]
+    strs = []
+    for _ in range(1500):
+        n = rng.randint(40, 400)
+        strs.append("".join(rng.choices(alpha, weights, k=n)).encode())
+    rc, ends = simlib.split([pat], strs)
+    assert rc == 0
+    bad = [(p, e) for p, e in zip(strs, ends) if oracle.split(pat, p).tolist() != e]
+    assert not bad, bad[:3]
