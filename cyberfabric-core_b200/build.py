@@ -9,6 +9,18 @@ SO = os.path.join(_DIR, "cfbpe", "libcfbpe.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 
+def source_hash():
+    """sha256 over csrc/* and include/cfbpe.h (what libcfbpe.so is built from)"""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(_DIR, "..", "include", "cfbpe.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def needs_build():
     if not os.path.exists(SO):
         return True
@@ -22,7 +34,7 @@ def build(force=False, verbose=False):
         return SO
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "-shared", "--cudart", "shared",
-           "-Xptxas", "-v" if verbose else "-O3",
+           "-Xptxas", "-v" if verbose else "-O3", '-DCFBPE_SRC_HASH="%s"' % source_hash(),
            os.path.join(CSRC, "cfbpe.cu"), os.path.join(CSRC, "vocab.cpp"), "-o", SO]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:

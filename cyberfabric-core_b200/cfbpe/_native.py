@@ -18,7 +18,7 @@ KERNEL_NAMES = ["pretok_split", "bpe_encode", "bpe_long", "flag_count", "tile_sc
 
 # every symbol include/cfbpe.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
-    "cfbpe_abi_version", "cfbpe_create", "cfbpe_destroy", "cfbpe_last_error", "cfbpe_vocab_load",
+    "cfbpe_abi_version", "cfbpe_build_id", "cfbpe_create", "cfbpe_destroy", "cfbpe_last_error", "cfbpe_vocab_load",
     "cfbpe_vocab_get_info", "cfbpe_vocab_export", "cfbpe_vocab_import", "cfbpe_encode_batch", "cfbpe_count_batch",
     "cfbpe_encode_batch_device", "cfbpe_device_status", "cfbpe_host_alloc", "cfbpe_host_free",
     "cfbpe_profile_enable", "cfbpe_profile_read",
@@ -55,6 +55,18 @@ def load():
     L = C.CDLL(SO_PATH)
     vp, u8p = C.c_void_p, C.c_void_p
     L.cfbpe_abi_version.restype = C.c_int
+    L.cfbpe_build_id.restype = C.c_char_p
+    # refuse a binary that was not built from the sources next to it (a failed rebuild must not go unnoticed)
+    bpy = os.path.join(os.path.dirname(_DIR), "build.py")
+    if os.path.exists(bpy) and os.path.isdir(os.path.join(os.path.dirname(_DIR), "csrc")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("cfbpe_build", bpy)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        want, got = mod.source_hash(), L.cfbpe_build_id().decode()
+        if want != got:
+            raise RuntimeError("libcfbpe.so is stale (built from %s, sources are %s): rebuild with "
+                               "`python -c 'import __graft_entry__ as g; g.build()'`" % (got, want))
     L.cfbpe_create.restype = C.c_int
     L.cfbpe_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
     L.cfbpe_destroy.argtypes = [vp]

@@ -298,15 +298,13 @@ bpe_encode_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
             const uint32_t nb = __shfl_down_sync(kFull, my_byte, 1);
             uint32_t rank = kNone;
             if (unresolved && lane + 1 < piece_end) rank = T.bytepair[(my_byte << 8) | nb];
+            const uint32_t pend_mask = (piece_end >= 32u) ? kFull : ((1u << piece_end) - 1u);
+            const uint32_t pmask = active ? (pend_mask & ~lanemask_lt(head_lane)) : (1u << lane);
             for (;;) {
-                // -- segmented argmin over each piece: key = rank<<5 | lane (rank < 2^21), leftmost wins ties
-                uint32_t key = (rank != kNone) ? ((rank << 5) | lane) : kNone;
-#pragma unroll
-                for (uint32_t d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_down_sync(kFull, key, d);
-                    if (lane + d < piece_end && o < key) key = o;
-                }
-                const uint32_t best = __shfl_sync(kFull, key, head_lane);   // min over my piece
+                // -- argmin over each piece in ONE redux: key = rank<<5 | lane (rank < 2^21, leftmost wins ties);
+                //    every lane names the lanes of its own piece as the member mask
+                const uint32_t key = (rank != kNone) ? ((rank << 5) | lane) : kNone;
+                const uint32_t best = __reduce_min_sync(pmask, key);
                 const bool winner = unresolved && best != kNone && (best & 31u) == lane;
                 const uint32_t winners = __ballot_sync(kFull, winner);
                 if (!winners) break;

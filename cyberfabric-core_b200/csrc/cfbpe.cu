@@ -191,6 +191,11 @@ extern "C" {
 
 int cfbpe_abi_version(void) { return static_cast<int>(CFBPE_ABI_VERSION); }
 
+#ifndef CFBPE_SRC_HASH
+#define CFBPE_SRC_HASH "unknown"
+#endif
+const char* cfbpe_build_id(void) { return CFBPE_SRC_HASH; }
+
 int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     if (!cfg || !out || cfg->struct_size < sizeof(cfbpe_config)) return CFBPE_EINVAL;
     *out = nullptr;

@@ -43,7 +43,6 @@ enum : uint32_t {
 constexpr uint32_t kPretokTableSize = S_COUNT * X_COUNT;   // u16 entries per pattern
 constexpr uint32_t kNumPatterns = 4;
 
-#ifndef __CUDA_ARCH__
 namespace fsm_detail {
 struct Traits { bool cased, contr_start, contr_suffix, slash, ws_eot; uint32_t max_digits; };
 inline Traits traits(uint32_t pat) {
@@ -197,6 +196,4 @@ inline void build_ascii_classes(uint8_t* out /* 128 */) {
         out[b] = static_cast<uint8_t>(x);
     }
 }
-#endif  // !__CUDA_ARCH__
-
 }  // namespace cfbpe

@@ -105,6 +105,8 @@ typedef struct cfbpe_profile {
 } cfbpe_profile;
 
 CFBPE_API int cfbpe_abi_version(void);
+/* sha256 (hex, first 16 chars) of the sources this binary was built from; lets the host layer refuse a stale build */
+CFBPE_API const char *cfbpe_build_id(void);
 
 CFBPE_API int cfbpe_create(const cfbpe_config *cfg, cfbpe_ctx **out);
 CFBPE_API void cfbpe_destroy(cfbpe_ctx *ctx);

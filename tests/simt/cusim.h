@@ -229,6 +229,12 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
     for (unsigned i = 0; i < 32; ++i) if (((live >> i) & 1u) && buf[i]) r |= 1u << i;
     return r;
 }
+inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {   // redux.sync.min: min over the lanes named in MY mask
+    const uint64_t* buf = cusim::warp_exchange(v);
+    unsigned r = 0xFFFFFFFFu;
+    for (unsigned i = 0; i < 32; ++i) if ((mask >> i) & 1u) { const unsigned o = static_cast<unsigned>(buf[i]); r = o < r ? o : r; }
+    return r;
+}
 inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
 inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, !pred) == 0; }
 
