@@ -48,7 +48,8 @@ struct DeviceStatus {
     uint32_t long_next;    // K2b work ticket
     uint32_t n_big;        // pieces longer than kBigPiece (stored from the back of the list)
     uint32_t pad;
-    uint64_t n_tokens;     // total ids produced (written by tile_scan)
+    uint64_t n_tokens;     // ids produced by this (sub-)batch (written by tile_scan)
+    uint64_t tok_end;      // token_base + n_tokens: where the next sub-batch of a pipelined call continues
 };
 
 struct LongPiece { uint64_t start; uint64_t end; uint32_t vocab; uint32_t pad; };
@@ -576,13 +577,15 @@ flag_count_kernel(const uint32_t* __restrict__ tok_bits, uint64_t n_words, uint3
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = t;
 }
 
-// single CTA; n_tiles arbitrary (looped)
+// single CTA; n_tiles arbitrary (looped).  token_base (nullable) = ids produced by the sub-batches before this one
+// (a pipelined host call chains them on the device), so tile_base and out_offsets are global ranks.
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(const uint32_t* __restrict__ tile_counts, uint32_t n_tiles, uint64_t* __restrict__ tile_base,
-                 DeviceStatus* status) {
+                 DeviceStatus* status, const uint64_t* __restrict__ token_base) {
     __shared__ uint64_t s_warp[32];
     __shared__ uint64_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+    const uint64_t base0 = token_base ? *token_base : 0;
+    if (threadIdx.x == 0) s_carry = base0;
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (uint32_t base = 0; base < n_tiles; base += blockDim.x) {
@@ -604,7 +607,7 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_counts, uint32_t n_tiles, uin
         if (threadIdx.x == blockDim.x - 1) s_carry = carry + woff + x;
         __syncthreads();
     }
-    if (threadIdx.x == 0) status->n_tokens = s_carry;
+    if (threadIdx.x == 0) { status->n_tokens = s_carry - base0; status->tok_end = s_carry; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -643,7 +646,7 @@ prompt_offsets_kernel(BatchView b, const uint32_t* __restrict__ tok_bits, const 
     const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i > b.n_prompts) return;
     auto rank_at = [&](uint64_t pos) -> uint64_t {
-        if (pos >= b.total_bytes) return status->n_tokens;
+        if (pos >= b.total_bytes) return status->tok_end;
         const uint64_t w = pos >> 5;
         const uint64_t tile = w / kScanTileWords;
         uint64_t r = tile_base[tile];

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -35,6 +36,10 @@ static inline void prof_mark(ProfEvents* p, int idx, cudaStream_t s, bool begin)
     p->launched[idx] = true;
 }
 
+constexpr int kMaxPipeChunks = 64;
+constexpr uint64_t kPipeChunkBytes = 12ull << 20;   // sub-batch size of a pipelined host call
+constexpr uint64_t kPipeMinBytes = 24ull << 20;     // smaller calls run as one shot
+
 struct VocabSlot {
     bool loaded = false;
     uint8_t* d_blob = nullptr;
@@ -48,7 +53,15 @@ struct cfbpe_ctx {
     std::string err;
     uint64_t max_bytes = 0;
     uint32_t max_prompts = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t h2d_stream = nullptr;   // pipelined host calls: uploads run ahead of the kernels ...
+    cudaStream_t d2h_stream = nullptr;   // ... and downloads trail them
+    cudaEvent_t ev_h2d[kMaxPipeChunks] = {};
+    cudaEvent_t ev_done[kMaxPipeChunks] = {};
+    uint64_t pipe_chunk = kPipeChunkBytes, pipe_min = kPipeMinBytes;   // CFBPE_PIPE_CHUNK_BYTES / CFBPE_PIPE_MIN_BYTES override (tests)
+    DeviceStatus* d_status_arr = nullptr; // one status per sub-batch
+    DeviceStatus* h_status_arr = nullptr; // pinned
+    uint64_t* h_offs_stage = nullptr;     // pinned: sub-batch-local offsets
     // inputs / outputs of the host API
     uint8_t* d_bytes = nullptr;
     uint64_t* d_offsets = nullptr;
@@ -141,6 +154,93 @@ void fill_profile(cfbpe_ctx* ctx, uint64_t n_bytes) {
     ctx->prof_ready = true;
 }
 
+
+// Pipelined host call: the batch is cut into sub-batches of ~kPipeChunkBytes on prompt boundaries; each is an
+// independent encode pass on its own slice of the workspace.  Uploads (h2d_stream) run ahead of the kernels
+// (stream), downloads (d2h_stream) trail them; token ranks are chained on the device (DeviceStatus::tok_end), so
+// ids and offsets land at their final places.  The host only waits for each sub-batch's status to learn how many
+// ids to fetch.
+int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const uint64_t* offsets, const uint8_t* vocab_ids,
+                       uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_counts, bool want_ids,
+                       uint64_t total) {
+    // ---- cut
+    uint32_t cut[kMaxPipeChunks + 1];
+    int nc = 0;
+    {
+        uint64_t chunk = ctx->pipe_chunk;
+        if ((total + chunk - 1) / chunk > static_cast<uint64_t>(kMaxPipeChunks)) chunk = (total + kMaxPipeChunks - 1) / kMaxPipeChunks;
+        cut[0] = 0;
+        uint32_t p = 0;
+        while (p < n) {
+            const uint64_t target = offsets[p] + chunk;
+            uint32_t lo = p + 1, hi = n;                 // first q > p with offsets[q] >= target (or n)
+            while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (offsets[mid] >= target) hi = mid; else lo = mid + 1; }
+            p = lo;
+            if (nc + 1 == kMaxPipeChunks) p = n;
+            cut[++nc] = p;
+        }
+    }
+    cudaStream_t cs = ctx->stream, hs = ctx->h2d_stream, ds = ctx->d2h_stream;
+    // local offsets of every sub-batch, staged in pinned memory (sub-batch k occupies [p_k + k, p_{k+1} + k])
+    for (int k = 0; k < nc; ++k) {
+        const uint32_t p0 = cut[k], p1 = cut[k + 1];
+        const uint64_t o0 = offsets[p0];
+        uint64_t* dst = ctx->h_offs_stage + p0 + k;
+        for (uint32_t i = p0; i <= p1; ++i) dst[i - p0] = offsets[i] - o0;
+    }
+    // ---- enqueue everything that does not depend on the host knowing a result
+    for (int k = 0; k < nc; ++k) {
+        const uint32_t p0 = cut[k], p1 = cut[k + 1], nk = p1 - p0;
+        const uint64_t o0 = offsets[p0], len = offsets[p1] - o0;
+        if (len) CK(cudaMemcpyAsync(ctx->d_bytes + o0, bytes + o0, len, cudaMemcpyHostToDevice, hs));
+        CK(cudaMemcpyAsync(ctx->d_offsets + p0 + k, ctx->h_offs_stage + p0 + k, (static_cast<uint64_t>(nk) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, hs));
+        if (vocab_ids && nk) CK(cudaMemcpyAsync(ctx->d_vocab_ids + p0, vocab_ids + p0, nk, cudaMemcpyHostToDevice, hs));
+        CK(cudaEventRecord(ctx->ev_h2d[k], hs));
+        CK(cudaStreamWaitEvent(cs, ctx->ev_h2d[k], 0));
+        Workspace w = ctx->ws;
+        const uint64_t w0 = (o0 >> 5) + 4ull * k;
+        w.piece_bits += w0; w.tok_bits += w0;
+        w.ids_by_pos += o0; w.lscratch.rank += o0; w.lscratch.aux0 += o0; w.lscratch.aux1 += o0;
+        w.long_list += (o0 >> 5) + k;
+        w.long_cap = static_cast<uint32_t>(len / 32 + 1);
+        const uint64_t t0 = (o0 >> 13) + 2ull * k;
+        w.tile_counts += t0; w.tile_base += t0;
+        w.status = ctx->d_status_arr + k;
+        BatchView b{ctx->d_bytes + o0, ctx->d_offsets + p0 + k, vocab_ids ? ctx->d_vocab_ids + p0 : nullptr, nk, len};
+        enqueue_encode(b, ctx->vs, ctx->uc, w, want_ids ? ctx->d_out_ids : nullptr, ctx->max_bytes,
+                       ctx->d_out_offsets + p0 + k, ctx->d_out_counts + p0, static_cast<uint32_t>(ctx->sm_count * 4), cs,
+                       static_cast<ProfEvents*>(nullptr), k ? &ctx->d_status_arr[k - 1].tok_end : nullptr);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_status_arr + k, ctx->d_status_arr + k, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, cs));
+        CK(cudaEventRecord(ctx->ev_done[k], cs));
+    }
+    // ---- trail the kernels with the downloads
+    int err = CFBPE_OK;
+    uint64_t tok_total = 0;
+    for (int k = 0; k < nc; ++k) {
+        CK(cudaEventSynchronize(ctx->ev_done[k]));
+        const DeviceStatus st = ctx->h_status_arr[k];
+        const uint32_t p0 = cut[k], p1 = cut[k + 1], nk = p1 - p0;
+        if (st.long_overflow && !err) err = fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
+        if (st.bad_utf8 && !err) err = fail(ctx, CFBPE_EILSEQ, "a prompt holds malformed UTF-8");
+        const uint64_t base = st.tok_end - st.n_tokens;
+        tok_total = st.tok_end;
+        if (err) continue;
+        if (want_ids && st.tok_end <= out_cap && st.n_tokens)
+            CK(cudaMemcpyAsync(out_ids + base, ctx->d_out_ids + base, st.n_tokens * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds));
+        if (out_offsets) CK(cudaMemcpyAsync(out_offsets + p0, ctx->d_out_offsets + p0 + k, (static_cast<uint64_t>(nk) + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ds));
+        if (out_counts && nk) CK(cudaMemcpyAsync(out_counts + p0, ctx->d_out_counts + p0, static_cast<uint64_t>(nk) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds));
+    }
+    CK(cudaStreamSynchronize(ds));
+    CK(cudaStreamSynchronize(cs));
+    if (err) return err;
+    if (want_ids && tok_total > out_cap) {
+        if (out_offsets) out_offsets[n] = tok_total;
+        return fail(ctx, CFBPE_ENOSPC, "out_cap too small: need " + std::to_string(tok_total) + " ids");
+    }
+    return CFBPE_OK;
+}
+
 // shared body of encode_batch / count_batch (host buffers)
 int run_host(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const uint64_t* offsets, const uint8_t* vocab_ids,
              uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_counts, bool want_ids) {
@@ -152,6 +252,8 @@ int run_host(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const uint64_t* o
     if (total && !bytes) return fail(ctx, CFBPE_EINVAL, "bytes is NULL");
     if (want_ids && (!out_offsets || (!out_ids && out_cap))) return fail(ctx, CFBPE_EINVAL, "output pointer is NULL");
     CK(cudaSetDevice(ctx->device));
+    if (!ctx->profiling && total >= ctx->pipe_min && n >= 2)
+        return run_host_pipelined(ctx, n, bytes, offsets, vocab_ids, out_ids, out_cap, out_offsets, out_counts, want_ids, total);
     cudaStream_t s = ctx->stream;
     ProfEvents* prof = ctx->profiling ? &ctx->prof : nullptr;
     if (prof) { std::memset(prof->launched, 0, sizeof prof->launched); cudaEventRecord(prof->total[0], s); cudaEventRecord(prof->h2d[0], s); }
@@ -214,14 +316,14 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     ctx->max_bytes = cfg->max_batch_bytes ? cfg->max_batch_bytes : (256ull << 20);
     ctx->max_prompts = cfg->max_prompts ? cfg->max_prompts : (1u << 20);
     const uint64_t mb = ctx->max_bytes, mp = ctx->max_prompts;
-    const uint64_t nw = n_flag_words(mb) + 2;
-    const uint64_t nt = n_scan_tiles(mb) + 1;
+    const uint64_t nw = n_flag_words(mb) + 4 + 4 * kMaxPipeChunks;      // + per-sub-batch slack of a pipelined call
+    const uint64_t nt = n_scan_tiles(mb) + 1 + 2 * kMaxPipeChunks;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_bytes, mb + 256) == cudaSuccess;
-    ok = ok && dmalloc(&ctx->d_offsets, mp + 1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_offsets, mp + 1 + kMaxPipeChunks) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_vocab_ids, mp + 1) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_out_ids, mb + 1) == cudaSuccess;
-    ok = ok && dmalloc(&ctx->d_out_offsets, mp + 1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_out_offsets, mp + 1 + kMaxPipeChunks) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_out_counts, mp + 1) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.piece_bits, nw) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.tok_bits, nw) == cudaSuccess;
@@ -229,12 +331,20 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     ok = ok && dmalloc(&ctx->ws.lscratch.rank, mb + 1) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.lscratch.aux0, mb + 1) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.lscratch.aux1, mb + 1) == cudaSuccess;
-    ctx->ws.long_cap = static_cast<uint32_t>(mb / 32 + 1);   // a long piece holds more than 32 bytes
+    ctx->ws.long_cap = static_cast<uint32_t>(mb / 32 + 1 + kMaxPipeChunks);   // a long piece holds more than 32 bytes
     ok = ok && dmalloc(&ctx->ws.long_list, ctx->ws.long_cap) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.tile_counts, nt) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.tile_base, nt) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.status, 1) == cudaSuccess;
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status), sizeof(DeviceStatus)) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_status_arr, kMaxPipeChunks) == cudaSuccess;
+    ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status_arr), sizeof(DeviceStatus) * kMaxPipeChunks) == cudaSuccess;
+    ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_offs_stage), sizeof(uint64_t) * (mp + 1 + kMaxPipeChunks)) == cudaSuccess;
+    for (int k = 0; ok && k < kMaxPipeChunks; ++k)
+        ok = cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_uc1, sizeof cfbpe_uc_stage1) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_uc2, sizeof cfbpe_uc_stage2) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_uc1, cfbpe_uc_stage1, sizeof cfbpe_uc_stage1, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -261,6 +371,8 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
         return CFBPE_ENOMEM;
     }
     ctx->uc = UcTables{ctx->d_uc1, ctx->d_uc2, ctx->d_ascii, ctx->d_fsm};
+    if (const char* e = std::getenv("CFBPE_PIPE_CHUNK_BYTES")) { const uint64_t v = std::strtoull(e, nullptr, 10); if (v >= 1024) ctx->pipe_chunk = v; }
+    if (const char* e = std::getenv("CFBPE_PIPE_MIN_BYTES")) { const uint64_t v = std::strtoull(e, nullptr, 10); if (v >= 1) ctx->pipe_min = v; }
     *out = ctx;
     return CFBPE_OK;
 }
@@ -276,6 +388,12 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     cudaFree(ctx->ws.long_list); cudaFree(ctx->ws.tile_counts); cudaFree(ctx->ws.tile_base); cudaFree(ctx->ws.status);
     cudaFree(ctx->d_uc1); cudaFree(ctx->d_uc2); cudaFree(ctx->d_ascii); cudaFree(ctx->d_fsm);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    if (ctx->h_status_arr) cudaFreeHost(ctx->h_status_arr);
+    if (ctx->h_offs_stage) cudaFreeHost(ctx->h_offs_stage);
+    cudaFree(ctx->d_status_arr);
+    for (int k = 0; k < kMaxPipeChunks; ++k) { if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]); if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]); }
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     for (auto& v : ctx->vocabs) if (v.d_blob) cudaFree(v.d_blob);
     for (int k = 0; k < CFBPE_NUM_KERNELS; ++k) for (int j = 0; j < 2; ++j) if (ctx->prof.ev[k][j]) cudaEventDestroy(ctx->prof.ev[k][j]);
     for (int j = 0; j < 2; ++j) {

@@ -33,7 +33,7 @@ inline uint32_t n_scan_tiles(uint64_t total_bytes) {
 template <typename Stream, typename Prof>
 inline void enqueue_encode(const BatchView& b, const VocabSet& vs, const UcTables& uc, const Workspace& w,
                            uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_counts,
-                           uint32_t long_grid, Stream stream, Prof* prof) {
+                           uint32_t long_grid, Stream stream, Prof* prof, const uint64_t* token_base = nullptr) {
     const uint64_t nw = n_flag_words(b.total_bytes);
     const uint32_t nt = n_scan_tiles(b.total_bytes);
     CFBPE_ZERO(w.status, sizeof(DeviceStatus), stream);
@@ -62,13 +62,14 @@ inline void enqueue_encode(const BatchView& b, const VocabSet& vs, const UcTable
         CFBPE_LAUNCH(flag_count_kernel, nt, 256, stream, w.tok_bits, nw, w.tile_counts);
         CFBPE_MARK(prof, K_COUNT, stream, false);
         CFBPE_MARK(prof, K_SCAN, stream, true);
-        CFBPE_LAUNCH(tile_scan_kernel, 1u, 1024, stream, w.tile_counts, nt, w.tile_base, w.status);
+        CFBPE_LAUNCH(tile_scan_kernel, 1u, 1024, stream, w.tile_counts, nt, w.tile_base, w.status, token_base);
         CFBPE_MARK(prof, K_SCAN, stream, false);
         CFBPE_MARK(prof, K_EMIT, stream, true);
         if (out_ids) {
             CFBPE_LAUNCH(emit_compact_kernel, nt, 256, stream, w.tok_bits, nw, w.tile_base, w.ids_by_pos, out_ids, out_cap);
         }
     } else {
+        CFBPE_LAUNCH(tile_scan_kernel, 1u, 32, stream, w.tile_counts, 0u, w.tile_base, w.status, token_base);   // tok_end = base
         CFBPE_MARK(prof, K_EMIT, stream, true);
     }
     CFBPE_LAUNCH(prompt_offsets_kernel, static_cast<unsigned>((static_cast<uint64_t>(b.n_prompts) + 1 + 255) / 256), 256, stream,

@@ -249,3 +249,37 @@ def test_long_pieces_on_device(plug, ctx, oracle_vocabs):
         r = encode(plug, ctx, SLOT_NAMES[pat], data, offs)
         assert np.array_equal(r.offsets, want_off)
         assert np.array_equal(r.ids, want_ids)
+
+
+def test_pipelined_host_path_matches_oracle(oracle_vocabs, tekken_bytes, monkeypatch):
+    """force the pipelined (sub-batched, 3-stream) host path with tiny sub-batches: many chunk seams, chained token ranks"""
+    from cfbpe import _native as N
+    from oracle import oracle
+    monkeypatch.setenv("CFBPE_PIPE_CHUNK_BYTES", "20000")
+    monkeypatch.setenv("CFBPE_PIPE_MIN_BYTES", "1")
+    c = N.Context(0, 8 << 20, 1 << 15)
+    c.vocab_load(0, tekken_bytes, N.FORMAT_TIKTOKEN, 0, 100256)
+    c.vocab_load(1, tekken_bytes, N.FORMAT_TIKTOKEN, 1, 150000)
+    prompts = [s.encode() for s in fuzzgen.fuzz_strings(4321, 12000, max_atoms=40) + fuzzgen.long_runs(8)] + [b"", b"", b"x" * 30000, b""]
+    data, offs = pack(prompts)
+    vid = (np.arange(len(prompts)) % 2).astype(np.uint8)
+    want_ids, want_off, want_counts = oracle.encode_batch([oracle_vocabs[0], oracle_vocabs[1]], [0, 1], data, offs, vocab_ids=vid,
+                                                          nthreads=os.cpu_count())
+    ids, off, counts = c.encode_batch(data, offs, vid)
+    assert np.array_equal(off, want_off)
+    assert np.array_equal(ids, want_ids)
+    assert np.array_equal(counts, want_counts)
+    assert np.array_equal(c.count_batch(data, offs, vid), want_counts)
+    # ENOSPC and malformed UTF-8 through the pipelined path
+    small = np.zeros(10, dtype=np.uint32)
+    with pytest.raises(N.NativeError) as ei:
+        c.encode_batch(data, offs, vid, small)
+    assert ei.value.code == N.ENOSPC
+    bad = [p for p in prompts[:3000]] + [b"\xff\xfe"] + [p for p in prompts[3000:6000]]
+    d2, o2 = pack(bad)
+    with pytest.raises(N.NativeError) as ei:
+        c.encode_batch(d2, o2)
+    assert ei.value.code == N.EILSEQ
+    ids, off, counts = c.encode_batch(data, offs, vid)      # still healthy
+    assert np.array_equal(ids, want_ids)
+    c.close()
