@@ -18,6 +18,7 @@
 
 #include "pretok.cuh"
 #include "pretok_fsm.h"
+#include "pretok_sync.cuh"
 #include "tables.h"
 
 namespace cfbpe {
@@ -99,13 +100,15 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
     // ---- find the first sync point in [cs, ce)
     uint64_t pos = cs;
     uint32_t state = kNoSync;
+    uint32_t prevx = X_EOT, nlet = 0;   // class of the previous character, consecutive letters before pos (<= 3)
     uint32_t pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
     while (pos < ce) {
         if (pos == pe) {  // step into the next non-empty prompt
             do { ++pidx; ps = pe; pe = b.offsets[pidx + 1]; } while (pe == ps);
             pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
         }
-        state = (pos == ps) ? S_START : sync_state(s, pos, ps, pe, uc, (pat & 1u) != 0);
+        prevx = X_EOT; nlet = 0;
+        state = (pos == ps) ? static_cast<uint32_t>(S_START) : sync_state(s, pos, ps, pe, uc, (pat & 1u) != 0, &prevx, &nlet);
         if (state != kNoSync) break;
         ++pos;
     }
@@ -144,11 +147,13 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
             pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
             tab = s_fsm + pat * kPretokTableSize;
             state = S_START;
+            prevx = X_EOT; nlet = 0;
             continue;
         }
         // hand over to the thread that started at the first sync point at or beyond the end of my chunk
-        // (after the retroactive boundaries above, which concern positions of mine)
-        if (pos >= ce && (bad || sync_state(s, pos, ps, pe, uc, (pat & 1u) != 0) != kNoSync)) break;
+        // (after the retroactive boundaries above, which concern positions of mine); same predicate as
+        // sync_state(), evaluated on the classes just seen
+        if (pos >= ce && (bad || sync_rule(x, prevx, nlet, (pat & 1u) != 0) != kNoSync)) break;
         if (a & A_B_NOW) {
             const uint64_t w = pos >> 5;
             if (w != cur_word) { or_bits(piece_bits, cur_word, cur_bits); cur_word = w; cur_bits = 0; }
@@ -157,8 +162,16 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
         if (a & A_SET_ALC) alc = pos + len;
         if (a & A_SET_LAST) last = pos;
         if (a & A_SET_LBE) lbe = pos + len;
-        if (skip) { state = S_START; pos += skip; }
-        else { state = a & A_STATE_MASK; pos += len; }
+        if (skip) {   // a contraction: apostrophe + one or two letters
+            state = S_START; pos += skip;
+            const uint32_t lb = s[pos - 1];
+            prevx = lb < 0x80 ? s_ascii[lb] : static_cast<uint32_t>(X_LL);   // last letter of the contraction (U+017F is Ll)
+            nlet = (skip == 3 && lb >= 0x80) ? 1u : skip - 1;
+        } else {
+            state = a & A_STATE_MASK; pos += len;
+            prevx = x;
+            nlet = x_is_letter(x) ? (nlet < 3 ? nlet + 1 : 3u) : 0u;
+        }
     }
     or_bits(piece_bits, cur_word, cur_bits);
     if (bad) atomicOr(&status->bad_utf8, 1u);
@@ -299,13 +312,19 @@ bpe_encode_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
             const uint32_t nb = __shfl_down_sync(kFull, my_byte, 1);
             uint32_t rank = kNone;
             if (unresolved && lane + 1 < piece_end) rank = T.bytepair[(my_byte << 8) | nb];
-            const uint32_t pend_mask = (piece_end >= 32u) ? kFull : ((1u << piece_end) - 1u);
-            const uint32_t pmask = active ? (pend_mask & ~lanemask_lt(head_lane)) : (1u << lane);
+            // longest unresolved piece of the window (warp-uniform) bounds the shuffle distance of the argmin
+            const uint32_t long8 = __ballot_sync(kFull, unresolved && plen > 8u);
+            const uint32_t long16 = __ballot_sync(kFull, unresolved && plen > 16u);
+            const uint32_t dmax = long16 ? 16u : (long8 ? 8u : 4u);
             for (;;) {
-                // -- argmin over each piece in ONE redux: key = rank<<5 | lane (rank < 2^21, leftmost wins ties);
-                //    every lane names the lanes of its own piece as the member mask
-                const uint32_t key = (rank != kNone) ? ((rank << 5) | lane) : kNone;
-                const uint32_t best = __reduce_min_sync(pmask, key);
+                // -- segmented argmin over each piece: key = rank<<5 | lane (rank < 2^21), leftmost wins ties.
+                //    (redux.sync with one member mask per piece was measured slower: it serialises per mask.)
+                uint32_t key = (rank != kNone) ? ((rank << 5) | lane) : kNone;
+                for (uint32_t d = 1; d <= dmax; d <<= 1) {
+                    const uint32_t o = __shfl_down_sync(kFull, key, d);
+                    if (lane + d < piece_end && o < key) key = o;
+                }
+                const uint32_t best = __shfl_sync(kFull, key, head_lane);   // min over my piece
                 const bool winner = unresolved && best != kNone && (best & 31u) == lane;
                 const uint32_t winners = __ballot_sync(kFull, winner);
                 if (!winners) break;
@@ -389,6 +408,8 @@ __device__ __forceinline__ bool select_chunk(uint32_t r, uint32_t rmin, uint32_t
 __global__ void __launch_bounds__(256)
 bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
+    __shared__ uint32_t s_subr[8][8][32];   // [warp][sub-chunk][lane] cached minimum rank ...
+    __shared__ uint32_t s_subp[8][8][32];   // ... and its position (phase B)
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_big = status->n_big;
     const uint32_t n_all = status->long_overflow ? 0u : status->n_long + n_big;
@@ -495,24 +516,34 @@ bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
             if (rmin != kNone && merged * 8u < m && m > 32u) { list_mode = true; break; }
         }
 
-        // ---- phase B: linked list, one merge per round
+        // ---- phase B: linked list, one merge per round.  Lane L owns parts [L<<csh, (L+1)<<csh); the minimum of each
+        //      eighth of that chunk is cached in shared memory, so a changed rank costs a re-scan of chunk/8 parts
         if (list_mode) {
             uint32_t csh = 0;
             while ((32u << csh) < m) ++csh;               // chunk = 2^csh parts per lane
+            const uint32_t ssh = csh >= 3 ? csh - 3 : 0;  // sub-chunk = 2^ssh parts, nsub = chunk / sub-chunk <= 8
+            const uint32_t nsub = 1u << (csh - ssh);
             for (uint32_t i = lane; i < m; i += 32) { a0[i] = i + 1; a1[i] = i ? i - 1 : kNone; }
             __syncwarp();
             const uint32_t lo = lane << csh;
-            const uint32_t hi = ((lane + 1) << csh) < m ? ((lane + 1) << csh) : m;
+            uint32_t* subr = &s_subr[threadIdx.x >> 5][0][lane];   // [k * 32]
+            uint32_t* subp = &s_subp[threadIdx.x >> 5][0][lane];
             uint32_t mymin = kNone, mypos = 0;
-            for (uint32_t x = lo; x < hi; ++x) { const uint32_t r = rk[x]; if (r < mymin) { mymin = r; mypos = x; } }
+            for (uint32_t k = 0; k < nsub; ++k) {
+                uint32_t r0 = kNone, p0 = 0;
+                const uint32_t x0 = lo + (k << ssh), x1 = (x0 + (1u << ssh)) < m ? (x0 + (1u << ssh)) : m;
+                for (uint32_t x = x0; x < x1; ++x) { const uint32_t r = rk[x]; if (r < r0) { r0 = r; p0 = x; } }
+                subr[k * 32] = r0; subp[k * 32] = p0;
+                if (r0 < mymin) { mymin = r0; mypos = p0; }
+            }
             for (;;) {
                 const uint32_t best = warp_min_u32(mymin != kNone ? ((mymin << 5) | lane) : kNone);
                 if (best == kNone) break;
                 const uint32_t r = best >> 5;
                 const uint32_t i = __shfl_sync(kFull, mypos, best & 31u);
                 const uint32_t j = a0[i];
-                const uint32_t k = a0[j];
                 const uint32_t q = a1[i];
+                const uint32_t k = a0[j];
                 uint32_t val = kNone;
                 if (lane == 0 && k < m) val = pair_lookup(T, r, id[k]);
                 if (lane == 1 && q != kNone) val = pair_lookup(T, id[q], r);
@@ -524,10 +555,21 @@ bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
                     if (q != kNone) rk[q] = newL;
                 }
                 __syncwarp();
+                // refresh the cached minima of the (at most three) sub-chunks whose ranks changed
                 const uint32_t oi = i >> csh, oj = j >> csh, oq = (q != kNone) ? (q >> csh) : 32u;
                 if (lane == oi || lane == oj || lane == oq) {
+#pragma unroll 1
+                    for (uint32_t t = 0; t < 3; ++t) {
+                        const uint32_t x = t == 0 ? i : (t == 1 ? j : q);
+                        if (x == kNone || (x >> csh) != lane) continue;
+                        const uint32_t ks = (x - lo) >> ssh;
+                        uint32_t r0 = kNone, p0 = 0;
+                        const uint32_t x0 = lo + (ks << ssh), x1 = (x0 + (1u << ssh)) < m ? (x0 + (1u << ssh)) : m;
+                        for (uint32_t y = x0; y < x1; ++y) { const uint32_t rr = rk[y]; if (rr < r0) { r0 = rr; p0 = y; } }
+                        subr[ks * 32] = r0; subp[ks * 32] = p0;
+                    }
                     mymin = kNone;
-                    for (uint32_t x = lo; x < hi; ++x) { const uint32_t rr = rk[x]; if (rr < mymin) { mymin = rr; mypos = x; } }
+                    for (uint32_t ks = 0; ks < nsub; ++ks) { const uint32_t rr = subr[ks * 32]; if (rr < mymin) { mymin = rr; mypos = subp[ks * 32]; } }
                 }
             }
         }

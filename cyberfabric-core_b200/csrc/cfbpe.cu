@@ -37,6 +37,7 @@ static inline void prof_mark(ProfEvents* p, int idx, cudaStream_t s, bool begin)
 }
 
 constexpr int kMaxPipeChunks = 64;
+constexpr int kSideStreams = 4;
 constexpr uint64_t kPipeChunkBytes = 12ull << 20;   // sub-batch size of a pipelined host call
 constexpr uint64_t kPipeMinBytes = 24ull << 20;     // smaller calls run as one shot
 
@@ -56,6 +57,8 @@ struct cfbpe_ctx {
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t h2d_stream = nullptr;   // pipelined host calls: uploads run ahead of the kernels ...
     cudaStream_t d2h_stream = nullptr;   // ... and downloads trail them
+    cudaStream_t side[kSideStreams] = {};  // long-piece tails + emit of sub-batch k overlap the front of k+1
+    cudaEvent_t ev_front[kMaxPipeChunks] = {};
     cudaEvent_t ev_h2d[kMaxPipeChunks] = {};
     cudaEvent_t ev_done[kMaxPipeChunks] = {};
     uint64_t pipe_chunk = kPipeChunkBytes, pipe_min = kPipeMinBytes;   // CFBPE_PIPE_CHUNK_BYTES / CFBPE_PIPE_MIN_BYTES override (tests)
@@ -207,12 +210,17 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         w.tile_counts += t0; w.tile_base += t0;
         w.status = ctx->d_status_arr + k;
         BatchView b{ctx->d_bytes + o0, ctx->d_offsets + p0 + k, vocab_ids ? ctx->d_vocab_ids + p0 : nullptr, nk, len};
-        enqueue_encode(b, ctx->vs, ctx->uc, w, want_ids ? ctx->d_out_ids : nullptr, ctx->max_bytes,
-                       ctx->d_out_offsets + p0 + k, ctx->d_out_counts + p0, static_cast<uint32_t>(ctx->sm_count * 4), cs,
-                       static_cast<ProfEvents*>(nullptr), k ? &ctx->d_status_arr[k - 1].tok_end : nullptr);
+        cudaStream_t ss = ctx->side[k % kSideStreams];
+        enqueue_front(b, ctx->vs, ctx->uc, w, cs, static_cast<ProfEvents*>(nullptr));
+        CK(cudaEventRecord(ctx->ev_front[k], cs));
+        CK(cudaStreamWaitEvent(ss, ctx->ev_front[k], 0));
+        enqueue_mid(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ss, static_cast<ProfEvents*>(nullptr));
+        if (k) CK(cudaStreamWaitEvent(ss, ctx->ev_done[k - 1], 0));     // token ranks chain through DeviceStatus::tok_end
+        enqueue_back(b, w, want_ids ? ctx->d_out_ids : nullptr, ctx->max_bytes, ctx->d_out_offsets + p0 + k, ctx->d_out_counts + p0,
+                     ss, static_cast<ProfEvents*>(nullptr), k ? &ctx->d_status_arr[k - 1].tok_end : nullptr);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(ctx->h_status_arr + k, ctx->d_status_arr + k, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, cs));
-        CK(cudaEventRecord(ctx->ev_done[k], cs));
+        CK(cudaMemcpyAsync(ctx->h_status_arr + k, ctx->d_status_arr + k, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, ss));
+        CK(cudaEventRecord(ctx->ev_done[k], ss));
     }
     // ---- trail the kernels with the downloads
     int err = CFBPE_OK;
@@ -233,6 +241,7 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
     }
     CK(cudaStreamSynchronize(ds));
     CK(cudaStreamSynchronize(cs));
+    for (int k = 0; k < kSideStreams; ++k) CK(cudaStreamSynchronize(ctx->side[k]));
     if (err) return err;
     if (want_ids && tok_total > out_cap) {
         if (out_offsets) out_offsets[n] = tok_total;
@@ -342,8 +351,10 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     ok = ok && dmalloc(&ctx->d_status_arr, kMaxPipeChunks) == cudaSuccess;
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status_arr), sizeof(DeviceStatus) * kMaxPipeChunks) == cudaSuccess;
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_offs_stage), sizeof(uint64_t) * (mp + 1 + kMaxPipeChunks)) == cudaSuccess;
+    for (int k = 0; ok && k < kSideStreams; ++k) ok = cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; ok && k < kMaxPipeChunks; ++k)
         ok = cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_front[k], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_uc1, sizeof cfbpe_uc_stage1) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_uc2, sizeof cfbpe_uc_stage2) == cudaSuccess;
@@ -391,7 +402,8 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     if (ctx->h_status_arr) cudaFreeHost(ctx->h_status_arr);
     if (ctx->h_offs_stage) cudaFreeHost(ctx->h_offs_stage);
     cudaFree(ctx->d_status_arr);
-    for (int k = 0; k < kMaxPipeChunks; ++k) { if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]); if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]); }
+    for (int k = 0; k < kMaxPipeChunks; ++k) { if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]); if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]); if (ctx->ev_front[k]) cudaEventDestroy(ctx->ev_front[k]); }
+    for (int k = 0; k < kSideStreams; ++k) if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     for (auto& v : ctx->vocabs) if (v.d_blob) cudaFree(v.d_blob);

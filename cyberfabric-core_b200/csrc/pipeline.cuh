@@ -29,38 +29,45 @@ inline uint32_t n_scan_tiles(uint64_t total_bytes) {
     return static_cast<uint32_t>((n_flag_words(total_bytes) + kScanTileWords - 1) / kScanTileWords);
 }
 
-// Enqueue the whole path.  out_ids may be nullptr (count only).  Everything is asynchronous on `stream`.
+// The path in three stages so that a pipelined host call can put them on different streams:
+//   front  zero the flags, K1 split, K2 encode (throughput-bound, one after the other on the main stream)
+//   mid    K2b long pieces + flag_count  (latency-bound tail: may overlap the next sub-batch's front)
+//   back   tile_scan (chained on the previous sub-batch's token total), emit, prompt offsets
 template <typename Stream, typename Prof>
-inline void enqueue_encode(const BatchView& b, const VocabSet& vs, const UcTables& uc, const Workspace& w,
-                           uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_counts,
-                           uint32_t long_grid, Stream stream, Prof* prof, const uint64_t* token_base = nullptr) {
+inline void enqueue_front(const BatchView& b, const VocabSet& vs, const UcTables& uc, const Workspace& w, Stream stream, Prof* prof) {
+    const uint64_t nw = n_flag_words(b.total_bytes);
+    CFBPE_ZERO(w.status, sizeof(DeviceStatus), stream);
+    if (!b.total_bytes) return;
+    CFBPE_ZERO(w.piece_bits, (nw + 2) * sizeof(uint32_t), stream);
+    CFBPE_ZERO(w.tok_bits, (nw + 2) * sizeof(uint32_t), stream);
+    const uint64_t n_chunks = (b.total_bytes + kSplitChunk - 1) / kSplitChunk;
+    CFBPE_MARK(prof, K_SPLIT, stream, true);
+    CFBPE_LAUNCH(pretok_split_kernel, static_cast<unsigned>((n_chunks + 255) / 256), 256, stream, b, vs, uc, w.piece_bits, w.status);
+    CFBPE_MARK(prof, K_SPLIT, stream, false);
+    const uint64_t n_warps = (b.total_bytes + kEncodeRange - 1) / kEncodeRange;
+    CFBPE_MARK(prof, K_ENCODE, stream, true);
+    CFBPE_LAUNCH(bpe_encode_kernel, static_cast<unsigned>((n_warps + 7) / 8), 256, stream,
+                 b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
+    CFBPE_MARK(prof, K_ENCODE, stream, false);
+}
+
+template <typename Stream, typename Prof>
+inline void enqueue_mid(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
+    if (!b.total_bytes) return;
+    CFBPE_MARK(prof, K_LONG, stream, true);
+    CFBPE_LAUNCH(bpe_long_kernel, long_grid, 256, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
+    CFBPE_MARK(prof, K_LONG, stream, false);
+    CFBPE_MARK(prof, K_COUNT, stream, true);
+    CFBPE_LAUNCH(flag_count_kernel, n_scan_tiles(b.total_bytes), 256, stream, w.tok_bits, n_flag_words(b.total_bytes), w.tile_counts);
+    CFBPE_MARK(prof, K_COUNT, stream, false);
+}
+
+template <typename Stream, typename Prof>
+inline void enqueue_back(const BatchView& b, const Workspace& w, uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets,
+                         uint32_t* out_counts, Stream stream, Prof* prof, const uint64_t* token_base) {
     const uint64_t nw = n_flag_words(b.total_bytes);
     const uint32_t nt = n_scan_tiles(b.total_bytes);
-    CFBPE_ZERO(w.status, sizeof(DeviceStatus), stream);
     if (b.total_bytes) {
-        CFBPE_ZERO(w.piece_bits, (nw + 2) * sizeof(uint32_t), stream);
-        CFBPE_ZERO(w.tok_bits, (nw + 2) * sizeof(uint32_t), stream);
-
-        const uint64_t n_chunks = (b.total_bytes + kSplitChunk - 1) / kSplitChunk;
-        CFBPE_MARK(prof, K_SPLIT, stream, true);
-        CFBPE_LAUNCH(pretok_split_kernel, static_cast<unsigned>((n_chunks + 255) / 256), 256, stream,
-                     b, vs, uc, w.piece_bits, w.status);
-        CFBPE_MARK(prof, K_SPLIT, stream, false);
-
-        const uint64_t n_warps = (b.total_bytes + kEncodeRange - 1) / kEncodeRange;
-        CFBPE_MARK(prof, K_ENCODE, stream, true);
-        CFBPE_LAUNCH(bpe_encode_kernel, static_cast<unsigned>((n_warps + 7) / 8), 256, stream,
-                     b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
-        CFBPE_MARK(prof, K_ENCODE, stream, false);
-
-        CFBPE_MARK(prof, K_LONG, stream, true);
-        CFBPE_LAUNCH(bpe_long_kernel, long_grid, 256, stream,
-                     b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
-        CFBPE_MARK(prof, K_LONG, stream, false);
-
-        CFBPE_MARK(prof, K_COUNT, stream, true);
-        CFBPE_LAUNCH(flag_count_kernel, nt, 256, stream, w.tok_bits, nw, w.tile_counts);
-        CFBPE_MARK(prof, K_COUNT, stream, false);
         CFBPE_MARK(prof, K_SCAN, stream, true);
         CFBPE_LAUNCH(tile_scan_kernel, 1u, 1024, stream, w.tile_counts, nt, w.tile_base, w.status, token_base);
         CFBPE_MARK(prof, K_SCAN, stream, false);
@@ -75,6 +82,16 @@ inline void enqueue_encode(const BatchView& b, const VocabSet& vs, const UcTable
     CFBPE_LAUNCH(prompt_offsets_kernel, static_cast<unsigned>((static_cast<uint64_t>(b.n_prompts) + 1 + 255) / 256), 256, stream,
                  b, w.tok_bits, w.tile_base, out_offsets, out_counts, w.status);
     CFBPE_MARK(prof, K_EMIT, stream, false);
+}
+
+// The whole path on one stream.  out_ids may be nullptr (count only).  Everything is asynchronous on `stream`.
+template <typename Stream, typename Prof>
+inline void enqueue_encode(const BatchView& b, const VocabSet& vs, const UcTables& uc, const Workspace& w,
+                           uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_counts,
+                           uint32_t long_grid, Stream stream, Prof* prof, const uint64_t* token_base = nullptr) {
+    enqueue_front(b, vs, uc, w, stream, prof);
+    enqueue_mid(b, vs, w, long_grid, stream, prof);
+    enqueue_back(b, w, out_ids, out_cap, out_offsets, out_counts, stream, prof, token_base);
 }
 
 }  // namespace cfbpe

@@ -224,40 +224,4 @@ CFBPE_HD uint64_t match_end(const uint8_t* __restrict__ s, uint64_t p, uint64_t 
     }
 }
 
-// "Sync points": positions where the automaton's state follows from a few characters of left context,
-// so a thread may begin there knowing nothing else.  Returns the state BEFORE the character at pos is
-// consumed, or kNoSync.  pos > ps, pos < pe.
-//   START   whitespace (not CR/LF) right after a non-whitespace character
-//           CR/LF right after a letter or digit
-//           a digit right after a non-digit
-//           a punctuation character (class OTHER, not an apostrophe) right after a letter or digit
-//   LETTERS (uncased patterns) the three previous characters are letters: contractions cover at most two
-//   W_Y     (cased patterns) the previous character is a lower-case letter and the two before it are letters
-constexpr uint32_t kNoSync = 0xFFu;
-constexpr uint32_t kSyncStart = 0, kSyncLetters = 1, kSyncWordLower = 20;   // = S_START, S_LETTERS, S_W_Y of pretok_fsm.h
-
-CFBPE_HD uint32_t sync_state(const uint8_t* __restrict__ s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc, bool cased) {
-    const uint32_t b = s[pos];
-    if ((b & 0xC0) == 0x80) return kNoSync;  // inside a character
-    int bad = 0;
-    const Ch cur = get_char(s, pos, pe, uc, &bad);
-    if (bad) return kNoSync;
-    const Ch prev = get_prev_char(s, pos, ps, pe, uc);
-    if (cur.cls == C_WS) return is_ws(prev.cls) ? kNoSync : kSyncStart;
-    if (cur.cls == C_CRLF) return (is_letter(prev.cls) || prev.cls == C_N) ? kSyncStart : kNoSync;
-    if (cur.cls == C_N) return prev.cls != C_N ? kSyncStart : kNoSync;
-    if (cur.cls == C_OTHER && cur.cp != '\'' && (is_letter(prev.cls) || prev.cls == C_N)) return kSyncStart;
-    if (is_letter(prev.cls) && (!cased || prev.cls == C_LL)) {
-        uint64_t q = pos - prev.len;
-        for (int k = 0; k < 2; ++k) {
-            if (q <= ps) return kNoSync;
-            const Ch c = get_prev_char(s, q, ps, pe, uc);
-            if (!is_letter(c.cls)) return kNoSync;
-            q -= c.len;
-        }
-        return cased ? kSyncWordLower : kSyncLetters;
-    }
-    return kNoSync;
-}
-
 }  // namespace cfbpe

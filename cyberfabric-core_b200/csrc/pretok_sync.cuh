@@ -1,0 +1,68 @@
+// pretok_sync.cuh -- "sync points": positions where the automaton's state follows from a few characters of
+// left context, so a K1 thread may begin there knowing nothing else (and the thread coming from the left hands over).
+//
+//   START   whitespace (not CR/LF) right after a non-whitespace character
+//           CR/LF right after a letter or digit
+//           a digit right after a non-digit
+//           a punctuation character (class OTHER, not an apostrophe, not a mark) right after a letter or digit
+//   LETTERS (uncased patterns) the three previous characters are letters: a contraction covers at most two
+//   W_Y     (cased patterns) the previous character is a lower-case letter and the two before it are letters
+//
+// sync_rule() is the predicate on classes; sync_state() evaluates it from memory (used to FIND a start);
+// the running thread evaluates the same predicate from the classes it has just seen (no loads).
+#pragma once
+#include "pretok.cuh"
+#include "pretok_fsm.h"
+
+namespace cfbpe {
+
+constexpr uint32_t kNoSync = 0xFFu;
+
+CFBPE_HD uint32_t ext_class(const Ch& c) {   // C_* class + code point -> X_* class
+    if (c.cp == ' ') return X_SPACE;
+    if (c.cp == '\'') return X_APOS;
+    if (c.cp == '/') return X_SLASH;
+    return c.cls;
+}
+CFBPE_HD bool x_is_letter(uint32_t x) { return x == X_LU || x == X_LL || x == X_LO; }
+CFBPE_HD bool x_is_ws(uint32_t x) { return x == X_WS || x == X_SPACE || x == X_CRLF; }
+
+// state BEFORE the character of class x is consumed, given the class of the previous character and the number
+// (saturated at 3) of consecutive letters right before it; kNoSync if the context does not determine it
+CFBPE_HD uint32_t sync_rule(uint32_t x, uint32_t prevx, uint32_t nlet, bool cased) {
+    const bool prev_ln = x_is_letter(prevx) || prevx == X_N;
+    if (x == X_WS || x == X_SPACE) return x_is_ws(prevx) ? kNoSync : static_cast<uint32_t>(S_START);
+    if (x == X_CRLF) return prev_ln ? static_cast<uint32_t>(S_START) : kNoSync;
+    if (x == X_N) return prevx != X_N ? static_cast<uint32_t>(S_START) : kNoSync;
+    if ((x == X_OTHER || x == X_SLASH) && prev_ln) return S_START;
+    if (nlet >= 3 && (cased ? prevx == X_LL : x_is_letter(prevx))) return cased ? static_cast<uint32_t>(S_W_Y) : static_cast<uint32_t>(S_LETTERS);
+    return kNoSync;
+}
+
+// evaluate the rule at byte position pos (ps < pos < pe) by decoding up to three characters to the left
+CFBPE_HD uint32_t sync_state(const uint8_t* __restrict__ s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc, bool cased,
+                             uint32_t* prevx_out = nullptr, uint32_t* nlet_out = nullptr) {
+    const uint32_t b = s[pos];
+    if ((b & 0xC0) == 0x80) return kNoSync;  // inside a character
+    int bad = 0;
+    const Ch cur = get_char(s, pos, pe, uc, &bad);
+    if (bad) return kNoSync;
+    const Ch prev = get_prev_char(s, pos, ps, pe, uc);
+    const uint32_t prevx = ext_class(prev);
+    uint32_t nlet = 0;
+    if (x_is_letter(prevx)) {
+        nlet = 1;
+        uint64_t q = pos - prev.len;
+        while (nlet < 3 && q > ps) {
+            const Ch c = get_prev_char(s, q, ps, pe, uc);
+            if (!is_letter(c.cls)) break;
+            ++nlet;
+            q -= c.len;
+        }
+    }
+    if (prevx_out) *prevx_out = prevx;
+    if (nlet_out) *nlet_out = nlet;
+    return sync_rule(ext_class(cur), prevx, nlet, cased);
+}
+
+}  // namespace cfbpe
