@@ -37,7 +37,7 @@ static inline void prof_mark(ProfEvents* p, int idx, cudaStream_t s, bool begin)
 }
 
 constexpr int kMaxPipeChunks = 64;
-constexpr int kSideStreams = 4;
+constexpr int kSideStreams = 16;
 constexpr uint64_t kPipeChunkBytes = 12ull << 20;   // sub-batch size of a pipelined host call
 constexpr uint64_t kPipeMinBytes = 24ull << 20;     // smaller calls run as one shot
 

@@ -13,8 +13,14 @@ ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--config", type=int, default=3)
 ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--mix", default="")  # e.g. 0,0,0,1 = adversarial only
 a = ap.parse_args()
-data, offs, vid, meta = W.make_config(a.config, a.scale)
+if a.mix:
+    mix = tuple(float(x) for x in a.mix.split(","))
+    data, offs, meta = W.make_batch(int(65536 * a.scale), 8, 4096, 3, mix=mix)
+    meta["vocabs"] = ["cl100k_base"]
+else:
+    data, offs, vid, meta = W.make_config(a.config, a.scale)
 name = meta["vocabs"][0]
 plug = P.GpuBpeTokenizerPlugin(0, (name,), 160 << 20, 1 << 17)
 dev = torch.device("cuda:0")
