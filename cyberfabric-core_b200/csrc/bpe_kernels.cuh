@@ -46,9 +46,9 @@ struct DeviceStatus {
     uint32_t bad_utf8;     // != 0: some prompt held malformed UTF-8
     uint32_t n_long;       // number of long pieces queued for K2b
     uint32_t long_overflow;
-    uint32_t long_next;    // K2b work ticket
+    uint32_t long_next;    // K2b work ticket (pieces of 33..kBigPiece bytes)
+    uint32_t big_next;     // K2b work ticket (longer pieces)
     uint32_t n_big;        // pieces longer than kBigPiece (stored from the back of the list)
-    uint32_t pad;
     uint64_t n_tokens;     // ids produced by this (sub-)batch (written by tile_scan)
     uint64_t tok_end;      // token_base + n_tokens: where the next sub-batch of a pipelined call continues
 };
@@ -405,20 +405,104 @@ __device__ __forceinline__ bool select_chunk(uint32_t r, uint32_t rmin, uint32_t
     return sel;
 }
 
-__global__ void __launch_bounds__(256)
+// phase B on whatever memory the pointers name (global scratch, or shared memory for the big-piece kernel).
+// Lane L owns parts [L<<csh, (L+1)<<csh); the minimum of each eighth of that chunk is cached in shared memory and
+// maintained incrementally: only a sub-chunk whose cached minimum element got a larger rank is re-scanned.
+template <typename Link>
+__device__ __forceinline__ void list_rounds(const TablesView& T, uint32_t* id, uint32_t* rk, Link* nx, Link* pv, uint32_t m,
+                                            uint32_t* subr, uint32_t* subp, uint32_t lane) {
+    constexpr uint32_t kNoPrev = static_cast<Link>(~static_cast<Link>(0));
+    uint32_t csh = 0;
+    while ((32u << csh) < m) ++csh;               // chunk = 2^csh parts per lane
+    const uint32_t ssh = csh >= 3 ? csh - 3 : 0;  // sub-chunk = 2^ssh parts, nsub = chunk / sub-chunk <= 8
+    const uint32_t nsub = 1u << (csh - ssh);
+    for (uint32_t i = lane; i < m; i += 32) { nx[i] = static_cast<Link>(i + 1); pv[i] = static_cast<Link>(i ? i - 1 : kNoPrev); }
+    __syncwarp();
+    const uint32_t lo = lane << csh;
+    auto rescan_sub = [&](uint32_t ks) {
+        uint32_t r0 = kNone, p0 = 0;
+        const uint32_t x0 = lo + (ks << ssh), x1 = (x0 + (1u << ssh)) < m ? (x0 + (1u << ssh)) : m;
+        uint32_t x = x0;
+        for (; x + 4 <= x1; x += 4) {   // four loads in flight
+            const uint32_t ra = rk[x], rb = rk[x + 1], rc = rk[x + 2], rd = rk[x + 3];
+            if (ra < r0) { r0 = ra; p0 = x; }
+            if (rb < r0) { r0 = rb; p0 = x + 1; }
+            if (rc < r0) { r0 = rc; p0 = x + 2; }
+            if (rd < r0) { r0 = rd; p0 = x + 3; }
+        }
+        for (; x < x1; ++x) { const uint32_t ra = rk[x]; if (ra < r0) { r0 = ra; p0 = x; } }
+        subr[ks * 32] = r0; subp[ks * 32] = p0;
+    };
+    uint32_t mymin = kNone, mypos = 0;
+    auto lane_min = [&]() {
+        mymin = kNone;
+        for (uint32_t ks = 0; ks < nsub; ++ks) { const uint32_t rr = subr[ks * 32]; if (rr < mymin) { mymin = rr; mypos = subp[ks * 32]; } }
+    };
+    if (lo < m) for (uint32_t ks = 0; ks < nsub; ++ks) rescan_sub(ks);
+    else for (uint32_t ks = 0; ks < nsub; ++ks) { subr[ks * 32] = kNone; subp[ks * 32] = 0; }
+    lane_min();
+    for (;;) {
+        const uint32_t best = warp_min_u32(mymin != kNone ? ((mymin << 5) | lane) : kNone);
+        if (best == kNone) break;
+        const uint32_t r = best >> 5;
+        const uint32_t i = __shfl_sync(kFull, mypos, best & 31u);
+        const uint32_t j = nx[i];
+        const uint32_t q = pv[i];
+        const uint32_t k = nx[j];
+        uint32_t val = kNone;
+        if (lane == 0 && k < m) val = pair_lookup(T, r, id[k]);
+        if (lane == 1 && q != kNoPrev) val = pair_lookup(T, id[q], r);
+        const uint32_t newR = __shfl_sync(kFull, val, 0);
+        const uint32_t newL = __shfl_sync(kFull, val, 1);
+        if (lane == 0) {
+            id[i] = r; id[j] = kNone; rk[j] = kNone; rk[i] = newR; nx[i] = static_cast<Link>(k);
+            if (k < m) pv[k] = static_cast<Link>(i);
+            if (q != kNoPrev) rk[q] = newL;
+        }
+        __syncwarp();
+        const uint32_t oi = i >> csh, oj = j >> csh, oq = (q != kNoPrev) ? (q >> csh) : 32u;
+        if (lane == oi || lane == oj || lane == oq) {
+            if (lane == oi) rescan_sub((i - lo) >> ssh);        // i was the minimum of its sub-chunk: its rank changed
+            if (lane == oj) { const uint32_t ks = (j - lo) >> ssh; if (subp[ks * 32] == j) rescan_sub(ks); }
+            if (lane == oq) {
+                const uint32_t ks = (q - lo) >> ssh;
+                const uint32_t cr = subr[ks * 32], cp = subp[ks * 32];
+                if (newL < cr || (newL == cr && q < cp)) { subr[ks * 32] = newL; subp[ks * 32] = q; }
+                else if (cp == q) rescan_sub(ks);
+            }
+            lane_min();
+        }
+    }
+}
+
+#ifdef CFBPE_SIM
+#define CFBPE_DYN_SMEM(name) unsigned char* name = cusim::dyn_smem()
+#else
+#define CFBPE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+constexpr uint32_t kBigSmemParts = 4096;                      // parts of one piece held in shared memory (phase B)
+constexpr uint32_t kBigWarps = 4;                             // warps per CTA of the big-piece kernel
+constexpr uint32_t kBigSmemPerWarp = kBigSmemParts * 12;      // id u32 + rk u32 + next u16 + prev u16
+constexpr uint32_t kBigSmemBytes = kBigWarps * kBigSmemPerWarp;
+
+// kBig = false: pieces of 33..kBigPiece bytes (many warps, state in global scratch)
+// kBig = true : longer pieces, served from the back of the list; phase B runs in shared memory (the serial
+//               chain of a non-repetitive 4 KiB piece is ~2500 rounds: L2 latency per step is what it costs)
+template <bool kBig>
+__global__ void __launch_bounds__(kBig ? kBigWarps * 32 : 256)
 bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
-    __shared__ uint32_t s_subr[8][8][32];   // [warp][sub-chunk][lane] cached minimum rank ...
-    __shared__ uint32_t s_subp[8][8][32];   // ... and its position (phase B)
+    __shared__ uint32_t s_subr[kBig ? kBigWarps : 8][8][32];   // [warp][sub-chunk][lane] cached minimum rank ...
+    __shared__ uint32_t s_subp[kBig ? kBigWarps : 8][8][32];   // ... and its position (phase B)
+    CFBPE_DYN_SMEM(dsm);
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t n_big = status->n_big;
-    const uint32_t n_all = status->long_overflow ? 0u : status->n_long + n_big;
+    const uint32_t n_items = status->long_overflow ? 0u : (kBig ? status->n_big : status->n_long);
     for (;;) {
         uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(&status->long_next, 1u);
+        if (lane == 0) item = atomicAdd(kBig ? &status->big_next : &status->long_next, 1u);
         item = __shfl_sync(kFull, item, 0);
-        if (item >= n_all) break;
-        const LongPiece lp = long_list[item < n_big ? long_cap - 1 - item : item - n_big];
+        if (item >= n_items) break;
+        const LongPiece lp = long_list[kBig ? long_cap - 1 - item : item];
         const TablesView T = vs.v[lp.vocab];
         const uint8_t* __restrict__ p = b.bytes + lp.start;
         const uint32_t n = static_cast<uint32_t>(lp.end - lp.start);
@@ -516,62 +600,25 @@ bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
             if (rmin != kNone && merged * 8u < m && m > 32u) { list_mode = true; break; }
         }
 
-        // ---- phase B: linked list, one merge per round.  Lane L owns parts [L<<csh, (L+1)<<csh); the minimum of each
-        //      eighth of that chunk is cached in shared memory, so a changed rank costs a re-scan of chunk/8 parts
+        // ---- phase B: linked list, one merge per round
         if (list_mode) {
-            uint32_t csh = 0;
-            while ((32u << csh) < m) ++csh;               // chunk = 2^csh parts per lane
-            const uint32_t ssh = csh >= 3 ? csh - 3 : 0;  // sub-chunk = 2^ssh parts, nsub = chunk / sub-chunk <= 8
-            const uint32_t nsub = 1u << (csh - ssh);
-            for (uint32_t i = lane; i < m; i += 32) { a0[i] = i + 1; a1[i] = i ? i - 1 : kNone; }
-            __syncwarp();
-            const uint32_t lo = lane << csh;
-            uint32_t* subr = &s_subr[threadIdx.x >> 5][0][lane];   // [k * 32]
+            uint32_t* subr = &s_subr[threadIdx.x >> 5][0][lane];
             uint32_t* subp = &s_subp[threadIdx.x >> 5][0][lane];
-            uint32_t mymin = kNone, mypos = 0;
-            for (uint32_t k = 0; k < nsub; ++k) {
-                uint32_t r0 = kNone, p0 = 0;
-                const uint32_t x0 = lo + (k << ssh), x1 = (x0 + (1u << ssh)) < m ? (x0 + (1u << ssh)) : m;
-                for (uint32_t x = x0; x < x1; ++x) { const uint32_t r = rk[x]; if (r < r0) { r0 = r; p0 = x; } }
-                subr[k * 32] = r0; subp[k * 32] = p0;
-                if (r0 < mymin) { mymin = r0; mypos = p0; }
-            }
-            for (;;) {
-                const uint32_t best = warp_min_u32(mymin != kNone ? ((mymin << 5) | lane) : kNone);
-                if (best == kNone) break;
-                const uint32_t r = best >> 5;
-                const uint32_t i = __shfl_sync(kFull, mypos, best & 31u);
-                const uint32_t j = a0[i];
-                const uint32_t q = a1[i];
-                const uint32_t k = a0[j];
-                uint32_t val = kNone;
-                if (lane == 0 && k < m) val = pair_lookup(T, r, id[k]);
-                if (lane == 1 && q != kNone) val = pair_lookup(T, id[q], r);
-                const uint32_t newR = __shfl_sync(kFull, val, 0);
-                const uint32_t newL = __shfl_sync(kFull, val, 1);
-                if (lane == 0) {
-                    id[i] = r; id[j] = kNone; rk[j] = kNone; rk[i] = newR; a0[i] = k;
-                    if (k < m) a1[k] = i;
-                    if (q != kNone) rk[q] = newL;
-                }
+            if (kBig && m <= kBigSmemParts) {
+                unsigned char* base = dsm + (threadIdx.x >> 5) * kBigSmemPerWarp;
+                uint32_t* sid = reinterpret_cast<uint32_t*>(base);
+                uint32_t* srk = sid + kBigSmemParts;
+                uint16_t* snx = reinterpret_cast<uint16_t*>(srk + kBigSmemParts);
+                uint16_t* spv = snx + kBigSmemParts;
+                for (uint32_t i = lane; i < m; i += 32) { sid[i] = id[i]; srk[i] = rk[i]; }
                 __syncwarp();
-                // refresh the cached minima of the (at most three) sub-chunks whose ranks changed
-                const uint32_t oi = i >> csh, oj = j >> csh, oq = (q != kNone) ? (q >> csh) : 32u;
-                if (lane == oi || lane == oj || lane == oq) {
-#pragma unroll 1
-                    for (uint32_t t = 0; t < 3; ++t) {
-                        const uint32_t x = t == 0 ? i : (t == 1 ? j : q);
-                        if (x == kNone || (x >> csh) != lane) continue;
-                        const uint32_t ks = (x - lo) >> ssh;
-                        uint32_t r0 = kNone, p0 = 0;
-                        const uint32_t x0 = lo + (ks << ssh), x1 = (x0 + (1u << ssh)) < m ? (x0 + (1u << ssh)) : m;
-                        for (uint32_t y = x0; y < x1; ++y) { const uint32_t rr = rk[y]; if (rr < r0) { r0 = rr; p0 = y; } }
-                        subr[ks * 32] = r0; subp[ks * 32] = p0;
-                    }
-                    mymin = kNone;
-                    for (uint32_t ks = 0; ks < nsub; ++ks) { const uint32_t rr = subr[ks * 32]; if (rr < mymin) { mymin = rr; mypos = subp[ks * 32]; } }
-                }
+                list_rounds<uint16_t>(T, sid, srk, snx, spv, m, subr, subp, lane);
+                __syncwarp();
+                for (uint32_t i = lane; i < m; i += 32) id[i] = sid[i];
+            } else {
+                list_rounds<uint32_t>(T, id, rk, a0, a1, m, subr, subp, lane);
             }
+            __syncwarp();
         }
         // ---- one flag per surviving part (dead slots hold kNone); order along the slice is token order
         for (uint32_t base = 0; base < m; base += 32) {

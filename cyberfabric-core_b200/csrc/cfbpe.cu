@@ -15,6 +15,7 @@
 
 struct ProfEvents;
 #define CFBPE_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define CFBPE_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define CFBPE_ZERO(ptr, bytes, stream) cudaMemsetAsync((ptr), 0, (bytes), (stream))
 #define CFBPE_MARK(prof, idx, stream, begin) prof_mark((prof), (idx), (stream), (begin))
 static inline void prof_mark(ProfEvents* p, int idx, cudaStream_t s, bool begin);
@@ -382,6 +383,11 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
         return CFBPE_ENOMEM;
     }
     ctx->uc = UcTables{ctx->d_uc1, ctx->d_uc2, ctx->d_ascii, ctx->d_fsm};
+    if (cudaFuncSetAttribute(bpe_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBigSmemBytes)) != cudaSuccess) {
+        cudaGetLastError();
+        cfbpe_destroy(ctx);
+        return CFBPE_EIO;
+    }
     if (const char* e = std::getenv("CFBPE_PIPE_CHUNK_BYTES")) { const uint64_t v = std::strtoull(e, nullptr, 10); if (v >= 1024) ctx->pipe_chunk = v; }
     if (const char* e = std::getenv("CFBPE_PIPE_MIN_BYTES")) { const uint64_t v = std::strtoull(e, nullptr, 10); if (v >= 1) ctx->pipe_min = v; }
     *out = ctx;

@@ -173,6 +173,8 @@ inline void syncthreads() {
     else while (b.bar_gen == gen) yield();
 }
 
+inline unsigned char* dyn_smem() { static unsigned char buf[256 * 1024] __attribute__((aligned(16))); return buf; }
+
 template <typename T> inline uint64_t to_u64(T v) { uint64_t u = 0; std::memcpy(&u, &v, sizeof(T)); return u; }
 template <typename T> inline T from_u64(uint64_t u) { T v; std::memcpy(&v, &u, sizeof(T)); return v; }
 

@@ -5,6 +5,7 @@
 #include "cusim.h"
 
 #define CFBPE_LAUNCH(kernel, grid, block, stream, ...) cusim::launch((grid), (block), [&] { kernel(__VA_ARGS__); })
+#define CFBPE_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) cusim::launch((grid), (block), [&] { kernel(__VA_ARGS__); })
 #define CFBPE_ZERO(ptr, bytes, stream) std::memset((ptr), 0, (bytes))
 #define CFBPE_MARK(prof, idx, stream, begin) ((void)0)
 
