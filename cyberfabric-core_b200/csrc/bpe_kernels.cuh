@@ -47,8 +47,8 @@ struct DeviceStatus {
     uint32_t n_long;       // number of long pieces queued for K2b
     uint32_t long_overflow;
     uint32_t long_next;    // K2b work ticket (pieces of 33..kBigPiece bytes)
-    uint32_t big_next;     // K2b work ticket (longer pieces)
     uint32_t n_big;        // pieces longer than kBigPiece (stored from the back of the list)
+    uint32_t pad;
     uint64_t n_tokens;     // ids produced by this (sub-)batch (written by tile_scan)
     uint64_t tok_end;      // token_base + n_tokens: where the next sub-batch of a pipelined call continues
 };
@@ -405,111 +405,132 @@ __device__ __forceinline__ bool select_chunk(uint32_t r, uint32_t rmin, uint32_t
     return sel;
 }
 
-// phase B on whatever memory the pointers name (global scratch, or shared memory for the big-piece kernel).
+// phase B: linked list over the compact array, ONE merge per round (exact sequential order).  The round is a
+// dependent chain  argmin -> link[i] -> {link[j], nid[j], id[q]} -> two table probes -> cached minima,  so the
+// data is laid out to keep that chain short:
+//   link[i] = next<<16 | prev           (one load names both neighbours; m <= 65535)
+//   nid[i]  = id of the part after i    (the right-hand probe needs no id[] load of the part after the partner)
 // Lane L owns parts [L<<csh, (L+1)<<csh); the minimum of each eighth of that chunk is cached in shared memory and
-// maintained incrementally: only a sub-chunk whose cached minimum element got a larger rank is re-scanned.
-template <typename Link>
-__device__ __forceinline__ void list_rounds(const TablesView& T, uint32_t* id, uint32_t* rk, Link* nx, Link* pv, uint32_t m,
+// maintained incrementally: only a sub-chunk whose cached minimum element got a larger rank is re-scanned, and the
+// winner's sub-chunk is pre-loaded while the probes are in flight.
+constexpr uint32_t kListMax = 65535;
+constexpr uint32_t kMedSmem = 256;   // bytes: pieces up to this size keep their merge state in shared memory
+__device__ __forceinline__ void list_rounds(const TablesView& T, uint32_t* __restrict__ id, uint32_t* __restrict__ rk,
+                                            uint32_t* __restrict__ link, uint32_t* __restrict__ nid, uint32_t m,
                                             uint32_t* subr, uint32_t* subp, uint32_t lane) {
-    constexpr uint32_t kNoPrev = static_cast<Link>(~static_cast<Link>(0));
+    constexpr uint32_t kNoPrev = 0xFFFFu;
     uint32_t csh = 0;
     while ((32u << csh) < m) ++csh;               // chunk = 2^csh parts per lane
     const uint32_t ssh = csh >= 3 ? csh - 3 : 0;  // sub-chunk = 2^ssh parts, nsub = chunk / sub-chunk <= 8
     const uint32_t nsub = 1u << (csh - ssh);
-    for (uint32_t i = lane; i < m; i += 32) { nx[i] = static_cast<Link>(i + 1); pv[i] = static_cast<Link>(i ? i - 1 : kNoPrev); }
+    for (uint32_t i = lane; i < m; i += 32) {
+        link[i] = ((i + 1) << 16) | (i ? i - 1 : kNoPrev);
+        nid[i] = (i + 1 < m) ? id[i + 1] : kNone;
+    }
     __syncwarp();
     const uint32_t lo = lane << csh;
-    auto rescan_sub = [&](uint32_t ks) {
-        uint32_t r0 = kNone, p0 = 0;
+    auto scan_sub = [&](uint32_t ks, uint32_t skip, uint32_t& r0, uint32_t& p0) {   // min over the sub-chunk except `skip`
+        r0 = kNone; p0 = 0;
         const uint32_t x0 = lo + (ks << ssh), x1 = (x0 + (1u << ssh)) < m ? (x0 + (1u << ssh)) : m;
         uint32_t x = x0;
         for (; x + 4 <= x1; x += 4) {   // four loads in flight
             const uint32_t ra = rk[x], rb = rk[x + 1], rc = rk[x + 2], rd = rk[x + 3];
-            if (ra < r0) { r0 = ra; p0 = x; }
-            if (rb < r0) { r0 = rb; p0 = x + 1; }
-            if (rc < r0) { r0 = rc; p0 = x + 2; }
-            if (rd < r0) { r0 = rd; p0 = x + 3; }
+            if (ra < r0 && x != skip) { r0 = ra; p0 = x; }
+            if (rb < r0 && x + 1 != skip) { r0 = rb; p0 = x + 1; }
+            if (rc < r0 && x + 2 != skip) { r0 = rc; p0 = x + 2; }
+            if (rd < r0 && x + 3 != skip) { r0 = rd; p0 = x + 3; }
         }
-        for (; x < x1; ++x) { const uint32_t ra = rk[x]; if (ra < r0) { r0 = ra; p0 = x; } }
-        subr[ks * 32] = r0; subp[ks * 32] = p0;
+        for (; x < x1; ++x) { const uint32_t ra = rk[x]; if (ra < r0 && x != skip) { r0 = ra; p0 = x; } }
     };
     uint32_t mymin = kNone, mypos = 0;
     auto lane_min = [&]() {
         mymin = kNone;
         for (uint32_t ks = 0; ks < nsub; ++ks) { const uint32_t rr = subr[ks * 32]; if (rr < mymin) { mymin = rr; mypos = subp[ks * 32]; } }
     };
-    if (lo < m) for (uint32_t ks = 0; ks < nsub; ++ks) rescan_sub(ks);
-    else for (uint32_t ks = 0; ks < nsub; ++ks) { subr[ks * 32] = kNone; subp[ks * 32] = 0; }
+    for (uint32_t ks = 0; ks < nsub; ++ks) {
+        uint32_t r0 = kNone, p0 = 0;
+        if (lo < m) scan_sub(ks, kNone, r0, p0);
+        subr[ks * 32] = r0; subp[ks * 32] = p0;
+    }
     lane_min();
     for (;;) {
-        const uint32_t best = warp_min_u32(mymin != kNone ? ((mymin << 5) | lane) : kNone);
+        const uint32_t best = __reduce_min_sync(kFull, mymin != kNone ? ((mymin << 5) | lane) : kNone);
         if (best == kNone) break;
-        const uint32_t r = best >> 5;
+        const uint32_t r = best >> 5;                          // rank == id of the merged token
         const uint32_t i = __shfl_sync(kFull, mypos, best & 31u);
-        const uint32_t j = nx[i];
-        const uint32_t q = pv[i];
-        const uint32_t k = nx[j];
-        uint32_t val = kNone;
-        if (lane == 0 && k < m) val = pair_lookup(T, r, id[k]);
+        const uint32_t li = link[i];
+        const uint32_t j = li >> 16, q = li & 0xFFFFu;
+        const uint32_t oi = i >> csh;
+        // the owner of i pre-loads the rest of i's sub-chunk while the probes below are in flight
+        uint32_t pr = kNone, pp = 0;
+        if (lane == oi) scan_sub((i - lo) >> ssh, i, pr, pp);
+        // lane 0: right-hand probe (merged, part after the partner); lane 1: left-hand probe (previous part, merged)
+        uint32_t val = kNone, k = 0;
+        if (lane == 0) {
+            k = link[j] >> 16;
+            const uint32_t idk = nid[j];
+            if (k < m) val = pair_lookup(T, r, idk);
+        }
         if (lane == 1 && q != kNoPrev) val = pair_lookup(T, id[q], r);
         const uint32_t newR = __shfl_sync(kFull, val, 0);
         const uint32_t newL = __shfl_sync(kFull, val, 1);
+        k = __shfl_sync(kFull, k, 0);
         if (lane == 0) {
-            id[i] = r; id[j] = kNone; rk[j] = kNone; rk[i] = newR; nx[i] = static_cast<Link>(k);
-            if (k < m) pv[k] = static_cast<Link>(i);
-            if (q != kNoPrev) rk[q] = newL;
+            id[i] = r; id[j] = kNone; rk[j] = kNone; rk[i] = newR;
+            link[i] = (k << 16) | q;
+            nid[i] = nid[j];
+            if (k < m) link[k] = (link[k] & 0xFFFF0000u) | i;
+            if (q != kNoPrev) { rk[q] = newL; nid[q] = r; }
         }
         __syncwarp();
-        const uint32_t oi = i >> csh, oj = j >> csh, oq = (q != kNoPrev) ? (q >> csh) : 32u;
+        const uint32_t oj = j >> csh, oq = (q != kNoPrev) ? (q >> csh) : 32u;
         if (lane == oi || lane == oj || lane == oq) {
-            if (lane == oi) rescan_sub((i - lo) >> ssh);        // i was the minimum of its sub-chunk: its rank changed
-            if (lane == oj) { const uint32_t ks = (j - lo) >> ssh; if (subp[ks * 32] == j) rescan_sub(ks); }
-            if (lane == oq) {
+            if (lane == oi) {       // i was its sub-chunk's minimum; the others were pre-loaded, but j / q may sit there too
+                const uint32_t ks = (i - lo) >> ssh;
+                if ((j >> ssh) == (i >> ssh) || (q != kNoPrev && (q >> ssh) == (i >> ssh))) scan_sub(ks, kNone, pr, pp);
+                else if (newR < pr || (newR == pr && i < pp)) { pr = newR; pp = i; }
+                subr[ks * 32] = pr; subp[ks * 32] = pp;
+            }
+            if (lane == oj && (j >> ssh) != (i >> ssh)) {
+                const uint32_t ks = (j - lo) >> ssh;
+                if (subp[ks * 32] == j) { uint32_t r0, p0; scan_sub(ks, kNone, r0, p0); subr[ks * 32] = r0; subp[ks * 32] = p0; }
+            }
+            if (lane == oq && (q >> ssh) != (i >> ssh)) {
                 const uint32_t ks = (q - lo) >> ssh;
                 const uint32_t cr = subr[ks * 32], cp = subp[ks * 32];
                 if (newL < cr || (newL == cr && q < cp)) { subr[ks * 32] = newL; subp[ks * 32] = q; }
-                else if (cp == q) rescan_sub(ks);
+                else if (cp == q) { uint32_t r0, p0; scan_sub(ks, kNone, r0, p0); subr[ks * 32] = r0; subp[ks * 32] = p0; }
             }
             lane_min();
         }
     }
 }
 
-#ifdef CFBPE_SIM
-#define CFBPE_DYN_SMEM(name) unsigned char* name = cusim::dyn_smem()
-#else
-#define CFBPE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
-#endif
-constexpr uint32_t kBigSmemParts = 4096;                      // parts of one piece held in shared memory (phase B)
-constexpr uint32_t kBigWarps = 4;                             // warps per CTA of the big-piece kernel
-constexpr uint32_t kBigSmemPerWarp = kBigSmemParts * 12;      // id u32 + rk u32 + next u16 + prev u16
-constexpr uint32_t kBigSmemBytes = kBigWarps * kBigSmemPerWarp;
-
-// kBig = false: pieces of 33..kBigPiece bytes (many warps, state in global scratch)
-// kBig = true : longer pieces, served from the back of the list; phase B runs in shared memory (the serial
-//               chain of a non-repetitive 4 KiB piece is ~2500 rounds: L2 latency per step is what it costs)
-template <bool kBig>
-__global__ void __launch_bounds__(kBig ? kBigWarps * 32 : 256)
+__global__ void __launch_bounds__(256)
 bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
-    __shared__ uint32_t s_subr[kBig ? kBigWarps : 8][8][32];   // [warp][sub-chunk][lane] cached minimum rank ...
-    __shared__ uint32_t s_subp[kBig ? kBigWarps : 8][8][32];   // ... and its position (phase B)
-    CFBPE_DYN_SMEM(dsm);
+    __shared__ uint32_t s_subr[8][8][32];   // [warp][sub-chunk][lane] cached minimum rank ...
+    __shared__ uint32_t s_subp[8][8][32];   // ... and its position (phase B)
+    __shared__ uint32_t s_med[8][4][kMedSmem];   // [warp][id | rank | aux0 | aux1] of a piece of <= kMedSmem bytes
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t n_items = status->long_overflow ? 0u : (kBig ? status->n_big : status->n_long);
+    const uint32_t n_big = status->n_big;
+    const uint32_t n_all = status->long_overflow ? 0u : status->n_long + n_big;
     for (;;) {
         uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(kBig ? &status->big_next : &status->long_next, 1u);
+        if (lane == 0) item = atomicAdd(&status->long_next, 1u);
         item = __shfl_sync(kFull, item, 0);
-        if (item >= n_items) break;
-        const LongPiece lp = long_list[kBig ? long_cap - 1 - item : item];
+        if (item >= n_all) break;
+        const LongPiece lp = long_list[item < n_big ? long_cap - 1 - item : item - n_big];
         const TablesView T = vs.v[lp.vocab];
         const uint8_t* __restrict__ p = b.bytes + lp.start;
         const uint32_t n = static_cast<uint32_t>(lp.end - lp.start);
-        uint32_t* __restrict__ id = ids_by_pos + lp.start;
-        uint32_t* __restrict__ rk = sc.rank + lp.start;
-        uint32_t* __restrict__ a0 = sc.aux0 + lp.start;
-        uint32_t* __restrict__ a1 = sc.aux1 + lp.start;
+        // state of the piece: shared memory for pieces of <= kMedSmem bytes (most of them), else its slice of scratch
+        uint32_t* const gid = ids_by_pos + lp.start;
+        const bool in_smem = n <= kMedSmem;
+        uint32_t* id = in_smem ? s_med[threadIdx.x >> 5][0] : gid;
+        uint32_t* rk = in_smem ? s_med[threadIdx.x >> 5][1] : sc.rank + lp.start;
+        uint32_t* a0 = in_smem ? s_med[threadIdx.x >> 5][2] : sc.aux0 + lp.start;
+        uint32_t* a1 = in_smem ? s_med[threadIdx.x >> 5][3] : sc.aux1 + lp.start;
 
         // ---- whole-piece shortcut (CoreBPE: `if piece in ranks`)
         if (n <= T.max_token_len) {
@@ -517,7 +538,7 @@ bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
             if (lane == 0) t = piece_lookup(T, p, n);
             t = __shfl_sync(kFull, t, 0);
             if (t != kNone) {
-                if (lane == 0) { id[0] = t; atomicOr(&tok_bits[lp.start >> 5], 1u << (lp.start & 31)); }
+                if (lane == 0) { gid[0] = t; atomicOr(&tok_bits[lp.start >> 5], 1u << (lp.start & 31)); }
                 continue;
             }
         }
@@ -597,33 +618,19 @@ bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
             const uint32_t merged = m - out;
             m = out;
             rmin = warp_min_u32(nmin);
-            if (rmin != kNone && merged * 8u < m && m > 32u) { list_mode = true; break; }
+            if (rmin != kNone && merged * 8u < m && m > 32u && m <= kListMax) { list_mode = true; break; }
         }
 
         // ---- phase B: linked list, one merge per round
         if (list_mode) {
-            uint32_t* subr = &s_subr[threadIdx.x >> 5][0][lane];
-            uint32_t* subp = &s_subp[threadIdx.x >> 5][0][lane];
-            if (kBig && m <= kBigSmemParts) {
-                unsigned char* base = dsm + (threadIdx.x >> 5) * kBigSmemPerWarp;
-                uint32_t* sid = reinterpret_cast<uint32_t*>(base);
-                uint32_t* srk = sid + kBigSmemParts;
-                uint16_t* snx = reinterpret_cast<uint16_t*>(srk + kBigSmemParts);
-                uint16_t* spv = snx + kBigSmemParts;
-                for (uint32_t i = lane; i < m; i += 32) { sid[i] = id[i]; srk[i] = rk[i]; }
-                __syncwarp();
-                list_rounds<uint16_t>(T, sid, srk, snx, spv, m, subr, subp, lane);
-                __syncwarp();
-                for (uint32_t i = lane; i < m; i += 32) id[i] = sid[i];
-            } else {
-                list_rounds<uint32_t>(T, id, rk, a0, a1, m, subr, subp, lane);
-            }
+            list_rounds(T, id, rk, a0, a1, m, &s_subr[threadIdx.x >> 5][0][lane], &s_subp[threadIdx.x >> 5][0][lane], lane);
             __syncwarp();
         }
         // ---- one flag per surviving part (dead slots hold kNone); order along the slice is token order
         for (uint32_t base = 0; base < m; base += 32) {
             const uint32_t i = base + lane;
             const bool alive = (i < m) && id[i] != kNone;
+            if (alive && in_smem) gid[i] = id[i];
             const uint32_t A = __ballot_sync(kFull, alive);
             if (lane == 0 && A) {
                 const uint64_t pos = lp.start + base;

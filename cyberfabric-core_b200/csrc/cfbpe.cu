@@ -383,11 +383,6 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
         return CFBPE_ENOMEM;
     }
     ctx->uc = UcTables{ctx->d_uc1, ctx->d_uc2, ctx->d_ascii, ctx->d_fsm};
-    if (cudaFuncSetAttribute(bpe_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBigSmemBytes)) != cudaSuccess) {
-        cudaGetLastError();
-        cfbpe_destroy(ctx);
-        return CFBPE_EIO;
-    }
     if (const char* e = std::getenv("CFBPE_PIPE_CHUNK_BYTES")) { const uint64_t v = std::strtoull(e, nullptr, 10); if (v >= 1024) ctx->pipe_chunk = v; }
     if (const char* e = std::getenv("CFBPE_PIPE_MIN_BYTES")) { const uint64_t v = std::strtoull(e, nullptr, 10); if (v >= 1) ctx->pipe_min = v; }
     *out = ctx;

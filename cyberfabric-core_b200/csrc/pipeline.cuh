@@ -56,10 +56,7 @@ template <typename Stream, typename Prof>
 inline void enqueue_mid(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
     if (!b.total_bytes) return;
     CFBPE_MARK(prof, K_LONG, stream, true);
-    // big pieces first: one CTA per SM, phase B in shared memory; then the many medium pieces
-    CFBPE_LAUNCH_SMEM(bpe_long_kernel<true>, long_grid / 4, kBigWarps * 32, kBigSmemBytes, stream,
-                      b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
-    CFBPE_LAUNCH(bpe_long_kernel<false>, long_grid, 256, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
+    CFBPE_LAUNCH(bpe_long_kernel, long_grid, 256, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
     CFBPE_MARK(prof, K_LONG, stream, false);
     CFBPE_MARK(prof, K_COUNT, stream, true);
     CFBPE_LAUNCH(flag_count_kernel, n_scan_tiles(b.total_bytes), 256, stream, w.tok_bits, n_flag_words(b.total_bytes), w.tile_counts);
