@@ -268,6 +268,7 @@ def main():
         for k in N.KERNEL_NAMES:
             kms[k] += pr["kernel_ms"][k] / args.steps
     n_long = pr["n_long_pieces"]
+    long_bytes, long_tokens = pr["n_long_bytes"], pr["n_long_tokens"]
     plug.ctx.profile_enable(False)
 
     # ---- end-to-end leg: pinned host buffers through the plugin / C ABI, H2D and D2H inside the timed region
@@ -297,7 +298,7 @@ def main():
     alg = {  # algorithmic bytes per launch
         "pretok_split": total * (1 + 1 / 8) + 8 * (n + 1),
         "bpe_encode": total * (1 + 1 / 8) + 4 * n_tokens + total / 8,
-        "bpe_long": 0.0,
+        "bpe_long": long_bytes + 4.0 * long_tokens + 24.0 * n_long,   # piece bytes in, ids out, work-list entries
         "flag_count": total / 8,
         "tile_scan": 0.0,
         "emit_compact": total / 8 + 8 * n_tokens + 12 * (n + 1),
@@ -326,7 +327,7 @@ def main():
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "vocab": rv.label, "vocab_stand_in": rv.stand_in, "prompts_per_gpu": n,
                    "total_bytes_per_gpu": total, "tokens_per_gpu": n_tokens, "bytes_per_token": total / max(n_tokens, 1),
-                   "long_pieces_per_gpu": int(n_long), "seed": cfg["seed"], "parallelism": "dp%d (batch-sharded, no data-path collective)" % world,
+                   "long_pieces_per_gpu": int(n_long), "long_piece_bytes_per_gpu": int(long_bytes), "seed": cfg["seed"], "parallelism": "dp%d (batch-sharded, no data-path collective)" % world,
                    "l2": "inputs (%.0f MB) and per-byte work arrays (> 1 GB) exceed the 126 MB L2; no flush needed" % (total / 1e6),
                    "scale": args.scale},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -51,6 +51,8 @@ struct DeviceStatus {
     uint32_t pad;
     uint64_t n_tokens;     // ids produced by this (sub-)batch (written by tile_scan)
     uint64_t tok_end;      // token_base + n_tokens: where the next sub-batch of a pipelined call continues
+    unsigned long long long_bytes;   // bytes inside pieces handled by K2b ...
+    unsigned long long long_tokens;  // ... and the ids they became (for the roofline of that kernel)
 };
 
 struct LongPiece { uint64_t start; uint64_t end; uint32_t vocab; uint32_t pad; };
@@ -253,6 +255,7 @@ bpe_encode_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
             uint64_t e = next_set_bit(piece_bits, ws + 32, pe);
             if (lane == 0) {   // big pieces fill the list from the back and are served first by K2b
                 const bool big = (e - ws) > kBigPiece;
+                atomicAdd(&status->long_bytes, static_cast<unsigned long long>(e - ws));
                 const uint32_t idx = atomicAdd(big ? &status->n_big : &status->n_long, 1u);
                 // a long piece holds > 32 bytes, so both counters together stay below long_cap = total/32 + 1
                 if (idx < long_cap) { LongPiece lp; lp.start = ws; lp.end = e; lp.vocab = vid; lp.pad = 0; long_list[big ? long_cap - 1 - idx : idx] = lp; }
@@ -538,7 +541,7 @@ bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
             if (lane == 0) t = piece_lookup(T, p, n);
             t = __shfl_sync(kFull, t, 0);
             if (t != kNone) {
-                if (lane == 0) { gid[0] = t; atomicOr(&tok_bits[lp.start >> 5], 1u << (lp.start & 31)); }
+                if (lane == 0) { gid[0] = t; atomicOr(&tok_bits[lp.start >> 5], 1u << (lp.start & 31)); atomicAdd(&status->long_tokens, 1ull); }
                 continue;
             }
         }
@@ -633,6 +636,7 @@ bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
             if (alive && in_smem) gid[i] = id[i];
             const uint32_t A = __ballot_sync(kFull, alive);
             if (lane == 0 && A) {
+                atomicAdd(&status->long_tokens, static_cast<unsigned long long>(__popc(A)));
                 const uint64_t pos = lp.start + base;
                 const uint32_t sh = static_cast<uint32_t>(pos & 31);
                 atomicOr(&tok_bits[pos >> 5], A << sh);

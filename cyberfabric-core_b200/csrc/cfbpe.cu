@@ -155,6 +155,8 @@ void fill_profile(cfbpe_ctx* ctx, uint64_t n_bytes) {
     p.n_tokens = ctx->h_status->n_tokens;
     p.n_long_pieces = static_cast<uint64_t>(ctx->h_status->n_long) + ctx->h_status->n_big;
     p.n_bytes = n_bytes;
+    p.n_long_bytes = ctx->h_status->long_bytes;
+    p.n_long_tokens = ctx->h_status->long_tokens;
     ctx->prof_ready = true;
 }
 

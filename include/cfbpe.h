@@ -102,6 +102,7 @@ typedef struct cfbpe_profile {
     uint32_t kernel_launches[CFBPE_NUM_KERNELS];
     float h2d_ms, d2h_ms, total_ms;
     uint64_t n_tokens, n_bytes, n_long_pieces;
+    uint64_t n_long_bytes, n_long_tokens; /* bytes in / ids out of the long-piece kernel */
 } cfbpe_profile;
 
 CFBPE_API int cfbpe_abi_version(void);
