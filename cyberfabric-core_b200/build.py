@@ -29,19 +29,20 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an experimental variant (A/B timing of kernel parameters) next to the product library"""
+    if out is None and not force and not needs_build():
         return SO
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "-shared", "--cudart", "shared",
            "-Xptxas", "-v" if verbose else "-O3", '-DCFBPE_SRC_HASH="%s"' % source_hash(),
-           os.path.join(CSRC, "cfbpe.cu"), os.path.join(CSRC, "vocab.cpp"), "-o", SO]
+           os.path.join(CSRC, "cfbpe.cu"), os.path.join(CSRC, "vocab.cpp"), "-o", out or SO] + ["-D" + d for d in defines]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
         raise RuntimeError("nvcc failed")
-    return SO
+    return out or SO
 
 
 if __name__ == "__main__":

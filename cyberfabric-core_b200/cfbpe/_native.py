@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_DIR, "libcfbpe.so")
+SO_PATH = os.environ.get("CFBPE_SO_VARIANT") or os.path.join(_DIR, "libcfbpe.so")   # CFBPE_SO_VARIANT: A/B builds (tools only)
 
 OK, ENOENT, EIO, ENOMEM, ENODEV, EINVAL, ENOSPC, EILSEQ = 0, -2, -5, -12, -19, -22, -28, -84
 FORMAT_TIKTOKEN, FORMAT_TEKKEN_JSON = 0, 1
@@ -65,7 +65,7 @@ def load():
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         want, got = mod.source_hash(), L.cfbpe_build_id().decode()
-        if want != got:
+        if want != got and not os.environ.get("CFBPE_SO_VARIANT"):
             raise RuntimeError("libcfbpe.so is stale (built from %s, sources are %s): rebuild with "
                                "`python -c 'import __graft_entry__ as g; g.build()'`" % (got, want))
     L.cfbpe_create.restype = C.c_int

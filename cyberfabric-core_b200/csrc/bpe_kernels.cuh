@@ -24,8 +24,14 @@
 namespace cfbpe {
 
 constexpr uint32_t kMaxVocabs = 8;
-constexpr uint32_t kSplitChunk = 64;     // bytes of text per K1 thread
-constexpr uint32_t kEncodeRange = 1024;  // bytes of text per K2 warp
+#ifndef CFBPE_SPLIT_CHUNK
+#define CFBPE_SPLIT_CHUNK 64
+#endif
+#ifndef CFBPE_ENCODE_RANGE
+#define CFBPE_ENCODE_RANGE 1024
+#endif
+constexpr uint32_t kSplitChunk = CFBPE_SPLIT_CHUNK;     // bytes of text per K1 thread
+constexpr uint32_t kEncodeRange = CFBPE_ENCODE_RANGE;  // bytes of text per K2 warp
 constexpr uint32_t kBigPiece = 256;      // bytes: K2b serves longer pieces first (tail latency)
 constexpr uint32_t kScanTileWords = 256;   // flag words per K3 tile (= 8 KiB of text); one word per thread
 
@@ -216,7 +222,10 @@ __device__ __forceinline__ uint64_t next_set_bit(const uint32_t* __restrict__ bi
     return p < limit ? p : limit;
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef CFBPE_K2_MINBLOCKS
+#define CFBPE_K2_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, CFBPE_K2_MINBLOCKS)
 bpe_encode_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits,
                   uint32_t* __restrict__ ids_by_pos,    // may be nullptr (count only)
                   uint32_t* __restrict__ tok_bits, LongPiece* __restrict__ long_list, uint32_t long_cap,
