@@ -377,6 +377,196 @@ bpe_encode_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
 }
 
 // ---------------------------------------------------------------------------------------
+// K2 (lane-per-piece form).  The window kernel above spends ~19 warp-instructions per byte because one
+// lane per BYTE executes the whole-piece lookup and every merge round, while only the head lane of each
+// piece does useful work in the lookup, and a round advances one merge per piece (ncu: profiles/).  Here a
+// lane owns PIECES:
+//   pass 1  each lane walks the pieces that start in its 16 bytes of the warp's 512-byte range and does
+//           CoreBPE's whole-piece lookup (short table: key = the piece's <= 12 bytes; long table: hash + verify).
+//           Hits are final.  Pieces longer than 32 bytes go to the K2b work list.
+//   pass 2  the misses of the whole warp are dealt out densely, 32 at a time, one piece per lane; each lane
+//           runs the exact sequential merge loop on its piece with the parts in shared memory
+//           (tiktoken/_educational.py:95-110: leftmost minimum rank, until no adjacent pair is a token).
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kPieceRange = 512;     // bytes of text per warp: 16 per lane
+constexpr uint32_t kPieceWarps = 4;       // warps per CTA
+
+// bytes [p, p+16) as four little-endian words, read with aligned 32-bit loads (p may be unaligned; the buffer is
+// readable up to 16 bytes past the last prompt byte)
+__device__ __forceinline__ void load16(const uint8_t* __restrict__ p, uint32_t& w0, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(addr & ~static_cast<uintptr_t>(3));
+    const uint32_t sh = static_cast<uint32_t>(addr & 3) * 8;
+    const uint32_t a = q[0], bq = q[1], c = q[2], d = q[3];
+    if (sh == 0) { w0 = a; w1 = bq; w2 = c; w3 = d; }
+    else {
+        const uint32_t e = q[4];
+        w0 = __funnelshift_r(a, bq, sh); w1 = __funnelshift_r(bq, c, sh); w2 = __funnelshift_r(c, d, sh); w3 = __funnelshift_r(d, e, sh);
+    }
+}
+
+// CoreBPE's `if piece in ranks` for a piece of 1..32 bytes at p
+__device__ __forceinline__ uint32_t whole_piece_lookup(const TablesView& T, const uint8_t* __restrict__ p, uint32_t len) {
+    if (len > T.max_token_len) return kNone;
+    uint32_t w0, w1, w2, w3;
+    load16(p, w0, w1, w2, w3);
+    uint64_t k0 = static_cast<uint64_t>(w0) | (static_cast<uint64_t>(w1) << 32);
+    uint32_t k1 = w2;
+    if (len < 8) k0 &= (1ull << (8 * len)) - 1ull;
+    if (len <= 8) k1 = 0; else if (len < 12) k1 &= (1u << (8 * (len - 8))) - 1u;
+    if (len <= kShortMaxLen) return short_lookup(T, k0, k1, len);
+    return long_lookup(T, long_hash(k0, k1, load_le32(p + len - 4), len), p, len);
+}
+
+// the exact merge loop on one piece of 2..32 bytes, parts in shared memory columns sid/srk (stride 32 words):
+//   sid[k*32] = start offset << 21 | id      srk[k*32] = rank of (part k, part k+1)
+__device__ __forceinline__ void merge_piece_in_lane(const TablesView& T, const uint8_t* __restrict__ text, uint64_t pos, uint32_t len,
+                                                    uint32_t* sid, uint32_t* srk, uint32_t* __restrict__ ids_by_pos,
+                                                    uint32_t* __restrict__ tok_bits) {
+    const uint8_t* __restrict__ p = text + pos;
+    uint32_t m = len;
+    uint32_t prev = p[0];
+    for (uint32_t k = 0; k < len; ++k) {
+        const uint32_t nxt = (k + 1 < len) ? p[k + 1] : 0u;
+        sid[k * 32] = (k << 21) | T.byte2id[prev];
+        srk[k * 32] = (k + 1 < len) ? T.bytepair[(prev << 8) | nxt] : kNone;
+        prev = nxt;
+    }
+    for (;;) {
+        uint32_t best = kNone, bi = 0;
+        for (uint32_t k = 0; k + 1 < m; ++k) { const uint32_t r = srk[k * 32]; if (r < best) { best = r; bi = k; } }   // strict <: leftmost
+        if (best == kNone) break;
+        const uint32_t st = sid[bi * 32] & ~kIdMask;
+        sid[bi * 32] = st | best;                             // rank == id of the merged token
+        for (uint32_t k = bi + 1; k + 1 < m; ++k) { sid[k * 32] = sid[(k + 1) * 32]; srk[k * 32] = srk[(k + 1) * 32]; }
+        --m;
+        srk[bi * 32] = (bi + 1 < m) ? pair_lookup(T, best, sid[(bi + 1) * 32] & kIdMask) : kNone;
+        if (bi > 0) srk[(bi - 1) * 32] = pair_lookup(T, sid[(bi - 1) * 32] & kIdMask, best);
+    }
+    uint64_t mask = 0;
+    const uint32_t sh = static_cast<uint32_t>(pos & 31);
+    for (uint32_t k = 0; k < m; ++k) {
+        const uint32_t v = sid[k * 32];
+        const uint32_t st = v >> 21;
+        ids_by_pos[pos + st] = v & kIdMask;
+        mask |= 1ull << (sh + st);
+    }
+    atomicOr(&tok_bits[pos >> 5], static_cast<uint32_t>(mask));
+    if (mask >> 32) atomicOr(&tok_bits[(pos >> 5) + 1], static_cast<uint32_t>(mask >> 32));
+}
+
+__device__ __forceinline__ uint32_t kth_set_bit(uint32_t mask, uint32_t k) {   // position of the k-th (0-based) set bit
+    for (uint32_t i = 0; i < k; ++i) mask &= mask - 1;
+    return __ffs(mask) - 1;
+}
+
+__global__ void __launch_bounds__(kPieceWarps * 32)
+bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits,
+                         uint32_t* __restrict__ ids_by_pos, uint32_t* __restrict__ tok_bits,
+                         LongPiece* __restrict__ long_list, uint32_t long_cap, DeviceStatus* status) {
+    __shared__ uint32_t s_id[kPieceWarps][32][32];   // [warp][part][lane]
+    __shared__ uint32_t s_rk[kPieceWarps][32][32];
+    const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const uint64_t warp = static_cast<uint64_t>(blockIdx.x) * kPieceWarps + wic;
+    const uint64_t r0 = warp * kPieceRange;
+    if (r0 >= b.total_bytes) return;   // whole warp exits together
+    const uint64_t r1 = (r0 + kPieceRange < b.total_bytes) ? r0 + kPieceRange : b.total_bytes;
+    const uint8_t* __restrict__ text = b.bytes;
+    const bool multi = b.vocab_ids != nullptr;
+
+    // ---- my 16 piece-start bits, and the first piece start after them
+    const uint64_t base = r0 + 16ull * lane;
+    const uint32_t my = (base < b.total_bytes) ? ((piece_bits[base >> 5] >> (16u * (lane & 1u))) & 0xFFFFu) : 0u;
+    uint32_t v = my ? (16u * lane + static_cast<uint32_t>(__ffs(my)) - 1u) : 0xFFFFu;   // offset of my first start in the range
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_down_sync(kFull, v, d); if (lane + d < 32 && o < v) v = o; }
+    uint32_t nf_rel = __shfl_down_sync(kFull, v, 1);
+    if (lane == 31) nf_rel = 0xFFFFu;
+    // a piece that runs past the range ends at the next start beyond it (or at the end of the data)
+    const bool any_open = __any_sync(kFull, my != 0 && nf_rel == 0xFFFFu);
+    uint64_t beyond = b.total_bytes;
+    if (any_open) beyond = next_set_bit(piece_bits, r1, b.total_bytes);
+    const uint64_t nf = (nf_rel == 0xFFFFu) ? beyond : r0 + nf_rel;
+
+    // ---- vocabulary of my pieces (multi-tenant batches: one prompt lookup per lane, then walk)
+    uint32_t pidx = 0, vid = 0;
+    uint64_t pe = ~0ull;
+    if (multi && my) {
+        pidx = find_prompt(b.offsets, b.n_prompts, base + static_cast<uint32_t>(__ffs(my)) - 1u);
+        pe = b.offsets[pidx + 1];
+        vid = b.vocab_ids[pidx];
+    }
+    TablesView T = vs.v[vid];
+
+    // ---- pass 1: whole-piece lookups
+    uint32_t need = 0, done = 0;
+    uint32_t bits = my;
+    while (bits) {
+        const uint32_t bpos = static_cast<uint32_t>(__ffs(bits)) - 1u;
+        bits &= bits - 1;
+        const uint64_t pos = base + bpos;
+        const uint64_t end = bits ? base + static_cast<uint32_t>(__ffs(bits)) - 1u : nf;
+        if (multi && pos >= pe) {
+            do { ++pidx; pe = b.offsets[pidx + 1]; } while (pos >= pe);
+            const uint32_t nv = b.vocab_ids[pidx];
+            if (nv != vid) { vid = nv; T = vs.v[vid]; }
+        }
+        if (end - pos > 32) {   // long piece: K2b
+            const bool big = (end - pos) > kBigPiece;
+            atomicAdd(&status->long_bytes, static_cast<unsigned long long>(end - pos));
+            const uint32_t idx = atomicAdd(big ? &status->n_big : &status->n_long, 1u);
+            if (idx < long_cap) { LongPiece lp; lp.start = pos; lp.end = end; lp.vocab = vid; lp.pad = 0; long_list[big ? long_cap - 1 - idx : idx] = lp; }
+            else atomicOr(&status->long_overflow, 1u);
+            continue;
+        }
+        const uint32_t len = static_cast<uint32_t>(end - pos);
+        const uint32_t tok = whole_piece_lookup(T, text + pos, len);
+        if (tok != kNone) { ids_by_pos[pos] = tok; done |= 1u << bpos; }
+        else need |= 1u << bpos;
+    }
+    {   // flags of the direct hits: two lanes share a 32-bit word
+        const uint32_t other = __shfl_xor_sync(kFull, done, 1);
+        if (!(lane & 1u) && base < b.total_bytes) { const uint32_t wbits = done | (other << 16); if (wbits) atomicOr(&tok_bits[base >> 5], wbits); }
+    }
+
+    // ---- pass 2: the misses, dealt out one piece per lane
+    const uint32_t cnt = __popc(need);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
+    const uint32_t prefix = incl - cnt;
+    const uint32_t total_need = __shfl_sync(kFull, incl, 31);
+    uint32_t* sid = &s_id[wic][0][lane];
+    uint32_t* srk = &s_rk[wic][0][lane];
+    for (uint32_t g0 = 0; g0 < total_need; g0 += 32) {
+        const uint32_t g = g0 + lane;
+        // owner = last lane whose exclusive prefix is <= g
+        uint32_t o = 0;
+#pragma unroll
+        for (uint32_t step = 16; step; step >>= 1) {
+            const uint32_t cand = o + step;
+            const uint32_t pc = __shfl_sync(kFull, prefix, cand & 31u);
+            if (cand < 32 && pc <= g) o = cand;
+        }
+        const uint32_t opre = __shfl_sync(kFull, prefix, o);
+        const uint32_t oneed = __shfl_sync(kFull, need, o);
+        const uint32_t omy = __shfl_sync(kFull, my, o);
+        const uint32_t onf_rel = __shfl_sync(kFull, nf_rel, o);
+        const uint32_t ovid = __shfl_sync(kFull, vid, o);
+        if (g < total_need) {
+            const uint32_t bpos = kth_set_bit(oneed, g - opre);
+            const uint64_t pos = r0 + 16ull * o + bpos;
+            const uint32_t rest = omy & ~((2u << bpos) - 1u);
+            const uint64_t end = rest ? r0 + 16ull * o + static_cast<uint32_t>(__ffs(rest)) - 1u : ((onf_rel == 0xFFFFu) ? beyond : r0 + onf_rel);
+            uint32_t pv = ovid;
+            if (multi) pv = b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)];   // the owner's vid is that of its LAST piece
+            if (pv != vid) { vid = pv; T = vs.v[vid]; }
+            merge_piece_in_lane(T, text, pos, static_cast<uint32_t>(end - pos), sid, srk, ids_by_pos, tok_bits);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // K2b: pieces longer than one window.  One WARP per piece (work list filled by K2, taken with an
 // atomic ticket).  The piece's parts live as a compact array in its own slice of per-byte scratch:
 //   id[i]  token id of part i            (ids_by_pos slice)

@@ -45,10 +45,16 @@ inline void enqueue_front(const BatchView& b, const VocabSet& vs, const UcTables
     CFBPE_MARK(prof, K_SPLIT, stream, true);
     CFBPE_LAUNCH(pretok_split_kernel, static_cast<unsigned>((n_chunks + 255) / 256), 256, stream, b, vs, uc, w.piece_bits, w.status);
     CFBPE_MARK(prof, K_SPLIT, stream, false);
-    const uint64_t n_warps = (b.total_bytes + kEncodeRange - 1) / kEncodeRange;
     CFBPE_MARK(prof, K_ENCODE, stream, true);
+#ifdef CFBPE_K2_WINDOWED
+    const uint64_t n_warps = (b.total_bytes + kEncodeRange - 1) / kEncodeRange;
     CFBPE_LAUNCH(bpe_encode_kernel, static_cast<unsigned>((n_warps + 7) / 8), 256, stream,
                  b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
+#else
+    const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
+    CFBPE_LAUNCH(bpe_encode_pieces_kernel, static_cast<unsigned>((n_warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, stream,
+                 b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
+#endif
     CFBPE_MARK(prof, K_ENCODE, stream, false);
 }
 

@@ -240,6 +240,7 @@ inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {   // redux.sync.m
 inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
 inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, !pred) == 0; }
 
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { sh &= 31; return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
