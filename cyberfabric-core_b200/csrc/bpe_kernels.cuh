@@ -634,15 +634,13 @@ __device__ __forceinline__ void list_rounds(const TablesView& T, uint32_t* __res
     auto scan_sub = [&](uint32_t ks, uint32_t skip, uint32_t& r0, uint32_t& p0) {   // min over the sub-chunk except `skip`
         r0 = kNone; p0 = 0;
         const uint32_t x0 = lo + (ks << ssh), x1 = (x0 + (1u << ssh)) < m ? (x0 + (1u << ssh)) : m;
-        uint32_t x = x0;
-        for (; x + 4 <= x1; x += 4) {   // four loads in flight
-            const uint32_t ra = rk[x], rb = rk[x + 1], rc = rk[x + 2], rd = rk[x + 3];
-            if (ra < r0 && x != skip) { r0 = ra; p0 = x; }
-            if (rb < r0 && x + 1 != skip) { r0 = rb; p0 = x + 1; }
-            if (rc < r0 && x + 2 != skip) { r0 = rc; p0 = x + 2; }
-            if (rd < r0 && x + 3 != skip) { r0 = rd; p0 = x + 3; }
+        for (uint32_t xb = x0; xb < x1; xb += 16) {   // 16 independent loads in flight (one L2 round trip), then the reduction
+            uint32_t v[16];
+#pragma unroll
+            for (uint32_t t = 0; t < 16; ++t) v[t] = (xb + t < x1 && xb + t != skip) ? rk[xb + t] : kNone;
+#pragma unroll
+            for (uint32_t t = 0; t < 16; ++t) if (v[t] < r0) { r0 = v[t]; p0 = xb + t; }
         }
-        for (; x < x1; ++x) { const uint32_t ra = rk[x]; if (ra < r0 && x != skip) { r0 = ra; p0 = x; } }
     };
     uint32_t mymin = kNone, mypos = 0;
     auto lane_min = [&]() {
@@ -708,12 +706,15 @@ __device__ __forceinline__ void list_rounds(const TablesView& T, uint32_t* __res
     }
 }
 
-__global__ void __launch_bounds__(256)
+// One warp per CTA: a warp that is deep in the serial chain of a long piece then holds one warp's worth of registers and
+// 6 KB of shared memory, not a whole CTA's, so the tail of this kernel can share the SMs with whatever runs next.
+constexpr uint32_t kLongWarps = 1;
+__global__ void __launch_bounds__(kLongWarps * 32)
 bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
-    __shared__ uint32_t s_subr[8][8][32];   // [warp][sub-chunk][lane] cached minimum rank ...
-    __shared__ uint32_t s_subp[8][8][32];   // ... and its position (phase B)
-    __shared__ uint32_t s_med[8][4][kMedSmem];   // [warp][id | rank | aux0 | aux1] of a piece of <= kMedSmem bytes
+    __shared__ uint32_t s_subr[kLongWarps][8][32];   // [warp][sub-chunk][lane] cached minimum rank ...
+    __shared__ uint32_t s_subp[kLongWarps][8][32];   // ... and its position (phase B)
+    __shared__ uint32_t s_med[kLongWarps][4][kMedSmem];   // [warp][id | rank | aux0 | aux1] of a piece of <= kMedSmem bytes
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_big = status->n_big;
     const uint32_t n_all = status->long_overflow ? 0u : status->n_long + n_big;

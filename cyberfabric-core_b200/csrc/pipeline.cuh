@@ -62,7 +62,7 @@ template <typename Stream, typename Prof>
 inline void enqueue_mid(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
     if (!b.total_bytes) return;
     CFBPE_MARK(prof, K_LONG, stream, true);
-    CFBPE_LAUNCH(bpe_long_kernel, long_grid, 256, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
+    CFBPE_LAUNCH(bpe_long_kernel, long_grid * (8 / kLongWarps), kLongWarps * 32, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
     CFBPE_MARK(prof, K_LONG, stream, false);
     CFBPE_MARK(prof, K_COUNT, stream, true);
     CFBPE_LAUNCH(flag_count_kernel, n_scan_tiles(b.total_bytes), 256, stream, w.tok_bits, n_flag_words(b.total_bytes), w.tile_counts);
