@@ -88,19 +88,61 @@ __device__ __forceinline__ void or_bits(uint32_t* __restrict__ words, uint64_t w
 // stream whatever match they are in (the first version walked whole matches per thread: 4.3 of 32
 // lanes active, profiles/ncu_lines_pretok_split_r01a.txt).
 // ---------------------------------------------------------------------------------------
+// The CTA's text (its 256 chunks, 64 bytes of left context, 256 bytes of run-on) staged in shared memory with coalesced
+// 16-byte loads.  Rows of 64 text bytes are 68 bytes apart so that the 32 lanes of a warp, which read at a 64-byte
+// stride, hit 32 different banks.  Positions outside the tile fall back to global memory.
+constexpr uint32_t kTilePre = 64, kTilePost = 256, kTileRow = 68;
+constexpr uint32_t kTileBytes = 256 * kSplitChunk;
+constexpr uint32_t kTileSmem = ((kTilePre + kTileBytes + kTilePost) / 64) * kTileRow;
+struct TileText {
+    const uint8_t* g;
+    const uint8_t* sm;
+    uint64_t lo;
+    uint32_t span;
+    __device__ __forceinline__ uint32_t operator[](uint64_t pos) const {
+        const uint64_t o = pos - lo;
+        if (o < span) { const uint32_t o32 = static_cast<uint32_t>(o); return sm[(o32 >> 6) * kTileRow + (o32 & 63u)]; }
+        return g[pos];
+    }
+};
+
 __global__ void __launch_bounds__(256)
 pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict__ piece_bits, DeviceStatus* status) {
     __shared__ uint16_t s_fsm[kNumPatterns * kPretokTableSize];
     __shared__ uint8_t s_ascii[128];
+    __shared__ __align__(16) uint8_t s_tile[kTileSmem];
     for (uint32_t i = threadIdx.x; i < kNumPatterns * kPretokTableSize; i += blockDim.x) s_fsm[i] = uc.fsm[i];
     if (threadIdx.x < 128) s_ascii[threadIdx.x] = uc.ascii_x[threadIdx.x];
+    TileText txt;
+    {
+        const uint64_t tile0 = static_cast<uint64_t>(blockIdx.x) * kTileBytes;
+        const uint64_t lo = tile0 >= kTilePre ? tile0 - kTilePre : 0;
+        uint64_t hi = tile0 + kTileBytes + kTilePost;
+        if (hi > b.total_bytes) hi = b.total_bytes;
+        const uint32_t span = hi > lo ? static_cast<uint32_t>(hi - lo) : 0u;
+        const uint8_t* src = b.bytes + lo;
+        if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+            for (uint32_t o = threadIdx.x * 16u; o < span; o += blockDim.x * 16u) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tile[(o >> 6) * kTileRow + (o & 63u)]);
+                if (o + 16u <= span) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(src + o);
+                    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+                } else {
+                    for (uint32_t t = o; t < span; ++t) s_tile[(t >> 6) * kTileRow + (t & 63u)] = src[t];
+                }
+            }
+        } else {
+            for (uint32_t o = threadIdx.x; o < span; o += blockDim.x) s_tile[(o >> 6) * kTileRow + (o & 63u)] = src[o];
+        }
+        txt.g = b.bytes; txt.sm = s_tile; txt.lo = lo; txt.span = span;
+    }
     __syncthreads();
 
     const uint64_t chunk = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const uint64_t cs = chunk * kSplitChunk;
     if (cs >= b.total_bytes) return;
     const uint64_t ce = (cs + kSplitChunk < b.total_bytes) ? cs + kSplitChunk : b.total_bytes;
-    const uint8_t* __restrict__ s = b.bytes;
+    const TileText& s = txt;
 
     uint32_t pidx = find_prompt(b.offsets, b.n_prompts, cs);
     uint64_t ps = b.offsets[pidx], pe = b.offsets[pidx + 1];

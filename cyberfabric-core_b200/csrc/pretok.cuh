@@ -26,6 +26,8 @@ struct UcTables {
     const uint16_t* fsm;     // [kNumPatterns * kPretokTableSize] transition tables (pretok_fsm.h)
 };
 
+// Text accessor: any type with operator[](uint64_t) -> byte.  A raw `const uint8_t*` works; K1 passes a view that serves
+// the CTA's tile from shared memory (TileText in bpe_kernels.cuh).
 struct Ch {
     uint32_t cp;
     uint32_t len;  // 0 = end of prompt
@@ -51,7 +53,8 @@ CFBPE_HD uint32_t uc_class(const UcTables& uc, uint32_t cp) {
 // Strict UTF-8 decode of the character starting at pos (< pe handled by caller: returns len 0 at pe).
 // A malformed sequence is reported through *bad and consumed as ONE byte of class OTHER so that
 // every scan still terminates; the batch is rejected with CFBPE_EILSEQ afterwards.
-CFBPE_HD Ch get_char(const uint8_t* __restrict__ s, uint64_t pos, uint64_t pe, const UcTables& uc, int* bad) {
+template <typename Txt>
+CFBPE_HD Ch get_char(const Txt& s, uint64_t pos, uint64_t pe, const UcTables& uc, int* bad) {
     Ch c;
     if (pos >= pe) { c.cp = 0; c.len = 0; c.cls = C_OTHER; return c; }
     const uint32_t b0 = s[pos];
@@ -77,7 +80,8 @@ CFBPE_HD Ch get_char(const uint8_t* __restrict__ s, uint64_t pos, uint64_t pe, c
 }
 
 // The character that ENDS at pos (pos > ps).  Steps back over at most three continuation bytes.
-CFBPE_HD Ch get_prev_char(const uint8_t* __restrict__ s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc) {
+template <typename Txt>
+CFBPE_HD Ch get_prev_char(const Txt& s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc) {
     uint64_t q = pos - 1;
     uint32_t back = 0;
     while (q > ps && back < 3 && (s[q] & 0xC0) == 0x80) { --q; ++back; }
@@ -118,7 +122,8 @@ CFBPE_HD PatTraits pat_traits(uint32_t pat) {
 }
 
 // bytes of a contraction ('s 't 'm 'd 'll 've 're, any case, U+017F counts as s) at pos, else 0
-CFBPE_HD uint32_t contraction_bytes(const uint8_t* __restrict__ s, uint64_t pos, uint64_t pe) {
+template <typename Txt>
+CFBPE_HD uint32_t contraction_bytes(const Txt& s, uint64_t pos, uint64_t pe) {
     if (pos + 1 >= pe || s[pos] != '\'') return 0;
     const uint32_t a = s[pos + 1] | 0x20;  // ASCII lower-case fold (only valid for letters; checked below)
     const bool a_letter = (a - 'a') < 26u;

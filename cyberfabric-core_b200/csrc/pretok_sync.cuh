@@ -40,7 +40,8 @@ CFBPE_HD uint32_t sync_rule(uint32_t x, uint32_t prevx, uint32_t nlet, bool case
 }
 
 // evaluate the rule at byte position pos (ps < pos < pe) by decoding up to three characters to the left
-CFBPE_HD uint32_t sync_state(const uint8_t* __restrict__ s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc, bool cased,
+template <typename Txt>
+CFBPE_HD uint32_t sync_state(const Txt& s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc, bool cased,
                              uint32_t* prevx_out = nullptr, uint32_t* nlet_out = nullptr) {
     const uint32_t b = s[pos];
     if ((b & 0xC0) == 0x80) return kNoSync;  // inside a character

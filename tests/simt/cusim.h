@@ -189,6 +189,8 @@ template <typename T> inline T from_u64(uint64_t u) { T v; std::memcpy(&v, &u, s
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+struct uint4 { unsigned x, y, z, w; };
 #define threadIdx (cusim::B().cur->tid)
 #define blockIdx (cusim::B().bid)
 #define blockDim (cusim::B().bdim)
