@@ -502,6 +502,9 @@ __device__ __forceinline__ uint32_t kth_set_bit(uint32_t mask, uint32_t k) {   /
     return __ffs(mask) - 1;
 }
 
+// kMode 0: everything.  1: only find the pieces longer than 32 bytes and queue them (so that the long-piece kernel can
+// start on another stream while mode 2 runs).  2: everything except queueing.
+template <int kMode>
 __global__ void __launch_bounds__(kPieceWarps * 32)
 bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits,
                          uint32_t* __restrict__ ids_by_pos, uint32_t* __restrict__ tok_bits,
@@ -554,6 +557,7 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
             if (nv != vid) { vid = nv; T = vs.v[vid]; }
         }
         if (end - pos > 32) {   // long piece: K2b
+            if (kMode == 2) continue;
             const bool big = (end - pos) > kBigPiece;
             atomicAdd(&status->long_bytes, static_cast<unsigned long long>(end - pos));
             const uint32_t idx = atomicAdd(big ? &status->n_big : &status->n_long, 1u);
@@ -561,11 +565,13 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
             else atomicOr(&status->long_overflow, 1u);
             continue;
         }
+        if (kMode == 1) continue;
         const uint32_t len = static_cast<uint32_t>(end - pos);
         const uint32_t tok = whole_piece_lookup(T, text + pos, len);
         if (tok != kNone) { ids_by_pos[pos] = tok; done |= 1u << bpos; }
         else need |= 1u << bpos;
     }
+    if (kMode == 1) return;
     {   // flags of the direct hits: two lanes share a 32-bit word
         const uint32_t other = __shfl_xor_sync(kFull, done, 1);
         if (!(lane & 1u) && base < b.total_bytes) { const uint32_t wbits = done | (other << 16); if (wbits) atomicOr(&tok_bits[base >> 5], wbits); }

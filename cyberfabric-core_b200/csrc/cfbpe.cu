@@ -19,6 +19,9 @@ struct ProfEvents;
 #define CFBPE_ZERO(ptr, bytes, stream) cudaMemsetAsync((ptr), 0, (bytes), (stream))
 #define CFBPE_MARK(prof, idx, stream, begin) prof_mark((prof), (idx), (stream), (begin))
 static inline void prof_mark(ProfEvents* p, int idx, cudaStream_t s, bool begin);
+// make `aux` wait for what is queued on `main` so far / make `main` wait for `aux`; no-ops when both are the same stream
+#define CFBPE_FORK(main, aux, ev) do { if ((main) != (aux)) { cudaEventRecord((ev), (main)); cudaStreamWaitEvent((aux), (ev), 0); } } while (0)
+#define CFBPE_JOIN(main, aux, ev) do { if ((main) != (aux)) { cudaEventRecord((ev), (aux)); cudaStreamWaitEvent((main), (ev), 0); } } while (0)
 
 #include "pipeline.cuh"
 #include "unicode_tables.h"
@@ -58,6 +61,9 @@ struct cfbpe_ctx {
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t h2d_stream = nullptr;   // pipelined host calls: uploads run ahead of the kernels ...
     cudaStream_t d2h_stream = nullptr;   // ... and downloads trail them
+    cudaStream_t aux_stream = nullptr;   // the long-piece kernel runs here, next to the short-piece kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_scan[kMaxPipeChunks] = {};
     cudaStream_t side[kSideStreams] = {};  // long-piece tails + emit of sub-batch k overlap the front of k+1
     cudaEvent_t ev_front[kMaxPipeChunks] = {};
     cudaEvent_t ev_h2d[kMaxPipeChunks] = {};
@@ -214,10 +220,13 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         w.status = ctx->d_status_arr + k;
         BatchView b{ctx->d_bytes + o0, ctx->d_offsets + p0 + k, vocab_ids ? ctx->d_vocab_ids + p0 : nullptr, nk, len};
         cudaStream_t ss = ctx->side[k % kSideStreams];
-        enqueue_front(b, ctx->vs, ctx->uc, w, cs, static_cast<ProfEvents*>(nullptr));
+        enqueue_split(b, ctx->vs, ctx->uc, w, cs, static_cast<ProfEvents*>(nullptr));
+        CK(cudaEventRecord(ctx->ev_scan[k], cs));
+        CK(cudaStreamWaitEvent(ss, ctx->ev_scan[k], 0));
+        enqueue_long(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ss, static_cast<ProfEvents*>(nullptr));   // tail overlaps what follows on cs
+        enqueue_short(b, ctx->vs, w, cs, static_cast<ProfEvents*>(nullptr));
         CK(cudaEventRecord(ctx->ev_front[k], cs));
         CK(cudaStreamWaitEvent(ss, ctx->ev_front[k], 0));
-        enqueue_mid(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ss, static_cast<ProfEvents*>(nullptr));
         if (k) CK(cudaStreamWaitEvent(ss, ctx->ev_done[k - 1], 0));     // token ranks chain through DeviceStatus::tok_end
         enqueue_back(b, w, want_ids ? ctx->d_out_ids : nullptr, ctx->max_bytes, ctx->d_out_offsets + p0 + k, ctx->d_out_counts + p0,
                      ss, static_cast<ProfEvents*>(nullptr), k ? &ctx->d_status_arr[k - 1].tok_end : nullptr);
@@ -276,7 +285,7 @@ int run_host(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const uint64_t* o
 
     BatchView b{ctx->d_bytes, ctx->d_offsets, vocab_ids ? ctx->d_vocab_ids : nullptr, n, total};
     enqueue_encode(b, ctx->vs, ctx->uc, ctx->ws, want_ids ? ctx->d_out_ids : nullptr, ctx->max_bytes, ctx->d_out_offsets,
-                   ctx->d_out_counts, static_cast<uint32_t>(ctx->sm_count * 4), s, prof);
+                   ctx->d_out_counts, static_cast<uint32_t>(ctx->sm_count * 4), s, ctx->aux_stream, ctx->ev_fork, ctx->ev_join, prof);
     CK(cudaGetLastError());
     if (prof) cudaEventRecord(prof->d2h[0], s);
     CK(cudaMemcpyAsync(ctx->h_status, ctx->ws.status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
@@ -355,6 +364,9 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status_arr), sizeof(DeviceStatus) * kMaxPipeChunks) == cudaSuccess;
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_offs_stage), sizeof(uint64_t) * (mp + 1 + kMaxPipeChunks)) == cudaSuccess;
     for (int k = 0; ok && k < kSideStreams; ++k) ok = cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; ok && k < kMaxPipeChunks; ++k) ok = cudaEventCreateWithFlags(&ctx->ev_scan[k], cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; ok && k < kMaxPipeChunks; ++k)
         ok = cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_front[k], cudaEventDisableTiming) == cudaSuccess &&
@@ -407,6 +419,10 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     cudaFree(ctx->d_status_arr);
     for (int k = 0; k < kMaxPipeChunks; ++k) { if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]); if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]); if (ctx->ev_front[k]) cudaEventDestroy(ctx->ev_front[k]); }
     for (int k = 0; k < kSideStreams; ++k) if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
+    for (int k = 0; k < kMaxPipeChunks; ++k) if (ctx->ev_scan[k]) cudaEventDestroy(ctx->ev_scan[k]);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     for (auto& v : ctx->vocabs) if (v.d_blob) cudaFree(v.d_blob);
@@ -509,7 +525,7 @@ int cfbpe_encode_batch_device(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t*
     if (prof) { std::memset(prof->launched, 0, sizeof prof->launched); cudaEventRecord(prof->total[0], s); cudaEventRecord(prof->h2d[0], s); cudaEventRecord(prof->h2d[1], s); }
     BatchView b{d_bytes, d_offsets, d_vocab_ids, n_prompts, total_bytes};
     enqueue_encode(b, ctx->vs, ctx->uc, ctx->ws, d_out_ids, out_cap, d_out_offsets, d_out_counts,
-                   static_cast<uint32_t>(ctx->sm_count * 4), s, prof);
+                   static_cast<uint32_t>(ctx->sm_count * 4), s, ctx->aux_stream, ctx->ev_fork, ctx->ev_join, prof);
     CK(cudaGetLastError());
     if (prof) { cudaEventRecord(prof->d2h[0], s); cudaEventRecord(prof->d2h[1], s); cudaEventRecord(prof->total[1], s); }
     if (n_tokens || prof) {

@@ -6,6 +6,7 @@
 //   CFBPE_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...)   launch with dynamic shared memory
 //   CFBPE_ZERO(ptr, bytes, stream)                   asynchronous zero fill
 //   CFBPE_MARK(prof, idx, stream, begin)             optional per-kernel event record
+//   CFBPE_FORK(main, aux, ev) / CFBPE_JOIN(main, aux, ev)   make aux wait for main / main wait for aux
 #pragma once
 #include "bpe_kernels.cuh"
 
@@ -30,12 +31,14 @@ inline uint32_t n_scan_tiles(uint64_t total_bytes) {
     return static_cast<uint32_t>((n_flag_words(total_bytes) + kScanTileWords - 1) / kScanTileWords);
 }
 
-// The path in three stages so that a pipelined host call can put them on different streams:
-//   front  zero the flags, K1 split, K2 encode (throughput-bound, one after the other on the main stream)
-//   mid    K2b long pieces + flag_count  (latency-bound tail: may overlap the next sub-batch's front)
-//   back   tile_scan (chained on the previous sub-batch's token total), emit, prompt offsets
+// The path in stages, so that a caller with more than one stream can overlap the latency-bound long-piece kernel with
+// the throughput-bound short-piece kernel (and, in a pipelined host call, with the next sub-batch):
+//   split   zero the flags, K1 split, find the long pieces (K2 in scan mode)
+//   long    K2b: pieces longer than 32 bytes                       } independent of each other:
+//   short   K2: whole-piece lookups and in-lane merges (<= 32 B)   } may run on two streams
+//   back    flag_count, tile_scan (chained on the previous sub-batch's token total), emit, prompt offsets
 template <typename Stream, typename Prof>
-inline void enqueue_front(const BatchView& b, const VocabSet& vs, const UcTables& uc, const Workspace& w, Stream stream, Prof* prof) {
+inline void enqueue_split(const BatchView& b, const VocabSet& vs, const UcTables& uc, const Workspace& w, Stream stream, Prof* prof) {
     const uint64_t nw = n_flag_words(b.total_bytes);
     CFBPE_ZERO(w.status, sizeof(DeviceStatus), stream);
     if (!b.total_bytes) return;
@@ -44,7 +47,17 @@ inline void enqueue_front(const BatchView& b, const VocabSet& vs, const UcTables
     const uint64_t n_chunks = (b.total_bytes + kSplitChunk - 1) / kSplitChunk;
     CFBPE_MARK(prof, K_SPLIT, stream, true);
     CFBPE_LAUNCH(pretok_split_kernel, static_cast<unsigned>((n_chunks + 255) / 256), 256, stream, b, vs, uc, w.piece_bits, w.status);
+#ifndef CFBPE_K2_WINDOWED
+    const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
+    CFBPE_LAUNCH(bpe_encode_pieces_kernel<1>, static_cast<unsigned>((n_warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, stream,
+                 b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
+#endif
     CFBPE_MARK(prof, K_SPLIT, stream, false);
+}
+
+template <typename Stream, typename Prof>
+inline void enqueue_short(const BatchView& b, const VocabSet& vs, const Workspace& w, Stream stream, Prof* prof) {
+    if (!b.total_bytes) return;
     CFBPE_MARK(prof, K_ENCODE, stream, true);
 #ifdef CFBPE_K2_WINDOWED
     const uint64_t n_warps = (b.total_bytes + kEncodeRange - 1) / kEncodeRange;
@@ -52,21 +65,18 @@ inline void enqueue_front(const BatchView& b, const VocabSet& vs, const UcTables
                  b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
 #else
     const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
-    CFBPE_LAUNCH(bpe_encode_pieces_kernel, static_cast<unsigned>((n_warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, stream,
+    CFBPE_LAUNCH(bpe_encode_pieces_kernel<2>, static_cast<unsigned>((n_warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, stream,
                  b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
 #endif
     CFBPE_MARK(prof, K_ENCODE, stream, false);
 }
 
 template <typename Stream, typename Prof>
-inline void enqueue_mid(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
+inline void enqueue_long(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
     if (!b.total_bytes) return;
     CFBPE_MARK(prof, K_LONG, stream, true);
     CFBPE_LAUNCH(bpe_long_kernel, long_grid * (8 / kLongWarps), kLongWarps * 32, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
     CFBPE_MARK(prof, K_LONG, stream, false);
-    CFBPE_MARK(prof, K_COUNT, stream, true);
-    CFBPE_LAUNCH(flag_count_kernel, n_scan_tiles(b.total_bytes), 256, stream, w.tok_bits, n_flag_words(b.total_bytes), w.tile_counts);
-    CFBPE_MARK(prof, K_COUNT, stream, false);
 }
 
 template <typename Stream, typename Prof>
@@ -75,6 +85,9 @@ inline void enqueue_back(const BatchView& b, const Workspace& w, uint32_t* out_i
     const uint64_t nw = n_flag_words(b.total_bytes);
     const uint32_t nt = n_scan_tiles(b.total_bytes);
     if (b.total_bytes) {
+        CFBPE_MARK(prof, K_COUNT, stream, true);
+        CFBPE_LAUNCH(flag_count_kernel, nt, 256, stream, w.tok_bits, nw, w.tile_counts);
+        CFBPE_MARK(prof, K_COUNT, stream, false);
         CFBPE_MARK(prof, K_SCAN, stream, true);
         CFBPE_LAUNCH(tile_scan_kernel, 1u, 1024, stream, w.tile_counts, nt, w.tile_base, w.status, token_base);
         CFBPE_MARK(prof, K_SCAN, stream, false);
@@ -91,13 +104,23 @@ inline void enqueue_back(const BatchView& b, const Workspace& w, uint32_t* out_i
     CFBPE_MARK(prof, K_EMIT, stream, false);
 }
 
-// The whole path on one stream.  out_ids may be nullptr (count only).  Everything is asynchronous on `stream`.
-template <typename Stream, typename Prof>
+// The whole path.  `aux` is a second stream for the long-piece kernel (pass the same stream to run everything in order);
+// CFBPE_FORK / CFBPE_JOIN order the two.  out_ids may be nullptr (count only).  Everything is asynchronous.
+template <typename Stream, typename Prof, typename Ev>
 inline void enqueue_encode(const BatchView& b, const VocabSet& vs, const UcTables& uc, const Workspace& w,
                            uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_counts,
-                           uint32_t long_grid, Stream stream, Prof* prof, const uint64_t* token_base = nullptr) {
-    enqueue_front(b, vs, uc, w, stream, prof);
-    enqueue_mid(b, vs, w, long_grid, stream, prof);
+                           uint32_t long_grid, Stream stream, Stream aux, Ev ev_fork, Ev ev_join, Prof* prof,
+                           const uint64_t* token_base = nullptr) {
+    enqueue_split(b, vs, uc, w, stream, prof);
+    CFBPE_FORK(stream, aux, ev_fork);
+#ifdef CFBPE_K2_WINDOWED
+    enqueue_short(b, vs, w, stream, prof);      // the windowed kernel queues the long pieces itself
+    enqueue_long(b, vs, w, long_grid, stream, prof);
+#else
+    enqueue_long(b, vs, w, long_grid, aux, prof);
+    enqueue_short(b, vs, w, stream, prof);
+#endif
+    CFBPE_JOIN(stream, aux, ev_join);
     enqueue_back(b, w, out_ids, out_cap, out_offsets, out_counts, stream, prof, token_base);
 }
 
