@@ -754,6 +754,48 @@ __device__ __forceinline__ void list_rounds(const TablesView& T, uint32_t* __res
     }
 }
 
+// phase B for pieces that live in shared memory (m <= kMedSmem): every lane owns at most 8 parts and simply re-reads
+// them each round -- cheaper than maintaining cached minima when a chunk is this small.
+__device__ __forceinline__ void list_rounds_small(const TablesView& T, uint32_t* id, uint32_t* rk, uint32_t* link, uint32_t* nid,
+                                                  uint32_t m, uint32_t lane) {
+    constexpr uint32_t kNoPrev = 0xFFFFu;
+    uint32_t csh = 0;
+    while ((32u << csh) < m) ++csh;               // chunk = 2^csh <= 8 parts per lane
+    for (uint32_t i = lane; i < m; i += 32) {
+        link[i] = ((i + 1) << 16) | (i ? i - 1 : kNoPrev);
+        nid[i] = (i + 1 < m) ? id[i + 1] : kNone;
+    }
+    __syncwarp();
+    const uint32_t lo = lane << csh;
+    const uint32_t hi = (lo + (1u << csh)) < m ? (lo + (1u << csh)) : m;
+    for (;;) {
+        uint32_t mymin = kNone, mypos = 0;
+        for (uint32_t x = lo; x < hi; ++x) { const uint32_t r = rk[x]; if (r < mymin) { mymin = r; mypos = x; } }
+        const uint32_t best = __reduce_min_sync(kFull, mymin != kNone ? ((mymin << 5) | lane) : kNone);
+        if (best == kNone) break;
+        const uint32_t r = best >> 5;
+        const uint32_t i = __shfl_sync(kFull, mypos, best & 31u);
+        const uint32_t li = link[i];
+        const uint32_t j = li >> 16, q = li & 0xFFFFu;
+        uint32_t val = kNone, k = 0;
+        if (lane == 0) {
+            k = link[j] >> 16;
+            if (k < m) val = pair_lookup(T, r, nid[j]);
+        }
+        if (lane == 1 && q != kNoPrev) val = pair_lookup(T, id[q], r);
+        const uint32_t newR = __shfl_sync(kFull, val, 0);
+        const uint32_t newL = __shfl_sync(kFull, val, 1);
+        if (lane == 0) {
+            id[i] = r; id[j] = kNone; rk[j] = kNone; rk[i] = newR;
+            link[i] = (k << 16) | q;
+            nid[i] = nid[j];
+            if (k < m) link[k] = (link[k] & 0xFFFF0000u) | i;
+            if (q != kNoPrev) { rk[q] = newL; nid[q] = r; }
+        }
+        __syncwarp();
+    }
+}
+
 // One warp per CTA: a warp that is deep in the serial chain of a long piece then holds one warp's worth of registers and
 // 6 KB of shared memory, not a whole CTA's, so the tail of this kernel can share the SMs with whatever runs next.
 constexpr uint32_t kLongWarps = 1;
@@ -874,7 +916,8 @@ bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
 
         // ---- phase B: linked list, one merge per round
         if (list_mode) {
-            list_rounds(T, id, rk, a0, a1, m, &s_subr[threadIdx.x >> 5][0][lane], &s_subp[threadIdx.x >> 5][0][lane], lane);
+            if (in_smem) list_rounds_small(T, id, rk, a0, a1, m, lane);
+            else list_rounds(T, id, rk, a0, a1, m, &s_subr[threadIdx.x >> 5][0][lane], &s_subp[threadIdx.x >> 5][0][lane], lane);
             __syncwarp();
         }
         // ---- one flag per surviving part (dead slots hold kNone); order along the slice is token order
