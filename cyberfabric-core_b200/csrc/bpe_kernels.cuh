@@ -467,12 +467,26 @@ __device__ __forceinline__ void merge_piece_in_lane(const TablesView& T, const u
                                                     uint32_t* __restrict__ tok_bits) {
     const uint8_t* __restrict__ p = text + pos;
     uint32_t m = len;
-    uint32_t prev = p[0];
-    for (uint32_t k = 0; k < len; ++k) {
-        const uint32_t nxt = (k + 1 < len) ? p[k + 1] : 0u;
-        sid[k * 32] = (k << 21) | T.byte2id[prev];
-        srk[k * 32] = (k + 1 < len) ? T.bytepair[(prev << 8) | nxt] : kNone;
-        prev = nxt;
+    // the piece's bytes (<= 32) in eight registers; parts = bytes, ranks from the raw byte-pair table, four loads in flight
+    uint32_t w[8];
+    load16(p, w[0], w[1], w[2], w[3]);
+    if (len > 16) load16(p + 16, w[4], w[5], w[6], w[7]); else { w[4] = w[5] = w[6] = w[7] = 0; }
+    auto byte_at = [&](uint32_t k) -> uint32_t {   // k < 32; selects without dynamic register indexing
+        const uint32_t lo4 = (k & 4u) ? ((k & 8u) ? ((k & 16u) ? w[7] : w[3]) : ((k & 16u) ? w[5] : w[1]))
+                                       : ((k & 8u) ? ((k & 16u) ? w[6] : w[2]) : ((k & 16u) ? w[4] : w[0]));
+        return (lo4 >> (8u * (k & 3u))) & 0xFFu;
+    };
+    for (uint32_t k0 = 0; k0 < len; k0 += 4) {
+        uint32_t bv[5], idv[4], rkv[4];
+#pragma unroll
+        for (uint32_t t = 0; t < 5; ++t) bv[t] = (k0 + t < len) ? byte_at(k0 + t) : 0u;
+#pragma unroll
+        for (uint32_t t = 0; t < 4; ++t) {
+            idv[t] = (k0 + t < len) ? T.byte2id[bv[t]] : 0u;
+            rkv[t] = (k0 + t + 1 < len) ? T.bytepair[(bv[t] << 8) | bv[t + 1]] : kNone;
+        }
+#pragma unroll
+        for (uint32_t t = 0; t < 4; ++t) if (k0 + t < len) { sid[(k0 + t) * 32] = ((k0 + t) << 21) | idv[t]; srk[(k0 + t) * 32] = rkv[t]; }
     }
     for (;;) {
         uint32_t best = kNone, bi = 0;
@@ -482,8 +496,11 @@ __device__ __forceinline__ void merge_piece_in_lane(const TablesView& T, const u
         sid[bi * 32] = st | best;                             // rank == id of the merged token
         for (uint32_t k = bi + 1; k + 1 < m; ++k) { sid[k * 32] = sid[(k + 1) * 32]; srk[k * 32] = srk[(k + 1) * 32]; }
         --m;
-        srk[bi * 32] = (bi + 1 < m) ? pair_lookup(T, best, sid[(bi + 1) * 32] & kIdMask) : kNone;
-        if (bi > 0) srk[(bi - 1) * 32] = pair_lookup(T, sid[(bi - 1) * 32] & kIdMask, best);
+        uint32_t nr, nl;
+        const bool wr = bi + 1 < m, wl = bi > 0;
+        pair_lookup2(T, best, wr ? (sid[(bi + 1) * 32] & kIdMask) : 0u, wr, wl ? (sid[(bi - 1) * 32] & kIdMask) : 0u, best, wl, nr, nl);
+        srk[bi * 32] = nr;
+        if (wl) srk[(bi - 1) * 32] = nl;
     }
     uint64_t mask = 0;
     const uint32_t sh = static_cast<uint32_t>(pos & 31);

@@ -118,6 +118,25 @@ CFBPE_HD uint32_t pair_lookup(const TablesView& t, uint32_t left, uint32_t right
         h = (h + 1) & t.pair_mask;
     }
 }
+// two independent probes with their first loads in flight together (a merge refreshes both neighbouring pairs)
+CFBPE_HD void pair_lookup2(const TablesView& t, uint32_t l0, uint32_t r0, bool want0, uint32_t l1, uint32_t r1, bool want1,
+                           uint32_t& out0, uint32_t& out1) {
+    const uint64_t key0 = (static_cast<uint64_t>(l0) << kIdBits) | r0, key1 = (static_cast<uint64_t>(l1) << kIdBits) | r1;
+    uint32_t h0 = pair_hash(l0, r0) & t.pair_mask, h1 = pair_hash(l1, r1) & t.pair_mask;
+    uint64_t s0 = want0 ? t.pair[h0] : kPairEmpty;
+    uint64_t s1 = want1 ? t.pair[h1] : kPairEmpty;
+    out0 = kNone; out1 = kNone;
+    for (;;) {
+        if ((s0 >> kIdBits) == key0) { out0 = static_cast<uint32_t>(s0) & kIdMask; break; }
+        if (s0 == kPairEmpty) break;
+        h0 = (h0 + 1) & t.pair_mask; s0 = t.pair[h0];
+    }
+    for (;;) {
+        if ((s1 >> kIdBits) == key1) { out1 = static_cast<uint32_t>(s1) & kIdMask; break; }
+        if (s1 == kPairEmpty) break;
+        h1 = (h1 + 1) & t.pair_mask; s1 = t.pair[h1];
+    }
+}
 // id of a token of len <= 12 whose bytes are packed little-endian in (k0,k1), or kNone
 CFBPE_HD uint32_t short_lookup(const TablesView& t, uint64_t k0, uint32_t k1, uint32_t len) {
     uint32_t h = short_hash(k0, k1, len) & t.short_mask;
