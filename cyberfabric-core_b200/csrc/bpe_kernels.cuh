@@ -88,61 +88,21 @@ __device__ __forceinline__ void or_bits(uint32_t* __restrict__ words, uint64_t w
 // stream whatever match they are in (the first version walked whole matches per thread: 4.3 of 32
 // lanes active, profiles/ncu_lines_pretok_split_r01a.txt).
 // ---------------------------------------------------------------------------------------
-// The CTA's text (its 256 chunks, 64 bytes of left context, 256 bytes of run-on) staged in shared memory with coalesced
-// 16-byte loads.  Rows of 64 text bytes are 68 bytes apart so that the 32 lanes of a warp, which read at a 64-byte
-// stride, hit 32 different banks.  Positions outside the tile fall back to global memory.
-constexpr uint32_t kTilePre = 64, kTilePost = 256, kTileRow = 68;
-constexpr uint32_t kTileBytes = 256 * kSplitChunk;
-constexpr uint32_t kTileSmem = ((kTilePre + kTileBytes + kTilePost) / 64) * kTileRow;
-struct TileText {
-    const uint8_t* g;
-    const uint8_t* sm;
-    uint64_t lo;
-    uint32_t span;
-    __device__ __forceinline__ uint32_t operator[](uint64_t pos) const {
-        const uint64_t o = pos - lo;
-        if (o < span) { const uint32_t o32 = static_cast<uint32_t>(o); return sm[(o32 >> 6) * kTileRow + (o32 & 63u)]; }
-        return g[pos];
-    }
-};
-
 __global__ void __launch_bounds__(256)
 pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict__ piece_bits, DeviceStatus* status) {
     __shared__ uint16_t s_fsm[kNumPatterns * kPretokTableSize];
     __shared__ uint8_t s_ascii[128];
-    __shared__ __align__(16) uint8_t s_tile[kTileSmem];
     for (uint32_t i = threadIdx.x; i < kNumPatterns * kPretokTableSize; i += blockDim.x) s_fsm[i] = uc.fsm[i];
     if (threadIdx.x < 128) s_ascii[threadIdx.x] = uc.ascii_x[threadIdx.x];
-    TileText txt;
-    {
-        const uint64_t tile0 = static_cast<uint64_t>(blockIdx.x) * kTileBytes;
-        const uint64_t lo = tile0 >= kTilePre ? tile0 - kTilePre : 0;
-        uint64_t hi = tile0 + kTileBytes + kTilePost;
-        if (hi > b.total_bytes) hi = b.total_bytes;
-        const uint32_t span = hi > lo ? static_cast<uint32_t>(hi - lo) : 0u;
-        const uint8_t* src = b.bytes + lo;
-        if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
-            for (uint32_t o = threadIdx.x * 16u; o < span; o += blockDim.x * 16u) {
-                uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tile[(o >> 6) * kTileRow + (o & 63u)]);
-                if (o + 16u <= span) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(src + o);
-                    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-                } else {
-                    for (uint32_t t = o; t < span; ++t) s_tile[(t >> 6) * kTileRow + (t & 63u)] = src[t];
-                }
-            }
-        } else {
-            for (uint32_t o = threadIdx.x; o < span; o += blockDim.x) s_tile[(o >> 6) * kTileRow + (o & 63u)] = src[o];
-        }
-        txt.g = b.bytes; txt.sm = s_tile; txt.lo = lo; txt.span = span;
-    }
     __syncthreads();
 
     const uint64_t chunk = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const uint64_t cs = chunk * kSplitChunk;
     if (cs >= b.total_bytes) return;
     const uint64_t ce = (cs + kSplitChunk < b.total_bytes) ? cs + kSplitChunk : b.total_bytes;
-    const TileText& s = txt;
+    // (a shared-memory text tile with coalesced 16-byte loads was measured slower here: occupancy fell from 67 % to
+    //  29 % and the accessor cost more than the L1 hits it replaced -- profiles/ncu_summary_r01k.json)
+    const uint8_t* __restrict__ s = b.bytes;
 
     uint32_t pidx = find_prompt(b.offsets, b.n_prompts, cs);
     uint64_t ps = b.offsets[pidx], pe = b.offsets[pidx + 1];
@@ -150,15 +110,15 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
     // ---- find the first sync point in [cs, ce)
     uint64_t pos = cs;
     uint32_t state = kNoSync;
-    uint32_t prevx = X_EOT, nlet = 0;   // class of the previous character, consecutive letters before pos (<= 3)
+    uint32_t prevx = X_EOT, nlet = 0, npun = 0;   // class of the previous character; consecutive letters (<= 3) / punctuation (<= 2) before pos
     uint32_t pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
     while (pos < ce) {
         if (pos == pe) {  // step into the next non-empty prompt
             do { ++pidx; ps = pe; pe = b.offsets[pidx + 1]; } while (pe == ps);
             pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
         }
-        prevx = X_EOT; nlet = 0;
-        state = (pos == ps) ? static_cast<uint32_t>(S_START) : sync_state(s, pos, ps, pe, uc, (pat & 1u) != 0, &prevx, &nlet);
+        prevx = X_EOT; nlet = 0; npun = 0;
+        state = (pos == ps) ? static_cast<uint32_t>(S_START) : sync_state(s, pos, ps, pe, uc, (pat & 1u) != 0, &prevx, &nlet, &npun);
         if (state != kNoSync) break;
         ++pos;
     }
@@ -197,13 +157,13 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
             pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
             tab = s_fsm + pat * kPretokTableSize;
             state = S_START;
-            prevx = X_EOT; nlet = 0;
+            prevx = X_EOT; nlet = 0; npun = 0;
             continue;
         }
         // hand over to the thread that started at the first sync point at or beyond the end of my chunk
         // (after the retroactive boundaries above, which concern positions of mine); same predicate as
         // sync_state(), evaluated on the classes just seen
-        if (pos >= ce && (bad || sync_rule(x, prevx, nlet, (pat & 1u) != 0) != kNoSync)) break;
+        if (pos >= ce && (bad || sync_rule(x, prevx, nlet, npun, (pat & 1u) != 0) != kNoSync)) break;
         if (a & A_B_NOW) {
             const uint64_t w = pos >> 5;
             if (w != cur_word) { or_bits(piece_bits, cur_word, cur_bits); cur_word = w; cur_bits = 0; }
@@ -217,10 +177,12 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
             const uint32_t lb = s[pos - 1];
             prevx = lb < 0x80 ? s_ascii[lb] : static_cast<uint32_t>(X_LL);   // last letter of the contraction (U+017F is Ll)
             nlet = (skip == 3 && lb >= 0x80) ? 1u : skip - 1;
+            npun = 0;
         } else {
             state = a & A_STATE_MASK; pos += len;
             prevx = x;
             nlet = x_is_letter(x) ? (nlet < 3 ? nlet + 1 : 3u) : 0u;
+            npun = x_is_run_punct(x, (pat & 1u) != 0) ? (npun < 2 ? npun + 1 : 2u) : 0u;
         }
     }
     or_bits(piece_bits, cur_word, cur_bits);
@@ -460,13 +422,13 @@ __device__ __forceinline__ uint32_t whole_piece_lookup(const TablesView& T, cons
     return long_lookup(T, long_hash(k0, k1, load_le32(p + len - 4), len), p, len);
 }
 
-// the exact merge loop on one piece of 2..32 bytes, parts in shared memory columns sid/srk (stride 32 words):
-//   sid[k*32] = start offset << 21 | id      srk[k*32] = rank of (part k, part k+1)
+// the exact merge loop on one piece of 2..32 bytes.  Part k = the part that STARTS at byte k of the piece; `alive` has
+// one bit per live part, so a merge clears a bit instead of shifting arrays.  Shared-memory columns (stride 32 words):
+//   sid[k*32] = id of part k      srk[k*32] = rank of (part k, next live part)
 __device__ __forceinline__ void merge_piece_in_lane(const TablesView& T, const uint8_t* __restrict__ text, uint64_t pos, uint32_t len,
                                                     uint32_t* sid, uint32_t* srk, uint32_t* __restrict__ ids_by_pos,
                                                     uint32_t* __restrict__ tok_bits) {
     const uint8_t* __restrict__ p = text + pos;
-    uint32_t m = len;
     // the piece's bytes (<= 32) in eight registers; parts = bytes, ranks from the raw byte-pair table, four loads in flight
     uint32_t w[8];
     load16(p, w[0], w[1], w[2], w[3]);
@@ -486,30 +448,36 @@ __device__ __forceinline__ void merge_piece_in_lane(const TablesView& T, const u
             rkv[t] = (k0 + t + 1 < len) ? T.bytepair[(bv[t] << 8) | bv[t + 1]] : kNone;
         }
 #pragma unroll
-        for (uint32_t t = 0; t < 4; ++t) if (k0 + t < len) { sid[(k0 + t) * 32] = ((k0 + t) << 21) | idv[t]; srk[(k0 + t) * 32] = rkv[t]; }
+        for (uint32_t t = 0; t < 4; ++t) if (k0 + t < len) { sid[(k0 + t) * 32] = idv[t]; srk[(k0 + t) * 32] = rkv[t]; }
     }
+    uint32_t alive = (len >= 32) ? kFull : ((1u << len) - 1u);
     for (;;) {
         uint32_t best = kNone, bi = 0;
-        for (uint32_t k = 0; k + 1 < m; ++k) { const uint32_t r = srk[k * 32]; if (r < best) { best = r; bi = k; } }   // strict <: leftmost
+        for (uint32_t bits = alive; bits; bits &= bits - 1) {     // ascending positions, strict < : leftmost minimum
+            const uint32_t k = static_cast<uint32_t>(__ffs(bits)) - 1u;
+            const uint32_t r = srk[k * 32];
+            if (r < best) { best = r; bi = k; }
+        }
         if (best == kNone) break;
-        const uint32_t st = sid[bi * 32] & ~kIdMask;
-        sid[bi * 32] = st | best;                             // rank == id of the merged token
-        for (uint32_t k = bi + 1; k + 1 < m; ++k) { sid[k * 32] = sid[(k + 1) * 32]; srk[k * 32] = srk[(k + 1) * 32]; }
-        --m;
+        const uint32_t above = alive & ~((2u << bi) - 1u);
+        const uint32_t nb = static_cast<uint32_t>(__ffs(above)) - 1u;          // the partner: it has one, its rank was not kNone
+        alive &= ~(1u << nb);
+        sid[bi * 32] = best;                                                    // rank == id of the merged token
+        const uint32_t above2 = alive & ~((2u << bi) - 1u);
+        const uint32_t below = alive & ((1u << bi) - 1u);
+        const bool wr = above2 != 0, wl = below != 0;
+        const uint32_t nn = wr ? static_cast<uint32_t>(__ffs(above2)) - 1u : 0u;
+        const uint32_t pv = wl ? 31u - static_cast<uint32_t>(__clz(below)) : 0u;
         uint32_t nr, nl;
-        const bool wr = bi + 1 < m, wl = bi > 0;
-        pair_lookup2(T, best, wr ? (sid[(bi + 1) * 32] & kIdMask) : 0u, wr, wl ? (sid[(bi - 1) * 32] & kIdMask) : 0u, best, wl, nr, nl);
+        pair_lookup2(T, best, wr ? sid[nn * 32] : 0u, wr, wl ? sid[pv * 32] : 0u, best, wl, nr, nl);
         srk[bi * 32] = nr;
-        if (wl) srk[(bi - 1) * 32] = nl;
+        if (wl) srk[pv * 32] = nl;
     }
-    uint64_t mask = 0;
-    const uint32_t sh = static_cast<uint32_t>(pos & 31);
-    for (uint32_t k = 0; k < m; ++k) {
-        const uint32_t v = sid[k * 32];
-        const uint32_t st = v >> 21;
-        ids_by_pos[pos + st] = v & kIdMask;
-        mask |= 1ull << (sh + st);
+    for (uint32_t bits = alive; bits; bits &= bits - 1) {
+        const uint32_t k = static_cast<uint32_t>(__ffs(bits)) - 1u;
+        ids_by_pos[pos + k] = sid[k * 32];
     }
+    const uint64_t mask = static_cast<uint64_t>(alive) << (pos & 31);
     atomicOr(&tok_bits[pos >> 5], static_cast<uint32_t>(mask));
     if (mask >> 32) atomicOr(&tok_bits[(pos >> 5) + 1], static_cast<uint32_t>(mask >> 32));
 }
@@ -561,7 +529,7 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
     TablesView T = vs.v[vid];
 
     // ---- pass 1: whole-piece lookups
-    uint32_t need = 0, done = 0;
+    uint32_t need_s = 0, need_m = 0, need_l = 0, done = 0;   // misses of <= 6, 7..12, 13..32 bytes
     uint32_t bits = my;
     while (bits) {
         const uint32_t bpos = static_cast<uint32_t>(__ffs(bits)) - 1u;
@@ -586,7 +554,9 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
         const uint32_t len = static_cast<uint32_t>(end - pos);
         const uint32_t tok = whole_piece_lookup(T, text + pos, len);
         if (tok != kNone) { ids_by_pos[pos] = tok; done |= 1u << bpos; }
-        else need |= 1u << bpos;
+        else if (len <= 6) need_s |= 1u << bpos;
+        else if (len <= 12) need_m |= 1u << bpos;
+        else need_l |= 1u << bpos;
     }
     if (kMode == 1) return;
     {   // flags of the direct hits: two lanes share a 32-bit word
@@ -594,39 +564,45 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
         if (!(lane & 1u) && base < b.total_bytes) { const uint32_t wbits = done | (other << 16); if (wbits) atomicOr(&tok_bits[base >> 5], wbits); }
     }
 
-    // ---- pass 2: the misses, dealt out one piece per lane
-    const uint32_t cnt = __popc(need);
-    uint32_t incl = cnt;
-#pragma unroll
-    for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
-    const uint32_t prefix = incl - cnt;
-    const uint32_t total_need = __shfl_sync(kFull, incl, 31);
+    // ---- pass 2: the misses, dealt out one piece per lane, in three length classes so that the lanes of a batch
+    //      carry similar work (the merge loop of a 30-byte piece is ~10x that of a 4-byte one)
     uint32_t* sid = &s_id[wic][0][lane];
     uint32_t* srk = &s_rk[wic][0][lane];
-    for (uint32_t g0 = 0; g0 < total_need; g0 += 32) {
-        const uint32_t g = g0 + lane;
-        // owner = last lane whose exclusive prefix is <= g
-        uint32_t o = 0;
+#pragma unroll 1
+    for (uint32_t cls = 0; cls < 3; ++cls) {
+        const uint32_t need_c = cls == 0 ? need_s : (cls == 1 ? need_m : need_l);
+        if (!__any_sync(kFull, need_c != 0)) continue;
+        const uint32_t cnt = __popc(need_c);
+        uint32_t incl = cnt;
 #pragma unroll
-        for (uint32_t step = 16; step; step >>= 1) {
-            const uint32_t cand = o + step;
-            const uint32_t pc = __shfl_sync(kFull, prefix, cand & 31u);
-            if (cand < 32 && pc <= g) o = cand;
-        }
-        const uint32_t opre = __shfl_sync(kFull, prefix, o);
-        const uint32_t oneed = __shfl_sync(kFull, need, o);
-        const uint32_t omy = __shfl_sync(kFull, my, o);
-        const uint32_t onf_rel = __shfl_sync(kFull, nf_rel, o);
-        const uint32_t ovid = __shfl_sync(kFull, vid, o);
-        if (g < total_need) {
-            const uint32_t bpos = kth_set_bit(oneed, g - opre);
-            const uint64_t pos = r0 + 16ull * o + bpos;
-            const uint32_t rest = omy & ~((2u << bpos) - 1u);
-            const uint64_t end = rest ? r0 + 16ull * o + static_cast<uint32_t>(__ffs(rest)) - 1u : ((onf_rel == 0xFFFFu) ? beyond : r0 + onf_rel);
-            uint32_t pv = ovid;
-            if (multi) pv = b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)];   // the owner's vid is that of its LAST piece
-            if (pv != vid) { vid = pv; T = vs.v[vid]; }
-            merge_piece_in_lane(T, text, pos, static_cast<uint32_t>(end - pos), sid, srk, ids_by_pos, tok_bits);
+        for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
+        const uint32_t prefix = incl - cnt;
+        const uint32_t total_need = __shfl_sync(kFull, incl, 31);
+        for (uint32_t g0 = 0; g0 < total_need; g0 += 32) {
+            const uint32_t g = g0 + lane;
+            // owner = last lane whose exclusive prefix is <= g
+            uint32_t o = 0;
+#pragma unroll
+            for (uint32_t step = 16; step; step >>= 1) {
+                const uint32_t cand = o + step;
+                const uint32_t pc = __shfl_sync(kFull, prefix, cand & 31u);
+                if (cand < 32 && pc <= g) o = cand;
+            }
+            const uint32_t opre = __shfl_sync(kFull, prefix, o);
+            const uint32_t oneed = __shfl_sync(kFull, need_c, o);
+            const uint32_t omy = __shfl_sync(kFull, my, o);
+            const uint32_t onf_rel = __shfl_sync(kFull, nf_rel, o);
+            const uint32_t ovid = __shfl_sync(kFull, vid, o);
+            if (g < total_need) {
+                const uint32_t bpos = kth_set_bit(oneed, g - opre);
+                const uint64_t pos = r0 + 16ull * o + bpos;
+                const uint32_t rest = omy & ~((2u << bpos) - 1u);
+                const uint64_t end = rest ? r0 + 16ull * o + static_cast<uint32_t>(__ffs(rest)) - 1u : ((onf_rel == 0xFFFFu) ? beyond : r0 + onf_rel);
+                uint32_t pv = ovid;
+                if (multi) pv = b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)];   // the owner's vid is that of its LAST piece
+                if (pv != vid) { vid = pv; T = vs.v[vid]; }
+                merge_piece_in_lane(T, text, pos, static_cast<uint32_t>(end - pos), sid, srk, ids_by_pos, tok_bits);
+            }
         }
     }
 }

@@ -7,6 +7,8 @@
 //           a punctuation character (class OTHER, not an apostrophe, not a mark) right after a letter or digit
 //   LETTERS (uncased patterns) the three previous characters are letters: a contraction covers at most two
 //   W_Y     (cased patterns) the previous character is a lower-case letter and the two before it are letters
+//   ORUN    the two previous characters are punctuation (not '/', which a newline trailer may have eaten; not a
+//           mark in the cased patterns, where marks are word characters): the second of them sits in a punctuation run
 //
 // sync_rule() is the predicate on classes; sync_state() evaluates it from memory (used to FIND a start);
 // the running thread evaluates the same predicate from the classes it has just seen (no loads).
@@ -26,23 +28,25 @@ CFBPE_HD uint32_t ext_class(const Ch& c) {   // C_* class + code point -> X_* cl
 }
 CFBPE_HD bool x_is_letter(uint32_t x) { return x == X_LU || x == X_LL || x == X_LO; }
 CFBPE_HD bool x_is_ws(uint32_t x) { return x == X_WS || x == X_SPACE || x == X_CRLF; }
+CFBPE_HD bool x_is_run_punct(uint32_t x, bool cased) { return x == X_OTHER || x == X_APOS || (!cased && x == X_M); }
 
 // state BEFORE the character of class x is consumed, given the class of the previous character and the number
 // (saturated at 3) of consecutive letters right before it; kNoSync if the context does not determine it
-CFBPE_HD uint32_t sync_rule(uint32_t x, uint32_t prevx, uint32_t nlet, bool cased) {
+CFBPE_HD uint32_t sync_rule(uint32_t x, uint32_t prevx, uint32_t nlet, uint32_t npun, bool cased) {
     const bool prev_ln = x_is_letter(prevx) || prevx == X_N;
     if (x == X_WS || x == X_SPACE) return x_is_ws(prevx) ? kNoSync : static_cast<uint32_t>(S_START);
     if (x == X_CRLF) return prev_ln ? static_cast<uint32_t>(S_START) : kNoSync;
     if (x == X_N) return prevx != X_N ? static_cast<uint32_t>(S_START) : kNoSync;
     if ((x == X_OTHER || x == X_SLASH) && prev_ln) return S_START;
     if (nlet >= 3 && (cased ? prevx == X_LL : x_is_letter(prevx))) return cased ? static_cast<uint32_t>(S_W_Y) : static_cast<uint32_t>(S_LETTERS);
+    if (npun >= 2) return S_ORUN;
     return kNoSync;
 }
 
 // evaluate the rule at byte position pos (ps < pos < pe) by decoding up to three characters to the left
 template <typename Txt>
 CFBPE_HD uint32_t sync_state(const Txt& s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc, bool cased,
-                             uint32_t* prevx_out = nullptr, uint32_t* nlet_out = nullptr) {
+                             uint32_t* prevx_out = nullptr, uint32_t* nlet_out = nullptr, uint32_t* npun_out = nullptr) {
     const uint32_t b = s[pos];
     if ((b & 0xC0) == 0x80) return kNoSync;  // inside a character
     int bad = 0;
@@ -61,9 +65,19 @@ CFBPE_HD uint32_t sync_state(const Txt& s, uint64_t pos, uint64_t ps, uint64_t p
             q -= c.len;
         }
     }
+    uint32_t npun = 0;
+    if (x_is_run_punct(prevx, cased)) {
+        npun = 1;
+        const uint64_t q = pos - prev.len;
+        if (q > ps) {
+            const Ch c = get_prev_char(s, q, ps, pe, uc);
+            if (x_is_run_punct(ext_class(c), cased)) npun = 2;
+        }
+    }
     if (prevx_out) *prevx_out = prevx;
     if (nlet_out) *nlet_out = nlet;
-    return sync_rule(ext_class(cur), prevx, nlet, cased);
+    if (npun_out) *npun_out = npun;
+    return sync_rule(ext_class(cur), prevx, nlet, npun, cased);
 }
 
 }  // namespace cfbpe

@@ -1,10 +1,12 @@
 #!/usr/bin/env python3
 """Top source lines of one kernel from an .ncu-rep (needs -lineinfo + --import-source on).
-usage: ncu_lines.py REPORT KERNEL_REGEX [N]"""
+usage: ncu_lines.py REPORT KERNEL_REGEX [N [LAUNCH_SKIP]]"""
 import csv, subprocess, sys, io
 rep, kern = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + kern],
+skip = sys.argv[4] if len(sys.argv) > 4 else "0"      # n-th launch matching the name (template instances share a base name)
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + kern,
+                      "--launch-skip", skip, "--launch-count", "1"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 cur_file, hdr, data = "", None, []
