@@ -747,6 +747,99 @@ __device__ __forceinline__ void list_rounds(const TablesView& T, uint32_t* __res
     }
 }
 
+// phase B, multi-merge form: up to 32 merges per round, still in the EXACT order of the sequential loop.
+// Each lane proposes the minimum pair of its chunk and looks up -- all lanes at once, one table round trip -- the two
+// pairs its merge would create.  The proposals are then taken in ascending (rank, position) order while that order is
+// provably what the sequential loop would do:
+//   * a proposal is only taken while its key is below `bound` = the smallest key of anything that might have to come
+//     first: the pairs created by the merges taken so far, and the second-smallest pair of every lane whose proposal
+//     has been consumed (its other pairs were not proposed);
+//   * a proposal that shares a part with a merge already taken is dropped (what replaced it is covered by `bound`);
+//     one that merely neighbours such a merge still exists but its looked-up pairs are stale: the round ends there.
+// The global minimum is always taken, so every round makes progress.  A 4 KiB piece of random letters needs ~250 such
+// rounds instead of ~2 500 single-merge rounds.
+__device__ __forceinline__ bool key_less(uint32_t r1, uint32_t p1, uint32_t r2, uint32_t p2) { return r1 < r2 || (r1 == r2 && p1 < p2); }
+
+__device__ __forceinline__ void list_rounds_multi(const TablesView& T, uint32_t* id, uint32_t* rk, uint32_t* link, uint32_t* nid,
+                                                  uint32_t m, uint32_t lane) {
+    constexpr uint32_t kNoPrev = 0xFFFFu;
+    for (uint32_t i = lane; i < m; i += 32) {
+        link[i] = ((i + 1) << 16) | (i ? i - 1 : kNoPrev);
+        nid[i] = (i + 1 < m) ? id[i + 1] : kNone;
+    }
+    __syncwarp();
+    const uint32_t c = (m + 31) / 32;
+    const uint32_t lo = lane * c < m ? lane * c : m;
+    const uint32_t hi = lo + c < m ? lo + c : m;
+    for (;;) {
+        // -- my chunk's smallest and second-smallest pair, 16 loads in flight
+        uint32_t m1 = kNone, p1 = 0, m2 = kNone, p2 = 0;
+        for (uint32_t xb = lo; xb < hi; xb += 16) {
+            uint32_t v[16];
+#pragma unroll
+            for (uint32_t t = 0; t < 16; ++t) v[t] = (xb + t < hi) ? rk[xb + t] : kNone;
+#pragma unroll
+            for (uint32_t t = 0; t < 16; ++t) {
+                if (v[t] < m1) { m2 = m1; p2 = p1; m1 = v[t]; p1 = xb + t; }
+                else if (v[t] < m2) { m2 = v[t]; p2 = xb + t; }
+            }
+        }
+        if (!__any_sync(kFull, m1 != kNone)) break;
+        // -- my proposal (x, its partner j, the parts around them) and the two pairs the merge would create
+        const bool valid = m1 != kNone;
+        const uint32_t x = p1, r = m1;
+        uint32_t j = 0, q = kNoPrev, k = m, L = kNone, R = kNone;
+        if (valid) {
+            const uint32_t li = link[x];
+            j = li >> 16; q = li & 0xFFFFu;
+            k = link[j] >> 16;
+            const uint32_t idk = nid[j];
+            const uint32_t idq = (q != kNoPrev) ? id[q] : 0u;
+            pair_lookup2(T, r, idk, k < m, idq, r, q != kNoPrev, R, L);
+        }
+        // -- take proposals in ascending key order while the sequential loop would
+        bool pending = valid, accepted = false;
+        uint32_t bound_r = kNone, bound_p = 0xFFFFFFFFu;
+        for (;;) {
+            const uint32_t br = __reduce_min_sync(kFull, pending ? r : kNone);
+            if (br == kNone) break;
+            const uint32_t bp = __reduce_min_sync(kFull, (pending && r == br) ? x : 0xFFFFFFFFu);
+            if (!key_less(br, bp, bound_r, bound_p)) break;
+            const uint32_t s = static_cast<uint32_t>(__ffs(__ballot_sync(kFull, pending && r == br && x == bp))) - 1u;
+            const uint32_t sq = __shfl_sync(kFull, q, s), sj = __shfl_sync(kFull, j, s), sk = __shfl_sync(kFull, k, s);
+            // against every merge already taken this round (u = mine, if I was taken):
+            //   gone   the proposal shares a part with u's pair: it no longer exists; what replaced it is in `bound`
+            //   stale  it still exists but u changed a neighbour, so its looked-up pairs are out of date: it has to wait
+            //          for the next round -- and everything after it in key order with it
+            const bool gone_here = accepted && (j == bp || x == sj);
+            const bool near_here = accepted && (x == sq || x == bp || x == sj || x == sk || j == sq || j == bp || j == sj || j == sk ||
+                                                q == bp || q == sj || k == bp || k == sj);
+            const bool gone = __any_sync(kFull, gone_here);
+            const bool stale = !gone && __any_sync(kFull, near_here);
+            if (stale) break;
+            const bool conflict = gone;
+            if (lane == s) { pending = false; accepted = !conflict; }
+            // whatever may now have to come before the remaining proposals
+            const uint32_t sL = __shfl_sync(kFull, L, s), sR = __shfl_sync(kFull, R, s);
+            const uint32_t s2r = __shfl_sync(kFull, m2, s), s2p = __shfl_sync(kFull, p2, s);
+            if (key_less(s2r, s2p, bound_r, bound_p)) { bound_r = s2r; bound_p = s2p; }
+            if (!conflict) {
+                if (key_less(sL, sq, bound_r, bound_p)) { bound_r = sL; bound_p = sq; }
+                if (key_less(sR, bp, bound_r, bound_p)) { bound_r = sR; bound_p = bp; }
+            }
+        }
+        // -- apply the merges that were taken (their neighbourhoods are disjoint)
+        if (accepted) {
+            id[x] = r; id[j] = kNone; rk[j] = kNone; rk[x] = R;
+            link[x] = (k << 16) | q;
+            nid[x] = nid[j];
+            if (k < m) link[k] = (link[k] & 0xFFFF0000u) | x;
+            if (q != kNoPrev) { rk[q] = L; nid[q] = r; }
+        }
+        __syncwarp();
+    }
+}
+
 // phase B for pieces that live in shared memory (m <= kMedSmem): every lane owns at most 8 parts and simply re-reads
 // them each round -- cheaper than maintaining cached minima when a chunk is this small.
 __device__ __forceinline__ void list_rounds_small(const TablesView& T, uint32_t* id, uint32_t* rk, uint32_t* link, uint32_t* nid,
@@ -909,8 +1002,12 @@ bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
 
         // ---- phase B: linked list, one merge per round
         if (list_mode) {
+#ifdef CFBPE_SINGLE_MERGE_ROUNDS
             if (in_smem) list_rounds_small(T, id, rk, a0, a1, m, lane);
             else list_rounds(T, id, rk, a0, a1, m, &s_subr[threadIdx.x >> 5][0][lane], &s_subp[threadIdx.x >> 5][0][lane], lane);
+#else
+            list_rounds_multi(T, id, rk, a0, a1, m, lane);
+#endif
             __syncwarp();
         }
         // ---- one flag per surviving part (dead slots hold kNone); order along the slice is token order
