@@ -136,7 +136,8 @@ CFBPE_API int cfbpe_count_batch(cfbpe_ctx *ctx, uint32_t n_prompts, const uint8_
                       const uint8_t *vocab_ids, uint32_t *out_counts);
 
 /* Same path on device-resident buffers, enqueued on `stream` (a cudaStream_t; NULL = the legacy
- * default stream).  d_out_ids may be NULL (count only).  n_tokens (host, may be NULL) is written
+ * default stream).  d_bytes must be readable for 32 bytes past total_bytes (the kernels read whole 16-byte
+ * groups); the contents of that padding do not matter.  d_out_ids may be NULL (count only).  n_tokens (host, may be NULL) is written
  * after an internal stream sync; with n_tokens == NULL the call is fully asynchronous and
  * d_out_offsets[n_prompts] holds the total.  Malformed UTF-8 is reported by the next call that
  * synchronises (or cfbpe_device_status). */

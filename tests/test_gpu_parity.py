@@ -283,3 +283,34 @@ def test_pipelined_host_path_matches_oracle(oracle_vocabs, tekken_bytes, monkeyp
     ids, off, counts = c.encode_batch(data, offs, vid)      # still healthy
     assert np.array_equal(ids, want_ids)
     c.close()
+
+
+def test_async_device_calls_and_buffer_reuse(plug, ctx, oracle_vocabs):
+    """back-to-back asynchronous device calls on one stream (what bench.py times), then sizes going down and up again:
+    the workspace is reused, results must not leak from one call into the next"""
+    import torch
+    from oracle import oracle
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    batches = []
+    for seed, n in [(1, 3000), (2, 40), (3, 9000), (4, 1)]:
+        prompts = [s.encode() for s in fuzzgen.fuzz_strings(seed, n, max_atoms=50)]
+        data, offs = pack(prompts)
+        want_ids, want_off, _ = oracle.encode_batch([oracle_vocabs[0]], [0], data, offs, nthreads=os.cpu_count())
+        total = int(offs[-1])
+        d_bytes = torch.zeros(total + 64, dtype=torch.uint8, device=dev)
+        d_bytes[:total] = torch.from_numpy(data).to(dev)
+        bufs = dict(d_bytes=d_bytes, d_offs=torch.from_numpy(offs.astype(np.int64)).to(dev),
+                    d_ids=torch.full((total + 1,), -1, dtype=torch.int32, device=dev),
+                    d_out=torch.zeros(len(prompts) + 1, dtype=torch.int64, device=dev),
+                    d_cnt=torch.zeros(max(len(prompts), 1), dtype=torch.int32, device=dev))
+        batches.append((prompts, total, bufs, want_ids, want_off))
+    for _ in range(2):
+        for prompts, total, b, want_ids, want_off in batches:        # enqueue everything without syncing in between
+            plug.ctx.encode_batch_device(len(prompts), b["d_bytes"].data_ptr(), total, b["d_offs"].data_ptr(), None, b["d_ids"].data_ptr(),
+                                         b["d_ids"].numel(), b["d_out"].data_ptr(), b["d_cnt"].data_ptr(), stream, sync=False)
+        plug.ctx.device_status(stream)
+        for prompts, total, b, want_ids, want_off in batches:
+            off = b["d_out"].cpu().numpy().astype(np.uint64)
+            assert np.array_equal(off, want_off)
+            assert np.array_equal(b["d_ids"][:int(off[-1])].cpu().numpy().view(np.uint32), want_ids)
