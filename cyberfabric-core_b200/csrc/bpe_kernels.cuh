@@ -172,17 +172,24 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
         if (a & A_SET_ALC) alc = pos + len;
         if (a & A_SET_LAST) last = pos;
         if (a & A_SET_LBE) lbe = pos + len;
+        // the hand-over predicate needs the classes of the last three characters only once pos reaches ce: track them
+        // from 16 bytes (>= 4 characters) before that, so that the counters are exact when they are first read
+        const bool track = pos + 16 >= ce;
         if (skip) {   // a contraction: apostrophe + one or two letters
             state = S_START; pos += skip;
-            const uint32_t lb = s[pos - 1];
-            prevx = lb < 0x80 ? s_ascii[lb] : static_cast<uint32_t>(X_LL);   // last letter of the contraction (U+017F is Ll)
-            nlet = (skip == 3 && lb >= 0x80) ? 1u : skip - 1;
-            npun = 0;
+            if (track) {
+                const uint32_t lb = s[pos - 1];
+                prevx = lb < 0x80 ? s_ascii[lb] : static_cast<uint32_t>(X_LL);   // last letter of the contraction (U+017F is Ll)
+                nlet = (skip == 3 && lb >= 0x80) ? 1u : skip - 1;
+                npun = 0;
+            }
         } else {
             state = a & A_STATE_MASK; pos += len;
-            prevx = x;
-            nlet = x_is_letter(x) ? (nlet < 3 ? nlet + 1 : 3u) : 0u;
-            npun = x_is_run_punct(x, (pat & 1u) != 0) ? (npun < 2 ? npun + 1 : 2u) : 0u;
+            if (track) {
+                prevx = x;
+                nlet = x_is_letter(x) ? (nlet < 3 ? nlet + 1 : 3u) : 0u;
+                npun = x_is_run_punct(x, (pat & 1u) != 0) ? (npun < 2 ? npun + 1 : 2u) : 0u;
+            } else { nlet = 0; npun = 0; }
         }
     }
     or_bits(piece_bits, cur_word, cur_bits);
@@ -797,36 +804,36 @@ __device__ __forceinline__ void list_rounds_multi(const TablesView& T, uint32_t*
             const uint32_t idq = (q != kNoPrev) ? id[q] : 0u;
             pair_lookup2(T, r, idk, k < m, idq, r, q != kNoPrev, R, L);
         }
-        // -- take proposals in ascending key order while the sequential loop would
+        // -- take proposals in ascending key order while the sequential loop would.  Lanes own ascending chunks, so
+        //    (rank, lane) orders the proposals exactly like (rank, position): one redux names the next one.
+        // what my merge, if taken, puts into `bound`: the smaller of its two new pairs and my chunk's second minimum ...
+        uint32_t c_r = m2, c_p = p2;
+        if (key_less(L, q, c_r, c_p)) { c_r = L; c_p = q; }
+        if (key_less(R, x, c_r, c_p)) { c_r = R; c_p = x; }
+        const uint32_t xq = x | (q << 16), jk = j | (k << 16);
         bool pending = valid, accepted = false;
         uint32_t bound_r = kNone, bound_p = 0xFFFFFFFFu;
         for (;;) {
-            const uint32_t br = __reduce_min_sync(kFull, pending ? r : kNone);
-            if (br == kNone) break;
-            const uint32_t bp = __reduce_min_sync(kFull, (pending && r == br) ? x : 0xFFFFFFFFu);
+            const uint32_t best = __reduce_min_sync(kFull, pending ? ((r << 5) | lane) : kNone);
+            if (best == kNone) break;
+            const uint32_t s = best & 31u, br = best >> 5;
+            const uint32_t sxq = __shfl_sync(kFull, xq, s), sjk = __shfl_sync(kFull, jk, s);
+            const uint32_t bp = sxq & 0xFFFFu, sq = sxq >> 16, sj = sjk & 0xFFFFu, sk = sjk >> 16;
             if (!key_less(br, bp, bound_r, bound_p)) break;
-            const uint32_t s = static_cast<uint32_t>(__ffs(__ballot_sync(kFull, pending && r == br && x == bp))) - 1u;
-            const uint32_t sq = __shfl_sync(kFull, q, s), sj = __shfl_sync(kFull, j, s), sk = __shfl_sync(kFull, k, s);
             // against every merge already taken this round (u = mine, if I was taken):
             //   gone   the proposal shares a part with u's pair: it no longer exists; what replaced it is in `bound`
             //   stale  it still exists but u changed a neighbour, so its looked-up pairs are out of date: it has to wait
             //          for the next round -- and everything after it in key order with it
-            const bool gone_here = accepted && (j == bp || x == sj);
-            const bool near_here = accepted && (x == sq || x == bp || x == sj || x == sk || j == sq || j == bp || j == sj || j == sk ||
-                                                q == bp || q == sj || k == bp || k == sj);
-            const bool gone = __any_sync(kFull, gone_here);
-            const bool stale = !gone && __any_sync(kFull, near_here);
-            if (stale) break;
-            const bool conflict = gone;
-            if (lane == s) { pending = false; accepted = !conflict; }
-            // whatever may now have to come before the remaining proposals
-            const uint32_t sL = __shfl_sync(kFull, L, s), sR = __shfl_sync(kFull, R, s);
-            const uint32_t s2r = __shfl_sync(kFull, m2, s), s2p = __shfl_sync(kFull, p2, s);
-            if (key_less(s2r, s2p, bound_r, bound_p)) { bound_r = s2r; bound_p = s2p; }
-            if (!conflict) {
-                if (key_less(sL, sq, bound_r, bound_p)) { bound_r = sL; bound_p = sq; }
-                if (key_less(sR, bp, bound_r, bound_p)) { bound_r = sR; bound_p = bp; }
-            }
+            const uint32_t gone_here = (accepted && (j == bp || x == sj)) ? 1u : 0u;
+            const uint32_t near_here = (accepted && (x == sq || x == bp || x == sj || x == sk || j == sq || j == bp || j == sj || j == sk ||
+                                                     q == bp || q == sj || k == bp || k == sj)) ? 2u : 0u;
+            const uint32_t flags = __reduce_or_sync(kFull, gone_here | near_here);
+            const bool gone = flags & 1u;
+            if (!gone && (flags & 2u)) break;
+            if (lane == s) { pending = false; accepted = !gone; }
+            // ... or, if it lost a part to an earlier merge, only my chunk's second minimum
+            const uint32_t sr = __shfl_sync(kFull, gone ? m2 : c_r, s), sp = __shfl_sync(kFull, gone ? p2 : c_p, s);
+            if (key_less(sr, sp, bound_r, bound_p)) { bound_r = sr; bound_p = sp; }
         }
         // -- apply the merges that were taken (their neighbourhoods are disjoint)
         if (accepted) {
@@ -1002,11 +1009,14 @@ bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
 
         // ---- phase B: linked list, one merge per round
         if (list_mode) {
-#ifdef CFBPE_SINGLE_MERGE_ROUNDS
+            // pieces in shared memory: a single-merge round is a short chain there (measured: the ordered take-loop of the
+            // multi-merge round costs more than it saves); pieces in global scratch: every round is several L2 round
+            // trips, so taking ~6 merges per round pays
             if (in_smem) list_rounds_small(T, id, rk, a0, a1, m, lane);
+#ifdef CFBPE_SINGLE_MERGE_ROUNDS
             else list_rounds(T, id, rk, a0, a1, m, &s_subr[threadIdx.x >> 5][0][lane], &s_subp[threadIdx.x >> 5][0][lane], lane);
 #else
-            list_rounds_multi(T, id, rk, a0, a1, m, lane);
+            else list_rounds_multi(T, id, rk, a0, a1, m, lane);
 #endif
             __syncwarp();
         }

@@ -285,7 +285,7 @@ int run_host(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const uint64_t* o
 
     BatchView b{ctx->d_bytes, ctx->d_offsets, vocab_ids ? ctx->d_vocab_ids : nullptr, n, total};
     enqueue_encode(b, ctx->vs, ctx->uc, ctx->ws, want_ids ? ctx->d_out_ids : nullptr, ctx->max_bytes, ctx->d_out_offsets,
-                   ctx->d_out_counts, static_cast<uint32_t>(ctx->sm_count * 4), s, ctx->aux_stream, ctx->ev_fork, ctx->ev_join, prof);
+                   ctx->d_out_counts, static_cast<uint32_t>(ctx->sm_count * 4), s, prof ? s : ctx->aux_stream, ctx->ev_fork, ctx->ev_join, prof);
     CK(cudaGetLastError());
     if (prof) cudaEventRecord(prof->d2h[0], s);
     CK(cudaMemcpyAsync(ctx->h_status, ctx->ws.status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
@@ -525,7 +525,7 @@ int cfbpe_encode_batch_device(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t*
     if (prof) { std::memset(prof->launched, 0, sizeof prof->launched); cudaEventRecord(prof->total[0], s); cudaEventRecord(prof->h2d[0], s); cudaEventRecord(prof->h2d[1], s); }
     BatchView b{d_bytes, d_offsets, d_vocab_ids, n_prompts, total_bytes};
     enqueue_encode(b, ctx->vs, ctx->uc, ctx->ws, d_out_ids, out_cap, d_out_offsets, d_out_counts,
-                   static_cast<uint32_t>(ctx->sm_count * 4), s, ctx->aux_stream, ctx->ev_fork, ctx->ev_join, prof);
+                   static_cast<uint32_t>(ctx->sm_count * 4), s, prof ? s : ctx->aux_stream, ctx->ev_fork, ctx->ev_join, prof);   // profiling: one stream, so that the per-kernel times do not overlap
     CK(cudaGetLastError());
     if (prof) { cudaEventRecord(prof->d2h[0], s); cudaEventRecord(prof->d2h[1], s); cudaEventRecord(prof->total[1], s); }
     if (n_tokens || prof) {
