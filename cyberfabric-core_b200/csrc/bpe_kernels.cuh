@@ -503,6 +503,8 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
                          LongPiece* __restrict__ long_list, uint32_t long_cap, DeviceStatus* status) {
     __shared__ uint32_t s_id[kPieceWarps][32][32];   // [warp][part][lane]
     __shared__ uint32_t s_rk[kPieceWarps][32][32];
+    __shared__ uint16_t s_queue[kPieceWarps][kPieceRange];   // the warp's misses: offset in range | (len-1) << 9
+    __shared__ uint32_t s_head[kPieceWarps];
     const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const uint64_t warp = static_cast<uint64_t>(blockIdx.x) * kPieceWarps + wic;
     const uint64_t r0 = warp * kPieceRange;
@@ -571,46 +573,44 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
         if (!(lane & 1u) && base < b.total_bytes) { const uint32_t wbits = done | (other << 16); if (wbits) atomicOr(&tok_bits[base >> 5], wbits); }
     }
 
-    // ---- pass 2: the misses, dealt out one piece per lane, in three length classes so that the lanes of a batch
-    //      carry similar work (the merge loop of a 30-byte piece is ~10x that of a 4-byte one)
-    uint32_t* sid = &s_id[wic][0][lane];
-    uint32_t* srk = &s_rk[wic][0][lane];
+    // ---- pass 2: the misses.  They are written to a per-warp queue, longest class first, and every lane then takes the
+    //      next entry as soon as it is free (the merge loop of a 30-byte piece is ~10x that of a 4-byte one; with fixed
+    //      batches of 32 most lanes sat idle: 6.7 active lanes per instruction in profiles/ncu_summary_r01k.json)
+    uint16_t* queue = s_queue[wic];
+    uint32_t qbase = 0;
 #pragma unroll 1
     for (uint32_t cls = 0; cls < 3; ++cls) {
-        const uint32_t need_c = cls == 0 ? need_s : (cls == 1 ? need_m : need_l);
-        if (!__any_sync(kFull, need_c != 0)) continue;
+        const uint32_t need_c = cls == 0 ? need_l : (cls == 1 ? need_m : need_s);
         const uint32_t cnt = __popc(need_c);
         uint32_t incl = cnt;
 #pragma unroll
         for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
-        const uint32_t prefix = incl - cnt;
-        const uint32_t total_need = __shfl_sync(kFull, incl, 31);
-        for (uint32_t g0 = 0; g0 < total_need; g0 += 32) {
-            const uint32_t g = g0 + lane;
-            // owner = last lane whose exclusive prefix is <= g
-            uint32_t o = 0;
-#pragma unroll
-            for (uint32_t step = 16; step; step >>= 1) {
-                const uint32_t cand = o + step;
-                const uint32_t pc = __shfl_sync(kFull, prefix, cand & 31u);
-                if (cand < 32 && pc <= g) o = cand;
-            }
-            const uint32_t opre = __shfl_sync(kFull, prefix, o);
-            const uint32_t oneed = __shfl_sync(kFull, need_c, o);
-            const uint32_t omy = __shfl_sync(kFull, my, o);
-            const uint32_t onf_rel = __shfl_sync(kFull, nf_rel, o);
-            const uint32_t ovid = __shfl_sync(kFull, vid, o);
-            if (g < total_need) {
-                const uint32_t bpos = kth_set_bit(oneed, g - opre);
-                const uint64_t pos = r0 + 16ull * o + bpos;
-                const uint32_t rest = omy & ~((2u << bpos) - 1u);
-                const uint64_t end = rest ? r0 + 16ull * o + static_cast<uint32_t>(__ffs(rest)) - 1u : ((onf_rel == 0xFFFFu) ? beyond : r0 + onf_rel);
-                uint32_t pv = ovid;
-                if (multi) pv = b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)];   // the owner's vid is that of its LAST piece
-                if (pv != vid) { vid = pv; T = vs.v[vid]; }
-                merge_piece_in_lane(T, text, pos, static_cast<uint32_t>(end - pos), sid, srk, ids_by_pos, tok_bits);
-            }
+        uint32_t slot = qbase + incl - cnt;
+        for (uint32_t bits2 = need_c; bits2; bits2 &= bits2 - 1) {
+            const uint32_t bpos = static_cast<uint32_t>(__ffs(bits2)) - 1u;
+            const uint32_t rest = my & ~((2u << bpos) - 1u);
+            const uint64_t pos = base + bpos;
+            const uint64_t end = rest ? base + static_cast<uint32_t>(__ffs(rest)) - 1u : nf;
+            queue[slot++] = static_cast<uint16_t>((16u * lane + bpos) | ((static_cast<uint32_t>(end - pos) - 1u) << 9));   // offset in range | (len-1)
         }
+        qbase += __shfl_sync(kFull, incl, 31);
+    }
+    if (lane == 0) s_head[wic] = 0;
+    __syncwarp();
+    if (qbase == 0) return;
+    uint32_t* sid = &s_id[wic][0][lane];
+    uint32_t* srk = &s_rk[wic][0][lane];
+    for (;;) {
+        const uint32_t g = atomicAdd(&s_head[wic], 1u);
+        if (g >= qbase) break;
+        const uint32_t e = queue[g];
+        const uint64_t pos = r0 + (e & 511u);
+        const uint32_t len = (e >> 9) + 1u;
+        if (multi) {
+            const uint32_t pv = b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)];
+            if (pv != vid) { vid = pv; T = vs.v[vid]; }
+        }
+        merge_piece_in_lane(T, text, pos, len, sid, srk, ids_by_pos, tok_bits);
     }
 }
 
