@@ -54,14 +54,14 @@ struct DeviceStatus {
     uint32_t long_overflow;
     uint32_t long_next;    // K2b work ticket (pieces of 33..kBigPiece bytes)
     uint32_t n_big;        // pieces longer than kBigPiece (stored from the back of the list)
-    uint32_t pad;
+    uint32_t defer_next;   // K2c work ticket (over the big pieces; those K2b deferred carry their part count)
     uint64_t n_tokens;     // ids produced by this (sub-)batch (written by tile_scan)
     uint64_t tok_end;      // token_base + n_tokens: where the next sub-batch of a pipelined call continues
     unsigned long long long_bytes;   // bytes inside pieces handled by K2b ...
     unsigned long long long_tokens;  // ... and the ids they became (for the roofline of that kernel)
 };
 
-struct LongPiece { uint64_t start; uint64_t end; uint32_t vocab; uint32_t pad; };
+struct LongPiece { uint64_t start; uint64_t end; uint32_t vocab; uint32_t pad; };   // pad: 0, or the part count K2b left for K2c
 
 // ---------------------------------------------------------------------------------------
 // small helpers
@@ -775,7 +775,7 @@ __device__ __forceinline__ void list_rounds_multi(const TablesView& T, uint32_t*
         nid[i] = (i + 1 < m) ? id[i + 1] : kNone;
     }
     __syncwarp();
-    const uint32_t c = (m + 31) / 32;
+    const uint32_t c = ((m + 31) / 32) | 1u;      // odd: when the state is in shared memory the lanes' chunks start in 32 different banks
     const uint32_t lo = lane * c < m ? lane * c : m;
     const uint32_t hi = lo + c < m ? lo + c : m;
     for (;;) {
@@ -847,6 +847,106 @@ __device__ __forceinline__ void list_rounds_multi(const TablesView& T, uint32_t*
     }
 }
 
+// phase B, parallel-cut form: every thread of a group of kWarps warps proposes the minimum pair of its chunk of the
+// piece, all proposals look up the two pairs their merge would create at once (one table round trip), and ONE min
+// reduction decides which of them the sequential loop would have taken next, in order:
+//   key(pair) = rank << kPosBits | position          (the sequential loop takes pairs in ascending key order)
+//   a proposal S with key a_S is followed, if taken, by nothing smaller than  c_S = min(second-smallest key of S's
+//   chunk, keys of the two pairs S creates);  so another proposal L may be taken in the same round only if NOT
+//   (a_S < a_L and c_S <= a_L)  for every S, i.e. iff  a_L < cut1 = min_S max(a_S + 1, c_S);
+//   two proposals closer than three live parts touch each other's looked-up neighbourhood: the later one (larger key)
+//   has to wait, and everything after it: cut2 = min key of those.  Found through a claim array (atomicMin of the key on
+//   the two parts of each proposed pair; a proposal that sees a smaller claim on one of its four parts is the later one).
+// Taken = key < min(cut1, cut2): their neighbourhoods are disjoint, they apply in parallel.  The global minimum is always
+// taken.  With P chunks about 1.2 sqrt(P) merges go through per round on random text (the first chunk hit twice ends the
+// prefix): a 4 KiB random word is ~60 rounds of 256 threads instead of ~1 200 single-merge rounds.  tools/model_parcut.py
+// checks the rule against the sequential loop on random rank orders.
+// On entry id[] / kk[] hold the ids and RANKS of the compact parts; kk[] is converted to keys here.
+constexpr uint32_t kNoKey = 0xFFFFFFFFu;
+template <uint32_t kWarps, uint32_t kPosBits>
+__device__ __forceinline__ void list_rounds_par(const TablesView& T, uint32_t* id, uint32_t* kk, uint32_t* link, uint32_t* claim,
+                                                uint32_t m, uint32_t* s_red) {
+    constexpr uint32_t kNoPrev = 0xFFFFu, kPosMask = (1u << kPosBits) - 1u, P = kWarps * 32;
+    const uint32_t tid = threadIdx.x % P, lane = tid & 31, wid = tid >> 5;
+    auto group_sync = [&]() { if (kWarps == 1) __syncwarp(); else __syncthreads(); };
+    for (uint32_t i = tid; i < m; i += P) {
+        const uint32_t r = kk[i];
+        kk[i] = (r == kNone) ? kNoKey : ((r << kPosBits) | i);
+        link[i] = ((i + 1) << 16) | (i ? i - 1 : kNoPrev);
+        claim[i] = kNoKey;
+    }
+    group_sync();
+    uint32_t c = (m + P - 1) / P;
+    if (c > 1) c |= 1u;                               // odd: the threads' chunks start in different banks
+    const uint32_t lo = tid * c < m ? tid * c : m;
+    const uint32_t hi = lo + c < m ? lo + c : m;
+    for (uint32_t round = 0;; ++round) {
+        // -- smallest and second-smallest key of my chunk
+        uint32_t m1 = kNoKey, m2 = kNoKey;
+        for (uint32_t x = lo; x < hi; ++x) {
+            const uint32_t v = kk[x];
+            const uint32_t hi2 = v > m1 ? v : m1;
+            m2 = hi2 < m2 ? hi2 : m2;
+            m1 = v < m1 ? v : m1;
+        }
+        // -- my proposal: parts q | x j | k, and the pairs (q, xj) and (xj, k)
+        const bool valid = m1 != kNoKey;
+        uint32_t x = 0, j = 0, q = kNoPrev, k = m, r = 0, Lk = kNoKey, Rk = kNoKey, v = kNoKey;
+        if (valid) {
+            x = m1 & kPosMask; r = m1 >> kPosBits;
+            const uint32_t li = link[x];
+            j = li >> 16; q = li & 0xFFFFu;
+            k = link[j] >> 16;
+            const uint32_t idk = (k < m) ? id[k] : 0u;
+            const uint32_t idq = (q != kNoPrev) ? id[q] : 0u;
+            uint32_t R, L;
+            pair_lookup2(T, r, idk, k < m, idq, r, q != kNoPrev, R, L);
+            if (R != kNone) Rk = (R << kPosBits) | x;
+            if (L != kNone) Lk = (L << kPosBits) | q;
+            uint32_t cc = m2 < Lk ? m2 : Lk;
+            cc = cc < Rk ? cc : Rk;
+            v = cc > m1 + 1u ? cc : m1 + 1u;
+            if (v == kNoKey) v = kNoKey - 1u;          // kNoKey is reserved for "no proposal anywhere"
+            atomicMin(&claim[x], m1);
+            atomicMin(&claim[j], m1);
+        }
+        group_sync();
+        if (valid) {
+            uint32_t lowest = claim[x];
+            const uint32_t cj = claim[j];
+            lowest = cj < lowest ? cj : lowest;
+            if (q != kNoPrev) { const uint32_t cq = claim[q]; lowest = cq < lowest ? cq : lowest; }
+            if (k < m) { const uint32_t ck = claim[k]; lowest = ck < lowest ? ck : lowest; }
+            if (lowest < m1) v = m1;                   // someone earlier touches my neighbourhood: the round ends before me
+        }
+        // -- cut = min over the group
+        uint32_t cut = __reduce_min_sync(kFull, v);
+        if (kWarps > 1) {
+            uint32_t* red = s_red + (round & 1u) * kWarps;
+            if (lane == 0) red[wid] = cut;
+            __syncthreads();
+            cut = red[0];
+#pragma unroll
+            for (uint32_t w = 1; w < kWarps; ++w) { const uint32_t o = red[w]; cut = o < cut ? o : cut; }
+        } else {
+            __syncwarp();
+        }
+        if (cut == kNoKey) break;
+        // -- apply what was taken; withdraw the claims
+        if (valid) {
+            claim[x] = kNoKey; claim[j] = kNoKey;
+            if (m1 < cut) {
+                id[x] = r; id[j] = kNone;
+                kk[j] = kNoKey; kk[x] = Rk;
+                link[x] = (k << 16) | q;
+                if (k < m) link[k] = (link[k] & 0xFFFF0000u) | x;
+                if (q != kNoPrev) kk[q] = Lk;
+            }
+        }
+        group_sync();
+    }
+}
+
 // phase B for pieces that live in shared memory (m <= kMedSmem): every lane owns at most 8 parts and simply re-reads
 // them each round -- cheaper than maintaining cached minima when a chunk is this small.
 __device__ __forceinline__ void list_rounds_small(const TablesView& T, uint32_t* id, uint32_t* rk, uint32_t* link, uint32_t* nid,
@@ -889,11 +989,41 @@ __device__ __forceinline__ void list_rounds_small(const TablesView& T, uint32_t*
     }
 }
 
+// one flag per surviving part of a piece (dead slots hold kNone); order along the piece's slice is token order.
+// copy_to != nullptr: the state lives in shared memory, the ids go to the slice as well.
+__device__ __forceinline__ void flag_parts(const uint32_t* id, uint32_t* copy_to, uint32_t m, uint64_t start,
+                                           uint32_t* __restrict__ tok_bits, DeviceStatus* status, uint32_t lane) {
+    for (uint32_t base = 0; base < m; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t v = (i < m) ? id[i] : kNone;
+        const bool alive = v != kNone;
+        if (alive && copy_to) copy_to[i] = v;
+        const uint32_t A = __ballot_sync(kFull, alive);
+        if (lane == 0 && A) {
+            atomicAdd(&status->long_tokens, static_cast<unsigned long long>(__popc(A)));
+            const uint64_t pos = start + base;
+            const uint32_t sh = static_cast<uint32_t>(pos & 31);
+            atomicOr(&tok_bits[pos >> 5], A << sh);
+            if (sh && (A >> (32 - sh))) atomicOr(&tok_bits[(pos >> 5) + 1], A >> (32 - sh));
+        }
+    }
+}
+
+constexpr uint32_t kDeferMaxParts = 4096;   // K2c: parts whose merge state fits 64 KB of shared memory
+constexpr uint32_t kListSmemBytes = kDeferMaxParts * 16;
+constexpr uint32_t kListMaxRank = (1u << 20) - 1u;   // K2c packs rank << 12 | position into 32 bits
+
+#ifdef CUSIM_EMULATOR
+#define CFBPE_DYN_SMEM(name) uint32_t* const name = reinterpret_cast<uint32_t*>(cusim::dyn_smem())
+#else
+#define CFBPE_DYN_SMEM(name) extern __shared__ __align__(16) uint32_t name[]
+#endif
+
 // One warp per CTA: a warp that is deep in the serial chain of a long piece then holds one warp's worth of registers and
 // 6 KB of shared memory, not a whole CTA's, so the tail of this kernel can share the SMs with whatever runs next.
 constexpr uint32_t kLongWarps = 1;
 __global__ void __launch_bounds__(kLongWarps * 32)
-bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
+bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
     __shared__ uint32_t s_subr[kLongWarps][8][32];   // [warp][sub-chunk][lane] cached minimum rank ...
     __shared__ uint32_t s_subp[kLongWarps][8][32];   // ... and its position (phase B)
@@ -906,7 +1036,8 @@ bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
         if (lane == 0) item = atomicAdd(&status->long_next, 1u);
         item = __shfl_sync(kFull, item, 0);
         if (item >= n_all) break;
-        const LongPiece lp = long_list[item < n_big ? long_cap - 1 - item : item - n_big];
+        const uint32_t slot = item < n_big ? long_cap - 1 - item : item - n_big;
+        const LongPiece lp = long_list[slot];
         const TablesView T = vs.v[lp.vocab];
         const uint8_t* __restrict__ p = b.bytes + lp.start;
         const uint32_t n = static_cast<uint32_t>(lp.end - lp.start);
@@ -1007,12 +1138,23 @@ bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
             if (rmin != kNone && merged * 8u < m && m > 32u && m <= kListMax) { list_mode = true; break; }
         }
 
-        // ---- phase B: linked list, one merge per round
+        // ---- phase B: linked list
         if (list_mode) {
             // pieces in shared memory: a single-merge round is a short chain there (measured: the ordered take-loop of the
-            // multi-merge round costs more than it saves); pieces in global scratch: every round is several L2 round
-            // trips, so taking ~6 merges per round pays
+            // multi-merge round costs more than it saves).  Bigger pieces: every round from global scratch is several L2
+            // round trips per lane, so their list phase is left to bpe_list_kernel, which gives one warp 64 KB of shared
+            // memory for it; only pieces too big even for that stay here.
+#ifdef CFBPE_SMALL_SINGLE_MERGE
             if (in_smem) list_rounds_small(T, id, rk, a0, a1, m, lane);
+#else
+            if (in_smem) list_rounds_par<1, 8>(T, id, rk, a0, a1, m, nullptr);
+#endif
+#ifndef CFBPE_NO_DEFER
+            else if (m <= kDeferMaxParts && T.n_ranks < kListMaxRank) {
+                if (lane == 0) long_list[slot].pad = m;
+                continue;
+            }
+#endif
 #ifdef CFBPE_SINGLE_MERGE_ROUNDS
             else list_rounds(T, id, rk, a0, a1, m, &s_subr[threadIdx.x >> 5][0][lane], &s_subp[threadIdx.x >> 5][0][lane], lane);
 #else
@@ -1020,21 +1162,47 @@ bpe_long_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
 #endif
             __syncwarp();
         }
-        // ---- one flag per surviving part (dead slots hold kNone); order along the slice is token order
-        for (uint32_t base = 0; base < m; base += 32) {
-            const uint32_t i = base + lane;
-            const bool alive = (i < m) && id[i] != kNone;
-            if (alive && in_smem) gid[i] = id[i];
-            const uint32_t A = __ballot_sync(kFull, alive);
-            if (lane == 0 && A) {
-                atomicAdd(&status->long_tokens, static_cast<unsigned long long>(__popc(A)));
-                const uint64_t pos = lp.start + base;
-                const uint32_t sh = static_cast<uint32_t>(pos & 31);
-                atomicOr(&tok_bits[pos >> 5], A << sh);
-                if (sh && (A >> (32 - sh))) atomicOr(&tok_bits[(pos >> 5) + 1], A >> (32 - sh));
-            }
-        }
+        flag_parts(id, in_smem ? gid : nullptr, m, lp.start, tok_bits, status, lane);
         __syncwarp();
+    }
+}
+
+// K2c: the list phase of the pieces K2b deferred (more than kMedSmem bytes, at most kDeferMaxParts parts left after the
+// batched rounds).  One CTA of kListWarps warps per piece with the whole merge state -- id | key | link | claim, 16 bytes
+// per part -- in 64 KB of dynamic shared memory, parallel-cut rounds (list_rounds_par): a round costs one table round trip
+// and a few hundred cycles of shared-memory work and takes ~20 merges.  Three such CTAs fit an SM.  Tickets run over the
+// big end of the long-piece list.
+constexpr uint32_t kListWarps = 8;
+__global__ void __launch_bounds__(kListWarps * 32)
+bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
+                uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
+    CFBPE_DYN_SMEM(s_dyn);
+    __shared__ uint32_t s_red[2 * kListWarps];
+    __shared__ uint32_t s_item;
+    const uint32_t n_big = status->long_overflow ? 0u : status->n_big;
+    uint32_t* const id = s_dyn;
+    uint32_t* const kk = s_dyn + kDeferMaxParts;
+    uint32_t* const link = s_dyn + 2 * kDeferMaxParts;
+    uint32_t* const claim = s_dyn + 3 * kDeferMaxParts;
+    (void)b;
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(&status->defer_next, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        __syncthreads();
+        if (item >= n_big) break;
+        const LongPiece lp = long_list[long_cap - 1 - item];
+        const uint32_t m = lp.pad;
+        if (!m) continue;
+        const TablesView T = vs.v[lp.vocab];
+        uint32_t* const gid = ids_by_pos + lp.start;
+        const uint32_t* const grk = sc.rank + lp.start;
+        for (uint32_t i = threadIdx.x; i < m; i += kListWarps * 32) { id[i] = gid[i]; kk[i] = grk[i]; }
+        __syncthreads();
+        list_rounds_par<kListWarps, 12>(T, id, kk, link, claim, m, s_red);
+        __syncthreads();
+        if (threadIdx.x < 32) flag_parts(id, gid, m, lp.start, tok_bits, status, threadIdx.x);
+        __syncthreads();
     }
 }
 

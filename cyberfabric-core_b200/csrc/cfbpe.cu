@@ -340,6 +340,7 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     const uint64_t nw = n_flag_words(mb) + 4 + 4 * kMaxPipeChunks;      // + per-sub-batch slack of a pipelined call
     const uint64_t nt = n_scan_tiles(mb) + 1 + 2 * kMaxPipeChunks;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(bpe_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kListSmemBytes)) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_bytes, mb + 256) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_offsets, mp + 1 + kMaxPipeChunks) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_vocab_ids, mp + 1) == cudaSuccess;

@@ -34,7 +34,7 @@ inline uint32_t n_scan_tiles(uint64_t total_bytes) {
 // The path in stages, so that a caller with more than one stream can overlap the latency-bound long-piece kernel with
 // the throughput-bound short-piece kernel (and, in a pipelined host call, with the next sub-batch):
 //   split   zero the flags, K1 split, find the long pieces (K2 in scan mode)
-//   long    K2b: pieces longer than 32 bytes                       } independent of each other:
+//   long    K2b (+ K2c): pieces longer than 32 bytes               } independent of each other:
 //   short   K2: whole-piece lookups and in-lane merges (<= 32 B)   } may run on two streams
 //   back    flag_count, tile_scan (chained on the previous sub-batch's token total), emit, prompt offsets
 template <typename Stream, typename Prof>
@@ -76,6 +76,10 @@ inline void enqueue_long(const BatchView& b, const VocabSet& vs, const Workspace
     if (!b.total_bytes) return;
     CFBPE_MARK(prof, K_LONG, stream, true);
     CFBPE_LAUNCH(bpe_long_kernel, long_grid * (8 / kLongWarps), kLongWarps * 32, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
+#ifndef CFBPE_NO_DEFER
+    // the list phase of the big pieces K2b deferred: three 64 KB CTAs per SM (long_grid = 4 x SM count)
+    CFBPE_LAUNCH_SMEM(bpe_list_kernel, long_grid - long_grid / 4, kListWarps * 32, kListSmemBytes, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
+#endif
     CFBPE_MARK(prof, K_LONG, stream, false);
 }
 

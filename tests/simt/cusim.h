@@ -10,6 +10,7 @@
 //
 // This is not a CPU fallback: libcfbpe.so contains none of it and fails without a device.
 #pragma once
+#define CUSIM_EMULATOR 1
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>

@@ -104,6 +104,7 @@ def test_adversarial_rank_orders(seed):
     ov = oracle.OracleVocab(rf)
     sv = simlib.SimVocab(rf, 0, 0, 0)
     prompts = [t.encode() for t in synth_vocab.make_texts(100 + seed, 250)]
+    prompts += [t.encode() for t in synth_vocab.make_texts(200 + seed, 10, max_len=3000)]   # list phase in bpe_list_kernel
     nlong = check_batch(sv, ov, 0, prompts)
     assert nlong > 50
 
@@ -113,7 +114,7 @@ def test_long_random_words_list_mode(sim_vocabs, oracle_vocabs):
     rng = random.Random(5)
     letters = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
     prompts = []
-    for n in [33, 40, 64, 65, 100, 257, 600, 1500, 4096]:
+    for n in [33, 40, 64, 65, 100, 257, 600, 1500, 4096, 6100]:   # 6100: too big for bpe_list_kernel, stays in K2b
         prompts.append("".join(rng.choice(letters) for _ in range(n)).encode())
         prompts.append("".join(rng.choice("etaoinshr") for _ in range(n)).encode())
         prompts.append(("xyz" * n)[:n].encode())
