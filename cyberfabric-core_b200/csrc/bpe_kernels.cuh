@@ -80,6 +80,36 @@ __device__ __forceinline__ void or_bits(uint32_t* __restrict__ words, uint64_t w
     if (bits) atomicOr(&words[word], bits);
 }
 
+// end of the run of bytes equal to c that starts at pos (pos < pe, s[pos] == c need not hold): first position in
+// [pos, pe) whose byte differs, 16 bytes per load once aligned
+__device__ __forceinline__ uint64_t same_byte_run_end(const uint8_t* __restrict__ s, uint64_t pos, uint64_t pe, uint32_t c) {
+    uint64_t e = pos;
+    while (e < pe && (reinterpret_cast<uintptr_t>(s + e) & 15u)) { if (s[e] != c) return e; ++e; }
+    const uint32_t w = c * 0x01010101u;
+    while (e + 16 <= pe) {
+        const uint4 v = *reinterpret_cast<const uint4*>(s + e);
+        if (v.x != w || v.y != w || v.z != w || v.w != w) break;
+        e += 16;
+    }
+    while (e < pe && s[e] == c) ++e;
+    return e;
+}
+__device__ __forceinline__ bool four_ascii_digits(uint32_t w) {
+    const uint32_t t = w ^ 0x30303030u;                       // a digit byte becomes 0..9
+    return ((((t & 0x7F7F7F7Fu) + 0x76767676u) | t) & 0x80808080u) == 0u;
+}
+__device__ __forceinline__ uint64_t ascii_digit_run_end(const uint8_t* __restrict__ s, uint64_t pos, uint64_t pe) {
+    uint64_t e = pos;
+    while (e < pe && (reinterpret_cast<uintptr_t>(s + e) & 15u)) { if ((s[e] - '0') >= 10u) return e; ++e; }
+    while (e + 16 <= pe) {
+        const uint4 v = *reinterpret_cast<const uint4*>(s + e);
+        if (!(four_ascii_digits(v.x) && four_ascii_digits(v.y) && four_ascii_digits(v.z) && four_ascii_digits(v.w))) break;
+        e += 16;
+    }
+    while (e < pe && (s[e] - '0') < 10u) ++e;
+    return e;
+}
+
 // ---------------------------------------------------------------------------------------
 // K1: pre-tokenizer split.  One thread per kSplitChunk bytes.  A thread starts at the first sync
 // point of its chunk (prompt start or is_sync_point) and runs the table-driven automaton of
@@ -131,10 +161,10 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
     uint64_t cur_word = pos >> 5;
     uint32_t cur_bits = 0;
     for (;;) {
-        uint32_t x, len;
+        uint32_t x, len, b0 = 0x100u;
         if (pos == pe) { x = X_EOT; len = 0; }
         else {
-            const uint32_t b0 = s[pos];
+            b0 = s[pos];
             if (b0 < 0x80) { x = s_ascii[b0]; len = 1; }
             else { const Ch c = get_char(s, pos, pe, uc, &bad); x = c.cls; len = c.len; }
         }
@@ -190,6 +220,33 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
                 nlet = x_is_letter(x) ? (nlet < 3 ? nlet + 1 : 3u) : 0u;
                 npun = x_is_run_punct(x, (pat & 1u) != 0) ? (npun < 2 ? npun + 1 : 2u) : 0u;
             } else { nlet = 0; npun = 0; }
+            // ---- runs that hold no sync point -- one whitespace byte repeated, ASCII digits -- are taken in bulk: the one
+            //      thread that entered such a run would otherwise walk it a character per iteration (~200 cycles each,
+            //      nothing else to hide the latency) while the rest of the grid has long finished
+            if (b0 < 0x80u && pos < pe) {
+                if ((x == X_SPACE || x == X_CRLF || x == X_WS) && s[pos] == b0) {
+                    const uint32_t a2 = tab[state * X_COUNT + x];
+                    if ((a2 & A_STATE_MASK) == state && !(a2 & (A_B_NOW | A_EMIT_ALC | A_EMIT_LAST | A_EMIT_LBE | A_CONTR))) {
+                        const uint64_t e = same_byte_run_end(s, pos, pe, b0);    // self-loop: only the remembered positions move
+                        if (a2 & A_SET_ALC) alc = e;
+                        if (a2 & A_SET_LAST) last = e - 1;
+                        if (a2 & A_SET_LBE) lbe = e;
+                        pos = e; prevx = x; nlet = 0; npun = 0;
+                    }
+                } else if (x == X_N && state >= S_D1 && state <= S_D3 && (s[pos] - '0') < 10u) {
+                    // \p{N}{1,md}: a boundary every md digits, counted from the start of the run
+                    const uint32_t md = (tab[S_D1 * X_COUNT + X_N] & A_B_NOW) ? 1u : ((tab[S_D2 * X_COUNT + X_N] & A_B_NOW) ? 2u : 3u);
+                    const uint64_t e = ascii_digit_run_end(s, pos, pe);
+                    const uint32_t d = state - S_D1 + 1u;                        // digits in the current piece so far
+                    for (uint64_t p = pos + (md - d); p < e; p += md) {
+                        const uint64_t w = p >> 5;
+                        if (w != cur_word) { or_bits(piece_bits, cur_word, cur_bits); cur_word = w; cur_bits = 0; }
+                        cur_bits |= 1u << (p & 31);
+                    }
+                    state = S_D1 + static_cast<uint32_t>((d - 1u + (e - pos)) % md);
+                    pos = e; prevx = X_N; nlet = 0; npun = 0;
+                }
+            }
         }
     }
     or_bits(piece_bits, cur_word, cur_bits);

@@ -152,3 +152,30 @@ def test_split_long_runs_across_chunks(pat):
     assert rc == 0
     bad = [(p, e) for p, e in zip(strs, ends) if oracle.split(pat, p).tolist() != e]
     assert not bad, bad[:3]
+
+
+@pytest.mark.parametrize("pat", [0, 1, 2, 3])
+def test_split_bulk_runs(pat):
+    """runs of one whitespace byte and of ASCII digits are consumed in bulk by K1 (they hold no sync point): every
+    run length modulo 3 and modulo 16, every alignment, every kind of neighbour"""
+    import random
+    rng = random.Random(70 + pat)
+    glue = ["a", "B", "中", "1", "٣", " ", "\t", "\n", "\r\n", "'s", "/", "!", "x y", "", " ", "　"]
+    strs = []
+    for _ in range(1200):
+        parts = []
+        for _ in range(rng.randint(1, 6)):
+            k = rng.randint(0, 5)
+            n = rng.choice([1, 2, 3, 4, 5, 15, 16, 17, 31, 32, 33, 63, 64, 65, rng.randint(1, 300)])
+            if k == 0: parts.append(" " * n)
+            elif k == 1: parts.append("\n" * n)
+            elif k == 2: parts.append("\t" * n)
+            elif k == 3: parts.append("".join(rng.choice("0123456789") for _ in range(n)))
+            elif k == 4: parts.append("\r" * n)
+            else: parts.append("".join(rng.choice(" \n\t\r") for _ in range(n)))
+            parts.append(rng.choice(glue))
+        strs.append("".join(parts).encode())
+    rc, ends = simlib.split([pat], strs)
+    assert rc == 0
+    bad = [(p, e) for p, e in zip(strs, ends) if oracle.split(pat, p).tolist() != e]
+    assert not bad, bad[:3]
