@@ -24,6 +24,16 @@
 namespace cfbpe {
 
 constexpr uint32_t kMaxVocabs = 8;
+// path counters for the emulator tests (which path did a test actually exercise); nothing on the device
+#ifdef CUSIM_EMULATOR
+inline unsigned long long* dbg_counters() { static unsigned long long c[8]; return c; }
+#define CFBPE_DBG_COUNT(i) (++dbg_counters()[i])
+#else
+#define CFBPE_DBG_COUNT(i) ((void)0)
+#endif
+// 0: pieces deferred to bpe_list_kernel  1: list -> batched switches (medium pieces)  2: the same in bpe_list_kernel
+// 3: K1 bulk whitespace runs  4: K1 bulk digit runs  5: pieces on the global-memory list path
+
 #ifndef CFBPE_SPLIT_CHUNK
 #define CFBPE_SPLIT_CHUNK 64
 #endif
@@ -227,6 +237,7 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
                 if ((x == X_SPACE || x == X_CRLF || x == X_WS) && s[pos] == b0) {
                     const uint32_t a2 = tab[state * X_COUNT + x];
                     if ((a2 & A_STATE_MASK) == state && !(a2 & (A_B_NOW | A_EMIT_ALC | A_EMIT_LAST | A_EMIT_LBE | A_CONTR))) {
+                        CFBPE_DBG_COUNT(3);
                         const uint64_t e = same_byte_run_end(s, pos, pe, b0);    // self-loop: only the remembered positions move
                         if (a2 & A_SET_ALC) alc = e;
                         if (a2 & A_SET_LAST) last = e - 1;
@@ -236,6 +247,7 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
                 } else if (x == X_N && state >= S_D1 && state <= S_D3 && (s[pos] - '0') < 10u) {
                     // \p{N}{1,md}: a boundary every md digits, counted from the start of the run
                     const uint32_t md = (tab[S_D1 * X_COUNT + X_N] & A_B_NOW) ? 1u : ((tab[S_D2 * X_COUNT + X_N] & A_B_NOW) ? 2u : 3u);
+                    CFBPE_DBG_COUNT(4);
                     const uint64_t e = ascii_digit_run_end(s, pos, pe);
                     const uint32_t d = state - S_D1 + 1u;                        // digits in the current piece so far
                     for (uint64_t p = pos + (md - d); p < e; p += md) {
@@ -712,6 +724,78 @@ __device__ __forceinline__ bool select_chunk(uint32_t r, uint32_t rmin, uint32_t
     return sel;
 }
 
+// One batched round (phase A) by ONE warp on the compact arrays id[] / rk[] of m parts: merges every non-overlapping
+// occurrence (leftmost first) of the minimum rank rmin, cut after the leftmost merge that creates a pair ranking below
+// rmin (the sequential loop would take that pair next).  a0 / a1 are scratch of m words.  Leaves dead slots (id == kNone)
+// for array_compact().
+__device__ __forceinline__ void array_round(const TablesView& T, uint32_t* id, uint32_t* rk, uint32_t* a0, uint32_t* a1,
+                                            uint32_t m, uint32_t rmin, uint32_t lane) {
+    // A1: select, look up the pairs each merge creates, find the cut
+    uint32_t carry = 0, prevS = 0, cut = kNone;
+    for (uint32_t base = 0; base < m && cut == kNone; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t r = (i + 1 < m) ? rk[i] : kNone;
+        uint32_t S;
+        const bool sel = select_chunk(r, rmin, lane, carry, S);
+        bool viol = false;
+        if (sel) {
+            const bool selm2 = (lane >= 2) ? ((S >> (lane - 2)) & 1u) : ((prevS >> (30 + lane)) & 1u);
+            uint32_t L = kNone, R = kNone;
+            if (i > 0) L = pair_lookup(T, selm2 ? rmin : id[i - 1], rmin);
+            if (i + 2 < m) R = pair_lookup(T, rmin, id[i + 2]);
+            a0[i] = L;
+            a1[i] = R;
+            viol = (L < rmin) || (R < rmin);
+        }
+        const uint32_t V = __ballot_sync(kFull, viol);
+        if (V) cut = base + (__ffs(V) - 1);
+        prevS = S;
+    }
+    __syncwarp();
+    // A2: apply the merges up to the cut, in place (two sub-steps per chunk: right ranks, then left ranks)
+    carry = 0; prevS = 0;
+    for (uint32_t base = 0; base < m && base <= cut; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t r = (i + 1 < m) ? rk[i] : kNone;
+        uint32_t S;
+        const bool sel = select_chunk(r, rmin, lane, carry, S);
+        const bool app = sel && i <= cut;
+        const bool selm2 = (lane >= 2) ? ((S >> (lane - 2)) & 1u) : ((prevS >> (30 + lane)) & 1u);
+        uint32_t L = kNone;
+        if (app) {
+            L = a0[i];
+            id[i] = rmin;             // rank == id of the merged token
+            id[i + 1] = kNone;        // partner dies
+            rk[i] = a1[i];
+        }
+        __syncwarp();
+        if (app && i > 0) rk[selm2 ? i - 2 : i - 1] = L;
+        __syncwarp();
+        prevS = S;
+    }
+}
+// squeeze the dead slots out (one warp); kPosBits != 0: rk[] holds list-mode keys, turned back into ranks.
+// Returns the new part count; rmin_out = the smallest rank left.
+template <uint32_t kPosBits>
+__device__ __forceinline__ uint32_t array_compact(uint32_t* id, uint32_t* rk, uint32_t m, uint32_t lane, uint32_t& rmin_out) {
+    uint32_t out = 0, nmin = kNone;
+    for (uint32_t base = 0; base < m; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t myid = (i < m) ? id[i] : kNone;
+        uint32_t myrk = (i < m) ? rk[i] : kNone;
+        if (kPosBits && myrk != kNone) myrk >>= kPosBits;      // kNoKey == kNone
+        const bool keep = myid != kNone;
+        const uint32_t K = __ballot_sync(kFull, keep);
+        const uint32_t pos = out + __popc(K & lanemask_lt(lane));
+        __syncwarp();
+        if (keep) { id[pos] = myid; rk[pos] = myrk; nmin = myrk < nmin ? myrk : nmin; }
+        out += __popc(K);
+    }
+    __syncwarp();
+    rmin_out = warp_min_u32(nmin);
+    return out;
+}
+
 // phase B: linked list over the compact array, ONE merge per round (exact sequential order).  The round is a
 // dependent chain  argmin -> link[i] -> {link[j], nid[j], id[q]} -> two table probes -> cached minima,  so the
 // data is laid out to keep that chain short:
@@ -920,8 +1004,12 @@ __device__ __forceinline__ void list_rounds_multi(const TablesView& T, uint32_t*
 // checks the rule against the sequential loop on random rank orders.
 // On entry id[] / kk[] hold the ids and RANKS of the compact parts; kk[] is converted to keys here.
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
+// Returns true when no pair is left.  Pairs of ONE rank are strictly ordered by position, so a stretch of them (a period,
+// "xyzxyz...") goes one merge per round here: after three rounds in a row that were cut by a pair of the rank just taken
+// the function returns false and the caller does a batched round (array_compact + array_round), which takes them all.
+// s_red: 2 * kWarps + 2 words of shared memory (kWarps > 1 only).
 template <uint32_t kWarps, uint32_t kPosBits>
-__device__ __forceinline__ void list_rounds_par(const TablesView& T, uint32_t* id, uint32_t* kk, uint32_t* link, uint32_t* claim,
+__device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* id, uint32_t* kk, uint32_t* link, uint32_t* claim,
                                                 uint32_t m, uint32_t* s_red) {
     constexpr uint32_t kNoPrev = 0xFFFFu, kPosMask = (1u << kPosBits) - 1u, P = kWarps * 32;
     const uint32_t tid = threadIdx.x % P, lane = tid & 31, wid = tid >> 5;
@@ -932,7 +1020,10 @@ __device__ __forceinline__ void list_rounds_par(const TablesView& T, uint32_t* i
         link[i] = ((i + 1) << 16) | (i ? i - 1 : kNoPrev);
         claim[i] = kNoKey;
     }
+    uint32_t* const eq_flag = s_red + 2 * kWarps;     // [2], by round parity
+    if (kWarps > 1 && tid == 0) { eq_flag[0] = 0; eq_flag[1] = 0; }
     group_sync();
+    uint32_t eq_run = 0;
     uint32_t c = (m + P - 1) / P;
     if (c > 1) c |= 1u;                               // odd: the threads' chunks start in different banks
     const uint32_t lo = tid * c < m ? tid * c : m;
@@ -968,6 +1059,7 @@ __device__ __forceinline__ void list_rounds_par(const TablesView& T, uint32_t* i
             atomicMin(&claim[j], m1);
         }
         group_sync();
+        if (kWarps > 1 && tid == 0) eq_flag[(round + 1u) & 1u] = 0;    // nobody reads or sets the other flag any more
         if (valid) {
             uint32_t lowest = claim[x];
             const uint32_t cj = claim[j];
@@ -988,7 +1080,11 @@ __device__ __forceinline__ void list_rounds_par(const TablesView& T, uint32_t* i
         } else {
             __syncwarp();
         }
-        if (cut == kNoKey) break;
+        if (cut == kNoKey) return true;
+        // -- a pair of the rank I just took ended the round (not the pair my own merge creates): same-rank stretch
+        bool eq = valid && m1 < cut && cut != m1 + 1u && (cut >> kPosBits) == (m1 >> kPosBits);
+        if (kWarps == 1) eq = __any_sync(kFull, eq);
+        else if (eq) eq_flag[round & 1u] = 1u;
         // -- apply what was taken; withdraw the claims
         if (valid) {
             claim[x] = kNoKey; claim[j] = kNoKey;
@@ -1001,6 +1097,9 @@ __device__ __forceinline__ void list_rounds_par(const TablesView& T, uint32_t* i
             }
         }
         group_sync();
+        if (kWarps > 1) eq = eq_flag[round & 1u] != 0u;
+        eq_run = eq ? eq_run + 1u : 0u;
+        if (eq_run >= 3u) return false;
     }
 }
 
@@ -1129,96 +1228,44 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
         rmin = warp_min_u32(rmin);
         __syncwarp();
 
-        // ---- phase A: batched rounds on the compact array
-        bool list_mode = false;
+        // ---- rounds: batched rounds on the compact array while they merge a useful fraction (runs, periods: O(log n)
+        //      rounds), list rounds otherwise; a list phase that meets many pairs of one rank comes back for a batched round
+        bool deferred = false;
         while (rmin != kNone) {
-            // A1: select, look up the pairs each merge creates, find the cut
-            uint32_t carry = 0, prevS = 0, cut = kNone;
-            for (uint32_t base = 0; base < m && cut == kNone; base += 32) {
-                const uint32_t i = base + lane;
-                const uint32_t r = (i + 1 < m) ? rk[i] : kNone;
-                uint32_t S;
-                const bool sel = select_chunk(r, rmin, lane, carry, S);
-                bool viol = false;
-                if (sel) {
-                    const bool selm2 = (lane >= 2) ? ((S >> (lane - 2)) & 1u) : ((prevS >> (30 + lane)) & 1u);
-                    uint32_t L = kNone, R = kNone;
-                    if (i > 0) L = pair_lookup(T, selm2 ? rmin : id[i - 1], rmin);
-                    if (i + 2 < m) R = pair_lookup(T, rmin, id[i + 2]);
-                    a0[i] = L;
-                    a1[i] = R;
-                    viol = (L < rmin) || (R < rmin);
-                }
-                const uint32_t V = __ballot_sync(kFull, viol);
-                if (V) cut = base + (__ffs(V) - 1);
-                prevS = S;
-            }
-            __syncwarp();
-            // A2: apply the merges up to the cut, in place (two sub-steps per chunk: right ranks, then left ranks)
-            carry = 0; prevS = 0;
-            for (uint32_t base = 0; base < m && base <= cut; base += 32) {
-                const uint32_t i = base + lane;
-                const uint32_t r = (i + 1 < m) ? rk[i] : kNone;
-                uint32_t S;
-                const bool sel = select_chunk(r, rmin, lane, carry, S);
-                const bool app = sel && i <= cut;
-                const bool selm2 = (lane >= 2) ? ((S >> (lane - 2)) & 1u) : ((prevS >> (30 + lane)) & 1u);
-                uint32_t L = kNone;
-                if (app) {
-                    L = a0[i];
-                    id[i] = rmin;             // rank == id of the merged token
-                    id[i + 1] = kNone;        // partner dies
-                    rk[i] = a1[i];
-                }
-                __syncwarp();
-                if (app && i > 0) rk[selm2 ? i - 2 : i - 1] = L;
-                __syncwarp();
-                prevS = S;
-            }
-            // A3: compact, and take the minimum of the new ranks
-            uint32_t out = 0, nmin = kNone;
-            for (uint32_t base = 0; base < m; base += 32) {
-                const uint32_t i = base + lane;
-                const uint32_t myid = (i < m) ? id[i] : kNone;
-                const uint32_t myrk = (i < m) ? rk[i] : kNone;
-                const bool keep = myid != kNone;
-                const uint32_t K = __ballot_sync(kFull, keep);
-                const uint32_t pos = out + __popc(K & lanemask_lt(lane));
-                __syncwarp();
-                if (keep) { id[pos] = myid; rk[pos] = myrk; nmin = myrk < nmin ? myrk : nmin; }
-                out += __popc(K);
-            }
-            __syncwarp();
-            const uint32_t merged = m - out;
-            m = out;
-            rmin = warp_min_u32(nmin);
-            if (rmin != kNone && merged * 8u < m && m > 32u && m <= kListMax) { list_mode = true; break; }
-        }
-
-        // ---- phase B: linked list
-        if (list_mode) {
-            // pieces in shared memory: a single-merge round is a short chain there (measured: the ordered take-loop of the
-            // multi-merge round costs more than it saves).  Bigger pieces: every round from global scratch is several L2
-            // round trips per lane, so their list phase is left to bpe_list_kernel, which gives one warp 64 KB of shared
-            // memory for it; only pieces too big even for that stay here.
+            array_round(T, id, rk, a0, a1, m, rmin, lane);
+            const uint32_t before = m;
+            m = array_compact<0>(id, rk, m, lane, rmin);
+            const uint32_t merged = before - m;
+            if (rmin == kNone || merged * 8u >= m || m <= 32u || m > kListMax) continue;
+            // -- list phase
+            if (in_smem) {
 #ifdef CFBPE_SMALL_SINGLE_MERGE
-            if (in_smem) list_rounds_small(T, id, rk, a0, a1, m, lane);
+                list_rounds_small(T, id, rk, a0, a1, m, lane); break;
 #else
-            if (in_smem) list_rounds_par<1, 8>(T, id, rk, a0, a1, m, nullptr);
-#endif
-#ifndef CFBPE_NO_DEFER
-            else if (m <= kDeferMaxParts && T.n_ranks < kListMaxRank) {
-                if (lane == 0) long_list[slot].pad = m;
+                if (list_rounds_par<1, 8>(T, id, rk, a0, a1, m, nullptr)) break;
+                if (lane == 0) CFBPE_DBG_COUNT(1);
+                m = array_compact<8>(id, rk, m, lane, rmin);
                 continue;
+#endif
+            }
+#ifndef CFBPE_NO_DEFER
+            if (m <= kDeferMaxParts && T.n_ranks < kListMaxRank) {   // bpe_list_kernel goes on from here, in shared memory
+                if (lane == 0) { long_list[slot].pad = m; CFBPE_DBG_COUNT(0); }
+                deferred = true;
+                break;
             }
 #endif
 #ifdef CFBPE_SINGLE_MERGE_ROUNDS
-            else list_rounds(T, id, rk, a0, a1, m, &s_subr[threadIdx.x >> 5][0][lane], &s_subp[threadIdx.x >> 5][0][lane], lane);
+            list_rounds(T, id, rk, a0, a1, m, &s_subr[threadIdx.x >> 5][0][lane], &s_subp[threadIdx.x >> 5][0][lane], lane);
 #else
-            else list_rounds_multi(T, id, rk, a0, a1, m, lane);
+            if (lane == 0) CFBPE_DBG_COUNT(5);
+            list_rounds_multi(T, id, rk, a0, a1, m, lane);
 #endif
             __syncwarp();
+            break;
         }
+        if (deferred) continue;
+        __syncwarp();
         flag_parts(id, in_smem ? gid : nullptr, m, lp.start, tok_bits, status, lane);
         __syncwarp();
     }
@@ -1234,8 +1281,8 @@ __global__ void __launch_bounds__(kListWarps * 32)
 bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
     CFBPE_DYN_SMEM(s_dyn);
-    __shared__ uint32_t s_red[2 * kListWarps];
-    __shared__ uint32_t s_item;
+    __shared__ uint32_t s_red[2 * kListWarps + 2];
+    __shared__ uint32_t s_item, s_m, s_rmin;
     const uint32_t n_big = status->long_overflow ? 0u : status->n_big;
     uint32_t* const id = s_dyn;
     uint32_t* const kk = s_dyn + kDeferMaxParts;
@@ -1249,14 +1296,34 @@ bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
         __syncthreads();
         if (item >= n_big) break;
         const LongPiece lp = long_list[long_cap - 1 - item];
-        const uint32_t m = lp.pad;
+        uint32_t m = lp.pad;
         if (!m) continue;
         const TablesView T = vs.v[lp.vocab];
         uint32_t* const gid = ids_by_pos + lp.start;
         const uint32_t* const grk = sc.rank + lp.start;
         for (uint32_t i = threadIdx.x; i < m; i += kListWarps * 32) { id[i] = gid[i]; kk[i] = grk[i]; }
         __syncthreads();
-        list_rounds_par<kListWarps, 12>(T, id, kk, link, claim, m, s_red);
+        for (;;) {
+            const bool done = list_rounds_par<kListWarps, 12>(T, id, kk, link, claim, m, s_red);
+            __syncthreads();
+            if (done) break;
+            // a stretch of same-rank pairs: batched rounds, by the first warp (their lookups are all the same few
+            // table slots, L1 hits; the passes over <= 4096 words of shared memory are a few microseconds)
+            if (threadIdx.x == 0) CFBPE_DBG_COUNT(2);
+            if (threadIdx.x < 32) {
+                uint32_t rmin, mm = array_compact<12>(id, kk, m, threadIdx.x, rmin);
+                while (rmin != kNone) {
+                    array_round(T, id, kk, link, claim, mm, rmin, threadIdx.x);
+                    const uint32_t before = mm;
+                    mm = array_compact<0>(id, kk, mm, threadIdx.x, rmin);
+                    if ((before - mm) * 8u < mm && mm > 32u) break;
+                }
+                if (threadIdx.x == 0) { s_m = mm; s_rmin = rmin; }
+            }
+            __syncthreads();
+            m = s_m;
+            if (s_rmin == kNone) break;
+        }
         __syncthreads();
         if (threadIdx.x < 32) flag_parts(id, gid, m, lp.start, tok_bits, status, threadIdx.x);
         __syncthreads();

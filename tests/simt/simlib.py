@@ -28,8 +28,15 @@ def lib():
         L.sim_encode_batch.restype = C.c_int
         L.sim_encode_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sim_dbg_counter.restype = C.c_ulonglong
+        L.sim_dbg_counter.argtypes = [C.c_uint32, C.c_int]
         _lib = L
     return _lib
+
+
+def dbg_counter(i, reset=False):
+    """path counters of csrc/bpe_kernels.cuh (emulator build only): which path did the kernels take"""
+    return int(lib().sim_dbg_counter(i, 1 if reset else 0))
 
 
 class SimVocab:

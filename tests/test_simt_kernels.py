@@ -175,7 +175,31 @@ def test_split_bulk_runs(pat):
             else: parts.append("".join(rng.choice(" \n\t\r") for _ in range(n)))
             parts.append(rng.choice(glue))
         strs.append("".join(parts).encode())
+    simlib.dbg_counter(3, reset=True); simlib.dbg_counter(4, reset=True)
     rc, ends = simlib.split([pat], strs)
     assert rc == 0
     bad = [(p, e) for p, e in zip(strs, ends) if oracle.split(pat, p).tolist() != e]
     assert not bad, bad[:3]
+    assert simlib.dbg_counter(3) > 100 and simlib.dbg_counter(4) > 100
+
+
+def test_periodic_pieces_switch_back_to_batched_rounds(sim_vocabs, oracle_vocabs):
+    """periods with a ragged tail or a foreign character inside: the list phase meets long stretches of one rank
+    (strictly ordered by position: one merge per round) and has to hand back to a batched round -- in the warp
+    kernel (<= 256 bytes) and in bpe_list_kernel (<= 4096 parts); beyond that the global-memory list path"""
+    import random
+    rng = random.Random(11)
+    letters = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
+    prompts = []
+    for n in [60, 130, 200, 256, 257, 700, 1800, 4096, 5200]:
+        for _ in range(6):
+            per = "".join(rng.choice(letters) for _ in range(rng.randint(2, 5)))
+            s = list((per * (n // len(per) + 1))[:n])
+            for _ in range(rng.randint(0, 3)):
+                s[rng.randrange(n)] = rng.choice(letters)
+            prompts.append("".join(s).encode())
+    for i in range(8): simlib.dbg_counter(i, reset=True)
+    check_batch(sim_vocabs[0], oracle_vocabs[0], 0, prompts)
+    check_batch(sim_vocabs[1], oracle_vocabs[1], 1, prompts)
+    assert simlib.dbg_counter(0) > 0 and simlib.dbg_counter(1) > 0 and simlib.dbg_counter(2) > 0 and simlib.dbg_counter(5) > 0, \
+        [simlib.dbg_counter(i) for i in range(8)]
