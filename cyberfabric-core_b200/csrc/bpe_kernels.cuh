@@ -232,8 +232,9 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
             } else { nlet = 0; npun = 0; }
             // ---- runs that hold no sync point -- one whitespace byte repeated, ASCII digits -- are taken in bulk: the one
             //      thread that entered such a run would otherwise walk it a character per iteration (~200 cycles each,
-            //      nothing else to hide the latency) while the rest of the grid has long finished
-            if (b0 < 0x80u && pos < pe) {
+            //      nothing else to hide the latency) while the rest of the grid has long finished.  Only beyond the end of
+            //      my chunk: inside it the walk is bounded anyway, and short runs (indentation, years) are cheaper per character
+            if (pos >= ce && b0 < 0x80u && pos < pe) {
                 if ((x == X_SPACE || x == X_CRLF || x == X_WS) && s[pos] == b0) {
                     const uint32_t a2 = tab[state * X_COUNT + x];
                     if ((a2 & A_STATE_MASK) == state && !(a2 & (A_B_NOW | A_EMIT_ALC | A_EMIT_LAST | A_EMIT_LBE | A_CONTR))) {
@@ -1007,7 +1008,7 @@ constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 // Returns true when no pair is left.  Pairs of ONE rank are strictly ordered by position, so a stretch of them (a period,
 // "xyzxyz...") goes one merge per round here: after three rounds in a row that were cut by a pair of the rank just taken
 // the function returns false and the caller does a batched round (array_compact + array_round), which takes them all.
-// s_red: 2 * kWarps + 2 words of shared memory (kWarps > 1 only).
+// s_red: 3 * kWarps + 2 words of shared memory (kWarps > 1 only).
 template <uint32_t kWarps, uint32_t kPosBits>
 __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* id, uint32_t* kk, uint32_t* link, uint32_t* claim,
                                                 uint32_t m, uint32_t* s_red) {
@@ -1099,7 +1100,25 @@ __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* i
         group_sync();
         if (kWarps > 1) eq = eq_flag[round & 1u] != 0u;
         eq_run = eq ? eq_run + 1u : 0u;
-        if (eq_run >= 3u) return false;
+        if (eq_run >= 3u) {
+            // how many pairs of that rank are there?  A batched round costs about as much as 3 (warp) to 20 (CTA) of these
+            // rounds: it has to take a fair share of the piece (random text repeats a pair a few times; that is not it)
+            const uint32_t er = cut >> kPosBits;
+            uint32_t cnt = 0;
+            for (uint32_t x = lo; x < hi; ++x) cnt += (kk[x] >> kPosBits) == er ? 1u : 0u;
+            cnt = __reduce_add_sync(kFull, cnt);
+            if (kWarps > 1) {
+                uint32_t* sum = s_red + 2 * kWarps + 2;
+                if (lane == 0) sum[wid] = cnt;
+                __syncthreads();
+                cnt = 0;
+#pragma unroll
+                for (uint32_t w = 0; w < kWarps; ++w) cnt += sum[w];
+                __syncthreads();
+            }
+            if (cnt >= 8u && cnt * 32u >= m) return false;
+            eq_run = 0;
+        }
     }
 }
 
@@ -1281,7 +1300,7 @@ __global__ void __launch_bounds__(kListWarps * 32)
 bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
     CFBPE_DYN_SMEM(s_dyn);
-    __shared__ uint32_t s_red[2 * kListWarps + 2];
+    __shared__ uint32_t s_red[3 * kListWarps + 2];
     __shared__ uint32_t s_item, s_m, s_rmin;
     const uint32_t n_big = status->long_overflow ? 0u : status->n_big;
     uint32_t* const id = s_dyn;

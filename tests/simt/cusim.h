@@ -246,6 +246,12 @@ inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
     for (unsigned i = 0; i < 32; ++i) if ((mask >> i) & 1u) r |= static_cast<unsigned>(buf[i]);
     return r;
 }
+inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
+    const uint64_t* buf = cusim::warp_exchange(v);
+    unsigned r = 0;
+    for (unsigned i = 0; i < 32; ++i) if ((mask >> i) & 1u) r += static_cast<unsigned>(buf[i]);
+    return r;
+}
 inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
 inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, !pred) == 0; }
 
