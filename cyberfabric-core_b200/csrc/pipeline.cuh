@@ -24,7 +24,7 @@ struct Workspace {
     DeviceStatus* status;
 };
 
-enum KernelIdx { K_SPLIT = 0, K_ENCODE = 1, K_LONG = 2, K_COUNT = 3, K_SCAN = 4, K_EMIT = 5 };
+enum KernelIdx { K_SPLIT = 0, K_ENCODE = 1, K_LONG = 2, K_COUNT = 3, K_SCAN = 4, K_EMIT = 5, K_LIST = 6, K_LONGSCAN = 7 };
 
 inline uint64_t n_flag_words(uint64_t total_bytes) { return (total_bytes + 31) >> 5; }
 inline uint32_t n_scan_tiles(uint64_t total_bytes) {
@@ -47,12 +47,14 @@ inline void enqueue_split(const BatchView& b, const VocabSet& vs, const UcTables
     const uint64_t n_chunks = (b.total_bytes + kSplitChunk - 1) / kSplitChunk;
     CFBPE_MARK(prof, K_SPLIT, stream, true);
     CFBPE_LAUNCH(pretok_split_kernel, static_cast<unsigned>((n_chunks + 255) / 256), 256, stream, b, vs, uc, w.piece_bits, w.status);
+    CFBPE_MARK(prof, K_SPLIT, stream, false);
 #ifndef CFBPE_K2_WINDOWED
     const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
+    CFBPE_MARK(prof, K_LONGSCAN, stream, true);
     CFBPE_LAUNCH(bpe_encode_pieces_kernel<1>, static_cast<unsigned>((n_warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, stream,
                  b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
+    CFBPE_MARK(prof, K_LONGSCAN, stream, false);
 #endif
-    CFBPE_MARK(prof, K_SPLIT, stream, false);
 }
 
 template <typename Stream, typename Prof>
@@ -76,11 +78,13 @@ inline void enqueue_long(const BatchView& b, const VocabSet& vs, const Workspace
     if (!b.total_bytes) return;
     CFBPE_MARK(prof, K_LONG, stream, true);
     CFBPE_LAUNCH(bpe_long_kernel, long_grid * (8 / kLongWarps), kLongWarps * 32, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
+    CFBPE_MARK(prof, K_LONG, stream, false);
 #ifndef CFBPE_NO_DEFER
+    CFBPE_MARK(prof, K_LIST, stream, true);
     // the list phase of the big pieces K2b deferred: three 64 KB CTAs per SM (long_grid = 4 x SM count)
     CFBPE_LAUNCH_SMEM(bpe_list_kernel, long_grid - long_grid / 4, kListWarps * 32, kListSmemBytes, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
+    CFBPE_MARK(prof, K_LIST, stream, false);
 #endif
-    CFBPE_MARK(prof, K_LONG, stream, false);
 }
 
 template <typename Stream, typename Prof>
