@@ -1296,7 +1296,7 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
 // and a few hundred cycles of shared-memory work and takes ~20 merges.  Three such CTAs fit an SM.  Tickets run over the
 // big end of the long-piece list.
 constexpr uint32_t kListWarps = 16;
-__global__ void __launch_bounds__(kListWarps * 32)
+__global__ void __launch_bounds__(kListWarps * 32, 3)
 bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
     CFBPE_DYN_SMEM(s_dyn);

@@ -19,7 +19,7 @@
 namespace cfbpe {
 
 constexpr uint32_t kTablesMagic = 0x45504243u;  // "CBPE"
-constexpr uint32_t kTablesVersion = 2;             // 2: the pair table is probed in buckets of four slots
+constexpr uint32_t kTablesVersion = 1;
 constexpr uint32_t kNone = 0xFFFFFFFFu;          // "no such token / no such pair"
 constexpr uint32_t kIdBits = 21;                 // vocab size < 2^21 - 1
 constexpr uint32_t kIdMask = (1u << kIdBits) - 1;
@@ -34,7 +34,7 @@ struct TablesHeader {
     // section offsets from blob start (bytes) and capacities (slots, powers of two)
     uint64_t off_byte2id;   // u32[256]     id of each single byte
     uint64_t off_bytepair;  // u32[65536]   merged id of raw byte pair (l<<8|r), or kNone
-    uint64_t off_pair;      // u64[cap_pair] (left<<42 | right<<21 | merged), kPairEmpty = free; buckets of 4, 32-byte aligned
+    uint64_t off_pair;      // u64[cap_pair] (left<<42 | right<<21 | merged), kPairEmpty = free
     uint64_t off_short;     // ShortSlot[cap_short]  tokens of <= 12 bytes, exact inline key
     uint64_t off_long;      // LongSlot[cap_long]    tokens of 13.. bytes, hash + verify
     uint64_t off_tokoff;    // u32[n_ranks+1]        start of each token in the byte blob
@@ -107,57 +107,34 @@ CFBPE_HD uint64_t long_hash(uint64_t k0, uint32_t k1, uint32_t last4, uint32_t l
 }
 
 // ---- lookups ----------------------------------------------------------------------------
-// The pair table is probed in BUCKETS of four slots (32 bytes, one sector): a lookup is one round trip to L2 whether the
-// pair exists or not -- most lookups of the merge loop are of pairs that do not (a bucket with a free slot ends the
-// search), and with one-slot linear probing those walked 2.5 dependent loads at load 0.5.  Load <= 0.5; a full bucket
-// (5 % of them) overflows into the next one.
-constexpr uint32_t kPairBucket = 4;
-struct PairBucket { uint64_t s[kPairBucket]; };
-CFBPE_HD PairBucket load_pair_bucket(const uint64_t* p) {   // p is 32-byte aligned
-    PairBucket b;
-#if defined(__CUDA_ARCH__)
-    const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(p)), c = __ldg(reinterpret_cast<const ulonglong2*>(p) + 1);
-    b.s[0] = a.x; b.s[1] = a.y; b.s[2] = c.x; b.s[3] = c.y;
-#else
-    b.s[0] = p[0]; b.s[1] = p[1]; b.s[2] = p[2]; b.s[3] = p[3];
-#endif
-    return b;
-}
-// 0: not in this bucket, go on;  1: found (out set);  2: not in the table
-CFBPE_HD uint32_t scan_pair_bucket(const PairBucket& b, uint64_t key, uint32_t& out) {
-    bool free_slot = false;
-#pragma unroll
-    for (uint32_t i = 0; i < kPairBucket; ++i) {
-        if ((b.s[i] >> kIdBits) == key) { out = static_cast<uint32_t>(b.s[i]) & kIdMask; return 1u; }
-        free_slot = free_slot || b.s[i] == kPairEmpty;
-    }
-    return free_slot ? 2u : 0u;
-}
-// merged id of (left,right) or kNone
+// merged id of (left,right) or kNone.  Linear probing, load <= 0.5.
 CFBPE_HD uint32_t pair_lookup(const TablesView& t, uint32_t left, uint32_t right) {
     const uint64_t key = (static_cast<uint64_t>(left) << kIdBits) | right;
-    uint32_t h = pair_hash(left, right) & t.pair_mask & ~(kPairBucket - 1u);
-    uint32_t out = kNone;
+    uint32_t h = pair_hash(left, right) & t.pair_mask;
     for (;;) {
-        const PairBucket b = load_pair_bucket(t.pair + h);
-        if (scan_pair_bucket(b, key, out)) return out;
-        h = (h + kPairBucket) & t.pair_mask;
+        const uint64_t s = t.pair[h];
+        if ((s >> kIdBits) == key) return static_cast<uint32_t>(s) & kIdMask;
+        if (s == kPairEmpty) return kNone;
+        h = (h + 1) & t.pair_mask;
     }
 }
-// two independent probes with their loads in flight together (a merge refreshes both neighbouring pairs)
+// two independent probes with their first loads in flight together (a merge refreshes both neighbouring pairs)
 CFBPE_HD void pair_lookup2(const TablesView& t, uint32_t l0, uint32_t r0, bool want0, uint32_t l1, uint32_t r1, bool want1,
                            uint32_t& out0, uint32_t& out1) {
     const uint64_t key0 = (static_cast<uint64_t>(l0) << kIdBits) | r0, key1 = (static_cast<uint64_t>(l1) << kIdBits) | r1;
-    uint32_t h0 = pair_hash(l0, r0) & t.pair_mask & ~(kPairBucket - 1u), h1 = pair_hash(l1, r1) & t.pair_mask & ~(kPairBucket - 1u);
-    PairBucket b0, b1;
-    if (want0) b0 = load_pair_bucket(t.pair + h0);
-    if (want1) b1 = load_pair_bucket(t.pair + h1);
+    uint32_t h0 = pair_hash(l0, r0) & t.pair_mask, h1 = pair_hash(l1, r1) & t.pair_mask;
+    uint64_t s0 = want0 ? t.pair[h0] : kPairEmpty;
+    uint64_t s1 = want1 ? t.pair[h1] : kPairEmpty;
     out0 = kNone; out1 = kNone;
-    if (want0) {
-        while (!scan_pair_bucket(b0, key0, out0)) { h0 = (h0 + kPairBucket) & t.pair_mask; b0 = load_pair_bucket(t.pair + h0); }
+    for (;;) {
+        if ((s0 >> kIdBits) == key0) { out0 = static_cast<uint32_t>(s0) & kIdMask; break; }
+        if (s0 == kPairEmpty) break;
+        h0 = (h0 + 1) & t.pair_mask; s0 = t.pair[h0];
     }
-    if (want1) {
-        while (!scan_pair_bucket(b1, key1, out1)) { h1 = (h1 + kPairBucket) & t.pair_mask; b1 = load_pair_bucket(t.pair + h1); }
+    for (;;) {
+        if ((s1 >> kIdBits) == key1) { out1 = static_cast<uint32_t>(s1) & kIdMask; break; }
+        if (s1 == kPairEmpty) break;
+        h1 = (h1 + 1) & t.pair_mask; s1 = t.pair[h1];
     }
 }
 // id of a token of len <= 12 whose bytes are packed little-endian in (k0,k1), or kNone

@@ -258,7 +258,7 @@ int build_tables(const std::vector<std::string>& tokens, uint32_t pattern_id, st
     uint64_t* pt = reinterpret_cast<uint64_t*>(base + h.off_pair);
     for (uint32_t i = 0; i < h.cap_pair; ++i) pt[i] = kPairEmpty;
     for (const PairE& p : pairs) {
-        uint32_t s = pair_hash(p.l, p.r) & (h.cap_pair - 1) & ~(kPairBucket - 1u);   // first free slot of the bucket, else of the next one
+        uint32_t s = pair_hash(p.l, p.r) & (h.cap_pair - 1);
         while (pt[s] != kPairEmpty) s = (s + 1) & (h.cap_pair - 1);
         pt[s] = pair_slot(p.l, p.r, p.m);
     }
@@ -311,8 +311,7 @@ int validate_tables(const uint8_t* blob, uint64_t size, std::string& err) {
     auto pow2 = [](uint32_t x) { return x && !(x & (x - 1)); };
     if (h.magic != kTablesMagic || h.version != kTablesVersion) { err = "table blob: bad magic/version"; return CFBPE_EINVAL; }
     if (h.total_bytes != size) { err = "table blob: size mismatch"; return CFBPE_EINVAL; }
-    if (!pow2(h.cap_pair) || !pow2(h.cap_short) || !pow2(h.cap_long) || h.cap_pair < 2 * kPairBucket || h.off_pair % 32 != 0 ||
-        h.n_pair_entries > h.cap_pair / 2) { err = "table blob: capacities"; return CFBPE_EINVAL; }
+    if (!pow2(h.cap_pair) || !pow2(h.cap_short) || !pow2(h.cap_long)) { err = "table blob: capacities"; return CFBPE_EINVAL; }
     if (h.n_ranks < 256 || h.n_ranks > kMaxRank || h.pattern_id >= CFBPE_PATTERN_COUNT || h.max_token_len > 255) { err = "table blob: header fields"; return CFBPE_EINVAL; }
     auto inside = [&](uint64_t off, uint64_t bytes) { return off % 16 == 0 && off <= size && bytes <= size - off; };
     if (!inside(h.off_byte2id, 1024) || !inside(h.off_bytepair, 65536 * 4) ||
