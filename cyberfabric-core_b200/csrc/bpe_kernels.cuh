@@ -1197,7 +1197,7 @@ constexpr uint32_t kListMaxRank = (1u << 20) - 1u;   // K2c packs rank << 12 | p
 // One warp per CTA: a warp that is deep in the serial chain of a long piece then holds one warp's worth of registers and
 // 6 KB of shared memory, not a whole CTA's, so the tail of this kernel can share the SMs with whatever runs next.
 constexpr uint32_t kLongWarps = 1;
-__global__ void __launch_bounds__(kLongWarps * 32)
+__global__ void __launch_bounds__(kLongWarps * 32, 32 / kLongWarps)
 bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
     __shared__ uint32_t s_subr[kLongWarps][8][32];   // [warp][sub-chunk][lane] cached minimum rank ...
