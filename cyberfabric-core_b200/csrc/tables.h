@@ -19,7 +19,7 @@
 namespace cfbpe {
 
 constexpr uint32_t kTablesMagic = 0x45504243u;  // "CBPE"
-constexpr uint32_t kTablesVersion = 2;             // 2: the pair table is a two-choice cuckoo table
+constexpr uint32_t kTablesVersion = 1;
 constexpr uint32_t kNone = 0xFFFFFFFFu;          // "no such token / no such pair"
 constexpr uint32_t kIdBits = 21;                 // vocab size < 2^21 - 1
 constexpr uint32_t kIdMask = (1u << kIdBits) - 1;
@@ -34,7 +34,7 @@ struct TablesHeader {
     // section offsets from blob start (bytes) and capacities (slots, powers of two)
     uint64_t off_byte2id;   // u32[256]     id of each single byte
     uint64_t off_bytepair;  // u32[65536]   merged id of raw byte pair (l<<8|r), or kNone
-    uint64_t off_pair;      // u64[cap_pair] (left<<42 | right<<21 | merged), kPairEmpty = free; two-choice cuckoo
+    uint64_t off_pair;      // u64[cap_pair] (left<<42 | right<<21 | merged), kPairEmpty = free
     uint64_t off_short;     // ShortSlot[cap_short]  tokens of <= 12 bytes, exact inline key
     uint64_t off_long;      // LongSlot[cap_long]    tokens of 13.. bytes, hash + verify
     uint64_t off_tokoff;    // u32[n_ranks+1]        start of each token in the byte blob
@@ -93,9 +93,6 @@ CFBPE_HD uint32_t mix32(uint32_t h) {  // 32-bit finaliser (lowbias32)
 CFBPE_HD uint32_t pair_hash(uint32_t left, uint32_t right) {
     return mix32(left * 0x9E3779B1u + right * 0x85EBCA77u + 0x165667B1u);
 }
-CFBPE_HD uint32_t pair_hash2(uint32_t left, uint32_t right) {   // the second cuckoo location
-    return mix32(left * 0xC2B2AE3Du + right * 0x27D4EB2Fu + 0x9E3779B9u);
-}
 CFBPE_HD uint64_t pair_slot(uint32_t left, uint32_t right, uint32_t merged) {
     return (static_cast<uint64_t>(left) << (2 * kIdBits)) | (static_cast<uint64_t>(right) << kIdBits) | merged;
 }
@@ -110,30 +107,35 @@ CFBPE_HD uint64_t long_hash(uint64_t k0, uint32_t k1, uint32_t last4, uint32_t l
 }
 
 // ---- lookups ----------------------------------------------------------------------------
-// merged id of (left,right) or kNone.  Cuckoo hashing: a pair lives in one of TWO slots, both loaded at once, so a lookup
-// is exactly one round trip to L2 whether the pair exists or not.  (Most lookups of the merge loop are of pairs that do
-// not exist; with linear probing a warp -- or a whole round of the list kernel, ~1000 lookups -- waited for the longest
-// probe chain: profiles/ncu_lines_bpe_list_r01n.txt.)  Load <= 0.25.
+// merged id of (left,right) or kNone.  Linear probing, load <= 0.25.
 CFBPE_HD uint32_t pair_lookup(const TablesView& t, uint32_t left, uint32_t right) {
     const uint64_t key = (static_cast<uint64_t>(left) << kIdBits) | right;
-    const uint64_t a = t.pair[pair_hash(left, right) & t.pair_mask], b = t.pair[pair_hash2(left, right) & t.pair_mask];
-    if ((a >> kIdBits) == key) return static_cast<uint32_t>(a) & kIdMask;
-    if ((b >> kIdBits) == key) return static_cast<uint32_t>(b) & kIdMask;
-    return kNone;
+    uint32_t h = pair_hash(left, right) & t.pair_mask;
+    for (;;) {
+        const uint64_t s = t.pair[h];
+        if ((s >> kIdBits) == key) return static_cast<uint32_t>(s) & kIdMask;
+        if (s == kPairEmpty) return kNone;
+        h = (h + 1) & t.pair_mask;
+    }
 }
-// two lookups with all four loads in flight together (a merge refreshes both neighbouring pairs)
+// two independent probes with their first loads in flight together (a merge refreshes both neighbouring pairs)
 CFBPE_HD void pair_lookup2(const TablesView& t, uint32_t l0, uint32_t r0, bool want0, uint32_t l1, uint32_t r1, bool want1,
                            uint32_t& out0, uint32_t& out1) {
     const uint64_t key0 = (static_cast<uint64_t>(l0) << kIdBits) | r0, key1 = (static_cast<uint64_t>(l1) << kIdBits) | r1;
-    const uint64_t a0 = want0 ? t.pair[pair_hash(l0, r0) & t.pair_mask] : kPairEmpty;
-    const uint64_t b0 = want0 ? t.pair[pair_hash2(l0, r0) & t.pair_mask] : kPairEmpty;
-    const uint64_t a1 = want1 ? t.pair[pair_hash(l1, r1) & t.pair_mask] : kPairEmpty;
-    const uint64_t b1 = want1 ? t.pair[pair_hash2(l1, r1) & t.pair_mask] : kPairEmpty;
+    uint32_t h0 = pair_hash(l0, r0) & t.pair_mask, h1 = pair_hash(l1, r1) & t.pair_mask;
+    uint64_t s0 = want0 ? t.pair[h0] : kPairEmpty;
+    uint64_t s1 = want1 ? t.pair[h1] : kPairEmpty;
     out0 = kNone; out1 = kNone;
-    if ((a0 >> kIdBits) == key0) out0 = static_cast<uint32_t>(a0) & kIdMask;
-    else if ((b0 >> kIdBits) == key0) out0 = static_cast<uint32_t>(b0) & kIdMask;
-    if ((a1 >> kIdBits) == key1) out1 = static_cast<uint32_t>(a1) & kIdMask;
-    else if ((b1 >> kIdBits) == key1) out1 = static_cast<uint32_t>(b1) & kIdMask;
+    for (;;) {
+        if ((s0 >> kIdBits) == key0) { out0 = static_cast<uint32_t>(s0) & kIdMask; break; }
+        if (s0 == kPairEmpty) break;
+        h0 = (h0 + 1) & t.pair_mask; s0 = t.pair[h0];
+    }
+    for (;;) {
+        if ((s1 >> kIdBits) == key1) { out1 = static_cast<uint32_t>(s1) & kIdMask; break; }
+        if (s1 == kPairEmpty) break;
+        h1 = (h1 + 1) & t.pair_mask; s1 = t.pair[h1];
+    }
 }
 // id of a token of len <= 12 whose bytes are packed little-endian in (k0,k1), or kNone
 CFBPE_HD uint32_t short_lookup(const TablesView& t, uint64_t k0, uint32_t k1, uint32_t len) {

@@ -235,7 +235,7 @@ int build_tables(const std::vector<std::string>& tokens, uint32_t pattern_id, st
     h.pattern_id = pattern_id;
     h.max_token_len = max_len;
     h.n_pair_entries = static_cast<uint32_t>(pairs.size());
-    h.cap_pair = pow2_at_least(pairs.size() * 4 + 16);   // load <= 0.25: a round of the list kernels waits for the longest of ~1000 probe chains
+    h.cap_pair = pow2_at_least(pairs.size() * 2 + 16);
     h.cap_short = pow2_at_least(static_cast<uint64_t>(n_short) * 2 + 16);
     h.cap_long = pow2_at_least(static_cast<uint64_t>(n_long) * 2 + 16);
     h.blob_bytes = static_cast<uint32_t>(blob_bytes);
@@ -257,28 +257,10 @@ int build_tables(const std::vector<std::string>& tokens, uint32_t pattern_id, st
     for (uint32_t i = 0; i < 65536; ++i) bytepair[i] = kNone;
     uint64_t* pt = reinterpret_cast<uint64_t*>(base + h.off_pair);
     for (uint32_t i = 0; i < h.cap_pair; ++i) pt[i] = kPairEmpty;
-    // cuckoo insertion: a pair goes to its first location if free, else its second, else it evicts the occupant of one of
-    // them, which moves to ITS other location, and so on (at load <= 0.25 the walks are a few steps; 4096 is "cannot happen")
-    {
-        const uint32_t mask = h.cap_pair - 1;
-        uint64_t rng = 0x9E3779B97F4A7C15ull;
-        for (const PairE& p : pairs) {
-            uint64_t cur = pair_slot(p.l, p.r, p.m);
-            uint32_t at = pair_hash(p.l, p.r) & mask;
-            bool placed = false;
-            for (int kick = 0; kick < 4096; ++kick) {
-                const uint32_t l = static_cast<uint32_t>(cur >> (2 * kIdBits)), r = static_cast<uint32_t>(cur >> kIdBits) & kIdMask;
-                const uint32_t s1 = pair_hash(l, r) & mask, s2 = pair_hash2(l, r) & mask;
-                if (pt[s1] == kPairEmpty) { pt[s1] = cur; placed = true; break; }
-                if (pt[s2] == kPairEmpty) { pt[s2] = cur; placed = true; break; }
-                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
-                at = (at == s1) ? s2 : ((at == s2) ? s1 : ((rng >> 63) ? s1 : s2));   // do not bounce straight back
-                const uint64_t victim = pt[at];
-                pt[at] = cur;
-                cur = victim;
-            }
-            if (!placed) { err = "pair table: cuckoo insertion failed"; return CFBPE_EINVAL; }
-        }
+    for (const PairE& p : pairs) {
+        uint32_t s = pair_hash(p.l, p.r) & (h.cap_pair - 1);
+        while (pt[s] != kPairEmpty) s = (s + 1) & (h.cap_pair - 1);
+        pt[s] = pair_slot(p.l, p.r, p.m);
     }
     // raw byte pair table: token whose bytes are exactly (a,b)
     for (uint32_t id = 0; id < n; ++id) {
