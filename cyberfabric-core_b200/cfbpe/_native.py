@@ -13,8 +13,8 @@ FORMAT_TIKTOKEN, FORMAT_TEKKEN_JSON = 0, 1
 PATTERN_CL100K, PATTERN_O200K, PATTERN_LLAMA3, PATTERN_TEKKEN = 0, 1, 2, 3
 PATTERN_IDS = {"cl100k": 0, "o200k": 1, "llama3": 2, "tekken": 3}
 MAX_VOCABS = 8
-NUM_KERNELS = 8
-KERNEL_NAMES = ["pretok_split", "bpe_encode", "bpe_long", "flag_count", "tile_scan", "emit_compact", "bpe_list", "long_scan"]
+NUM_KERNELS = 10
+KERNEL_NAMES = ["pretok_split", "bpe_encode", "bpe_long", "flag_count", "tile_scan", "emit_compact", "bpe_list", "long_scan", "bpe_merge", "reserved"]
 
 # every symbol include/cfbpe.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [

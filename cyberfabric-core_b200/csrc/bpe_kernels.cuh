@@ -69,7 +69,19 @@ struct DeviceStatus {
     uint64_t tok_end;      // token_base + n_tokens: where the next sub-batch of a pipelined call continues
     unsigned long long long_bytes;   // bytes inside pieces handled by K2b ...
     unsigned long long long_tokens;  // ... and the ids they became (for the roofline of that kernel)
+    uint32_t miss_n[3];    // short pieces that are not one token, by length class: 13..32 | 7..12 | 2..6 bytes (K2a -> K2m)
+    uint32_t miss_next[3]; // K2m work tickets
+    uint32_t miss_overflow;
+    uint32_t pad2;
 };
+
+// K2a's lists of the short pieces that need the merge loop, one per length class (worst-case capacities: a class with
+// pieces of >= L bytes holds at most total / L of them)
+struct MissLists {
+    uint32_t* list[3];
+    uint32_t cap[3];
+};
+__host__ __device__ inline uint32_t miss_class_min_len(uint32_t c) { return c == 0 ? 13u : (c == 1 ? 7u : 1u); }
 
 struct LongPiece { uint64_t start; uint64_t end; uint32_t vocab; uint32_t pad; };   // pad: 0, or the part count K2b left for K2c
 
@@ -681,6 +693,132 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
             if (pv != vid) { vid = pv; T = vs.v[vid]; }
         }
         merge_piece_in_lane(T, text, pos, len, sid, srk, ids_by_pos, tok_bits);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2a + K2m: the short pieces (<= 32 bytes), in two kernels so that both run with full warps.
+//   K2a  bpe_lookup_kernel   every piece once: CoreBPE's `if piece in ranks`.  A warp lists the piece starts of its 512
+//        bytes in shared memory and its lanes take them round-robin (a lane that owned 16 BYTES had between one and
+//        eight pieces to look up); a hit stores the id and its flag, a miss goes to the CTA's list of its length class,
+//        which the CTA appends to the global list with one atomic per class.
+//   K2m  bpe_merge_kernel    the misses, one LANE per piece (merge_piece_in_lane), 32 pieces of one length class per
+//        warp ticket -- in the fused version the merge loops ran with 4-5 active lanes, because a warp only had the
+//        ~15 misses of its own 512 bytes to spread over its lanes (profiles/ncu_lines_bpe_encode_r01n.txt).
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kLookupWarps = 8;
+__global__ void __launch_bounds__(kLookupWarps * 32)
+bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits, uint32_t* __restrict__ ids_by_pos,
+                  uint32_t* __restrict__ tok_bits, MissLists ml, DeviceStatus* status) {
+    __shared__ uint16_t s_pos[kLookupWarps][kPieceRange + 2];
+    __shared__ uint32_t s_flags[kLookupWarps][kPieceRange / 32];
+    __shared__ uint32_t s_miss0[kLookupWarps * kPieceRange / 13 + 8];
+    __shared__ uint32_t s_miss1[kLookupWarps * kPieceRange / 7 + 8];
+    __shared__ uint32_t s_miss2[kLookupWarps * kPieceRange / 2 + 8];
+    __shared__ uint32_t s_cnt[3], s_base[3];
+    const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    if (lane < kPieceRange / 32) s_flags[wic][lane] = 0;
+    __syncthreads();
+    const uint64_t warp = static_cast<uint64_t>(blockIdx.x) * kLookupWarps + wic;
+    const uint64_t r0 = warp * kPieceRange;
+    const uint8_t* __restrict__ text = b.bytes;
+    const bool multi = b.vocab_ids != nullptr;
+    if (r0 < b.total_bytes) {
+        const uint64_t r1 = (r0 + kPieceRange < b.total_bytes) ? r0 + kPieceRange : b.total_bytes;
+        // ---- the piece starts of my range, in order, as offsets
+        const uint64_t base = r0 + 16ull * lane;
+        const uint32_t my = (base < b.total_bytes) ? ((piece_bits[base >> 5] >> (16u * (lane & 1u))) & 0xFFFFu) : 0u;
+        const uint32_t cnt = __popc(my);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
+        const uint32_t n_w = __shfl_sync(kFull, incl, 31);
+        uint32_t slot = incl - cnt;
+        for (uint32_t bits = my; bits; bits &= bits - 1) s_pos[wic][slot++] = static_cast<uint16_t>(16u * lane + static_cast<uint32_t>(__ffs(bits)) - 1u);
+        __syncwarp();
+        // the last piece ends at the next start beyond the range (or at the end of the data)
+        uint64_t beyond = b.total_bytes;
+        if (n_w) beyond = next_set_bit(piece_bits, r1, b.total_bytes);
+        TablesView T = vs.v[0];
+        uint32_t vid = 0;
+        for (uint32_t i = lane; i < n_w; i += 32) {
+            const uint32_t off = s_pos[wic][i];
+            const uint64_t pos = r0 + off;
+            const uint64_t end = (i + 1 < n_w) ? r0 + s_pos[wic][i + 1] : beyond;
+            if (end - pos > 32) continue;                         // long piece: K2b
+            const uint32_t len = static_cast<uint32_t>(end - pos);
+            if (multi) {
+                const uint32_t pv = b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)];
+                if (pv != vid) { vid = pv; T = vs.v[vid]; }
+            }
+            const uint32_t tok = (len == 1) ? T.byte2id[text[pos]] : whole_piece_lookup(T, text + pos, len);   // a byte is a token
+            if (tok != kNone) {
+                ids_by_pos[pos] = tok;
+                atomicOr(&s_flags[wic][off >> 5], 1u << (off & 31));
+            } else {
+                const uint32_t c = len >= 13 ? 0u : (len >= 7 ? 1u : 2u);
+                const uint32_t k = atomicAdd(&s_cnt[c], 1u);
+                (c == 0 ? s_miss0 : (c == 1 ? s_miss1 : s_miss2))[k] = static_cast<uint32_t>(pos);
+            }
+        }
+        __syncwarp();
+        if (lane < kPieceRange / 32) {
+            const uint32_t f = s_flags[wic][lane];
+            if (f) atomicOr(&tok_bits[(r0 >> 5) + lane], f);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const uint32_t n = s_cnt[threadIdx.x];
+        uint32_t g = n ? atomicAdd(&status->miss_n[threadIdx.x], n) : 0u;
+        if (n && g + n > ml.cap[threadIdx.x]) { atomicOr(&status->miss_overflow, 1u); g = 0xFFFFFFFFu; }
+        s_base[threadIdx.x] = g;
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t c = 0; c < 3; ++c) {
+        const uint32_t n = s_cnt[c], g = s_base[c];
+        if (g == 0xFFFFFFFFu) continue;
+        const uint32_t* src = c == 0 ? s_miss0 : (c == 1 ? s_miss1 : s_miss2);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) ml.list[c][g + i] = src[i];
+    }
+}
+
+__global__ void __launch_bounds__(kPieceWarps * 32)
+bpe_merge_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits, uint32_t* __restrict__ ids_by_pos,
+                 uint32_t* __restrict__ tok_bits, MissLists ml, DeviceStatus* status) {
+    __shared__ uint32_t s_id[kPieceWarps][32][32];   // [warp][part][lane]
+    __shared__ uint32_t s_rk[kPieceWarps][32][32];
+    const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const uint8_t* __restrict__ text = b.bytes;
+    const bool multi = b.vocab_ids != nullptr;
+    uint32_t* sid = &s_id[wic][0][lane];
+    uint32_t* srk = &s_rk[wic][0][lane];
+    if (status->miss_overflow) return;
+    TablesView T = vs.v[0];
+    uint32_t vid = 0;
+#pragma unroll 1
+    for (uint32_t c = 0; c < 3; ++c) {     // longest class first
+        const uint32_t n = status->miss_n[c];
+        const uint32_t* __restrict__ list = ml.list[c];
+        for (;;) {
+            uint32_t t0 = 0;
+            if (lane == 0) t0 = atomicAdd(&status->miss_next[c], 32u);
+            t0 = __shfl_sync(kFull, t0, 0);
+            if (t0 >= n) break;
+            const uint32_t i = t0 + lane;
+            if (i < n) {
+                const uint64_t pos = list[i];
+                const uint64_t end = next_set_bit(piece_bits, pos + 1, b.total_bytes);
+                if (multi) {
+                    const uint32_t pv = b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)];
+                    if (pv != vid) { vid = pv; T = vs.v[vid]; }
+                }
+                merge_piece_in_lane(T, text, pos, static_cast<uint32_t>(end - pos), sid, srk, ids_by_pos, tok_bits);
+            }
+            __syncwarp();
+        }
     }
 }
 

@@ -218,13 +218,14 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         const uint64_t t0 = (o0 >> 13) + 2ull * k;
         w.tile_counts += t0; w.tile_base += t0;
         w.status = ctx->d_status_arr + k;
+        w.miss = slice_miss(ctx->ws.miss, o0, len, static_cast<uint32_t>(k));
         BatchView b{ctx->d_bytes + o0, ctx->d_offsets + p0 + k, vocab_ids ? ctx->d_vocab_ids + p0 : nullptr, nk, len};
         cudaStream_t ss = ctx->side[k % kSideStreams];
         enqueue_split(b, ctx->vs, ctx->uc, w, cs, static_cast<ProfEvents*>(nullptr));
         CK(cudaEventRecord(ctx->ev_scan[k], cs));
         CK(cudaStreamWaitEvent(ss, ctx->ev_scan[k], 0));
         enqueue_long(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ss, static_cast<ProfEvents*>(nullptr));   // tail overlaps what follows on cs
-        enqueue_short(b, ctx->vs, w, cs, static_cast<ProfEvents*>(nullptr));
+        enqueue_short(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), cs, static_cast<ProfEvents*>(nullptr));
         CK(cudaEventRecord(ctx->ev_front[k], cs));
         CK(cudaStreamWaitEvent(ss, ctx->ev_front[k], 0));
         if (k) CK(cudaStreamWaitEvent(ss, ctx->ev_done[k - 1], 0));     // token ranks chain through DeviceStatus::tok_end
@@ -241,7 +242,7 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         CK(cudaEventSynchronize(ctx->ev_done[k]));
         const DeviceStatus st = ctx->h_status_arr[k];
         const uint32_t p0 = cut[k], p1 = cut[k + 1], nk = p1 - p0;
-        if (st.long_overflow && !err) err = fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
+        if ((st.long_overflow || st.miss_overflow) && !err) err = fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
         if (st.bad_utf8 && !err) err = fail(ctx, CFBPE_EILSEQ, "a prompt holds malformed UTF-8");
         const uint64_t base = st.tok_end - st.n_tokens;
         tok_total = st.tok_end;
@@ -293,7 +294,7 @@ int run_host(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const uint64_t* o
     if (out_counts && n) CK(cudaMemcpyAsync(out_counts, ctx->d_out_counts, static_cast<uint64_t>(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const DeviceStatus st = *ctx->h_status;
-    if (st.long_overflow) return fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
+    if (st.long_overflow || st.miss_overflow) return fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
     if (st.bad_utf8) return fail(ctx, CFBPE_EILSEQ, "a prompt holds malformed UTF-8");
     if (want_ids) {
         if (st.n_tokens > out_cap) {
@@ -336,6 +337,7 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->max_bytes = cfg->max_batch_bytes ? cfg->max_batch_bytes : (256ull << 20);
     ctx->max_prompts = cfg->max_prompts ? cfg->max_prompts : (1u << 20);
+    if (ctx->max_bytes >= (1ull << 32) - 4096) { delete ctx; return CFBPE_EINVAL; }   // byte positions inside a batch are 32-bit in the work lists
     const uint64_t mb = ctx->max_bytes, mp = ctx->max_prompts;
     const uint64_t nw = n_flag_words(mb) + 4 + 4 * kMaxPipeChunks;      // + per-sub-batch slack of a pipelined call
     const uint64_t nt = n_scan_tiles(mb) + 1 + 2 * kMaxPipeChunks;
@@ -355,6 +357,11 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     ok = ok && dmalloc(&ctx->ws.lscratch.aux1, mb + 1) == cudaSuccess;
     ctx->ws.long_cap = static_cast<uint32_t>(mb / 32 + 1 + kMaxPipeChunks);   // a long piece holds more than 32 bytes
     ok = ok && dmalloc(&ctx->ws.long_list, ctx->ws.long_cap) == cudaSuccess;
+    for (uint32_t c = 0; c < 3; ++c) {
+        const uint64_t words = miss_list_words(mb, c, kMaxPipeChunks);
+        ok = ok && dmalloc(&ctx->ws.miss.list[c], words) == cudaSuccess;
+        ctx->ws.miss.cap[c] = static_cast<uint32_t>(words);
+    }
     ok = ok && dmalloc(&ctx->ws.tile_counts, nt) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.tile_base, nt) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.status, 1) == cudaSuccess;
@@ -412,6 +419,7 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     cudaFree(ctx->d_out_ids); cudaFree(ctx->d_out_offsets); cudaFree(ctx->d_out_counts);
     cudaFree(ctx->ws.piece_bits); cudaFree(ctx->ws.tok_bits); cudaFree(ctx->ws.ids_by_pos);
     cudaFree(ctx->ws.lscratch.rank); cudaFree(ctx->ws.lscratch.aux0); cudaFree(ctx->ws.lscratch.aux1);
+    for (uint32_t c = 0; c < 3; ++c) cudaFree(ctx->ws.miss.list[c]);
     cudaFree(ctx->ws.long_list); cudaFree(ctx->ws.tile_counts); cudaFree(ctx->ws.tile_base); cudaFree(ctx->ws.status);
     cudaFree(ctx->d_uc1); cudaFree(ctx->d_uc2); cudaFree(ctx->d_ascii); cudaFree(ctx->d_fsm);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -535,7 +543,7 @@ int cfbpe_encode_batch_device(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t*
         if (prof) fill_profile(ctx, total_bytes);
         const DeviceStatus st = *ctx->h_status;
         if (n_tokens) *n_tokens = st.n_tokens;
-        if (st.long_overflow) return fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
+        if (st.long_overflow || st.miss_overflow) return fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
         if (st.bad_utf8) return fail(ctx, CFBPE_EILSEQ, "a prompt holds malformed UTF-8");
         if (d_out_ids && st.n_tokens > out_cap) return fail(ctx, CFBPE_ENOSPC, "out_cap too small: need " + std::to_string(st.n_tokens) + " ids");
     }
@@ -548,7 +556,7 @@ int cfbpe_device_status(cfbpe_ctx* ctx, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CK(cudaMemcpyAsync(ctx->h_status, ctx->ws.status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (ctx->h_status->long_overflow) return fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
+    if (ctx->h_status->long_overflow || ctx->h_status->miss_overflow) return fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
     if (ctx->h_status->bad_utf8) return fail(ctx, CFBPE_EILSEQ, "a prompt holds malformed UTF-8");
     return CFBPE_OK;
 }

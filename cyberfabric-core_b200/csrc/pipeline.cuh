@@ -22,9 +22,25 @@ struct Workspace {
     uint32_t* tile_counts;  // [n_tiles]
     uint64_t* tile_base;    // [n_tiles]
     DeviceStatus* status;
+    MissLists miss;         // K2a -> K2m: short pieces that need the merge loop, by length class
 };
 
-enum KernelIdx { K_SPLIT = 0, K_ENCODE = 1, K_LONG = 2, K_COUNT = 3, K_SCAN = 4, K_EMIT = 5, K_LIST = 6, K_LONGSCAN = 7 };
+// the slice of the miss lists that belongs to a sub-batch of `len` bytes starting at byte o0 (k-th sub-batch)
+inline MissLists slice_miss(const MissLists& all, uint64_t o0, uint64_t len, uint32_t k) {
+    MissLists m;
+    for (uint32_t c = 0; c < 3; ++c) {
+        const uint32_t L = miss_class_min_len(c) < 2 ? 2u : miss_class_min_len(c);   // no one-byte piece is ever a miss
+        m.list[c] = all.list[c] + o0 / L + 2ull * k;
+        m.cap[c] = static_cast<uint32_t>(len / L + 2);
+    }
+    return m;
+}
+inline uint64_t miss_list_words(uint64_t max_bytes, uint32_t c, uint32_t max_chunks) {
+    const uint32_t L = miss_class_min_len(c) < 2 ? 2u : miss_class_min_len(c);
+    return max_bytes / L + 2ull * max_chunks + 64;
+}
+
+enum KernelIdx { K_SPLIT = 0, K_ENCODE = 1, K_LONG = 2, K_COUNT = 3, K_SCAN = 4, K_EMIT = 5, K_LIST = 6, K_LONGSCAN = 7, K_MERGE = 8 };
 
 inline uint64_t n_flag_words(uint64_t total_bytes) { return (total_bytes + 31) >> 5; }
 inline uint32_t n_scan_tiles(uint64_t total_bytes) {
@@ -58,19 +74,31 @@ inline void enqueue_split(const BatchView& b, const VocabSet& vs, const UcTables
 }
 
 template <typename Stream, typename Prof>
-inline void enqueue_short(const BatchView& b, const VocabSet& vs, const Workspace& w, Stream stream, Prof* prof) {
+inline void enqueue_short(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
     if (!b.total_bytes) return;
+#if defined(CFBPE_K2_WINDOWED)
     CFBPE_MARK(prof, K_ENCODE, stream, true);
-#ifdef CFBPE_K2_WINDOWED
     const uint64_t n_warps = (b.total_bytes + kEncodeRange - 1) / kEncodeRange;
     CFBPE_LAUNCH(bpe_encode_kernel, static_cast<unsigned>((n_warps + 7) / 8), 256, stream,
                  b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
-#else
+    CFBPE_MARK(prof, K_ENCODE, stream, false);
+#elif defined(CFBPE_K2_FUSED)
+    CFBPE_MARK(prof, K_ENCODE, stream, true);
     const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
     CFBPE_LAUNCH(bpe_encode_pieces_kernel<2>, static_cast<unsigned>((n_warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, stream,
                  b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
-#endif
     CFBPE_MARK(prof, K_ENCODE, stream, false);
+#else
+    const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
+    CFBPE_MARK(prof, K_ENCODE, stream, true);
+    CFBPE_LAUNCH(bpe_lookup_kernel, static_cast<unsigned>((n_warps + kLookupWarps - 1) / kLookupWarps), kLookupWarps * 32, stream,
+                 b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.miss, w.status);
+    CFBPE_MARK(prof, K_ENCODE, stream, false);
+    CFBPE_MARK(prof, K_MERGE, stream, true);
+    CFBPE_LAUNCH(bpe_merge_kernel, long_grid + long_grid / 2, kPieceWarps * 32, stream,      // 6 CTAs of 32 KB per SM
+                 b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.miss, w.status);
+    CFBPE_MARK(prof, K_MERGE, stream, false);
+#endif
 }
 
 template <typename Stream, typename Prof>
@@ -122,11 +150,11 @@ inline void enqueue_encode(const BatchView& b, const VocabSet& vs, const UcTable
     enqueue_split(b, vs, uc, w, stream, prof);
     CFBPE_FORK(stream, aux, ev_fork);
 #ifdef CFBPE_K2_WINDOWED
-    enqueue_short(b, vs, w, stream, prof);      // the windowed kernel queues the long pieces itself
+    enqueue_short(b, vs, w, long_grid, stream, prof);      // the windowed kernel queues the long pieces itself
     enqueue_long(b, vs, w, long_grid, stream, prof);
 #else
     enqueue_long(b, vs, w, long_grid, aux, prof);
-    enqueue_short(b, vs, w, stream, prof);
+    enqueue_short(b, vs, w, long_grid, stream, prof);
 #endif
     CFBPE_JOIN(stream, aux, ev_join);
     enqueue_back(b, w, out_ids, out_cap, out_offsets, out_counts, stream, prof, token_base);

@@ -96,9 +96,9 @@ typedef struct cfbpe_vocab_info {
 } cfbpe_vocab_info;
 
 /* per-call device timings, filled when profiling is on (cfbpe_profile_enable) */
-#define CFBPE_NUM_KERNELS 8
+#define CFBPE_NUM_KERNELS 10
 typedef struct cfbpe_profile {
-    float kernel_ms[CFBPE_NUM_KERNELS]; /* 0 pretok_split, 1 bpe_encode, 2 bpe_long, 3 flag_count, 4 tile_scan, 5 emit_compact (+ offsets), 6 bpe_list, 7 long_scan */
+    float kernel_ms[CFBPE_NUM_KERNELS]; /* 0 pretok_split, 1 bpe_encode, 2 bpe_long, 3 flag_count, 4 tile_scan, 5 emit_compact (+ offsets), 6 bpe_list, 7 long_scan, 8 bpe_merge, 9 reserved */
     uint32_t kernel_launches[CFBPE_NUM_KERNELS];
     float h2d_ms, d2h_ms, total_ms;
     uint64_t n_tokens, n_bytes, n_long_pieces;

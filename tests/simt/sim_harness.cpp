@@ -116,13 +116,20 @@ __attribute__((visibility("default"))) int sim_encode_batch(void* const* vocabs,
     std::vector<uint64_t> tile_base(nt + 1);
     std::vector<LongPiece> ll(total / 32 + 1);
     DeviceStatus st{};
+    std::vector<uint32_t> miss[3];
+    MissLists ml;
+    for (uint32_t c = 0; c < 3; ++c) {
+        miss[c].resize(miss_list_words(total, c, 1));
+        ml.list[c] = miss[c].data();
+        ml.cap[c] = static_cast<uint32_t>(miss[c].size());
+    }
     Workspace w{piece_bits.data(), tok_bits.data(), ids.data(), LongScratch{rk.data(), nx.data(), pv.data()},
-                ll.data(), static_cast<uint32_t>(ll.size()), tile_counts.data(), tile_base.data(), &st};
+                ll.data(), static_cast<uint32_t>(ll.size()), tile_counts.data(), tile_base.data(), &st, ml};
     int* prof = nullptr;
     enqueue_encode(b, vs, uc_tables(), w, out_ids, out_cap, out_offsets, out_counts, 4u, 0, 0, 0, 0, prof);
     if (n_long_out) *n_long_out = static_cast<uint64_t>(st.n_long) + st.n_big;
     if (st.bad_utf8) return CFBPE_EILSEQ;
-    if (st.long_overflow) return CFBPE_EIO;
+    if (st.long_overflow || st.miss_overflow) return CFBPE_EIO;
     if (out_ids && st.n_tokens > out_cap) return CFBPE_ENOSPC;
     return 0;
 }
