@@ -42,8 +42,8 @@ static inline void prof_mark(ProfEvents* p, int idx, cudaStream_t s, bool begin)
 
 constexpr int kMaxPipeChunks = 64;
 constexpr int kSideStreams = 16;
-constexpr uint64_t kPipeChunkBytes = 12ull << 20;   // sub-batch size of a pipelined host call
-constexpr uint64_t kPipeMinBytes = 24ull << 20;     // smaller calls run as one shot
+constexpr uint64_t kPipeChunkBytes = 24ull << 20;   // sub-batch size of a pipelined host call (measured best on 134 MB: profiles/e2e_subbatch_sizes_r01n.jsonl)
+constexpr uint64_t kPipeMinBytes = 40ull << 20;     // smaller calls run as one shot
 
 struct VocabSlot {
     bool loaded = false;
