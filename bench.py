@@ -295,13 +295,18 @@ def main():
 
     # ---- roofline of the dominant kernel
     hbm_gbs, peak_src = peaks()
+    n_miss, n_list, list_parts = pr["n_miss_pieces"], pr["n_list_pieces"], pr["n_list_parts"]
     alg = {  # algorithmic bytes per launch
-        "pretok_split": total * (1 + 1 / 8) + 8 * (n + 1),
-        "bpe_encode": total * (1 + 1 / 8) + 4 * n_tokens + total / 8,
-        "bpe_long": long_bytes + 4.0 * long_tokens + 24.0 * n_long,   # piece bytes in, ids out, work-list entries
+        "pretok_split": total * (1 + 1 / 8) + 8 * (n + 1),                       # text in, piece-start flags out, offsets
+        "long_scan": total / 8 + 24.0 * n_long,                                   # flags in, work-list entries out
+        "bpe_encode": total * (1 + 1 / 8) + 4 * (n_tokens - long_tokens) + total / 8 + 4.0 * n_miss,   # text + flags in; ids, id flags, miss lists out
+        "bpe_merge": n_miss * (4 + 8 + 8),                                        # list entry, ~8 piece bytes, ~2 ids (estimate)
+        "bpe_long": long_bytes + 4.0 * (long_tokens + list_parts) + 24.0 * n_long,   # piece bytes in, ids (or hand-over state) out, work-list entries
+        "bpe_list": 12.0 * list_parts,                                            # id + rank of every part in, ids out
         "flag_count": total / 8,
         "tile_scan": 0.0,
         "emit_compact": total / 8 + 8 * n_tokens + 12 * (n + 1),
+        "reserved": 0.0,
     }
     dom = max(kms, key=lambda k: kms[k])
     achieved = alg[dom] / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0

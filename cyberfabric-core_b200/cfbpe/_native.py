@@ -39,7 +39,8 @@ class Profile(C.Structure):
     _fields_ = [("kernel_ms", C.c_float * NUM_KERNELS), ("kernel_launches", C.c_uint32 * NUM_KERNELS),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("n_tokens", C.c_uint64), ("n_bytes", C.c_uint64), ("n_long_pieces", C.c_uint64),
-                ("n_long_bytes", C.c_uint64), ("n_long_tokens", C.c_uint64)]
+                ("n_long_bytes", C.c_uint64), ("n_long_tokens", C.c_uint64),
+                ("n_miss_pieces", C.c_uint64), ("n_list_pieces", C.c_uint64), ("n_list_parts", C.c_uint64)]
 
 
 _lib = None
@@ -237,4 +238,5 @@ class Context:
                 "kernel_launches": {KERNEL_NAMES[i]: p.kernel_launches[i] for i in range(NUM_KERNELS)},
                 "h2d_ms": p.h2d_ms, "d2h_ms": p.d2h_ms, "total_ms": p.total_ms, "n_tokens": p.n_tokens,
                 "n_bytes": p.n_bytes, "n_long_pieces": p.n_long_pieces, "n_long_bytes": p.n_long_bytes,
-                "n_long_tokens": p.n_long_tokens}
+                "n_long_tokens": p.n_long_tokens, "n_miss_pieces": p.n_miss_pieces, "n_list_pieces": p.n_list_pieces,
+                "n_list_parts": p.n_list_parts}

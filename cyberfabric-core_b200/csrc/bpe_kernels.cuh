@@ -72,7 +72,8 @@ struct DeviceStatus {
     uint32_t miss_n[3];    // short pieces that are not one token, by length class: 13..32 | 7..12 | 2..6 bytes (K2a -> K2m)
     uint32_t miss_next[3]; // K2m work tickets
     uint32_t miss_overflow;
-    uint32_t pad2;
+    uint32_t defer_n;      // pieces K2b handed to K2c ...
+    unsigned long long defer_parts;   // ... and their parts at hand-over
 };
 
 // K2a's lists of the short pieces that need the merge loop, one per length class (worst-case capacities: a class with
@@ -1407,7 +1408,7 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
             }
 #ifndef CFBPE_NO_DEFER
             if (m <= kDeferMaxParts && T.n_ranks < kListMaxRank) {   // bpe_list_kernel goes on from here, in shared memory
-                if (lane == 0) { long_list[slot].pad = m; CFBPE_DBG_COUNT(0); }
+                if (lane == 0) { long_list[slot].pad = m; atomicAdd(&status->defer_n, 1u); atomicAdd(&status->defer_parts, static_cast<unsigned long long>(m)); CFBPE_DBG_COUNT(0); }
                 deferred = true;
                 break;
             }

@@ -152,7 +152,7 @@ void fill_profile(cfbpe_ctx* ctx, uint64_t n_bytes) {
         if (!ctx->prof.launched[k]) continue;
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->prof.ev[k][0], ctx->prof.ev[k][1]) == cudaSuccess) p.kernel_ms[k] = ms;
-        p.kernel_launches[k] = (k == K_EMIT) ? 2 : 1;
+        p.kernel_launches[k] = (k == K_EMIT) ? 2 : 1;   // emit_compact + prompt_offsets
     }
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->prof.h2d[0], ctx->prof.h2d[1]) == cudaSuccess) p.h2d_ms = ms;
@@ -163,6 +163,9 @@ void fill_profile(cfbpe_ctx* ctx, uint64_t n_bytes) {
     p.n_bytes = n_bytes;
     p.n_long_bytes = ctx->h_status->long_bytes;
     p.n_long_tokens = ctx->h_status->long_tokens;
+    p.n_miss_pieces = static_cast<uint64_t>(ctx->h_status->miss_n[0]) + ctx->h_status->miss_n[1] + ctx->h_status->miss_n[2];
+    p.n_list_pieces = ctx->h_status->defer_n;
+    p.n_list_parts = ctx->h_status->defer_parts;
     ctx->prof_ready = true;
 }
 

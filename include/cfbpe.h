@@ -102,7 +102,9 @@ typedef struct cfbpe_profile {
     uint32_t kernel_launches[CFBPE_NUM_KERNELS];
     float h2d_ms, d2h_ms, total_ms;
     uint64_t n_tokens, n_bytes, n_long_pieces;
-    uint64_t n_long_bytes, n_long_tokens; /* bytes in / ids out of the long-piece kernel */
+    uint64_t n_long_bytes, n_long_tokens; /* bytes in / ids out of the long-piece kernels */
+    uint64_t n_miss_pieces;               /* short pieces that were not one token (merged by bpe_merge) */
+    uint64_t n_list_pieces, n_list_parts; /* long pieces whose list phase ran in bpe_list, and their parts at hand-over */
 } cfbpe_profile;
 
 CFBPE_API int cfbpe_abi_version(void);

@@ -46,7 +46,7 @@ def test_struct_layouts_match_the_header():
     from cfbpe import _native as N
     assert ctypes.sizeof(N.Config) == 24
     assert ctypes.sizeof(N.VocabInfo) == 24
-    assert ctypes.sizeof(N.Profile) == 4 * 10 + 4 * 10 + 12 + 4 + 40
+    assert ctypes.sizeof(N.Profile) == 4 * 10 + 4 * 10 + 12 + 4 + 64
 
 
 def test_create_fails_without_a_device(lib):
