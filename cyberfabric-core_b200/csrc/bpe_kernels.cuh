@@ -1148,9 +1148,13 @@ constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 // "xyzxyz...") goes one merge per round here: after three rounds in a row that were cut by a pair of the rank just taken
 // the function returns false and the caller does a batched round (array_compact + array_round), which takes them all.
 // s_red: 3 * kWarps + 2 words of shared memory (kWarps > 1 only).
+// dirty != nullptr (one word per thread): a thread keeps its proposal -- chunk minima, neighbours, the two looked-up pairs --
+// from round to round and recomputes only after its merge was taken, after a conflict, or after another thread's merge wrote
+// into its chunk (the writer marks the owner).  Per round ~20 of 512 proposals are taken; without this the other ~490 threads
+// redid the chunk scan and both table probes every round (160 warp instructions per merge, profiles/ncu_lines_bpe_list_r01n.txt).
 template <uint32_t kWarps, uint32_t kPosBits>
 __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* id, uint32_t* kk, uint32_t* link, uint32_t* claim,
-                                                uint32_t m, uint32_t* s_red) {
+                                                uint32_t m, uint32_t* s_red, uint32_t* dirty = nullptr) {
     constexpr uint32_t kNoPrev = 0xFFFFu, kPosMask = (1u << kPosBits) - 1u, P = kWarps * 32;
     const uint32_t tid = threadIdx.x % P, lane = tid & 31, wid = tid >> 5;
     auto group_sync = [&]() { if (kWarps == 1) __syncwarp(); else __syncthreads(); };
@@ -1160,6 +1164,7 @@ __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* i
         link[i] = ((i + 1) << 16) | (i ? i - 1 : kNoPrev);
         claim[i] = kNoKey;
     }
+    if (dirty) dirty[tid] = 0;
     uint32_t* const eq_flag = s_red + 2 * kWarps;     // [2], by round parity
     if (kWarps > 1 && tid == 0) { eq_flag[0] = 0; eq_flag[1] = 0; }
     group_sync();
@@ -1168,29 +1173,41 @@ __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* i
     if (c > 1) c |= 1u;                               // odd: the threads' chunks start in different banks
     const uint32_t lo = tid * c < m ? tid * c : m;
     const uint32_t hi = lo + c < m ? lo + c : m;
+    const uint32_t inv_c = (1u << 20) / c + 1u;       // owner of position p = (p * inv_c) >> 20  (exact for p < 4096)
+    bool have = false;
+    uint32_t m1 = kNoKey, m2 = kNoKey, j = 0, q = kNoPrev, k = m, Lk = kNoKey, Rk = kNoKey;
     for (uint32_t round = 0;; ++round) {
-        // -- smallest and second-smallest key of my chunk
-        uint32_t m1 = kNoKey, m2 = kNoKey;
-        for (uint32_t x = lo; x < hi; ++x) {
-            const uint32_t v = kk[x];
-            const uint32_t hi2 = v > m1 ? v : m1;
-            m2 = hi2 < m2 ? hi2 : m2;
-            m1 = v < m1 ? v : m1;
+        if (dirty && have && dirty[tid]) have = false;
+        if (!have) {
+            if (dirty) dirty[tid] = 0;
+            // -- smallest and second-smallest key of my chunk
+            m1 = kNoKey; m2 = kNoKey;
+            for (uint32_t x = lo; x < hi; ++x) {
+                const uint32_t v = kk[x];
+                const uint32_t hi2 = v > m1 ? v : m1;
+                m2 = hi2 < m2 ? hi2 : m2;
+                m1 = v < m1 ? v : m1;
+            }
+            // -- my proposal: parts q | x j | k, and the pairs (q, xj) and (xj, k)
+            Lk = kNoKey; Rk = kNoKey;
+            if (m1 != kNoKey) {
+                const uint32_t x = m1 & kPosMask, r = m1 >> kPosBits;
+                const uint32_t li = link[x];
+                j = li >> 16; q = li & 0xFFFFu;
+                k = link[j] >> 16;
+                const uint32_t idk = (k < m) ? id[k] : 0u;
+                const uint32_t idq = (q != kNoPrev) ? id[q] : 0u;
+                uint32_t R, L;
+                pair_lookup2(T, r, idk, k < m, idq, r, q != kNoPrev, R, L);
+                if (R != kNone) Rk = (R << kPosBits) | x;
+                if (L != kNone) Lk = (L << kPosBits) | q;
+            }
+            have = dirty != nullptr;
         }
-        // -- my proposal: parts q | x j | k, and the pairs (q, xj) and (xj, k)
         const bool valid = m1 != kNoKey;
-        uint32_t x = 0, j = 0, q = kNoPrev, k = m, r = 0, Lk = kNoKey, Rk = kNoKey, v = kNoKey;
+        const uint32_t x = m1 & kPosMask, r = m1 >> kPosBits;
+        uint32_t v = kNoKey;
         if (valid) {
-            x = m1 & kPosMask; r = m1 >> kPosBits;
-            const uint32_t li = link[x];
-            j = li >> 16; q = li & 0xFFFFu;
-            k = link[j] >> 16;
-            const uint32_t idk = (k < m) ? id[k] : 0u;
-            const uint32_t idq = (q != kNoPrev) ? id[q] : 0u;
-            uint32_t R, L;
-            pair_lookup2(T, r, idk, k < m, idq, r, q != kNoPrev, R, L);
-            if (R != kNone) Rk = (R << kPosBits) | x;
-            if (L != kNone) Lk = (L << kPosBits) | q;
             uint32_t cc = m2 < Lk ? m2 : Lk;
             cc = cc < Rk ? cc : Rk;
             v = cc > m1 + 1u ? cc : m1 + 1u;
@@ -1206,7 +1223,7 @@ __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* i
             lowest = cj < lowest ? cj : lowest;
             if (q != kNoPrev) { const uint32_t cq = claim[q]; lowest = cq < lowest ? cq : lowest; }
             if (k < m) { const uint32_t ck = claim[k]; lowest = ck < lowest ? ck : lowest; }
-            if (lowest < m1) v = m1;                   // someone earlier touches my neighbourhood: the round ends before me
+            if (lowest < m1) { v = m1; have = false; } // someone earlier touches my neighbourhood: the round ends before me
         }
         // -- cut = min over the group
         uint32_t cut = __reduce_min_sync(kFull, v);
@@ -1234,6 +1251,11 @@ __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* i
                 link[x] = (k << 16) | q;
                 if (k < m) link[k] = (link[k] & 0xFFFF0000u) | x;
                 if (q != kNoPrev) kk[q] = Lk;
+                have = false;
+                if (dirty) {      // the pairs at j and q may belong to other threads' chunks
+                    if (j >= hi) dirty[(j * inv_c) >> 20] = 1u;
+                    if (q != kNoPrev && q < lo) dirty[(q * inv_c) >> 20] = 1u;
+                }
             }
         }
         group_sync();
@@ -1244,7 +1266,7 @@ __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* i
             // rounds: it has to take a fair share of the piece (random text repeats a pair a few times; that is not it)
             const uint32_t er = cut >> kPosBits;
             uint32_t cnt = 0;
-            for (uint32_t x = lo; x < hi; ++x) cnt += (kk[x] >> kPosBits) == er ? 1u : 0u;
+            for (uint32_t y = lo; y < hi; ++y) cnt += (kk[y] >> kPosBits) == er ? 1u : 0u;
             cnt = __reduce_add_sync(kFull, cnt);
             if (kWarps > 1) {
                 uint32_t* sum = s_red + 2 * kWarps + 2;
@@ -1441,6 +1463,7 @@ bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
     CFBPE_DYN_SMEM(s_dyn);
     __shared__ uint32_t s_red[3 * kListWarps + 2];
     __shared__ uint32_t s_item, s_m, s_rmin;
+    __shared__ uint32_t s_dirty[kListWarps * 32];
     const uint32_t n_big = status->long_overflow ? 0u : status->n_big;
     uint32_t* const id = s_dyn;
     uint32_t* const kk = s_dyn + kDeferMaxParts;
@@ -1462,7 +1485,7 @@ bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
         for (uint32_t i = threadIdx.x; i < m; i += kListWarps * 32) { id[i] = gid[i]; kk[i] = grk[i]; }
         __syncthreads();
         for (;;) {
-            const bool done = list_rounds_par<kListWarps, 12>(T, id, kk, link, claim, m, s_red);
+            const bool done = list_rounds_par<kListWarps, 12>(T, id, kk, link, claim, m, s_red, s_dirty);
             __syncthreads();
             if (done) break;
             // a stretch of same-rank pairs: batched rounds, by the first warp (their lookups are all the same few
