@@ -33,6 +33,7 @@ inline unsigned long long* dbg_counters() { static unsigned long long c[8]; retu
 #endif
 // 0: pieces deferred to bpe_list_kernel  1: list -> batched switches (medium pieces)  2: the same in bpe_list_kernel
 // 3: K1 bulk whitespace runs  4: K1 bulk digit runs  5: pieces on the global-memory list path
+// 6: rounds of bpe_list_kernel  7: merges taken in them
 
 #ifndef CFBPE_SPLIT_CHUNK
 #define CFBPE_SPLIT_CHUNK 64
@@ -1238,6 +1239,8 @@ __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* i
             __syncwarp();
         }
         if (cut == kNoKey) return true;
+        if (kWarps > 1 && tid == 0) CFBPE_DBG_COUNT(6);
+        if (kWarps > 1 && valid && m1 < cut) CFBPE_DBG_COUNT(7);
         // -- a pair of the rank I just took ended the round (not the pair my own merge creates): same-rank stretch
         bool eq = valid && m1 < cut && cut != m1 + 1u && (cut >> kPosBits) == (m1 >> kPosBits);
         if (kWarps == 1) eq = __any_sync(kFull, eq);
@@ -1357,12 +1360,14 @@ constexpr uint32_t kListMaxRank = (1u << 20) - 1u;   // K2c packs rank << 12 | p
 
 // One warp per CTA: a warp that is deep in the serial chain of a long piece then holds one warp's worth of registers and
 // 6 KB of shared memory, not a whole CTA's, so the tail of this kernel can share the SMs with whatever runs next.
-constexpr uint32_t kLongWarps = 1;
+constexpr uint32_t kLongWarps = 4;
 __global__ void __launch_bounds__(kLongWarps * 32, 32 / kLongWarps)
 bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
+#ifdef CFBPE_SINGLE_MERGE_ROUNDS
     __shared__ uint32_t s_subr[kLongWarps][8][32];   // [warp][sub-chunk][lane] cached minimum rank ...
     __shared__ uint32_t s_subp[kLongWarps][8][32];   // ... and its position (phase B)
+#endif
     __shared__ uint32_t s_med[kLongWarps][4][kMedSmem];   // [warp][id | rank | aux0 | aux1] of a piece of <= kMedSmem bytes
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_big = status->n_big;
@@ -1456,7 +1461,7 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
 // per part -- in 64 KB of dynamic shared memory, parallel-cut rounds (list_rounds_par): a round costs one table round trip
 // and a few hundred cycles of shared-memory work and takes ~20 merges.  Three such CTAs fit an SM.  Tickets run over the
 // big end of the long-piece list.
-constexpr uint32_t kListWarps = 16;
+constexpr uint32_t kListWarps = 4;
 __global__ void __launch_bounds__(kListWarps * 32, 3)
 bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {

@@ -375,7 +375,11 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status_arr), sizeof(DeviceStatus) * kMaxPipeChunks) == cudaSuccess;
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_offs_stage), sizeof(uint64_t) * (mp + 1 + kMaxPipeChunks)) == cudaSuccess;
     for (int k = 0; ok && k < kSideStreams; ++k) ok = cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
+    {   // the long-piece kernels are latency-bound and small: their CTAs go first, the short-piece kernels fill the rest
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        ok = ok && cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+    }
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; ok && k < kMaxPipeChunks; ++k) ok = cudaEventCreateWithFlags(&ctx->ev_scan[k], cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; ok && k < kMaxPipeChunks; ++k)

@@ -109,8 +109,9 @@ inline void enqueue_long(const BatchView& b, const VocabSet& vs, const Workspace
     CFBPE_MARK(prof, K_LONG, stream, false);
 #ifndef CFBPE_NO_DEFER
     CFBPE_MARK(prof, K_LIST, stream, true);
-    // the list phase of the big pieces K2b deferred: three 64 KB CTAs per SM (long_grid = 4 x SM count)
-    CFBPE_LAUNCH_SMEM(bpe_list_kernel, long_grid - long_grid / 4, kListWarps * 32, kListSmemBytes, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
+    // the list phase of the big pieces K2b deferred: two 64 KB CTAs per SM (long_grid = 4 x SM count), so that the short-piece
+    // kernels on the other stream keep ~100 KB of shared memory per SM
+    CFBPE_LAUNCH_SMEM(bpe_list_kernel, long_grid / 2, kListWarps * 32, kListSmemBytes, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
     CFBPE_MARK(prof, K_LIST, stream, false);
 #endif
 }
