@@ -64,6 +64,7 @@ struct cfbpe_ctx {
     cudaStream_t aux_stream = nullptr;   // the long-piece kernel runs here, next to the short-piece kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_scan[kMaxPipeChunks] = {};
+    cudaStream_t stream2 = nullptr;        // second front stream of a pipelined host call
     cudaStream_t side[kSideStreams] = {};  // long-piece tails + emit of sub-batch k overlap the front of k+1
     cudaEvent_t ev_front[kMaxPipeChunks] = {};
     cudaEvent_t ev_h2d[kMaxPipeChunks] = {};
@@ -211,7 +212,8 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         CK(cudaMemcpyAsync(ctx->d_offsets + p0 + k, ctx->h_offs_stage + p0 + k, (static_cast<uint64_t>(nk) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, hs));
         if (vocab_ids && nk) CK(cudaMemcpyAsync(ctx->d_vocab_ids + p0, vocab_ids + p0, nk, cudaMemcpyHostToDevice, hs));
         CK(cudaEventRecord(ctx->ev_h2d[k], hs));
-        CK(cudaStreamWaitEvent(cs, ctx->ev_h2d[k], 0));
+        cudaStream_t ck = (k & 1) ? ctx->stream2 : cs;   // two front streams: the tails of sub-batch k overlap the front of k+1
+        CK(cudaStreamWaitEvent(ck, ctx->ev_h2d[k], 0));
         Workspace w = ctx->ws;
         const uint64_t w0 = (o0 >> 5) + 4ull * k;
         w.piece_bits += w0; w.tok_bits += w0;
@@ -224,12 +226,12 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         w.miss = slice_miss(ctx->ws.miss, o0, len, static_cast<uint32_t>(k));
         BatchView b{ctx->d_bytes + o0, ctx->d_offsets + p0 + k, vocab_ids ? ctx->d_vocab_ids + p0 : nullptr, nk, len};
         cudaStream_t ss = ctx->side[k % kSideStreams];
-        enqueue_split(b, ctx->vs, ctx->uc, w, cs, static_cast<ProfEvents*>(nullptr));
-        CK(cudaEventRecord(ctx->ev_scan[k], cs));
+        enqueue_split(b, ctx->vs, ctx->uc, w, ck, static_cast<ProfEvents*>(nullptr));
+        CK(cudaEventRecord(ctx->ev_scan[k], ck));
         CK(cudaStreamWaitEvent(ss, ctx->ev_scan[k], 0));
         enqueue_long(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ss, static_cast<ProfEvents*>(nullptr));   // tail overlaps what follows on cs
-        enqueue_short(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), cs, static_cast<ProfEvents*>(nullptr));
-        CK(cudaEventRecord(ctx->ev_front[k], cs));
+        enqueue_short(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ck, static_cast<ProfEvents*>(nullptr));
+        CK(cudaEventRecord(ctx->ev_front[k], ck));
         CK(cudaStreamWaitEvent(ss, ctx->ev_front[k], 0));
         if (k) CK(cudaStreamWaitEvent(ss, ctx->ev_done[k - 1], 0));     // token ranks chain through DeviceStatus::tok_end
         enqueue_back(b, w, want_ids ? ctx->d_out_ids : nullptr, ctx->max_bytes, ctx->d_out_offsets + p0 + k, ctx->d_out_counts + p0,
@@ -257,6 +259,7 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
     }
     CK(cudaStreamSynchronize(ds));
     CK(cudaStreamSynchronize(cs));
+    CK(cudaStreamSynchronize(ctx->stream2));
     for (int k = 0; k < kSideStreams; ++k) CK(cudaStreamSynchronize(ctx->side[k]));
     if (err) return err;
     if (want_ids && tok_total > out_cap) {
@@ -374,7 +377,12 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     ok = ok && dmalloc(&ctx->d_status_arr, kMaxPipeChunks) == cudaSuccess;
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status_arr), sizeof(DeviceStatus) * kMaxPipeChunks) == cudaSuccess;
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_offs_stage), sizeof(uint64_t) * (mp + 1 + kMaxPipeChunks)) == cudaSuccess;
-    for (int k = 0; ok && k < kSideStreams; ++k) ok = cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        for (int k = 0; ok && k < kSideStreams; ++k) ok = cudaStreamCreateWithPriority(&ctx->side[k], cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+    }
     {   // the long-piece kernels are latency-bound and small: their CTAs go first, the short-piece kernels fill the rest
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -434,6 +442,7 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     if (ctx->h_offs_stage) cudaFreeHost(ctx->h_offs_stage);
     cudaFree(ctx->d_status_arr);
     for (int k = 0; k < kMaxPipeChunks; ++k) { if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]); if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]); if (ctx->ev_front[k]) cudaEventDestroy(ctx->ev_front[k]); }
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     for (int k = 0; k < kSideStreams; ++k) if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
     for (int k = 0; k < kMaxPipeChunks; ++k) if (ctx->ev_scan[k]) cudaEventDestroy(ctx->ev_scan[k]);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
