@@ -160,6 +160,7 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
 
     uint32_t pidx = find_prompt(b.offsets, b.n_prompts, cs);
     uint64_t ps = b.offsets[pidx], pe = b.offsets[pidx + 1];
+    uc.ascii_x = s_ascii;   // the copy in shared memory
 
     // ---- find the first sync point in [cs, ce)
     uint64_t pos = cs;
@@ -182,8 +183,14 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
     const uint16_t* tab = s_fsm + pat * kPretokTableSize;
     uint64_t alc = 0, last = 0, lbe = 0;
     int bad = 0;
-    uint64_t cur_word = pos >> 5;
-    uint32_t cur_bits = 0;
+    // boundaries inside my chunk collect in one 64-bit mask (the chunk is 64-byte aligned: two flag words, OR-ed in at the
+    // end because the thread to my left may have set bits there while handing over); those beyond it go out one by one
+    static_assert(kSplitChunk <= 64, "the chunk mask is one 64-bit word");
+    uint64_t mine = 0;
+    auto mark = [&](uint64_t p) {
+        if (p - cs < kSplitChunk) mine |= 1ull << (p - cs);
+        else atomicOr(&piece_bits[p >> 5], 1u << (p & 31));
+    };
     for (;;) {
         uint32_t x, len, b0 = 0x100u;
         if (pos == pe) { x = X_EOT; len = 0; }
@@ -200,9 +207,9 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
         }
         // retroactive boundaries (all at positions I own)
         if (a & (A_EMIT_ALC | A_EMIT_LAST | A_EMIT_LBE)) {
-            if (a & A_EMIT_ALC) { if ((alc >> 5) == cur_word) cur_bits |= 1u << (alc & 31); else atomicOr(&piece_bits[alc >> 5], 1u << (alc & 31)); }
-            if (a & A_EMIT_LAST) { if ((last >> 5) == cur_word) cur_bits |= 1u << (last & 31); else atomicOr(&piece_bits[last >> 5], 1u << (last & 31)); }
-            if (a & A_EMIT_LBE) { if ((lbe >> 5) == cur_word) cur_bits |= 1u << (lbe & 31); else atomicOr(&piece_bits[lbe >> 5], 1u << (lbe & 31)); }
+            if (a & A_EMIT_ALC) mark(alc);
+            if (a & A_EMIT_LAST) mark(last);
+            if (a & A_EMIT_LBE) mark(lbe);
         }
         if (x == X_EOT) {
             if (pos >= b.total_bytes) break;
@@ -218,11 +225,7 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
         // (after the retroactive boundaries above, which concern positions of mine); same predicate as
         // sync_state(), evaluated on the classes just seen
         if (pos >= ce && (bad || sync_rule(x, prevx, nlet, npun, (pat & 1u) != 0) != kNoSync)) break;
-        if (a & A_B_NOW) {
-            const uint64_t w = pos >> 5;
-            if (w != cur_word) { or_bits(piece_bits, cur_word, cur_bits); cur_word = w; cur_bits = 0; }
-            cur_bits |= 1u << (pos & 31);
-        }
+        if (a & A_B_NOW) mark(pos);
         if (a & A_SET_ALC) alc = pos + len;
         if (a & A_SET_LAST) last = pos;
         if (a & A_SET_LBE) lbe = pos + len;
@@ -265,10 +268,14 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
                     CFBPE_DBG_COUNT(4);
                     const uint64_t e = ascii_digit_run_end(s, pos, pe);
                     const uint32_t d = state - S_D1 + 1u;                        // digits in the current piece so far
-                    for (uint64_t p = pos + (md - d); p < e; p += md) {
-                        const uint64_t w = p >> 5;
-                        if (w != cur_word) { or_bits(piece_bits, cur_word, cur_bits); cur_word = w; cur_bits = 0; }
-                        cur_bits |= 1u << (p & 31);
+                    {   // only beyond my chunk (pos >= ce): word-wise
+                        uint64_t cw = ~0ull; uint32_t cb = 0;
+                        for (uint64_t p = pos + (md - d); p < e; p += md) {
+                            const uint64_t w = p >> 5;
+                            if (w != cw) { if (cb) atomicOr(&piece_bits[cw], cb); cw = w; cb = 0; }
+                            cb |= 1u << (p & 31);
+                        }
+                        if (cb) atomicOr(&piece_bits[cw], cb);
                     }
                     state = S_D1 + static_cast<uint32_t>((d - 1u + (e - pos)) % md);
                     pos = e; prevx = X_N; nlet = 0; npun = 0;
@@ -276,7 +283,8 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
             }
         }
     }
-    or_bits(piece_bits, cur_word, cur_bits);
+    or_bits(piece_bits, cs >> 5, static_cast<uint32_t>(mine));
+    or_bits(piece_bits, (cs >> 5) + 1, static_cast<uint32_t>(mine >> 32));
     if (bad) atomicOr(&status->bad_utf8, 1u);
 }
 

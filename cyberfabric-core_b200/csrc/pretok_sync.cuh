@@ -49,21 +49,18 @@ CFBPE_HD uint32_t sync_state(const Txt& s, uint64_t pos, uint64_t ps, uint64_t p
                              uint32_t* prevx_out = nullptr, uint32_t* nlet_out = nullptr, uint32_t* npun_out = nullptr) {
     const uint32_t b = s[pos];
     if ((b & 0xC0) == 0x80) return kNoSync;  // inside a character
-    // two ASCII special cases of the rule below, decided from raw bytes (most positions of Latin-script text end here)
+    // four ASCII bytes of context: the rule from the class table alone, no decoding (almost every position of Latin-script
+    // text ends here, and all lanes run the same few instructions)
     if (pos >= ps + 3) {
         const uint32_t b1 = s[pos - 1], b2 = s[pos - 2], b3 = s[pos - 3];
-        const bool l1 = ((b1 | 0x20u) - 'a') < 26u, l2 = ((b2 | 0x20u) - 'a') < 26u, l3 = ((b3 | 0x20u) - 'a') < 26u;
-        if (b == ' ' && b1 < 0x80 && ascii_class(b1) != C_WS && ascii_class(b1) != C_CRLF) {   // space after an ASCII non-space
-            if (prevx_out) *prevx_out = b1 == '\'' ? X_APOS : (b1 == '/' ? X_SLASH : ascii_class(b1));
-            if (nlet_out) *nlet_out = 0;
-            if (npun_out) *npun_out = 0;
-            return S_START;
-        }
-        if (((b | 0x20u) - 'a') < 26u && l1 && l2 && l3 && (!cased || (b1 - 'a') < 26u)) {           // fourth letter of an ASCII word
-            if (prevx_out) *prevx_out = (b1 - 'a') < 26u ? X_LL : X_LU;
-            if (nlet_out) *nlet_out = 3;
-            if (npun_out) *npun_out = 0;
-            return cased ? static_cast<uint32_t>(S_W_Y) : static_cast<uint32_t>(S_LETTERS);
+        if ((b | b1 | b2 | b3) < 0x80u) {
+            const uint32_t x = uc.ascii_x[b], p1 = uc.ascii_x[b1], p2 = uc.ascii_x[b2], p3 = uc.ascii_x[b3];
+            const uint32_t nlet = x_is_letter(p1) ? (x_is_letter(p2) ? (x_is_letter(p3) ? 3u : 2u) : 1u) : 0u;
+            const uint32_t npun = x_is_run_punct(p1, cased) ? (x_is_run_punct(p2, cased) ? 2u : 1u) : 0u;
+            if (prevx_out) *prevx_out = p1;
+            if (nlet_out) *nlet_out = nlet;
+            if (npun_out) *npun_out = npun;
+            return sync_rule(x, p1, nlet, npun, cased);
         }
     }
     int bad = 0;
