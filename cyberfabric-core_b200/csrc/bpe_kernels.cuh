@@ -1190,12 +1190,25 @@ __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* i
         if (!have) {
             if (dirty) dirty[tid] = 0;
             // -- smallest and second-smallest key of my chunk
+            // (eight loads in flight, two independent min chains: this scan is on the critical path of the round)
             m1 = kNoKey; m2 = kNoKey;
-            for (uint32_t x = lo; x < hi; ++x) {
-                const uint32_t v = kk[x];
-                const uint32_t hi2 = v > m1 ? v : m1;
-                m2 = hi2 < m2 ? hi2 : m2;
-                m1 = v < m1 ? v : m1;
+            uint32_t n1 = kNoKey, n2 = kNoKey;
+            for (uint32_t xb = lo; xb < hi; xb += 8) {
+                uint32_t v[8];
+#pragma unroll
+                for (uint32_t t = 0; t < 8; ++t) v[t] = (xb + t < hi) ? kk[xb + t] : kNoKey;
+#pragma unroll
+                for (uint32_t t = 0; t < 8; t += 2) {
+                    const uint32_t a = v[t], b = v[t + 1];
+                    const uint32_t ha = a > m1 ? a : m1, hb = b > n1 ? b : n1;
+                    m2 = ha < m2 ? ha : m2; n2 = hb < n2 ? hb : n2;
+                    m1 = a < m1 ? a : m1; n1 = b < n1 ? b : n1;
+                }
+            }
+            {   // merge the two chains: smallest and second smallest of {m1, m2, n1, n2}
+                const uint32_t lo1 = m1 < n1 ? m1 : n1, hi1 = m1 < n1 ? n1 : m1;
+                const uint32_t s2 = m2 < n2 ? m2 : n2;
+                m1 = lo1; m2 = hi1 < s2 ? hi1 : s2;
             }
             // -- my proposal: parts q | x j | k, and the pairs (q, xj) and (xj, k)
             Lk = kNoKey; Rk = kNoKey;

@@ -42,7 +42,7 @@ static inline void prof_mark(ProfEvents* p, int idx, cudaStream_t s, bool begin)
 
 constexpr int kMaxPipeChunks = 64;
 constexpr int kSideStreams = 16;
-constexpr uint64_t kPipeChunkBytes = 24ull << 20;   // sub-batch size of a pipelined host call (measured best on 134 MB: profiles/e2e_subbatch_sizes_r01n.jsonl)
+constexpr uint64_t kPipeChunkBytes = 64ull << 20;   // middle sub-batches of a pipelined host call (the first and last are a third of this); measured: profiles/e2e_subbatch_sizes_r01p.jsonl
 constexpr uint64_t kPipeMinBytes = 40ull << 20;     // smaller calls run as one shot
 
 struct VocabSlot {
@@ -183,17 +183,27 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
     uint32_t cut[kMaxPipeChunks + 1];
     int nc = 0;
     {
+        // a small first sub-batch (the kernels start after a third of an upload slot) and a small last one (what is left to
+        // download when the kernels end), equal ones in between
         uint64_t chunk = ctx->pipe_chunk;
-        if ((total + chunk - 1) / chunk > static_cast<uint64_t>(kMaxPipeChunks)) chunk = (total + kMaxPipeChunks - 1) / kMaxPipeChunks;
+        if ((total + chunk - 1) / chunk + 2 > static_cast<uint64_t>(kMaxPipeChunks)) chunk = (total + kMaxPipeChunks - 3) / (kMaxPipeChunks - 2);
+        const uint64_t edge = chunk / 3 ? chunk / 3 : 1;
+        uint64_t n_mid = total > 2 * edge ? (total - 2 * edge + chunk - 1) / chunk : 0;
+        const uint64_t mid = n_mid ? (total - 2 * edge + n_mid - 1) / n_mid : 0;
         cut[0] = 0;
         uint32_t p = 0;
+        uint64_t target = edge;
         while (p < n) {
-            const uint64_t target = offsets[p] + chunk;
             uint32_t lo = p + 1, hi = n;                 // first q > p with offsets[q] >= target (or n)
-            while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (offsets[mid] >= target) hi = mid; else lo = mid + 1; }
+            while (lo < hi) { const uint32_t m2 = lo + (hi - lo) / 2; if (offsets[m2] >= target) hi = m2; else lo = m2 + 1; }
             p = lo;
             if (nc + 1 == kMaxPipeChunks) p = n;
             cut[++nc] = p;
+            if (p < n) {
+                const uint64_t done = offsets[p];
+                target = (n_mid && done + edge / 2 < total - edge) ? done + mid : total;
+                if (target > total - edge && target < total && done < total - edge) target = total - edge;
+            }
         }
     }
     cudaStream_t cs = ctx->stream, hs = ctx->h2d_stream, ds = ctx->d2h_stream;
