@@ -33,7 +33,9 @@ for r in rows[2:]:
         d["duration_ms"] = d.pop("duration")
     res.append(d)
     if "dram_read" in d:
-        traffic[name.replace("_kernel", "")] = d["dram_read"] + d.get("dram_write", 0)
+        short = name.replace("_kernel", "").replace("void ", "")
+        short = {"bpe_lookup": "bpe_encode", "bpe_encode_pieces<1>": "long_scan", "bpe_encode_pieces<2>": "bpe_encode_fused"}.get(short, short)   # bench.py's names
+        traffic[short] = d["dram_read"] + d.get("dram_write", 0)
 json.dump(res, open(out, "w"), indent=1)
 if len(sys.argv) > 3:
     json.dump(traffic, open(sys.argv[3], "w"), indent=1)
