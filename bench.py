@@ -332,7 +332,7 @@ def main():
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "vocab": rv.label, "vocab_stand_in": rv.stand_in, "prompts_per_gpu": n,
                    "total_bytes_per_gpu": total, "tokens_per_gpu": n_tokens, "bytes_per_token": total / max(n_tokens, 1),
-                   "long_pieces_per_gpu": int(n_long), "long_piece_bytes_per_gpu": int(long_bytes), "seed": cfg["seed"], "parallelism": "dp%d (batch-sharded, no data-path collective)" % world,
+                   "long_pieces_per_gpu": int(n_long), "long_piece_bytes_per_gpu": int(long_bytes), "short_miss_pieces_per_gpu": int(n_miss), "list_pieces_per_gpu": int(n_list), "list_parts_per_gpu": int(list_parts), "seed": cfg["seed"], "parallelism": "dp%d (batch-sharded, no data-path collective)" % world,
                    "l2": "inputs (%.0f MB) and per-byte work arrays (> 1 GB) exceed the 126 MB L2; no flush needed" % (total / 1e6),
                    "scale": args.scale},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
