@@ -1193,7 +1193,20 @@ __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* i
             // (eight loads in flight, two independent min chains: this scan is on the critical path of the round)
             m1 = kNoKey; m2 = kNoKey;
             uint32_t n1 = kNoKey, n2 = kNoKey;
-            for (uint32_t xb = lo; xb < hi; xb += 8) {
+            uint32_t xb = lo;
+            for (; xb + 8 <= hi; xb += 8) {            // whole batches: no bounds checks
+                uint32_t v[8];
+#pragma unroll
+                for (uint32_t t = 0; t < 8; ++t) v[t] = kk[xb + t];
+#pragma unroll
+                for (uint32_t t = 0; t < 8; t += 2) {
+                    const uint32_t a = v[t], b = v[t + 1];
+                    const uint32_t ha = a > m1 ? a : m1, hb = b > n1 ? b : n1;
+                    m2 = ha < m2 ? ha : m2; n2 = hb < n2 ? hb : n2;
+                    m1 = a < m1 ? a : m1; n1 = b < n1 ? b : n1;
+                }
+            }
+            if (xb < hi) {                             // the rest: one predicated batch
                 uint32_t v[8];
 #pragma unroll
                 for (uint32_t t = 0; t < 8; ++t) v[t] = (xb + t < hi) ? kk[xb + t] : kNoKey;
@@ -1229,9 +1242,11 @@ __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* i
         const bool valid = m1 != kNoKey;
         const uint32_t x = m1 & kPosMask, r = m1 >> kPosBits;
         uint32_t v = kNoKey;
+        bool viol = false;                             // my merge creates a pair that ranks below it: that pair is next, whatever else is there
         if (valid) {
             uint32_t cc = m2 < Lk ? m2 : Lk;
             cc = cc < Rk ? cc : Rk;
+            viol = cc <= m1;
             v = cc > m1 + 1u ? cc : m1 + 1u;
             if (v == kNoKey) v = kNoKey - 1u;          // kNoKey is reserved for "no proposal anywhere"
             atomicMin(&claim[x], m1);
@@ -1262,8 +1277,8 @@ __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* i
         if (cut == kNoKey) return true;
         if (kWarps > 1 && tid == 0) CFBPE_DBG_COUNT(6);
         if (kWarps > 1 && valid && m1 < cut) CFBPE_DBG_COUNT(7);
-        // -- a pair of the rank I just took ended the round (not the pair my own merge creates): same-rank stretch
-        bool eq = valid && m1 < cut && cut != m1 + 1u && (cut >> kPosBits) == (m1 >> kPosBits);
+        // -- a pair of the rank I just took ended the round (and not because my own merge creates a lower pair): same-rank stretch
+        bool eq = valid && m1 < cut && !viol && (cut >> kPosBits) == (m1 >> kPosBits);
         if (kWarps == 1) eq = __any_sync(kFull, eq);
         else if (eq) eq_flag[round & 1u] = 1u;
         // -- apply what was taken; withdraw the claims
@@ -1482,7 +1497,10 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
 // per part -- in 64 KB of dynamic shared memory, parallel-cut rounds (list_rounds_par): a round costs one table round trip
 // and a few hundred cycles of shared-memory work and takes ~20 merges.  Three such CTAs fit an SM.  Tickets run over the
 // big end of the long-piece list.
-constexpr uint32_t kListWarps = 4;
+#ifndef CFBPE_LIST_WARPS
+#define CFBPE_LIST_WARPS 8
+#endif
+constexpr uint32_t kListWarps = CFBPE_LIST_WARPS;
 __global__ void __launch_bounds__(kListWarps * 32, 3)
 bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
