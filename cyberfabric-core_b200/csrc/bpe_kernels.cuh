@@ -547,17 +547,18 @@ __device__ __forceinline__ void merge_piece_in_lane(const TablesView& T, const u
             rkv[t] = (k0 + t + 1 < len) ? T.bytepair[(bv[t] << 8) | bv[t + 1]] : kNone;
         }
 #pragma unroll
-        for (uint32_t t = 0; t < 4; ++t) if (k0 + t < len) { sid[(k0 + t) * 32] = idv[t]; srk[(k0 + t) * 32] = rkv[t]; }
+        for (uint32_t t = 0; t < 4; ++t) if (k0 + t < len) { sid[(k0 + t) * 32] = idv[t]; srk[(k0 + t) * 32] = rkv[t] == kNone ? kNone : ((rkv[t] << 5) | (k0 + t)); }
     }
     uint32_t alive = (len >= 32) ? kFull : ((1u << len) - 1u);
     for (;;) {
-        uint32_t best = kNone, bi = 0;
-        for (uint32_t bits = alive; bits; bits &= bits - 1) {     // ascending positions, strict < : leftmost minimum
+        uint32_t bkey = kNone;
+        for (uint32_t bits = alive; bits; bits &= bits - 1) {     // key = rank << 5 | position: the minimum is the leftmost minimum rank
             const uint32_t k = static_cast<uint32_t>(__ffs(bits)) - 1u;
             const uint32_t r = srk[k * 32];
-            if (r < best) { best = r; bi = k; }
+            bkey = r < bkey ? r : bkey;
         }
-        if (best == kNone) break;
+        if (bkey == kNone) break;
+        const uint32_t best = bkey >> 5, bi = bkey & 31u;
         const uint32_t above = alive & ~((2u << bi) - 1u);
         const uint32_t nb = static_cast<uint32_t>(__ffs(above)) - 1u;          // the partner: it has one, its rank was not kNone
         alive &= ~(1u << nb);
@@ -569,8 +570,8 @@ __device__ __forceinline__ void merge_piece_in_lane(const TablesView& T, const u
         const uint32_t pv = wl ? 31u - static_cast<uint32_t>(__clz(below)) : 0u;
         uint32_t nr, nl;
         pair_lookup2(T, best, wr ? sid[nn * 32] : 0u, wr, wl ? sid[pv * 32] : 0u, best, wl, nr, nl);
-        srk[bi * 32] = nr;
-        if (wl) srk[pv * 32] = nl;
+        srk[bi * 32] = nr == kNone ? kNone : ((nr << 5) | bi);
+        if (wl) srk[pv * 32] = nl == kNone ? kNone : ((nl << 5) | pv);
     }
     for (uint32_t bits = alive; bits; bits &= bits - 1) {
         const uint32_t k = static_cast<uint32_t>(__ffs(bits)) - 1u;
@@ -716,7 +717,7 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
 //        warp ticket -- in the fused version the merge loops ran with 4-5 active lanes, because a warp only had the
 //        ~15 misses of its own 512 bytes to spread over its lanes (profiles/ncu_lines_bpe_encode_r01n.txt).
 // ---------------------------------------------------------------------------------------
-constexpr uint32_t kLookupWarps = 8;
+constexpr uint32_t kLookupWarps = 4;
 __global__ void __launch_bounds__(kLookupWarps * 32)
 bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits, uint32_t* __restrict__ ids_by_pos,
                   uint32_t* __restrict__ tok_bits, MissLists ml, DeviceStatus* status) {

@@ -148,6 +148,25 @@ CFBPE_HD uint32_t short_lookup(const TablesView& t, uint64_t k0, uint32_t k1, ui
         h = (h + 1) & t.short_mask;
     }
 }
+// four bytes at p (any alignment) as a little-endian word: two aligned loads and a funnel shift on the device
+// (both the text and the token blob are readable 16 bytes past their end)
+CFBPE_HD uint32_t load_u32_any(const uint8_t* p) {
+#if defined(__CUDA_ARCH__)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+    const uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
+    return sh ? __funnelshift_r(q[0], q[1], sh) : q[0];
+#else
+    return static_cast<uint32_t>(p[0]) | (static_cast<uint32_t>(p[1]) << 8) | (static_cast<uint32_t>(p[2]) << 16) |
+           (static_cast<uint32_t>(p[3]) << 24);
+#endif
+}
+// len >= 4 bytes equal?  four at a time, the last word overlapping
+CFBPE_HD bool bytes_equal(const uint8_t* a, const uint8_t* b, uint32_t len) {
+    uint32_t i = 0;
+    for (; i + 4 <= len; i += 4) if (load_u32_any(a + i) != load_u32_any(b + i)) return false;
+    return i == len || load_u32_any(a + len - 4) == load_u32_any(b + len - 4);
+}
 // id of a token of len >= 13 given its hash and a pointer to its bytes, or kNone
 CFBPE_HD uint32_t long_lookup(const TablesView& t, uint64_t hash, const uint8_t* bytes, uint32_t len) {
     uint32_t h = static_cast<uint32_t>(hash >> 17) & t.long_mask;
@@ -157,10 +176,7 @@ CFBPE_HD uint32_t long_lookup(const TablesView& t, uint64_t hash, const uint8_t*
         if (s.hash == hash && (s.meta >> 24) == (len & 0xFF)) {
             const uint32_t id = s.meta & 0x00FFFFFFu;
             if (t.tokoff[id + 1] - t.tokoff[id] == len) {
-                const uint8_t* tb = t.blob + s.blob_off;
-                uint32_t i = 0;
-                while (i < len && tb[i] == bytes[i]) ++i;
-                if (i == len) return id;
+                if (bytes_equal(t.blob + s.blob_off, bytes, len)) return id;
             }
         }
         h = (h + 1) & t.long_mask;
