@@ -15,6 +15,8 @@ the per-shard token totals are all_gathered every step (the path's only exchange
   roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs the measured HBM copy peak
   cpu_baseline  the oracle port on the host cores, bounded sample, rank 0 only
 """
+import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initialises: the pipelined host path keeps ~20 streams busy (DESIGN.md section 4)
 import argparse
 import json
 import os

@@ -5,6 +5,7 @@ import os
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # effective if CUDA is not initialised yet; see csrc/cfbpe.cu:cfbpe_create
 _DIR = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("CFBPE_SO_VARIANT") or os.path.join(_DIR, "libcfbpe.so")   # CFBPE_SO_VARIANT: A/B builds (tools only)
 

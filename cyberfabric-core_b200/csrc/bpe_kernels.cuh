@@ -1668,4 +1668,13 @@ prompt_offsets_kernel(BatchView b, const uint32_t* __restrict__ tok_bits, const 
     if (i < b.n_prompts && out_counts) out_counts[i] = static_cast<uint32_t>(rank_at(b.offsets[i + 1]) - r);
 }
 
+// the status of a sub-batch, stored straight into pinned host memory: a cudaMemcpyAsync would queue behind the previous
+// sub-batch's id download on the same copy engine, and the host would learn too late that the next download can start
+__global__ void status_publish_kernel(const DeviceStatus* __restrict__ d, DeviceStatus* h) {
+    static_assert(sizeof(DeviceStatus) % 4 == 0 && sizeof(DeviceStatus) <= 256, "one word per thread of a 64-thread block");
+    const uint32_t n = sizeof(DeviceStatus) / 4;
+    if (threadIdx.x < n) reinterpret_cast<volatile uint32_t*>(h)[threadIdx.x] = reinterpret_cast<const uint32_t*>(d)[threadIdx.x];
+    __threadfence_system();
+}
+
 }  // namespace cfbpe

@@ -4,6 +4,7 @@
 // computes runs the kernels of bpe_kernels.cuh on the device or returns an error.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,8 +43,12 @@ static inline void prof_mark(ProfEvents* p, int idx, cudaStream_t s, bool begin)
 
 constexpr int kMaxPipeChunks = 64;
 constexpr int kSideStreams = 16;
-constexpr uint64_t kPipeChunkBytes = 64ull << 20;   // middle sub-batches of a pipelined host call (the first and last are a third of this); measured: profiles/e2e_subbatch_sizes_r01p.jsonl
-constexpr uint64_t kPipeMinBytes = 40ull << 20;     // smaller calls run as one shot
+#ifndef CFBPE_FRONT_STREAMS
+#define CFBPE_FRONT_STREAMS 6
+#endif
+constexpr int kFrontStreams = CFBPE_FRONT_STREAMS;
+constexpr uint64_t kPipeChunkBytes = 12ull << 20;   // middle sub-batches of a pipelined host call (the first and last are a third of this); measured: profiles/e2e_subbatch_sizes_r01q.jsonl
+constexpr uint64_t kPipeMinBytes = 16ull << 20;     // smaller calls run as one shot
 
 struct VocabSlot {
     bool loaded = false;
@@ -64,11 +69,13 @@ struct cfbpe_ctx {
     cudaStream_t aux_stream = nullptr;   // the long-piece kernel runs here, next to the short-piece kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_scan[kMaxPipeChunks] = {};
-    cudaStream_t stream2 = nullptr;        // second front stream of a pipelined host call
+    cudaStream_t front[kFrontStreams] = {};   // front streams 1.. of a pipelined host call (0 = stream)
     cudaStream_t side[kSideStreams] = {};  // long-piece tails + emit of sub-batch k overlap the front of k+1
     cudaEvent_t ev_front[kMaxPipeChunks] = {};
     cudaEvent_t ev_h2d[kMaxPipeChunks] = {};
     cudaEvent_t ev_done[kMaxPipeChunks] = {};
+    cudaEvent_t ev_chain[kMaxPipeChunks] = {};
+    cudaEvent_t (*trace)[6] = nullptr;           // CFBPE_PIPE_TRACE=1: timed events per sub-batch (h2d, split, short, long, back, d2h) + [nc][0] = start   // tile_scan of sub-batch k done: the next sub-batch's scan may read tok_end
     uint64_t pipe_chunk = kPipeChunkBytes, pipe_min = kPipeMinBytes;   // CFBPE_PIPE_CHUNK_BYTES / CFBPE_PIPE_MIN_BYTES override (tests)
     DeviceStatus* d_status_arr = nullptr; // one status per sub-batch
     DeviceStatus* h_status_arr = nullptr; // pinned
@@ -215,6 +222,15 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         for (uint32_t i = p0; i <= p1; ++i) dst[i - p0] = offsets[i] - o0;
     }
     // ---- enqueue everything that does not depend on the host knowing a result
+    const bool trace = getenv("CFBPE_PIPE_TRACE") != nullptr;
+    if (trace && !ctx->trace) {
+        ctx->trace = new cudaEvent_t[kMaxPipeChunks + 1][6];
+        for (int k = 0; k <= kMaxPipeChunks; ++k) for (int j = 0; j < 6; ++j) cudaEventCreate(&ctx->trace[k][j]);
+    }
+    if (trace) CK(cudaEventRecord(ctx->trace[nc][0], hs));
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+    double host_enq[kMaxPipeChunks] = {}, host_dl[kMaxPipeChunks] = {};
     for (int k = 0; k < nc; ++k) {
         const uint32_t p0 = cut[k], p1 = cut[k + 1], nk = p1 - p0;
         const uint64_t o0 = offsets[p0], len = offsets[p1] - o0;
@@ -222,8 +238,9 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         CK(cudaMemcpyAsync(ctx->d_offsets + p0 + k, ctx->h_offs_stage + p0 + k, (static_cast<uint64_t>(nk) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, hs));
         if (vocab_ids && nk) CK(cudaMemcpyAsync(ctx->d_vocab_ids + p0, vocab_ids + p0, nk, cudaMemcpyHostToDevice, hs));
         CK(cudaEventRecord(ctx->ev_h2d[k], hs));
-        cudaStream_t ck = (k & 1) ? ctx->stream2 : cs;   // two front streams: the tails of sub-batch k overlap the front of k+1
-        CK(cudaStreamWaitEvent(ck, ctx->ev_h2d[k], 0));
+        if (trace) CK(cudaEventRecord(ctx->trace[k][0], hs));
+        const int fk = k < kFrontStreams ? k : kFrontStreams - 1;
+        cudaStream_t ck = fk ? ctx->front[fk] : cs;   // the short-piece kernels of sub-batch k: priority falls with k (earlier sub-batches finish, and download, first)
         Workspace w = ctx->ws;
         const uint64_t w0 = (o0 >> 5) + 4ull * k;
         w.piece_bits += w0; w.tok_bits += w0;
@@ -235,20 +252,30 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         w.status = ctx->d_status_arr + k;
         w.miss = slice_miss(ctx->ws.miss, o0, len, static_cast<uint32_t>(k));
         BatchView b{ctx->d_bytes + o0, ctx->d_offsets + p0 + k, vocab_ids ? ctx->d_vocab_ids + p0 : nullptr, nk, len};
+        // split, long pieces and the back stage run on a top-priority stream of their own: the long-piece kernels are a latency
+        // chain that uses little of the machine, so they start as early as possible and the short-piece kernels fill the rest
         cudaStream_t ss = ctx->side[k % kSideStreams];
-        enqueue_split(b, ctx->vs, ctx->uc, w, ck, static_cast<ProfEvents*>(nullptr));
-        CK(cudaEventRecord(ctx->ev_scan[k], ck));
-        CK(cudaStreamWaitEvent(ss, ctx->ev_scan[k], 0));
+        CK(cudaStreamWaitEvent(ss, ctx->ev_h2d[k], 0));
+        enqueue_split(b, ctx->vs, ctx->uc, w, ss, static_cast<ProfEvents*>(nullptr));
+        CK(cudaEventRecord(ctx->ev_scan[k], ss));
+        if (trace) CK(cudaEventRecord(ctx->trace[k][1], ss));
+        CK(cudaStreamWaitEvent(ck, ctx->ev_scan[k], 0));
         enqueue_long(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ss, static_cast<ProfEvents*>(nullptr));   // tail overlaps what follows on cs
+        if (trace) CK(cudaEventRecord(ctx->trace[k][3], ss));
         enqueue_short(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ck, static_cast<ProfEvents*>(nullptr));
         CK(cudaEventRecord(ctx->ev_front[k], ck));
+        if (trace) CK(cudaEventRecord(ctx->trace[k][2], ck));
         CK(cudaStreamWaitEvent(ss, ctx->ev_front[k], 0));
-        if (k) CK(cudaStreamWaitEvent(ss, ctx->ev_done[k - 1], 0));     // token ranks chain through DeviceStatus::tok_end
-        enqueue_back(b, w, want_ids ? ctx->d_out_ids : nullptr, ctx->max_bytes, ctx->d_out_offsets + p0 + k, ctx->d_out_counts + p0,
-                     ss, static_cast<ProfEvents*>(nullptr), k ? &ctx->d_status_arr[k - 1].tok_end : nullptr);
+        enqueue_count(b, w, ss, static_cast<ProfEvents*>(nullptr));
+        if (k) CK(cudaStreamWaitEvent(ss, ctx->ev_chain[k - 1], 0));    // token ranks chain through DeviceStatus::tok_end: only the scan waits
+        enqueue_scan(b, w, ss, static_cast<ProfEvents*>(nullptr), k ? &ctx->d_status_arr[k - 1].tok_end : nullptr);
+        CK(cudaEventRecord(ctx->ev_chain[k], ss));
+        enqueue_emit(b, w, want_ids ? ctx->d_out_ids : nullptr, ctx->max_bytes, ctx->d_out_offsets + p0 + k, ctx->d_out_counts + p0,
+                     ss, static_cast<ProfEvents*>(nullptr));
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(ctx->h_status_arr + k, ctx->d_status_arr + k, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, ss));
+        status_publish_kernel<<<1, 64, 0, ss>>>(ctx->d_status_arr + k, ctx->h_status_arr + k);
         CK(cudaEventRecord(ctx->ev_done[k], ss));
+        if (trace) { CK(cudaEventRecord(ctx->trace[k][4], ss)); host_enq[k] = host_ms(); }
     }
     // ---- trail the kernels with the downloads
     int err = CFBPE_OK;
@@ -266,11 +293,21 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
             CK(cudaMemcpyAsync(out_ids + base, ctx->d_out_ids + base, st.n_tokens * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds));
         if (out_offsets) CK(cudaMemcpyAsync(out_offsets + p0, ctx->d_out_offsets + p0 + k, (static_cast<uint64_t>(nk) + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ds));
         if (out_counts && nk) CK(cudaMemcpyAsync(out_counts + p0, ctx->d_out_counts + p0, static_cast<uint64_t>(nk) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds));
+        if (trace) { CK(cudaEventRecord(ctx->trace[k][5], ds)); host_dl[k] = host_ms(); }
     }
     CK(cudaStreamSynchronize(ds));
     CK(cudaStreamSynchronize(cs));
-    CK(cudaStreamSynchronize(ctx->stream2));
+    for (int k = 1; k < kFrontStreams; ++k) CK(cudaStreamSynchronize(ctx->front[k]));
     for (int k = 0; k < kSideStreams; ++k) CK(cudaStreamSynchronize(ctx->side[k]));
+    if (trace && !err) {
+        fprintf(stderr, "pipe trace (ms since the first upload was enqueued): sub-batch bytes | h2d split short long_end back d2h\n");
+        for (int k = 0; k < nc; ++k) {
+            float t[6];
+            for (int j = 0; j < 6; ++j) cudaEventElapsedTime(&t[j], ctx->trace[nc][0], ctx->trace[k][j]);
+            fprintf(stderr, "  %2d %9llu | %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f | host: enqueued %.2f download issued %.2f\n", k,
+                    static_cast<unsigned long long>(offsets[cut[k + 1]] - offsets[cut[k]]), t[0], t[1], t[2], t[3], t[4], t[5], host_enq[k], host_dl[k]);
+        }
+    }
     if (err) return err;
     if (want_ids && tok_total > out_cap) {
         if (out_offsets) out_offsets[n] = tok_total;
@@ -339,6 +376,10 @@ const char* cfbpe_build_id(void) { return CFBPE_SRC_HASH; }
 int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     if (!cfg || !out || cfg->struct_size < sizeof(cfbpe_config)) return CFBPE_EINVAL;
     *out = nullptr;
+    // a pipelined host call keeps ~20 streams busy; with the default 8 hardware connections streams share queues and a
+    // download waits behind another sub-batch's pending status copy (tools/pipe_trace.py: 7.1 -> 6.1 ms).  Only effective if
+    // the process has not initialised CUDA yet; hosts that have should export it themselves.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return CFBPE_ENODEV;
     if (cfg->device < 0 || cfg->device >= ndev) return CFBPE_ENODEV;
@@ -357,7 +398,9 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     const uint64_t mb = ctx->max_bytes, mp = ctx->max_prompts;
     const uint64_t nw = n_flag_words(mb) + 4 + 4 * kMaxPipeChunks;      // + per-sub-batch slack of a pipelined call
     const uint64_t nt = n_scan_tiles(mb) + 1 + 2 * kMaxPipeChunks;
-    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    int prio_lo0 = 0, prio_hi0 = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo0, &prio_hi0);
+    bool ok = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi0) == cudaSuccess;   // front stream of sub-batch 0
     ok = ok && cudaFuncSetAttribute(bpe_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kListSmemBytes)) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_bytes, mb + 256) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_offsets, mp + 1 + kMaxPipeChunks) == cudaSuccess;
@@ -387,10 +430,14 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     ok = ok && dmalloc(&ctx->d_status_arr, kMaxPipeChunks) == cudaSuccess;
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status_arr), sizeof(DeviceStatus) * kMaxPipeChunks) == cudaSuccess;
     ok = ok && cudaMallocHost(reinterpret_cast<void**>(&ctx->h_offs_stage), sizeof(uint64_t) * (mp + 1 + kMaxPipeChunks)) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
-    {
+    {   // a pipelined host call gives earlier sub-batches the higher priority, so that they finish first and their downloads
+        // run while the later ones compute (with equal priorities the sub-batches finished together and the downloads queued up
+        // at the end: tools/pipe_trace.py)
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        const int levels = prio_lo - prio_hi + 1;
+        for (int k = 1; ok && k < kFrontStreams; ++k)
+            ok = cudaStreamCreateWithPriority(&ctx->front[k], cudaStreamNonBlocking, prio_hi + (k < levels ? k : levels - 1)) == cudaSuccess;
         for (int k = 0; ok && k < kSideStreams; ++k) ok = cudaStreamCreateWithPriority(&ctx->side[k], cudaStreamNonBlocking, prio_hi) == cudaSuccess;
     }
     {   // the long-piece kernels are latency-bound and small: their CTAs go first, the short-piece kernels fill the rest
@@ -403,7 +450,8 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     for (int k = 0; ok && k < kMaxPipeChunks; ++k)
         ok = cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_front[k], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_chain[k], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_uc1, sizeof cfbpe_uc_stage1) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_uc2, sizeof cfbpe_uc_stage2) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_uc1, cfbpe_uc_stage1, sizeof cfbpe_uc_stage1, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -451,8 +499,8 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     if (ctx->h_status_arr) cudaFreeHost(ctx->h_status_arr);
     if (ctx->h_offs_stage) cudaFreeHost(ctx->h_offs_stage);
     cudaFree(ctx->d_status_arr);
-    for (int k = 0; k < kMaxPipeChunks; ++k) { if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]); if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]); if (ctx->ev_front[k]) cudaEventDestroy(ctx->ev_front[k]); }
-    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (int k = 0; k < kMaxPipeChunks; ++k) { if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]); if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]); if (ctx->ev_front[k]) cudaEventDestroy(ctx->ev_front[k]); if (ctx->ev_chain[k]) cudaEventDestroy(ctx->ev_chain[k]); }
+    for (int k = 1; k < kFrontStreams; ++k) if (ctx->front[k]) cudaStreamDestroy(ctx->front[k]);
     for (int k = 0; k < kSideStreams; ++k) if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
     for (int k = 0; k < kMaxPipeChunks; ++k) if (ctx->ev_scan[k]) cudaEventDestroy(ctx->ev_scan[k]);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);

@@ -116,29 +116,42 @@ inline void enqueue_long(const BatchView& b, const VocabSet& vs, const Workspace
 #endif
 }
 
+// back = count | scan | emit.  Only the scan reads what the previous sub-batch of a pipelined call produced (token_base), so
+// a caller that chains sub-batches waits between count and scan and can let the emits of consecutive sub-batches overlap.
 template <typename Stream, typename Prof>
-inline void enqueue_back(const BatchView& b, const Workspace& w, uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets,
-                         uint32_t* out_counts, Stream stream, Prof* prof, const uint64_t* token_base) {
-    const uint64_t nw = n_flag_words(b.total_bytes);
-    const uint32_t nt = n_scan_tiles(b.total_bytes);
+inline void enqueue_count(const BatchView& b, const Workspace& w, Stream stream, Prof* prof) {
+    if (!b.total_bytes) return;
+    CFBPE_MARK(prof, K_COUNT, stream, true);
+    CFBPE_LAUNCH(flag_count_kernel, n_scan_tiles(b.total_bytes), 256, stream, w.tok_bits, n_flag_words(b.total_bytes), w.tile_counts);
+    CFBPE_MARK(prof, K_COUNT, stream, false);
+}
+template <typename Stream, typename Prof>
+inline void enqueue_scan(const BatchView& b, const Workspace& w, Stream stream, Prof* prof, const uint64_t* token_base) {
     if (b.total_bytes) {
-        CFBPE_MARK(prof, K_COUNT, stream, true);
-        CFBPE_LAUNCH(flag_count_kernel, nt, 256, stream, w.tok_bits, nw, w.tile_counts);
-        CFBPE_MARK(prof, K_COUNT, stream, false);
         CFBPE_MARK(prof, K_SCAN, stream, true);
-        CFBPE_LAUNCH(tile_scan_kernel, 1u, 1024, stream, w.tile_counts, nt, w.tile_base, w.status, token_base);
+        CFBPE_LAUNCH(tile_scan_kernel, 1u, 1024, stream, w.tile_counts, n_scan_tiles(b.total_bytes), w.tile_base, w.status, token_base);
         CFBPE_MARK(prof, K_SCAN, stream, false);
-        CFBPE_MARK(prof, K_EMIT, stream, true);
-        if (out_ids) {
-            CFBPE_LAUNCH(emit_compact_kernel, nt, 256, stream, w.tok_bits, nw, w.tile_base, w.ids_by_pos, out_ids, out_cap);
-        }
     } else {
         CFBPE_LAUNCH(tile_scan_kernel, 1u, 32, stream, w.tile_counts, 0u, w.tile_base, w.status, token_base);   // tok_end = base
-        CFBPE_MARK(prof, K_EMIT, stream, true);
+    }
+}
+template <typename Stream, typename Prof>
+inline void enqueue_emit(const BatchView& b, const Workspace& w, uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets,
+                         uint32_t* out_counts, Stream stream, Prof* prof) {
+    CFBPE_MARK(prof, K_EMIT, stream, true);
+    if (b.total_bytes && out_ids) {
+        CFBPE_LAUNCH(emit_compact_kernel, n_scan_tiles(b.total_bytes), 256, stream, w.tok_bits, n_flag_words(b.total_bytes), w.tile_base, w.ids_by_pos, out_ids, out_cap);
     }
     CFBPE_LAUNCH(prompt_offsets_kernel, static_cast<unsigned>((static_cast<uint64_t>(b.n_prompts) + 1 + 255) / 256), 256, stream,
                  b, w.tok_bits, w.tile_base, out_offsets, out_counts, w.status);
     CFBPE_MARK(prof, K_EMIT, stream, false);
+}
+template <typename Stream, typename Prof>
+inline void enqueue_back(const BatchView& b, const Workspace& w, uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets,
+                         uint32_t* out_counts, Stream stream, Prof* prof, const uint64_t* token_base) {
+    enqueue_count(b, w, stream, prof);
+    enqueue_scan(b, w, stream, prof, token_base);
+    enqueue_emit(b, w, out_ids, out_cap, out_offsets, out_counts, stream, prof);
 }
 
 // The whole path.  `aux` is a second stream for the long-piece kernel (pass the same stream to run everything in order);

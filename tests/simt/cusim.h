@@ -255,6 +255,8 @@ inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
 inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
 inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, !pred) == 0; }
 
+inline void __threadfence_system() {}
+inline void __threadfence() {}
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { sh &= 31; return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
