@@ -203,3 +203,27 @@ def test_periodic_pieces_switch_back_to_batched_rounds(sim_vocabs, oracle_vocabs
     check_batch(sim_vocabs[1], oracle_vocabs[1], 1, prompts)
     assert simlib.dbg_counter(0) > 0 and simlib.dbg_counter(1) > 0 and simlib.dbg_counter(2) > 0 and simlib.dbg_counter(5) > 0, \
         [simlib.dbg_counter(i) for i in range(8)]
+
+
+@pytest.mark.parametrize("pat", [1, 3])
+def test_split_cased_runs_resolved_by_lookback(pat):
+    """cased patterns: inside runs of upper-case / both-sets (Lo, Lm, M) characters the state is found by looking back to
+    the character that decides (csrc/pretok_sync.cuh:cased_word_sync) -- long CJK and all-caps runs with every kind of
+    character in front of them (lower case, contraction suffixes, marks after punctuation, digits, nothing)"""
+    import random
+    rng = random.Random(90 + pat)
+    heads = ["", "a", "ab", "abc", "x's", "x'll", "'s", "'", "''", "!", "!!", "1", " ", "\n", "A", "Ab", "aB", "中a", "a中", "́", "'́", "''́", "é", "É"]
+    runs = [lambda n: "".join(rng.choice("中文字漢") for _ in range(n)), lambda n: "".join(rng.choice("ABCDÉ") for _ in range(n)),
+            lambda n: "".join(rng.choice("中文́AB") for _ in range(n)), lambda n: "".join(rng.choice("中A") for _ in range(n)),
+            lambda n: "".join(rng.choice("中文ａʰ") for _ in range(n))]
+    tails = ["", "a", "B", "b c", "'s", "!", " x", "1", "\n", "́a"]
+    strs = []
+    for _ in range(1500):
+        parts = []
+        for _ in range(rng.randint(1, 4)):
+            parts += [rng.choice(heads), rng.choice(runs)(rng.choice([1, 2, 3, 5, 20, 21, 22, 40, 70, 150, 260])), rng.choice(tails)]
+        strs.append("".join(parts).encode())
+    rc, ends = simlib.split([pat], strs)
+    assert rc == 0
+    bad = [(p, e) for p, e in zip(strs, ends) if oracle.split(pat, p).tolist() != e]
+    assert not bad, bad[:3]
