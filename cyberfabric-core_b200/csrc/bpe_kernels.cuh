@@ -167,28 +167,22 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
     uint32_t state = kNoSync;
     uint32_t prevx = X_EOT, nlet = 0, npun = 0;   // class of the previous character; consecutive letters (<= 3) / punctuation (<= 2) before pos
     uint32_t pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
-    uint64_t lbe0 = 0;
-    bool cased_scan = true;      // the look-back of cased_word_sync is O(run): after a failure it is not repeated inside the same run
     while (pos < ce) {
         if (pos == pe) {  // step into the next non-empty prompt
             do { ++pidx; ps = pe; pe = b.offsets[pidx + 1]; } while (pe == ps);
             pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
         }
         prevx = X_EOT; nlet = 0; npun = 0;
-        state = (pos == ps) ? static_cast<uint32_t>(S_START)
-                            : sync_state(s, pos, ps, pe, uc, (pat & 1u) != 0, &prevx, &nlet, &npun, &lbe0, cased_scan);
+        state = (pos == ps) ? static_cast<uint32_t>(S_START) : sync_state(s, pos, ps, pe, uc, (pat & 1u) != 0, &prevx, &nlet, &npun);
         if (state != kNoSync) break;
-        // failed inside a run: not again until the run ends (the same rule, character by character, as the hand-over below)
-        if ((s[pos] & 0xC0) != 0x80) cased_scan = !((pat & 1u) && (prevx == X_LU || prevx == X_LO || prevx == X_M));
         ++pos;
     }
     if (state == kNoSync) return;
 
     // ---- run the automaton
     const uint16_t* tab = s_fsm + pat * kPretokTableSize;
-    uint64_t alc = 0, last = 0, lbe = lbe0;
+    uint64_t alc = 0, last = 0, lbe = 0;
     int bad = 0;
-    bool cased_fail = false;     // hand-over: cased_word_sync already failed inside the current upper-case / both-sets run
     // boundaries inside my chunk collect in one 64-bit mask (the chunk is 64-byte aligned: two flag words, OR-ed in at the
     // end because the thread to my left may have set bits there while handing over); those beyond it go out one by one
     static_assert(kSplitChunk <= 64, "the chunk mask is one 64-bit word");
@@ -231,10 +225,6 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
         // (after the retroactive boundaries above, which concern positions of mine); same predicate as
         // sync_state(), evaluated on the classes just seen
         if (pos >= ce && (bad || sync_rule(x, prevx, nlet, npun, (pat & 1u) != 0) != kNoSync)) break;
-        if (pos >= ce && (pat & 1u) && (prevx == X_LU || prevx == X_LO || prevx == X_M)) {   // the look-back form of the predicate
-            if (!cased_fail && cased_word_sync(s, pos, ps, pe, uc, static_cast<uint64_t*>(nullptr)) != kNoSync) break;
-            cased_fail = true;
-        } else cased_fail = false;
         if (a & A_B_NOW) mark(pos);
         if (a & A_SET_ALC) alc = pos + len;
         if (a & A_SET_LAST) last = pos;

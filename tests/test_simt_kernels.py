@@ -206,10 +206,10 @@ def test_periodic_pieces_switch_back_to_batched_rounds(sim_vocabs, oracle_vocabs
 
 
 @pytest.mark.parametrize("pat", [1, 3])
-def test_split_cased_runs_resolved_by_lookback(pat):
-    """cased patterns: inside runs of upper-case / both-sets (Lo, Lm, M) characters the state is found by looking back to
-    the character that decides (csrc/pretok_sync.cuh:cased_word_sync) -- long CJK and all-caps runs with every kind of
-    character in front of them (lower case, contraction suffixes, marks after punctuation, digits, nothing)"""
+def test_split_cased_runs(pat):
+    """cased patterns: runs of upper-case / both-sets (Lo, Lm, M) characters, where the automaton's state depends on how
+    the word began -- long CJK and all-caps runs with every kind of character in front of them (lower case, contraction
+    suffixes, marks after punctuation, digits, nothing), crossing chunk boundaries everywhere"""
     import random
     rng = random.Random(90 + pat)
     heads = ["", "a", "ab", "abc", "x's", "x'll", "'s", "'", "''", "!", "!!", "1", " ", "\n", "A", "Ab", "aB", "中a", "a中", "́", "'́", "''́", "é", "É"]
