@@ -134,6 +134,15 @@ __device__ __forceinline__ uint64_t ascii_digit_run_end(const uint8_t* __restric
     return e;
 }
 
+// out of line: it is rare, and inlined it cost the split kernel 14 registers
+#ifdef CUSIM_EMULATOR
+inline uint32_t exact_state_cold(const uint8_t* s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc, const uint16_t* tab) {
+#else
+__device__ __noinline__ uint32_t exact_state_cold(const uint8_t* s, uint64_t pos, uint64_t ps, uint64_t pe, UcTables uc, const uint16_t* tab) {
+#endif
+    return exact_state_before(s, pos, ps, pe, uc, tab, true);
+}
+
 // ---------------------------------------------------------------------------------------
 // K1: pre-tokenizer split.  One thread per kSplitChunk bytes.  A thread starts at the first sync
 // point of its chunk (prompt start or is_sync_point) and runs the table-driven automaton of
@@ -142,7 +151,7 @@ __device__ __forceinline__ uint64_t ascii_digit_run_end(const uint8_t* __restric
 // stream whatever match they are in (the first version walked whole matches per thread: 4.3 of 32
 // lanes active, profiles/ncu_lines_pretok_split_r01a.txt).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict__ piece_bits, DeviceStatus* status) {
     __shared__ uint16_t s_fsm[kNumPatterns * kPretokTableSize];
     __shared__ uint8_t s_ascii[128];
@@ -181,7 +190,7 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
 
     // ---- run the automaton
     const uint16_t* tab = s_fsm + pat * kPretokTableSize;
-    uint64_t alc = 0, last = 0, lbe = 0;
+    uint64_t alc = 0, last = 0, lbe = pos;     // (lbe: what W_XB0 would hold if that is what S_W_U turns out to be)
     int bad = 0;
     // boundaries inside my chunk collect in one 64-bit mask (the chunk is 64-byte aligned: two flag words, OR-ed in at the
     // end because the thread to my left may have set bits there while handing over); those beyond it go out one by one
@@ -200,6 +209,10 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
             else { const Ch c = get_char(s, pos, pe, uc, &bad); x = c.cls; len = c.len; }
         }
         uint32_t a = tab[state * X_COUNT + x];
+        if (a & A_RESOLVE) {   // I started inside a run of both-sets letters and now it matters which part of the word this is
+            const uint32_t real = exact_state_cold(s, pos, ps, pe, uc, tab);
+            a = tab[real * X_COUNT + x];
+        }
         uint32_t skip = 0;
         if (a & A_CONTR) {
             skip = contraction_bytes(s, pos, pe);

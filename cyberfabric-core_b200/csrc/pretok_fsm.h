@@ -31,14 +31,17 @@ enum : uint32_t {
 enum : uint32_t {
     S_START = 0, S_LETTERS, S_D1, S_D2, S_D3, S_ORUN, S_OTRAIL, S_PFX_O,
     S_WS_N1S, S_WS_N1, S_WS_NMS, S_WS_NM, S_WS_C0, S_WS_C1S, S_WS_C1, S_WS_CMS, S_WS_CM,
-    S_W_X0, S_W_XB0, S_W_XBU, S_W_Y, S_COUNT
+    S_W_X0, S_W_XB0, S_W_XBU, S_W_Y,
+    S_W_U,      // cased word, right after a both-sets letter, [upper] or [lower] part not known (a thread that STARTED there)
+    S_COUNT
 };
 // action bits
 enum : uint32_t {
     A_STATE_MASK = 31, A_B_NOW = 1u << 5, A_EMIT_ALC = 1u << 6, A_EMIT_LAST = 1u << 7, A_EMIT_LBE = 1u << 8,
     A_SET_ALC = 1u << 9, A_SET_LAST = 1u << 10, A_SET_LBE = 1u << 11,
     A_CONTR = 1u << 12,         // a contraction may start here: if it does, skip it and go to START
-    A_CONTR_SUFFIX = 1u << 13   // ... and it belongs to the piece that just ended (no boundary here)
+    A_CONTR_SUFFIX = 1u << 13,  // ... and it belongs to the piece that just ended (no boundary here)
+    A_RESOLVE = 1u << 14        // state S_W_U meets an upper-case letter: the real state (W_Y or W_XB0) has to be found first
 };
 constexpr uint32_t kPretokTableSize = S_COUNT * X_COUNT;   // u16 entries per pattern
 constexpr uint32_t kNumPatterns = 4;
@@ -168,6 +171,12 @@ inline uint32_t transition(uint32_t pat, uint32_t st, uint32_t x) {
     case S_W_Y:
         if (x == X_LL || x == X_LO || x == X_M) return S_W_Y;
         if (x == X_LU) return A_B_NOW | S_W_X0;
+        return word_end(T, x);
+    case S_W_U:     // W_Y and W_XB0 agree on everything but an upper-case letter (boundary | none) -- and on lbe, kept as W_XB0 would
+        if (!T.cased) return start_with(T, x);
+        if (x == X_LO || x == X_M) return S_W_U | A_SET_LBE;
+        if (x == X_LL) return S_W_Y;
+        if (x == X_LU) return A_RESOLVE | S_W_U;
         return word_end(T, x);
     default: return start_with(T, x);
     }

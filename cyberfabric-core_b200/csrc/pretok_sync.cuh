@@ -7,6 +7,8 @@
 //           a punctuation character (class OTHER, not an apostrophe, not a mark) right after a letter or digit
 //   LETTERS (uncased patterns) the three previous characters are letters: a contraction covers at most two
 //   W_Y     (cased patterns) the previous character is a lower-case letter and the two before it are letters
+//   W_U     (cased patterns) the previous character is a both-sets LETTER (Lo/Lm: CJK, kana, ...): the word is in its
+//           [upper] or its [lower] part, which only matters when an upper-case letter follows (pretok_fsm.h S_W_U)
 //   ORUN    the two previous characters are punctuation (not '/', which a newline trailer may have eaten; not a
 //           mark in the cased patterns, where marks are word characters): the second of them sits in a punctuation run
 //
@@ -39,6 +41,7 @@ CFBPE_HD uint32_t sync_rule(uint32_t x, uint32_t prevx, uint32_t nlet, uint32_t 
     if (x == X_N) return prevx != X_N ? static_cast<uint32_t>(S_START) : kNoSync;
     if ((x == X_OTHER || x == X_SLASH) && prev_ln) return S_START;
     if (nlet >= 3 && (cased ? prevx == X_LL : x_is_letter(prevx))) return cased ? static_cast<uint32_t>(S_W_Y) : static_cast<uint32_t>(S_LETTERS);
+    if (cased && prevx == X_LO) return S_W_U;
     if (npun >= 2) return S_ORUN;
     return kNoSync;
 }
@@ -92,6 +95,33 @@ CFBPE_HD uint32_t sync_state(const Txt& s, uint64_t pos, uint64_t ps, uint64_t p
     if (nlet_out) *nlet_out = nlet;
     if (npun_out) *npun_out = npun;
     return sync_rule(ext_class(cur), prevx, nlet, npun, cased);
+}
+
+// The automaton's real state before pos, for a thread in S_W_U that meets an upper-case letter: walk left to the nearest
+// position whose state the class rules give outright (or the prompt start), then run the automaton forward to pos without
+// emitting anything.  O(distance), and rare: an upper-case letter inside a run of CJK-like letters.
+template <typename Txt>
+CFBPE_HD uint32_t exact_state_before(const Txt& s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc, const uint16_t* tab, bool cased) {
+    uint64_t q = pos;
+    uint32_t state = S_START;
+    while (q > ps) {
+        q -= get_prev_char(s, q, ps, pe, uc).len;
+        if (q == ps) break;
+        const uint32_t st = sync_state(s, q, ps, pe, uc, cased);
+        if (st != kNoSync && st != S_W_U) { state = st; break; }
+    }
+    while (q < pos) {
+        int bad = 0;
+        const Ch c = get_char(s, q, pe, uc, &bad);
+        const uint32_t a = tab[state * X_COUNT + ext_class(c)];
+        if (a & A_CONTR) {
+            const uint32_t skip = contraction_bytes(s, q, pe);
+            if (skip) { state = S_START; q += skip; continue; }
+        }
+        state = a & A_STATE_MASK;
+        q += c.len ? c.len : 1;
+    }
+    return state;
 }
 
 }  // namespace cfbpe
