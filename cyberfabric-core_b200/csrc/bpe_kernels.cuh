@@ -73,6 +73,8 @@ struct DeviceStatus {
     uint32_t miss_n[3];    // short pieces that are not one token, by length class: 13..32 | 7..12 | 2..6 bytes (K2a -> K2m)
     uint32_t miss_next[3]; // K2m work tickets
     uint32_t miss_overflow;
+    uint32_t fix_n;        // K1 threads that stopped in S_W_U (pretok_fixup_kernel finishes them)
+    uint32_t pad3;
     uint32_t defer_n;      // pieces K2b handed to K2c ...
     unsigned long long defer_parts;   // ... and their parts at hand-over
 };
@@ -134,15 +136,6 @@ __device__ __forceinline__ uint64_t ascii_digit_run_end(const uint8_t* __restric
     return e;
 }
 
-// out of line: it is rare, and inlined it cost the split kernel 14 registers
-#ifdef CUSIM_EMULATOR
-inline uint32_t exact_state_cold(const uint8_t* s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc, const uint16_t* tab) {
-#else
-__device__ __noinline__ uint32_t exact_state_cold(const uint8_t* s, uint64_t pos, uint64_t ps, uint64_t pe, UcTables uc, const uint16_t* tab) {
-#endif
-    return exact_state_before(s, pos, ps, pe, uc, tab, true);
-}
-
 // ---------------------------------------------------------------------------------------
 // K1: pre-tokenizer split.  One thread per kSplitChunk bytes.  A thread starts at the first sync
 // point of its chunk (prompt start or is_sync_point) and runs the table-driven automaton of
@@ -151,32 +144,35 @@ __device__ __noinline__ uint32_t exact_state_cold(const uint8_t* s, uint64_t pos
 // stream whatever match they are in (the first version walked whole matches per thread: 4.3 of 32
 // lanes active, profiles/ncu_lines_pretok_split_r01a.txt).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 5)
-pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict__ piece_bits, DeviceStatus* status) {
-    __shared__ uint16_t s_fsm[kNumPatterns * kPretokTableSize];
-    __shared__ uint8_t s_ascii[128];
-    for (uint32_t i = threadIdx.x; i < kNumPatterns * kPretokTableSize; i += blockDim.x) s_fsm[i] = uc.fsm[i];
-    if (threadIdx.x < 128) s_ascii[threadIdx.x] = uc.ascii_x[threadIdx.x];
-    __syncthreads();
+// A thread that started in S_W_U (pretok_sync.cuh) and meets an upper-case letter needs the automaton's real state.  Finding
+// it is a look-back of unbounded length: inlined -- or even called -- in the hot loop it cost the kernel registers and 17 %
+// of its speed, so the thread files the position and stops, and pretok_fixup_kernel (next launch, almost always empty)
+// finds the state and finishes that thread's job.
+struct SplitFix { uint64_t pos, ce; };
 
-    const uint64_t chunk = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const uint64_t cs = chunk * kSplitChunk;
-    if (cs >= b.total_bytes) return;
-    const uint64_t ce = (cs + kSplitChunk < b.total_bytes) ? cs + kSplitChunk : b.total_bytes;
+// kFix = false: the thread of chunk [cs, ce).  kFix = true: resume at fix_pos on behalf of the thread whose chunk ended at ce.
+template <bool kFix>
+__device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet& vs, UcTables uc, const uint16_t* s_fsm, const uint8_t* s_ascii,
+                                             uint32_t* __restrict__ piece_bits, DeviceStatus* status, SplitFix* fix_list, uint32_t fix_cap,
+                                             uint64_t cs, uint64_t ce, uint64_t fix_pos) {
     // (a shared-memory text tile with coalesced 16-byte loads was measured slower here: occupancy fell from 67 % to
     //  29 % and the accessor cost more than the L1 hits it replaced -- profiles/ncu_summary_r01k.json)
     const uint8_t* __restrict__ s = b.bytes;
 
-    uint32_t pidx = find_prompt(b.offsets, b.n_prompts, cs);
+    uint32_t pidx = find_prompt(b.offsets, b.n_prompts, kFix ? fix_pos : cs);
     uint64_t ps = b.offsets[pidx], pe = b.offsets[pidx + 1];
     uc.ascii_x = s_ascii;   // the copy in shared memory
 
     // ---- find the first sync point in [cs, ce)
-    uint64_t pos = cs;
+    uint64_t pos = kFix ? fix_pos : cs;
     uint32_t state = kNoSync;
     uint32_t prevx = X_EOT, nlet = 0, npun = 0;   // class of the previous character; consecutive letters (<= 3) / punctuation (<= 2) before pos
     uint32_t pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
-    while (pos < ce) {
+    if (kFix) {   // the real state at fix_pos (inside a prompt, after a both-sets letter), and the classes the hand-over looks at
+        sync_state(s, pos, ps, pe, uc, true, &prevx, &nlet, &npun);
+        state = exact_state_before(s, pos, ps, pe, uc, s_fsm + pat * kPretokTableSize, true);
+    }
+    while (!kFix && pos < ce) {
         if (pos == pe) {  // step into the next non-empty prompt
             do { ++pidx; ps = pe; pe = b.offsets[pidx + 1]; } while (pe == ps);
             pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
@@ -197,7 +193,7 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
     static_assert(kSplitChunk <= 64, "the chunk mask is one 64-bit word");
     uint64_t mine = 0;
     auto mark = [&](uint64_t p) {
-        if (p - cs < kSplitChunk) mine |= 1ull << (p - cs);
+        if (!kFix && p - cs < kSplitChunk) mine |= 1ull << (p - cs);
         else atomicOr(&piece_bits[p >> 5], 1u << (p & 31));
     };
     for (;;) {
@@ -209,9 +205,10 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
             else { const Ch c = get_char(s, pos, pe, uc, &bad); x = c.cls; len = c.len; }
         }
         uint32_t a = tab[state * X_COUNT + x];
-        if (a & A_RESOLVE) {   // I started inside a run of both-sets letters and now it matters which part of the word this is
-            const uint32_t real = exact_state_cold(s, pos, ps, pe, uc, tab);
-            a = tab[real * X_COUNT + x];
+        if (!kFix && (a & A_RESOLVE)) {   // started inside a run of both-sets letters, and now it matters which part of the word this is
+            const uint32_t k = atomicAdd(&status->fix_n, 1u);
+            if (k < fix_cap) { SplitFix f; f.pos = pos; f.ce = ce; fix_list[k] = f; }
+            break;
         }
         uint32_t skip = 0;
         if (a & A_CONTR) {
@@ -296,10 +293,43 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
             }
         }
     }
-    or_bits(piece_bits, cs >> 5, static_cast<uint32_t>(mine));
-    or_bits(piece_bits, (cs >> 5) + 1, static_cast<uint32_t>(mine >> 32));
+    if (!kFix) {
+        or_bits(piece_bits, cs >> 5, static_cast<uint32_t>(mine));
+        or_bits(piece_bits, (cs >> 5) + 1, static_cast<uint32_t>(mine >> 32));
+    }
     if (bad) atomicOr(&status->bad_utf8, 1u);
 }
+
+__global__ void __launch_bounds__(256)
+pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict__ piece_bits, DeviceStatus* status, SplitFix* fix_list, uint32_t fix_cap) {
+    __shared__ uint16_t s_fsm[kNumPatterns * kPretokTableSize];
+    __shared__ uint8_t s_ascii[128];
+    for (uint32_t i = threadIdx.x; i < kNumPatterns * kPretokTableSize; i += blockDim.x) s_fsm[i] = uc.fsm[i];
+    if (threadIdx.x < 128) s_ascii[threadIdx.x] = uc.ascii_x[threadIdx.x];
+    __syncthreads();
+    const uint64_t chunk = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t cs = chunk * kSplitChunk;
+    if (cs >= b.total_bytes) return;
+    const uint64_t ce = (cs + kSplitChunk < b.total_bytes) ? cs + kSplitChunk : b.total_bytes;
+    split_thread<false>(b, vs, uc, s_fsm, s_ascii, piece_bits, status, fix_list, fix_cap, cs, ce, 0);
+}
+
+// the threads of pretok_split_kernel that stopped in S_W_U at an upper-case letter: one thread each (grid-stride)
+__global__ void __launch_bounds__(256)
+pretok_fixup_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict__ piece_bits, DeviceStatus* status, const SplitFix* fix_list, uint32_t fix_cap) {
+    __shared__ uint16_t s_fsm[kNumPatterns * kPretokTableSize];
+    __shared__ uint8_t s_ascii[128];
+    const uint32_t n = status->fix_n < fix_cap ? status->fix_n : fix_cap;
+    if (blockIdx.x * blockDim.x >= n) return;          // nothing filed: the usual case
+    for (uint32_t i = threadIdx.x; i < kNumPatterns * kPretokTableSize; i += blockDim.x) s_fsm[i] = uc.fsm[i];
+    if (threadIdx.x < 128) s_ascii[threadIdx.x] = uc.ascii_x[threadIdx.x];
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const SplitFix f = fix_list[i];
+        split_thread<true>(b, vs, uc, s_fsm, s_ascii, piece_bits, status, nullptr, 0, 0, f.ce, f.pos);
+    }
+}
+
 
 // ---------------------------------------------------------------------------------------
 // K2: encode.  One warp owns the pieces that START in its kEncodeRange bytes.  It walks them in

@@ -251,6 +251,8 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         w.tile_counts += t0; w.tile_base += t0;
         w.status = ctx->d_status_arr + k;
         w.miss = slice_miss(ctx->ws.miss, o0, len, static_cast<uint32_t>(k));
+        w.fix_list += (o0 >> 6) + 2ull * k;
+        w.fix_cap = static_cast<uint32_t>(len / 64 + 2);
         BatchView b{ctx->d_bytes + o0, ctx->d_offsets + p0 + k, vocab_ids ? ctx->d_vocab_ids + p0 : nullptr, nk, len};
         // split, long pieces and the back stage run on a top-priority stream of their own: the long-piece kernels are a latency
         // chain that uses little of the machine, so they start as early as possible and the short-piece kernels fill the rest
@@ -421,6 +423,8 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
         ok = ok && dmalloc(&ctx->ws.miss.list[c], words) == cudaSuccess;
         ctx->ws.miss.cap[c] = static_cast<uint32_t>(words);
     }
+    ctx->ws.fix_cap = static_cast<uint32_t>(mb / 64 + 2 + 2 * kMaxPipeChunks);
+    ok = ok && dmalloc(&ctx->ws.fix_list, ctx->ws.fix_cap) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.tile_counts, nt) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.tile_base, nt) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.status, 1) == cudaSuccess;
@@ -493,6 +497,7 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     cudaFree(ctx->ws.piece_bits); cudaFree(ctx->ws.tok_bits); cudaFree(ctx->ws.ids_by_pos);
     cudaFree(ctx->ws.lscratch.rank); cudaFree(ctx->ws.lscratch.aux0); cudaFree(ctx->ws.lscratch.aux1);
     for (uint32_t c = 0; c < 3; ++c) cudaFree(ctx->ws.miss.list[c]);
+    cudaFree(ctx->ws.fix_list);
     cudaFree(ctx->ws.long_list); cudaFree(ctx->ws.tile_counts); cudaFree(ctx->ws.tile_base); cudaFree(ctx->ws.status);
     cudaFree(ctx->d_uc1); cudaFree(ctx->d_uc2); cudaFree(ctx->d_ascii); cudaFree(ctx->d_fsm);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);

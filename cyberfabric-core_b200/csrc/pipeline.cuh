@@ -23,6 +23,8 @@ struct Workspace {
     uint64_t* tile_base;    // [n_tiles]
     DeviceStatus* status;
     MissLists miss;         // K2a -> K2m: short pieces that need the merge loop, by length class
+    SplitFix* fix_list;     // K1 -> fixup: threads that stopped in S_W_U   [total / 64 + 2]
+    uint32_t fix_cap;
 };
 
 // the slice of the miss lists that belongs to a sub-batch of `len` bytes starting at byte o0 (k-th sub-batch)
@@ -62,7 +64,8 @@ inline void enqueue_split(const BatchView& b, const VocabSet& vs, const UcTables
     CFBPE_ZERO(w.tok_bits, (nw + 2) * sizeof(uint32_t), stream);
     const uint64_t n_chunks = (b.total_bytes + kSplitChunk - 1) / kSplitChunk;
     CFBPE_MARK(prof, K_SPLIT, stream, true);
-    CFBPE_LAUNCH(pretok_split_kernel, static_cast<unsigned>((n_chunks + 255) / 256), 256, stream, b, vs, uc, w.piece_bits, w.status);
+    CFBPE_LAUNCH(pretok_split_kernel, static_cast<unsigned>((n_chunks + 255) / 256), 256, stream, b, vs, uc, w.piece_bits, w.status, w.fix_list, w.fix_cap);
+    CFBPE_LAUNCH(pretok_fixup_kernel, 296u, 256, stream, b, vs, uc, w.piece_bits, w.status, w.fix_list, w.fix_cap);   // almost always empty
     CFBPE_MARK(prof, K_SPLIT, stream, false);
 #ifndef CFBPE_K2_WINDOWED
     const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;

@@ -77,6 +77,8 @@ __attribute__((visibility("default"))) uint32_t sim_pair_lookup(void* vp, uint32
 }
 
 // K1 only: piece-start bits (n_words+2 words) for a packed batch; patterns[] per vocab id
+static unsigned long long fixups_seen = 0;
+__attribute__((visibility("default"))) unsigned long long sim_split_fixups(int reset) { const unsigned long long v = fixups_seen; if (reset) fixups_seen = 0; return v; }
 __attribute__((visibility("default"))) int sim_split(const uint32_t* patterns, uint32_t n_patterns, uint32_t n_prompts,
                                                      const uint8_t* bytes, const uint64_t* offsets, const uint8_t* vocab_ids,
                                                      uint32_t* piece_bits) {
@@ -91,7 +93,11 @@ __attribute__((visibility("default"))) int sim_split(const uint32_t* patterns, u
     if (total) {
         const uint64_t n_chunks = (total + kSplitChunk - 1) / kSplitChunk;
         UcTables uc = uc_tables();
-        cusim::launch(static_cast<unsigned>((n_chunks + 255) / 256), 256, [&] { pretok_split_kernel(b, vs, uc, piece_bits, &st); });
+        std::vector<SplitFix> fix(total / 64 + 2);
+        const uint32_t fix_cap = static_cast<uint32_t>(fix.size());
+        cusim::launch(static_cast<unsigned>((n_chunks + 255) / 256), 256, [&] { pretok_split_kernel(b, vs, uc, piece_bits, &st, fix.data(), fix_cap); });
+        cusim::launch(2u, 256, [&] { pretok_fixup_kernel(b, vs, uc, piece_bits, &st, fix.data(), fix_cap); });
+        fixups_seen += st.fix_n;
     }
     return st.bad_utf8 ? CFBPE_EILSEQ : 0;
 }
@@ -116,6 +122,7 @@ __attribute__((visibility("default"))) int sim_encode_batch(void* const* vocabs,
     std::vector<uint64_t> tile_base(nt + 1);
     std::vector<LongPiece> ll(total / 32 + 1);
     DeviceStatus st{};
+    std::vector<SplitFix> fix(total / 64 + 2);
     std::vector<uint32_t> miss[3];
     MissLists ml;
     for (uint32_t c = 0; c < 3; ++c) {
@@ -124,7 +131,7 @@ __attribute__((visibility("default"))) int sim_encode_batch(void* const* vocabs,
         ml.cap[c] = static_cast<uint32_t>(miss[c].size());
     }
     Workspace w{piece_bits.data(), tok_bits.data(), ids.data(), LongScratch{rk.data(), nx.data(), pv.data()},
-                ll.data(), static_cast<uint32_t>(ll.size()), tile_counts.data(), tile_base.data(), &st, ml};
+                ll.data(), static_cast<uint32_t>(ll.size()), tile_counts.data(), tile_base.data(), &st, ml, fix.data(), static_cast<uint32_t>(fix.size())};
     int* prof = nullptr;
     enqueue_encode(b, vs, uc_tables(), w, out_ids, out_cap, out_offsets, out_counts, 4u, 0, 0, 0, 0, prof);
     if (n_long_out) *n_long_out = static_cast<uint64_t>(st.n_long) + st.n_big;

@@ -28,10 +28,17 @@ def lib():
         L.sim_encode_batch.restype = C.c_int
         L.sim_encode_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sim_split_fixups.restype = C.c_ulonglong
+        L.sim_split_fixups.argtypes = [C.c_int]
         L.sim_dbg_counter.restype = C.c_ulonglong
         L.sim_dbg_counter.argtypes = [C.c_uint32, C.c_int]
         _lib = L
     return _lib
+
+
+def split_fixups(reset=False):
+    """K1 threads that stopped in S_W_U and were finished by pretok_fixup_kernel, in sim_split calls so far"""
+    return int(lib().sim_split_fixups(1 if reset else 0))
 
 
 def dbg_counter(i, reset=False):

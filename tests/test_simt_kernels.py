@@ -223,7 +223,9 @@ def test_split_cased_runs(pat):
         for _ in range(rng.randint(1, 4)):
             parts += [rng.choice(heads), rng.choice(runs)(rng.choice([1, 2, 3, 5, 20, 21, 22, 40, 70, 150, 260])), rng.choice(tails)]
         strs.append("".join(parts).encode())
+    simlib.split_fixups(reset=True)
     rc, ends = simlib.split([pat], strs)
     assert rc == 0
     bad = [(p, e) for p, e in zip(strs, ends) if oracle.split(pat, p).tolist() != e]
     assert not bad, bad[:3]
+    assert simlib.split_fixups() > 50      # threads that started in S_W_U, met an upper-case letter and were finished by the fixup kernel
