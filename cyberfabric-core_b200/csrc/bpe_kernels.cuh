@@ -148,18 +148,18 @@ __device__ __forceinline__ uint64_t ascii_digit_run_end(const uint8_t* __restric
 // it is a look-back of unbounded length: inlined -- or even called -- in the hot loop it cost the kernel registers and 17 %
 // of its speed, so the thread files the position and stops, and pretok_fixup_kernel (next launch, almost always empty)
 // finds the state and finishes that thread's job.
-struct SplitFix { uint64_t pos, ce; };
+struct SplitFix { uint64_t pos, ce; uint32_t pidx, pad; };   // pidx: the prompt the thread was in (pos may be its END = the next one's start)
 
 // kFix = false: the thread of chunk [cs, ce).  kFix = true: resume at fix_pos on behalf of the thread whose chunk ended at ce.
 template <bool kFix>
 __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet& vs, UcTables uc, const uint16_t* s_fsm, const uint8_t* s_ascii,
                                              uint32_t* __restrict__ piece_bits, DeviceStatus* status, SplitFix* fix_list, uint32_t fix_cap,
-                                             uint64_t cs, uint64_t ce, uint64_t fix_pos) {
+                                             uint64_t cs, uint64_t ce, uint64_t fix_pos, uint32_t fix_pidx) {
     // (a shared-memory text tile with coalesced 16-byte loads was measured slower here: occupancy fell from 67 % to
     //  29 % and the accessor cost more than the L1 hits it replaced -- profiles/ncu_summary_r01k.json)
     const uint8_t* __restrict__ s = b.bytes;
 
-    uint32_t pidx = find_prompt(b.offsets, b.n_prompts, kFix ? fix_pos : cs);
+    uint32_t pidx = kFix ? fix_pidx : find_prompt(b.offsets, b.n_prompts, cs);
     uint64_t ps = b.offsets[pidx], pe = b.offsets[pidx + 1];
     uc.ascii_x = s_ascii;   // the copy in shared memory
 
@@ -168,9 +168,10 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
     uint32_t state = kNoSync;
     uint32_t prevx = X_EOT, nlet = 0, npun = 0;   // class of the previous character; consecutive letters (<= 3) / punctuation (<= 2) before pos
     uint32_t pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
-    if (kFix) {   // the real state at fix_pos (inside a prompt, after a both-sets letter), and the classes the hand-over looks at
+    uint64_t lbe_fix = 0;
+    if (kFix) {   // the real state at fix_pos (inside a prompt, after a letter), and the classes the hand-over looks at
         sync_state(s, pos, ps, pe, uc, true, &prevx, &nlet, &npun);
-        state = exact_state_before(s, pos, ps, pe, uc, s_fsm + pat * kPretokTableSize, true);
+        state = exact_state_before(s, pos, ps, pe, uc, s_fsm + pat * kPretokTableSize, true, &lbe_fix);
     }
     while (!kFix && pos < ce) {
         if (pos == pe) {  // step into the next non-empty prompt
@@ -186,7 +187,7 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
 
     // ---- run the automaton
     const uint16_t* tab = s_fsm + pat * kPretokTableSize;
-    uint64_t alc = 0, last = 0, lbe = pos;     // (lbe: what W_XB0 would hold if that is what S_W_U turns out to be)
+    uint64_t alc = 0, last = 0, lbe = kFix ? lbe_fix : pos;     // (lbe = pos: what W_XB0 would hold if that is what S_W_U turns out to be)
     int bad = 0;
     // boundaries inside my chunk collect in one 64-bit mask (the chunk is 64-byte aligned: two flag words, OR-ed in at the
     // end because the thread to my left may have set bits there while handing over); those beyond it go out one by one
@@ -205,9 +206,9 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
             else { const Ch c = get_char(s, pos, pe, uc, &bad); x = c.cls; len = c.len; }
         }
         uint32_t a = tab[state * X_COUNT + x];
-        if (!kFix && (a & A_RESOLVE)) {   // started inside a run of both-sets letters, and now it matters which part of the word this is
+        if (!kFix && (a & A_RESOLVE)) {   // started inside a run of both-sets / upper-case letters, and now it matters what came before it
             const uint32_t k = atomicAdd(&status->fix_n, 1u);
-            if (k < fix_cap) { SplitFix f; f.pos = pos; f.ce = ce; fix_list[k] = f; }
+            if (k < fix_cap) { SplitFix f; f.pos = pos; f.ce = ce; f.pidx = pidx; f.pad = 0; fix_list[k] = f; }
             break;
         }
         uint32_t skip = 0;
@@ -311,7 +312,7 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
     const uint64_t cs = chunk * kSplitChunk;
     if (cs >= b.total_bytes) return;
     const uint64_t ce = (cs + kSplitChunk < b.total_bytes) ? cs + kSplitChunk : b.total_bytes;
-    split_thread<false>(b, vs, uc, s_fsm, s_ascii, piece_bits, status, fix_list, fix_cap, cs, ce, 0);
+    split_thread<false>(b, vs, uc, s_fsm, s_ascii, piece_bits, status, fix_list, fix_cap, cs, ce, 0, 0);
 }
 
 // the threads of pretok_split_kernel that stopped in S_W_U at an upper-case letter: one thread each (grid-stride)
@@ -326,7 +327,7 @@ pretok_fixup_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
     __syncthreads();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const SplitFix f = fix_list[i];
-        split_thread<true>(b, vs, uc, s_fsm, s_ascii, piece_bits, status, nullptr, 0, 0, f.ce, f.pos);
+        split_thread<true>(b, vs, uc, s_fsm, s_ascii, piece_bits, status, nullptr, 0, 0, f.ce, f.pos, f.pidx);
     }
 }
 

@@ -33,6 +33,7 @@ enum : uint32_t {
     S_WS_N1S, S_WS_N1, S_WS_NMS, S_WS_NM, S_WS_C0, S_WS_C1S, S_WS_C1, S_WS_CMS, S_WS_CM,
     S_W_X0, S_W_XB0, S_W_XBU, S_W_Y,
     S_W_U,      // cased word, right after a both-sets letter, [upper] or [lower] part not known (a thread that STARTED there)
+    S_W_V,      // cased word, inside a run of upper-case letters, W_X0 or W_XBU not known (likewise)
     S_COUNT
 };
 // action bits
@@ -41,7 +42,7 @@ enum : uint32_t {
     A_SET_ALC = 1u << 9, A_SET_LAST = 1u << 10, A_SET_LBE = 1u << 11,
     A_CONTR = 1u << 12,         // a contraction may start here: if it does, skip it and go to START
     A_CONTR_SUFFIX = 1u << 13,  // ... and it belongs to the piece that just ended (no boundary here)
-    A_RESOLVE = 1u << 14        // state S_W_U meets an upper-case letter: the real state (W_Y or W_XB0) has to be found first
+    A_RESOLVE = 1u << 14        // S_W_U meets an upper-case letter / S_W_V meets the end of the word: the real state has to be found first
 };
 constexpr uint32_t kPretokTableSize = S_COUNT * X_COUNT;   // u16 entries per pattern
 constexpr uint32_t kNumPatterns = 4;
@@ -101,6 +102,7 @@ inline uint32_t transition(uint32_t pat, uint32_t st, uint32_t x) {
         uint32_t a = S_START;
         if (!T.ws_eot && (st == S_WS_C1S || st == S_WS_C1 || st == S_WS_CMS || st == S_WS_CM)) a |= A_EMIT_ALC;
         if (st == S_W_XBU) a |= A_EMIT_LBE;
+        if (st == S_W_V && T.cased) a |= A_RESOLVE;      // W_XBU would emit, W_X0 would not
         return a;
     }
     switch (st) {
@@ -172,6 +174,12 @@ inline uint32_t transition(uint32_t pat, uint32_t st, uint32_t x) {
         if (x == X_LL || x == X_LO || x == X_M) return S_W_Y;
         if (x == X_LU) return A_B_NOW | S_W_X0;
         return word_end(T, x);
+    case S_W_V:     // W_X0 and W_XBU agree until the word ends (W_XBU then gives back what greedy [upper]* took: boundary at lbe)
+        if (!T.cased) return start_with(T, x);
+        if (x == X_LU) return S_W_V;
+        if (x == X_LO || x == X_M) return S_W_XB0 | A_SET_LBE;
+        if (x == X_LL) return S_W_Y;
+        return A_RESOLVE | S_W_V;
     case S_W_U:     // W_Y and W_XB0 agree on everything but an upper-case letter (boundary | none) -- and on lbe, kept as W_XB0 would
         if (!T.cased) return start_with(T, x);
         if (x == X_LO || x == X_M) return S_W_U | A_SET_LBE;

@@ -9,6 +9,8 @@
 //   W_Y     (cased patterns) the previous character is a lower-case letter and the two before it are letters
 //   W_U     (cased patterns) the previous character is a both-sets LETTER (Lo/Lm: CJK, kana, ...): the word is in its
 //           [upper] or its [lower] part, which only matters when an upper-case letter follows (pretok_fsm.h S_W_U)
+//   W_V     (cased patterns) the three previous characters are letters, the last one upper case: W_X0 or W_XBU, which only
+//           matters when the word ends (pretok_fsm.h S_W_V)
 //   ORUN    the two previous characters are punctuation (not '/', which a newline trailer may have eaten; not a
 //           mark in the cased patterns, where marks are word characters): the second of them sits in a punctuation run
 //
@@ -42,6 +44,7 @@ CFBPE_HD uint32_t sync_rule(uint32_t x, uint32_t prevx, uint32_t nlet, uint32_t 
     if ((x == X_OTHER || x == X_SLASH) && prev_ln) return S_START;
     if (nlet >= 3 && (cased ? prevx == X_LL : x_is_letter(prevx))) return cased ? static_cast<uint32_t>(S_W_Y) : static_cast<uint32_t>(S_LETTERS);
     if (cased && prevx == X_LO) return S_W_U;
+    if (cased && prevx == X_LU && nlet >= 3) return S_W_V;      // (three letters: not inside or right after a contraction suffix)
     if (npun >= 2) return S_ORUN;
     return kNoSync;
 }
@@ -97,18 +100,19 @@ CFBPE_HD uint32_t sync_state(const Txt& s, uint64_t pos, uint64_t ps, uint64_t p
     return sync_rule(ext_class(cur), prevx, nlet, npun, cased);
 }
 
-// The automaton's real state before pos, for a thread in S_W_U that meets an upper-case letter: walk left to the nearest
+// The automaton's real state (and lbe) before pos, for a thread in S_W_U / S_W_V that has to know: walk left to the nearest
 // position whose state the class rules give outright (or the prompt start), then run the automaton forward to pos without
 // emitting anything.  O(distance), and rare: an upper-case letter inside a run of CJK-like letters.
 template <typename Txt>
-CFBPE_HD uint32_t exact_state_before(const Txt& s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc, const uint16_t* tab, bool cased) {
-    uint64_t q = pos;
+CFBPE_HD uint32_t exact_state_before(const Txt& s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc, const uint16_t* tab, bool cased,
+                                     uint64_t* lbe_out = nullptr) {
+    uint64_t q = pos, lbe = 0;
     uint32_t state = S_START;
     while (q > ps) {
         q -= get_prev_char(s, q, ps, pe, uc).len;
         if (q == ps) break;
         const uint32_t st = sync_state(s, q, ps, pe, uc, cased);
-        if (st != kNoSync && st != S_W_U) { state = st; break; }
+        if (st != kNoSync && st != S_W_U && st != S_W_V) { state = st; break; }
     }
     while (q < pos) {
         int bad = 0;
@@ -120,7 +124,9 @@ CFBPE_HD uint32_t exact_state_before(const Txt& s, uint64_t pos, uint64_t ps, ui
         }
         state = a & A_STATE_MASK;
         q += c.len ? c.len : 1;
+        if (a & A_SET_LBE) lbe = q;
     }
+    if (lbe_out) *lbe_out = lbe;
     return state;
 }
 

@@ -8,17 +8,20 @@ for p in (ROOT, os.path.join(ROOT, "cyberfabric-core_b200")):
 import numpy as np, torch
 from cfbpe import plugin as P
 
-plug = P.GpuBpeTokenizerPlugin(0, ("cl100k_base",), 64 << 20, 1 << 16)
+VOCAB = sys.argv[1] if len(sys.argv) > 1 else "cl100k_base"
+plug = P.GpuBpeTokenizerPlugin(0, (VOCAB,), 64 << 20, 1 << 16)
 dev = torch.device("cuda:0")
 letters = np.frombuffer(b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ", dtype=np.uint8)
 def gen(kind, ln, rng):
     if kind == "rand52": return letters[rng.integers(52, size=ln)]
     if kind == "rand26": return letters[rng.integers(26, size=ln)]
+    if kind.startswith("uniform"): return uniform({"a": 97, "sp": 32, "bang": 33, "nl": 10, "0": 48}[kind[8:]], ln)
     if kind.startswith("period"):
         per = letters[rng.integers(52, size=int(kind[6:]))]
         return np.resize(per, ln)
     raise ValueError(kind)
-for kind in ("rand52", "rand26", "period2", "period3", "period4"):
+def uniform(ch, ln): return np.full(ln, ch, dtype=np.uint8)
+for kind in ("rand52", "rand26", "period2", "period3", "period4", "uniform_a", "uniform_sp", "uniform_bang", "uniform_nl", "uniform_0"):
     rng = np.random.Generator(np.random.PCG64(7))
     n = 819 if kind.startswith("rand") else 273
     lens = rng.integers(8, 4097, size=n)
@@ -35,5 +38,5 @@ for kind in ("rand52", "rand26", "period2", "period3", "period4"):
     for i in range(4):
         plug.ctx.encode_batch_device(n, d_bytes.data_ptr(), total, d_offs.data_ptr(), None, d_ids.data_ptr(), d_ids.numel(), d_off.data_ptr(), d_cnt.data_ptr(), s, sync=True)
         pr = plug.ctx.profile_read(); a.append(pr["kernel_ms"]["bpe_long"]); b.append(pr["kernel_ms"]["bpe_list"])
-    print(json.dumps({"kind": kind, "prompts": n, "bytes": total, "bpe_long_ms": round(min(a[1:]), 3), "bpe_list_ms": round(min(b[1:]), 3),
+    print(json.dumps({"kind": kind, "prompts": n, "bytes": total, "split_ms": round(pr["kernel_ms"]["pretok_split"], 3), "bpe_long_ms": round(min(a[1:]), 3), "bpe_list_ms": round(min(b[1:]), 3),
                       "list_pieces": pr["n_list_pieces"], "list_parts": pr["n_list_parts"]}), flush=True)
