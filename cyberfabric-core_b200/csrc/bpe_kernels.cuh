@@ -171,7 +171,7 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
     uint64_t lbe_fix = 0;
     if (kFix) {   // the real state at fix_pos (inside a prompt, after a letter), and the classes the hand-over looks at
         sync_state(s, pos, ps, pe, uc, true, &prevx, &nlet, &npun);
-        state = exact_state_before(s, pos, ps, pe, uc, s_fsm + pat * kPretokTableSize, true, &lbe_fix);
+        state = resolve_word_state(s, pos, ps, pe, uc, s_fsm + pat * kPretokTableSize, &lbe_fix);
     }
     while (!kFix && pos < ce) {
         if (pos == pe) {  // step into the next non-empty prompt

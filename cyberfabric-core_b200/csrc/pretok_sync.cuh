@@ -130,4 +130,47 @@ CFBPE_HD uint32_t exact_state_before(const Txt& s, uint64_t pos, uint64_t ps, ui
     return state;
 }
 
+// The same answer, found the short way when the look-back is simple (it nearly always is): what decides is the character in
+// front of the run of upper-case letters (S_W_V) or of both-sets characters (S_W_U) that ends at pos.
+//   upper-case run:  W_X0 unless a both-sets character stands in front of it (then the long way)
+//   both-sets run:   W_Y if a lower-case letter stands in front of it -- unless an apostrophe one or two characters further
+//                    left may make that letter a contraction suffix (then the long way); W_XB0 (lbe = pos) otherwise
+template <typename Txt>
+CFBPE_HD uint32_t resolve_word_state(const Txt& s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc, const uint16_t* tab,
+                                     uint64_t* lbe_out) {
+    uint64_t q = pos;
+    Ch c = get_prev_char(s, q, ps, pe, uc);
+    uint32_t x = ext_class(c);
+    if (x == X_LU) {
+        for (;;) {
+            while (q > ps && (static_cast<uint32_t>(s[q - 1]) - 'A') < 26u) --q;      // ASCII capitals: a byte at a time
+            if (q == ps) { x = X_EOT; break; }
+            c = get_prev_char(s, q, ps, pe, uc);
+            x = ext_class(c);
+            if (x != X_LU) break;
+            q -= c.len;
+        }
+        if (x != X_LO && x != X_M) { *lbe_out = 0; return S_W_X0; }
+        return exact_state_before(s, pos, ps, pe, uc, tab, true, lbe_out);
+    }
+    while (x == X_LO || x == X_M) {
+        q -= c.len;
+        if (q == ps) { x = X_EOT; break; }
+        c = get_prev_char(s, q, ps, pe, uc);
+        x = ext_class(c);
+    }
+    *lbe_out = pos;
+    if (x != X_LL) return S_W_XB0;
+    uint64_t t = q - c.len;                     // start of the lower-case letter
+    if (t > ps) {
+        const Ch p1 = get_prev_char(s, t, ps, pe, uc);
+        const uint32_t x1 = ext_class(p1);
+        if (x1 == X_APOS) return exact_state_before(s, pos, ps, pe, uc, tab, true, lbe_out);
+        t -= p1.len;
+        if (t > ps && x_is_letter(x1) && ext_class(get_prev_char(s, t, ps, pe, uc)) == X_APOS)
+            return exact_state_before(s, pos, ps, pe, uc, tab, true, lbe_out);
+    }
+    return S_W_Y;
+}
+
 }  // namespace cfbpe
