@@ -42,6 +42,13 @@ inline uint64_t miss_list_words(uint64_t max_bytes, uint32_t c, uint32_t max_chu
     return max_bytes / L + 2ull * max_chunks + 64;
 }
 
+// K2b CTAs per SM (long_grid = 4 x SM count).  8 x 128 threads x 64 registers is the whole register file of an SM: the
+// short-piece kernels on the other stream then wait for K2b instead of running beside it.
+#ifndef CFBPE_LONG_CTAS
+#define CFBPE_LONG_CTAS 8
+#endif
+constexpr uint32_t kLongCtasPerSm = CFBPE_LONG_CTAS;
+
 enum KernelIdx { K_SPLIT = 0, K_ENCODE = 1, K_LONG = 2, K_COUNT = 3, K_SCAN = 4, K_EMIT = 5, K_LIST = 6, K_LONGSCAN = 7, K_MERGE = 8 };
 
 inline uint64_t n_flag_words(uint64_t total_bytes) { return (total_bytes + 31) >> 5; }
@@ -108,7 +115,7 @@ template <typename Stream, typename Prof>
 inline void enqueue_long(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
     if (!b.total_bytes) return;
     CFBPE_MARK(prof, K_LONG, stream, true);
-    CFBPE_LAUNCH(bpe_long_kernel, long_grid * (8 / kLongWarps), kLongWarps * 32, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
+    CFBPE_LAUNCH(bpe_long_kernel, (long_grid / 4) * kLongCtasPerSm, kLongWarps * 32, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
     CFBPE_MARK(prof, K_LONG, stream, false);
 #ifndef CFBPE_NO_DEFER
     CFBPE_MARK(prof, K_LIST, stream, true);
