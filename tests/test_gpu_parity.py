@@ -251,6 +251,34 @@ def test_long_pieces_on_device(plug, ctx, oracle_vocabs):
         assert np.array_equal(r.ids, want_ids)
 
 
+@pytest.mark.parametrize("pat", [1, 3])
+def test_cased_runs_and_periodic_pieces_on_device(plug, ctx, oracle_vocabs, pat):
+    """what the second half of round 1 added: threads that start in the undecided states W_U / W_V and are finished by
+    pretok_fixup_kernel (CJK and all-caps runs under the cased patterns), whitespace / digit runs taken in bulk, periodic
+    pieces that make the list kernels hand back to batched rounds, pieces of 4097.. parts (global-memory list path)"""
+    import random
+    from oracle import oracle
+    rng = random.Random(31 + pat)
+    heads = ["", "a", "abc", "x's", "x'LL", "'", "''", "!", "1", " ", "\n", "A", "aB", "a中", "́", "''́", "é"]
+    runs = [lambda n: "".join(rng.choice("中文字漢") for _ in range(n)), lambda n: "".join(rng.choice("ABCDÉ") for _ in range(n)),
+            lambda n: "".join(rng.choice("中文́AB") for _ in range(n)), lambda n: "".join(rng.choice("中A") for _ in range(n)),
+            lambda n: " " * n, lambda n: "\n" * n, lambda n: "".join(rng.choice("0123456789") for _ in range(n)),
+            lambda n: ("".join(rng.choice("erabAB") for _ in range(rng.randint(2, 5))) * n)[:n]]
+    tails = ["", "a", "B", "b c", "'s", "!", " x", "1", "\n", "́a"]
+    prompts = []
+    for _ in range(4000):
+        parts = []
+        for _ in range(rng.randint(1, 4)):
+            parts += [rng.choice(heads), rng.choice(runs)(rng.choice([1, 2, 3, 5, 21, 22, 40, 70, 150, 260, 700, 1805, 5000])), rng.choice(tails)]
+        prompts.append("".join(parts).encode())
+    data, offs = pack(prompts)
+    want_ids, want_off, want_counts = oracle.encode_batch([oracle_vocabs[pat]], [pat], data, offs, nthreads=os.cpu_count())
+    r = encode(plug, ctx, SLOT_NAMES[pat], data, offs)
+    assert np.array_equal(r.offsets, want_off)
+    assert np.array_equal(r.ids, want_ids)
+    assert np.array_equal(r.counts, want_counts)
+
+
 def test_pipelined_host_path_matches_oracle(oracle_vocabs, tekken_bytes, monkeypatch):
     """force the pipelined (sub-batched, 3-stream) host path with tiny sub-batches: many chunk seams, chained token ranks"""
     from cfbpe import _native as N
