@@ -764,22 +764,15 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
 constexpr uint32_t kLookupWarps = 4;
 __global__ void __launch_bounds__(kLookupWarps * 32)
 bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits, uint32_t* __restrict__ ids_by_pos,
-                  uint32_t* __restrict__ tok_bits, MissLists ml, LongPiece* __restrict__ long_list, uint32_t long_cap, DeviceStatus* status) {
+                  uint32_t* __restrict__ tok_bits, MissLists ml, DeviceStatus* status) {
     __shared__ uint16_t s_pos[kLookupWarps][kPieceRange + 2];
     __shared__ uint32_t s_flags[kLookupWarps][kPieceRange / 32];
     __shared__ uint32_t s_miss0[kLookupWarps * kPieceRange / 13 + 8];
     __shared__ uint32_t s_miss1[kLookupWarps * kPieceRange / 7 + 8];
     __shared__ uint32_t s_miss2[kLookupWarps * kPieceRange / 2 + 8];
     __shared__ uint32_t s_cnt[3], s_base[3];
-    // pieces longer than 32 bytes go to the work list of the long-piece kernels (two-ended: > kBigPiece from the back) --
-    // a separate pass over the flags used to find them (0.24 ms); here they fall out of the same enumeration
-    __shared__ LongPiece s_long[2][kLookupWarps * kPieceRange / 33 + 2];
-    __shared__ uint32_t s_lcnt[2], s_lbase[2];
-    __shared__ unsigned long long s_lbytes;
     const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
-    if (threadIdx.x < 2) s_lcnt[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_lbytes = 0;
     if (lane < kPieceRange / 32) s_flags[wic][lane] = 0;
     __syncthreads();
     const uint64_t warp = static_cast<uint64_t>(blockIdx.x) * kLookupWarps + wic;
@@ -808,19 +801,12 @@ bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
             const uint32_t off = s_pos[wic][i];
             const uint64_t pos = r0 + off;
             const uint64_t end = (i + 1 < n_w) ? r0 + s_pos[wic][i + 1] : beyond;
+            if (end - pos > 32) continue;                         // long piece: K2b
+            const uint32_t len = static_cast<uint32_t>(end - pos);
             if (multi) {
                 const uint32_t pv = b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)];
                 if (pv != vid) { vid = pv; T = vs.v[vid]; }
             }
-            if (end - pos > 32) {                                 // long piece: K2b
-                const uint32_t big = (end - pos) > kBigPiece ? 1u : 0u;
-                const uint32_t k = atomicAdd(&s_lcnt[big], 1u);
-                LongPiece lp; lp.start = pos; lp.end = end; lp.vocab = vid; lp.pad = 0;
-                s_long[big][k] = lp;
-                atomicAdd(&s_lbytes, static_cast<unsigned long long>(end - pos));
-                continue;
-            }
-            const uint32_t len = static_cast<uint32_t>(end - pos);
             const uint32_t tok = (len == 1) ? T.byte2id[text[pos]] : whole_piece_lookup(T, text + pos, len);   // a byte is a token
             if (tok != kNone) {
                 ids_by_pos[pos] = tok;
@@ -844,20 +830,7 @@ bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
         if (n && g + n > ml.cap[threadIdx.x]) { atomicOr(&status->miss_overflow, 1u); g = 0xFFFFFFFFu; }
         s_base[threadIdx.x] = g;
     }
-    if (threadIdx.x >= 32 && threadIdx.x < 34) {
-        const uint32_t e = threadIdx.x - 32, n = s_lcnt[e];
-        uint32_t g = n ? atomicAdd(e ? &status->n_big : &status->n_long, n) : 0u;
-        if (n && g + n > long_cap) { atomicOr(&status->long_overflow, 1u); g = 0xFFFFFFFFu; }
-        s_lbase[e] = g;
-    }
-    if (threadIdx.x == 64 && s_lbytes) atomicAdd(&status->long_bytes, s_lbytes);
     __syncthreads();
-#pragma unroll
-    for (uint32_t e = 0; e < 2; ++e) {
-        const uint32_t n = s_lcnt[e], g = s_lbase[e];
-        if (g == 0xFFFFFFFFu) continue;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) long_list[e ? long_cap - 1 - (g + i) : g + i] = s_long[e][i];
-    }
 #pragma unroll
     for (uint32_t c = 0; c < 3; ++c) {
         const uint32_t n = s_cnt[c], g = s_base[c];

@@ -259,7 +259,6 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         cudaStream_t ss = ctx->side[k % kSideStreams];
         CK(cudaStreamWaitEvent(ss, ctx->ev_h2d[k], 0));
         enqueue_split(b, ctx->vs, ctx->uc, w, ss, static_cast<ProfEvents*>(nullptr));
-        enqueue_lookup(b, ctx->vs, w, ss, static_cast<ProfEvents*>(nullptr));
         CK(cudaEventRecord(ctx->ev_scan[k], ss));
         if (trace) CK(cudaEventRecord(ctx->trace[k][1], ss));
         CK(cudaStreamWaitEvent(ck, ctx->ev_scan[k], 0));

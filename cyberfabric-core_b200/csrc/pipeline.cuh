@@ -74,26 +74,12 @@ inline void enqueue_split(const BatchView& b, const VocabSet& vs, const UcTables
     CFBPE_LAUNCH(pretok_split_kernel, static_cast<unsigned>((n_chunks + 255) / 256), 256, stream, b, vs, uc, w.piece_bits, w.status, w.fix_list, w.fix_cap);
     CFBPE_LAUNCH(pretok_fixup_kernel, 296u, 256, stream, b, vs, uc, w.piece_bits, w.status, w.fix_list, w.fix_cap);   // almost always empty
     CFBPE_MARK(prof, K_SPLIT, stream, false);
-#if !defined(CFBPE_K2_WINDOWED) && defined(CFBPE_K2_FUSED)
+#ifndef CFBPE_K2_WINDOWED
     const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
     CFBPE_MARK(prof, K_LONGSCAN, stream, true);
     CFBPE_LAUNCH(bpe_encode_pieces_kernel<1>, static_cast<unsigned>((n_warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, stream,
                  b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
     CFBPE_MARK(prof, K_LONGSCAN, stream, false);
-#endif
-}
-
-// K2a: every piece once (hits -> ids, misses -> lists, long pieces -> work list).  The long-piece kernels and the merge kernel
-// both start from its output.
-template <typename Stream, typename Prof>
-inline void enqueue_lookup(const BatchView& b, const VocabSet& vs, const Workspace& w, Stream stream, Prof* prof) {
-#if !defined(CFBPE_K2_WINDOWED) && !defined(CFBPE_K2_FUSED)
-    if (!b.total_bytes) return;
-    const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
-    CFBPE_MARK(prof, K_ENCODE, stream, true);
-    CFBPE_LAUNCH(bpe_lookup_kernel, static_cast<unsigned>((n_warps + kLookupWarps - 1) / kLookupWarps), kLookupWarps * 32, stream,
-                 b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.miss, w.long_list, w.long_cap, w.status);
-    CFBPE_MARK(prof, K_ENCODE, stream, false);
 #endif
 }
 
@@ -113,6 +99,11 @@ inline void enqueue_short(const BatchView& b, const VocabSet& vs, const Workspac
                  b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
     CFBPE_MARK(prof, K_ENCODE, stream, false);
 #else
+    const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
+    CFBPE_MARK(prof, K_ENCODE, stream, true);
+    CFBPE_LAUNCH(bpe_lookup_kernel, static_cast<unsigned>((n_warps + kLookupWarps - 1) / kLookupWarps), kLookupWarps * 32, stream,
+                 b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.miss, w.status);
+    CFBPE_MARK(prof, K_ENCODE, stream, false);
     CFBPE_MARK(prof, K_MERGE, stream, true);
     CFBPE_LAUNCH(bpe_merge_kernel, long_grid + long_grid / 2, kPieceWarps * 32, stream,      // 6 CTAs of 32 KB per SM
                  b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.miss, w.status);
@@ -181,7 +172,6 @@ inline void enqueue_encode(const BatchView& b, const VocabSet& vs, const UcTable
                            uint32_t long_grid, Stream stream, Stream aux, Ev ev_fork, Ev ev_join, Prof* prof,
                            const uint64_t* token_base = nullptr) {
     enqueue_split(b, vs, uc, w, stream, prof);
-    enqueue_lookup(b, vs, w, stream, prof);
     CFBPE_FORK(stream, aux, ev_fork);
 #ifdef CFBPE_K2_WINDOWED
     enqueue_short(b, vs, w, long_grid, stream, prof);      // the windowed kernel queues the long pieces itself
