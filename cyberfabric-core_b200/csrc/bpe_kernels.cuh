@@ -65,7 +65,7 @@ struct DeviceStatus {
     uint32_t long_overflow;
     uint32_t long_next;    // K2b work ticket (pieces of 33..kBigPiece bytes)
     uint32_t n_big;        // pieces longer than kBigPiece (stored from the back of the list)
-    uint32_t defer_next;   // K2c work ticket (over the big pieces)
+    uint32_t defer_next;   // K2c work ticket (over the big pieces; those K2b deferred carry their part count)
     uint64_t n_tokens;     // ids produced by this (sub-)batch (written by tile_scan)
     uint64_t tok_end;      // token_base + n_tokens: where the next sub-batch of a pipelined call continues
     unsigned long long long_bytes;   // bytes inside pieces handled by K2b ...
@@ -1463,9 +1463,6 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
         const TablesView T = vs.v[lp.vocab];
         const uint8_t* __restrict__ p = b.bytes + lp.start;
         const uint32_t n = static_cast<uint32_t>(lp.end - lp.start);
-#ifndef CFBPE_NO_DEFER
-        if (item < n_big && lp.end - lp.start <= kDeferMaxParts && T.n_ranks < kListMaxRank) continue;   // bpe_list_kernel's: the whole piece in shared memory
-#endif
         // state of the piece: shared memory for pieces of <= kMedSmem bytes (most of them), else its slice of scratch
         uint32_t* const gid = ids_by_pos + lp.start;
         const bool in_smem = n <= kMedSmem;
@@ -1499,6 +1496,7 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
 
         // ---- rounds: batched rounds on the compact array while they merge a useful fraction (runs, periods: O(log n)
         //      rounds), list rounds otherwise; a list phase that meets many pairs of one rank comes back for a batched round
+        bool deferred = false;
         while (rmin != kNone) {
             array_round(T, id, rk, a0, a1, m, rmin, lane);
             const uint32_t before = m;
@@ -1516,6 +1514,13 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
                 continue;
 #endif
             }
+#ifndef CFBPE_NO_DEFER
+            if (m <= kDeferMaxParts && T.n_ranks < kListMaxRank) {   // bpe_list_kernel goes on from here, in shared memory
+                if (lane == 0) { long_list[slot].pad = m; atomicAdd(&status->defer_n, 1u); atomicAdd(&status->defer_parts, static_cast<unsigned long long>(m)); CFBPE_DBG_COUNT(0); }
+                deferred = true;
+                break;
+            }
+#endif
 #ifdef CFBPE_SINGLE_MERGE_ROUNDS
             list_rounds(T, id, rk, a0, a1, m, &s_subr[threadIdx.x >> 5][0][lane], &s_subp[threadIdx.x >> 5][0][lane], lane);
 #else
@@ -1525,15 +1530,14 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
             __syncwarp();
             break;
         }
+        if (deferred) continue;
         __syncwarp();
         flag_parts(id, in_smem ? gid : nullptr, m, lp.start, tok_bits, status, lane);
         __syncwarp();
     }
 }
 
-// K2c: the big pieces (more than kBigPiece = kMedSmem bytes, at most kDeferMaxParts), from bytes to ids, independent of K2b
-// (earlier versions ran the batched rounds in K2b on global scratch and handed the list phase over: the kernel boundary put
-// K2c behind ALL of K2b on the critical path).  Was: the list phase of the pieces K2b deferred (at most kDeferMaxParts parts after the
+// K2c: the list phase of the pieces K2b deferred (more than kMedSmem bytes, at most kDeferMaxParts parts left after the
 // batched rounds).  One CTA of kListWarps warps per piece with the whole merge state -- id | key | link | claim, 16 bytes
 // per part -- in 64 KB of dynamic shared memory, parallel-cut rounds (list_rounds_par): a round costs one table round trip
 // and a few hundred cycles of shared-memory work and takes ~20 merges.  Three such CTAs fit an SM.  Tickets run over the
@@ -1554,6 +1558,7 @@ bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
     uint32_t* const kk = s_dyn + kDeferMaxParts;
     uint32_t* const link = s_dyn + 2 * kDeferMaxParts;
     uint32_t* const claim = s_dyn + 3 * kDeferMaxParts;
+    (void)b;
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(&status->defer_next, 1u);
         __syncthreads();
@@ -1561,37 +1566,22 @@ bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
         __syncthreads();
         if (item >= n_big) break;
         const LongPiece lp = long_list[long_cap - 1 - item];
-        const uint32_t n = static_cast<uint32_t>(lp.end - lp.start);
+        uint32_t m = lp.pad;
+        if (!m) continue;
         const TablesView T = vs.v[lp.vocab];
-        if (lp.end - lp.start > kDeferMaxParts || T.n_ranks >= kListMaxRank) continue;   // bpe_long_kernel keeps it (the same test there)
-        const uint8_t* __restrict__ p = b.bytes + lp.start;
         uint32_t* const gid = ids_by_pos + lp.start;
-        if (threadIdx.x == 0) { atomicAdd(&status->defer_n, 1u); atomicAdd(&status->defer_parts, static_cast<unsigned long long>(n)); CFBPE_DBG_COUNT(0); }
-        // ---- whole-piece shortcut (CoreBPE: `if piece in ranks`)
-        if (n <= T.max_token_len) {
-            if (threadIdx.x == 0) s_rmin = piece_lookup(T, p, n);
-            __syncthreads();
-            const uint32_t t = s_rmin;
-            __syncthreads();
-            if (t != kNone) {
-                if (threadIdx.x == 0) { gid[0] = t; atomicOr(&tok_bits[lp.start >> 5], 1u << (lp.start & 31)); atomicAdd(&status->long_tokens, 1ull); }
-                continue;
-            }
-        }
-        // ---- parts = bytes
-        for (uint32_t i = threadIdx.x; i < n; i += kListWarps * 32) {
-            const uint32_t c0 = p[i];
-            id[i] = T.byte2id[c0];
-            kk[i] = (i + 1 < n) ? T.bytepair[(c0 << 8) | p[i + 1]] : kNone;
-        }
+        const uint32_t* const grk = sc.rank + lp.start;
+        for (uint32_t i = threadIdx.x; i < m; i += kListWarps * 32) { id[i] = gid[i]; kk[i] = grk[i]; }
         __syncthreads();
-        // ---- rounds: batched rounds (first warp; runs and periods collapse in O(log n) of them) while they merge a useful
-        //      fraction, list rounds (whole CTA) otherwise; a list phase that meets a same-rank stretch comes back
-        uint32_t m = n;
-        bool keys = false;      // kk[] holds list-mode keys (after a list phase) rather than ranks
         for (;;) {
+            const bool done = list_rounds_par<kListWarps, 12>(T, id, kk, link, claim, m, s_red, s_dirty);
+            __syncthreads();
+            if (done) break;
+            // a stretch of same-rank pairs: batched rounds, by the first warp (their lookups are all the same few
+            // table slots, L1 hits; the passes over <= 4096 words of shared memory are a few microseconds)
+            if (threadIdx.x == 0) CFBPE_DBG_COUNT(2);
             if (threadIdx.x < 32) {
-                uint32_t rmin, mm = keys ? array_compact<12>(id, kk, m, threadIdx.x, rmin) : array_compact<0>(id, kk, m, threadIdx.x, rmin);
+                uint32_t rmin, mm = array_compact<12>(id, kk, m, threadIdx.x, rmin);
                 while (rmin != kNone) {
                     array_round(T, id, kk, link, claim, mm, rmin, threadIdx.x);
                     const uint32_t before = mm;
@@ -1602,14 +1592,7 @@ bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
             }
             __syncthreads();
             m = s_m;
-            const uint32_t rmin_now = s_rmin;
-            __syncthreads();
-            if (rmin_now == kNone) break;
-            const bool done = list_rounds_par<kListWarps, 12>(T, id, kk, link, claim, m, s_red, s_dirty);
-            __syncthreads();
-            if (done) break;
-            keys = true;
-            if (threadIdx.x == 0) CFBPE_DBG_COUNT(2);
+            if (s_rmin == kNone) break;
         }
         __syncthreads();
         if (threadIdx.x < 32) flag_parts(id, gid, m, lp.start, tok_bits, status, threadIdx.x);

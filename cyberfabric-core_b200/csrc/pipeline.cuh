@@ -111,22 +111,16 @@ inline void enqueue_short(const BatchView& b, const VocabSet& vs, const Workspac
 #endif
 }
 
-// K2b (pieces of 33..256 bytes, and those too big for shared memory) and K2c (257..4096 bytes, whole piece in shared memory)
-// are independent of each other: two streams if the caller has them.
 template <typename Stream, typename Prof>
 inline void enqueue_long(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
     if (!b.total_bytes) return;
     CFBPE_MARK(prof, K_LONG, stream, true);
     CFBPE_LAUNCH(bpe_long_kernel, (long_grid / 4) * kLongCtasPerSm, kLongWarps * 32, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
     CFBPE_MARK(prof, K_LONG, stream, false);
-}
-template <typename Stream, typename Prof>
-inline void enqueue_list(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
 #ifndef CFBPE_NO_DEFER
-    if (!b.total_bytes) return;
     CFBPE_MARK(prof, K_LIST, stream, true);
-    // two 64 KB CTAs per SM (long_grid = 4 x SM count), so that the short-piece kernels on the other stream keep ~100 KB of
-    // shared memory per SM
+    // the list phase of the big pieces K2b deferred: two 64 KB CTAs per SM (long_grid = 4 x SM count), so that the short-piece
+    // kernels on the other stream keep ~100 KB of shared memory per SM
     CFBPE_LAUNCH_SMEM(bpe_list_kernel, long_grid / 2, kListWarps * 32, kListSmemBytes, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
     CFBPE_MARK(prof, K_LIST, stream, false);
 #endif
@@ -175,20 +169,16 @@ inline void enqueue_back(const BatchView& b, const Workspace& w, uint32_t* out_i
 template <typename Stream, typename Prof, typename Ev>
 inline void enqueue_encode(const BatchView& b, const VocabSet& vs, const UcTables& uc, const Workspace& w,
                            uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_counts,
-                           uint32_t long_grid, Stream stream, Stream aux, Stream aux2, Ev ev_fork, Ev ev_join, Ev ev_join2, Prof* prof,
+                           uint32_t long_grid, Stream stream, Stream aux, Ev ev_fork, Ev ev_join, Prof* prof,
                            const uint64_t* token_base = nullptr) {
     enqueue_split(b, vs, uc, w, stream, prof);
     CFBPE_FORK(stream, aux, ev_fork);
 #ifdef CFBPE_K2_WINDOWED
     enqueue_short(b, vs, w, long_grid, stream, prof);      // the windowed kernel queues the long pieces itself
     enqueue_long(b, vs, w, long_grid, stream, prof);
-    enqueue_list(b, vs, w, long_grid, stream, prof);
 #else
-    CFBPE_FORK(stream, aux2, ev_fork);
-    enqueue_list(b, vs, w, long_grid, aux2, prof);          // the biggest pieces: the longest chain, first
     enqueue_long(b, vs, w, long_grid, aux, prof);
     enqueue_short(b, vs, w, long_grid, stream, prof);
-    CFBPE_JOIN(stream, aux2, ev_join2);
 #endif
     CFBPE_JOIN(stream, aux, ev_join);
     enqueue_back(b, w, out_ids, out_cap, out_offsets, out_counts, stream, prof, token_base);
