@@ -16,6 +16,7 @@ the per-shard token totals are all_gathered every step (the path's only exchange
   cpu_baseline  the oracle port on the host cores, bounded sample, rank 0 only
 """
 import os
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL's version / debug lines must not mix with the ONE JSON line on stdout
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initialises: the pipelined host path keeps ~20 streams busy (DESIGN.md section 4)
 import argparse
 import json

@@ -51,9 +51,12 @@ class OracleVocab:
         self.n_ranks = lib().oracle_vocab_size(self._h)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().oracle_vocab_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().oracle_vocab_free(self._h)
+                self._h = None
+        except Exception:      # interpreter shutdown: the module globals may be gone already
+            pass
 
     def encode(self, pattern_id: int, data: bytes) -> np.ndarray:
         out = np.empty(max(len(data), 1), dtype=np.uint32)
