@@ -16,7 +16,6 @@ the per-shard token totals are all_gathered every step (the path's only exchange
   cpu_baseline  the oracle port on the host cores, bounded sample, rank 0 only
 """
 import os
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL's version / debug lines must not mix with the ONE JSON line on stdout
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initialises: the pipelined host path keeps ~20 streams busy (DESIGN.md section 4)
 import argparse
 import json
@@ -142,8 +141,17 @@ def run_reference(args):
                              "sample": "each step: " + sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit_line(json.dumps(line))
     return 0
+
+
+# stdout carries exactly ONE JSON line: libraries (NCCL prints its version there) get stderr instead
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_line(text):
+    os.write(_REAL_STDOUT, (text + "\n").encode())
 
 
 def main():
@@ -350,7 +358,7 @@ def main():
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit_line(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
