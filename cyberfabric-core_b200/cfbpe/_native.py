@@ -22,7 +22,7 @@ EXPORTS = [
     "cfbpe_abi_version", "cfbpe_build_id", "cfbpe_create", "cfbpe_destroy", "cfbpe_last_error", "cfbpe_vocab_load",
     "cfbpe_vocab_get_info", "cfbpe_vocab_export", "cfbpe_vocab_import", "cfbpe_encode_batch", "cfbpe_count_batch",
     "cfbpe_encode_batch_device", "cfbpe_device_status", "cfbpe_host_alloc", "cfbpe_host_free",
-    "cfbpe_profile_enable", "cfbpe_profile_read",
+    "cfbpe_profile_enable", "cfbpe_profile_read", "cfbpe_decode_batch",
 ]
 
 
@@ -88,6 +88,8 @@ def load():
     L.cfbpe_encode_batch.argtypes = [vp, C.c_uint32, u8p, vp, u8p, vp, C.c_uint64, vp, vp]
     L.cfbpe_count_batch.restype = C.c_int
     L.cfbpe_count_batch.argtypes = [vp, C.c_uint32, u8p, vp, u8p, vp]
+    L.cfbpe_decode_batch.restype = C.c_int
+    L.cfbpe_decode_batch.argtypes = [vp, C.c_uint32, vp, vp, u8p, vp, C.c_uint64, vp]
     L.cfbpe_encode_batch_device.restype = C.c_int
     L.cfbpe_encode_batch_device.argtypes = [vp, C.c_uint32, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp,
                                             C.POINTER(C.c_uint64), vp]
@@ -212,6 +214,22 @@ class Context:
         self._check(load().cfbpe_count_batch(self._h, n, data.ctypes.data if data.size else None, offsets.ctypes.data,
                                              vid, out_counts.ctypes.data))
         return out_counts[:n]
+
+    def decode_batch(self, ids: np.ndarray, id_offsets: np.ndarray, vocab_ids=None, out_cap=None):
+        """ids (uint32, packed) + id_offsets (uint64, n+1) -> (bytes uint8, byte offsets uint64 n+1)"""
+        n = len(id_offsets) - 1
+        out_offsets = np.zeros(n + 1, dtype=np.uint64)
+        cap = int(out_cap) if out_cap is not None else max(int(len(ids)) * 8 + 64, 64)
+        vid = None if vocab_ids is None else vocab_ids.ctypes.data
+        while True:
+            out = np.empty(max(cap, 1), dtype=np.uint8)
+            rc = load().cfbpe_decode_batch(self._h, n, ids.ctypes.data if ids.size else None, id_offsets.ctypes.data, vid,
+                                           out.ctypes.data, cap, out_offsets.ctypes.data)
+            if rc == ENOSPC and out_cap is None:
+                cap = int(out_offsets[n])
+                continue
+            self._check(rc)
+            return out[:int(out_offsets[n])], out_offsets
 
     # ---- device-buffer API (raw pointers; torch tensors pass .data_ptr())
     def encode_batch_device(self, n_prompts, d_bytes, total_bytes, d_offsets, d_vocab_ids, d_out_ids, out_cap,

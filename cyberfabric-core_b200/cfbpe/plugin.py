@@ -114,6 +114,20 @@ class CountTokensRequest:
 
 
 @dataclass
+class DecodeBatchRequest:
+    vocab: VocabRef
+    ids: np.ndarray              # uint32, packed ids of all sequences
+    offsets: np.ndarray          # uint64, n+1 (in ids)
+    vocabs_per_prompt: Optional[Sequence[VocabRef]] = None
+
+
+@dataclass
+class DecodeBatchResponse:
+    bytes: np.ndarray            # uint8, the sequences' bytes back to back (tiktoken decode_bytes; not necessarily valid UTF-8)
+    offsets: np.ndarray          # uint64, n+1
+
+
+@dataclass
 class Usage:
     """gts.x.llmgw.core.usage.v1~"""
     input_tokens: int
@@ -128,6 +142,9 @@ class TokenizerPluginClient:
         raise NotImplementedError
 
     def count_tokens(self, ctx: SecurityContext, req: CountTokensRequest) -> np.ndarray:
+        raise NotImplementedError
+
+    def decode_batch(self, ctx: SecurityContext, req: "DecodeBatchRequest") -> "DecodeBatchResponse":
         raise NotImplementedError
 
 
@@ -266,6 +283,16 @@ class GpuBpeTokenizerPlugin(TokenizerPluginClient):
             return self.ctx.count_batch(req.bytes, req.offsets, vid, out_counts)
         except N.NativeError as e:
             raise _map_native(e) from e
+
+    def decode_batch(self, ctx: SecurityContext, req: DecodeBatchRequest) -> DecodeBatchResponse:
+        if req.ids.dtype != np.uint32 or req.offsets.dtype != np.uint64 or len(req.offsets) < 1:
+            raise InvalidInput("ids must be uint32 and offsets uint64 with n+1 entries")
+        vid = self._vocab_ids(req)
+        try:
+            out, offs = self.ctx.decode_batch(req.ids, req.offsets, vid)
+        except N.NativeError as e:
+            raise _map_native(e) from e
+        return DecodeBatchResponse(out, offs)
 
     def close(self):
         self.ctx.close()

@@ -1712,6 +1712,88 @@ prompt_offsets_kernel(BatchView b, const uint32_t* __restrict__ tok_bits, const 
     if (i < b.n_prompts && out_counts) out_counts[i] = static_cast<uint32_t>(rank_at(b.offsets[i + 1]) - r);
 }
 
+// ---------------------------------------------------------------------------------------
+// Decode: ids -> bytes.  tiktoken's decode_bytes: the concatenation of the tokens' bytes.
+//   decode_len:    length of every token (0xFFFFFFFF + status->bad_utf8-style flag for an id outside the vocabulary),
+//                  and the sum per tile of kDecodeTile tokens
+//   tile_scan:     (the kernel of K3) exclusive scan of the tile sums
+//   decode_copy:   one CTA per tile: scan of the lengths inside the tile, then every thread copies its token's bytes
+//   decode_offsets: byte offset of the first token of every sequence
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kDecodeTile = 1024;      // tokens per tile (4 per thread)
+struct DecodeView {
+    const uint32_t* ids;         // packed ids of all sequences
+    const uint64_t* id_offsets;  // [n_seqs + 1]
+    const uint8_t* vocab_ids;    // [n_seqs] or nullptr
+    uint32_t n_seqs;
+    uint64_t n_ids;
+};
+
+__global__ void __launch_bounds__(256)
+decode_len_kernel(DecodeView d, VocabSet vs, uint32_t* __restrict__ lens, uint32_t* __restrict__ tile_sums, DeviceStatus* status) {
+    __shared__ uint32_t s_tmp[8];
+    const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kDecodeTile;
+    uint32_t sum = 0;
+    for (uint32_t t = threadIdx.x; t < kDecodeTile; t += blockDim.x) {
+        const uint64_t i = base + t;
+        if (i >= d.n_ids) break;
+        uint32_t vid = 0;
+        if (d.vocab_ids) vid = d.vocab_ids[find_prompt(d.id_offsets, d.n_seqs, i)];
+        const TablesView& T = vs.v[vid];
+        const uint32_t id = d.ids[i];
+        uint32_t len = 0;
+        if (id < T.n_ranks) len = T.tokoff[id + 1] - T.tokoff[id];
+        else atomicOr(&status->bad_utf8, 1u);          // reported as "unknown token id" by the decode entry point
+        lens[i] = len;
+        sum += len;
+    }
+    const uint32_t total = block_reduce_add_256(sum, s_tmp);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256)
+decode_copy_kernel(DecodeView d, VocabSet vs, const uint32_t* __restrict__ lens, const uint64_t* __restrict__ tile_base,
+                   uint8_t* __restrict__ out, uint64_t out_cap) {
+    __shared__ uint32_t s_warp[8];
+    const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kDecodeTile + 4ull * threadIdx.x;   // my four consecutive tokens
+    uint32_t l[4], mine = 0;
+#pragma unroll
+    for (uint32_t t = 0; t < 4; ++t) { l[t] = (base + t < d.n_ids) ? lens[base + t] : 0u; mine += l[t]; }
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = mine;
+#pragma unroll
+    for (uint32_t s = 1; s < 32; s <<= 1) { const uint32_t o = __shfl_up_sync(kFull, x, s); if (lane >= s) x += o; }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (uint32_t k = 0; k < wid; ++k) woff += s_warp[k];
+    uint64_t o = tile_base[blockIdx.x] + woff + (x - mine);
+#pragma unroll
+    for (uint32_t t = 0; t < 4; ++t) {
+        if (base + t >= d.n_ids || !l[t]) continue;
+        uint32_t vid = 0;
+        if (d.vocab_ids) vid = d.vocab_ids[find_prompt(d.id_offsets, d.n_seqs, base + t)];
+        const TablesView& T = vs.v[vid];
+        const uint8_t* src = T.blob + T.tokoff[d.ids[base + t]];
+        for (uint32_t k = 0; k < l[t]; ++k) if (o + k < out_cap) out[o + k] = src[k];
+        o += l[t];
+    }
+}
+
+// out_offsets[s] = bytes before the first token of sequence s (out_offsets[n_seqs] = total).  One thread per sequence.
+__global__ void __launch_bounds__(256)
+decode_offsets_kernel(DecodeView d, const uint32_t* __restrict__ lens, const uint64_t* __restrict__ tile_base,
+                      uint64_t* __restrict__ out_offsets, const DeviceStatus* status) {
+    const uint64_t sidx = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (sidx > d.n_seqs) return;
+    const uint64_t i = d.id_offsets[sidx];
+    if (i >= d.n_ids) { out_offsets[sidx] = status->tok_end; return; }     // tile_scan left the total there
+    const uint64_t tile = i / kDecodeTile;
+    uint64_t r = tile_base[tile];
+    for (uint64_t k = tile * kDecodeTile; k < i; ++k) r += lens[k];
+    out_offsets[sidx] = r;
+}
+
 // the status of a sub-batch, stored straight into pinned host memory: a cudaMemcpyAsync would queue behind the previous
 // sub-batch's id download on the same copy engine, and the host would learn too late that the next download can start
 __global__ void status_publish_kernel(const DeviceStatus* __restrict__ d, DeviceStatus* h) {

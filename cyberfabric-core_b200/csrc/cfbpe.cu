@@ -66,6 +66,8 @@ struct cfbpe_ctx {
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t h2d_stream = nullptr;   // pipelined host calls: uploads run ahead of the kernels ...
     cudaStream_t d2h_stream = nullptr;   // ... and downloads trail them
+    uint32_t* d_dec_sums = nullptr;      // decode: bytes per tile of kDecodeTile tokens ...
+    uint64_t* d_dec_base = nullptr;      // ... and their exclusive scan
     cudaStream_t aux_stream = nullptr;   // the long-piece kernel runs here, next to the short-piece kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_scan[kMaxPipeChunks] = {};
@@ -425,6 +427,8 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     }
     ctx->ws.fix_cap = static_cast<uint32_t>(mb / 64 + 2 + 2 * kMaxPipeChunks);
     ok = ok && dmalloc(&ctx->ws.fix_list, ctx->ws.fix_cap) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_dec_sums, mb / kDecodeTile + 2) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_dec_base, mb / kDecodeTile + 2) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.tile_counts, nt) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.tile_base, nt) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.status, 1) == cudaSuccess;
@@ -497,6 +501,7 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     cudaFree(ctx->ws.piece_bits); cudaFree(ctx->ws.tok_bits); cudaFree(ctx->ws.ids_by_pos);
     cudaFree(ctx->ws.lscratch.rank); cudaFree(ctx->ws.lscratch.aux0); cudaFree(ctx->ws.lscratch.aux1);
     for (uint32_t c = 0; c < 3; ++c) cudaFree(ctx->ws.miss.list[c]);
+    cudaFree(ctx->d_dec_sums); cudaFree(ctx->d_dec_base);
     cudaFree(ctx->ws.fix_list);
     cudaFree(ctx->ws.long_list); cudaFree(ctx->ws.tile_counts); cudaFree(ctx->ws.tile_base); cudaFree(ctx->ws.status);
     cudaFree(ctx->d_uc1); cudaFree(ctx->d_uc2); cudaFree(ctx->d_ascii); cudaFree(ctx->d_fsm);
@@ -595,6 +600,51 @@ int cfbpe_count_batch(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t* bytes, 
     if (!ctx) return CFBPE_EINVAL;
     if (!out_counts && n_prompts) return fail(ctx, CFBPE_EINVAL, "out_counts is NULL");
     return run_host(ctx, n_prompts, bytes, offsets, vocab_ids, nullptr, 0, nullptr, out_counts, false);
+}
+
+int cfbpe_decode_batch(cfbpe_ctx* ctx, uint32_t n_seqs, const uint32_t* ids, const uint64_t* id_offsets,
+                       const uint8_t* vocab_ids, uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets) {
+    if (!ctx) return CFBPE_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    if (!id_offsets || !out_offsets) return fail(ctx, CFBPE_EINVAL, "offsets pointer is NULL");
+    if (n_seqs > ctx->max_prompts) return fail(ctx, CFBPE_EINVAL, "batch exceeds the limits of this context");
+    if (id_offsets[0] != 0) return fail(ctx, CFBPE_EINVAL, "id_offsets[0] must be 0");
+    for (uint32_t i = 0; i < n_seqs; ++i) if (id_offsets[i + 1] < id_offsets[i]) return fail(ctx, CFBPE_EINVAL, "id_offsets must not decrease");
+    const uint64_t n_ids = id_offsets[n_seqs];
+    if (n_ids > ctx->max_bytes) return fail(ctx, CFBPE_EINVAL, "batch exceeds the limits of this context");
+    if (n_ids && !ids) return fail(ctx, CFBPE_EINVAL, "ids is NULL");
+    for (uint32_t i = 0; vocab_ids && i < n_seqs; ++i)
+        if (vocab_ids[i] >= kMaxVocabs || !ctx->vocabs[vocab_ids[i]].loaded) return fail(ctx, CFBPE_ENOENT, "vocab " + std::to_string(vocab_ids[i]) + " is not loaded");
+    if (!vocab_ids && !ctx->vocabs[0].loaded) return fail(ctx, CFBPE_ENOENT, "vocab 0 is not loaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (n_ids) CK(cudaMemcpyAsync(ctx->d_out_ids, ids, n_ids * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_offsets, id_offsets, (static_cast<uint64_t>(n_seqs) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    if (vocab_ids && n_seqs) CK(cudaMemcpyAsync(ctx->d_vocab_ids, vocab_ids, n_seqs, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->ws.status, 0, sizeof(DeviceStatus), s));
+    DecodeView d{ctx->d_out_ids, ctx->d_offsets, vocab_ids ? ctx->d_vocab_ids : nullptr, n_seqs, n_ids};
+    const uint32_t n_tiles = static_cast<uint32_t>((n_ids + kDecodeTile - 1) / kDecodeTile);
+    if (n_tiles) decode_len_kernel<<<n_tiles, 256, 0, s>>>(d, ctx->vs, ctx->ws.ids_by_pos, ctx->d_dec_sums, ctx->ws.status);
+    tile_scan_kernel<<<1, n_tiles ? 1024 : 32, 0, s>>>(ctx->d_dec_sums, n_tiles, ctx->d_dec_base, ctx->ws.status, nullptr);
+    if (n_tiles) decode_copy_kernel<<<n_tiles, 256, 0, s>>>(d, ctx->vs, ctx->ws.ids_by_pos, ctx->d_dec_base, ctx->d_bytes, ctx->max_bytes);
+    decode_offsets_kernel<<<static_cast<unsigned>((static_cast<uint64_t>(n_seqs) + 1 + 255) / 256), 256, 0, s>>>(d, ctx->ws.ids_by_pos, ctx->d_dec_base, ctx->d_out_offsets, ctx->ws.status);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_status, ctx->ws.status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const DeviceStatus st = *ctx->h_status;
+    if (st.bad_utf8) return fail(ctx, CFBPE_EINVAL, "a token id is outside its vocabulary");
+    const uint64_t total = st.tok_end;
+    if (total > ctx->max_bytes) return fail(ctx, CFBPE_EINVAL, "the decoded batch exceeds max_batch_bytes of this context");
+    CK(cudaMemcpyAsync(out_offsets, ctx->d_out_offsets, (static_cast<uint64_t>(n_seqs) + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (total > out_cap || (total && !out_bytes)) {
+        CK(cudaStreamSynchronize(s));
+        out_offsets[n_seqs] = total;
+        return fail(ctx, CFBPE_ENOSPC, "out_cap too small: need " + std::to_string(total) + " bytes");
+    }
+    if (total) CK(cudaMemcpyAsync(out_bytes, ctx->d_bytes, total, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return CFBPE_OK;
 }
 
 int cfbpe_encode_batch_device(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t* d_bytes, uint64_t total_bytes,

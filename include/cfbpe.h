@@ -137,6 +137,15 @@ CFBPE_API int cfbpe_encode_batch(cfbpe_ctx *ctx, uint32_t n_prompts, const uint8
 CFBPE_API int cfbpe_count_batch(cfbpe_ctx *ctx, uint32_t n_prompts, const uint8_t *bytes, const uint64_t *offsets,
                       const uint8_t *vocab_ids, uint32_t *out_counts);
 
+/* Decode (tiktoken CoreBPE.decode_bytes): out_bytes = the concatenation of the tokens' bytes.
+ * ids: the packed token ids of n_seqs sequences, id_offsets[n_seqs + 1] their boundaries (in ids), vocab_ids[n_seqs] or NULL.
+ * out_offsets[n_seqs + 1]: byte boundaries of the decoded sequences in out_bytes.  CFBPE_ENOSPC if out_cap is too small
+ * (out_offsets[n_seqs] = bytes needed), CFBPE_EINVAL for an id outside its vocabulary or a batch beyond the context's limits
+ * (at most max_batch_bytes ids and max_batch_bytes decoded bytes).  Host buffers; no reference interface exists for it
+ * (the reference ships no tokenizer: SURVEY.md F1). */
+CFBPE_API int cfbpe_decode_batch(cfbpe_ctx* ctx, uint32_t n_seqs, const uint32_t* ids, const uint64_t* id_offsets,
+                                 const uint8_t* vocab_ids, uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets);
+
 /* Same path on device-resident buffers, enqueued on `stream` (a cudaStream_t; NULL = the legacy
  * default stream).  d_bytes must be readable for 32 bytes past total_bytes (the kernels read whole 16-byte
  * groups); the contents of that padding do not matter.  d_out_ids may be NULL (count only).  n_tokens (host, may be NULL) is written

@@ -279,6 +279,34 @@ def test_cased_runs_and_periodic_pieces_on_device(plug, ctx, oracle_vocabs, pat)
     assert np.array_equal(r.counts, want_counts)
 
 
+def test_decode_batch_is_the_inverse_of_encode(plug, ctx, tekken_bytes):
+    """decode = concatenation of the tokens' bytes (tiktoken decode_bytes).  Checked against
+    the rank file directly (token bytes by id) and as a round trip of encode over fuzz prompts, two vocabularies in one batch"""
+    from cfbpe import plugin as P, _native as N
+    toks = [base64.b64decode(l.split()[0]) for l in tekken_bytes.splitlines() if l.strip()]
+    prompts = [s.encode() for s in fuzzgen.fuzz_strings(4242, 3000, max_atoms=40)] + [b"", b"a", "中文".encode() * 700]
+    data, offs = pack(prompts)
+    vocabs = [P.VocabRef(SLOT_NAMES[i % 2]) for i in range(len(prompts))]
+    enc = plug.encode_batch(ctx, P.EncodeBatchRequest(P.VocabRef(SLOT_NAMES[0]), data, offs, vocabs_per_prompt=vocabs))
+    dec = plug.decode_batch(ctx, P.DecodeBatchRequest(P.VocabRef(SLOT_NAMES[0]), enc.ids, enc.offsets, vocabs_per_prompt=vocabs))
+    assert np.array_equal(dec.offsets, offs)
+    assert bytes(dec.bytes) == bytes(data)
+    # ids straight from the rank file, not only what encode produces
+    rng = np.random.default_rng(5)
+    ids = rng.integers(0, 100256, size=50000, dtype=np.uint32)
+    ioffs = np.array([0, 1, 1, 777, 30000, 50000], dtype=np.uint64)
+    dec = plug.decode_batch(ctx, P.DecodeBatchRequest(P.VocabRef(SLOT_NAMES[0]), ids, ioffs))
+    want = [b"".join(toks[int(t)] for t in ids[int(a):int(b)]) for a, b in zip(ioffs[:-1], ioffs[1:])]
+    assert bytes(dec.bytes) == b"".join(want)
+    assert dec.offsets.tolist() == [0] + list(np.cumsum([len(w) for w in want]))
+    # errors: an id outside the vocabulary, an output buffer that is too small
+    with pytest.raises(P.InvalidInput):
+        plug.decode_batch(ctx, P.DecodeBatchRequest(P.VocabRef(SLOT_NAMES[0]), np.array([5, 100256], dtype=np.uint32), np.array([0, 2], dtype=np.uint64)))
+    with pytest.raises(N.NativeError) as ei:
+        plug.ctx.decode_batch(ids, ioffs, None, out_cap=10)
+    assert ei.value.code == N.ENOSPC
+
+
 def test_pipelined_host_path_matches_oracle(oracle_vocabs, tekken_bytes, monkeypatch):
     """force the pipelined (sub-batched, 3-stream) host path with tiny sub-batches: many chunk seams, chained token ranks"""
     from cfbpe import _native as N
