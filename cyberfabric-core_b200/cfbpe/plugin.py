@@ -345,3 +345,103 @@ class LlmGatewayTokenizerService:
     def check_budget(self, ctx: SecurityContext, model: str, messages: Sequence[dict], remaining_tokens: int) -> bool:
         """pre-call estimate used by check_budget (modules/llm-gateway/docs/DESIGN.md:833-855)"""
         return self.count_tokens(ctx, model, messages).input_tokens <= remaining_tokens
+
+
+# --------------------------------------------------------------------------- micro-batcher (SURVEY.md section 8(f) item 4)
+class CountTokensMicroBatcher:
+    """Coalesces concurrent count_tokens calls (one chat request each, a few KB) into GPU-sized batches.
+
+    The gateway's request handlers call `count(ctx, model, texts)` from many threads (tokio tasks behind spawn_blocking in the
+    Rust host); a single worker drains the queue, packs what is waiting -- up to max_batch_bytes, or whatever arrived within
+    max_wait_s of the first item -- into ONE CountTokensRequest with one vocabulary per prompt, and hands every caller its own
+    counts.  In ModKit terms this is a `stateful` lifecycle task (docs/modkit_unified_system/08_lifecycle_stateful_tasks.md:14-58):
+    start() / stop() are its hooks.  A failed batch fails exactly the calls that were in it."""
+
+    def __init__(self, plugin: TokenizerPluginClient, max_batch_bytes: int = 8 << 20, max_wait_s: float = 0.0005, max_queue: int = 65536):
+        import queue
+        self._plugin, self._max_bytes, self._max_wait = plugin, int(max_batch_bytes), float(max_wait_s)
+        self._q = queue.Queue(maxsize=max_queue)
+        self._worker: Optional[threading.Thread] = None
+        self._stop = threading.Event()
+        self.batches = 0          # how many plugin calls were made (for tests / metrics)
+        self.items = 0
+
+    def start(self):
+        if self._worker is None:
+            self._stop.clear()
+            self._worker = threading.Thread(target=self._run, name="count-tokens-batcher", daemon=True)
+            self._worker.start()
+        return self
+
+    def stop(self):
+        self._stop.set()
+        if self._worker is not None:
+            self._q.put(None)
+            self._worker.join()
+            self._worker = None
+
+    def count(self, ctx: SecurityContext, model: str, texts: Sequence[str], timeout: Optional[float] = None) -> np.ndarray:
+        """token counts of `texts` under `model`'s vocabulary; blocks until the batch this call rode in is done"""
+        import queue
+        if self._worker is None:
+            raise ServiceUnavailable("the micro-batcher is not running")
+        item = {"ctx": ctx, "model": model, "texts": [t.encode("utf-8") for t in texts], "done": threading.Event(), "out": None, "err": None}
+        try:
+            self._q.put(item, timeout=timeout)
+        except queue.Full:
+            raise ServiceUnavailable("the count_tokens queue is full") from None
+        if not item["done"].wait(timeout):
+            raise ServiceUnavailable("count_tokens timed out")
+        if item["err"] is not None:
+            raise item["err"]
+        return item["out"]
+
+    def _run(self):
+        import queue, time
+        while not self._stop.is_set():
+            first = self._q.get()
+            if first is None:
+                break
+            batch, size = [first], sum(len(t) for t in first["texts"])
+            deadline = time.monotonic() + self._max_wait
+            while size < self._max_bytes:
+                try:
+                    nxt = self._q.get(timeout=max(0.0, deadline - time.monotonic()))
+                except queue.Empty:
+                    break
+                if nxt is None:
+                    self._stop.set()
+                    break
+                batch.append(nxt)
+                size += sum(len(t) for t in nxt["texts"])
+            self._flush(batch)
+        while True:               # fail what is still queued
+            try:
+                it = self._q.get_nowait()
+            except queue.Empty:
+                break
+            if it is not None:
+                it["err"] = ServiceUnavailable("the micro-batcher stopped"); it["done"].set()
+
+    def _flush(self, batch):
+        pieces = [t for it in batch for t in it["texts"]]
+        offs = np.zeros(len(pieces) + 1, dtype=np.uint64)
+        if pieces:
+            offs[1:] = np.cumsum([len(t) for t in pieces])
+        data = np.frombuffer(b"".join(pieces), dtype=np.uint8) if pieces else np.zeros(0, dtype=np.uint8)
+        vocabs = [VocabRef(it["model"]) for it in batch for _ in it["texts"]]
+        try:
+            counts = self._plugin.count_tokens(batch[0]["ctx"], CountTokensRequest(vocabs[0] if vocabs else VocabRef(batch[0]["model"]), data, offs,
+                                                                                  vocabs_per_prompt=vocabs)) if pieces else np.zeros(0, dtype=np.uint32)
+            k = 0
+            for it in batch:
+                n = len(it["texts"])
+                it["out"] = np.array(counts[k:k + n], dtype=np.uint32)
+                k += n
+        except Exception as e:    # noqa: BLE001 -- every caller of this batch gets the error
+            for it in batch:
+                it["err"] = e
+        self.batches += 1
+        self.items += len(batch)
+        for it in batch:
+            it["done"].set()

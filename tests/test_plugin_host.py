@@ -95,3 +95,50 @@ def test_shard_by_bytes_is_a_balanced_partition():
     parts = [D.shard_batch(data, offs, None, r, 4) for r in range(4)]
     assert np.array_equal(np.concatenate([p[0] for p in parts]), data)
     assert all(p[1][0] == 0 for p in parts)
+
+
+def test_micro_batcher_coalesces_concurrent_calls_and_isolates_failures():
+    """SURVEY.md section 8(f) item 4: concurrent count_tokens calls ride in shared batches; every caller gets its own counts;
+    a failing batch fails only its own callers; stop() fails what is queued"""
+    import threading, time
+    import numpy as np
+    from cfbpe import plugin as P
+
+    class WordCounter(P.TokenizerPluginClient):       # one "token" per space-separated word; "boom" poisons its batch
+        def __init__(self): self.calls = []
+        def count_tokens(self, ctx, req):
+            time.sleep(0.002)
+            n = len(req.offsets) - 1
+            assert len(req.vocabs_per_prompt) == n
+            texts = [bytes(req.bytes[int(req.offsets[i]):int(req.offsets[i + 1])]).decode() for i in range(n)]
+            self.calls.append(n)
+            if any("boom" in t for t in texts):
+                raise P.InvalidInput("boom")
+            return np.array([len(t.split()) for t in texts], dtype=np.uint32)
+
+    plug = WordCounter()
+    mb = P.CountTokensMicroBatcher(plug, max_wait_s=0.02).start()
+    ctx = P.SecurityContext.anonymous()
+    results, errors = {}, {}
+    def call(i):
+        try:
+            results[i] = mb.count(ctx, "cl100k_base", ["w " * (i % 7 + 1), "x"], timeout=10).tolist()
+        except P.TokenizerError as e:
+            errors[i] = e
+    threads = [threading.Thread(target=call, args=(i,)) for i in range(64)]
+    [t.start() for t in threads]; [t.join() for t in threads]
+    assert not errors and all(results[i] == [i % 7 + 1, 1] for i in range(64))
+    assert mb.items == 64 and mb.batches < 32          # coalesced
+    assert mb.count(ctx, "cl100k_base", [], timeout=10).tolist() == []
+    try:
+        mb.count(ctx, "cl100k_base", ["boom"], timeout=10)
+        assert False
+    except P.InvalidInput:
+        pass
+    assert mb.count(ctx, "cl100k_base", ["still fine"], timeout=10).tolist() == [2]
+    mb.stop()
+    try:
+        mb.count(ctx, "cl100k_base", ["late"], timeout=1)
+        assert False
+    except P.ServiceUnavailable:
+        pass
