@@ -1,11 +1,14 @@
 // bpe_kernels.cuh -- the encode hot path as CUDA kernels for sm_100a.
 //
-//   K1 pretok_split_kernel   packed prompt bytes -> piece-start bitmask        
-//   K2 bpe_encode_kernel     pieces -> token ids (whole-piece lookup, then the
-//                            min-rank merge loop, one lane per byte)           (a2)
-//   K2b bpe_long_kernel      pieces longer than one warp window               (a2)
-//   K3 flag_count / tile_scan / emit_compact
-//                            token flags -> dense id stream + offsets + counts (a3, a4)
+//   K1  pretok_split_kernel (+ pretok_fixup_kernel)   packed prompt bytes -> piece-start bitmask      
+//   K2s bpe_encode_pieces_kernel<1>   finds the pieces longer than 32 bytes (work list of K2b / K2c)
+//   K2a bpe_lookup_kernel             every short piece once: whole-piece lookup (CoreBPE's shortcut)       (a2)
+//   K2m bpe_merge_kernel              the misses: exact min-rank merge loop, one lane per piece              (a2)
+//   K2b bpe_long_kernel               pieces of 33.. bytes, one warp each: batched rounds + parallel-cut rounds (a2)
+//   K2c bpe_list_kernel               the list phase of big pieces, one CTA each, state in shared memory     (a2)
+//   K3  flag_count / tile_scan / emit_compact / prompt_offsets   token flags -> dense id stream + offsets + counts (a3, a4)
+//   decode_len / decode_copy / decode_offsets                    ids -> bytes
+//   (bpe_encode_pieces_kernel<2>, the fused predecessor of K2a + K2m, is kept as the CFBPE_K2_FUSED A/B build)
 //
 // Pure integer/indexing work: no tensor cores (north_star).  Bounds: HBM for the byte and id
 // streams, L2 latency for the rank-table lookups.
@@ -38,11 +41,7 @@ inline unsigned long long* dbg_counters() { static unsigned long long c[8]; retu
 #ifndef CFBPE_SPLIT_CHUNK
 #define CFBPE_SPLIT_CHUNK 64
 #endif
-#ifndef CFBPE_ENCODE_RANGE
-#define CFBPE_ENCODE_RANGE 1024
-#endif
 constexpr uint32_t kSplitChunk = CFBPE_SPLIT_CHUNK;     // bytes of text per K1 thread
-constexpr uint32_t kEncodeRange = CFBPE_ENCODE_RANGE;  // bytes of text per K2 warp
 constexpr uint32_t kBigPiece = 256;      // bytes: K2b serves longer pieces first (tail latency)
 constexpr uint32_t kScanTileWords = 256;   // flag words per K3 tile (= 8 KiB of text); one word per thread
 
@@ -333,13 +332,7 @@ pretok_fixup_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
 
 
 // ---------------------------------------------------------------------------------------
-// K2: encode.  One warp owns the pieces that START in its kEncodeRange bytes.  It walks them in
-// windows of up to 32 bytes made of whole pieces, one lane per byte:
-//   1. whole-piece lookup (CoreBPE's `if piece in ranks` shortcut) from the head lane;
-//   2. for the pieces that miss: parts = bytes, rank of each adjacent pair from the tables,
-//      then repeat { per-piece argmin (leftmost) by segmented warp shuffle; merge } until no
-//      pair of the piece is in the vocabulary (tiktoken/_educational.py:95-110);
-//   3. surviving lanes hold the ids: ids_by_pos[byte position] and one flag bit per id.
+// bit helpers shared by the K2 kernels
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
@@ -369,159 +362,6 @@ __device__ __forceinline__ uint64_t next_set_bit(const uint32_t* __restrict__ bi
     return p < limit ? p : limit;
 }
 
-#ifndef CFBPE_K2_MINBLOCKS
-#define CFBPE_K2_MINBLOCKS 4
-#endif
-__global__ void __launch_bounds__(256, CFBPE_K2_MINBLOCKS)
-bpe_encode_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits,
-                  uint32_t* __restrict__ ids_by_pos,    // may be nullptr (count only)
-                  uint32_t* __restrict__ tok_bits, LongPiece* __restrict__ long_list, uint32_t long_cap,
-                  DeviceStatus* status) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t r0 = warp * kEncodeRange;
-    if (r0 >= b.total_bytes) return;   // whole warp exits together
-    const uint64_t r1 = (r0 + kEncodeRange < b.total_bytes) ? r0 + kEncodeRange : b.total_bytes;
-    const uint64_t n_words = (b.total_bytes + 31) >> 5;
-    const uint8_t* __restrict__ text = b.bytes;
-
-    uint64_t ws = next_set_bit(piece_bits, r0, r1);
-    if (ws >= r1) return;
-    uint32_t pidx = find_prompt(b.offsets, b.n_prompts, ws);
-    uint64_t pe = b.offsets[pidx + 1];
-    uint32_t vid = b.vocab_ids ? b.vocab_ids[pidx] : 0;
-    TablesView T = vs.v[vid];
-
-    while (ws < r1) {
-        // ---- window geometry (warp-uniform)
-        if (ws >= pe) {   // first piece of a later prompt (usually the next one)
-            if (pidx + 2 <= b.n_prompts && b.offsets[pidx + 2] > ws) ++pidx;
-            else pidx = find_prompt(b.offsets, b.n_prompts, ws);
-            pe = b.offsets[pidx + 1];
-            const uint32_t nv = b.vocab_ids ? b.vocab_ids[pidx] : 0;
-            if (nv != vid) { vid = nv; T = vs.v[vid]; }
-        }
-        const uint32_t avail = (pe - ws < 32) ? static_cast<uint32_t>(pe - ws) : 32u;
-        uint64_t pb = load_bits33(piece_bits, n_words, ws);          // bit i: a piece starts at ws+i
-        if (pe - ws <= 32) pb |= 1ull << (pe - ws);                  // the prompt end closes the last piece
-        const uint64_t bnd = pb & ~1ull & ((2ull << avail) - 1);     // boundaries at 1..avail
-        uint32_t wlen;
-        if (!bnd) {
-            // ---- piece longer than a window: queue it for K2b
-            uint64_t e = next_set_bit(piece_bits, ws + 32, pe);
-            if (lane == 0) {   // big pieces fill the list from the back and are served first by K2b
-                const bool big = (e - ws) > kBigPiece;
-                atomicAdd(&status->long_bytes, static_cast<unsigned long long>(e - ws));
-                const uint32_t idx = atomicAdd(big ? &status->n_big : &status->n_long, 1u);
-                // a long piece holds > 32 bytes, so both counters together stay below long_cap = total/32 + 1
-                if (idx < long_cap) { LongPiece lp; lp.start = ws; lp.end = e; lp.vocab = vid; lp.pad = 0; long_list[big ? long_cap - 1 - idx : idx] = lp; }
-                else atomicOr(&status->long_overflow, 1u);
-            }
-            ws = e;   // pieces tile a prompt: e is the next piece start, or the prompt end
-            if (ws >= pe && ws < r1) ws = next_set_bit(piece_bits, ws, r1);
-            continue;
-        }
-        {
-            const uint64_t c = r1 - ws;   // pieces starting at >= r1 belong to the next warp
-            const uint64_t at_or_after = (c <= 32) ? (bnd >> c) << c : 0;
-            if (at_or_after) wlen = static_cast<uint32_t>(__ffsll(static_cast<long long>(at_or_after)) - 1);
-            else wlen = 63u - static_cast<uint32_t>(__clzll(static_cast<long long>(bnd)));
-        }
-        const uint32_t wmask = (wlen >= 32) ? kFull : ((1u << wlen) - 1u);
-        const uint32_t heads = static_cast<uint32_t>(pb) & wmask;            // piece starts inside the window
-        const bool active = lane < wlen;
-
-        // ---- per-lane piece geometry
-        const uint32_t my_byte = active ? text[ws + lane] : 0u;
-        const uint32_t head_lane = 31u - __clz(heads & (lanemask_lt(lane) | (1u << lane)));   // start of my piece
-        const uint32_t above = heads & ~(lanemask_lt(lane) | (1u << lane));
-        const uint32_t piece_end = above ? (__ffs(above) - 1u) : wlen;                        // one past my piece
-        const bool is_head = active && ((heads >> lane) & 1u);
-        const uint32_t plen = piece_end - head_lane;
-
-        // ---- whole-piece lookup: gather up to 12 bytes of key from the lanes to the right
-        uint32_t w4 = my_byte;
-        w4 |= __shfl_down_sync(kFull, my_byte, 1) << 8;
-        w4 |= __shfl_down_sync(kFull, my_byte, 2) << 16;
-        w4 |= __shfl_down_sync(kFull, my_byte, 3) << 24;                   // bytes lane..lane+3 (garbage past wlen is masked below)
-        const uint32_t w4b = __shfl_down_sync(kFull, w4, 4);
-        const uint32_t w4c = __shfl_down_sync(kFull, w4, 8);
-        uint32_t tok = kNone;
-        if (is_head && plen <= T.max_token_len) {
-            uint64_t k0 = static_cast<uint64_t>(w4) | (static_cast<uint64_t>(w4b) << 32);
-            uint32_t k1 = w4c;
-            if (plen < 8) k0 &= (1ull << (8 * plen)) - 1ull;
-            if (plen <= 8) k1 = 0; else if (plen < 12) k1 &= (1u << (8 * (plen - 8))) - 1u;
-            if (plen <= kShortMaxLen) {
-                tok = short_lookup(T, k0, k1, plen);
-            } else {
-                const uint8_t* p = text + ws + lane;
-                tok = long_lookup(T, long_hash(k0, k1, load_le32(p + plen - 4), plen), p, plen);
-            }
-        }
-        const uint32_t hit_heads = __ballot_sync(kFull, tok != kNone);
-        // lanes of pieces that still need the merge loop
-        const bool unresolved = active && !((hit_heads >> head_lane) & 1u);
-        uint32_t alive = __ballot_sync(kFull, unresolved);      // one part per byte
-        uint32_t out_mask = hit_heads;                          // lanes that hold a final id
-
-        if (alive) {
-            uint32_t id = unresolved ? T.byte2id[my_byte] : kNone;
-            // rank of (my part, next part); initial parts are single bytes -> direct byte-pair table
-            const uint32_t nb = __shfl_down_sync(kFull, my_byte, 1);
-            uint32_t rank = kNone;
-            if (unresolved && lane + 1 < piece_end) rank = T.bytepair[(my_byte << 8) | nb];
-            // longest unresolved piece of the window (warp-uniform) bounds the shuffle distance of the argmin
-            const uint32_t long8 = __ballot_sync(kFull, unresolved && plen > 8u);
-            const uint32_t long16 = __ballot_sync(kFull, unresolved && plen > 16u);
-            const uint32_t dmax = long16 ? 16u : (long8 ? 8u : 4u);
-            for (;;) {
-                // -- segmented argmin over each piece: key = rank<<5 | lane (rank < 2^21), leftmost wins ties.
-                //    (redux.sync with one member mask per piece was measured slower: it serialises per mask.)
-                uint32_t key = (rank != kNone) ? ((rank << 5) | lane) : kNone;
-                for (uint32_t d = 1; d <= dmax; d <<= 1) {
-                    const uint32_t o = __shfl_down_sync(kFull, key, d);
-                    if (lane + d < piece_end && o < key) key = o;
-                }
-                const uint32_t best = __shfl_sync(kFull, key, head_lane);   // min over my piece
-                const bool winner = unresolved && best != kNone && (best & 31u) == lane;
-                const uint32_t winners = __ballot_sync(kFull, winner);
-                if (!winners) break;
-                // -- the right partner of every winner dies: next alive lane above each winner bit.  Adding
-                //    (winners << 1) to the NOT-alive mask ripples each carry up to exactly that lane.
-                const uint32_t not_alive = ~alive;
-                const uint32_t dead = ((not_alive + (winners << 1)) ^ not_alive) & alive;
-                alive &= ~dead;
-                if (winner) id = best >> 5;                        // rank == id of the merged token
-                // -- refresh the two ranks each merge touches
-                const uint32_t nxt_mask = alive & ~(lanemask_lt(lane) | (1u << lane));
-                const uint32_t nxt = nxt_mask ? (__ffs(nxt_mask) - 1u) : 32u;
-                const uint32_t nid = __shfl_sync(kFull, id, nxt & 31u);
-                const bool alive_now = (alive >> lane) & 1u;
-                const bool nxt_is_winner = nxt < 32u && ((winners >> nxt) & 1u);
-                if (alive_now && unresolved && (winner || nxt_is_winner)) {
-                    rank = (nxt < piece_end) ? pair_lookup(T, id, nid) : kNone;
-                }
-                if (!alive_now) rank = kNone;
-            }
-            if (unresolved && ((alive >> lane) & 1u)) tok = id;
-            out_mask |= alive;
-        }
-
-        // ---- emit
-        if ((out_mask >> lane) & 1u) {
-            if (ids_by_pos) ids_by_pos[ws + lane] = tok;
-        }
-        if (lane == 0) {
-            const uint64_t w = ws >> 5;
-            const uint32_t sh = static_cast<uint32_t>(ws & 31);
-            atomicOr(&tok_bits[w], out_mask << sh);
-            if (sh && (out_mask >> (32 - sh))) atomicOr(&tok_bits[w + 1], out_mask >> (32 - sh));
-        }
-        ws += wlen;
-        if (ws >= pe && ws < r1) ws = next_set_bit(piece_bits, ws, r1);   // skip empty prompts / reach next prompt's first piece
-    }
-}
 
 // ---------------------------------------------------------------------------------------
 // K2 (lane-per-piece form).  The window kernel above spends ~19 warp-instructions per byte because one
@@ -990,104 +830,8 @@ __device__ __forceinline__ uint32_t array_compact(uint32_t* id, uint32_t* rk, ui
     return out;
 }
 
-// phase B: linked list over the compact array, ONE merge per round (exact sequential order).  The round is a
-// dependent chain  argmin -> link[i] -> {link[j], nid[j], id[q]} -> two table probes -> cached minima,  so the
-// data is laid out to keep that chain short:
-//   link[i] = next<<16 | prev           (one load names both neighbours; m <= 65535)
-//   nid[i]  = id of the part after i    (the right-hand probe needs no id[] load of the part after the partner)
-// Lane L owns parts [L<<csh, (L+1)<<csh); the minimum of each eighth of that chunk is cached in shared memory and
-// maintained incrementally: only a sub-chunk whose cached minimum element got a larger rank is re-scanned, and the
-// winner's sub-chunk is pre-loaded while the probes are in flight.
 constexpr uint32_t kListMax = 65535;
 constexpr uint32_t kMedSmem = 256;   // bytes: pieces up to this size keep their merge state in shared memory
-__device__ __forceinline__ void list_rounds(const TablesView& T, uint32_t* __restrict__ id, uint32_t* __restrict__ rk,
-                                            uint32_t* __restrict__ link, uint32_t* __restrict__ nid, uint32_t m,
-                                            uint32_t* subr, uint32_t* subp, uint32_t lane) {
-    constexpr uint32_t kNoPrev = 0xFFFFu;
-    uint32_t csh = 0;
-    while ((32u << csh) < m) ++csh;               // chunk = 2^csh parts per lane
-    const uint32_t ssh = csh >= 3 ? csh - 3 : 0;  // sub-chunk = 2^ssh parts, nsub = chunk / sub-chunk <= 8
-    const uint32_t nsub = 1u << (csh - ssh);
-    for (uint32_t i = lane; i < m; i += 32) {
-        link[i] = ((i + 1) << 16) | (i ? i - 1 : kNoPrev);
-        nid[i] = (i + 1 < m) ? id[i + 1] : kNone;
-    }
-    __syncwarp();
-    const uint32_t lo = lane << csh;
-    auto scan_sub = [&](uint32_t ks, uint32_t skip, uint32_t& r0, uint32_t& p0) {   // min over the sub-chunk except `skip`
-        r0 = kNone; p0 = 0;
-        const uint32_t x0 = lo + (ks << ssh), x1 = (x0 + (1u << ssh)) < m ? (x0 + (1u << ssh)) : m;
-        for (uint32_t xb = x0; xb < x1; xb += 16) {   // 16 independent loads in flight (one L2 round trip), then the reduction
-            uint32_t v[16];
-#pragma unroll
-            for (uint32_t t = 0; t < 16; ++t) v[t] = (xb + t < x1 && xb + t != skip) ? rk[xb + t] : kNone;
-#pragma unroll
-            for (uint32_t t = 0; t < 16; ++t) if (v[t] < r0) { r0 = v[t]; p0 = xb + t; }
-        }
-    };
-    uint32_t mymin = kNone, mypos = 0;
-    auto lane_min = [&]() {
-        mymin = kNone;
-        for (uint32_t ks = 0; ks < nsub; ++ks) { const uint32_t rr = subr[ks * 32]; if (rr < mymin) { mymin = rr; mypos = subp[ks * 32]; } }
-    };
-    for (uint32_t ks = 0; ks < nsub; ++ks) {
-        uint32_t r0 = kNone, p0 = 0;
-        if (lo < m) scan_sub(ks, kNone, r0, p0);
-        subr[ks * 32] = r0; subp[ks * 32] = p0;
-    }
-    lane_min();
-    for (;;) {
-        const uint32_t best = __reduce_min_sync(kFull, mymin != kNone ? ((mymin << 5) | lane) : kNone);
-        if (best == kNone) break;
-        const uint32_t r = best >> 5;                          // rank == id of the merged token
-        const uint32_t i = __shfl_sync(kFull, mypos, best & 31u);
-        const uint32_t li = link[i];
-        const uint32_t j = li >> 16, q = li & 0xFFFFu;
-        const uint32_t oi = i >> csh;
-        // the owner of i pre-loads the rest of i's sub-chunk while the probes below are in flight
-        uint32_t pr = kNone, pp = 0;
-        if (lane == oi) scan_sub((i - lo) >> ssh, i, pr, pp);
-        // lane 0: right-hand probe (merged, part after the partner); lane 1: left-hand probe (previous part, merged)
-        uint32_t val = kNone, k = 0;
-        if (lane == 0) {
-            k = link[j] >> 16;
-            const uint32_t idk = nid[j];
-            if (k < m) val = pair_lookup(T, r, idk);
-        }
-        if (lane == 1 && q != kNoPrev) val = pair_lookup(T, id[q], r);
-        const uint32_t newR = __shfl_sync(kFull, val, 0);
-        const uint32_t newL = __shfl_sync(kFull, val, 1);
-        k = __shfl_sync(kFull, k, 0);
-        if (lane == 0) {
-            id[i] = r; id[j] = kNone; rk[j] = kNone; rk[i] = newR;
-            link[i] = (k << 16) | q;
-            nid[i] = nid[j];
-            if (k < m) link[k] = (link[k] & 0xFFFF0000u) | i;
-            if (q != kNoPrev) { rk[q] = newL; nid[q] = r; }
-        }
-        __syncwarp();
-        const uint32_t oj = j >> csh, oq = (q != kNoPrev) ? (q >> csh) : 32u;
-        if (lane == oi || lane == oj || lane == oq) {
-            if (lane == oi) {       // i was its sub-chunk's minimum; the others were pre-loaded, but j / q may sit there too
-                const uint32_t ks = (i - lo) >> ssh;
-                if ((j >> ssh) == (i >> ssh) || (q != kNoPrev && (q >> ssh) == (i >> ssh))) scan_sub(ks, kNone, pr, pp);
-                else if (newR < pr || (newR == pr && i < pp)) { pr = newR; pp = i; }
-                subr[ks * 32] = pr; subp[ks * 32] = pp;
-            }
-            if (lane == oj && (j >> ssh) != (i >> ssh)) {
-                const uint32_t ks = (j - lo) >> ssh;
-                if (subp[ks * 32] == j) { uint32_t r0, p0; scan_sub(ks, kNone, r0, p0); subr[ks * 32] = r0; subp[ks * 32] = p0; }
-            }
-            if (lane == oq && (q >> ssh) != (i >> ssh)) {
-                const uint32_t ks = (q - lo) >> ssh;
-                const uint32_t cr = subr[ks * 32], cp = subp[ks * 32];
-                if (newL < cr || (newL == cr && q < cp)) { subr[ks * 32] = newL; subp[ks * 32] = q; }
-                else if (cp == q) { uint32_t r0, p0; scan_sub(ks, kNone, r0, p0); subr[ks * 32] = r0; subp[ks * 32] = p0; }
-            }
-            lane_min();
-        }
-    }
-}
 
 // phase B, multi-merge form: up to 32 merges per round, still in the EXACT order of the sequential loop.
 // Each lane proposes the minimum pair of its chunk and looks up -- all lanes at once, one table round trip -- the two
@@ -1367,48 +1111,6 @@ __device__ __forceinline__ bool list_rounds_par(const TablesView& T, uint32_t* i
     }
 }
 
-// phase B for pieces that live in shared memory (m <= kMedSmem): every lane owns at most 8 parts and simply re-reads
-// them each round -- cheaper than maintaining cached minima when a chunk is this small.
-__device__ __forceinline__ void list_rounds_small(const TablesView& T, uint32_t* id, uint32_t* rk, uint32_t* link, uint32_t* nid,
-                                                  uint32_t m, uint32_t lane) {
-    constexpr uint32_t kNoPrev = 0xFFFFu;
-    uint32_t csh = 0;
-    while ((32u << csh) < m) ++csh;               // chunk = 2^csh <= 8 parts per lane
-    for (uint32_t i = lane; i < m; i += 32) {
-        link[i] = ((i + 1) << 16) | (i ? i - 1 : kNoPrev);
-        nid[i] = (i + 1 < m) ? id[i + 1] : kNone;
-    }
-    __syncwarp();
-    const uint32_t lo = lane << csh;
-    const uint32_t hi = (lo + (1u << csh)) < m ? (lo + (1u << csh)) : m;
-    for (;;) {
-        uint32_t mymin = kNone, mypos = 0;
-        for (uint32_t x = lo; x < hi; ++x) { const uint32_t r = rk[x]; if (r < mymin) { mymin = r; mypos = x; } }
-        const uint32_t best = __reduce_min_sync(kFull, mymin != kNone ? ((mymin << 5) | lane) : kNone);
-        if (best == kNone) break;
-        const uint32_t r = best >> 5;
-        const uint32_t i = __shfl_sync(kFull, mypos, best & 31u);
-        const uint32_t li = link[i];
-        const uint32_t j = li >> 16, q = li & 0xFFFFu;
-        uint32_t val = kNone, k = 0;
-        if (lane == 0) {
-            k = link[j] >> 16;
-            if (k < m) val = pair_lookup(T, r, nid[j]);
-        }
-        if (lane == 1 && q != kNoPrev) val = pair_lookup(T, id[q], r);
-        const uint32_t newR = __shfl_sync(kFull, val, 0);
-        const uint32_t newL = __shfl_sync(kFull, val, 1);
-        if (lane == 0) {
-            id[i] = r; id[j] = kNone; rk[j] = kNone; rk[i] = newR;
-            link[i] = (k << 16) | q;
-            nid[i] = nid[j];
-            if (k < m) link[k] = (link[k] & 0xFFFF0000u) | i;
-            if (q != kNoPrev) { rk[q] = newL; nid[q] = r; }
-        }
-        __syncwarp();
-    }
-}
-
 // one flag per surviving part of a piece (dead slots hold kNone); order along the piece's slice is token order.
 // copy_to != nullptr: the state lives in shared memory, the ids go to the slice as well.
 __device__ __forceinline__ void flag_parts(const uint32_t* id, uint32_t* copy_to, uint32_t m, uint64_t start,
@@ -1445,10 +1147,6 @@ constexpr uint32_t kLongWarps = 4;
 __global__ void __launch_bounds__(kLongWarps * 32, 32 / kLongWarps)
 bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
-#ifdef CFBPE_SINGLE_MERGE_ROUNDS
-    __shared__ uint32_t s_subr[kLongWarps][8][32];   // [warp][sub-chunk][lane] cached minimum rank ...
-    __shared__ uint32_t s_subp[kLongWarps][8][32];   // ... and its position (phase B)
-#endif
     __shared__ uint32_t s_med[kLongWarps][4][kMedSmem];   // [warp][id | rank | aux0 | aux1] of a piece of <= kMedSmem bytes
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_big = status->n_big;
@@ -1505,14 +1203,10 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
             if (rmin == kNone || merged * 8u >= m || m <= 32u || m > kListMax) continue;
             // -- list phase
             if (in_smem) {
-#ifdef CFBPE_SMALL_SINGLE_MERGE
-                list_rounds_small(T, id, rk, a0, a1, m, lane); break;
-#else
                 if (list_rounds_par<1, 8>(T, id, rk, a0, a1, m, nullptr)) break;
                 if (lane == 0) CFBPE_DBG_COUNT(1);
                 m = array_compact<8>(id, rk, m, lane, rmin);
                 continue;
-#endif
             }
 #ifndef CFBPE_NO_DEFER
             if (m <= kDeferMaxParts && T.n_ranks < kListMaxRank) {   // bpe_list_kernel goes on from here, in shared memory
@@ -1521,12 +1215,8 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
                 break;
             }
 #endif
-#ifdef CFBPE_SINGLE_MERGE_ROUNDS
-            list_rounds(T, id, rk, a0, a1, m, &s_subr[threadIdx.x >> 5][0][lane], &s_subp[threadIdx.x >> 5][0][lane], lane);
-#else
             if (lane == 0) CFBPE_DBG_COUNT(5);
             list_rounds_multi(T, id, rk, a0, a1, m, lane);
-#endif
             __syncwarp();
             break;
         }

@@ -74,25 +74,17 @@ inline void enqueue_split(const BatchView& b, const VocabSet& vs, const UcTables
     CFBPE_LAUNCH(pretok_split_kernel, static_cast<unsigned>((n_chunks + 255) / 256), 256, stream, b, vs, uc, w.piece_bits, w.status, w.fix_list, w.fix_cap);
     CFBPE_LAUNCH(pretok_fixup_kernel, 296u, 256, stream, b, vs, uc, w.piece_bits, w.status, w.fix_list, w.fix_cap);   // almost always empty
     CFBPE_MARK(prof, K_SPLIT, stream, false);
-#ifndef CFBPE_K2_WINDOWED
     const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
     CFBPE_MARK(prof, K_LONGSCAN, stream, true);
     CFBPE_LAUNCH(bpe_encode_pieces_kernel<1>, static_cast<unsigned>((n_warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, stream,
                  b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
     CFBPE_MARK(prof, K_LONGSCAN, stream, false);
-#endif
 }
 
 template <typename Stream, typename Prof>
 inline void enqueue_short(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
     if (!b.total_bytes) return;
-#if defined(CFBPE_K2_WINDOWED)
-    CFBPE_MARK(prof, K_ENCODE, stream, true);
-    const uint64_t n_warps = (b.total_bytes + kEncodeRange - 1) / kEncodeRange;
-    CFBPE_LAUNCH(bpe_encode_kernel, static_cast<unsigned>((n_warps + 7) / 8), 256, stream,
-                 b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
-    CFBPE_MARK(prof, K_ENCODE, stream, false);
-#elif defined(CFBPE_K2_FUSED)
+#if defined(CFBPE_K2_FUSED)
     CFBPE_MARK(prof, K_ENCODE, stream, true);
     const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
     CFBPE_LAUNCH(bpe_encode_pieces_kernel<2>, static_cast<unsigned>((n_warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, stream,
@@ -173,13 +165,8 @@ inline void enqueue_encode(const BatchView& b, const VocabSet& vs, const UcTable
                            const uint64_t* token_base = nullptr) {
     enqueue_split(b, vs, uc, w, stream, prof);
     CFBPE_FORK(stream, aux, ev_fork);
-#ifdef CFBPE_K2_WINDOWED
-    enqueue_short(b, vs, w, long_grid, stream, prof);      // the windowed kernel queues the long pieces itself
-    enqueue_long(b, vs, w, long_grid, stream, prof);
-#else
     enqueue_long(b, vs, w, long_grid, aux, prof);
     enqueue_short(b, vs, w, long_grid, stream, prof);
-#endif
     CFBPE_JOIN(stream, aux, ev_join);
     enqueue_back(b, w, out_ids, out_cap, out_offsets, out_counts, stream, prof, token_base);
 }
