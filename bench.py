@@ -349,7 +349,7 @@ def main():
                    "l2": "inputs (%.0f MB) and per-byte work arrays (> 1 GB) exceed the 126 MB L2; no flush needed" % (total / 1e6),
                    "scale": args.scale},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": 12 * args.steps,   # split, split fix-up, long-piece scan, piece lookup, short-piece merges, long pieces (medium), long pieces (big), big-piece lists, flag_count, tile_scan, emit, offsets
+        "gpu_launches": 11 * args.steps,   # split, split fix-up, long-piece scan, piece lookup, short-piece merges, long pieces, long-piece lists, flag_count, tile_scan, emit, offsets
         "kernel_ms": kms,   # CUDA-event durations; bpe_long runs on a second stream next to bpe_encode, so they overlap
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],

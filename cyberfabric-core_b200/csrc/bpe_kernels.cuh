@@ -73,7 +73,7 @@ struct DeviceStatus {
     uint32_t miss_next[3]; // K2m work tickets
     uint32_t miss_overflow;
     uint32_t fix_n;        // K1 threads that stopped in S_W_U (pretok_fixup_kernel finishes them)
-    uint32_t big_next;     // K2b work ticket of the launch that serves the big pieces
+    uint32_t pad3;
     uint32_t defer_n;      // pieces K2b handed to K2c ...
     unsigned long long defer_parts;   // ... and their parts at hand-over
 };
@@ -1146,18 +1146,17 @@ constexpr uint32_t kListMaxRank = (1u << 20) - 1u;   // K2c packs rank << 12 | p
 constexpr uint32_t kLongWarps = 4;
 __global__ void __launch_bounds__(kLongWarps * 32, 32 / kLongWarps)
 bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* status,
-                uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits, uint32_t which) {
-    // which = 0: the pieces of 33..kBigPiece bytes; 1: the big ones.  Two launches, so that bpe_list_kernel -- which takes over
-    // the list phase of the big pieces -- waits only for the (short) launch that feeds it, not for all the medium pieces.
+                uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
     __shared__ uint32_t s_med[kLongWarps][4][kMedSmem];   // [warp][id | rank | aux0 | aux1] of a piece of <= kMedSmem bytes
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t n_mine = status->long_overflow ? 0u : (which ? status->n_big : status->n_long);
+    const uint32_t n_big = status->n_big;
+    const uint32_t n_all = status->long_overflow ? 0u : status->n_long + n_big;
     for (;;) {
         uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(which ? &status->big_next : &status->long_next, 1u);
+        if (lane == 0) item = atomicAdd(&status->long_next, 1u);
         item = __shfl_sync(kFull, item, 0);
-        if (item >= n_mine) break;
-        const uint32_t slot = which ? long_cap - 1 - item : item;
+        if (item >= n_all) break;
+        const uint32_t slot = item < n_big ? long_cap - 1 - item : item - n_big;
         const LongPiece lp = long_list[slot];
         const TablesView T = vs.v[lp.vocab];
         const uint8_t* __restrict__ p = b.bytes + lp.start;

@@ -68,10 +68,8 @@ struct cfbpe_ctx {
     cudaStream_t d2h_stream = nullptr;   // ... and downloads trail them
     uint32_t* d_dec_sums = nullptr;      // decode: bytes per tile of kDecodeTile tokens ...
     uint64_t* d_dec_base = nullptr;      // ... and their exclusive scan
-    cudaStream_t aux_stream = nullptr, aux2_stream = nullptr;   // the two long-piece branches run here, next to the short-piece kernels
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
-    cudaStream_t list_streams[4] = {};   // the big-piece branch of the sub-batches of a pipelined host call
-    cudaEvent_t ev_list[kMaxPipeChunks] = {};
+    cudaStream_t aux_stream = nullptr;   // the long-piece kernel runs here, next to the short-piece kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_scan[kMaxPipeChunks] = {};
     cudaStream_t front[kFrontStreams] = {};   // front streams 1.. of a pipelined host call (0 = stream)
     cudaStream_t side[kSideStreams] = {};  // long-piece tails + emit of sub-batch k overlap the front of k+1
@@ -266,14 +264,7 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         CK(cudaEventRecord(ctx->ev_scan[k], ss));
         if (trace) CK(cudaEventRecord(ctx->trace[k][1], ss));
         CK(cudaStreamWaitEvent(ck, ctx->ev_scan[k], 0));
-        {   // the big-piece branch on a stream of its own; the back stage waits for it
-            cudaStream_t ls = ctx->list_streams[k & 3];
-            CK(cudaStreamWaitEvent(ls, ctx->ev_scan[k], 0));
-            enqueue_long_big(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ls, static_cast<ProfEvents*>(nullptr));
-            CK(cudaEventRecord(ctx->ev_list[k], ls));
-        }
         enqueue_long(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ss, static_cast<ProfEvents*>(nullptr));   // tail overlaps what follows on cs
-        CK(cudaStreamWaitEvent(ss, ctx->ev_list[k], 0));
         if (trace) CK(cudaEventRecord(ctx->trace[k][3], ss));
         enqueue_short(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ck, static_cast<ProfEvents*>(nullptr));
         CK(cudaEventRecord(ctx->ev_front[k], ck));
@@ -312,7 +303,6 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
     CK(cudaStreamSynchronize(cs));
     for (int k = 1; k < kFrontStreams; ++k) CK(cudaStreamSynchronize(ctx->front[k]));
     for (int k = 0; k < kSideStreams; ++k) CK(cudaStreamSynchronize(ctx->side[k]));
-    for (int k = 0; k < 4; ++k) CK(cudaStreamSynchronize(ctx->list_streams[k]));
     if (trace && !err) {
         fprintf(stderr, "pipe trace (ms since the first upload was enqueued): sub-batch bytes | h2d split short long_end back d2h\n");
         for (int k = 0; k < nc; ++k) {
@@ -353,7 +343,7 @@ int run_host(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const uint64_t* o
 
     BatchView b{ctx->d_bytes, ctx->d_offsets, vocab_ids ? ctx->d_vocab_ids : nullptr, n, total};
     enqueue_encode(b, ctx->vs, ctx->uc, ctx->ws, want_ids ? ctx->d_out_ids : nullptr, ctx->max_bytes, ctx->d_out_offsets,
-                   ctx->d_out_counts, static_cast<uint32_t>(ctx->sm_count * 4), s, prof ? s : ctx->aux_stream, prof ? s : ctx->aux2_stream, ctx->ev_fork, ctx->ev_join, ctx->ev_join2, prof);
+                   ctx->d_out_counts, static_cast<uint32_t>(ctx->sm_count * 4), s, prof ? s : ctx->aux_stream, ctx->ev_fork, ctx->ev_join, prof);
     CK(cudaGetLastError());
     if (prof) cudaEventRecord(prof->d2h[0], s);
     CK(cudaMemcpyAsync(ctx->h_status, ctx->ws.status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
@@ -462,12 +452,8 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         ok = ok && cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
-        ok = ok && cudaStreamCreateWithPriority(&ctx->aux2_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
-        for (int k = 0; ok && k < 4; ++k) ok = cudaStreamCreateWithPriority(&ctx->list_streams[k], cudaStreamNonBlocking, prio_hi) == cudaSuccess;
     }
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) == cudaSuccess;
-    for (int k = 0; ok && k < kMaxPipeChunks; ++k) ok = cudaEventCreateWithFlags(&ctx->ev_list[k], cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; ok && k < kMaxPipeChunks; ++k) ok = cudaEventCreateWithFlags(&ctx->ev_scan[k], cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; ok && k < kMaxPipeChunks; ++k)
         ok = cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming) == cudaSuccess &&
@@ -528,10 +514,6 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     for (int k = 0; k < kSideStreams; ++k) if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
     for (int k = 0; k < kMaxPipeChunks; ++k) if (ctx->ev_scan[k]) cudaEventDestroy(ctx->ev_scan[k]);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
-    if (ctx->aux2_stream) cudaStreamDestroy(ctx->aux2_stream);
-    for (int k = 0; k < 4; ++k) if (ctx->list_streams[k]) cudaStreamDestroy(ctx->list_streams[k]);
-    for (int k = 0; k < kMaxPipeChunks; ++k) if (ctx->ev_list[k]) cudaEventDestroy(ctx->ev_list[k]);
-    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
@@ -681,7 +663,7 @@ int cfbpe_encode_batch_device(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t*
     if (prof) { std::memset(prof->launched, 0, sizeof prof->launched); cudaEventRecord(prof->total[0], s); cudaEventRecord(prof->h2d[0], s); cudaEventRecord(prof->h2d[1], s); }
     BatchView b{d_bytes, d_offsets, d_vocab_ids, n_prompts, total_bytes};
     enqueue_encode(b, ctx->vs, ctx->uc, ctx->ws, d_out_ids, out_cap, d_out_offsets, d_out_counts,
-                   static_cast<uint32_t>(ctx->sm_count * 4), s, prof ? s : ctx->aux_stream, prof ? s : ctx->aux2_stream, ctx->ev_fork, ctx->ev_join, ctx->ev_join2, prof);   // profiling: one stream, so that the per-kernel times do not overlap
+                   static_cast<uint32_t>(ctx->sm_count * 4), s, prof ? s : ctx->aux_stream, ctx->ev_fork, ctx->ev_join, prof);   // profiling: one stream, so that the per-kernel times do not overlap
     CK(cudaGetLastError());
     if (prof) { cudaEventRecord(prof->d2h[0], s); cudaEventRecord(prof->d2h[1], s); cudaEventRecord(prof->total[1], s); }
     if (n_tokens || prof) {

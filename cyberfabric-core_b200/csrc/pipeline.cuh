@@ -103,27 +103,19 @@ inline void enqueue_short(const BatchView& b, const VocabSet& vs, const Workspac
 #endif
 }
 
-// The long pieces in two branches that do not wait for each other:
-//   big     K2b over the pieces longer than 256 bytes (batched rounds on global scratch), then K2c (their list phase)
-//   medium  K2b over the pieces of 33..256 bytes
-template <typename Stream, typename Prof>
-inline void enqueue_long_big(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
-    if (!b.total_bytes) return;
-    CFBPE_MARK(prof, K_LIST, stream, true);
-    CFBPE_LAUNCH(bpe_long_kernel, (long_grid / 4) * kLongCtasPerSm, kLongWarps * 32, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits, 1u);
-#ifndef CFBPE_NO_DEFER
-    // two 64 KB CTAs per SM (long_grid = 4 x SM count), so that the short-piece kernels on the other stream keep ~100 KB of
-    // shared memory per SM
-    CFBPE_LAUNCH_SMEM(bpe_list_kernel, long_grid / 2, kListWarps * 32, kListSmemBytes, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
-#endif
-    CFBPE_MARK(prof, K_LIST, stream, false);
-}
 template <typename Stream, typename Prof>
 inline void enqueue_long(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
     if (!b.total_bytes) return;
     CFBPE_MARK(prof, K_LONG, stream, true);
-    CFBPE_LAUNCH(bpe_long_kernel, (long_grid / 4) * kLongCtasPerSm, kLongWarps * 32, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits, 0u);
+    CFBPE_LAUNCH(bpe_long_kernel, (long_grid / 4) * kLongCtasPerSm, kLongWarps * 32, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
     CFBPE_MARK(prof, K_LONG, stream, false);
+#ifndef CFBPE_NO_DEFER
+    CFBPE_MARK(prof, K_LIST, stream, true);
+    // the list phase of the big pieces K2b deferred: two 64 KB CTAs per SM (long_grid = 4 x SM count), so that the short-piece
+    // kernels on the other stream keep ~100 KB of shared memory per SM
+    CFBPE_LAUNCH_SMEM(bpe_list_kernel, long_grid / 2, kListWarps * 32, kListSmemBytes, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
+    CFBPE_MARK(prof, K_LIST, stream, false);
+#endif
 }
 
 // back = count | scan | emit.  Only the scan reads what the previous sub-batch of a pipelined call produced (token_base), so
@@ -169,15 +161,12 @@ inline void enqueue_back(const BatchView& b, const Workspace& w, uint32_t* out_i
 template <typename Stream, typename Prof, typename Ev>
 inline void enqueue_encode(const BatchView& b, const VocabSet& vs, const UcTables& uc, const Workspace& w,
                            uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_counts,
-                           uint32_t long_grid, Stream stream, Stream aux, Stream aux2, Ev ev_fork, Ev ev_join, Ev ev_join2, Prof* prof,
+                           uint32_t long_grid, Stream stream, Stream aux, Ev ev_fork, Ev ev_join, Prof* prof,
                            const uint64_t* token_base = nullptr) {
     enqueue_split(b, vs, uc, w, stream, prof);
     CFBPE_FORK(stream, aux, ev_fork);
-    CFBPE_FORK(stream, aux2, ev_fork);
-    enqueue_long_big(b, vs, w, long_grid, aux, prof);        // the longest chain: first, on the first aux stream
-    enqueue_long(b, vs, w, long_grid, aux2, prof);
+    enqueue_long(b, vs, w, long_grid, aux, prof);
     enqueue_short(b, vs, w, long_grid, stream, prof);
-    CFBPE_JOIN(stream, aux2, ev_join2);
     CFBPE_JOIN(stream, aux, ev_join);
     enqueue_back(b, w, out_ids, out_cap, out_offsets, out_counts, stream, prof, token_base);
 }

@@ -133,7 +133,7 @@ __attribute__((visibility("default"))) int sim_encode_batch(void* const* vocabs,
     Workspace w{piece_bits.data(), tok_bits.data(), ids.data(), LongScratch{rk.data(), nx.data(), pv.data()},
                 ll.data(), static_cast<uint32_t>(ll.size()), tile_counts.data(), tile_base.data(), &st, ml, fix.data(), static_cast<uint32_t>(fix.size())};
     int* prof = nullptr;
-    enqueue_encode(b, vs, uc_tables(), w, out_ids, out_cap, out_offsets, out_counts, 4u, 0, 0, 0, 0, 0, 0, prof);
+    enqueue_encode(b, vs, uc_tables(), w, out_ids, out_cap, out_offsets, out_counts, 4u, 0, 0, 0, 0, prof);
     if (n_long_out) *n_long_out = static_cast<uint64_t>(st.n_long) + st.n_big;
     if (st.bad_utf8) return CFBPE_EILSEQ;
     if (st.long_overflow || st.miss_overflow) return CFBPE_EIO;
