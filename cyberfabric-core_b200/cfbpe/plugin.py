@@ -342,6 +342,44 @@ class LlmGatewayTokenizerService:
         counts = self._plugin().count_tokens(ctx, CountTokensRequest(VocabRef(model), data, offs))
         return Usage(int(counts.sum()))
 
+    def encode_with_special(self, ctx: SecurityContext, model: str, texts: Sequence[str], special_tokens: dict,
+                            allowed_special="all", disallowed_special="all") -> List[np.ndarray]:
+        """tiktoken's `Encoding.encode(text, allowed_special=..., disallowed_special=...)`:
+        the text is cut at every occurrence of an allowed special token (leftmost first), the stretches between them go
+        through encode_ordinary -- all stretches of all texts in ONE plugin batch -- and the special ids are put back in.
+        special_tokens: {"<|endoftext|>": 100257, ...}; allowed / disallowed: "all" or a set of token strings; a text
+        that holds a disallowed special token raises InvalidInput (tiktoken raises ValueError)."""
+        import re
+        allowed = set(special_tokens) if allowed_special == "all" else set(allowed_special)
+        disallowed = (set(special_tokens) - allowed) if disallowed_special == "all" else set(disallowed_special)
+        unknown = allowed - set(special_tokens)
+        if unknown:
+            raise InvalidInput("allowed special tokens without an id: %s" % sorted(unknown))
+        if disallowed:
+            bad = re.compile("|".join(re.escape(t) for t in sorted(disallowed, key=len, reverse=True)))
+            for t in texts:
+                m = bad.search(t)
+                if m:
+                    raise InvalidInput("the text holds the special token %r, which is not allowed here" % m.group())
+        cut = re.compile("|".join(re.escape(t) for t in sorted(allowed, key=len, reverse=True))) if allowed else None
+        plan, stretches = [], []          # per text: list of ("s", stretch index) | ("t", special id)
+        for t in texts:
+            steps, pos = [], 0
+            for m in (cut.finditer(t) if cut else ()):
+                if m.start() > pos:
+                    steps.append(("s", len(stretches))); stretches.append(t[pos:m.start()])
+                steps.append(("t", int(special_tokens[m.group()])))
+                pos = m.end()
+            if pos < len(t):
+                steps.append(("s", len(stretches))); stretches.append(t[pos:])
+            plan.append(steps)
+        enc = self.encode(ctx, model, stretches) if stretches else []
+        out = []
+        for steps in plan:
+            parts = [enc[i] if kind == "s" else np.array([i], dtype=np.uint32) for kind, i in steps]
+            out.append(np.concatenate(parts).astype(np.uint32) if parts else np.zeros(0, dtype=np.uint32))
+        return out
+
     def check_budget(self, ctx: SecurityContext, model: str, messages: Sequence[dict], remaining_tokens: int) -> bool:
         """pre-call estimate used by check_budget (modules/llm-gateway/docs/DESIGN.md:833-855)"""
         return self.count_tokens(ctx, model, messages).input_tokens <= remaining_tokens

@@ -142,3 +142,47 @@ def test_micro_batcher_coalesces_concurrent_calls_and_isolates_failures():
         assert False
     except P.ServiceUnavailable:
         pass
+
+
+def test_encode_with_special_tokens_matches_tiktoken():
+    """tiktoken's encode(text, allowed_special=...) = cut at the special tokens, encode_ordinary in
+    between.  The gateway service does the cutting and one batched plugin call; here the plugin is the CPU oracle (test
+    infrastructure) and the expected ids come from tiktoken itself, built on the committed Tekken ranks."""
+    tiktoken = pytest.importorskip("tiktoken")
+    import base64
+    import numpy as np
+    from cfbpe import plugin as P
+    from oracle import oracle, patterns
+    from conftest import TEKKEN_PATH
+    raw = open(TEKKEN_PATH, "rb").read()
+    ranks = {}
+    for line in raw.splitlines():
+        tok, r = line.split()
+        if int(r) < 100256:
+            ranks[base64.b64decode(tok)] = int(r)
+    specials = {"<|endoftext|>": 100257, "<|fim_prefix|>": 100258, "<|endofprompt|>": 100276}
+    enc = tiktoken.Encoding("standin", pat_str=patterns.PATTERNS[0], mergeable_ranks=ranks, special_tokens=specials)
+    ov = oracle.OracleVocab(raw, max_ranks=100256) if "max_ranks" in oracle.OracleVocab.__init__.__code__.co_varnames else None
+
+    class OraclePlugin(P.TokenizerPluginClient):
+        def encode_batch(self, ctx, req):
+            ids, offs, counts = oracle.encode_batch([ov], [0], req.bytes, req.offsets, nthreads=2)
+            return P.EncodeBatchResponse(ids, offs, counts)
+
+    if ov is None:
+        pytest.skip("oracle wrapper without max_ranks")
+    hub = P.ClientHub()
+    inst = P.PluginInstance("gts.x.core.modkit.plugin.v1~x.llmgw.tokenizer.plugin.v1~test.oracle.v1", "cyberfabric", 10)
+    hub.register_scoped(P.TokenizerPluginClient, inst.id, OraclePlugin())
+    svc = P.LlmGatewayTokenizerService(hub, [inst], vendor="cyberfabric")
+    ctx = P.SecurityContext.anonymous()
+    texts = ["hello <|endoftext|> world<|endoftext|>", "<|fim_prefix|>", "", "no specials here", "a<|endofprompt|><|endoftext|>b  ", "<|endoftext|><|endoftext|>x"]
+    got = svc.encode_with_special(ctx, "cl100k_base", texts, specials)
+    for t, g in zip(texts, got):
+        assert g.tolist() == enc.encode(t, allowed_special="all"), t
+    got = svc.encode_with_special(ctx, "cl100k_base", ["x <|endoftext|> y"], specials, allowed_special={"<|endoftext|>"}, disallowed_special=())
+    assert got[0].tolist() == enc.encode("x <|endoftext|> y", allowed_special={"<|endoftext|>"}, disallowed_special=())
+    got = svc.encode_with_special(ctx, "cl100k_base", ["x <|endoftext|> y"], specials, allowed_special=(), disallowed_special=())
+    assert got[0].tolist() == enc.encode("x <|endoftext|> y", allowed_special=set(), disallowed_special=())
+    with pytest.raises(P.InvalidInput):
+        svc.encode_with_special(ctx, "cl100k_base", ["x <|endoftext|> y"], specials, allowed_special=())
