@@ -48,6 +48,10 @@ inline uint64_t miss_list_words(uint64_t max_bytes, uint32_t c, uint32_t max_chu
 #define CFBPE_LONG_CTAS 8
 #endif
 constexpr uint32_t kLongCtasPerSm = CFBPE_LONG_CTAS;
+#ifndef CFBPE_LIST_CTAS
+#define CFBPE_LIST_CTAS 2
+#endif
+constexpr uint32_t kListCtasPerSm = CFBPE_LIST_CTAS;   // K2c CTAs (64 KB of shared memory each) per SM
 
 enum KernelIdx { K_SPLIT = 0, K_ENCODE = 1, K_LONG = 2, K_COUNT = 3, K_SCAN = 4, K_EMIT = 5, K_LIST = 6, K_LONGSCAN = 7, K_MERGE = 8 };
 
@@ -113,7 +117,7 @@ inline void enqueue_long(const BatchView& b, const VocabSet& vs, const Workspace
     CFBPE_MARK(prof, K_LIST, stream, true);
     // the list phase of the big pieces K2b deferred: two 64 KB CTAs per SM (long_grid = 4 x SM count), so that the short-piece
     // kernels on the other stream keep ~100 KB of shared memory per SM
-    CFBPE_LAUNCH_SMEM(bpe_list_kernel, long_grid / 2, kListWarps * 32, kListSmemBytes, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
+    CFBPE_LAUNCH_SMEM(bpe_list_kernel, (long_grid / 4) * kListCtasPerSm, kListWarps * 32, kListSmemBytes, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
     CFBPE_MARK(prof, K_LIST, stream, false);
 #endif
 }
