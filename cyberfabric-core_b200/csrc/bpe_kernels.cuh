@@ -485,7 +485,7 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
     const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const uint64_t warp = static_cast<uint64_t>(blockIdx.x) * kPieceWarps + wic;
     const uint64_t r0 = warp * kPieceRange;
-    if (r0 >= b.total_bytes) return;   // whole warp exits together
+    if (kMode != 1 && r0 >= b.total_bytes) return;   // whole warp exits together (mode 1 has CTA barriers below: everybody stays)
     const uint64_t r1 = (r0 + kPieceRange < b.total_bytes) ? r0 + kPieceRange : b.total_bytes;
     const uint8_t* __restrict__ text = b.bytes;
     const bool multi = b.vocab_ids != nullptr;
@@ -503,6 +503,40 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
     uint64_t beyond = b.total_bytes;
     if (any_open) beyond = next_set_bit(piece_bits, r1, b.total_bytes);
     const uint64_t nf = (nf_rel == 0xFFFFu) ? beyond : r0 + nf_rel;
+
+    if (kMode == 1) {
+        // the only piece of my 16 bytes that can be longer than 32 is the LAST one that starts there (the others end inside
+        // them).  The counters are bumped once per CTA, not once per piece: with half a million long pieces (CJK text) the
+        // kernel was bound by atomics on three addresses (1.0 ms; 0.24 ms on the bench mix).
+        __shared__ uint32_t s_n[2], s_at[2];
+        __shared__ unsigned long long s_bytes;
+        if (threadIdx.x < 2) s_n[threadIdx.x] = 0;
+        if (threadIdx.x == 0) s_bytes = 0;
+        __syncthreads();
+        bool is_long = false, big = false;
+        uint32_t k = 0, pv = 0;
+        uint64_t pos = 0;
+        if (my && r0 < b.total_bytes) {
+            pos = base + (31u - static_cast<uint32_t>(__clz(my)));
+            if (nf - pos > 32) {
+                is_long = true;
+                big = (nf - pos) > kBigPiece;
+                pv = multi ? b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)] : 0u;
+                k = atomicAdd(&s_n[big ? 1 : 0], 1u);
+                atomicAdd(&s_bytes, static_cast<unsigned long long>(nf - pos));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 && s_n[threadIdx.x]) s_at[threadIdx.x] = atomicAdd(threadIdx.x ? &status->n_big : &status->n_long, s_n[threadIdx.x]);
+        if (threadIdx.x == 2 && s_bytes) atomicAdd(&status->long_bytes, s_bytes);
+        __syncthreads();
+        if (is_long) {
+            const uint32_t idx = s_at[big ? 1 : 0] + k;
+            if (idx < long_cap) { LongPiece lp; lp.start = pos; lp.end = nf; lp.vocab = pv; lp.pad = 0; long_list[big ? long_cap - 1 - idx : idx] = lp; }
+            else atomicOr(&status->long_overflow, 1u);
+        }
+        return;
+    }
 
     // ---- vocabulary of my pieces (multi-tenant batches: one prompt lookup per lane, then walk)
     uint32_t pidx = 0, vid = 0;
