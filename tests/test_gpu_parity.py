@@ -123,6 +123,9 @@ def test_full_size_config3_properties(plug, ctx, tekken_bytes):
         ids = r.ids[int(r.offsets[i]):int(r.offsets[i + 1])]
         dec = b"".join(toks[t] for t in ids)
         assert dec == bytes(data[int(offs[i]):int(offs[i + 1])])
+    # ... and the whole batch through the device decode path: byte for byte the input, same prompt boundaries
+    dec = plug.decode_batch(ctx, P.DecodeBatchRequest(P.VocabRef("cl100k_base"), r.ids, r.offsets))
+    assert np.array_equal(dec.offsets, offs) and np.array_equal(dec.bytes, data)
     ov = oracle.OracleVocab(rv.file_bytes, rv.max_ranks)
     sel = rng.integers(0, n, size=2000)
     for i in sel:
