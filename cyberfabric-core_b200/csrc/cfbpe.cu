@@ -47,7 +47,7 @@ constexpr int kSideStreams = 16;
 #define CFBPE_FRONT_STREAMS 6
 #endif
 constexpr int kFrontStreams = CFBPE_FRONT_STREAMS;
-constexpr uint64_t kPipeChunkBytes = 12ull << 20;   // middle sub-batches of a pipelined host call (the first and last are a third of this); measured: profiles/e2e_subbatch_sizes_r01r.jsonl
+constexpr uint64_t kPipeChunkBytes = 12ull << 20;   // largest sub-batch of a pipelined host call (the sizes ramp up to it and down again); measured: profiles/e2e_subbatch_sizes_r01t.jsonl
 constexpr uint64_t kPipeMinBytes = 16ull << 20;     // smaller calls run as one shot
 
 struct VocabSlot {
