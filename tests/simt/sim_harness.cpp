@@ -141,4 +141,27 @@ __attribute__((visibility("default"))) int sim_encode_batch(void* const* vocabs,
     return 0;
 }
 
+// the decode path (ids -> bytes) on host memory; returns the number of decoded bytes in out_offsets[n_seqs]
+__attribute__((visibility("default"))) int sim_decode_batch(void* const* vocabs, uint32_t n_vocabs, uint32_t n_seqs, const uint32_t* ids,
+                                                            const uint64_t* id_offsets, const uint8_t* vocab_ids, uint8_t* out, uint64_t out_cap,
+                                                            uint64_t* out_offsets) {
+    VocabSet vs{};
+    for (uint32_t i = 0; i < n_vocabs && i < kMaxVocabs; ++i) {
+        SimVocab* v = static_cast<SimVocab*>(vocabs[i]);
+        vs.v[i] = make_view(v->blob.data(), v->hdr);
+    }
+    const uint64_t n_ids = id_offsets[n_seqs];
+    DecodeView d{ids, id_offsets, vocab_ids, n_seqs, n_ids};
+    const uint32_t n_tiles = static_cast<uint32_t>((n_ids + kDecodeTile - 1) / kDecodeTile);
+    std::vector<uint32_t> lens(n_ids + 1), sums(n_tiles + 1);
+    std::vector<uint64_t> base(n_tiles + 1);
+    DeviceStatus st{};
+    if (n_tiles) cusim::launch(n_tiles, 256, [&] { decode_len_kernel(d, vs, lens.data(), sums.data(), &st); });
+    cusim::launch(1u, n_tiles ? 1024u : 32u, [&] { tile_scan_kernel(sums.data(), n_tiles, base.data(), &st, nullptr); });
+    if (st.bad_utf8) return CFBPE_EINVAL;
+    if (n_tiles) cusim::launch(n_tiles, 256, [&] { decode_copy_kernel(d, vs, lens.data(), base.data(), out, out_cap); });
+    cusim::launch(static_cast<unsigned>((static_cast<uint64_t>(n_seqs) + 1 + 255) / 256), 256, [&] { decode_offsets_kernel(d, lens.data(), base.data(), out_offsets, &st); });
+    return st.tok_end > out_cap ? CFBPE_ENOSPC : 0;
+}
+
 }  // extern "C"

@@ -28,6 +28,8 @@ def lib():
         L.sim_encode_batch.restype = C.c_int
         L.sim_encode_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sim_decode_batch.restype = C.c_int
+        L.sim_decode_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.sim_split_fixups.restype = C.c_ulonglong
         L.sim_split_fixups.argtypes = [C.c_int]
         L.sim_dbg_counter.restype = C.c_ulonglong
@@ -114,3 +116,18 @@ def encode_batch(vocabs, prompts, vocab_ids=None, out_cap=None):
                                 None if vid is None else vid.ctypes.data, ids.ctypes.data, cap,
                                 out_off.ctypes.data, counts.ctypes.data, C.byref(nlong))
     return rc, ids, out_off, counts[:len(prompts)], nlong.value
+
+
+def decode_batch(vocabs, ids, id_offsets, vocab_ids=None, out_cap=None):
+    """the decode kernels on the emulator: (rc, bytes uint8, byte offsets uint64 n+1)"""
+    ids = np.ascontiguousarray(ids, dtype=np.uint32)
+    id_offsets = np.ascontiguousarray(id_offsets, dtype=np.uint64)
+    n = len(id_offsets) - 1
+    cap = int(out_cap) if out_cap is not None else int(len(ids)) * 260 + 64
+    out = np.zeros(max(cap, 1), dtype=np.uint8)
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    vh = (C.c_void_p * len(vocabs))(*[v._h for v in vocabs])
+    vid = None if vocab_ids is None else np.ascontiguousarray(vocab_ids, dtype=np.uint8)
+    rc = lib().sim_decode_batch(vh, len(vocabs), n, ids.ctypes.data, id_offsets.ctypes.data,
+                                None if vid is None else vid.ctypes.data, out.ctypes.data, cap, out_off.ctypes.data)
+    return rc, out[:int(out_off[n])] if rc == 0 else out[:0], out_off

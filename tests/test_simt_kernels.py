@@ -229,3 +229,22 @@ def test_split_cased_runs(pat):
     bad = [(p, e) for p, e in zip(strs, ends) if oracle.split(pat, p).tolist() != e]
     assert not bad, bad[:3]
     assert simlib.split_fixups() > 50      # threads that started in S_W_U, met an upper-case letter and were finished by the fixup kernel
+
+
+def test_decode_kernels_invert_encode(sim_vocabs):
+    """the decode kernels (ids -> bytes) on the emulator: the inverse of the encode path on fuzz prompts, two vocabularies in one
+    batch, empty sequences, more ids than one scan tile; an id outside the vocabulary and a short buffer are reported"""
+    prompts = [s.encode() for s in fuzzgen.fuzz_strings(321, 400)] + [b"", b"x", ("word " * 900).encode(), b""]
+    vids = np.array([i % 2 for i in range(len(prompts))], dtype=np.uint8)
+    rc, ids, off, counts, _ = simlib.encode_batch([sim_vocabs[0], sim_vocabs[1]], prompts, vocab_ids=vids)
+    assert rc == 0
+    n_ids = int(off[len(prompts)])
+    rc, out, boff = simlib.decode_batch([sim_vocabs[0], sim_vocabs[1]], ids[:n_ids], off, vocab_ids=vids)
+    assert rc == 0
+    data = b"".join(prompts)
+    assert bytes(out) == data
+    assert boff.tolist() == [0] + list(np.cumsum([len(p) for p in prompts]))
+    rc, _, _ = simlib.decode_batch([sim_vocabs[0]], np.array([1, 2, 5_000_000], dtype=np.uint32), np.array([0, 3], dtype=np.uint64))
+    assert rc != 0
+    rc, _, need = simlib.decode_batch([sim_vocabs[0], sim_vocabs[1]], ids[:n_ids], off, vocab_ids=vids, out_cap=10)
+    assert rc != 0 and int(need[len(prompts)]) == len(data)
