@@ -25,6 +25,7 @@ static inline void prof_mark(ProfEvents* p, int idx, cudaStream_t s, bool begin)
 #define CFBPE_JOIN(main, aux, ev) do { if ((main) != (aux)) { cudaEventRecord((ev), (aux)); cudaStreamWaitEvent((main), (ev), 0); } } while (0)
 
 #include "pipeline.cuh"
+#include "subbatch.h"
 #include "unicode_tables.h"
 #include "vocab.h"
 
@@ -190,43 +191,7 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
                        uint64_t total) {
     // ---- cut
     uint32_t cut[kMaxPipeChunks + 1];
-    int nc = 0;
-    {
-        // sub-batch sizes ramp up from a small first one (the kernels start early) to pipe_chunk (big sub-batches keep the
-        // kernels efficient) and down again to a small last one (little left to download when the kernels end):
-        //   edge, 2 edge, 4 edge, ... pipe_chunk ... pipe_chunk, ..., 4 edge, 2 edge, edge      with edge = pipe_chunk / 8
-        uint64_t chunk = ctx->pipe_chunk;
-        if ((total + chunk - 1) / chunk + 8 > static_cast<uint64_t>(kMaxPipeChunks)) chunk = (total + kMaxPipeChunks - 9) / (kMaxPipeChunks - 8);
-        uint64_t sizes[kMaxPipeChunks];
-        int ns = 0;
-        {
-            uint64_t ramp[8]; int nr = 0;
-            for (uint64_t e = chunk / 8 ? chunk / 8 : 1; e < chunk && nr < 3; e *= 2) ramp[nr++] = e;
-            uint64_t ramps = 0;
-            for (int i = 0; i < nr; ++i) ramps += 2 * ramp[i];
-            while (nr && ramps > total) { ramps -= 2 * ramp[nr - 1]; --nr; }
-            const uint64_t middle = total - ramps;
-            const uint64_t n_mid = (middle + chunk - 1) / chunk;
-            for (int i = 0; i < nr; ++i) sizes[ns++] = ramp[i];
-            for (uint64_t i = 0; i < n_mid; ++i) sizes[ns++] = (middle + n_mid - 1) / n_mid;
-            for (int i = nr - 1; i >= 0; --i) sizes[ns++] = ramp[i];
-            if (!ns) sizes[ns++] = total ? total : 1;
-        }
-        cut[0] = 0;
-        uint32_t p = 0;
-        uint64_t target = 0;
-        for (int k = 0; k < ns && p < n; ++k) {
-            target += sizes[k];
-            if (k == ns - 1 || target > total) target = total;
-            if (offsets[p] >= target && k < ns - 1) continue;      // a long prompt already covered this slot
-            uint32_t lo = p + 1, hi = n;                 // first q > p with offsets[q] >= target (or n)
-            while (lo < hi) { const uint32_t m2 = lo + (hi - lo) / 2; if (offsets[m2] >= target) hi = m2; else lo = m2 + 1; }
-            p = lo;
-            if (nc + 1 == kMaxPipeChunks) p = n;
-            cut[++nc] = p;
-        }
-        if (p < n) { if (nc && nc == kMaxPipeChunks) cut[nc] = n; else cut[++nc] = n; }
-    }
+    const int nc = plan_sub_batches(offsets, n, total, ctx->pipe_chunk, kMaxPipeChunks, cut);
     cudaStream_t cs = ctx->stream, hs = ctx->h2d_stream, ds = ctx->d2h_stream;
     // local offsets of every sub-batch, staged in pinned memory (sub-batch k occupies [p_k + k, p_{k+1} + k])
     for (int k = 0; k < nc; ++k) {

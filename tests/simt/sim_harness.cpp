@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../cyberfabric-core_b200/csrc/pipeline.cuh"
+#include "../../cyberfabric-core_b200/csrc/subbatch.h"
 #include "../../cyberfabric-core_b200/csrc/unicode_tables.h"
 #include "../../cyberfabric-core_b200/csrc/vocab.h"
 #include "../../include/cfbpe.h"
@@ -139,6 +140,11 @@ __attribute__((visibility("default"))) int sim_encode_batch(void* const* vocabs,
     if (st.long_overflow || st.miss_overflow) return CFBPE_EIO;
     if (out_ids && st.n_tokens > out_cap) return CFBPE_ENOSPC;
     return 0;
+}
+
+// the sub-batch plan of a pipelined host call (host code of the product, csrc/subbatch.h)
+__attribute__((visibility("default"))) int sim_plan_sub_batches(const uint64_t* offsets, uint32_t n, uint64_t chunk, int max_chunks, uint32_t* cut) {
+    return plan_sub_batches(offsets, n, offsets[n], chunk, max_chunks, cut);
 }
 
 // the decode path (ids -> bytes) on host memory; returns the number of decoded bytes in out_offsets[n_seqs]

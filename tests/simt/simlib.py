@@ -30,6 +30,8 @@ def lib():
                                        C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sim_decode_batch.restype = C.c_int
         L.sim_decode_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.sim_plan_sub_batches.restype = C.c_int
+        L.sim_plan_sub_batches.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]
         L.sim_split_fixups.restype = C.c_ulonglong
         L.sim_split_fixups.argtypes = [C.c_int]
         L.sim_dbg_counter.restype = C.c_ulonglong
@@ -131,3 +133,11 @@ def decode_batch(vocabs, ids, id_offsets, vocab_ids=None, out_cap=None):
     rc = lib().sim_decode_batch(vh, len(vocabs), n, ids.ctypes.data, id_offsets.ctypes.data,
                                 None if vid is None else vid.ctypes.data, out.ctypes.data, cap, out_off.ctypes.data)
     return rc, out[:int(out_off[n])] if rc == 0 else out[:0], out_off
+
+
+def plan_sub_batches(offsets, chunk, max_chunks=64):
+    """csrc/subbatch.h:plan_sub_batches -> list of prompt indices cut[0..nc]"""
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    cut = np.zeros(max_chunks + 1, dtype=np.uint32)
+    nc = lib().sim_plan_sub_batches(offsets.ctypes.data, len(offsets) - 1, int(chunk), max_chunks, cut.ctypes.data)
+    return cut[:nc + 1].tolist()

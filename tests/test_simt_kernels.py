@@ -248,3 +248,27 @@ def test_decode_kernels_invert_encode(sim_vocabs):
     assert rc != 0
     rc, _, need = simlib.decode_batch([sim_vocabs[0], sim_vocabs[1]], ids[:n_ids], off, vocab_ids=vids, out_cap=10)
     assert rc != 0 and int(need[len(prompts)]) == len(data)
+
+
+def test_sub_batch_plan_covers_every_prompt_once():
+    """csrc/subbatch.h (host code of the pipelined call): whole prompts, in order, none lost, none empty, at most max_chunks
+    sub-batches, sizes ramping up to `chunk` and down again; long prompts, empty prompts, tiny and huge batches"""
+    import random
+    rng = random.Random(9)
+    for trial in range(300):
+        n = rng.choice([1, 2, 3, 17, 500, 5000])
+        kind = rng.randint(0, 3)
+        lens = [rng.choice([0, 1, 7, 4096]) if kind == 0 else rng.randint(0, 4096) if kind == 1 else rng.randint(0, 40) if kind == 2
+                else rng.choice([0, 0, 3, 300000]) for _ in range(n)]
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        chunk = rng.choice([1, 64, 1000, 12 << 10, 12 << 20])
+        mc = rng.choice([9, 10, 16, 64])
+        cut = simlib.plan_sub_batches(offs, chunk, mc)
+        assert cut[0] == 0 and cut[-1] == n and len(cut) - 1 <= mc, (trial, cut[:5], n)
+        assert all(a < b for a, b in zip(cut[:-1], cut[1:])), (trial, cut[:8])
+    # the shape on the bench batch: 65 536 prompts of 8..4096 bytes, 12 MiB sub-batches
+    lens = np.random.default_rng(3).integers(8, 4097, size=65536)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    cut = simlib.plan_sub_batches(offs, 12 << 20)
+    sizes = [int(offs[b] - offs[a]) for a, b in zip(cut[:-1], cut[1:])]
+    assert sizes[0] < 2 << 20 and sizes[-1] < 2 << 20 and max(sizes) < 13 << 20 and sizes[0] < sizes[1] < sizes[2] < sizes[3]
