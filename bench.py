@@ -39,6 +39,14 @@ WORKLOAD = "BASELINE.json configs[2]: 65536 prompts/GPU, lengths uniform 8-4096 
            "5% digits/whitespace, 5% adversarial), cl100k pattern"
 
 
+def workload_config(rv, n_prompts, total_bytes, seed, scale):
+    """what names the workload -- identical in the CUDA arm and the reference arm (the driver compares the two dicts);
+    measured properties of the batch (tokens, long pieces ...) are reported under `workload_stats` instead"""
+    return {"workload": WORKLOAD, "vocab": rv.label, "vocab_stand_in": rv.stand_in, "prompts_per_gpu": int(n_prompts),
+            "total_bytes_per_gpu": int(total_bytes), "seed": int(seed), "scale": float(scale),
+            "l2": "inputs (%.0f MB) and per-byte work arrays (> 1 GB) exceed the 126 MB L2; no flush needed" % (total_bytes / 1e6)}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -122,7 +130,7 @@ def run_reference(args):
     from cfbpe import vocabs as V
     from cfbpe import workload as W
     data, offs, vid, meta = W.make_config(CONFIG_ID, 1.0)
-    rv = V.resolve("cl100k_base")
+    rv = V.resolve("cl100k_base", allow_stand_in=True)
     threads = os.cpu_count() or 1
     per_step = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
     for _ in range(args.warmup):
@@ -136,7 +144,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "vocab": rv.label, "total_bytes_per_gpu": meta["total_bytes"], "seed": 3},
+            "config": workload_config(rv, len(offs) - 1, meta["total_bytes"], W.CONFIGS[CONFIG_ID]["seed"], 1.0),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "each step: " + sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -190,7 +198,7 @@ def main():
     # ---- init: one rank parses the rank file, NCCL broadcasts the packed tables
     def factory(blobs):
         return P.GpuBpeTokenizerPlugin(device=local_rank, vocab_names=("cl100k_base",), max_batch_bytes=160 << 20,
-                                       max_prompts=1 << 17, import_blobs=blobs)
+                                       max_prompts=1 << 17, import_blobs=blobs, allow_stand_in=True)
     plug = D.load_vocab_everywhere(factory, ["cl100k_base"], 0, dev) if world > 1 else factory(None)
     rv = plug.resolved["cl100k_base"]
     ctx = P.SecurityContext.anonymous()
@@ -298,6 +306,21 @@ def main():
     e2e_value = total_all * args.steps / (e2e_ms * 1e-3)
     assert int(r.offsets[n]) == n_tokens
     clocks = sampler.stop() if rank == 0 else None
+    # ---- parity of what was just timed, on EVERY rank (ranks != 0 run on NCCL-broadcast tables): each rank hashes its id stream and
+    #      hands rank 0 a seeded sample of its prompts with the ids the e2e leg produced and the ids the device leg left in HBM;
+    #      rank 0 encodes the samples with the oracle (checker only, outside the timed regions) and compares
+    import hashlib
+    dev_ids = d_ids[:n_tokens].cpu().numpy().view(np.uint32)
+    dev_off = d_out_off.cpu().numpy().astype(np.uint64)
+    same_legs = bool(np.array_equal(dev_ids, r.ids[:n_tokens]) and np.array_equal(dev_off, r.offsets))
+    pick = np.sort(np.random.default_rng(1000 + rank).choice(n, size=min(n, 512), replace=False))
+    mine = {"rank": rank, "ids_sha256": hashlib.sha256(dev_ids.tobytes()).hexdigest()[:16], "n_tokens": n_tokens, "same_legs": same_legs,
+            "prompts": [bytes(data[int(offs[i]):int(offs[i + 1])]) for i in pick],
+            "ids": [dev_ids[int(dev_off[i]):int(dev_off[i + 1])].copy() for i in pick]}
+    gathered = [mine]
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(mine, gathered, dst=0)
     h2d = total + (n + 1) * 8
     d2h = n_tokens * 4 + (n + 1) * 8 + n * 4 + 24
 
@@ -305,6 +328,21 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return 0
+
+    from oracle import oracle
+    ov = oracle.OracleVocab(rv.file_bytes, rv.max_ranks)
+    ok_ranks, bad = 0, []
+    for g in gathered:
+        good = g["same_legs"] and all(np.array_equal(ov.encode(rv.pattern_id, p), i) for p, i in zip(g["prompts"], g["ids"]))
+        ok_ranks += 1 if good else 0
+        if not good:
+            bad.append(g["rank"])
+    parity = {"parity_checked_ranks": ok_ranks, "ranks": world, "prompts_per_rank": len(gathered[0]["prompts"]),
+              "checker": "oracle port, per-prompt ids; device leg == e2e leg on every rank", "mismatching_ranks": bad,
+              "ids_sha256_per_rank": [g["ids_sha256"] for g in gathered]}
+    if bad:
+        sys.stderr.write("bench.py: PARITY FAILURE on ranks %s\n" % bad)
+        return 3
 
     # ---- roofline of the dominant kernel
     hbm_gbs, peak_src = peaks()
@@ -323,11 +361,16 @@ def main():
     }
     dom = max(kms, key=lambda k: kms[k])
     achieved = alg[dom] / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0
-    traffic = None
+    # dram bytes of that kernel from the committed `ncu --set full` capture -- only if the capture is of THIS build of the kernels
+    traffic, traffic_note = None, "no ncu capture committed for this build"
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dom)
+            tj = json.load(open(tpath))
+            if tj.get("build_id") == N.load().cfbpe_build_id().decode():
+                traffic, traffic_note = tj.get(dom), "profiles/ncu_traffic.json (build %s)" % tj.get("build_id")
+            else:
+                traffic_note = "profiles/ncu_traffic.json is of build %s, this is %s: stale, not reported" % (tj.get("build_id"), N.load().cfbpe_build_id().decode())
         except Exception:
             traffic = None
     path_alg = total + 4 * n_tokens + 21 * n
@@ -343,16 +386,17 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "vocab": rv.label, "vocab_stand_in": rv.stand_in, "prompts_per_gpu": n,
-                   "total_bytes_per_gpu": total, "tokens_per_gpu": n_tokens, "bytes_per_token": total / max(n_tokens, 1),
-                   "long_pieces_per_gpu": int(n_long), "long_piece_bytes_per_gpu": int(long_bytes), "short_miss_pieces_per_gpu": int(n_miss), "list_pieces_per_gpu": int(n_list), "list_parts_per_gpu": int(list_parts), "seed": cfg["seed"], "parallelism": "dp%d (batch-sharded, no data-path collective)" % world,
-                   "l2": "inputs (%.0f MB) and per-byte work arrays (> 1 GB) exceed the 126 MB L2; no flush needed" % (total / 1e6),
-                   "scale": args.scale},
+        "config": workload_config(rv, n, total, cfg["seed"], args.scale),
+        "parallelism": "dp%d (batch-sharded, no data-path collective; rank r encodes the batch of seed %d + r)" % (world, cfg["seed"]),
+        "workload_stats": {"tokens_per_gpu": n_tokens, "bytes_per_token": total / max(n_tokens, 1), "long_pieces_per_gpu": int(n_long),
+                           "long_piece_bytes_per_gpu": int(long_bytes), "short_miss_pieces_per_gpu": int(n_miss),
+                           "list_pieces_per_gpu": int(n_list), "list_parts_per_gpu": int(list_parts)},
+        "parity": parity,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": 11 * args.steps,   # split, split fix-up, long-piece scan, piece lookup, short-piece merges, long pieces, long-piece lists, flag_count, tile_scan, emit, offsets
         "kernel_ms": kms,   # CUDA-event durations; bpe_long runs on a second stream next to bpe_encode, so they overlap
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
+                     "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
                      "path_algorithmic_bytes": path_alg,
                      "path_achieved_gbs": path_alg / (kernels_ms * 1e-3) / 1e9 if kernels_ms > 0 else 0.0},
         "cpu_baseline": cpu,

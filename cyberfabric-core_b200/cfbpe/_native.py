@@ -185,10 +185,27 @@ class Context:
         self._check(load().cfbpe_vocab_import(self._h, vocab_id, blob.ctypes.data, blob.size))
 
     # ---- host-buffer API
+    @staticmethod
+    def _check_inputs(data, offsets, vocab_ids, what="bytes", dtype=np.uint8):
+        """The C ABI takes pointers without lengths: what it cannot check is checked here (the Rust binding does the same on
+        its slices) -- dtypes, contiguity, offsets[n] inside the buffer, one vocab id per prompt."""
+        def bad(msg):
+            return NativeError(EINVAL, msg)
+        if not isinstance(offsets, np.ndarray) or offsets.dtype != np.uint64 or offsets.ndim != 1 or len(offsets) < 1 or not offsets.flags.c_contiguous:
+            raise bad("offsets must be a C-contiguous uint64 array of n+1 entries")
+        if not isinstance(data, np.ndarray) or data.dtype != dtype or data.ndim != 1 or not data.flags.c_contiguous:
+            raise bad("%s must be a C-contiguous 1-D %s array" % (what, np.dtype(dtype).name))
+        n = len(offsets) - 1
+        if int(offsets[n]) > data.size:
+            raise bad("offsets[n] = %d exceeds len(%s) = %d" % (int(offsets[n]), what, data.size))
+        if vocab_ids is not None:
+            if not isinstance(vocab_ids, np.ndarray) or vocab_ids.dtype != np.uint8 or vocab_ids.ndim != 1 or len(vocab_ids) < n or not vocab_ids.flags.c_contiguous:
+                raise bad("vocab_ids must be a C-contiguous uint8 array with one entry per prompt")
+        return n
+
     def encode_batch(self, data: np.ndarray, offsets: np.ndarray, vocab_ids=None, out_ids=None, out_offsets=None,
                      out_counts=None):
-        n = len(offsets) - 1
-        assert data.dtype == np.uint8 and offsets.dtype == np.uint64
+        n = self._check_inputs(data, offsets, vocab_ids)
         total = int(offsets[n])
         if out_ids is None:
             out_ids = np.empty(max(total, 1), dtype=np.uint32)
@@ -196,10 +213,7 @@ class Context:
             out_offsets = np.empty(n + 1, dtype=np.uint64)
         if out_counts is None:
             out_counts = np.empty(max(n, 1), dtype=np.uint32)
-        vid = None
-        if vocab_ids is not None:
-            assert vocab_ids.dtype == np.uint8 and len(vocab_ids) >= n
-            vid = vocab_ids.ctypes.data
+        vid = None if vocab_ids is None else vocab_ids.ctypes.data
         rc = load().cfbpe_encode_batch(self._h, n, data.ctypes.data if data.size else None, offsets.ctypes.data, vid,
                                        out_ids.ctypes.data, out_ids.size, out_offsets.ctypes.data,
                                        out_counts.ctypes.data)
@@ -207,7 +221,7 @@ class Context:
         return out_ids[:int(out_offsets[n])], out_offsets, out_counts[:n]
 
     def count_batch(self, data: np.ndarray, offsets: np.ndarray, vocab_ids=None, out_counts=None):
-        n = len(offsets) - 1
+        n = self._check_inputs(data, offsets, vocab_ids)
         if out_counts is None:
             out_counts = np.empty(max(n, 1), dtype=np.uint32)
         vid = None if vocab_ids is None else vocab_ids.ctypes.data
@@ -218,7 +232,7 @@ class Context:
     def decode_batch(self, ids: np.ndarray, id_offsets: np.ndarray, vocab_ids=None, out_cap=None, out_bytes=None, out_offsets=None):
         """ids (uint32, packed) + id_offsets (uint64, n+1) -> (bytes uint8, byte offsets uint64 n+1).
         out_bytes / out_offsets: caller's buffers (pinned ones make the download several times faster)"""
-        n = len(id_offsets) - 1
+        n = self._check_inputs(ids, id_offsets, vocab_ids, "ids", np.uint32)
         if out_offsets is None:
             out_offsets = np.zeros(n + 1, dtype=np.uint64)
         vid = None if vocab_ids is None else vocab_ids.ctypes.data

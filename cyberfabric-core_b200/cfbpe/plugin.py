@@ -204,7 +204,13 @@ class GpuBpeTokenizerPlugin(TokenizerPluginClient):
     VENDOR = "cyberfabric"
 
     def __init__(self, device: int = 0, vocab_names: Sequence[str] = ("cl100k_base",), max_batch_bytes: int = 0,
-                 max_prompts: int = 0, priority: int = 10, import_blobs: Optional[Dict[str, np.ndarray]] = None):
+                 max_prompts: int = 0, priority: int = 10, import_blobs: Optional[Dict[str, np.ndarray]] = None,
+                 allow_stand_in: bool = False):
+        """allow_stand_in: see cfbpe.vocabs.resolve -- benchmarks and tests only; a production plugin fails with VocabNotFound
+        when a real rank file is missing instead of counting tokens with another vocabulary"""
+        self.allow_stand_in = allow_stand_in
+        self.max_batch_bytes = int(max_batch_bytes) if max_batch_bytes else 256 << 20     # cfbpe_create's defaults
+        self.max_prompts = int(max_prompts) if max_prompts else 1 << 20
         try:
             self.ctx = N.Context(device, max_batch_bytes, max_prompts)
         except N.NativeError as e:
@@ -214,7 +220,7 @@ class GpuBpeTokenizerPlugin(TokenizerPluginClient):
         self._lock = threading.Lock()
         self.instance = PluginInstance(
             id=GTS_PLUGIN_SCHEMA + "cyberfabric.gpu_bpe.b200.v1", vendor=self.VENDOR, priority=priority,
-            properties={"device": device})
+            properties={"device": device, "vocabs": {}})
         for name in vocab_names:
             self.load_vocab(name, None if import_blobs is None else import_blobs.get(name))
 
@@ -226,7 +232,10 @@ class GpuBpeTokenizerPlugin(TokenizerPluginClient):
             slot = len(self._slot)
             if slot >= N.MAX_VOCABS:
                 raise InvalidInput("too many vocabularies loaded")
-            rv = V.resolve(name)
+            try:
+                rv = V.resolve(name, self.allow_stand_in)
+            except V.VocabUnavailable as e:
+                raise VocabNotFound(str(e)) from e
             try:
                 if blob is not None:
                     self.ctx.vocab_import(slot, blob)
@@ -236,6 +245,8 @@ class GpuBpeTokenizerPlugin(TokenizerPluginClient):
                 raise _map_native(e) from e
             self._slot[name] = slot
             self.resolved[name] = rv
+            # what a registry / operator sees about this instance: which file each vocabulary really is
+            self.instance.properties["vocabs"][name] = {"slot": slot, "label": rv.label, "stand_in": rv.stand_in, "sha256": rv.sha256}
             return slot
 
     def export_vocab(self, name: str) -> np.ndarray:
@@ -260,8 +271,15 @@ class GpuBpeTokenizerPlugin(TokenizerPluginClient):
 
     @staticmethod
     def _check_arrays(req):
-        if req.bytes.dtype != np.uint8 or req.offsets.dtype != np.uint64 or len(req.offsets) < 1:
+        """what the C ABI cannot check (it takes no buffer lengths): dtypes, contiguity, and that the last offset stays
+        inside the byte buffer -- otherwise the upload would read past the caller's array"""
+        b, o = req.bytes, req.offsets
+        if not isinstance(b, np.ndarray) or not isinstance(o, np.ndarray) or b.dtype != np.uint8 or o.dtype != np.uint64 or o.ndim != 1 or len(o) < 1:
             raise InvalidInput("bytes must be uint8 and offsets uint64 with n+1 entries")
+        if not b.flags.c_contiguous or not o.flags.c_contiguous or b.ndim != 1:
+            raise InvalidInput("bytes and offsets must be C-contiguous 1-D arrays")
+        if int(o[0]) != 0 or int(o[-1]) > b.size:
+            raise InvalidInput("offsets[0] must be 0 and offsets[n] (%d) must not exceed len(bytes) (%d)" % (int(o[-1]), b.size))
 
     # -- TokenizerPluginClient
     def encode_batch(self, ctx: SecurityContext, req: EncodeBatchRequest, out: Optional[EncodeBatchResponse] = None) -> EncodeBatchResponse:
@@ -287,6 +305,8 @@ class GpuBpeTokenizerPlugin(TokenizerPluginClient):
     def decode_batch(self, ctx: SecurityContext, req: DecodeBatchRequest) -> DecodeBatchResponse:
         if req.ids.dtype != np.uint32 or req.offsets.dtype != np.uint64 or len(req.offsets) < 1:
             raise InvalidInput("ids must be uint32 and offsets uint64 with n+1 entries")
+        if not req.ids.flags.c_contiguous or not req.offsets.flags.c_contiguous or int(req.offsets[-1]) > req.ids.size:
+            raise InvalidInput("offsets[n] must not exceed len(ids); arrays must be C-contiguous")
         vid = self._vocab_ids(req)
         try:
             out, offs = self.ctx.decode_batch(req.ids, req.offsets, vid)
@@ -343,12 +363,13 @@ class LlmGatewayTokenizerService:
         return Usage(int(counts.sum()))
 
     def encode_with_special(self, ctx: SecurityContext, model: str, texts: Sequence[str], special_tokens: dict,
-                            allowed_special="all", disallowed_special="all") -> List[np.ndarray]:
+                            allowed_special=(), disallowed_special="all") -> List[np.ndarray]:
         """tiktoken's `Encoding.encode(text, allowed_special=..., disallowed_special=...)`:
         the text is cut at every occurrence of an allowed special token (leftmost first), the stretches between them go
         through encode_ordinary -- all stretches of all texts in ONE plugin batch -- and the special ids are put back in.
         special_tokens: {"<|endoftext|>": 100257, ...}; allowed / disallowed: "all" or a set of token strings; a text
-        that holds a disallowed special token raises InvalidInput (tiktoken raises ValueError)."""
+        that holds a disallowed special token raises InvalidInput (tiktoken raises ValueError).  Defaults as tiktoken's:
+        nothing allowed, everything disallowed -- user text that spells a control token is refused, not turned into one."""
         import re
         allowed = set(special_tokens) if allowed_special == "all" else set(allowed_special)
         disallowed = (set(special_tokens) - allowed) if disallowed_special == "all" else set(disallowed_special)
@@ -395,12 +416,19 @@ class CountTokensMicroBatcher:
     counts.  In ModKit terms this is a `stateful` lifecycle task (docs/modkit_unified_system/08_lifecycle_stateful_tasks.md:14-58):
     start() / stop() are its hooks.  A failed batch fails exactly the calls that were in it."""
 
-    def __init__(self, plugin: TokenizerPluginClient, max_batch_bytes: int = 8 << 20, max_wait_s: float = 0.0005, max_queue: int = 65536):
+    def __init__(self, plugin: TokenizerPluginClient, max_batch_bytes: int = 8 << 20, max_wait_s: float = 0.0005, max_queue: int = 65536,
+                 max_batch_prompts: int = 1 << 16):
         import queue
-        self._plugin, self._max_bytes, self._max_wait = plugin, int(max_batch_bytes), float(max_wait_s)
+        # a batch never exceeds what the plugin's device context accepts (otherwise one oversize batch fails every caller in it)
+        lim_b = getattr(plugin, "max_batch_bytes", None)
+        lim_p = getattr(plugin, "max_prompts", None)
+        self._max_bytes = int(min(max_batch_bytes, lim_b)) if lim_b else int(max_batch_bytes)
+        self._max_prompts = int(min(max_batch_prompts, lim_p)) if lim_p else int(max_batch_prompts)
+        self._plugin, self._max_wait = plugin, float(max_wait_s)
         self._q = queue.Queue(maxsize=max_queue)
         self._worker: Optional[threading.Thread] = None
         self._stop = threading.Event()
+        self._carry = None        # an item that did not fit the batch being packed: first of the next one
         self.batches = 0          # how many plugin calls were made (for tests / metrics)
         self.items = 0
 
@@ -419,11 +447,21 @@ class CountTokensMicroBatcher:
             self._worker = None
 
     def count(self, ctx: SecurityContext, model: str, texts: Sequence[str], timeout: Optional[float] = None) -> np.ndarray:
-        """token counts of `texts` under `model`'s vocabulary; blocks until the batch this call rode in is done"""
+        """token counts of `texts` under `model`'s vocabulary; blocks until the batch this call rode in is done.
+        What can be checked per request is checked HERE, before the request joins a batch with other tenants' requests:
+        an unknown model or an oversize request fails this caller only."""
         import queue
         if self._worker is None:
             raise ServiceUnavailable("the micro-batcher is not running")
-        item = {"ctx": ctx, "model": model, "texts": [t.encode("utf-8") for t in texts], "done": threading.Event(), "out": None, "err": None}
+        enc = [t.encode("utf-8") for t in texts]
+        size = sum(len(t) for t in enc)
+        if size > self._max_bytes or len(enc) > self._max_prompts:
+            raise InvalidInput("the request (%d bytes, %d texts) exceeds the batch limits (%d bytes, %d prompts)"
+                               % (size, len(enc), self._max_bytes, self._max_prompts))
+        resolve = getattr(self._plugin, "_resolve_slot", None)
+        if resolve is not None:
+            resolve(VocabRef(model))          # VocabNotFound for this caller alone
+        item = {"ctx": ctx, "model": model, "texts": enc, "size": size, "done": threading.Event(), "out": None, "err": None}
         try:
             self._q.put(item, timeout=timeout)
         except queue.Full:
@@ -437,12 +475,13 @@ class CountTokensMicroBatcher:
     def _run(self):
         import queue, time
         while not self._stop.is_set():
-            first = self._q.get()
+            first = self._carry if self._carry is not None else self._q.get()
+            self._carry = None
             if first is None:
                 break
-            batch, size = [first], sum(len(t) for t in first["texts"])
+            batch, size, n = [first], first["size"], len(first["texts"])
             deadline = time.monotonic() + self._max_wait
-            while size < self._max_bytes:
+            while size < self._max_bytes and n < self._max_prompts:
                 try:
                     nxt = self._q.get(timeout=max(0.0, deadline - time.monotonic()))
                 except queue.Empty:
@@ -450,9 +489,15 @@ class CountTokensMicroBatcher:
                 if nxt is None:
                     self._stop.set()
                     break
+                if size + nxt["size"] > self._max_bytes or n + len(nxt["texts"]) > self._max_prompts:
+                    self._carry = nxt          # does not fit: it opens the next batch
+                    break
                 batch.append(nxt)
-                size += sum(len(t) for t in nxt["texts"])
+                size += nxt["size"]
+                n += len(nxt["texts"])
             self._flush(batch)
+        if self._carry is not None:
+            self._carry["err"] = ServiceUnavailable("the micro-batcher stopped"); self._carry["done"].set(); self._carry = None
         while True:               # fail what is still queued
             try:
                 it = self._q.get_nowait()
@@ -461,25 +506,43 @@ class CountTokensMicroBatcher:
             if it is not None:
                 it["err"] = ServiceUnavailable("the micro-batcher stopped"); it["done"].set()
 
-    def _flush(self, batch):
+    def _call(self, batch):
+        """one plugin call for `batch`; fills out / raises"""
         pieces = [t for it in batch for t in it["texts"]]
-        offs = np.zeros(len(pieces) + 1, dtype=np.uint64)
-        if pieces:
-            offs[1:] = np.cumsum([len(t) for t in pieces])
-        data = np.frombuffer(b"".join(pieces), dtype=np.uint8) if pieces else np.zeros(0, dtype=np.uint8)
-        vocabs = [VocabRef(it["model"]) for it in batch for _ in it["texts"]]
-        try:
-            counts = self._plugin.count_tokens(batch[0]["ctx"], CountTokensRequest(vocabs[0] if vocabs else VocabRef(batch[0]["model"]), data, offs,
-                                                                                  vocabs_per_prompt=vocabs)) if pieces else np.zeros(0, dtype=np.uint32)
-            k = 0
+        if not pieces:
             for it in batch:
-                n = len(it["texts"])
-                it["out"] = np.array(counts[k:k + n], dtype=np.uint32)
-                k += n
-        except Exception as e:    # noqa: BLE001 -- every caller of this batch gets the error
+                it["out"] = np.zeros(0, dtype=np.uint32)
+            return
+        offs = np.zeros(len(pieces) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(t) for t in pieces])
+        data = np.frombuffer(b"".join(pieces), dtype=np.uint8)
+        vocabs = [VocabRef(it["model"]) for it in batch for _ in it["texts"]]
+        # the call carries the first request's SecurityContext only as the transport identity: counting tokens reads no
+        # tenant-scoped state, and every caller gets exactly its own prompts' counts back
+        counts = self._plugin.count_tokens(batch[0]["ctx"], CountTokensRequest(vocabs[0], data, offs, vocabs_per_prompt=vocabs))
+        k = 0
+        for it in batch:
+            n = len(it["texts"])
+            it["out"] = np.array(counts[k:k + n], dtype=np.uint32)
+            k += n
+
+    def _flush(self, batch):
+        """A failed batch is retried request by request, so a bad request (malformed UTF-8, a model whose vocabulary was
+        unloaded meanwhile) fails its own caller and nobody else's -- requests of different tenants share batches."""
+        try:
+            self._call(batch)
+            self.batches += 1
+        except TokenizerError:
+            for it in batch:
+                try:
+                    self._call([it])
+                except Exception as e:    # noqa: BLE001
+                    it["err"] = e
+                self.batches += 1
+        except Exception as e:    # noqa: BLE001 -- not an input problem: every caller of this batch gets the error
             for it in batch:
                 it["err"] = e
-        self.batches += 1
+            self.batches += 1
         self.items += len(batch)
         for it in batch:
             it["done"].set()

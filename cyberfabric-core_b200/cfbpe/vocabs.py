@@ -7,8 +7,12 @@ lives here until the registry grows one.
 Real OpenAI / Meta rank files are NOT on this box (no network).  A VocabSpec
 therefore resolves in this order:
   1. a real rank file found in $CFBPE_VOCAB_DIR or vocabs/ whose sha256 matches the published one;
-  2. the committed Mistral Tekken rank file truncated to the same vocabulary size, used with the
-     requested pattern -- labelled `stand_in=True` so that every benchmark line says so.
+  2. ONLY when the caller opts in (allow_stand_in=True / CFBPE_ALLOW_STAND_IN=1: benchmarks and tests): the committed
+     Mistral Tekken rank file truncated to the same vocabulary size, used with the requested pattern -- labelled
+     `stand_in=True` so that every benchmark line and the plugin instance's properties say so.  Otherwise: VocabUnavailable.
+
+Tekken ids here are raw ranks 0..n-1 of the rank file; mistral_common shifts them by its 1000 reserved special-token ids
+(`id = rank + 1000`).  A gateway that serves Mistral models adds that offset above this layer.
 """
 import hashlib
 import os
@@ -71,7 +75,15 @@ def _read(path):
         return f.read()
 
 
-def resolve(name: str) -> ResolvedVocab:
+class VocabUnavailable(LookupError):
+    """the vocabulary is unknown, or its real rank file is not on this host and stand-ins were not asked for"""
+
+
+def resolve(name: str, allow_stand_in: bool = False) -> ResolvedVocab:
+    """allow_stand_in: serve a vocabulary whose real rank file is absent from the truncated Tekken file (benchmarks and
+    tests only -- its token counts are NOT the real model's).  Off by default: a gateway must not bill from a stand-in."""
+    if name not in SPECS:
+        raise VocabUnavailable("unknown vocabulary %r" % name)
     spec = SPECS[name]
     if name == "tekken":
         data = _read(TEKKEN_FILE)
@@ -85,6 +97,9 @@ def resolve(name: str) -> ResolvedVocab:
             if want and sha != want:
                 raise ValueError("%s: sha256 %s does not match the published %s" % (p, sha, want))
             return ResolvedVocab(spec, data, 0, False, spec.real_file, sha)
+    if not (allow_stand_in or os.environ.get("CFBPE_ALLOW_STAND_IN") == "1"):
+        raise VocabUnavailable("%s: %s is not in $CFBPE_VOCAB_DIR or %s (stand-ins are opt-in: allow_stand_in=True)"
+                               % (name, spec.real_file, VOCAB_DIR))
     data = _read(TEKKEN_FILE)
     n = min(spec.n_ranks, 150000)
     return ResolvedVocab(spec, data, n, True, "STAND-IN tekken_240911[:%d] + %s pattern" % (n, spec.pattern),
@@ -92,5 +107,8 @@ def resolve(name: str) -> ResolvedVocab:
 
 
 def for_model(canonical_id: str) -> str:
-    """vocab name for a model-registry canonical id; KeyError if the model is unknown"""
-    return MODEL_VOCABS[canonical_id]
+    """vocab name for a model-registry canonical id; VocabUnavailable if the model is unknown"""
+    try:
+        return MODEL_VOCABS[canonical_id]
+    except KeyError:
+        raise VocabUnavailable("no vocabulary is registered for model %r" % canonical_id) from None

@@ -71,6 +71,10 @@ struct cfbpe_ctx {
     uint64_t* d_dec_base = nullptr;      // ... and their exclusive scan
     cudaStream_t aux_stream = nullptr;   // the long-piece kernel runs here, next to the short-piece kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_ws = nullptr;         // recorded at the end of an asynchronous device-path call: the workspace is busy until then
+    bool ws_pending = false;             // ... and whether one is outstanding
+    uint64_t dev_out_cap = 0;            // out_cap of the last device-path call (cfbpe_device_status reports ENOSPC against it)
+    bool dev_want_ids = false;
     cudaEvent_t ev_scan[kMaxPipeChunks] = {};
     cudaStream_t front[kFrontStreams] = {};   // front streams 1.. of a pipelined host call (0 = stream)
     cudaStream_t side[kSideStreams] = {};  // long-piece tails + emit of sub-batch k overlap the front of k+1
@@ -147,7 +151,7 @@ int install_blob(cfbpe_ctx* ctx, uint32_t vocab_id, std::vector<uint8_t>&& blob)
     CK(cudaMalloc(reinterpret_cast<void**>(&d), blob.size()));
     cudaError_t e = cudaMemcpy(d, blob.data(), blob.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(d); return fail(ctx, CFBPE_EIO, std::string("table upload: ") + cudaGetErrorString(e)); }
-    if (v.d_blob) { cudaStreamSynchronize(ctx->stream); cudaFree(v.d_blob); }
+    if (v.d_blob) { cudaDeviceSynchronize(); cudaFree(v.d_blob); }   // kernels of a device-path call on any stream may still read the old tables
     v.d_blob = d;
     v.h_blob = std::move(blob);
     std::memcpy(&v.hdr, v.h_blob.data(), sizeof(TablesHeader));
@@ -308,6 +312,7 @@ int run_host(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const uint64_t* o
     if (total && !bytes) return fail(ctx, CFBPE_EINVAL, "bytes is NULL");
     if (want_ids && (!out_offsets || (!out_ids && out_cap))) return fail(ctx, CFBPE_EINVAL, "output pointer is NULL");
     CK(cudaSetDevice(ctx->device));
+    if (ctx->ws_pending) { CK(cudaEventSynchronize(ctx->ev_ws)); ctx->ws_pending = false; }   // an asynchronous device-path call still owns the workspace
     if (!ctx->profiling && total >= ctx->pipe_min && n >= 2)
         return run_host_pipelined(ctx, n, bytes, offsets, vocab_ids, out_ids, out_cap, out_offsets, out_counts, want_ids, total);
     cudaStream_t s = ctx->stream;
@@ -357,10 +362,8 @@ const char* cfbpe_build_id(void) { return CFBPE_SRC_HASH; }
 int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     if (!cfg || !out || cfg->struct_size < sizeof(cfbpe_config)) return CFBPE_EINVAL;
     *out = nullptr;
-    // a pipelined host call keeps ~20 streams busy; with the default 8 hardware connections streams share queues and a
-    // download waits behind another sub-batch's pending status copy (tools/pipe_trace.py: 7.1 -> 6.1 ms).  Only effective if
-    // the process has not initialised CUDA yet; hosts that have should export it themselves.
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    // (a pipelined host call keeps ~20 streams busy: hosts should export CUDA_DEVICE_MAX_CONNECTIONS=32 before CUDA
+    //  initialises -- INTEGRATION.md; the library does not touch the process environment)
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return CFBPE_ENODEV;
     if (cfg->device < 0 || cfg->device >= ndev) return CFBPE_ENODEV;
@@ -431,6 +434,7 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
         ok = ok && cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
     }
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_ws, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; ok && k < kMaxPipeChunks; ++k) ok = cudaEventCreateWithFlags(&ctx->ev_scan[k], cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; ok && k < kMaxPipeChunks; ++k)
         ok = cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming) == cudaSuccess &&
@@ -472,7 +476,7 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
 void cfbpe_destroy(cfbpe_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();             // device-path calls may still be running on the caller's streams
     cudaFree(ctx->d_bytes); cudaFree(ctx->d_offsets); cudaFree(ctx->d_vocab_ids);
     cudaFree(ctx->d_out_ids); cudaFree(ctx->d_out_offsets); cudaFree(ctx->d_out_counts);
     cudaFree(ctx->ws.piece_bits); cudaFree(ctx->ws.tok_bits); cudaFree(ctx->ws.ids_by_pos);
@@ -492,6 +496,7 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     for (int k = 0; k < kMaxPipeChunks; ++k) if (ctx->ev_scan[k]) cudaEventDestroy(ctx->ev_scan[k]);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_ws) cudaEventDestroy(ctx->ev_ws);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
@@ -595,6 +600,7 @@ int cfbpe_decode_batch(cfbpe_ctx* ctx, uint32_t n_seqs, const uint32_t* ids, con
         if (vocab_ids[i] >= kMaxVocabs || !ctx->vocabs[vocab_ids[i]].loaded) return fail(ctx, CFBPE_ENOENT, "vocab " + std::to_string(vocab_ids[i]) + " is not loaded");
     if (!vocab_ids && !ctx->vocabs[0].loaded) return fail(ctx, CFBPE_ENOENT, "vocab 0 is not loaded");
     CK(cudaSetDevice(ctx->device));
+    if (ctx->ws_pending) { CK(cudaEventSynchronize(ctx->ev_ws)); ctx->ws_pending = false; }
     cudaStream_t s = ctx->stream;
     if (n_ids) CK(cudaMemcpyAsync(ctx->d_out_ids, ids, n_ids * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_offsets, id_offsets, (static_cast<uint64_t>(n_seqs) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
@@ -636,12 +642,18 @@ int cfbpe_encode_batch_device(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t*
     if (!ctx->vocabs[0].loaded && !d_vocab_ids) return fail(ctx, CFBPE_ENOENT, "vocab 0 is not loaded");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // one workspace per context: a call on another stream waits (on the device) for the previous device-path call
+    if (ctx->ws_pending) CK(cudaStreamWaitEvent(s, ctx->ev_ws, 0));
     ProfEvents* prof = ctx->profiling ? &ctx->prof : nullptr;
     if (prof) { std::memset(prof->launched, 0, sizeof prof->launched); cudaEventRecord(prof->total[0], s); cudaEventRecord(prof->h2d[0], s); cudaEventRecord(prof->h2d[1], s); }
     BatchView b{d_bytes, d_offsets, d_vocab_ids, n_prompts, total_bytes};
     enqueue_encode(b, ctx->vs, ctx->uc, ctx->ws, d_out_ids, out_cap, d_out_offsets, d_out_counts,
                    static_cast<uint32_t>(ctx->sm_count * 4), s, prof ? s : ctx->aux_stream, ctx->ev_fork, ctx->ev_join, prof);   // profiling: one stream, so that the per-kernel times do not overlap
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_ws, s));
+    ctx->ws_pending = true;
+    ctx->dev_out_cap = out_cap;
+    ctx->dev_want_ids = d_out_ids != nullptr;
     if (prof) { cudaEventRecord(prof->d2h[0], s); cudaEventRecord(prof->d2h[1], s); cudaEventRecord(prof->total[1], s); }
     if (n_tokens || prof) {
         CK(cudaMemcpyAsync(ctx->h_status, ctx->ws.status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
@@ -664,6 +676,8 @@ int cfbpe_device_status(cfbpe_ctx* ctx, void* stream) {
     CK(cudaStreamSynchronize(s));
     if (ctx->h_status->long_overflow || ctx->h_status->miss_overflow) return fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
     if (ctx->h_status->bad_utf8) return fail(ctx, CFBPE_EILSEQ, "a prompt holds malformed UTF-8");
+    if (ctx->dev_want_ids && ctx->h_status->n_tokens > ctx->dev_out_cap)
+        return fail(ctx, CFBPE_ENOSPC, "out_cap too small: need " + std::to_string(ctx->h_status->n_tokens) + " ids");
     return CFBPE_OK;
 }
 

@@ -9,6 +9,7 @@ for p in (ROOT, os.path.join(ROOT, "cyberfabric-core_b200"), os.path.join(ROOT, 
     if p not in sys.path:
         sys.path.insert(0, p)
 
+os.environ.setdefault("CFBPE_ALLOW_STAND_IN", "1")   # tests run on the stand-in vocabularies (the real OpenAI / Meta rank files are not on the box)
 TEKKEN_PATH = os.path.join(ROOT, "vocabs", "tekken_240911.tiktoken")
 # (pattern id, vocab size) of each benchmark slot; see cfbpe/vocabs.py
 COMBOS = [(0, 100256), (1, 150000), (2, 128000), (3, 130072)]

@@ -63,11 +63,13 @@ def test_fuzz_against_oracle(plug, ctx, oracle_vocabs, pat, n_ranks):
     assert np.array_equal(r.counts, want_counts)
 
 
-@pytest.mark.parametrize("cfg_id,scale", [(2, 1.0), (3, 0.125), (4, 0.25)])
-def test_benchmark_configs_against_oracle(plug, ctx, cfg_id, scale):
+@pytest.mark.parametrize("cfg_id", [1, 2, 3, 4])
+def test_benchmark_configs_full_size_against_oracle(plug, ctx, cfg_id):
+    """BASELINE.json configs 1-4 at FULL size: every id, offset and count equal to the oracle's (no sampling, no scaling)"""
+    from cfbpe import plugin as P
     from cfbpe import workload as W
     from oracle import oracle
-    data, offs, vid, meta = W.make_config(cfg_id, scale)
+    data, offs, vid, meta = W.make_config(cfg_id, 1.0)
     name = meta["vocabs"][0]
     rv = plug.resolved[name]
     ov = oracle.OracleVocab(rv.file_bytes, rv.max_ranks)
@@ -75,24 +77,122 @@ def test_benchmark_configs_against_oracle(plug, ctx, cfg_id, scale):
     r = encode(plug, ctx, name, data, offs)
     assert np.array_equal(r.offsets, want_off)
     assert np.array_equal(r.ids, want_ids)
+    assert np.array_equal(r.counts, want_counts)
+    counts = plug.count_tokens(ctx, P.CountTokensRequest(P.VocabRef(name), data, offs))
+    assert np.array_equal(counts, want_counts)
 
 
-def test_multi_tenant_vocab_mix_against_oracle(plug, ctx):
+def test_multi_tenant_vocab_mix_full_size_against_oracle(plug, ctx):
+    """BASELINE.json config 5 at FULL size: 256 tenants x 256 prompts, vocabulary = tenant mod 3, one batch"""
     from cfbpe import plugin as P
     from cfbpe import workload as W
     from oracle import oracle
-    data, offs, vid, meta = W.make_config(5, 0.05)
+    data, offs, vid, meta = W.make_config(5, 1.0)
     names = meta["vocabs"]
     ovs, pats = [], []
     for nm in names:
         rv = plug.resolved[nm]
         ovs.append(oracle.OracleVocab(rv.file_bytes, rv.max_ranks))
         pats.append(rv.pattern_id)
-    want_ids, want_off, _ = oracle.encode_batch(ovs, pats, data, offs, vocab_ids=vid, nthreads=os.cpu_count())
+    want_ids, want_off, want_counts = oracle.encode_batch(ovs, pats, data, offs, vocab_ids=vid, nthreads=os.cpu_count())
     refs = [P.VocabRef(names[int(v)]) for v in vid]
     r = encode(plug, ctx, names[0], data, offs, per_prompt=refs)
     assert np.array_equal(r.offsets, want_off)
     assert np.array_equal(r.ids, want_ids)
+    assert np.array_equal(r.counts, want_counts)
+
+
+def _tiktoken_encoding(tekken_bytes, pat, n_ranks, special=None):
+    tiktoken = pytest.importorskip("tiktoken")
+    from oracle import patterns as PT
+    lines = tekken_bytes.splitlines()[:n_ranks]
+    ranks = {base64.b64decode(l.split()[0]): i for i, l in enumerate(lines)}
+    return tiktoken.Encoding("live%d" % pat, pat_str=PT.PATTERNS[pat], mergeable_ranks=ranks, special_tokens=special or {})
+
+
+@pytest.mark.parametrize("pat,n_ranks", COMBOS)
+def test_cuda_path_directly_against_live_tiktoken(plug, ctx, tekken_bytes, pat, n_ranks):
+    """the pin without the C port in between: libcfbpe.so vs tiktoken 0.12.0 `encode_ordinary_batch` on the same strings
+    (fuzz strings, adversarial runs, and the prompts of BASELINE.json config 2)"""
+    from cfbpe import workload as W
+    enc = _tiktoken_encoding(tekken_bytes, pat, n_ranks)
+    strs = fuzzgen.fuzz_strings(31000 + pat, 6000, max_atoms=48) + fuzzgen.long_runs(91 + pat)
+    d2, o2, _, _ = W.make_config(2, 1.0)
+    strs += [bytes(d2[int(o2[i]):int(o2[i + 1])]).decode("utf-8") for i in range(len(o2) - 1)]
+    want = enc.encode_ordinary_batch(strs, num_threads=min(32, os.cpu_count() or 1))
+    data, offs = pack([s.encode() for s in strs])
+    r = encode(plug, ctx, SLOT_NAMES[pat], data, offs)
+    want_off = np.zeros(len(strs) + 1, dtype=np.uint64)
+    want_off[1:] = np.cumsum([len(w) for w in want])
+    assert np.array_equal(r.offsets, want_off)
+    assert np.array_equal(r.ids, np.concatenate([np.asarray(w, dtype=np.uint32) for w in want]))
+
+
+def test_encode_with_special_on_device_against_tiktoken(plug, ctx, tekken_bytes):
+    """special tokens over the CUDA path vs `tiktoken.Encoding.encode(text, allowed_special=...)`"""
+    from cfbpe import plugin as P
+    special = {"<|endoftext|>": 100257, "<|fim_prefix|>": 100258, "<|endofprompt|>": 100276}
+    enc = _tiktoken_encoding(tekken_bytes, 0, 100256, special)
+    hub = P.ClientHub()
+    hub.register_scoped(P.TokenizerPluginClient, plug.instance.id, plug)
+    svc = P.LlmGatewayTokenizerService(hub, [plug.instance])
+    base = fuzzgen.fuzz_strings(77, 400, max_atoms=30)
+    keys = list(special)
+    texts = []
+    for i, t in enumerate(base):
+        k = keys[i % 3]
+        texts.append([t, k + t, t + k, t[: len(t) // 2] + k + t[len(t) // 2:] + k + k, k][i % 5])
+    got = svc.encode_with_special(ctx, "cl100k_base", texts, special, allowed_special="all")
+    for t, g in zip(texts, got):
+        assert g.tolist() == enc.encode(t, allowed_special="all"), repr(t)
+    only = {"<|endoftext|>"}
+    plain = [t for t in texts if "<|fim_prefix|>" not in t and "<|endofprompt|>" not in t]
+    got = svc.encode_with_special(ctx, "cl100k_base", plain, special, allowed_special=only)
+    for t, g in zip(plain, got):
+        assert g.tolist() == enc.encode(t, allowed_special=only), repr(t)
+    with pytest.raises(P.InvalidInput):          # tiktoken raises ValueError: the default disallows every special token
+        svc.encode_with_special(ctx, "cl100k_base", ["a <|endoftext|> b"], special)
+    # disallowed_special=() : the special token's text is encoded as ordinary text
+    got = svc.encode_with_special(ctx, "cl100k_base", ["a <|endoftext|> b"], special, allowed_special=(), disallowed_special=())
+    assert got[0].tolist() == enc.encode("a <|endoftext|> b", allowed_special=set(), disallowed_special=())
+
+
+def test_micro_batcher_on_device_from_64_threads(plug, ctx, oracle_vocabs):
+    """SURVEY.md 8(f) item 4 on the real plugin: 64 request threads, two vocabularies, every caller gets its own counts;
+    one bad request fails alone"""
+    import threading
+    from cfbpe import plugin as P
+    mb = P.CountTokensMicroBatcher(plug, max_batch_bytes=4 << 20, max_wait_s=0.001).start()
+    texts = fuzzgen.fuzz_strings(555, 64 * 24, max_atoms=40)
+    models = ["cl100k_base", "tekken"]
+    pat_of = {"cl100k_base": 0, "tekken": 3}
+    results, errors = {}, []
+
+    def worker(t):
+        try:
+            for j in range(8):
+                mine = texts[(t * 8 + j) * 3:(t * 8 + j) * 3 + 3]
+                m = models[(t + j) % 2]
+                results[(t, j)] = (m, mine, mb.count(ctx, m, mine, timeout=60))
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(64)]
+    for x in th:
+        x.start()
+    bad = None
+    try:
+        mb.count(ctx, "no-such-model", ["x"], timeout=60)
+    except P.TokenizerError as e:
+        bad = e
+    for x in th:
+        x.join()
+    mb.stop()
+    assert not errors, errors[:1]
+    assert isinstance(bad, P.VocabNotFound)
+    assert len(results) == 64 * 8 and mb.batches < mb.items
+    for m, mine, counts in results.values():
+        want = [len(oracle_vocabs[pat_of[m]].encode(pat_of[m], s.encode())) for s in mine]
+        assert counts.tolist() == want
 
 
 def test_full_size_config3_properties(plug, ctx, tekken_bytes):

@@ -60,12 +60,24 @@ def test_vocab_registry_resolution():
     rv = V.resolve("tekken")
     assert not rv.stand_in and rv.max_ranks == 130072 and rv.pattern_id == 3
     for name, pat in (("cl100k_base", 0), ("o200k_base", 1), ("llama3", 2)):
-        rv = V.resolve(name)
+        rv = V.resolve(name, allow_stand_in=True)
         assert rv.pattern_id == pat
         assert rv.stand_in and "STAND-IN" in rv.label          # the real rank files are not on this box
     assert V.for_model("openai::gpt-4o") == "o200k_base"
-    with pytest.raises(KeyError):
+    with pytest.raises(V.VocabUnavailable):
         V.for_model("nobody::nothing")
+    with pytest.raises(V.VocabUnavailable):
+        V.resolve("no-such-vocab")
+
+
+def test_stand_in_vocabularies_are_opt_in(monkeypatch):
+    """a production plugin must not count tokens of openai::gpt-4 with another vocabulary: without the opt-in a missing real
+    rank file is an error, not a silent stand-in"""
+    monkeypatch.delenv("CFBPE_ALLOW_STAND_IN", raising=False)
+    with pytest.raises(V.VocabUnavailable):
+        V.resolve("cl100k_base")
+    assert V.resolve("cl100k_base", allow_stand_in=True).stand_in
+    assert not V.resolve("tekken").stand_in
 
 
 def test_workload_is_deterministic_and_valid_utf8():
@@ -136,12 +148,57 @@ def test_micro_batcher_coalesces_concurrent_calls_and_isolates_failures():
     except P.InvalidInput:
         pass
     assert mb.count(ctx, "cl100k_base", ["still fine"], timeout=10).tolist() == [2]
+    # requests of different tenants share batches: a bad request must fail ITS caller only (the batch is retried item by item)
+    mb2 = P.CountTokensMicroBatcher(plug, max_wait_s=0.05).start()
+    res2, err2 = {}, {}
+    def call2(i):
+        try:
+            res2[i] = mb2.count(ctx, "cl100k_base", ["boom"] if i == 5 else ["a b c"], timeout=10).tolist()
+        except P.TokenizerError as e:
+            err2[i] = e
+    threads = [threading.Thread(target=call2, args=(i,)) for i in range(16)]
+    [t.start() for t in threads]; [t.join() for t in threads]
+    assert list(err2) == [5] and isinstance(err2[5], P.InvalidInput)
+    assert all(res2[i] == [3] for i in range(16) if i != 5)
+    mb2.stop()
+    # a batch never exceeds the limits it was given; an oversize request is refused up front, alone
+    mb3 = P.CountTokensMicroBatcher(plug, max_batch_bytes=64, max_batch_prompts=4, max_wait_s=0.05).start()
+    with pytest.raises(P.InvalidInput):
+        mb3.count(ctx, "cl100k_base", ["x" * 65], timeout=10)
+    with pytest.raises(P.InvalidInput):
+        mb3.count(ctx, "cl100k_base", ["a"] * 5, timeout=10)
+    res3 = {}
+    threads = [threading.Thread(target=lambda i=i: res3.__setitem__(i, mb3.count(ctx, "cl100k_base", ["w " * 20], timeout=10).tolist())) for i in range(6)]
+    [t.start() for t in threads]; [t.join() for t in threads]
+    assert all(res3[i] == [20] for i in range(6)) and mb3.batches >= 6      # 40-byte requests, 64-byte batches: one per call
+    mb3.stop()
     mb.stop()
     try:
         mb.count(ctx, "cl100k_base", ["late"], timeout=1)
         assert False
     except P.ServiceUnavailable:
         pass
+
+
+def test_plugin_rejects_offsets_beyond_the_buffer():
+    """the C ABI takes no buffer lengths: the host layer must refuse offsets[n] > len(bytes), wrong dtypes and strided arrays
+    before any pointer crosses the boundary (an oversize last offset would make the upload read past the caller's array)"""
+    from cfbpe import _native as N
+    chk = P.GpuBpeTokenizerPlugin._check_arrays
+    ok = P.EncodeBatchRequest(P.VocabRef("x"), np.zeros(8, np.uint8), np.array([0, 3, 8], np.uint64))
+    chk(ok)
+    for b, o in [(np.zeros(8, np.uint8), np.array([0, 3, 9], np.uint64)), (np.zeros(8, np.uint8), np.array([1, 3, 8], np.uint64)),
+                 (np.zeros(16, np.uint8)[::2], np.array([0, 8], np.uint64)), (np.zeros(8, np.int8), np.array([0, 8], np.uint64)),
+                 (np.zeros(8, np.uint8), np.array([0, 8], np.int64)), (np.zeros((2, 4), np.uint8), np.array([0, 8], np.uint64))]:
+        with pytest.raises(P.InvalidInput):
+            chk(P.EncodeBatchRequest(P.VocabRef("x"), b, o))
+    ci = N.Context._check_inputs
+    assert ci(np.zeros(8, np.uint8), np.array([0, 8], np.uint64), None) == 1
+    for args in [(np.zeros(8, np.uint8), np.array([0, 9], np.uint64), None), (np.zeros(8, np.uint8), np.array([0, 4, 8], np.uint64), np.zeros(1, np.uint8)),
+                 (np.zeros(8, np.uint8), np.array([0, 8], np.uint64), np.zeros(1, np.int32)), (np.zeros(8, np.uint32), np.array([0, 8], np.uint64), None)]:
+        with pytest.raises(N.NativeError) as ei:
+            ci(*args)
+        assert ei.value.code == N.EINVAL
 
 
 def test_encode_with_special_tokens_matches_tiktoken():
@@ -177,7 +234,7 @@ def test_encode_with_special_tokens_matches_tiktoken():
     svc = P.LlmGatewayTokenizerService(hub, [inst], vendor="cyberfabric")
     ctx = P.SecurityContext.anonymous()
     texts = ["hello <|endoftext|> world<|endoftext|>", "<|fim_prefix|>", "", "no specials here", "a<|endofprompt|><|endoftext|>b  ", "<|endoftext|><|endoftext|>x"]
-    got = svc.encode_with_special(ctx, "cl100k_base", texts, specials)
+    got = svc.encode_with_special(ctx, "cl100k_base", texts, specials, allowed_special="all")
     for t, g in zip(texts, got):
         assert g.tolist() == enc.encode(t, allowed_special="all"), t
     got = svc.encode_with_special(ctx, "cl100k_base", ["x <|endoftext|> y"], specials, allowed_special={"<|endoftext|>"}, disallowed_special=())
@@ -186,3 +243,7 @@ def test_encode_with_special_tokens_matches_tiktoken():
     assert got[0].tolist() == enc.encode("x <|endoftext|> y", allowed_special=set(), disallowed_special=())
     with pytest.raises(P.InvalidInput):
         svc.encode_with_special(ctx, "cl100k_base", ["x <|endoftext|> y"], specials, allowed_special=())
+    with pytest.raises(P.InvalidInput):      # the default is tiktoken's: nothing allowed, everything disallowed (no special-token injection)
+        svc.encode_with_special(ctx, "cl100k_base", ["x <|endoftext|> y"], specials)
+    with pytest.raises(ValueError):
+        enc.encode("x <|endoftext|> y")

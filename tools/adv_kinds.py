@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Long-piece kernel times for the adversarial prompts of the bench mix, one kind at a time (819 prompts of 8..4096 bytes
 each, as in BASELINE.json configs[2]) -- which kind makes the tail of bpe_list (a measurement aid)."""
+import os; os.environ.setdefault("CFBPE_ALLOW_STAND_IN", "1")   # measurement aids run on the stand-in vocabularies
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "cyberfabric-core_b200")):

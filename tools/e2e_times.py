@@ -10,7 +10,7 @@ from cfbpe import _native as N, vocabs as V, workload as W
 
 data, offs, vid, meta = W.make_config(3, 1.0)
 total, n = int(offs[-1]), len(offs) - 1
-rv = V.resolve("cl100k_base")
+rv = V.resolve("cl100k_base", allow_stand_in=True)
 for chunk, pmin in [(0, 1 << 40), (6 << 20, 1), (12 << 20, 1), (24 << 20, 1), (48 << 20, 1), (70 << 20, 1)]:
     if chunk:
         os.environ["CFBPE_PIPE_CHUNK_BYTES"] = str(chunk)

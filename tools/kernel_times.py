@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
 """Per-kernel device times (library CUDA events) for differently mixed batches -- a measurement aid, not a bench."""
+import os; os.environ.setdefault("CFBPE_ALLOW_STAND_IN", "1")
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "cyberfabric-core_b200")):

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """bpe_long / bpe_list device time for 1 .. N long random pieces of one size: the latency of a single piece and how the
 list kernel fills the machine (a measurement aid)."""
+import os; os.environ.setdefault("CFBPE_ALLOW_STAND_IN", "1")   # measurement aids run on the stand-in vocabularies
 import os, sys, json, random
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "cyberfabric-core_b200")):

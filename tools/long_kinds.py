@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
 """bpe_long device time for batches made of ONE kind of long piece each (a measurement aid)."""
+import os; os.environ.setdefault("CFBPE_ALLOW_STAND_IN", "1")   # measurement aids run on the stand-in vocabularies
 import os, sys, json, random
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "cyberfabric-core_b200")):

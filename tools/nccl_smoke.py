@@ -2,6 +2,7 @@
 """Multi-GPU smoke (run under torchrun, one process per GPU): rank 0 parses the rank file, the packed tables travel by
 NCCL broadcast, every rank encodes its byte-balanced shard of ONE batch, per-shard token totals and per-prompt counts
 are all_gathered; rank 0 checks the reassembled result against the oracle."""
+import os; os.environ.setdefault("CFBPE_ALLOW_STAND_IN", "1")   # measurement aids run on the stand-in vocabularies
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "cyberfabric-core_b200"), os.path.join(ROOT, "tests")):

@@ -11,7 +11,7 @@ import numpy as np
 from cfbpe import _native as N, vocabs as V, workload as W
 data, offs, vid, meta = W.make_config(3, 1.0)
 total, n = int(offs[-1]), len(offs) - 1
-rv = V.resolve("cl100k_base")
+rv = V.resolve("cl100k_base", allow_stand_in=True)
 c = N.Context(0, 160 << 20, 1 << 17)
 c.vocab_load(0, rv.file_bytes, rv.spec.fmt, rv.pattern_id, rv.max_ranks)
 hb = c.pinned(total + 64, np.uint8); hb.array[:total] = data

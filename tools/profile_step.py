@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
 """Run W+K device-resident encode steps of BASELINE.json configs[2] (for ncu captures; not a bench)."""
+import os; os.environ.setdefault("CFBPE_ALLOW_STAND_IN", "1")   # measurement aids run on the stand-in vocabularies
 import argparse, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "cyberfabric-core_b200")):
