@@ -46,7 +46,8 @@ constexpr uint32_t kBigPiece = 256;      // bytes: K2b serves longer pieces firs
 constexpr uint32_t kScanTileWords = 256;   // flag words per K3 tile (= 8 KiB of text); one word per thread
 
 struct VocabSet {
-    TablesView v[kMaxVocabs];
+    TablesView v[kMaxVocabs];      // slots that are not loaded alias a loaded one (a bad id from a device-path caller must not fault) ...
+    uint32_t loaded_mask;          // ... and prompt_map_kernel reports it (DeviceStatus::bad_vocab)
 };
 
 struct BatchView {
@@ -73,7 +74,7 @@ struct DeviceStatus {
     uint32_t miss_next[3]; // K2m work tickets
     uint32_t miss_overflow;
     uint32_t fix_n;        // K1 threads that stopped in S_W_U (pretok_fixup_kernel finishes them)
-    uint32_t pad3;
+    uint32_t bad_vocab;    // != 0: a prompt names a vocabulary id that is not loaded (device-path callers; the host paths check before)
     uint32_t defer_n;      // pieces K2b handed to K2c ...
     unsigned long long defer_parts;   // ... and their parts at hand-over
 };
@@ -147,18 +148,24 @@ __device__ __forceinline__ uint64_t ascii_digit_run_end(const uint8_t* __restric
 // it is a look-back of unbounded length: inlined -- or even called -- in the hot loop it cost the kernel registers and 17 %
 // of its speed, so the thread files the position and stops, and pretok_fixup_kernel (next launch, almost always empty)
 // finds the state and finishes that thread's job.
-struct SplitFix { uint64_t pos, ce; uint32_t pidx, pad; };   // pidx: the prompt the thread was in (pos may be its END = the next one's start)
+struct SplitFix { uint32_t pos, ce; };   // byte positions inside the (sub-)batch (< 4 GiB): where to resume, and from where on the walker may hand over
 
-// kFix = false: the thread of chunk [cs, ce).  kFix = true: resume at fix_pos on behalf of the thread whose chunk ended at ce.
-template <bool kFix>
+// kMode 0: the thread of chunk [cs, ce) (first form of K1: one thread per 64 bytes).
+// kMode 1: resume at fix_pos on behalf of a walker that stopped in an undecided state; the real state is found by looking back.
+// kMode 2: resume at fix_pos with the state and remembered positions a lane of pretok_split16_kernel hands over (long runs).
+// kRow / kTabSize: row stride and size per pattern of the transition table at s_fsm (12-wide in the first form, 16-wide in K1 v2).
+template <int kMode, uint32_t kRow = X_COUNT, uint32_t kTabSize = kPretokTableSize>
 __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet& vs, UcTables uc, const uint16_t* s_fsm, const uint8_t* s_ascii,
                                              uint32_t* __restrict__ piece_bits, DeviceStatus* status, SplitFix* fix_list, uint32_t fix_cap,
-                                             uint64_t cs, uint64_t ce, uint64_t fix_pos, uint32_t fix_pidx) {
+                                             uint64_t cs, uint64_t ce, uint64_t fix_pos, uint32_t fix_pidx,
+                                             uint32_t state2 = 0, uint64_t alc2 = 0, uint64_t last2 = 0, uint64_t lbe2 = 0) {
+    constexpr bool kFix = kMode != 0;       // resumed walkers mark with atomics and never search for a sync point
     // (a shared-memory text tile with coalesced 16-byte loads was measured slower here: occupancy fell from 67 % to
     //  29 % and the accessor cost more than the L1 hits it replaced -- profiles/ncu_summary_r01k.json)
     const uint8_t* __restrict__ s = b.bytes;
 
-    uint32_t pidx = kFix ? fix_pidx : find_prompt(b.offsets, b.n_prompts, cs);
+    // (a resumed walker has consumed at least one byte of the prompt it is in: fix_pos may be that prompt's END)
+    uint32_t pidx = kFix ? (fix_pidx != 0xFFFFFFFFu ? fix_pidx : find_prompt(b.offsets, b.n_prompts, fix_pos - 1)) : find_prompt(b.offsets, b.n_prompts, cs);
     uint64_t ps = b.offsets[pidx], pe = b.offsets[pidx + 1];
     uc.ascii_x = s_ascii;   // the copy in shared memory
 
@@ -168,9 +175,16 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
     uint32_t prevx = X_EOT, nlet = 0, npun = 0;   // class of the previous character; consecutive letters (<= 3) / punctuation (<= 2) before pos
     uint32_t pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
     uint64_t lbe_fix = 0;
-    if (kFix) {   // the real state at fix_pos (inside a prompt, after a letter), and the classes the hand-over looks at
+    if (kMode == 1) {   // the real state at fix_pos (inside a prompt, after a letter), and the classes the hand-over looks at
         sync_state(s, pos, ps, pe, uc, true, &prevx, &nlet, &npun);
-        state = resolve_word_state(s, pos, ps, pe, uc, s_fsm + pat * kPretokTableSize, &lbe_fix);
+        state = resolve_word_state<kRow>(s, pos, ps, pe, uc, s_fsm + pat * kTabSize, &lbe_fix);
+    }
+#ifdef CUSIM_EMULATOR
+    if (kMode == 1 && getenv("CFBPE_DBG")) fprintf(stderr, "fixup: pos %llu ce %llu state %u lbe %llu pidx %u ps %llu pe %llu\n", (unsigned long long)pos, (unsigned long long)ce, state, (unsigned long long)lbe_fix, pidx, (unsigned long long)ps, (unsigned long long)pe);
+#endif
+    if (kMode == 2) {   // state handed over; the classes of the last three characters from memory
+        if (pos < pe) sync_state(s, pos, ps, pe, uc, (pat & 1u) != 0, &prevx, &nlet, &npun);
+        state = state2; lbe_fix = lbe2;
     }
     while (!kFix && pos < ce) {
         if (pos == pe) {  // step into the next non-empty prompt
@@ -185,8 +199,8 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
     if (state == kNoSync) return;
 
     // ---- run the automaton
-    const uint16_t* tab = s_fsm + pat * kPretokTableSize;
-    uint64_t alc = 0, last = 0, lbe = kFix ? lbe_fix : pos;     // (lbe = pos: what W_XB0 would hold if that is what S_W_U turns out to be)
+    const uint16_t* tab = s_fsm + pat * kTabSize;
+    uint64_t alc = kMode == 2 ? alc2 : 0, last = kMode == 2 ? last2 : 0, lbe = kFix ? lbe_fix : pos;     // (lbe = pos: what W_XB0 would hold if that is what S_W_U turns out to be)
     int bad = 0;
     // boundaries inside my chunk collect in one 64-bit mask (the chunk is 64-byte aligned: two flag words, OR-ed in at the
     // end because the thread to my left may have set bits there while handing over); those beyond it go out one by one
@@ -204,10 +218,11 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
             if (b0 < 0x80) { x = s_ascii[b0]; len = 1; }
             else { const Ch c = get_char(s, pos, pe, uc, &bad); x = c.cls; len = c.len; }
         }
-        uint32_t a = tab[state * X_COUNT + x];
-        if (!kFix && (a & A_RESOLVE)) {   // started inside a run of both-sets / upper-case letters, and now it matters what came before it
+        uint32_t a = tab[state * kRow + x];
+        if (kMode != 1 && (a & A_RESOLVE)) {   // started inside a run of both-sets / upper-case letters, and now it matters what came before it
             const uint32_t k = atomicAdd(&status->fix_n, 1u);
-            if (k < fix_cap) { SplitFix f; f.pos = pos; f.ce = ce; f.pidx = pidx; f.pad = 0; fix_list[k] = f; }
+            if (k < fix_cap) { SplitFix f; f.pos = static_cast<uint32_t>(pos); f.ce = static_cast<uint32_t>(ce); fix_list[k] = f; }
+            else atomicOr(&status->long_overflow, 1u);
             break;
         }
         uint32_t skip = 0;
@@ -226,7 +241,7 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
             do { ++pidx; ps = pe; pe = b.offsets[pidx + 1]; } while (pe == ps);
             if (pos >= ce) break;            // the next prompt's first byte is a sync point of a later chunk
             pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
-            tab = s_fsm + pat * kPretokTableSize;
+            tab = s_fsm + pat * kTabSize;
             state = S_START;
             prevx = X_EOT; nlet = 0; npun = 0;
             continue;
@@ -263,7 +278,7 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
             //      my chunk: inside it the walk is bounded anyway, and short runs (indentation, years) are cheaper per character
             if (pos >= ce && b0 < 0x80u && pos < pe) {
                 if ((x == X_SPACE || x == X_CRLF || x == X_WS) && s[pos] == b0) {
-                    const uint32_t a2 = tab[state * X_COUNT + x];
+                    const uint32_t a2 = tab[state * kRow + x];
                     if ((a2 & A_STATE_MASK) == state && !(a2 & (A_B_NOW | A_EMIT_ALC | A_EMIT_LAST | A_EMIT_LBE | A_CONTR))) {
                         CFBPE_DBG_COUNT(3);
                         const uint64_t e = same_byte_run_end(s, pos, pe, b0);    // self-loop: only the remembered positions move
@@ -274,7 +289,7 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
                     }
                 } else if (x == X_N && state >= S_D1 && state <= S_D3 && (s[pos] - '0') < 10u) {
                     // \p{N}{1,md}: a boundary every md digits, counted from the start of the run
-                    const uint32_t md = (tab[S_D1 * X_COUNT + X_N] & A_B_NOW) ? 1u : ((tab[S_D2 * X_COUNT + X_N] & A_B_NOW) ? 2u : 3u);
+                    const uint32_t md = (tab[S_D1 * kRow + X_N] & A_B_NOW) ? 1u : ((tab[S_D2 * kRow + X_N] & A_B_NOW) ? 2u : 3u);
                     CFBPE_DBG_COUNT(4);
                     const uint64_t e = ascii_digit_run_end(s, pos, pe);
                     const uint32_t d = state - S_D1 + 1u;                        // digits in the current piece so far
@@ -311,7 +326,7 @@ pretok_split_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
     const uint64_t cs = chunk * kSplitChunk;
     if (cs >= b.total_bytes) return;
     const uint64_t ce = (cs + kSplitChunk < b.total_bytes) ? cs + kSplitChunk : b.total_bytes;
-    split_thread<false>(b, vs, uc, s_fsm, s_ascii, piece_bits, status, fix_list, fix_cap, cs, ce, 0, 0);
+    split_thread<0>(b, vs, uc, s_fsm, s_ascii, piece_bits, status, fix_list, fix_cap, cs, ce, 0, 0);
 }
 
 // the threads of pretok_split_kernel that stopped in S_W_U at an upper-case letter: one thread each (grid-stride)
@@ -326,15 +341,19 @@ pretok_fixup_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
     __syncthreads();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const SplitFix f = fix_list[i];
-        split_thread<true>(b, vs, uc, s_fsm, s_ascii, piece_bits, status, nullptr, 0, 0, f.ce, f.pos, f.pidx);
+        split_thread<1>(b, vs, uc, s_fsm, s_ascii, piece_bits, status, nullptr, 0, 0, f.ce, f.pos, 0xFFFFFFFFu);
     }
 }
 
 
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+}  // namespace cfbpe
+#include "pretok_lanes.cuh"     // K1, second form: one lane per 16 bytes (uses split_thread<2> for long runs)
+namespace cfbpe {
+
 // ---------------------------------------------------------------------------------------
 // bit helpers shared by the K2 kernels
 // ---------------------------------------------------------------------------------------
-constexpr uint32_t kFull = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t lanemask_lt(uint32_t lane) { return (1u << lane) - 1u; }
 

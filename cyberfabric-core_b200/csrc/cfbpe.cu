@@ -25,6 +25,7 @@ static inline void prof_mark(ProfEvents* p, int idx, cudaStream_t s, bool begin)
 #define CFBPE_JOIN(main, aux, ev) do { if ((main) != (aux)) { cudaEventRecord((ev), (aux)); cudaStreamWaitEvent((main), (ev), 0); } } while (0)
 
 #include "pipeline.cuh"
+#include "pretok_ctx.h"
 #include "subbatch.h"
 #include "unicode_tables.h"
 #include "vocab.h"
@@ -100,6 +101,7 @@ struct cfbpe_ctx {
     uint8_t* d_uc2 = nullptr;
     uint8_t* d_ascii = nullptr;
     uint16_t* d_fsm = nullptr;
+    uint8_t* d_split_tables = nullptr;   // SplitTablesHost: class bytes, 16-wide transition tables, context automaton (pretok_ctx.h)
     UcTables uc{};
     VocabSlot vocabs[CFBPE_MAX_VOCABS];
     VocabSet vs{};
@@ -157,6 +159,10 @@ int install_blob(cfbpe_ctx* ctx, uint32_t vocab_id, std::vector<uint8_t>&& blob)
     std::memcpy(&v.hdr, v.h_blob.data(), sizeof(TablesHeader));
     v.loaded = true;
     ctx->vs.v[vocab_id] = make_view(v.d_blob, v.hdr);
+    ctx->vs.loaded_mask |= 1u << vocab_id;
+    // slots that are not loaded alias a loaded one: a bad vocabulary id handed in by a device-path caller is reported
+    // (DeviceStatus::bad_vocab -> CFBPE_ENOENT) instead of dereferencing a null table
+    for (uint32_t i = 0; i < CFBPE_MAX_VOCABS; ++i) if (!ctx->vocabs[i].loaded) ctx->vs.v[i] = ctx->vs.v[vocab_id];
     return CFBPE_OK;
 }
 
@@ -226,7 +232,8 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         cudaStream_t ck = fk ? ctx->front[fk] : cs;   // the short-piece kernels of sub-batch k: priority falls with k (earlier sub-batches finish, and download, first)
         Workspace w = ctx->ws;
         const uint64_t w0 = (o0 >> 5) + 4ull * k;
-        w.piece_bits += w0; w.tok_bits += w0;
+        w.piece_bits += w0; w.tok_bits += w0; w.pstart_bits += w0;
+        w.block_prompt += (o0 >> kPromptBlockShift) + 2ull * k;
         w.ids_by_pos += o0; w.lscratch.rank += o0; w.lscratch.aux0 += o0; w.lscratch.aux1 += o0;
         w.long_list += (o0 >> 5) + k;
         w.long_cap = static_cast<uint32_t>(len / 32 + 1);
@@ -234,8 +241,8 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         w.tile_counts += t0; w.tile_base += t0;
         w.status = ctx->d_status_arr + k;
         w.miss = slice_miss(ctx->ws.miss, o0, len, static_cast<uint32_t>(k));
-        w.fix_list += (o0 >> 6) + 2ull * k;
-        w.fix_cap = static_cast<uint32_t>(len / 64 + 2);
+        w.fix_list += (o0 >> 4) + 2ull * k;
+        w.fix_cap = static_cast<uint32_t>(len / 16 + 2);
         BatchView b{ctx->d_bytes + o0, ctx->d_offsets + p0 + k, vocab_ids ? ctx->d_vocab_ids + p0 : nullptr, nk, len};
         // split, long pieces and the back stage run on a top-priority stream of their own: the long-piece kernels are a latency
         // chain that uses little of the machine, so they start as early as possible and the short-piece kernels fill the rest
@@ -270,6 +277,7 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         const DeviceStatus st = ctx->h_status_arr[k];
         const uint32_t p0 = cut[k], p1 = cut[k + 1], nk = p1 - p0;
         if ((st.long_overflow || st.miss_overflow) && !err) err = fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
+        if (st.bad_vocab && !err) err = fail(ctx, CFBPE_ENOENT, "a prompt names a vocabulary that is not loaded");
         if (st.bad_utf8 && !err) err = fail(ctx, CFBPE_EILSEQ, "a prompt holds malformed UTF-8");
         const uint64_t base = st.tok_end - st.n_tokens;
         tok_total = st.tok_end;
@@ -334,6 +342,7 @@ int run_host(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const uint64_t* o
     CK(cudaStreamSynchronize(s));
     const DeviceStatus st = *ctx->h_status;
     if (st.long_overflow || st.miss_overflow) return fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
+    if (st.bad_vocab) return fail(ctx, CFBPE_ENOENT, "a prompt names a vocabulary that is not loaded");
     if (st.bad_utf8) return fail(ctx, CFBPE_EILSEQ, "a prompt holds malformed UTF-8");
     if (want_ids) {
         if (st.n_tokens > out_cap) {
@@ -405,7 +414,9 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
         ok = ok && dmalloc(&ctx->ws.miss.list[c], words) == cudaSuccess;
         ctx->ws.miss.cap[c] = static_cast<uint32_t>(words);
     }
-    ctx->ws.fix_cap = static_cast<uint32_t>(mb / 64 + 2 + 2 * kMaxPipeChunks);
+    ok = ok && dmalloc(&ctx->ws.pstart_bits, nw) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.block_prompt, (mb >> kPromptBlockShift) + 2 + 2 * kMaxPipeChunks) == cudaSuccess;
+    ctx->ws.fix_cap = static_cast<uint32_t>(mb / 16 + 2 + 2 * kMaxPipeChunks);
     ok = ok && dmalloc(&ctx->ws.fix_list, ctx->ws.fix_cap) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_dec_sums, mb / kDecodeTile + 2) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_dec_base, mb / kDecodeTile + 2) == cudaSuccess;
@@ -455,6 +466,12 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
         ok = ok && cudaMemcpy(ctx->d_ascii, ascii, 128, cudaMemcpyHostToDevice) == cudaSuccess;
         ok = ok && cudaMemcpy(ctx->d_fsm, fsm.data(), fsm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
     }
+    {
+        std::vector<SplitTablesHost> st(1);
+        build_split_tables(st.data());
+        ok = ok && dmalloc(&ctx->d_split_tables, sizeof(SplitTablesHost)) == cudaSuccess;
+        ok = ok && cudaMemcpy(ctx->d_split_tables, st.data(), sizeof(SplitTablesHost), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     ok = ok && cudaMemset(ctx->d_bytes, 0, mb + 256) == cudaSuccess;
     for (int k = 0; ok && k < CFBPE_NUM_KERNELS; ++k)
         ok = cudaEventCreate(&ctx->prof.ev[k][0]) == cudaSuccess && cudaEventCreate(&ctx->prof.ev[k][1]) == cudaSuccess;
@@ -466,7 +483,10 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
         cfbpe_destroy(ctx);
         return CFBPE_ENOMEM;
     }
-    ctx->uc = UcTables{ctx->d_uc1, ctx->d_uc2, ctx->d_ascii, ctx->d_fsm};
+    ctx->uc = UcTables{ctx->d_uc1, ctx->d_uc2, ctx->d_ascii, ctx->d_fsm,
+                       ctx->d_split_tables + offsetof(SplitTablesHost, cls256),
+                       reinterpret_cast<const uint16_t*>(ctx->d_split_tables + offsetof(SplitTablesHost, fsm16)),
+                       reinterpret_cast<const uint16_t*>(ctx->d_split_tables + offsetof(SplitTablesHost, ctx16))};
     if (const char* e = std::getenv("CFBPE_PIPE_CHUNK_BYTES")) { const uint64_t v = std::strtoull(e, nullptr, 10); if (v >= 1024) ctx->pipe_chunk = v; }
     if (const char* e = std::getenv("CFBPE_PIPE_MIN_BYTES")) { const uint64_t v = std::strtoull(e, nullptr, 10); if (v >= 1) ctx->pipe_min = v; }
     *out = ctx;
@@ -483,7 +503,7 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     cudaFree(ctx->ws.lscratch.rank); cudaFree(ctx->ws.lscratch.aux0); cudaFree(ctx->ws.lscratch.aux1);
     for (uint32_t c = 0; c < 3; ++c) cudaFree(ctx->ws.miss.list[c]);
     cudaFree(ctx->d_dec_sums); cudaFree(ctx->d_dec_base);
-    cudaFree(ctx->ws.fix_list);
+    cudaFree(ctx->ws.fix_list); cudaFree(ctx->ws.pstart_bits); cudaFree(ctx->ws.block_prompt); cudaFree(ctx->d_split_tables);
     cudaFree(ctx->ws.long_list); cudaFree(ctx->ws.tile_counts); cudaFree(ctx->ws.tile_base); cudaFree(ctx->ws.status);
     cudaFree(ctx->d_uc1); cudaFree(ctx->d_uc2); cudaFree(ctx->d_ascii); cudaFree(ctx->d_fsm);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -640,6 +660,7 @@ int cfbpe_encode_batch_device(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t*
     if (n_prompts > ctx->max_prompts || total_bytes > ctx->max_bytes) return fail(ctx, CFBPE_EINVAL, "batch exceeds the limits of this context");
     if (!d_offsets || !d_out_offsets || (total_bytes && !d_bytes)) return fail(ctx, CFBPE_EINVAL, "device pointer is NULL");
     if (!ctx->vocabs[0].loaded && !d_vocab_ids) return fail(ctx, CFBPE_ENOENT, "vocab 0 is not loaded");
+    if (!ctx->vs.loaded_mask) return fail(ctx, CFBPE_ENOENT, "no vocabulary is loaded");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // one workspace per context: a call on another stream waits (on the device) for the previous device-path call
@@ -662,6 +683,7 @@ int cfbpe_encode_batch_device(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t*
         const DeviceStatus st = *ctx->h_status;
         if (n_tokens) *n_tokens = st.n_tokens;
         if (st.long_overflow || st.miss_overflow) return fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
+        if (st.bad_vocab) return fail(ctx, CFBPE_ENOENT, "a prompt names a vocabulary that is not loaded");
         if (st.bad_utf8) return fail(ctx, CFBPE_EILSEQ, "a prompt holds malformed UTF-8");
         if (d_out_ids && st.n_tokens > out_cap) return fail(ctx, CFBPE_ENOSPC, "out_cap too small: need " + std::to_string(st.n_tokens) + " ids");
     }
@@ -675,6 +697,7 @@ int cfbpe_device_status(cfbpe_ctx* ctx, void* stream) {
     CK(cudaMemcpyAsync(ctx->h_status, ctx->ws.status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (ctx->h_status->long_overflow || ctx->h_status->miss_overflow) return fail(ctx, CFBPE_EIO, "internal: long-piece list overflow");
+    if (ctx->h_status->bad_vocab) return fail(ctx, CFBPE_ENOENT, "a prompt names a vocabulary that is not loaded");
     if (ctx->h_status->bad_utf8) return fail(ctx, CFBPE_EILSEQ, "a prompt holds malformed UTF-8");
     if (ctx->dev_want_ids && ctx->h_status->n_tokens > ctx->dev_out_cap)
         return fail(ctx, CFBPE_ENOSPC, "out_cap too small: need " + std::to_string(ctx->h_status->n_tokens) + " ids");

@@ -23,8 +23,10 @@ struct Workspace {
     uint64_t* tile_base;    // [n_tiles]
     DeviceStatus* status;
     MissLists miss;         // K2a -> K2m: short pieces that need the merge loop, by length class
-    SplitFix* fix_list;     // K1 -> fixup: threads that stopped in S_W_U   [total / 64 + 2]
+    SplitFix* fix_list;     // K1 -> fixup: walkers that stopped in an undecided state (at most one per 16-byte block)   [total / 16 + 2]
     uint32_t fix_cap;
+    uint32_t* pstart_bits;  // 1 bit per byte: a prompt starts here (and one at the end of the data)   [n_words + 2]
+    uint32_t* block_prompt; // the prompt that holds the first byte of every 512-byte block           [total / 512 + 2]
 };
 
 // the slice of the miss lists that belongs to a sub-batch of `len` bytes starting at byte o0 (k-th sub-batch)
@@ -73,9 +75,17 @@ inline void enqueue_split(const BatchView& b, const VocabSet& vs, const UcTables
     if (!b.total_bytes) return;
     CFBPE_ZERO(w.piece_bits, (nw + 2) * sizeof(uint32_t), stream);
     CFBPE_ZERO(w.tok_bits, (nw + 2) * sizeof(uint32_t), stream);
-    const uint64_t n_chunks = (b.total_bytes + kSplitChunk - 1) / kSplitChunk;
     CFBPE_MARK(prof, K_SPLIT, stream, true);
+#ifdef CFBPE_SPLIT_LEGACY      // A/B build: the first form of K1, one thread per 64-byte chunk
+    const uint64_t n_chunks = (b.total_bytes + kSplitChunk - 1) / kSplitChunk;
     CFBPE_LAUNCH(pretok_split_kernel, static_cast<unsigned>((n_chunks + 255) / 256), 256, stream, b, vs, uc, w.piece_bits, w.status, w.fix_list, w.fix_cap);
+#else
+    CFBPE_ZERO(w.pstart_bits, (nw + 2) * sizeof(uint32_t), stream);
+    CFBPE_LAUNCH(prompt_map_kernel, static_cast<unsigned>((static_cast<uint64_t>(b.n_prompts) + 1 + 255) / 256), 256, stream, b, vs, w.pstart_bits, w.block_prompt, w.status);
+    const uint64_t n_blocks16 = (b.total_bytes + 15) / 16;
+    CFBPE_LAUNCH(pretok_split16_kernel, static_cast<unsigned>((n_blocks16 + kSplitOwned - 1) / kSplitOwned), kSplitCta, stream,
+                 b, vs, uc, w.pstart_bits, w.block_prompt, w.piece_bits, w.status, w.fix_list, w.fix_cap);
+#endif
     CFBPE_LAUNCH(pretok_fixup_kernel, 296u, 256, stream, b, vs, uc, w.piece_bits, w.status, w.fix_list, w.fix_cap);   // almost always empty
     CFBPE_MARK(prof, K_SPLIT, stream, false);
     const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;

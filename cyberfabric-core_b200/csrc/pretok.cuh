@@ -24,6 +24,10 @@ struct UcTables {
     const uint8_t* stage2;   // [nblocks*128] nibbles
     const uint8_t* ascii_x;  // [128] extended class of each ASCII byte (pretok_fsm.h)
     const uint16_t* fsm;     // [kNumPatterns * kPretokTableSize] transition tables (pretok_fsm.h)
+    // tables of the lane-per-16-bytes split kernel (pretok_ctx.h)
+    const uint8_t* cls256;   // [256] byte -> class byte
+    const uint16_t* fsm16;   // [kNumPatterns * kFsm16Size] the transition tables with a row stride of 16
+    const uint16_t* ctx16;   // [2 * kCtx16Size] the context automaton, per casedness
 };
 
 // Text accessor: any type with operator[](uint64_t) -> byte.  A raw `const uint8_t*` works; K1 passes a view that serves

@@ -1,0 +1,301 @@
+// pretok_lanes.cuh -- K1, second form: the pre-tokenizer split with ONE LANE PER 16 BYTES.
+//
+// The first form (split_thread in bpe_kernels.cuh: a thread per 64-byte chunk, byte loads, a ~170-instruction loop body
+// per character, 15.5 of 32 lanes active -- profiles/ncu_summary_r01s.json) was bound by instruction issue at 2 % of the
+// HBM roofline.  Here a warp reads 512 contiguous bytes with one 16-byte load per lane, every lane classifies its 16
+// bytes in registers (class table in shared memory), and the automaton of pretok_fsm.h runs in LOCK-STEP over byte
+// indices: iteration k of the unrolled loop handles byte k of every lane's window, so all byte extraction is static and
+// the loop body is ~35 instructions with no divergence in the common (ASCII) case.
+//
+// How a lane knows its state without the lanes to its left: the context automaton of pretok_ctx.h.  A lane gets the exact
+// context at the start of its block from its left neighbour (the context after any 16 bytes depends on those bytes only),
+// walks its block, and at the first position the context table calls a sync point it adopts the state named there.  From
+// there it runs the split automaton to the end of its block AND ON into the next block (whose class bytes it has from its
+// right neighbour through shared memory) until it stands on the first sync point of that block -- the very position where
+// the right neighbour started, found through the same table lookup on the same context.  Every byte is covered by exactly
+// one walker.  A walker that crosses the whole next block without meeting a sync point is in a long run (one whitespace byte
+// repeated, digits, CJK under a cased pattern): the per-character walker of the first form takes over from its state
+// (bulk run handling, undecided states and the fix-up kernel stay as they were).
+//
+// A CTA of 256 threads owns 254 blocks; threads 0 and 255 classify the blocks on either side and do not walk (ghosts), so
+// neighbours never cross a CTA.  Prompt starts come as a bit array (prompt_map_kernel, one thread per prompt), so no lane
+// searches the offsets; multi-vocabulary batches find their prompt through one u32 per 512 bytes.
+#pragma once
+#include "pretok_ctx.h"
+
+namespace cfbpe {
+
+constexpr uint32_t kSplitCta = 256;                 // threads per CTA
+constexpr uint32_t kSplitOwned = kSplitCta - 2;     // blocks of 16 bytes a CTA owns
+constexpr uint32_t kPromptBlockShift = 9;           // block_prompt: one entry per 512 bytes
+constexpr uint32_t kNoRow = 0xFFFFu;
+
+__device__ __forceinline__ uint32_t bit_at(const uint32_t* __restrict__ bits, uint64_t pos) { return (bits[pos >> 5] >> (pos & 31)) & 1u; }
+
+// the prompt that holds byte pos (< total): block_prompt names the one holding the first byte of pos's 512-byte block
+__device__ __forceinline__ uint32_t prompt_at(const BatchView& b, const uint32_t* __restrict__ block_prompt, uint64_t pos) {
+    uint32_t p = block_prompt[pos >> kPromptBlockShift];
+    while (b.offsets[p + 1] <= pos) ++p;
+    return p;
+}
+
+// One thread per prompt (and one for the end of the data): the prompt-start bit array K1 reads instead of searching the
+// offsets, the prompt of every 512-byte block (multi-vocabulary batches), and the check of the vocabulary ids (a device-path
+// caller's ids were never seen by the host).
+__global__ void __launch_bounds__(256)
+prompt_map_kernel(BatchView b, VocabSet vs, uint32_t* __restrict__ pstart_bits, uint32_t* __restrict__ block_prompt, DeviceStatus* status) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i > b.n_prompts) return;
+    if (i == b.n_prompts) { atomicOr(&pstart_bits[b.total_bytes >> 5], 1u << (b.total_bytes & 31)); return; }   // "a prompt starts" at the end of the data
+    const uint64_t s = b.offsets[i], e = b.offsets[i + 1];
+    if (b.vocab_ids) {
+        const uint32_t v = b.vocab_ids[i];
+        if (v >= kMaxVocabs || !((vs.loaded_mask >> v) & 1u)) atomicOr(&status->bad_vocab, 1u);
+    }
+    if (e <= s) return;
+    atomicOr(&pstart_bits[s >> 5], 1u << (s & 31));
+    for (uint64_t blk = (s + (1u << kPromptBlockShift) - 1) >> kPromptBlockShift; (blk << kPromptBlockShift) < e; ++blk)
+        block_prompt[blk] = static_cast<uint32_t>(i);
+}
+
+// a block with bytes >= 0x80: decode every character that starts in it (class | (len - 1) << 4 replaces X_LEAD) and check
+// that every continuation byte belongs to a character -- a stray one is malformed UTF-8 (get_char checks the rest: lead
+// byte ranges, continuation bytes present, overlongs, surrogates, characters cut by a prompt end)
+__device__ __noinline__ uint4 classify_non_ascii(const uint8_t* __restrict__ s, uint64_t base, uint64_t total, const uint32_t* __restrict__ pstart_bits,
+                                                 const UcTables uc, uint4 cwv, DeviceStatus* status) {
+    uint32_t cw[4] = {cwv.x, cwv.y, cwv.z, cwv.w};
+    int bad_flag = 0;
+    int* bad = &bad_flag;
+    uint32_t need = 0;     // continuation bytes the block should start with: a character that began in the block before
+    for (uint32_t j = 1; j <= 3 && j <= base; ++j) {
+        if (bit_at(pstart_bits, base - j + 1)) break;          // a prompt starts between that byte and my block
+        const uint32_t c = s[base - j];
+        if ((c & 0xC0u) == 0x80u) continue;
+        if (c >= 0xC0u) { const uint32_t len = c < 0xE0u ? 2u : (c < 0xF0u ? 3u : 4u); if (len > j) need = len - j; }
+        break;
+    }
+    for (uint32_t k = 0; k < 16; ++k) {
+        const uint64_t pos = base + k;
+        if (pos >= total) break;
+        if (bit_at(pstart_bits, pos)) need = 0;
+        const uint32_t cb = (cw[k >> 2] >> (8u * (k & 3u))) & 0xFFu;
+        if (cb == X_CONT) { if (need) --need; else *bad = 1; }
+        else if (cb == X_LEAD) {
+            uint64_t pe = pos + 4 < total ? pos + 4 : total;     // the character may not run past the end of its prompt
+            for (uint32_t j = 3; j >= 1; --j) if (pos + j < total && bit_at(pstart_bits, pos + j)) pe = pos + j;
+            const Ch c = get_char(s, pos, pe, uc, bad);
+            const uint32_t len = c.len ? c.len : 1u;
+            const uint32_t ncb = c.cls | ((len - 1u) << 4);
+            cw[k >> 2] = (cw[k >> 2] & ~(0xFFu << (8u * (k & 3u)))) | (ncb << (8u * (k & 3u)));
+            need = len - 1u;
+        } else need = 0;
+    }
+    if (bad_flag) atomicOr(&status->bad_utf8, 1u);
+    return make_uint4(cw[0], cw[1], cw[2], cw[3]);
+}
+
+// the pattern of the prompt that holds byte pos (multi-vocabulary batches, at prompt starts only)
+// (pats: the pattern ids of the eight vocabulary slots, four bits each -- a VocabSet by reference would be copied to the stack)
+__device__ __noinline__ uint32_t pattern_at(const uint64_t* __restrict__ offsets, const uint8_t* __restrict__ vocab_ids, uint32_t pats,
+                                            const uint32_t* __restrict__ block_prompt, uint64_t pos) {
+    uint32_t p = block_prompt[pos >> kPromptBlockShift];
+    while (offsets[p + 1] <= pos) ++p;
+    return (pats >> (4u * (vocab_ids[p] & 7u))) & 15u;
+}
+
+// The rare actions of a step, out of line: an undecided state that has to be resolved (the fix-up kernel goes on from here),
+// a contraction that may start here, boundaries at remembered positions.
+// Returns {action bits (A_B_NOW cleared for a contraction suffix), bytes of the contraction, marks, 1 = this walker stops}.
+__device__ __noinline__ uint4 split_rare(uint32_t a, uint32_t k, uint64_t base, uint64_t total, const uint8_t* __restrict__ s,
+                                         const uint32_t* __restrict__ pstart_bits, DeviceStatus* status, SplitFix* fix_list, uint32_t fix_cap,
+                                         uint32_t alc, uint32_t last, uint32_t lbe) {
+    if (a & A_RESOLVE) {
+        const uint32_t q = atomicAdd(&status->fix_n, 1u);
+        if (q < fix_cap) { SplitFix f; f.pos = static_cast<uint32_t>(base + k); f.ce = static_cast<uint32_t>(base + 16); fix_list[q] = f; }
+        else atomicOr(&status->long_overflow, 1u);
+        return make_uint4(a, 0u, 0u, 1u);
+    }
+    uint32_t skip = 0, marks = 0;
+    if (a & A_CONTR) {
+        const uint64_t pos = base + k;
+        uint64_t pe = pos + 3 < total ? pos + 3 : total;          // a contraction does not cross the end of its prompt
+        if (pos + 2 < total && bit_at(pstart_bits, pos + 2)) pe = pos + 2;
+        if (pos + 1 < total && bit_at(pstart_bits, pos + 1)) pe = pos + 1;
+        skip = contraction_bytes(s, pos, pe);
+        if (skip && (a & A_CONTR_SUFFIX)) a &= ~A_B_NOW;          // the contraction belongs to the piece that just ended
+    }
+    if (a & A_EMIT_ALC) marks |= 1u << (alc & 31u);
+    if (a & A_EMIT_LAST) marks |= 1u << (last & 31u);
+    if (a & A_EMIT_LBE) marks |= 1u << (lbe & 31u);
+    return make_uint4(a, skip, marks, 0u);
+}
+
+__global__ void __launch_bounds__(kSplitCta)
+pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __restrict__ pstart_bits,
+                      const uint32_t* __restrict__ block_prompt, uint32_t* __restrict__ piece_bits, DeviceStatus* status,
+                      SplitFix* fix_list, uint32_t fix_cap) {
+    __shared__ uint16_t s_fsm[kNumPatterns * kFsm16Size];
+    __shared__ uint16_t s_ctx[2 * kCtx16Size];
+    __shared__ uint8_t s_cls[256];
+    __shared__ uint4 s_cw[kSplitCta];
+    __shared__ uint8_t s_end_ctx[kSplitCta];
+    for (uint32_t i = threadIdx.x; i < kNumPatterns * kFsm16Size; i += kSplitCta) s_fsm[i] = uc.fsm16[i];
+    for (uint32_t i = threadIdx.x; i < 2 * kCtx16Size; i += kSplitCta) s_ctx[i] = uc.ctx16[i];
+    s_cls[threadIdx.x] = uc.cls256[threadIdx.x];
+    __syncthreads();
+
+    const uint32_t t = threadIdx.x, lane = t & 31u;
+    const uint8_t* __restrict__ s = b.bytes;
+    const uint64_t total = b.total_bytes;
+    const bool multi = b.vocab_ids != nullptr;
+    const int64_t blk = static_cast<int64_t>(blockIdx.x) * kSplitOwned + static_cast<int64_t>(t) - 1;
+    const uint64_t base = blk > 0 ? static_cast<uint64_t>(blk) * 16u : 0u;
+    const bool have = blk >= 0 && base < total;
+    const bool owner = have && t >= 1 && t <= kSplitOwned;
+
+    // ---- my 16 bytes -> 16 class bytes
+    uint32_t cw[4] = {0, 0, 0, 0};
+    uint32_t P = 0;                 // prompt-start bits of [base, base + 32)
+    uint32_t pat = vs.v[0].pattern_id;
+    uint32_t pats = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < kMaxVocabs; ++i) pats |= (vs.v[i].pattern_id & 15u) << (4u * i);
+    bool nonascii = false;
+    if (have) {
+        const uint4 w = *reinterpret_cast<const uint4*>(s + base);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+            cw[j] = s_cls[ww[j] & 0xFFu] | (static_cast<uint32_t>(s_cls[(ww[j] >> 8) & 0xFFu]) << 8) |
+                    (static_cast<uint32_t>(s_cls[(ww[j] >> 16) & 0xFFu]) << 16) | (static_cast<uint32_t>(s_cls[ww[j] >> 24]) << 24);
+        const uint64_t wi = base >> 5;
+        P = (base & 16u) ? ((pstart_bits[wi] >> 16) | (pstart_bits[wi + 1] << 16)) : pstart_bits[wi];
+        nonascii = ((w.x | w.y | w.z | w.w) & 0x80808080u) != 0u;
+        if (nonascii) {
+            const uint4 r = classify_non_ascii(s, base, total, pstart_bits, uc, make_uint4(cw[0], cw[1], cw[2], cw[3]), status);
+            cw[0] = r.x; cw[1] = r.y; cw[2] = r.z; cw[3] = r.w;
+        }
+        if (multi) pat = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, base);
+    }
+    // ---- the exact context at the end of my block: the context automaton over its last three characters
+    uint32_t endc = kCtxStart;
+    if (have) {
+        uint32_t cased = pat & 1u;
+        auto ctx_step = [&](uint32_t k) {
+            if ((P >> k) & 1u) {
+                endc = kCtxStart;
+                if (multi && base + k < total) cased = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, base + k) & 1u;
+            }
+            const uint32_t x = (cw[k >> 2] >> (8u * (k & 3u))) & 15u;
+            endc = s_ctx[cased * kCtx16Size + (endc << 4) + x] & 0xFFu;
+        };
+        if (!nonascii) { ctx_step(13); ctx_step(14); ctx_step(15); }       // three ASCII bytes are three characters
+        else {                                                              // twelve bytes hold at least three characters
+#pragma unroll
+            for (uint32_t k = 4; k < 16; ++k) ctx_step(k);
+        }
+    }
+    s_cw[t] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+    s_end_ctx[t] = static_cast<uint8_t>(endc);
+    __syncthreads();
+
+    // ---- walk: from my first sync point to the first sync point of the next block.  Four bytes (one class word) per trip of
+    //      the loop, the eight words of the window in a shift register: all byte extraction is static, and the body is small
+    //      enough to stay in the instruction cache (fully unrolled, with the rare paths inline, it was 12 000 instructions)
+    uint32_t mine = 0;              // bit k: a piece starts at base + k (every mark of the 32 steps lies inside the window: a remembered
+                                    // position is emitted at a later character than the one that set it)
+    bool done = !owner;
+    uint32_t srow = kNoRow, ctx = kCtxStart, alc = 0, last = 0, lbe = 0, skip_to = 0;
+    uint32_t w0 = cw[0], w1 = cw[1], w2 = cw[2], w3 = cw[3], w4 = 0, w5 = 0, w6 = 0, w7 = 0;
+    if (owner) {
+        const uint4 nx = s_cw[t + 1];
+        w4 = nx.x; w5 = nx.y; w6 = nx.z; w7 = nx.w;
+        ctx = s_end_ctx[t - 1];
+    }
+    const uint16_t* tab = s_fsm + pat * kFsm16Size;
+    const uint16_t* ctab = s_ctx + (pat & 1u) * kCtx16Size;
+#pragma unroll 1
+    for (uint32_t j = 0; j < 8; ++j) {
+        if (j == 4 && srow == kNoRow) done = true;             // no sync point in my own block: the walker from the left covers it
+        if (j >= 4 && __all_sync(kFull, done)) break;
+        const uint32_t word = w0;
+        w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7;
+        const uint32_t Pw = (P >> (4u * j)) & 15u;
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {
+            // the common path is straight-line code (selects, no branches): 32 lanes in 32 different situations execute it together
+            const uint32_t k = 4u * j + i;
+            const uint32_t cb = (word >> (8u * i)) & 0xFFu;
+            const uint32_t x = cb & 15u;
+            if (((Pw >> i) & 1u) && !done) {    // a prompt starts here (or the data ends): the prompt before it ends.  Rare.
+                if (srow != kNoRow) {
+                    const uint32_t a = tab[srow + X_EOT];
+                    if (a & (A_RESOLVE | A_EMIT_ALC | A_EMIT_LAST | A_EMIT_LBE)) {
+                        const uint4 r = split_rare(a & ~A_CONTR, k, base, total, s, pstart_bits, status, fix_list, fix_cap, alc, last, lbe);
+                        mine |= r.z;
+                        done = r.w != 0u;
+                    }
+                }
+                if (k >= 16 || base + k >= total) done = true;          // the owner of that block starts there
+                if (!done) {
+                    srow = S_START << 4; ctx = kCtxStart; skip_to = 0;
+                    if (multi) {
+                        pat = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, base + k);
+                        tab = s_fsm + pat * kFsm16Size;
+                        ctab = s_ctx + (pat & 1u) * kCtx16Size;
+                    }
+                }
+            }
+            // context automaton: a continuation byte (class X_CONT) leaves the context as it is and is never a sync point
+            const uint32_t c = ctab[(ctx << 4) + x];
+            ctx = c & 0xFFu;
+            const uint32_t sy = c >> 8;
+            const bool synced = srow != kNoRow;
+            // this byte is a character of mine: I am walking (or this is my first sync point), and it is not inside a contraction taken whole
+            const bool mine_now = !done && x != X_CONT && k >= skip_to && (synced || sy != kNoSync);
+            const uint32_t row = mine_now ? (synced ? srow : (sy << 4)) : 0u;
+            uint32_t a = tab[row + x];
+            uint32_t skip = 0;
+            if (mine_now && (a & (A_RESOLVE | A_CONTR | A_EMIT_ALC | A_EMIT_LAST | A_EMIT_LBE))) {      // rare
+                const uint4 r = split_rare(a, k, base, total, s, pstart_bits, status, fix_list, fix_cap, alc, last, lbe);
+                a = r.x; skip = r.y; mine |= r.z;
+                done = r.w != 0u;
+            }
+            const bool hand = k >= 16 && sy != kNoSync;                  // hand-over: the next block's owner started exactly here
+            const bool step = mine_now && !hand && !done;
+            done = done || (mine_now && hand);
+            const uint32_t len = (cb >> 4) + 1u;
+            mine |= step ? (((a >> 5) & 1u) << k) : 0u;                  // A_B_NOW
+            alc = (step && (a & A_SET_ALC)) ? k + len : alc;
+            last = (step && (a & A_SET_LAST)) ? k : last;
+            lbe = (step && (a & A_SET_LBE)) ? k + len : lbe;
+            skip_to = (step && skip) ? k + skip : skip_to;
+            srow = step ? (skip ? (S_START << 4) : ((a & A_STATE_MASK) << 4)) : srow;
+        }
+    }
+    // ---- a walker that crossed the whole next block: the per-character walker goes on from its state
+    if (!done) {
+        uint64_t pos = base + (skip_to > 32u ? skip_to : 32u);
+        while (pos < total && (s[pos] & 0xC0u) == 0x80u) ++pos;          // byte 32 may lie inside the character that began at byte 29..31
+        split_thread<2, 16, kFsm16Size>(b, vs, uc, s_fsm, s_cls, piece_bits, status, fix_list, fix_cap, 0, pos, pos, 0xFFFFFFFFu,
+                                        skip_to > 32u ? static_cast<uint32_t>(S_START) : (srow >> 4), base + alc, base + last, base + lbe);
+    }
+
+    // ---- flags out: my 16 bits + what the lane to my left marked in my block; two lanes share a 32-bit word
+    uint32_t v = mine & 0xFFFFu;
+    const uint32_t spill = mine >> 16;
+    const uint32_t incoming = __shfl_up_sync(kFull, spill, 1);
+    if (lane) v |= incoming;
+    const uint32_t nv = __shfl_down_sync(kFull, v, 1);
+    if (blk >= 0) {
+        const uint64_t wi = base >> 5;
+        if (lane & 1u) {            // even block: low half; the odd block to my right is lane + 1 (or, for lane 31, my own spill)
+            const uint32_t word = v | ((lane == 31u ? spill : nv) << 16);
+            if (word) atomicOr(&piece_bits[wi], word);
+        } else if (lane == 0u) {    // odd block whose partner sits in the warp before
+            if (v) atomicOr(&piece_bits[wi], v << 16);
+        }
+    }
+}
+
+}  // namespace cfbpe

@@ -103,7 +103,7 @@ CFBPE_HD uint32_t sync_state(const Txt& s, uint64_t pos, uint64_t ps, uint64_t p
 // The automaton's real state (and lbe) before pos, for a thread in S_W_U / S_W_V that has to know: walk left to the nearest
 // position whose state the class rules give outright (or the prompt start), then run the automaton forward to pos without
 // emitting anything.  O(distance), and rare: an upper-case letter inside a run of CJK-like letters.
-template <typename Txt>
+template <uint32_t kRow = X_COUNT, typename Txt>
 CFBPE_HD uint32_t exact_state_before(const Txt& s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc, const uint16_t* tab, bool cased,
                                      uint64_t* lbe_out = nullptr) {
     uint64_t q = pos, lbe = 0;
@@ -117,7 +117,7 @@ CFBPE_HD uint32_t exact_state_before(const Txt& s, uint64_t pos, uint64_t ps, ui
     while (q < pos) {
         int bad = 0;
         const Ch c = get_char(s, q, pe, uc, &bad);
-        const uint32_t a = tab[state * X_COUNT + ext_class(c)];
+        const uint32_t a = tab[state * kRow + ext_class(c)];
         if (a & A_CONTR) {
             const uint32_t skip = contraction_bytes(s, q, pe);
             if (skip) { state = S_START; q += skip; continue; }
@@ -135,7 +135,7 @@ CFBPE_HD uint32_t exact_state_before(const Txt& s, uint64_t pos, uint64_t ps, ui
 //   upper-case run:  W_X0 unless a both-sets character stands in front of it (then the long way)
 //   both-sets run:   W_Y if a lower-case letter stands in front of it -- unless an apostrophe one or two characters further
 //                    left may make that letter a contraction suffix (then the long way); W_XB0 (lbe = pos) otherwise
-template <typename Txt>
+template <uint32_t kRow = X_COUNT, typename Txt>
 CFBPE_HD uint32_t resolve_word_state(const Txt& s, uint64_t pos, uint64_t ps, uint64_t pe, const UcTables& uc, const uint16_t* tab,
                                      uint64_t* lbe_out) {
     uint64_t q = pos;
@@ -151,7 +151,7 @@ CFBPE_HD uint32_t resolve_word_state(const Txt& s, uint64_t pos, uint64_t ps, ui
             q -= c.len;
         }
         if (x != X_LO && x != X_M) { *lbe_out = 0; return S_W_X0; }
-        return exact_state_before(s, pos, ps, pe, uc, tab, true, lbe_out);
+        return exact_state_before<kRow>(s, pos, ps, pe, uc, tab, true, lbe_out);
     }
     while (x == X_LO || x == X_M) {
         q -= c.len;
@@ -165,10 +165,10 @@ CFBPE_HD uint32_t resolve_word_state(const Txt& s, uint64_t pos, uint64_t ps, ui
     if (t > ps) {
         const Ch p1 = get_prev_char(s, t, ps, pe, uc);
         const uint32_t x1 = ext_class(p1);
-        if (x1 == X_APOS) return exact_state_before(s, pos, ps, pe, uc, tab, true, lbe_out);
+        if (x1 == X_APOS) return exact_state_before<kRow>(s, pos, ps, pe, uc, tab, true, lbe_out);
         t -= p1.len;
         if (t > ps && x_is_letter(x1) && ext_class(get_prev_char(s, t, ps, pe, uc)) == X_APOS)
-            return exact_state_before(s, pos, ps, pe, uc, tab, true, lbe_out);
+            return exact_state_before<kRow>(s, pos, ps, pe, uc, tab, true, lbe_out);
     }
     return S_W_Y;
 }

@@ -188,10 +188,12 @@ template <typename T> inline T from_u64(uint64_t u) { T v; std::memcpy(&v, &u, s
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 struct uint4 { unsigned x, y, z, w; };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 #define threadIdx (cusim::B().cur->tid)
 #define blockIdx (cusim::B().bid)
 #define blockDim (cusim::B().bdim)

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../cyberfabric-core_b200/csrc/pipeline.cuh"
+#include "../../cyberfabric-core_b200/csrc/pretok_ctx.h"
 #include "../../cyberfabric-core_b200/csrc/subbatch.h"
 #include "../../cyberfabric-core_b200/csrc/unicode_tables.h"
 #include "../../cyberfabric-core_b200/csrc/vocab.h"
@@ -30,10 +31,12 @@ struct SimVocab {
 static UcTables uc_tables() {
     static uint16_t fsm[kNumPatterns * kPretokTableSize];
     static uint8_t ascii[128];
+    static SplitTablesHost st;
     static bool init = false;
-    if (!init) { build_pretok_tables(fsm); build_ascii_classes(ascii); init = true; }
-    return UcTables{cfbpe_uc_stage1, cfbpe_uc_stage2, ascii, fsm};
+    if (!init) { build_pretok_tables(fsm); build_ascii_classes(ascii); build_split_tables(&st); init = true; }
+    return UcTables{cfbpe_uc_stage1, cfbpe_uc_stage2, ascii, fsm, st.cls256, st.fsm16, st.ctx16};
 }
+extern "C" __attribute__((visibility("default"))) uint32_t sim_ctx_count(uint32_t cased) { uc_tables(); SplitTablesHost st; build_split_tables(&st); return st.n_ctx[cased & 1]; }
 
 extern "C" {
 
@@ -78,7 +81,9 @@ __attribute__((visibility("default"))) uint32_t sim_pair_lookup(void* vp, uint32
 }
 
 // K1 only: piece-start bits (n_words+2 words) for a packed batch; patterns[] per vocab id
-static unsigned long long fixups_seen = 0;
+static unsigned long long fixups_seen = 0, resumes_seen = 0;
+static int legacy_split = 0;
+__attribute__((visibility("default"))) void sim_use_legacy_split(int on) { legacy_split = on; }
 __attribute__((visibility("default"))) unsigned long long sim_split_fixups(int reset) { const unsigned long long v = fixups_seen; if (reset) fixups_seen = 0; return v; }
 __attribute__((visibility("default"))) int sim_split(const uint32_t* patterns, uint32_t n_patterns, uint32_t n_prompts,
                                                      const uint8_t* bytes, const uint64_t* offsets, const uint8_t* vocab_ids,
@@ -91,14 +96,24 @@ __attribute__((visibility("default"))) int sim_split(const uint32_t* patterns, u
     DeviceStatus st{};
     const uint64_t nw = n_flag_words(total);
     std::memset(piece_bits, 0, (nw + 2) * 4);
+    vs.loaded_mask = n_patterns >= 32 ? 0xFFFFFFFFu : ((1u << n_patterns) - 1u);
     if (total) {
-        const uint64_t n_chunks = (total + kSplitChunk - 1) / kSplitChunk;
         UcTables uc = uc_tables();
-        std::vector<SplitFix> fix(total / 64 + 2);
+        std::vector<SplitFix> fix(total / 16 + 2);
         const uint32_t fix_cap = static_cast<uint32_t>(fix.size());
-        cusim::launch(static_cast<unsigned>((n_chunks + 255) / 256), 256, [&] { pretok_split_kernel(b, vs, uc, piece_bits, &st, fix.data(), fix_cap); });
+        if (legacy_split) {
+            const uint64_t n_chunks = (total + kSplitChunk - 1) / kSplitChunk;
+            cusim::launch(static_cast<unsigned>((n_chunks + 255) / 256), 256, [&] { pretok_split_kernel(b, vs, uc, piece_bits, &st, fix.data(), fix_cap); });
+        } else {
+            std::vector<uint32_t> pstart(nw + 2), bprompt((total >> kPromptBlockShift) + 2);
+            cusim::launch(static_cast<unsigned>((static_cast<uint64_t>(n_prompts) + 1 + 255) / 256), 256, [&] { prompt_map_kernel(b, vs, pstart.data(), bprompt.data(), &st); });
+            const uint64_t n_blocks16 = (total + 15) / 16;
+            cusim::launch(static_cast<unsigned>((n_blocks16 + kSplitOwned - 1) / kSplitOwned), kSplitCta,
+                          [&] { pretok_split16_kernel(b, vs, uc, pstart.data(), bprompt.data(), piece_bits, &st, fix.data(), fix_cap); });
+        }
         cusim::launch(2u, 256, [&] { pretok_fixup_kernel(b, vs, uc, piece_bits, &st, fix.data(), fix_cap); });
         fixups_seen += st.fix_n;
+        resumes_seen += cfbpe::dbg_counters()[3] + cfbpe::dbg_counters()[4];
     }
     return st.bad_utf8 ? CFBPE_EILSEQ : 0;
 }
@@ -123,7 +138,7 @@ __attribute__((visibility("default"))) int sim_encode_batch(void* const* vocabs,
     std::vector<uint64_t> tile_base(nt + 1);
     std::vector<LongPiece> ll(total / 32 + 1);
     DeviceStatus st{};
-    std::vector<SplitFix> fix(total / 64 + 2);
+    std::vector<SplitFix> fix(total / 16 + 2);
     std::vector<uint32_t> miss[3];
     MissLists ml;
     for (uint32_t c = 0; c < 3; ++c) {
@@ -131,8 +146,11 @@ __attribute__((visibility("default"))) int sim_encode_batch(void* const* vocabs,
         ml.list[c] = miss[c].data();
         ml.cap[c] = static_cast<uint32_t>(miss[c].size());
     }
+    std::vector<uint32_t> pstart(nw + 2), bprompt((total >> kPromptBlockShift) + 2);
     Workspace w{piece_bits.data(), tok_bits.data(), ids.data(), LongScratch{rk.data(), nx.data(), pv.data()},
-                ll.data(), static_cast<uint32_t>(ll.size()), tile_counts.data(), tile_base.data(), &st, ml, fix.data(), static_cast<uint32_t>(fix.size())};
+                ll.data(), static_cast<uint32_t>(ll.size()), tile_counts.data(), tile_base.data(), &st, ml, fix.data(), static_cast<uint32_t>(fix.size()),
+                pstart.data(), bprompt.data()};
+    vs.loaded_mask = n_vocabs >= 32 ? 0xFFFFFFFFu : ((1u << n_vocabs) - 1u);
     int* prof = nullptr;
     enqueue_encode(b, vs, uc_tables(), w, out_ids, out_cap, out_offsets, out_counts, 4u, 0, 0, 0, 0, prof);
     if (n_long_out) *n_long_out = static_cast<uint64_t>(st.n_long) + st.n_big;
