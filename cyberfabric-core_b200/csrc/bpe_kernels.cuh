@@ -347,10 +347,6 @@ pretok_fixup_kernel(BatchView b, VocabSet vs, UcTables uc, uint32_t* __restrict_
 
 
 constexpr uint32_t kFull = 0xFFFFFFFFu;
-}  // namespace cfbpe
-#include "pretok_lanes.cuh"     // K1, second form: one lane per 16 bytes (uses split_thread<2> for long runs)
-namespace cfbpe {
-
 // ---------------------------------------------------------------------------------------
 // bit helpers shared by the K2 kernels
 // ---------------------------------------------------------------------------------------
@@ -1547,3 +1543,4 @@ __global__ void status_publish_kernel(const DeviceStatus* __restrict__ d, Device
 }
 
 }  // namespace cfbpe
+#include "pretok_lanes.cuh"     // K1, second form: one lane per 16 bytes (uses split_thread<2> for long runs, load16 for unaligned buffers)

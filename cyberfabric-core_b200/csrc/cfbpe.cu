@@ -223,7 +223,9 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
     for (int k = 0; k < nc; ++k) {
         const uint32_t p0 = cut[k], p1 = cut[k + 1], nk = p1 - p0;
         const uint64_t o0 = offsets[p0], len = offsets[p1] - o0;
-        if (len) CK(cudaMemcpyAsync(ctx->d_bytes + o0, bytes + o0, len, cudaMemcpyHostToDevice, hs));
+        // every sub-batch lands on a 16-byte boundary of the device buffer (K1 reads 16 bytes per lane with one load)
+        uint8_t* const d_sub = ctx->d_bytes + ((o0 + 15) & ~15ull) + 16ull * k;
+        if (len) CK(cudaMemcpyAsync(d_sub, bytes + o0, len, cudaMemcpyHostToDevice, hs));
         CK(cudaMemcpyAsync(ctx->d_offsets + p0 + k, ctx->h_offs_stage + p0 + k, (static_cast<uint64_t>(nk) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, hs));
         if (vocab_ids && nk) CK(cudaMemcpyAsync(ctx->d_vocab_ids + p0, vocab_ids + p0, nk, cudaMemcpyHostToDevice, hs));
         CK(cudaEventRecord(ctx->ev_h2d[k], hs));
@@ -243,7 +245,7 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         w.miss = slice_miss(ctx->ws.miss, o0, len, static_cast<uint32_t>(k));
         w.fix_list += (o0 >> 4) + 2ull * k;
         w.fix_cap = static_cast<uint32_t>(len / 16 + 2);
-        BatchView b{ctx->d_bytes + o0, ctx->d_offsets + p0 + k, vocab_ids ? ctx->d_vocab_ids + p0 : nullptr, nk, len};
+        BatchView b{d_sub, ctx->d_offsets + p0 + k, vocab_ids ? ctx->d_vocab_ids + p0 : nullptr, nk, len};
         // split, long pieces and the back stage run on a top-priority stream of their own: the long-piece kernels are a latency
         // chain that uses little of the machine, so they start as early as possible and the short-piece kernels fill the rest
         cudaStream_t ss = ctx->side[k % kSideStreams];
@@ -395,7 +397,8 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     cudaDeviceGetStreamPriorityRange(&prio_lo0, &prio_hi0);
     bool ok = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi0) == cudaSuccess;   // front stream of sub-batch 0
     ok = ok && cudaFuncSetAttribute(bpe_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kListSmemBytes)) == cudaSuccess;
-    ok = ok && dmalloc(&ctx->d_bytes, mb + 256) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(pretok_split16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kNumPatterns * kProdTableBytes)) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->d_bytes, mb + 256 + 16 * (kMaxPipeChunks + 1)) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_offsets, mp + 1 + kMaxPipeChunks) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_vocab_ids, mp + 1) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_out_ids, mb + 1) == cudaSuccess;
@@ -472,7 +475,7 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
         ok = ok && dmalloc(&ctx->d_split_tables, sizeof(SplitTablesHost)) == cudaSuccess;
         ok = ok && cudaMemcpy(ctx->d_split_tables, st.data(), sizeof(SplitTablesHost), cudaMemcpyHostToDevice) == cudaSuccess;
     }
-    ok = ok && cudaMemset(ctx->d_bytes, 0, mb + 256) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_bytes, 0, mb + 256 + 16 * (kMaxPipeChunks + 1)) == cudaSuccess;
     for (int k = 0; ok && k < CFBPE_NUM_KERNELS; ++k)
         ok = cudaEventCreate(&ctx->prof.ev[k][0]) == cudaSuccess && cudaEventCreate(&ctx->prof.ev[k][1]) == cudaSuccess;
     for (int k = 0; ok && k < 2; ++k)
@@ -486,7 +489,11 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     ctx->uc = UcTables{ctx->d_uc1, ctx->d_uc2, ctx->d_ascii, ctx->d_fsm,
                        ctx->d_split_tables + offsetof(SplitTablesHost, cls256),
                        reinterpret_cast<const uint16_t*>(ctx->d_split_tables + offsetof(SplitTablesHost, fsm16)),
-                       reinterpret_cast<const uint16_t*>(ctx->d_split_tables + offsetof(SplitTablesHost, ctx16))};
+                       reinterpret_cast<const uint16_t*>(ctx->d_split_tables + offsetof(SplitTablesHost, ctx16)),
+                       reinterpret_cast<const uint64_t*>(ctx->d_split_tables + offsetof(SplitTablesHost, prod)),
+                       reinterpret_cast<const ProdInfo*>(ctx->d_split_tables + offsetof(SplitTablesHost, prod_info)),
+                       ctx->d_split_tables + offsetof(SplitTablesHost, prod_skip),
+                       ctx->d_split_tables + offsetof(SplitTablesHost, prod_start)};
     if (const char* e = std::getenv("CFBPE_PIPE_CHUNK_BYTES")) { const uint64_t v = std::strtoull(e, nullptr, 10); if (v >= 1024) ctx->pipe_chunk = v; }
     if (const char* e = std::getenv("CFBPE_PIPE_MIN_BYTES")) { const uint64_t v = std::strtoull(e, nullptr, 10); if (v >= 1) ctx->pipe_min = v; }
     *out = ctx;

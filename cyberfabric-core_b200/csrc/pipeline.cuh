@@ -69,7 +69,8 @@ inline uint32_t n_scan_tiles(uint64_t total_bytes) {
 //   short   K2: whole-piece lookups and in-lane merges (<= 32 B)   } may run on two streams
 //   back    flag_count, tile_scan (chained on the previous sub-batch's token total), emit, prompt offsets
 template <typename Stream, typename Prof>
-inline void enqueue_split(const BatchView& b, const VocabSet& vs, const UcTables& uc, const Workspace& w, Stream stream, Prof* prof) {
+inline void enqueue_split(const BatchView& b, const VocabSet& vs, const UcTables& uc, const Workspace& w, Stream stream, Prof* prof,
+                          uint32_t split_grid = 0) {
     const uint64_t nw = n_flag_words(b.total_bytes);
     CFBPE_ZERO(w.status, sizeof(DeviceStatus), stream);
     if (!b.total_bytes) return;
@@ -82,9 +83,14 @@ inline void enqueue_split(const BatchView& b, const VocabSet& vs, const UcTables
 #else
     CFBPE_ZERO(w.pstart_bits, (nw + 2) * sizeof(uint32_t), stream);
     CFBPE_LAUNCH(prompt_map_kernel, static_cast<unsigned>((static_cast<uint64_t>(b.n_prompts) + 1 + 255) / 256), 256, stream, b, vs, w.pstart_bits, w.block_prompt, w.status);
-    const uint64_t n_blocks16 = (b.total_bytes + 15) / 16;
-    CFBPE_LAUNCH(pretok_split16_kernel, static_cast<unsigned>((n_blocks16 + kSplitOwned - 1) / kSplitOwned), kSplitCta, stream,
-                 b, vs, uc, w.pstart_bits, w.block_prompt, w.piece_bits, w.status, w.fix_list, w.fix_cap);
+    {   // K1: persistent CTAs (the product tables are loaded once per CTA), tiles of kSplitOwned 16-byte blocks
+        const uint64_t n_blocks16 = (b.total_bytes + 15) / 16;
+        const uint32_t n_tiles = static_cast<uint32_t>((n_blocks16 + kSplitOwned - 1) / kSplitOwned);
+        const uint32_t n_tabs = b.vocab_ids ? kNumPatterns : 1u;
+        const uint32_t cap = split_grid ? split_grid : 592u;
+        CFBPE_LAUNCH_SMEM(pretok_split16_kernel, n_tiles < cap ? n_tiles : cap, kSplitCta, n_tabs * kProdTableBytes, stream,
+                          b, vs, uc, w.pstart_bits, w.block_prompt, w.piece_bits, w.status, w.fix_list, w.fix_cap, n_tabs, n_tiles);
+    }
 #endif
     CFBPE_LAUNCH(pretok_fixup_kernel, 296u, 256, stream, b, vs, uc, w.piece_bits, w.status, w.fix_list, w.fix_cap);   // almost always empty
     CFBPE_MARK(prof, K_SPLIT, stream, false);

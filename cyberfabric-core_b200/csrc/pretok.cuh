@@ -28,6 +28,10 @@ struct UcTables {
     const uint8_t* cls256;   // [256] byte -> class byte
     const uint16_t* fsm16;   // [kNumPatterns * kFsm16Size] the transition tables with a row stride of 16
     const uint16_t* ctx16;   // [2 * kCtx16Size] the context automaton, per casedness
+    const uint64_t* prod;    // [kNumPatterns * kProdMax * 16] the product automaton (split state x context)
+    const struct ProdInfo* prod_info;   // [kNumPatterns * kProdMax]
+    const uint8_t* prod_skip;           // [kNumPatterns * 2 * kCtxMax]
+    const uint8_t* prod_start;          // [kNumPatterns]
 };
 
 // Text accessor: any type with operator[](uint64_t) -> byte.  A raw `const uint8_t*` works; K1 passes a view that serves

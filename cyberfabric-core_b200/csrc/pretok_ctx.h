@@ -30,12 +30,39 @@ constexpr uint32_t kCtxMax = 64;                     // contexts per casedness (
 constexpr uint32_t kCtx16Size = kCtxMax * 16;        // u16 entries per casedness
 constexpr uint32_t kCtxStart = 0;                    // the context at a prompt start: (X_EOT, 0, 0)
 
+// ---- the PRODUCT automaton: split state x context in one table, so that a step of the walk is ONE lookup ----
+// A walker is in one of: DONE (state 0: nothing left to do, every entry leads back to it), NOSYNC(c) (states 1 + c: it has
+// not met a sync point yet, only the context moves), SKIPn(c) (inside a contraction that was taken whole: n characters
+// to go, then START), or (q, c) with q a state of pretok_fsm.h.  ~90 states per pattern are reachable.
+// Entry (two words, read with one 8-byte load), for state s and class x:
+//   lo  bits 14..7  next state (so lo & PE_NEXT_MASK is the byte offset of its row: 16 classes x 8 bytes = 128 bytes a row)
+//       bit 0 A_B_NOW   bits 1..3 SET_ALC | SET_LAST | SET_LBE   bit 4 the position is a sync point (hand-over in the second
+//       block)   bit 5 rare: a contraction may start here, or an undecided state has to be resolved (out-of-line path)
+//       bits 16..18 EMIT_ALC | EMIT_LAST | EMIT_LBE
+//   hi  byte mask of the remembered positions this step sets (0xFF per position: alc | last << 8 | lbe << 16)
+// Continuation bytes (class X_CONT) and the classes that never occur map every state to itself without flags.
+constexpr uint32_t kProdMax = 128;                   // states per pattern (the enumeration finds < 100: checked by the tests)
+constexpr uint32_t kProdRowBytes = 16 * 8;           // 16 classes x 8 bytes
+constexpr uint32_t kProdTableBytes = kProdMax * kProdRowBytes;      // 16 KB per pattern
+enum : uint32_t {
+    PE_B_NOW = 1u << 0, PE_SET_ALC = 1u << 1, PE_SET_LAST = 1u << 2, PE_SET_LBE = 1u << 3, PE_SYNC = 1u << 4, PE_RARE = 1u << 5,
+    PE_NEXT_SHIFT = 7, PE_NEXT_MASK = 0xFFu << 7, PE_EMIT_ALC = 1u << 16, PE_EMIT_LAST = 1u << 17, PE_EMIT_LBE = 1u << 18,
+    PE_EMIT_ANY = 7u << 16
+};
+enum : uint32_t { PQ_DONE = 0xFF, PQ_NOSYNC = 0xFE, PQ_SKIP1 = 0xFD, PQ_SKIP2 = 0xFC };    // pseudo split states in ProdInfo::q
+struct ProdInfo { uint8_t q, ctx; };                 // what a product state is made of
+
 struct SplitTablesHost {
     uint8_t cls256[256];
     uint16_t fsm16[kNumPatterns * kFsm16Size];
     uint16_t ctx16[2 * kCtx16Size];
     uint16_t ctxinfo[2 * kCtxMax];
     uint32_t n_ctx[2];
+    uint64_t prod[kNumPatterns * kProdMax * 16];     // [pattern][state * 16 + class]
+    ProdInfo prod_info[kNumPatterns * kProdMax];
+    uint8_t prod_skip[kNumPatterns * 2 * kCtxMax];   // [pattern][n - 1][context] -> state SKIPn(context)
+    uint8_t prod_start[kNumPatterns];                // the state (S_START, kCtxStart): where a prompt begins
+    uint32_t n_prod[kNumPatterns];
 };
 
 inline void build_split_tables(SplitTablesHost* t) {
@@ -72,6 +99,58 @@ inline void build_split_tables(SplitTablesHost* t) {
         }
         t->n_ctx[cased] = n;
         for (uint32_t c = 0; c < n; ++c) t->ctxinfo[cased * kCtxMax + c] = info[c];
+    }
+    // ---- product automaton, per pattern: breadth first from DONE, the NOSYNC states and the state of a prompt start
+    for (uint32_t pat = 0; pat < kNumPatterns; ++pat) {
+        const uint32_t cased = pat & 1u, nctx = t->n_ctx[cased];
+        const uint16_t* ctx = t->ctx16 + cased * kCtx16Size;
+        const uint16_t* fsm = t->fsm16 + pat * kFsm16Size;
+        ProdInfo* info = t->prod_info + pat * kProdMax;
+        uint64_t* tab = t->prod + static_cast<uint64_t>(pat) * kProdMax * 16;
+        uint32_t n = 0;
+        auto get = [&](uint32_t q, uint32_t c) -> uint32_t {
+            for (uint32_t i = 0; i < n; ++i) if (info[i].q == q && info[i].ctx == c) return i;
+            if (n >= kProdMax) return 0;                              // (never: checked by the tests through n_prod)
+            info[n].q = static_cast<uint8_t>(q); info[n].ctx = static_cast<uint8_t>(c);
+            return n++;
+        };
+        get(PQ_DONE, 0);
+        for (uint32_t c = 0; c < nctx; ++c) get(PQ_NOSYNC, c);       // states 1 + c
+        t->prod_start[pat] = static_cast<uint8_t>(get(S_START, kCtxStart));
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t q = info[i].q, c = info[i].ctx;
+            for (uint32_t x = 0; x < 16; ++x) {
+                uint64_t e = static_cast<uint64_t>(i) << PE_NEXT_SHIFT;                        // stay, no flags
+                if (q != PQ_DONE && x < X_EOT) {
+                    const uint32_t ce = ctx[c * 16 + x], c2 = ce & 0xFFu, sy = ce >> 8;
+                    uint32_t lo = sy != kNoSync ? static_cast<uint32_t>(PE_SYNC) : 0u, hi = 0;
+                    uint32_t q2 = q;
+                    if (q == PQ_NOSYNC && sy != kNoSync) q2 = sy;                             // the first sync point: the state follows from the context
+                    if (q2 == PQ_NOSYNC) lo |= get(PQ_NOSYNC, c2) << PE_NEXT_SHIFT;
+                    else if (q2 == PQ_SKIP2) lo = get(PQ_SKIP1, c2) << PE_NEXT_SHIFT;          // (no position inside a contraction is examined:
+                    else if (q2 == PQ_SKIP1) lo = get(S_START, c2) << PE_NEXT_SHIFT;           //  no hand-over there)
+                    else {
+                        const uint32_t a = fsm[q2 * 16 + x];
+                        if (a & A_B_NOW) lo |= PE_B_NOW;
+                        if (a & A_SET_ALC) { lo |= PE_SET_ALC; hi |= 0xFFu; }
+                        if (a & A_SET_LAST) { lo |= PE_SET_LAST; hi |= 0xFF00u; }
+                        if (a & A_SET_LBE) { lo |= PE_SET_LBE; hi |= 0xFF0000u; }
+                        if (a & A_EMIT_ALC) lo |= PE_EMIT_ALC;
+                        if (a & A_EMIT_LAST) lo |= PE_EMIT_LAST;
+                        if (a & A_EMIT_LBE) lo |= PE_EMIT_LBE;
+                        if (a & (A_CONTR | A_RESOLVE)) lo |= PE_RARE;
+                        if (a & A_CONTR) {                                                    // the states a contraction leads to
+                            t->prod_skip[(pat * 2 + 0) * kCtxMax + c2] = static_cast<uint8_t>(get(PQ_SKIP1, c2));
+                            t->prod_skip[(pat * 2 + 1) * kCtxMax + c2] = static_cast<uint8_t>(get(PQ_SKIP2, c2));
+                        }
+                        lo |= ((a & A_RESOLVE) ? 0u : get(a & A_STATE_MASK, c2)) << PE_NEXT_SHIFT;   // (resolve: the rare path stops the walker)
+                    }
+                    e = lo | (static_cast<uint64_t>(hi) << 32);
+                }
+                tab[i * 16 + x] = e;
+            }
+        }
+        t->n_prod[pat] = n;
     }
 }
 

@@ -103,52 +103,72 @@ __device__ __noinline__ uint32_t pattern_at(const uint64_t* __restrict__ offsets
     return (pats >> (4u * (vocab_ids[p] & 7u))) & 15u;
 }
 
-// The rare actions of a step, out of line: an undecided state that has to be resolved (the fix-up kernel goes on from here),
-// a contraction that may start here, boundaries at remembered positions.
-// Returns {action bits (A_B_NOW cleared for a contraction suffix), bytes of the contraction, marks, 1 = this walker stops}.
-__device__ __noinline__ uint4 split_rare(uint32_t a, uint32_t k, uint64_t base, uint64_t total, const uint8_t* __restrict__ s,
-                                         const uint32_t* __restrict__ pstart_bits, DeviceStatus* status, SplitFix* fix_list, uint32_t fix_cap,
-                                         uint32_t alc, uint32_t last, uint32_t lbe) {
+// The rare actions of a step, out of line: an undecided state that has to be resolved (the fix-up kernel goes on from here:
+// the walker stops), or a contraction that may start at this apostrophe.  Returns the entry to go on with: unchanged when
+// there is no contraction; else its next state replaced by SKIPn (and A_B_NOW cleared when the contraction is the suffix of
+// the word that just ended); 0 (= DONE, no flags) when the walker stops.
+__device__ __noinline__ uint32_t split_rare(uint32_t lo, uint32_t a, uint32_t k, uint64_t base, uint64_t total, const uint8_t* __restrict__ s,
+                                            const uint32_t* __restrict__ pstart_bits, DeviceStatus* status, SplitFix* fix_list, uint32_t fix_cap,
+                                            const uint8_t* skip_tab, uint32_t next_ctx) {
     if (a & A_RESOLVE) {
         const uint32_t q = atomicAdd(&status->fix_n, 1u);
         if (q < fix_cap) { SplitFix f; f.pos = static_cast<uint32_t>(base + k); f.ce = static_cast<uint32_t>(base + 16); fix_list[q] = f; }
         else atomicOr(&status->long_overflow, 1u);
-        return make_uint4(a, 0u, 0u, 1u);
+        return 0u;
     }
-    uint32_t skip = 0, marks = 0;
-    if (a & A_CONTR) {
-        const uint64_t pos = base + k;
-        uint64_t pe = pos + 3 < total ? pos + 3 : total;          // a contraction does not cross the end of its prompt
-        if (pos + 2 < total && bit_at(pstart_bits, pos + 2)) pe = pos + 2;
-        if (pos + 1 < total && bit_at(pstart_bits, pos + 1)) pe = pos + 1;
-        skip = contraction_bytes(s, pos, pe);
-        if (skip && (a & A_CONTR_SUFFIX)) a &= ~A_B_NOW;          // the contraction belongs to the piece that just ended
-    }
-    if (a & A_EMIT_ALC) marks |= 1u << (alc & 31u);
-    if (a & A_EMIT_LAST) marks |= 1u << (last & 31u);
-    if (a & A_EMIT_LBE) marks |= 1u << (lbe & 31u);
-    return make_uint4(a, skip, marks, 0u);
+    const uint64_t pos = base + k;
+    uint64_t pe = pos + 3 < total ? pos + 3 : total;          // a contraction does not cross the end of its prompt
+    if (pos + 2 < total && bit_at(pstart_bits, pos + 2)) pe = pos + 2;
+    if (pos + 1 < total && bit_at(pstart_bits, pos + 1)) pe = pos + 1;
+    const uint32_t skip = contraction_bytes(s, pos, pe);
+    if (!skip) return lo;
+    const uint32_t chars = (skip == 3 && s[pos + 1] < 0x80u) ? 2u : 1u;     // 'll 've 're: two characters follow the apostrophe; 's ... and U+017F: one
+    if (a & A_CONTR_SUFFIX) lo &= ~PE_B_NOW;                  // the contraction belongs to the piece that just ended
+    return (lo & ~PE_NEXT_MASK) | (static_cast<uint32_t>(skip_tab[(chars - 1u) * kCtxMax + next_ctx]) << PE_NEXT_SHIFT);
 }
 
+constexpr uint32_t kSplitStaticSmem = 0;   // (documentation: the tables below are static shared memory; the product tables are dynamic)
+
+// n_tabs: product tables in shared memory -- 1 (single-vocabulary batch: the table of pattern pat0) or kNumPatterns
 __global__ void __launch_bounds__(kSplitCta)
 pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __restrict__ pstart_bits,
                       const uint32_t* __restrict__ block_prompt, uint32_t* __restrict__ piece_bits, DeviceStatus* status,
-                      SplitFix* fix_list, uint32_t fix_cap) {
-    __shared__ uint16_t s_fsm[kNumPatterns * kFsm16Size];
+                      SplitFix* fix_list, uint32_t fix_cap, uint32_t n_tabs, uint32_t n_tiles) {
+    CFBPE_DYN_SMEM(s_dyn);                                   // n_tabs product tables of kProdTableBytes
+    __shared__ uint16_t s_fsm[kNumPatterns * kFsm16Size];    // for the end-of-prompt transition and the per-character walker
     __shared__ uint16_t s_ctx[2 * kCtx16Size];
     __shared__ uint8_t s_cls[256];
+    __shared__ ProdInfo s_info[kNumPatterns * kProdMax];
+    __shared__ uint8_t s_skip[kNumPatterns * 2 * kCtxMax];
+    __shared__ uint8_t s_start[kNumPatterns];
     __shared__ uint4 s_cw[kSplitCta];
     __shared__ uint8_t s_end_ctx[kSplitCta];
-    for (uint32_t i = threadIdx.x; i < kNumPatterns * kFsm16Size; i += kSplitCta) s_fsm[i] = uc.fsm16[i];
-    for (uint32_t i = threadIdx.x; i < 2 * kCtx16Size; i += kSplitCta) s_ctx[i] = uc.ctx16[i];
-    s_cls[threadIdx.x] = uc.cls256[threadIdx.x];
-    __syncthreads();
-
     const uint32_t t = threadIdx.x, lane = t & 31u;
+    const bool multi = b.vocab_ids != nullptr;
+    const uint32_t pat0 = vs.v[0].pattern_id;
+    {   // tables: once per CTA (a CTA walks many tiles)
+        const uint64_t* src = uc.prod + (n_tabs == 1 ? static_cast<uint64_t>(pat0) * kProdMax * 16 : 0);
+        uint64_t* dst = reinterpret_cast<uint64_t*>(s_dyn);
+        for (uint32_t i = t; i < n_tabs * kProdMax * 16; i += kSplitCta) dst[i] = src[i];
+        for (uint32_t i = t; i < kNumPatterns * kFsm16Size; i += kSplitCta) s_fsm[i] = uc.fsm16[i];
+        for (uint32_t i = t; i < 2 * kCtx16Size; i += kSplitCta) s_ctx[i] = uc.ctx16[i];
+        for (uint32_t i = t; i < kNumPatterns * kProdMax; i += kSplitCta) s_info[i] = uc.prod_info[i];
+        for (uint32_t i = t; i < kNumPatterns * 2 * kCtxMax; i += kSplitCta) s_skip[i] = uc.prod_skip[i];
+        if (t < kNumPatterns) s_start[t] = uc.prod_start[t];
+        s_cls[t] = uc.cls256[t];
+    }
+    __syncthreads();
     const uint8_t* __restrict__ s = b.bytes;
     const uint64_t total = b.total_bytes;
-    const bool multi = b.vocab_ids != nullptr;
-    const int64_t blk = static_cast<int64_t>(blockIdx.x) * kSplitOwned + static_cast<int64_t>(t) - 1;
+    const bool aligned = (reinterpret_cast<uintptr_t>(s) & 15u) == 0u;
+    uint32_t pats = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < kMaxVocabs; ++i) pats |= (vs.v[i].pattern_id & 15u) << (4u * i);
+    const uint8_t* const tabs = reinterpret_cast<const uint8_t*>(s_dyn);
+
+#pragma unroll 1
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t blk = static_cast<int64_t>(tile) * kSplitOwned + static_cast<int64_t>(t) - 1;
     const uint64_t base = blk > 0 ? static_cast<uint64_t>(blk) * 16u : 0u;
     const bool have = blk >= 0 && base < total;
     const bool owner = have && t >= 1 && t <= kSplitOwned;
@@ -156,21 +176,19 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
     // ---- my 16 bytes -> 16 class bytes
     uint32_t cw[4] = {0, 0, 0, 0};
     uint32_t P = 0;                 // prompt-start bits of [base, base + 32)
-    uint32_t pat = vs.v[0].pattern_id;
-    uint32_t pats = 0;
-#pragma unroll
-    for (uint32_t i = 0; i < kMaxVocabs; ++i) pats |= (vs.v[i].pattern_id & 15u) << (4u * i);
+    uint32_t pat = pat0;
     bool nonascii = false;
     if (have) {
-        const uint4 w = *reinterpret_cast<const uint4*>(s + base);
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        uint32_t ww[4];
+        if (aligned) { const uint4 w = *reinterpret_cast<const uint4*>(s + base); ww[0] = w.x; ww[1] = w.y; ww[2] = w.z; ww[3] = w.w; }
+        else load16(s + base, ww[0], ww[1], ww[2], ww[3]);       // a device-path caller's buffer that is not 16-byte aligned
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j)
             cw[j] = s_cls[ww[j] & 0xFFu] | (static_cast<uint32_t>(s_cls[(ww[j] >> 8) & 0xFFu]) << 8) |
                     (static_cast<uint32_t>(s_cls[(ww[j] >> 16) & 0xFFu]) << 16) | (static_cast<uint32_t>(s_cls[ww[j] >> 24]) << 24);
         const uint64_t wi = base >> 5;
         P = (base & 16u) ? ((pstart_bits[wi] >> 16) | (pstart_bits[wi + 1] << 16)) : pstart_bits[wi];
-        nonascii = ((w.x | w.y | w.z | w.w) & 0x80808080u) != 0u;
+        nonascii = ((ww[0] | ww[1] | ww[2] | ww[3]) & 0x80808080u) != 0u;
         if (nonascii) {
             const uint4 r = classify_non_ascii(s, base, total, pstart_bits, uc, make_uint4(cw[0], cw[1], cw[2], cw[3]), status);
             cw[0] = r.x; cw[1] = r.y; cw[2] = r.z; cw[3] = r.w;
@@ -195,90 +213,87 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
             for (uint32_t k = 4; k < 16; ++k) ctx_step(k);
         }
     }
+    __syncthreads();                                        // (the previous tile's walkers are done with s_cw)
     s_cw[t] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
     s_end_ctx[t] = static_cast<uint8_t>(endc);
     __syncthreads();
 
-    // ---- walk: from my first sync point to the first sync point of the next block.  Four bytes (one class word) per trip of
-    //      the loop, the eight words of the window in a shift register: all byte extraction is static, and the body is small
-    //      enough to stay in the instruction cache (fully unrolled, with the rare paths inline, it was 12 000 instructions)
+    // ---- walk: from my first sync point to the first sync point of the next block.  One lookup in the product table per
+    //      byte; four bytes (one class word) per trip of the loop, the eight words of the window in a shift register.
     uint32_t mine = 0;              // bit k: a piece starts at base + k (every mark of the 32 steps lies inside the window: a remembered
                                     // position is emitted at a later character than the one that set it)
-    bool done = !owner;
-    uint32_t srow = kNoRow, ctx = kCtxStart, alc = 0, last = 0, lbe = 0, skip_to = 0;
+    uint32_t rem = 0;               // remembered positions, relative to base: alc | last << 8 | lbe << 16
+    uint32_t st = 0;                // byte offset of my state's row in the product table; 0 = DONE
     uint32_t w0 = cw[0], w1 = cw[1], w2 = cw[2], w3 = cw[3], w4 = 0, w5 = 0, w6 = 0, w7 = 0;
+    uint32_t slot = n_tabs == 1 ? 0u : pat;
     if (owner) {
         const uint4 nx = s_cw[t + 1];
         w4 = nx.x; w5 = nx.y; w6 = nx.z; w7 = nx.w;
-        ctx = s_end_ctx[t - 1];
+        st = (1u + s_end_ctx[t - 1]) << PE_NEXT_SHIFT;     // NOSYNC(context at the end of the block to my left)
     }
-    const uint16_t* tab = s_fsm + pat * kFsm16Size;
-    const uint16_t* ctab = s_ctx + (pat & 1u) * kCtx16Size;
+    const uint8_t* tab = tabs + slot * kProdTableBytes;
 #pragma unroll 1
     for (uint32_t j = 0; j < 8; ++j) {
-        if (j == 4 && srow == kNoRow) done = true;             // no sync point in my own block: the walker from the left covers it
-        if (j >= 4 && __all_sync(kFull, done)) break;
+        if (j == 4 && s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)].q == PQ_NOSYNC) st = 0;   // no sync point in my own block: the walker from the left covers it
+        if (j >= 4 && __all_sync(kFull, st == 0u)) break;
         const uint32_t word = w0;
         w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7;
         const uint32_t Pw = (P >> (4u * j)) & 15u;
 #pragma unroll
         for (uint32_t i = 0; i < 4; ++i) {
-            // the common path is straight-line code (selects, no branches): 32 lanes in 32 different situations execute it together
             const uint32_t k = 4u * j + i;
+            if (((Pw >> i) & 1u) && st != 0u) {     // a prompt starts here (or the data ends): the prompt before it ends.  Rare.
+                const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
+                bool stop = k >= 16 || base + k >= total;                    // (the owner of that block starts there)
+                if (pi.q < S_COUNT) {
+                    const uint32_t a = s_fsm[pat * kFsm16Size + pi.q * 16 + X_EOT];
+                    if (a & A_EMIT_ALC) mine |= 1u << (rem & 31u);
+                    if (a & A_EMIT_LAST) mine |= 1u << ((rem >> 8) & 31u);
+                    if (a & A_EMIT_LBE) mine |= 1u << ((rem >> 16) & 31u);
+                    if (a & A_RESOLVE) { split_rare(0, a, k, base, total, s, pstart_bits, status, fix_list, fix_cap, s_skip, 0); stop = true; }
+                }
+                if (multi && !stop) {
+                    pat = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, base + k);
+                    tab = tabs + pat * kProdTableBytes;
+                }
+                st = stop ? 0u : (static_cast<uint32_t>(s_start[pat]) << PE_NEXT_SHIFT);
+            }
             const uint32_t cb = (word >> (8u * i)) & 0xFFu;
-            const uint32_t x = cb & 15u;
-            if (((Pw >> i) & 1u) && !done) {    // a prompt starts here (or the data ends): the prompt before it ends.  Rare.
-                if (srow != kNoRow) {
-                    const uint32_t a = tab[srow + X_EOT];
-                    if (a & (A_RESOLVE | A_EMIT_ALC | A_EMIT_LAST | A_EMIT_LBE)) {
-                        const uint4 r = split_rare(a & ~A_CONTR, k, base, total, s, pstart_bits, status, fix_list, fix_cap, alc, last, lbe);
-                        mine |= r.z;
-                        done = r.w != 0u;
-                    }
-                }
-                if (k >= 16 || base + k >= total) done = true;          // the owner of that block starts there
-                if (!done) {
-                    srow = S_START << 4; ctx = kCtxStart; skip_to = 0;
-                    if (multi) {
-                        pat = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, base + k);
-                        tab = s_fsm + pat * kFsm16Size;
-                        ctab = s_ctx + (pat & 1u) * kCtx16Size;
-                    }
+            const uint2 e = *reinterpret_cast<const uint2*>(tab + st + ((cb & 15u) << 3));
+            uint32_t lo = e.x, hi = e.y;
+            if (lo & (PE_EMIT_ANY | PE_RARE)) {      // boundaries at remembered positions (indentation, cased words); contractions
+                if (lo & PE_EMIT_ALC) mine |= 1u << (rem & 31u);
+                if (lo & PE_EMIT_LAST) mine |= 1u << ((rem >> 8) & 31u);
+                if (lo & PE_EMIT_LBE) mine |= 1u << ((rem >> 16) & 31u);
+                if (lo & PE_RARE) {
+                    const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
+                    const uint32_t q = pi.q == PQ_NOSYNC ? (s_ctx[(pat & 1u) * kCtx16Size + (pi.ctx << 4) + (cb & 15u)] >> 8) : pi.q;   // (first sync point: the state the context names)
+                    const uint32_t a = s_fsm[pat * kFsm16Size + q * 16 + (cb & 15u)];
+                    const uint32_t nctx = s_info[pat * kProdMax + ((lo & PE_NEXT_MASK) >> PE_NEXT_SHIFT)].ctx;
+                    lo = split_rare(lo, a, k, base, total, s, pstart_bits, status, fix_list, fix_cap, s_skip + pat * 2 * kCtxMax,
+                                    (a & A_RESOLVE) ? 0u : nctx);
+                    if (lo == 0u) hi = 0u;
                 }
             }
-            // context automaton: a continuation byte (class X_CONT) leaves the context as it is and is never a sync point
-            const uint32_t c = ctab[(ctx << 4) + x];
-            ctx = c & 0xFFu;
-            const uint32_t sy = c >> 8;
-            const bool synced = srow != kNoRow;
-            // this byte is a character of mine: I am walking (or this is my first sync point), and it is not inside a contraction taken whole
-            const bool mine_now = !done && x != X_CONT && k >= skip_to && (synced || sy != kNoSync);
-            const uint32_t row = mine_now ? (synced ? srow : (sy << 4)) : 0u;
-            uint32_t a = tab[row + x];
-            uint32_t skip = 0;
-            if (mine_now && (a & (A_RESOLVE | A_CONTR | A_EMIT_ALC | A_EMIT_LAST | A_EMIT_LBE))) {      // rare
-                const uint4 r = split_rare(a, k, base, total, s, pstart_bits, status, fix_list, fix_cap, alc, last, lbe);
-                a = r.x; skip = r.y; mine |= r.z;
-                done = r.w != 0u;
-            }
-            const bool hand = k >= 16 && sy != kNoSync;                  // hand-over: the next block's owner started exactly here
-            const bool step = mine_now && !hand && !done;
-            done = done || (mine_now && hand);
-            const uint32_t len = (cb >> 4) + 1u;
-            mine |= step ? (((a >> 5) & 1u) << k) : 0u;                  // A_B_NOW
-            alc = (step && (a & A_SET_ALC)) ? k + len : alc;
-            last = (step && (a & A_SET_LAST)) ? k : last;
-            lbe = (step && (a & A_SET_LBE)) ? k + len : lbe;
-            skip_to = (step && skip) ? k + skip : skip_to;
-            srow = step ? (skip ? (S_START << 4) : ((a & A_STATE_MASK) << 4)) : srow;
+            if (j >= 4 && (lo & PE_SYNC)) { lo = 0u; hi = 0u; }     // hand-over: the next block's owner started exactly here
+            mine |= (lo & PE_B_NOW) << k;
+            const uint32_t kk = k * 0x010101u + ((cb >> 4) + 1u) * 0x010001u;    // alc, lbe: the position after this character; last: this one
+            rem = (rem & ~hi) | (kk & hi);
+            st = lo & PE_NEXT_MASK;
         }
     }
     // ---- a walker that crossed the whole next block: the per-character walker goes on from its state
-    if (!done) {
-        uint64_t pos = base + (skip_to > 32u ? skip_to : 32u);
+    if (st != 0u) {
+        const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
+        uint64_t pos = base + 32u;
         while (pos < total && (s[pos] & 0xC0u) == 0x80u) ++pos;          // byte 32 may lie inside the character that began at byte 29..31
+        uint32_t q = pi.q;
+        if (q == PQ_SKIP1 || q == PQ_SKIP2) {                            // inside a contraction: step over what is left of it
+            for (uint32_t n = (q == PQ_SKIP2 ? 2u : 1u); n && pos < total; --n) { ++pos; while (pos < total && (s[pos] & 0xC0u) == 0x80u) ++pos; }
+            q = S_START;
+        }
         split_thread<2, 16, kFsm16Size>(b, vs, uc, s_fsm, s_cls, piece_bits, status, fix_list, fix_cap, 0, pos, pos, 0xFFFFFFFFu,
-                                        skip_to > 32u ? static_cast<uint32_t>(S_START) : (srow >> 4), base + alc, base + last, base + lbe);
+                                        q, base + (rem & 0xFFu), base + ((rem >> 8) & 0xFFu), base + ((rem >> 16) & 0xFFu));
     }
 
     // ---- flags out: my 16 bits + what the lane to my left marked in my block; two lanes share a 32-bit word
@@ -296,6 +311,7 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
             if (v) atomicOr(&piece_bits[wi], v << 16);
         }
     }
+    }   // tiles
 }
 
 }  // namespace cfbpe

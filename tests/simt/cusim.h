@@ -193,6 +193,7 @@ template <typename T> inline T from_u64(uint64_t u) { T v; std::memcpy(&v, &u, s
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 #define threadIdx (cusim::B().cur->tid)
 #define blockIdx (cusim::B().bid)

@@ -34,9 +34,10 @@ static UcTables uc_tables() {
     static SplitTablesHost st;
     static bool init = false;
     if (!init) { build_pretok_tables(fsm); build_ascii_classes(ascii); build_split_tables(&st); init = true; }
-    return UcTables{cfbpe_uc_stage1, cfbpe_uc_stage2, ascii, fsm, st.cls256, st.fsm16, st.ctx16};
+    return UcTables{cfbpe_uc_stage1, cfbpe_uc_stage2, ascii, fsm, st.cls256, st.fsm16, st.ctx16, st.prod, st.prod_info, st.prod_skip, st.prod_start};
 }
-extern "C" __attribute__((visibility("default"))) uint32_t sim_ctx_count(uint32_t cased) { uc_tables(); SplitTablesHost st; build_split_tables(&st); return st.n_ctx[cased & 1]; }
+extern "C" __attribute__((visibility("default"))) uint32_t sim_ctx_count(uint32_t cased) { static SplitTablesHost st; build_split_tables(&st); return st.n_ctx[cased & 1]; }
+extern "C" __attribute__((visibility("default"))) uint32_t sim_prod_count(uint32_t pat) { static SplitTablesHost st; build_split_tables(&st); return st.n_prod[pat & 3]; }
 
 extern "C" {
 
@@ -108,8 +109,10 @@ __attribute__((visibility("default"))) int sim_split(const uint32_t* patterns, u
             std::vector<uint32_t> pstart(nw + 2), bprompt((total >> kPromptBlockShift) + 2);
             cusim::launch(static_cast<unsigned>((static_cast<uint64_t>(n_prompts) + 1 + 255) / 256), 256, [&] { prompt_map_kernel(b, vs, pstart.data(), bprompt.data(), &st); });
             const uint64_t n_blocks16 = (total + 15) / 16;
-            cusim::launch(static_cast<unsigned>((n_blocks16 + kSplitOwned - 1) / kSplitOwned), kSplitCta,
-                          [&] { pretok_split16_kernel(b, vs, uc, pstart.data(), bprompt.data(), piece_bits, &st, fix.data(), fix_cap); });
+            const uint32_t n_tiles = static_cast<uint32_t>((n_blocks16 + kSplitOwned - 1) / kSplitOwned);
+            const uint32_t n_tabs = vocab_ids ? kNumPatterns : 1u;
+            cusim::launch(n_tiles < 3 ? n_tiles : 3u, kSplitCta,      // fewer CTAs than tiles: the persistent loop runs
+                          [&] { pretok_split16_kernel(b, vs, uc, pstart.data(), bprompt.data(), piece_bits, &st, fix.data(), fix_cap, n_tabs, n_tiles); });
         }
         cusim::launch(2u, 256, [&] { pretok_fixup_kernel(b, vs, uc, piece_bits, &st, fix.data(), fix_cap); });
         fixups_seen += st.fix_n;
