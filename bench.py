@@ -121,6 +121,34 @@ def cpu_encode_rate(data, offs, rv, threads, target_s=12.0):
     return b / t, "first %d prompts (%d bytes) of the same batch, %.1f s wall" % (k, b, t), t, b
 
 
+def tiktoken_context_rate(data, offs, rv, threads, target_s=6.0):
+    """context only (not the baseline of record): tiktoken 0.12.0 `encode_ordinary_batch(num_threads=threads)` on a prefix of the
+    same batch, with the same ranks and pattern.  Returns a dict, or None when tiktoken is not importable."""
+    try:
+        import base64
+        import tiktoken
+        from oracle import patterns as PT
+    except Exception:
+        return None
+    lines = rv.file_bytes.splitlines()
+    if rv.max_ranks:
+        lines = lines[:rv.max_ranks]
+    ranks = {base64.b64decode(l.split()[0]): i for i, l in enumerate(lines) if l.strip()}
+    enc = tiktoken.Encoding("bench", pat_str=PT.PATTERNS[rv.pattern_id], mergeable_ranks=ranks, special_tokens={})
+    n = len(offs) - 1
+
+    def run(k):
+        texts = [bytes(data[int(offs[i]):int(offs[i + 1])]).decode("utf-8") for i in range(k)]
+        t0 = time.perf_counter()
+        enc.encode_ordinary_batch(texts, num_threads=threads)
+        return time.perf_counter() - t0, int(offs[k])
+    t, b = run(min(n, 512))
+    k = int(min(n, max(512, 512 * target_s / max(t, 1e-3))))
+    t, b = run(k)
+    return {"value": b / t, "unit": UNIT, "cores": threads, "kind": "tiktoken 0.12.0 encode_ordinary_batch (python lists in and out)",
+            "sample": "first %d prompts (%d bytes), %.1f s wall" % (k, b, t)}
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation on the host cores.  The reference tree has no tokenizer to
     compile, so this is the oracle port (oracle/bpe_oracle.c) on every host thread."""
@@ -376,11 +404,12 @@ def main():
     path_alg = total + 4 * n_tokens + 21 * n
     kernels_ms = sum(kms.values())
 
-    cpu = None
+    cpu, cpu_ctx = None, None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         rate, sample, _, _ = cpu_encode_rate(data, offs, rv, threads)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        cpu_ctx = tiktoken_context_rate(data, offs, rv, threads)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -400,6 +429,7 @@ def main():
                      "path_algorithmic_bytes": path_alg,
                      "path_achieved_gbs": path_alg / (kernels_ms * 1e-3) / 1e9 if kernels_ms > 0 else 0.0},
         "cpu_baseline": cpu,
+        "cpu_baseline_context": cpu_ctx,
         "clocks": clocks,
     }
     emit_line(json.dumps(line))

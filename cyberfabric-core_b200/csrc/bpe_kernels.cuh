@@ -158,8 +158,14 @@ template <int kMode, uint32_t kRow = X_COUNT, uint32_t kTabSize = kPretokTableSi
 __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet& vs, UcTables uc, const uint16_t* s_fsm, const uint8_t* s_ascii,
                                              uint32_t* __restrict__ piece_bits, DeviceStatus* status, SplitFix* fix_list, uint32_t fix_cap,
                                              uint64_t cs, uint64_t ce, uint64_t fix_pos, uint32_t fix_pidx,
-                                             uint32_t state2 = 0, uint64_t alc2 = 0, uint64_t last2 = 0, uint64_t lbe2 = 0) {
+                                             uint32_t state2 = 0, uint64_t alc2 = 0, uint64_t last2 = 0, uint64_t lbe2 = 0, uint32_t pats2 = 0) {
     constexpr bool kFix = kMode != 0;       // resumed walkers mark with atomics and never search for a sync point
+    // (mode 2 gets the pattern ids of the vocabulary slots packed four bits each: a VocabSet passed down an out-of-line call would
+    //  be copied to the stack)
+    auto pat_of = [&](uint32_t p) -> uint32_t {
+        const uint32_t v = b.vocab_ids ? b.vocab_ids[p] : 0u;
+        return kMode == 2 ? ((pats2 >> (4u * (v & 7u))) & 15u) : vs.v[v].pattern_id;
+    };
     // (a shared-memory text tile with coalesced 16-byte loads was measured slower here: occupancy fell from 67 % to
     //  29 % and the accessor cost more than the L1 hits it replaced -- profiles/ncu_summary_r01k.json)
     const uint8_t* __restrict__ s = b.bytes;
@@ -173,7 +179,7 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
     uint64_t pos = kFix ? fix_pos : cs;
     uint32_t state = kNoSync;
     uint32_t prevx = X_EOT, nlet = 0, npun = 0;   // class of the previous character; consecutive letters (<= 3) / punctuation (<= 2) before pos
-    uint32_t pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
+    uint32_t pat = pat_of(pidx);
     uint64_t lbe_fix = 0;
     if (kMode == 1) {   // the real state at fix_pos (inside a prompt, after a letter), and the classes the hand-over looks at
         sync_state(s, pos, ps, pe, uc, true, &prevx, &nlet, &npun);
@@ -189,7 +195,7 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
     while (!kFix && pos < ce) {
         if (pos == pe) {  // step into the next non-empty prompt
             do { ++pidx; ps = pe; pe = b.offsets[pidx + 1]; } while (pe == ps);
-            pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
+            pat = pat_of(pidx);
         }
         prevx = X_EOT; nlet = 0; npun = 0;
         state = (pos == ps) ? static_cast<uint32_t>(S_START) : sync_state(s, pos, ps, pe, uc, (pat & 1u) != 0, &prevx, &nlet, &npun);
@@ -240,7 +246,7 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
             if (pos >= b.total_bytes) break;
             do { ++pidx; ps = pe; pe = b.offsets[pidx + 1]; } while (pe == ps);
             if (pos >= ce) break;            // the next prompt's first byte is a sync point of a later chunk
-            pat = vs.v[b.vocab_ids ? b.vocab_ids[pidx] : 0].pattern_id;
+            pat = pat_of(pidx);
             tab = s_fsm + pat * kTabSize;
             state = S_START;
             prevx = X_EOT; nlet = 0; npun = 0;

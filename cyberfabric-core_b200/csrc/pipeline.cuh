@@ -83,12 +83,13 @@ inline void enqueue_split(const BatchView& b, const VocabSet& vs, const UcTables
 #else
     CFBPE_ZERO(w.pstart_bits, (nw + 2) * sizeof(uint32_t), stream);
     CFBPE_LAUNCH(prompt_map_kernel, static_cast<unsigned>((static_cast<uint64_t>(b.n_prompts) + 1 + 255) / 256), 256, stream, b, vs, w.pstart_bits, w.block_prompt, w.status);
-    {   // K1: persistent CTAs (the product tables are loaded once per CTA), tiles of kSplitOwned 16-byte blocks
+    {   // K1: persistent CTAs (the product tables are loaded once per CTA); a warp takes tiles of kSplitWarpOwned 16-byte blocks
         const uint64_t n_blocks16 = (b.total_bytes + 15) / 16;
-        const uint32_t n_tiles = static_cast<uint32_t>((n_blocks16 + kSplitOwned - 1) / kSplitOwned);
+        const uint32_t n_tiles = static_cast<uint32_t>((n_blocks16 + kSplitWarpOwned - 1) / kSplitWarpOwned);
         const uint32_t n_tabs = b.vocab_ids ? kNumPatterns : 1u;
-        const uint32_t cap = split_grid ? split_grid : 592u;
-        CFBPE_LAUNCH_SMEM(pretok_split16_kernel, n_tiles < cap ? n_tiles : cap, kSplitCta, n_tabs * kProdTableBytes, stream,
+        const uint32_t cap = split_grid ? split_grid : 740u;      // 5 CTAs of 48 registers x 256 threads per SM
+        const uint32_t n_ctas = (n_tiles + kSplitCta / 32 - 1) / (kSplitCta / 32);
+        CFBPE_LAUNCH_SMEM(pretok_split16_kernel, n_ctas < cap ? n_ctas : cap, kSplitCta, n_tabs * kProdTableBytes, stream,
                           b, vs, uc, w.pstart_bits, w.block_prompt, w.piece_bits, w.status, w.fix_list, w.fix_cap, n_tabs, n_tiles);
     }
 #endif

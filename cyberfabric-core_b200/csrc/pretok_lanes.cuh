@@ -26,7 +26,6 @@
 namespace cfbpe {
 
 constexpr uint32_t kSplitCta = 256;                 // threads per CTA
-constexpr uint32_t kSplitOwned = kSplitCta - 2;     // blocks of 16 bytes a CTA owns
 constexpr uint32_t kPromptBlockShift = 9;           // block_prompt: one entry per 512 bytes
 constexpr uint32_t kNoRow = 0xFFFFu;
 
@@ -58,40 +57,60 @@ prompt_map_kernel(BatchView b, VocabSet vs, uint32_t* __restrict__ pstart_bits, 
         block_prompt[blk] = static_cast<uint32_t>(i);
 }
 
-// a block with bytes >= 0x80: decode every character that starts in it (class | (len - 1) << 4 replaces X_LEAD) and check
-// that every continuation byte belongs to a character -- a stray one is malformed UTF-8 (get_char checks the rest: lead
-// byte ranges, continuation bytes present, overlongs, surrogates, characters cut by a prompt end)
+// A block with bytes >= 0x80: decode every character that starts in it (class | (len - 1) << 4 replaces X_LEAD) and check
+// the UTF-8: lead byte ranges, continuation bytes present and in range, no overlongs, no surrogates, nothing above U+10FFFF,
+// no character cut by the end of its prompt, and every continuation byte inside a character (pretok.cuh::get_char, restated on
+// the block's bytes in registers: a 20-byte window -- the block and the four bytes after it -- shifted one byte per step).
+// P: prompt-start bits of [base, base + 32).
 __device__ __noinline__ uint4 classify_non_ascii(const uint8_t* __restrict__ s, uint64_t base, uint64_t total, const uint32_t* __restrict__ pstart_bits,
-                                                 const UcTables uc, uint4 cwv, DeviceStatus* status) {
-    uint32_t cw[4] = {cwv.x, cwv.y, cwv.z, cwv.w};
-    int bad_flag = 0;
-    int* bad = &bad_flag;
+                                                 const UcTables uc, uint4 raw, uint4 cwv, uint32_t P, DeviceStatus* status) {
+    uint32_t bad = 0;
     uint32_t need = 0;     // continuation bytes the block should start with: a character that began in the block before
-    for (uint32_t j = 1; j <= 3 && j <= base; ++j) {
-        if (bit_at(pstart_bits, base - j + 1)) break;          // a prompt starts between that byte and my block
-        const uint32_t c = s[base - j];
-        if ((c & 0xC0u) == 0x80u) continue;
-        if (c >= 0xC0u) { const uint32_t len = c < 0xE0u ? 2u : (c < 0xF0u ? 3u : 4u); if (len > j) need = len - j; }
-        break;
+    if ((raw.x & 0xC0u) == 0x80u && !(P & 1u)) {
+        for (uint32_t j = 1; j <= 3 && j <= base; ++j) {
+            if (j > 1 && bit_at(pstart_bits, base - j + 1)) break;        // a prompt starts between that byte and my block
+            const uint32_t c = s[base - j];
+            if ((c & 0xC0u) == 0x80u) continue;
+            if (c >= 0xC0u) { const uint32_t len = c < 0xE0u ? 2u : (c < 0xF0u ? 3u : 4u); if (len > j) need = len - j; }
+            break;
+        }
     }
+    uint64_t lo = raw.x | (static_cast<uint64_t>(raw.y) << 32), hi = raw.z | (static_cast<uint64_t>(raw.w) << 32);
+    uint64_t ext = load_u32_any(s + base + 16);      // (the buffer is readable 32 bytes past its end)
+    uint64_t clo = cwv.x | (static_cast<uint64_t>(cwv.y) << 32), chi = cwv.z | (static_cast<uint64_t>(cwv.w) << 32);
+    uint64_t out_lo = 0, out_hi = 0;
+    const uint32_t n = total - base < 16 ? static_cast<uint32_t>(total - base) : 16u;
     for (uint32_t k = 0; k < 16; ++k) {
-        const uint64_t pos = base + k;
-        if (pos >= total) break;
-        if (bit_at(pstart_bits, pos)) need = 0;
-        const uint32_t cb = (cw[k >> 2] >> (8u * (k & 3u))) & 0xFFu;
-        if (cb == X_CONT) { if (need) --need; else *bad = 1; }
-        else if (cb == X_LEAD) {
-            uint64_t pe = pos + 4 < total ? pos + 4 : total;     // the character may not run past the end of its prompt
-            for (uint32_t j = 3; j >= 1; --j) if (pos + j < total && bit_at(pstart_bits, pos + j)) pe = pos + j;
-            const Ch c = get_char(s, pos, pe, uc, bad);
-            const uint32_t len = c.len ? c.len : 1u;
-            const uint32_t ncb = c.cls | ((len - 1u) << 4);
-            cw[k >> 2] = (cw[k >> 2] & ~(0xFFu << (8u * (k & 3u)))) | (ncb << (8u * (k & 3u)));
-            need = len - 1u;
-        } else need = 0;
+        const uint32_t w = static_cast<uint32_t>(lo);                      // bytes k .. k+3
+        uint32_t cb = static_cast<uint32_t>(clo) & 0xFFu;
+        if (k < n) {
+            if ((P >> k) & 1u) need = 0;
+            if (cb == X_CONT) { if (need) --need; else bad = 1; }
+            else if (cb == X_LEAD) {
+                const uint32_t b0 = w & 0xFFu, b1 = (w >> 8) & 0xFFu, b2 = (w >> 16) & 0xFFu, b3 = w >> 24;
+                uint32_t len, cp;
+                bool ok;
+                if (b0 >= 0xC2u && b0 <= 0xDFu) { len = 2; cp = ((b0 & 0x1Fu) << 6) | (b1 & 0x3Fu); ok = (b1 & 0xC0u) == 0x80u; }
+                else if (b0 >= 0xE0u && b0 <= 0xEFu) {
+                    len = 3; cp = ((b0 & 0x0Fu) << 12) | ((b1 & 0x3Fu) << 6) | (b2 & 0x3Fu);
+                    ok = (b1 & 0xC0u) == 0x80u && (b2 & 0xC0u) == 0x80u && cp >= 0x800u && !(cp >= 0xD800u && cp <= 0xDFFFu);
+                } else if (b0 >= 0xF0u && b0 <= 0xF4u) {
+                    len = 4; cp = ((b0 & 0x07u) << 18) | ((b1 & 0x3Fu) << 12) | ((b2 & 0x3Fu) << 6) | (b3 & 0x3Fu);
+                    ok = (b1 & 0xC0u) == 0x80u && (b2 & 0xC0u) == 0x80u && (b3 & 0xC0u) == 0x80u && cp >= 0x10000u && cp <= 0x10FFFFu;
+                } else { len = 1; cp = 0; ok = false; }
+                // the character must end inside its prompt: no prompt start (nor the end of the data) among its continuation bytes
+                ok = ok && k + len <= n + (total - base > 16 ? 4u : 0u) && !((P >> (k + 1)) & ((1u << (len - 1u)) - 1u));
+                if (!ok) { bad = 1; len = 1; cb = X_OTHER; }           // (consumed as one byte of class OTHER, like get_char)
+                else cb = uc_class(uc, cp) | ((len - 1u) << 4);
+                need = len - 1u;
+            } else need = 0;
+        }
+        if (k < 8) out_lo |= static_cast<uint64_t>(cb) << (8u * k); else out_hi |= static_cast<uint64_t>(cb) << (8u * (k - 8u));
+        lo = (lo >> 8) | (hi << 56); hi = (hi >> 8) | (ext << 56); ext >>= 8;
+        clo = (clo >> 8) | (chi << 56); chi >>= 8;
     }
-    if (bad_flag) atomicOr(&status->bad_utf8, 1u);
-    return make_uint4(cw[0], cw[1], cw[2], cw[3]);
+    if (bad) atomicOr(&status->bad_utf8, 1u);
+    return make_uint4(static_cast<uint32_t>(out_lo), static_cast<uint32_t>(out_lo >> 32), static_cast<uint32_t>(out_hi), static_cast<uint32_t>(out_hi >> 32));
 }
 
 // the pattern of the prompt that holds byte pos (multi-vocabulary batches, at prompt starts only)
@@ -127,7 +146,38 @@ __device__ __noinline__ uint32_t split_rare(uint32_t lo, uint32_t a, uint32_t k,
     return (lo & ~PE_NEXT_MASK) | (static_cast<uint32_t>(skip_tab[(chars - 1u) * kCtxMax + next_ctx]) << PE_NEXT_SHIFT);
 }
 
-constexpr uint32_t kSplitStaticSmem = 0;   // (documentation: the tables below are static shared memory; the product tables are dynamic)
+// A prompt starts at byte k of the window (or the data ends there): the prompt before it ends.  Out of line (one lane in a
+// hundred meets one).  Returns {new state row, marks, new pattern}.
+__device__ __noinline__ uint4 split_prompt_start(uint32_t st, uint32_t pat, uint32_t k, uint32_t rem, uint64_t base, uint64_t total,
+                                                 const uint16_t* s_fsm, const ProdInfo* s_info, const uint8_t* s_start, const uint8_t* __restrict__ s,
+                                                 const uint32_t* __restrict__ pstart_bits, DeviceStatus* status, SplitFix* fix_list, uint32_t fix_cap,
+                                                 const uint64_t* __restrict__ offsets, const uint8_t* __restrict__ vocab_ids, uint32_t pats,
+                                                 const uint32_t* __restrict__ block_prompt) {
+    const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
+    bool stop = k >= 16 || base + k >= total;                    // (the owner of that block starts there)
+    uint32_t marks = 0;
+    if (pi.q < S_COUNT) {
+        const uint32_t a = s_fsm[pat * kFsm16Size + pi.q * 16 + X_EOT];
+        if (a & A_EMIT_ALC) marks |= 1u << (rem & 31u);
+        if (a & A_EMIT_LAST) marks |= 1u << ((rem >> 8) & 31u);
+        if (a & A_EMIT_LBE) marks |= 1u << ((rem >> 16) & 31u);
+        if (a & A_RESOLVE) { split_rare(0, a, k, base, total, s, pstart_bits, status, fix_list, fix_cap, nullptr, 0); stop = true; }
+    }
+    if (vocab_ids && !stop) pat = pattern_at(offsets, vocab_ids, pats, block_prompt, base + k);
+    return make_uint4(stop ? 0u : (static_cast<uint32_t>(s_start[pat]) << PE_NEXT_SHIFT), marks, pat, 0u);
+}
+
+// the per-character walker of the first form, out of line (it is large, and rare: long runs without a sync point)
+__device__ __noinline__ void split_resume(const BatchView b, uint32_t pats, const UcTables uc, const uint16_t* s_fsm, const uint8_t* s_cls,
+                                         uint32_t* __restrict__ piece_bits, DeviceStatus* status, SplitFix* fix_list, uint32_t fix_cap,
+                                         uint64_t pos, uint32_t pidx, uint32_t q, uint64_t alc, uint64_t last, uint64_t lbe) {
+    const VocabSet* none = nullptr;      // (mode 2 never reads it: the patterns come packed)
+    split_thread<2, 16, kFsm16Size>(b, *none, uc, s_fsm, s_cls, piece_bits, status, fix_list, fix_cap, 0, pos, pos, pidx, q, alc, last, lbe, pats);
+}
+
+constexpr uint32_t kSplitWarpOwned = 30;            // blocks of 16 bytes a WARP owns: lanes 1..30; lanes 0 and 31 classify the blocks on
+                                                    // either side and do not walk (ghosts), so neighbours are one shuffle away and no
+                                                    // warp ever waits for another (a CTA-wide exchange spent 39 % of the time in barriers)
 
 // n_tabs: product tables in shared memory -- 1 (single-vocabulary batch: the table of pattern pat0) or kNumPatterns
 __global__ void __launch_bounds__(kSplitCta)
@@ -141,12 +191,10 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
     __shared__ ProdInfo s_info[kNumPatterns * kProdMax];
     __shared__ uint8_t s_skip[kNumPatterns * 2 * kCtxMax];
     __shared__ uint8_t s_start[kNumPatterns];
-    __shared__ uint4 s_cw[kSplitCta];
-    __shared__ uint8_t s_end_ctx[kSplitCta];
     const uint32_t t = threadIdx.x, lane = t & 31u;
     const bool multi = b.vocab_ids != nullptr;
     const uint32_t pat0 = vs.v[0].pattern_id;
-    {   // tables: once per CTA (a CTA walks many tiles)
+    {   // tables: once per CTA (its warps walk many tiles)
         const uint64_t* src = uc.prod + (n_tabs == 1 ? static_cast<uint64_t>(pat0) * kProdMax * 16 : 0);
         uint64_t* dst = reinterpret_cast<uint64_t*>(s_dyn);
         for (uint32_t i = t; i < n_tabs * kProdMax * 16; i += kSplitCta) dst[i] = src[i];
@@ -165,152 +213,140 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
 #pragma unroll
     for (uint32_t i = 0; i < kMaxVocabs; ++i) pats |= (vs.v[i].pattern_id & 15u) << (4u * i);
     const uint8_t* const tabs = reinterpret_cast<const uint8_t*>(s_dyn);
+    const uint32_t warps_total = gridDim.x * (kSplitCta / 32u);
 
 #pragma unroll 1
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t blk = static_cast<int64_t>(tile) * kSplitOwned + static_cast<int64_t>(t) - 1;
-    const uint64_t base = blk > 0 ? static_cast<uint64_t>(blk) * 16u : 0u;
-    const bool have = blk >= 0 && base < total;
-    const bool owner = have && t >= 1 && t <= kSplitOwned;
+    for (uint32_t tile = blockIdx.x * (kSplitCta / 32u) + (t >> 5); tile < n_tiles; tile += warps_total) {
+        const int64_t blk = static_cast<int64_t>(tile) * kSplitWarpOwned + static_cast<int64_t>(lane) - 1;
+        const uint64_t base = blk > 0 ? static_cast<uint64_t>(blk) * 16u : 0u;
+        const bool have = blk >= 0 && base < total;
+        const bool owner = have && lane >= 1 && lane <= kSplitWarpOwned;
 
-    // ---- my 16 bytes -> 16 class bytes
-    uint32_t cw[4] = {0, 0, 0, 0};
-    uint32_t P = 0;                 // prompt-start bits of [base, base + 32)
-    uint32_t pat = pat0;
-    bool nonascii = false;
-    if (have) {
-        uint32_t ww[4];
-        if (aligned) { const uint4 w = *reinterpret_cast<const uint4*>(s + base); ww[0] = w.x; ww[1] = w.y; ww[2] = w.z; ww[3] = w.w; }
-        else load16(s + base, ww[0], ww[1], ww[2], ww[3]);       // a device-path caller's buffer that is not 16-byte aligned
+        // ---- my 16 bytes -> 16 class bytes
+        uint32_t cw[4] = {0, 0, 0, 0};
+        uint32_t P = 0;                 // prompt-start bits of [base, base + 32)
+        uint32_t pat = pat0;
+        bool nonascii = false;
+        if (have) {
+            uint32_t ww[4];
+            if (aligned) { const uint4 w = *reinterpret_cast<const uint4*>(s + base); ww[0] = w.x; ww[1] = w.y; ww[2] = w.z; ww[3] = w.w; }
+            else load16(s + base, ww[0], ww[1], ww[2], ww[3]);       // a device-path caller's buffer that is not 16-byte aligned
 #pragma unroll
-        for (uint32_t j = 0; j < 4; ++j)
-            cw[j] = s_cls[ww[j] & 0xFFu] | (static_cast<uint32_t>(s_cls[(ww[j] >> 8) & 0xFFu]) << 8) |
-                    (static_cast<uint32_t>(s_cls[(ww[j] >> 16) & 0xFFu]) << 16) | (static_cast<uint32_t>(s_cls[ww[j] >> 24]) << 24);
-        const uint64_t wi = base >> 5;
-        P = (base & 16u) ? ((pstart_bits[wi] >> 16) | (pstart_bits[wi + 1] << 16)) : pstart_bits[wi];
-        nonascii = ((ww[0] | ww[1] | ww[2] | ww[3]) & 0x80808080u) != 0u;
-        if (nonascii) {
-            const uint4 r = classify_non_ascii(s, base, total, pstart_bits, uc, make_uint4(cw[0], cw[1], cw[2], cw[3]), status);
-            cw[0] = r.x; cw[1] = r.y; cw[2] = r.z; cw[3] = r.w;
-        }
-        if (multi) pat = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, base);
-    }
-    // ---- the exact context at the end of my block: the context automaton over its last three characters
-    uint32_t endc = kCtxStart;
-    if (have) {
-        uint32_t cased = pat & 1u;
-        auto ctx_step = [&](uint32_t k) {
-            if ((P >> k) & 1u) {
-                endc = kCtxStart;
-                if (multi && base + k < total) cased = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, base + k) & 1u;
+            for (uint32_t j = 0; j < 4; ++j)
+                cw[j] = s_cls[ww[j] & 0xFFu] | (static_cast<uint32_t>(s_cls[(ww[j] >> 8) & 0xFFu]) << 8) |
+                        (static_cast<uint32_t>(s_cls[(ww[j] >> 16) & 0xFFu]) << 16) | (static_cast<uint32_t>(s_cls[ww[j] >> 24]) << 24);
+            const uint64_t wi = base >> 5;
+            P = (base & 16u) ? ((pstart_bits[wi] >> 16) | (pstart_bits[wi + 1] << 16)) : pstart_bits[wi];
+            nonascii = ((ww[0] | ww[1] | ww[2] | ww[3]) & 0x80808080u) != 0u;
+            if (nonascii) {
+                const uint4 r = classify_non_ascii(s, base, total, pstart_bits, uc, make_uint4(ww[0], ww[1], ww[2], ww[3]),
+                                                   make_uint4(cw[0], cw[1], cw[2], cw[3]), P, status);
+                cw[0] = r.x; cw[1] = r.y; cw[2] = r.z; cw[3] = r.w;
             }
-            const uint32_t x = (cw[k >> 2] >> (8u * (k & 3u))) & 15u;
-            endc = s_ctx[cased * kCtx16Size + (endc << 4) + x] & 0xFFu;
-        };
-        if (!nonascii) { ctx_step(13); ctx_step(14); ctx_step(15); }       // three ASCII bytes are three characters
-        else {                                                              // twelve bytes hold at least three characters
-#pragma unroll
-            for (uint32_t k = 4; k < 16; ++k) ctx_step(k);
+            if (multi) pat = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, base);
         }
-    }
-    __syncthreads();                                        // (the previous tile's walkers are done with s_cw)
-    s_cw[t] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
-    s_end_ctx[t] = static_cast<uint8_t>(endc);
-    __syncthreads();
-
-    // ---- walk: from my first sync point to the first sync point of the next block.  One lookup in the product table per
-    //      byte; four bytes (one class word) per trip of the loop, the eight words of the window in a shift register.
-    uint32_t mine = 0;              // bit k: a piece starts at base + k (every mark of the 32 steps lies inside the window: a remembered
-                                    // position is emitted at a later character than the one that set it)
-    uint32_t rem = 0;               // remembered positions, relative to base: alc | last << 8 | lbe << 16
-    uint32_t st = 0;                // byte offset of my state's row in the product table; 0 = DONE
-    uint32_t w0 = cw[0], w1 = cw[1], w2 = cw[2], w3 = cw[3], w4 = 0, w5 = 0, w6 = 0, w7 = 0;
-    uint32_t slot = n_tabs == 1 ? 0u : pat;
-    if (owner) {
-        const uint4 nx = s_cw[t + 1];
-        w4 = nx.x; w5 = nx.y; w6 = nx.z; w7 = nx.w;
-        st = (1u + s_end_ctx[t - 1]) << PE_NEXT_SHIFT;     // NOSYNC(context at the end of the block to my left)
-    }
-    const uint8_t* tab = tabs + slot * kProdTableBytes;
+        // ---- the exact context at the end of my block: the context automaton over its last three characters
+        uint32_t endc = kCtxStart;
+        if (have) {
+            uint32_t cased = pat & 1u;
+            // (a prompt of another casedness may have started before the bytes looked at)
+            if (multi && (P & 0xFFFFu)) { const uint64_t q = base + (nonascii ? 4u : 13u); if (q < total) cased = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, q) & 1u; }
+            auto ctx_step = [&](uint32_t k) {
+                if ((P >> k) & 1u) {
+                    endc = kCtxStart;
+                    if (multi && base + k < total) cased = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, base + k) & 1u;
+                }
+                const uint32_t x = (cw[k >> 2] >> (8u * (k & 3u))) & 15u;
+                endc = s_ctx[cased * kCtx16Size + (endc << 4) + x] & 0xFFu;
+            };
+            if (!nonascii) { ctx_step(13); ctx_step(14); ctx_step(15); }       // three ASCII bytes are three characters
+            else {                                                              // twelve bytes hold at least three characters
 #pragma unroll 1
-    for (uint32_t j = 0; j < 8; ++j) {
-        if (j == 4 && s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)].q == PQ_NOSYNC) st = 0;   // no sync point in my own block: the walker from the left covers it
-        if (j >= 4 && __all_sync(kFull, st == 0u)) break;
-        const uint32_t word = w0;
-        w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7;
-        const uint32_t Pw = (P >> (4u * j)) & 15u;
-#pragma unroll
-        for (uint32_t i = 0; i < 4; ++i) {
-            const uint32_t k = 4u * j + i;
-            if (((Pw >> i) & 1u) && st != 0u) {     // a prompt starts here (or the data ends): the prompt before it ends.  Rare.
-                const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
-                bool stop = k >= 16 || base + k >= total;                    // (the owner of that block starts there)
-                if (pi.q < S_COUNT) {
-                    const uint32_t a = s_fsm[pat * kFsm16Size + pi.q * 16 + X_EOT];
-                    if (a & A_EMIT_ALC) mine |= 1u << (rem & 31u);
-                    if (a & A_EMIT_LAST) mine |= 1u << ((rem >> 8) & 31u);
-                    if (a & A_EMIT_LBE) mine |= 1u << ((rem >> 16) & 31u);
-                    if (a & A_RESOLVE) { split_rare(0, a, k, base, total, s, pstart_bits, status, fix_list, fix_cap, s_skip, 0); stop = true; }
-                }
-                if (multi && !stop) {
-                    pat = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, base + k);
-                    tab = tabs + pat * kProdTableBytes;
-                }
-                st = stop ? 0u : (static_cast<uint32_t>(s_start[pat]) << PE_NEXT_SHIFT);
+                for (uint32_t k = 4; k < 16; ++k) ctx_step(k);
             }
-            const uint32_t cb = (word >> (8u * i)) & 0xFFu;
-            const uint2 e = *reinterpret_cast<const uint2*>(tab + st + ((cb & 15u) << 3));
-            uint32_t lo = e.x, hi = e.y;
-            if (lo & (PE_EMIT_ANY | PE_RARE)) {      // boundaries at remembered positions (indentation, cased words); contractions
-                if (lo & PE_EMIT_ALC) mine |= 1u << (rem & 31u);
-                if (lo & PE_EMIT_LAST) mine |= 1u << ((rem >> 8) & 31u);
-                if (lo & PE_EMIT_LBE) mine |= 1u << ((rem >> 16) & 31u);
-                if (lo & PE_RARE) {
-                    const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
-                    const uint32_t q = pi.q == PQ_NOSYNC ? (s_ctx[(pat & 1u) * kCtx16Size + (pi.ctx << 4) + (cb & 15u)] >> 8) : pi.q;   // (first sync point: the state the context names)
-                    const uint32_t a = s_fsm[pat * kFsm16Size + q * 16 + (cb & 15u)];
-                    const uint32_t nctx = s_info[pat * kProdMax + ((lo & PE_NEXT_MASK) >> PE_NEXT_SHIFT)].ctx;
-                    lo = split_rare(lo, a, k, base, total, s, pstart_bits, status, fix_list, fix_cap, s_skip + pat * 2 * kCtxMax,
-                                    (a & A_RESOLVE) ? 0u : nctx);
-                    if (lo == 0u) hi = 0u;
-                }
-            }
-            if (j >= 4 && (lo & PE_SYNC)) { lo = 0u; hi = 0u; }     // hand-over: the next block's owner started exactly here
-            mine |= (lo & PE_B_NOW) << k;
-            const uint32_t kk = k * 0x010101u + ((cb >> 4) + 1u) * 0x010001u;    // alc, lbe: the position after this character; last: this one
-            rem = (rem & ~hi) | (kk & hi);
-            st = lo & PE_NEXT_MASK;
         }
-    }
-    // ---- a walker that crossed the whole next block: the per-character walker goes on from its state
-    if (st != 0u) {
-        const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
-        uint64_t pos = base + 32u;
-        while (pos < total && (s[pos] & 0xC0u) == 0x80u) ++pos;          // byte 32 may lie inside the character that began at byte 29..31
-        uint32_t q = pi.q;
-        if (q == PQ_SKIP1 || q == PQ_SKIP2) {                            // inside a contraction: step over what is left of it
-            for (uint32_t n = (q == PQ_SKIP2 ? 2u : 1u); n && pos < total; --n) { ++pos; while (pos < total && (s[pos] & 0xC0u) == 0x80u) ++pos; }
-            q = S_START;
-        }
-        split_thread<2, 16, kFsm16Size>(b, vs, uc, s_fsm, s_cls, piece_bits, status, fix_list, fix_cap, 0, pos, pos, 0xFFFFFFFFu,
-                                        q, base + (rem & 0xFFu), base + ((rem >> 8) & 0xFFu), base + ((rem >> 16) & 0xFFu));
-    }
+        // ---- neighbours: the class bytes of the block to my right, the context at the end of the block to my left
+        const uint32_t left_ctx = __shfl_up_sync(kFull, endc, 1);
+        uint32_t w0 = cw[0], w1 = cw[1], w2 = cw[2], w3 = cw[3];
+        uint32_t w4 = __shfl_down_sync(kFull, w0, 1), w5 = __shfl_down_sync(kFull, w1, 1), w6 = __shfl_down_sync(kFull, w2, 1), w7 = __shfl_down_sync(kFull, w3, 1);
 
-    // ---- flags out: my 16 bits + what the lane to my left marked in my block; two lanes share a 32-bit word
-    uint32_t v = mine & 0xFFFFu;
-    const uint32_t spill = mine >> 16;
-    const uint32_t incoming = __shfl_up_sync(kFull, spill, 1);
-    if (lane) v |= incoming;
-    const uint32_t nv = __shfl_down_sync(kFull, v, 1);
-    if (blk >= 0) {
-        const uint64_t wi = base >> 5;
-        if (lane & 1u) {            // even block: low half; the odd block to my right is lane + 1 (or, for lane 31, my own spill)
-            const uint32_t word = v | ((lane == 31u ? spill : nv) << 16);
-            if (word) atomicOr(&piece_bits[wi], word);
-        } else if (lane == 0u) {    // odd block whose partner sits in the warp before
-            if (v) atomicOr(&piece_bits[wi], v << 16);
+        // ---- walk: from my first sync point to the first sync point of the next block.  One lookup in the product table per
+        //      byte; the eight class words of the window in a shift register; ONE copy of the step in the instruction stream
+        //      (unrolled it overflowed the instruction cache: the warps of an SM are all at different places of the kernel)
+        uint32_t mine = 0;              // bit k: a piece starts at base + k (every mark of the 32 steps lies inside the window: a remembered
+                                        // position is emitted at a later character than the one that set it)
+        uint32_t rem = 0;               // remembered positions, relative to base: alc | last << 8 | lbe << 16
+        uint32_t st = owner ? ((1u + left_ctx) << PE_NEXT_SHIFT) : 0u;     // row of my state in the product table; 0 = DONE; NOSYNC(context to my left)
+        const uint8_t* tab = tabs + (n_tabs == 1 ? 0u : pat) * kProdTableBytes;
+#pragma unroll 1
+        for (uint32_t j = 0; j < 8; ++j) {
+            if (j == 4 && s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)].q == PQ_NOSYNC) st = 0;   // no sync point in my own block: the walker from the left covers it
+            if (j >= 4 && __all_sync(kFull, st == 0u)) break;
+            uint32_t word = w0;
+            w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7;
+            uint32_t Pw = (P >> (4u * j)) & 15u;
+            const uint32_t sync_mask = j >= 4 ? static_cast<uint32_t>(PE_SYNC) : 0u;
+#pragma unroll 1
+            for (uint32_t k = 4u * j; k < 4u * j + 4u; ++k, word >>= 8, Pw >>= 1) {
+                if ((Pw & 1u) && st != 0u) {     // a prompt starts here (or the data ends): the prompt before it ends.  Rare.
+                    const uint4 r = split_prompt_start(st, pat, k, rem, base, total, s_fsm, s_info, s_start, s, pstart_bits, status, fix_list, fix_cap,
+                                                       b.offsets, b.vocab_ids, pats, block_prompt);
+                    st = r.x; mine |= r.y; pat = r.z;
+                    tab = tabs + (n_tabs == 1 ? 0u : pat) * kProdTableBytes;
+                }
+                const uint32_t cb = word & 0xFFu;
+                const uint2 e = *reinterpret_cast<const uint2*>(tab + st + ((cb & 15u) << 3));
+                uint32_t lo = e.x, hi = e.y;
+                if (lo & (PE_EMIT_ANY | PE_RARE)) {      // boundaries at remembered positions (indentation, cased words); contractions
+                    if (lo & PE_EMIT_ALC) mine |= 1u << (rem & 31u);
+                    if (lo & PE_EMIT_LAST) mine |= 1u << ((rem >> 8) & 31u);
+                    if (lo & PE_EMIT_LBE) mine |= 1u << ((rem >> 16) & 31u);
+                    if (lo & PE_RARE) {
+                        const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
+                        const uint32_t q = pi.q == PQ_NOSYNC ? (s_ctx[(pat & 1u) * kCtx16Size + (pi.ctx << 4) + (cb & 15u)] >> 8) : pi.q;   // (first sync point: the state the context names)
+                        const uint32_t a = s_fsm[pat * kFsm16Size + q * 16 + (cb & 15u)];
+                        const uint32_t nctx = s_info[pat * kProdMax + ((lo & PE_NEXT_MASK) >> PE_NEXT_SHIFT)].ctx;
+                        lo = split_rare(lo, a, k, base, total, s, pstart_bits, status, fix_list, fix_cap, s_skip + pat * 2 * kCtxMax,
+                                        (a & A_RESOLVE) ? 0u : nctx);
+                        if (lo == 0u) hi = 0u;
+                    }
+                }
+                if (lo & sync_mask) { lo = 0u; hi = 0u; }               // hand-over: the next block's owner started exactly here
+                mine |= (lo & PE_B_NOW) << k;
+                const uint32_t kk = k * 0x010101u + ((cb >> 4) + 1u) * 0x010001u;    // alc, lbe: the position after this character; last: this one
+                rem = (rem & ~hi) | (kk & hi);
+                st = lo & PE_NEXT_MASK;
+            }
         }
-    }
+        // ---- a walker that crossed the whole next block: the per-character walker goes on from its state
+        if (st != 0u) {
+            const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
+            uint64_t pos = base + 32u;
+            while (pos < total && (s[pos] & 0xC0u) == 0x80u) ++pos;          // byte 32 may lie inside the character that began at byte 29..31
+            uint32_t q = pi.q;
+            if (q == PQ_SKIP1 || q == PQ_SKIP2) {                            // inside a contraction: step over what is left of it
+                for (uint32_t n = (q == PQ_SKIP2 ? 2u : 1u); n && pos < total; --n) { ++pos; while (pos < total && (s[pos] & 0xC0u) == 0x80u) ++pos; }
+                q = S_START;
+            }
+            split_resume(b, pats, uc, s_fsm, s_cls, piece_bits, status, fix_list, fix_cap, pos, prompt_at(b, block_prompt, pos - 1),
+                         q, base + (rem & 0xFFu), base + ((rem >> 8) & 0xFFu), base + ((rem >> 16) & 0xFFu));
+        }
+
+        // ---- flags out: my 16 bits + what the lane to my left marked in my block; two lanes share a 32-bit word
+        //      (30 blocks a warp: odd lanes hold even blocks)
+        uint32_t v = mine & 0xFFFFu;
+        const uint32_t spill = mine >> 16;
+        const uint32_t incoming = __shfl_up_sync(kFull, spill, 1);
+        if (lane) v |= incoming;
+        const uint32_t nv = __shfl_down_sync(kFull, v, 1);
+        if (blk >= 0) {
+            const uint64_t wi = base >> 5;
+            if (lane & 1u) {            // even block: low half; the odd block to my right is lane + 1 (lane 31, the ghost, has none in this warp)
+                const uint32_t word = v | (lane == 31u ? 0u : (nv << 16));
+                if (word) atomicOr(&piece_bits[wi], word);
+            } else if (lane == 0u) {    // the ghost to the left owns nothing here
+            }
+        }
     }   // tiles
 }
 

@@ -480,29 +480,78 @@ ORACLE_API long oracle_encode(const oracle_vocab *v, int pattern_id, const uint8
     return r;
 }
 
+/* ---- batch driver: a persistent pool of worker threads (created once, parked on a condition variable between calls),
+ * a scratch id buffer that is kept across calls (a fresh 4-bytes-per-input-byte malloc was page-faulted by every call), and a
+ * parallel second phase that moves every prompt's ids to their final place.  This is the CPU baseline of record of bench.py
+ * (`cpu_baseline`, `--impl reference`): the port should lose to the GPU because of the hardware, not because of its driver. */
 typedef struct {
     const oracle_vocab *const *vocabs; const int *patterns; const uint8_t *vocab_ids;
     uint32_t n; const uint8_t *bytes; const uint64_t *offsets;
-    uint32_t *tmp; uint32_t *counts; volatile long *next; volatile int *err;
+    uint32_t *tmp; uint32_t *counts; uint32_t *out_ids; const uint64_t *out_offsets;
+    volatile long next; volatile int err; int phase;
 } batch_job;
 
-static void *batch_worker(void *arg) {
-    batch_job *j = arg;
-    work_t w = {0};
+static void batch_phase(batch_job *j, work_t *w) {
     for (;;) {
-        long i0 = __sync_fetch_and_add(j->next, 16);
+        long i0 = __sync_fetch_and_add(&j->next, 16);
         if (i0 >= (long)j->n) break;
         long i1 = i0 + 16 < (long)j->n ? i0 + 16 : (long)j->n;
         for (long i = i0; i < i1; i++) {
-            unsigned vid = j->vocab_ids ? j->vocab_ids[i] : 0;
-            long c = encode_one(j->vocabs[vid], j->patterns[vid], j->bytes + j->offsets[i],
-                                (size_t)(j->offsets[i + 1] - j->offsets[i]), j->tmp + j->offsets[i], &w);
-            if (c < 0) { *j->err = 1; c = 0; }
-            j->counts[i] = (uint32_t)c;
+            if (j->phase == 0) {
+                unsigned vid = j->vocab_ids ? j->vocab_ids[i] : 0;
+                long c = encode_one(j->vocabs[vid], j->patterns[vid], j->bytes + j->offsets[i],
+                                    (size_t)(j->offsets[i + 1] - j->offsets[i]), j->tmp + j->offsets[i], w);
+                if (c < 0) { j->err = 1; c = 0; }
+                j->counts[i] = (uint32_t)c;
+            } else {
+                memcpy(j->out_ids + j->out_offsets[i], j->tmp + j->offsets[i], (size_t)j->counts[i] * sizeof(uint32_t));
+            }
         }
     }
-    work_free(&w);
+}
+
+#define POOL_MAX 1024
+static struct {
+    pthread_mutex_t mu; pthread_cond_t go, done;
+    pthread_t th[POOL_MAX]; int n_threads;      /* workers created so far */
+    batch_job *job; int want;                   /* current job and how many workers should take part */
+    unsigned long gen; int running;             /* generation counter; workers still inside the current phase */
+    uint32_t *tmp; uint64_t tmp_cap;            /* scratch ids, kept across calls */
+    pthread_mutex_t call_mu;                    /* one batch call at a time */
+} g_pool = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, NULL, 0, 0, 0, NULL, 0, PTHREAD_MUTEX_INITIALIZER };
+
+static void *pool_worker(void *arg) {
+    const int id = (int)(intptr_t)arg;
+    work_t w = {0};
+    unsigned long seen = 0;
+    pthread_mutex_lock(&g_pool.mu);
+    for (;;) {
+        while (g_pool.gen == seen) pthread_cond_wait(&g_pool.go, &g_pool.mu);
+        seen = g_pool.gen;
+        if (id >= g_pool.want) continue;        /* this phase runs on fewer threads */
+        batch_job *j = g_pool.job;
+        pthread_mutex_unlock(&g_pool.mu);
+        batch_phase(j, &w);
+        pthread_mutex_lock(&g_pool.mu);
+        if (--g_pool.running == 0) pthread_cond_signal(&g_pool.done);
+    }
     return NULL;
+}
+
+static void pool_run(batch_job *j, int nthreads, work_t *w) {      /* the caller is thread 0 */
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.n_threads < nthreads - 1 && g_pool.n_threads < POOL_MAX) {
+        if (pthread_create(&g_pool.th[g_pool.n_threads], NULL, pool_worker, (void *)(intptr_t)g_pool.n_threads)) break;
+        g_pool.n_threads++;
+    }
+    const int helpers = nthreads - 1 < g_pool.n_threads ? nthreads - 1 : g_pool.n_threads;
+    g_pool.job = j; g_pool.want = helpers; g_pool.running = helpers; g_pool.gen++;
+    pthread_cond_broadcast(&g_pool.go);
+    pthread_mutex_unlock(&g_pool.mu);
+    batch_phase(j, w);
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.running) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+    pthread_mutex_unlock(&g_pool.mu);
 }
 
 /* Batch encode over a packed prompt buffer with nthreads host threads.
@@ -513,23 +562,24 @@ ORACLE_API int oracle_encode_batch(const oracle_vocab *const *vocabs, const int 
                                    uint32_t n, const uint8_t *bytes, const uint64_t *offsets,
                                    uint32_t *out_ids, uint64_t *out_offsets, uint32_t *out_counts, int nthreads) {
     pthread_once(&g_feat_once, feat_init);
-    uint64_t total = offsets[n];
-    uint32_t *tmp = malloc((total + 1) * sizeof(uint32_t));
-    volatile long next = 0; volatile int err = 0;
-    batch_job job = { vocabs, patterns, vocab_ids, n, bytes, offsets, tmp, out_counts, &next, &err };
     if (nthreads < 1) nthreads = 1;
-    pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nthreads);
-    for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, batch_worker, &job);
-    batch_worker(&job);
-    for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
-    free(th);
-    uint64_t acc = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        out_offsets[i] = acc;
-        if (out_ids) memcpy(out_ids + acc, tmp + offsets[i], (size_t)out_counts[i] * sizeof(uint32_t));
-        acc += out_counts[i];
+    if (nthreads > POOL_MAX) nthreads = POOL_MAX;
+    pthread_mutex_lock(&g_pool.call_mu);
+    const uint64_t total = offsets[n];
+    if (g_pool.tmp_cap < total + 1) {
+        free(g_pool.tmp);
+        g_pool.tmp_cap = total + 1 + total / 8;
+        g_pool.tmp = malloc(g_pool.tmp_cap * sizeof(uint32_t));
     }
+    batch_job job = { vocabs, patterns, vocab_ids, n, bytes, offsets, g_pool.tmp, out_counts, out_ids, out_offsets, 0, 0, 0 };
+    work_t w = {0};
+    pool_run(&job, nthreads, &w);
+    uint64_t acc = 0;
+    for (uint32_t i = 0; i < n; i++) { out_offsets[i] = acc; acc += out_counts[i]; }
     out_offsets[n] = acc;
-    free(tmp);
+    if (out_ids) { job.phase = 1; job.next = 0; pool_run(&job, nthreads, &w); }
+    work_free(&w);
+    const int err = job.err;
+    pthread_mutex_unlock(&g_pool.call_mu);
     return err ? -1 : 0;
 }

@@ -109,9 +109,9 @@ __attribute__((visibility("default"))) int sim_split(const uint32_t* patterns, u
             std::vector<uint32_t> pstart(nw + 2), bprompt((total >> kPromptBlockShift) + 2);
             cusim::launch(static_cast<unsigned>((static_cast<uint64_t>(n_prompts) + 1 + 255) / 256), 256, [&] { prompt_map_kernel(b, vs, pstart.data(), bprompt.data(), &st); });
             const uint64_t n_blocks16 = (total + 15) / 16;
-            const uint32_t n_tiles = static_cast<uint32_t>((n_blocks16 + kSplitOwned - 1) / kSplitOwned);
+            const uint32_t n_tiles = static_cast<uint32_t>((n_blocks16 + kSplitWarpOwned - 1) / kSplitWarpOwned);
             const uint32_t n_tabs = vocab_ids ? kNumPatterns : 1u;
-            cusim::launch(n_tiles < 3 ? n_tiles : 3u, kSplitCta,      // fewer CTAs than tiles: the persistent loop runs
+            cusim::launch(n_tiles < 17 ? 1u : 2u, kSplitCta,      // fewer warps than tiles: the persistent loop runs
                           [&] { pretok_split16_kernel(b, vs, uc, pstart.data(), bprompt.data(), piece_bits, &st, fix.data(), fix_cap, n_tabs, n_tiles); });
         }
         cusim::launch(2u, 256, [&] { pretok_fixup_kernel(b, vs, uc, piece_bits, &st, fix.data(), fix_cap); });

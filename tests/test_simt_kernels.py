@@ -272,3 +272,27 @@ def test_sub_batch_plan_covers_every_prompt_once():
     cut = simlib.plan_sub_batches(offs, 12 << 20)
     sizes = [int(offs[b] - offs[a]) for a, b in zip(cut[:-1], cut[1:])]
     assert sizes[0] < 2 << 20 and sizes[-1] < 2 << 20 and max(sizes) < 13 << 20 and sizes[0] < sizes[1] < sizes[2] < sizes[3]
+
+
+def test_split_pattern_changes_at_every_prompt():
+    """multi-tenant batches: the pattern (and its casedness, which the context automaton depends on) changes from prompt to
+    prompt, with prompts so short that several of them share a 16-byte block of K1"""
+    import random
+    rng = random.Random(11)
+    strs = fuzzgen.fuzz_strings(321, 3000, max_atoms=6) + fuzzgen.fuzz_strings(322, 600, max_atoms=30)
+    prompts = [s.encode() for s in strs]
+    for i in range(0, len(prompts), 7):
+        prompts[i] = prompts[i][:rng.randint(0, 3)].decode("utf-8", "ignore").encode()     # 0..3-byte prompts too
+    vids = [rng.randrange(4) for _ in prompts]
+    rc, ends = simlib.split([0, 1, 2, 3], prompts, vocab_ids=vids)
+    assert rc == 0
+    bad = [(v, p, e) for v, p, e in zip(vids, prompts, ends) if oracle.split(v, p).tolist() != e]
+    assert not bad, bad[:3]
+
+
+def test_split_tables_are_small_and_complete():
+    """the enumerations behind K1's tables (pretok_ctx.h) stay inside their fixed capacities"""
+    L = simlib.lib()
+    L.sim_ctx_count.restype = L.sim_prod_count.restype = __import__("ctypes").c_uint32
+    assert all(0 < L.sim_ctx_count(c) <= 64 for c in (0, 1))
+    assert all(0 < L.sim_prod_count(p) < 128 for p in range(4))
