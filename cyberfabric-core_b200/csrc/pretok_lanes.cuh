@@ -60,7 +60,7 @@ prompt_map_kernel(BatchView b, VocabSet vs, uint32_t* __restrict__ pstart_bits, 
 // A block with bytes >= 0x80: decode every character that starts in it (class | (len - 1) << 4 replaces X_LEAD) and check
 // the UTF-8: lead byte ranges, continuation bytes present and in range, no overlongs, no surrogates, nothing above U+10FFFF,
 // no character cut by the end of its prompt, and every continuation byte inside a character (pretok.cuh::get_char, restated on
-// the block's bytes in registers: a 20-byte window -- the block and the four bytes after it -- shifted one byte per step).
+// the block's bytes in registers: a 20-byte window -- the block and the four bytes after it).
 // P: prompt-start bits of [base, base + 32).
 __device__ __noinline__ uint4 classify_non_ascii(const uint8_t* __restrict__ s, uint64_t base, uint64_t total, const uint32_t* __restrict__ pstart_bits,
                                                  const UcTables uc, uint4 raw, uint4 cwv, uint32_t P, DeviceStatus* status) {
@@ -75,42 +75,54 @@ __device__ __noinline__ uint4 classify_non_ascii(const uint8_t* __restrict__ s, 
             break;
         }
     }
-    uint64_t lo = raw.x | (static_cast<uint64_t>(raw.y) << 32), hi = raw.z | (static_cast<uint64_t>(raw.w) << 32);
-    uint64_t ext = load_u32_any(s + base + 16);      // (the buffer is readable 32 bytes past its end)
+    // one trip per LEAD byte (a CJK block has five), not per byte
+    const uint64_t lo = raw.x | (static_cast<uint64_t>(raw.y) << 32), hi = raw.z | (static_cast<uint64_t>(raw.w) << 32);
+    const uint64_t ext = load_u32_any(s + base + 16);                      // (the buffer is readable 32 bytes past its end)
     uint64_t clo = cwv.x | (static_cast<uint64_t>(cwv.y) << 32), chi = cwv.z | (static_cast<uint64_t>(cwv.w) << 32);
-    uint64_t out_lo = 0, out_hi = 0;
     const uint32_t n = total - base < 16 ? static_cast<uint32_t>(total - base) : 16u;
-    for (uint32_t k = 0; k < 16; ++k) {
-        const uint32_t w = static_cast<uint32_t>(lo);                      // bytes k .. k+3
-        uint32_t cb = static_cast<uint32_t>(clo) & 0xFFu;
-        if (k < n) {
-            if ((P >> k) & 1u) need = 0;
-            if (cb == X_CONT) { if (need) --need; else bad = 1; }
-            else if (cb == X_LEAD) {
-                const uint32_t b0 = w & 0xFFu, b1 = (w >> 8) & 0xFFu, b2 = (w >> 16) & 0xFFu, b3 = w >> 24;
-                uint32_t len, cp;
-                bool ok;
-                if (b0 >= 0xC2u && b0 <= 0xDFu) { len = 2; cp = ((b0 & 0x1Fu) << 6) | (b1 & 0x3Fu); ok = (b1 & 0xC0u) == 0x80u; }
-                else if (b0 >= 0xE0u && b0 <= 0xEFu) {
-                    len = 3; cp = ((b0 & 0x0Fu) << 12) | ((b1 & 0x3Fu) << 6) | (b2 & 0x3Fu);
-                    ok = (b1 & 0xC0u) == 0x80u && (b2 & 0xC0u) == 0x80u && cp >= 0x800u && !(cp >= 0xD800u && cp <= 0xDFFFu);
-                } else if (b0 >= 0xF0u && b0 <= 0xF4u) {
-                    len = 4; cp = ((b0 & 0x07u) << 18) | ((b1 & 0x3Fu) << 12) | ((b2 & 0x3Fu) << 6) | (b3 & 0x3Fu);
-                    ok = (b1 & 0xC0u) == 0x80u && (b2 & 0xC0u) == 0x80u && (b3 & 0xC0u) == 0x80u && cp >= 0x10000u && cp <= 0x10FFFFu;
-                } else { len = 1; cp = 0; ok = false; }
-                // the character must end inside its prompt: no prompt start (nor the end of the data) among its continuation bytes
-                ok = ok && k + len <= n + (total - base > 16 ? 4u : 0u) && !((P >> (k + 1)) & ((1u << (len - 1u)) - 1u));
-                if (!ok) { bad = 1; len = 1; cb = X_OTHER; }           // (consumed as one byte of class OTHER, like get_char)
-                else cb = uc_class(uc, cp) | ((len - 1u) << 4);
-                need = len - 1u;
-            } else need = 0;
+    const uint32_t valid = n >= 16 ? 0xFFFFu : ((1u << n) - 1u);
+    auto byte_mask = [](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t v) -> uint32_t {      // bit k: class byte k == v
+        uint32_t m = 0;
+        const uint32_t ws[4] = {w0, w1, w2, w3};
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t nz = (((ws[j] ^ (v * 0x01010101u)) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | (ws[j] ^ (v * 0x01010101u));    // bit 7 of a byte: byte != v
+            m |= (((((~nz) & 0x80808080u) >> 7) * 0x01020408u) >> 24 & 15u) << (4u * j);
         }
-        if (k < 8) out_lo |= static_cast<uint64_t>(cb) << (8u * k); else out_hi |= static_cast<uint64_t>(cb) << (8u * (k - 8u));
-        lo = (lo >> 8) | (hi << 56); hi = (hi >> 8) | (ext << 56); ext >>= 8;
-        clo = (clo >> 8) | (chi << 56); chi >>= 8;
+        return m;
+    };
+    const uint32_t conts = byte_mask(cwv.x, cwv.y, cwv.z, cwv.w, X_CONT) & valid;
+    uint32_t leads = byte_mask(cwv.x, cwv.y, cwv.z, cwv.w, X_LEAD) & valid;
+    uint32_t expected = (1u << need) - 1u;         // continuation bytes that belong to a character
+    while (leads) {
+        const uint32_t k = static_cast<uint32_t>(__ffs(leads)) - 1u;
+        leads &= leads - 1u;
+        // bytes k .. k+3 of the 20-byte window
+        const uint32_t w = k < 8 ? static_cast<uint32_t>(k ? ((lo >> (8u * k)) | (hi << (64u - 8u * k))) : lo)
+                                 : static_cast<uint32_t>(k > 8 ? ((hi >> (8u * (k - 8u))) | (ext << (64u - 8u * (k - 8u)))) : hi);
+        const uint32_t b0 = w & 0xFFu, b1 = (w >> 8) & 0xFFu, b2 = (w >> 16) & 0xFFu, b3 = w >> 24;
+        uint32_t len, cp;
+        bool ok;
+        if (b0 >= 0xC2u && b0 <= 0xDFu) { len = 2; cp = ((b0 & 0x1Fu) << 6) | (b1 & 0x3Fu); ok = (b1 & 0xC0u) == 0x80u; }
+        else if (b0 >= 0xE0u && b0 <= 0xEFu) {
+            len = 3; cp = ((b0 & 0x0Fu) << 12) | ((b1 & 0x3Fu) << 6) | (b2 & 0x3Fu);
+            ok = (b1 & 0xC0u) == 0x80u && (b2 & 0xC0u) == 0x80u && cp >= 0x800u && !(cp >= 0xD800u && cp <= 0xDFFFu);
+        } else if (b0 >= 0xF0u && b0 <= 0xF4u) {
+            len = 4; cp = ((b0 & 0x07u) << 18) | ((b1 & 0x3Fu) << 12) | ((b2 & 0x3Fu) << 6) | (b3 & 0x3Fu);
+            ok = (b1 & 0xC0u) == 0x80u && (b2 & 0xC0u) == 0x80u && (b3 & 0xC0u) == 0x80u && cp >= 0x10000u && cp <= 0x10FFFFu;
+        } else { len = 1; cp = 0; ok = false; }
+        // the character must end inside its prompt: no prompt start (nor the end of the data) among its continuation bytes
+        ok = ok && k + len <= n + (total - base > 16 ? 4u : 0u) && !((P >> (k + 1)) & ((1u << (len - 1u)) - 1u));
+        uint32_t cb;
+        if (!ok) { bad = 1; len = 1; cb = X_OTHER; }               // (consumed as one byte of class OTHER, like get_char)
+        else cb = uc_class(uc, cp) | ((len - 1u) << 4);
+        expected |= ((1u << (len - 1u)) - 1u) << (k + 1u);
+        if (k < 8) clo = (clo & ~(0xFFull << (8u * k))) | (static_cast<uint64_t>(cb) << (8u * k));
+        else chi = (chi & ~(0xFFull << (8u * (k - 8u)))) | (static_cast<uint64_t>(cb) << (8u * (k - 8u)));
     }
+    if ((conts & ~expected) != 0u) bad = 1;          // a continuation byte that no character claims
     if (bad) atomicOr(&status->bad_utf8, 1u);
-    return make_uint4(static_cast<uint32_t>(out_lo), static_cast<uint32_t>(out_lo >> 32), static_cast<uint32_t>(out_hi), static_cast<uint32_t>(out_hi >> 32));
+    return make_uint4(static_cast<uint32_t>(clo), static_cast<uint32_t>(clo >> 32), static_cast<uint32_t>(chi), static_cast<uint32_t>(chi >> 32));
 }
 
 // the pattern of the prompt that holds byte pos (multi-vocabulary batches, at prompt starts only)
@@ -180,7 +192,7 @@ constexpr uint32_t kSplitWarpOwned = 30;            // blocks of 16 bytes a WARP
                                                     // warp ever waits for another (a CTA-wide exchange spent 39 % of the time in barriers)
 
 // n_tabs: product tables in shared memory -- 1 (single-vocabulary batch: the table of pattern pat0) or kNumPatterns
-__global__ void __launch_bounds__(kSplitCta)
+__global__ void __launch_bounds__(kSplitCta, 5)
 pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __restrict__ pstart_bits,
                       const uint32_t* __restrict__ block_prompt, uint32_t* __restrict__ piece_bits, DeviceStatus* status,
                       SplitFix* fix_list, uint32_t fix_cap, uint32_t n_tabs, uint32_t n_tiles) {
@@ -260,7 +272,21 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
                 endc = s_ctx[cased * kCtx16Size + (endc << 4) + x] & 0xFFu;
             };
             if (!nonascii) { ctx_step(13); ctx_step(14); ctx_step(15); }       // three ASCII bytes are three characters
-            else {                                                              // twelve bytes hold at least three characters
+            else if (!(P & 0xFFFFu)) {                                         // the last three characters that START in my block
+                uint32_t starts = 0;                                            // bit k: byte k is not a continuation byte
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j) {
+                    const uint32_t nz = (((cw[j] ^ 0x0C0C0C0Cu) & 0x0F0F0F0Fu) + 0x0F0F0F0Fu) & 0x10101010u;     // low nibble != X_CONT
+                    starts |= ((((nz >> 4) * 0x01020408u) >> 24) & 15u) << (4u * j);
+                }
+                const uint32_t c1 = 31u - static_cast<uint32_t>(__clz(starts)); starts &= ~(1u << c1);
+                const uint32_t c2 = 31u - static_cast<uint32_t>(__clz(starts)); starts &= ~(1u << c2);
+                const uint32_t c3 = starts ? 31u - static_cast<uint32_t>(__clz(starts)) : c2;
+                auto cls_at = [&](uint32_t k) { const uint32_t w = k < 8 ? (k < 4 ? cw[0] : cw[1]) : (k < 12 ? cw[2] : cw[3]); return (w >> (8u * (k & 3u))) & 15u; };
+                endc = s_ctx[cased * kCtx16Size + (endc << 4) + cls_at(c3)] & 0xFFu;
+                endc = s_ctx[cased * kCtx16Size + (endc << 4) + cls_at(c2)] & 0xFFu;
+                endc = s_ctx[cased * kCtx16Size + (endc << 4) + cls_at(c1)] & 0xFFu;
+            } else {                                                            // a prompt starts inside: twelve bytes hold at least three characters
 #pragma unroll 1
                 for (uint32_t k = 4; k < 16; ++k) ctx_step(k);
             }
@@ -278,45 +304,58 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
         uint32_t rem = 0;               // remembered positions, relative to base: alc | last << 8 | lbe << 16
         uint32_t st = owner ? ((1u + left_ctx) << PE_NEXT_SHIFT) : 0u;     // row of my state in the product table; 0 = DONE; NOSYNC(context to my left)
         const uint8_t* tab = tabs + (n_tabs == 1 ? 0u : pat) * kProdTableBytes;
+        // one byte: ONE lookup in the product table.  kb = first byte index of the group of four, i = index in the group.
+        auto step = [&](const uint32_t i, const uint32_t cb, const uint32_t kb, const uint32_t kb3, const uint32_t sync_mask, uint32_t& gm) {
+            const uint2 e = *reinterpret_cast<const uint2*>(tab + st + ((cb & 15u) << 3));
+            uint32_t lo = e.x, hi = e.y;
+            if (lo & (PE_EMIT_ANY | PE_RARE)) {      // boundaries at remembered positions (indentation, cased words); contractions
+                if (lo & PE_EMIT_ALC) mine |= 1u << (rem & 31u);
+                if (lo & PE_EMIT_LAST) mine |= 1u << ((rem >> 8) & 31u);
+                if (lo & PE_EMIT_LBE) mine |= 1u << ((rem >> 16) & 31u);
+                if (lo & PE_RARE) {
+                    const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
+                    const uint32_t q = pi.q == PQ_NOSYNC ? (s_ctx[(pat & 1u) * kCtx16Size + (pi.ctx << 4) + (cb & 15u)] >> 8) : pi.q;   // (first sync point: the state the context names)
+                    const uint32_t a = s_fsm[pat * kFsm16Size + q * 16 + (cb & 15u)];
+                    const uint32_t nctx = s_info[pat * kProdMax + ((lo & PE_NEXT_MASK) >> PE_NEXT_SHIFT)].ctx;
+                    lo = split_rare(lo, a, kb + i, base, total, s, pstart_bits, status, fix_list, fix_cap, s_skip + pat * 2 * kCtxMax,
+                                    (a & A_RESOLVE) ? 0u : nctx);
+                    if (lo == 0u) hi = 0u;
+                }
+            }
+            if (lo & sync_mask) { lo = 0u; hi = 0u; }               // hand-over: the next block's owner started exactly here
+            gm |= (lo & PE_B_NOW) << i;
+            const uint32_t kk = kb3 + i * 0x010101u + ((cb >> 4) + 1u) * 0x010001u;    // alc, lbe: the position after this character; last: this one
+            rem = (rem & ~hi) | (kk & hi);
+            st = lo & PE_NEXT_MASK;
+        };
 #pragma unroll 1
         for (uint32_t j = 0; j < 8; ++j) {
             if (j == 4 && s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)].q == PQ_NOSYNC) st = 0;   // no sync point in my own block: the walker from the left covers it
             if (j >= 4 && __all_sync(kFull, st == 0u)) break;
-            uint32_t word = w0;
+            const uint32_t word = w0;
             w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7;
-            uint32_t Pw = (P >> (4u * j)) & 15u;
+            const uint32_t kb = 4u * j, kb3 = kb * 0x010101u;
+            const uint32_t Pw = (P >> kb) & 15u;
             const uint32_t sync_mask = j >= 4 ? static_cast<uint32_t>(PE_SYNC) : 0u;
+            uint32_t gm = 0;            // the group's A_B_NOW marks
+            if (Pw && st != 0u) {       // a prompt starts inside these four bytes (or the data ends): rare, one byte at a time
 #pragma unroll 1
-            for (uint32_t k = 4u * j; k < 4u * j + 4u; ++k, word >>= 8, Pw >>= 1) {
-                if ((Pw & 1u) && st != 0u) {     // a prompt starts here (or the data ends): the prompt before it ends.  Rare.
-                    const uint4 r = split_prompt_start(st, pat, k, rem, base, total, s_fsm, s_info, s_start, s, pstart_bits, status, fix_list, fix_cap,
-                                                       b.offsets, b.vocab_ids, pats, block_prompt);
-                    st = r.x; mine |= r.y; pat = r.z;
-                    tab = tabs + (n_tabs == 1 ? 0u : pat) * kProdTableBytes;
-                }
-                const uint32_t cb = word & 0xFFu;
-                const uint2 e = *reinterpret_cast<const uint2*>(tab + st + ((cb & 15u) << 3));
-                uint32_t lo = e.x, hi = e.y;
-                if (lo & (PE_EMIT_ANY | PE_RARE)) {      // boundaries at remembered positions (indentation, cased words); contractions
-                    if (lo & PE_EMIT_ALC) mine |= 1u << (rem & 31u);
-                    if (lo & PE_EMIT_LAST) mine |= 1u << ((rem >> 8) & 31u);
-                    if (lo & PE_EMIT_LBE) mine |= 1u << ((rem >> 16) & 31u);
-                    if (lo & PE_RARE) {
-                        const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
-                        const uint32_t q = pi.q == PQ_NOSYNC ? (s_ctx[(pat & 1u) * kCtx16Size + (pi.ctx << 4) + (cb & 15u)] >> 8) : pi.q;   // (first sync point: the state the context names)
-                        const uint32_t a = s_fsm[pat * kFsm16Size + q * 16 + (cb & 15u)];
-                        const uint32_t nctx = s_info[pat * kProdMax + ((lo & PE_NEXT_MASK) >> PE_NEXT_SHIFT)].ctx;
-                        lo = split_rare(lo, a, k, base, total, s, pstart_bits, status, fix_list, fix_cap, s_skip + pat * 2 * kCtxMax,
-                                        (a & A_RESOLVE) ? 0u : nctx);
-                        if (lo == 0u) hi = 0u;
+                for (uint32_t i = 0; i < 4; ++i) {
+                    if (((Pw >> i) & 1u) && st != 0u) {
+                        const uint4 r = split_prompt_start(st, pat, kb + i, rem, base, total, s_fsm, s_info, s_start, s, pstart_bits, status, fix_list, fix_cap,
+                                                           b.offsets, b.vocab_ids, pats, block_prompt);
+                        st = r.x; mine |= r.y; pat = r.z;
+                        tab = tabs + (n_tabs == 1 ? 0u : pat) * kProdTableBytes;
                     }
+                    uint32_t g1 = 0;
+                    step(0, (word >> (8u * i)) & 0xFFu, kb + i, kb3 + i * 0x010101u, sync_mask, g1);
+                    gm |= g1 << i;
                 }
-                if (lo & sync_mask) { lo = 0u; hi = 0u; }               // hand-over: the next block's owner started exactly here
-                mine |= (lo & PE_B_NOW) << k;
-                const uint32_t kk = k * 0x010101u + ((cb >> 4) + 1u) * 0x010001u;    // alc, lbe: the position after this character; last: this one
-                rem = (rem & ~hi) | (kk & hi);
-                st = lo & PE_NEXT_MASK;
+            } else {
+#pragma unroll
+                for (uint32_t i = 0; i < 4; ++i) step(i, (word >> (8u * i)) & 0xFFu, kb, kb3, sync_mask, gm);
             }
+            mine |= gm << kb;
         }
         // ---- a walker that crossed the whole next block: the per-character walker goes on from its state
         if (st != 0u) {

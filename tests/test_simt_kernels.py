@@ -296,3 +296,30 @@ def test_split_tables_are_small_and_complete():
     L.sim_ctx_count.restype = L.sim_prod_count.restype = __import__("ctypes").c_uint32
     assert all(0 < L.sim_ctx_count(c) <= 64 for c in (0, 1))
     assert all(0 < L.sim_prod_count(p) < 128 for p in range(4))
+
+
+def test_utf8_validation_at_every_alignment():
+    """K1 decodes and validates UTF-8 from 16-byte blocks in registers: every malformed sequence must be reported, and no valid
+    one, wherever it falls relative to the block boundaries and to the prompt boundaries"""
+    bad = [b"\xff", b"\x80", b"\xbf", b"\xc3", b"\xc3(", b"\xe2\x82", b"\xe2(\xa1", b"\xe2\x82(", b"\xed\xa0\x80", b"\xf4\x90\x80\x80",
+           b"\xc0\xaf", b"\xc1\xbf", b"\xe0\x80\xaf", b"\xf0\x80\x80\xaf", b"\xf0\x9f\x98", b"\xf5\x80\x80\x80", b"\xe4\xb8\xad\x80",
+           b"\xf0\x9f\x98\x80\x80"]
+    good = ["é", "中", "😀", "éé中中😀😀", "　", "á", "ʰ"]
+    for pad in range(0, 36):
+        head = b"x" * pad
+        cases_bad = [head + b + tail for b in bad for tail in (b"", b" tail text that goes on for a while")]
+        cases_good = [head + g.encode() + tail for g in good for tail in (b"", b" tail text that goes on for a while")]
+        for c in cases_bad:
+            rc, _ = simlib.split([0], [b"ok", c, b"fine"])
+            assert rc == -84, (pad, c)
+            with pytest.raises(ValueError):
+                oracle.split(0, c)
+        rc, ends = simlib.split([3], cases_good)
+        assert rc == 0, pad
+        for c, e in zip(cases_good, ends):
+            assert oracle.split(3, c).tolist() == e, (pad, c)
+    # a character cut by the end of its prompt is malformed even when the next prompt starts with the missing bytes
+    rc, _ = simlib.split([0], [b"abc\xe4\xb8", b"\xad def"])
+    assert rc == -84
+    rc, _ = simlib.split([0], [b"x" * 14 + b"\xe4\xb8", b"\xad def"])
+    assert rc == -84
