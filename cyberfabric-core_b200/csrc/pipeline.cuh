@@ -87,7 +87,7 @@ inline void enqueue_split(const BatchView& b, const VocabSet& vs, const UcTables
         const uint64_t n_blocks16 = (b.total_bytes + 15) / 16;
         const uint32_t n_tiles = static_cast<uint32_t>((n_blocks16 + kSplitWarpOwned - 1) / kSplitWarpOwned);
         const uint32_t n_tabs = b.vocab_ids ? kNumPatterns : 1u;
-        const uint32_t cap = split_grid ? split_grid : 740u;      // 5 CTAs of 48 registers x 256 threads per SM
+        const uint32_t cap = split_grid ? split_grid : 148u * CFBPE_SPLIT_CTAS;      // resident CTAs: 148 SMs x CTAs per SM (launch bounds)
         const uint32_t n_ctas = (n_tiles + kSplitCta / 32 - 1) / (kSplitCta / 32);
         CFBPE_LAUNCH_SMEM(pretok_split16_kernel, n_ctas < cap ? n_ctas : cap, kSplitCta, n_tabs * kProdTableBytes, stream,
                           b, vs, uc, w.pstart_bits, w.block_prompt, w.piece_bits, w.status, w.fix_list, w.fix_cap, n_tabs, n_tiles);

@@ -134,49 +134,82 @@ __device__ __noinline__ uint32_t pattern_at(const uint64_t* __restrict__ offsets
     return (pats >> (4u * (vocab_ids[p] & 7u))) & 15u;
 }
 
-// The rare actions of a step, out of line: an undecided state that has to be resolved (the fix-up kernel goes on from here:
-// the walker stops), or a contraction that may start at this apostrophe.  Returns the entry to go on with: unchanged when
-// there is no contraction; else its next state replaced by SKIPn (and A_B_NOW cleared when the contraction is the suffix of
-// the word that just ended); 0 (= DONE, no flags) when the walker stops.
-__device__ __noinline__ uint32_t split_rare(uint32_t lo, uint32_t a, uint32_t k, uint64_t base, uint64_t total, const uint8_t* __restrict__ s,
-                                            const uint32_t* __restrict__ pstart_bits, DeviceStatus* status, SplitFix* fix_list, uint32_t fix_cap,
-                                            const uint8_t* skip_tab, uint32_t next_ctx) {
+// What the out-of-line paths need, in shared memory: a call then carries a pointer and the walker's few registers instead of
+// a dozen arguments (the marshalling code sat in the hot loop four times and pushed it out of the 6 KB L0 instruction cache:
+// 54 % of the stall samples were instruction fetches -- profiles/ncu_summary_r02e.json).
+struct SplitEnv {
+    const uint8_t* s; const uint32_t* pstart_bits; const uint32_t* block_prompt; const uint64_t* offsets; const uint8_t* vocab_ids;
+    DeviceStatus* status; SplitFix* fix_list;
+    uint64_t total; uint32_t fix_cap, pats, n_tabs;
+    const uint16_t* fsm; const uint16_t* ctx; const ProdInfo* info; const uint8_t* skip; const uint8_t* start; const uint8_t* tabs;
+};
+
+// The rare actions of a step: an undecided state that has to be resolved (the fix-up kernel goes on from here: the walker
+// stops), or a contraction that may start at this apostrophe.  st: row of the state BEFORE the step; lo: its table entry for
+// class byte cb at window byte k.  Returns the entry to go on with: unchanged when there is no contraction; else its next state
+// replaced by SKIPn (and A_B_NOW cleared when the contraction is the suffix of the word that just ended); 0 (= DONE, no flags)
+// when the walker stops.
+__device__ __noinline__ uint32_t split_rare(const SplitEnv* env, uint32_t lo, uint32_t st, uint32_t cb, uint32_t k, uint32_t pat, uint64_t base) {
+    const ProdInfo pi = env->info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
+    const uint32_t x = cb & 15u;
+    const uint32_t q = pi.q == PQ_NOSYNC ? (env->ctx[(pat & 1u) * kCtx16Size + (pi.ctx << 4) + x] >> 8) : pi.q;   // (first sync point: the state the context names)
+    const uint32_t a = q < S_COUNT ? env->fsm[pat * kFsm16Size + q * 16 + x] : 0u;
     if (a & A_RESOLVE) {
-        const uint32_t q = atomicAdd(&status->fix_n, 1u);
-        if (q < fix_cap) { SplitFix f; f.pos = static_cast<uint32_t>(base + k); f.ce = static_cast<uint32_t>(base + 16); fix_list[q] = f; }
-        else atomicOr(&status->long_overflow, 1u);
+        const uint32_t n = atomicAdd(&env->status->fix_n, 1u);
+        if (n < env->fix_cap) { SplitFix f; f.pos = static_cast<uint32_t>(base + k); f.ce = static_cast<uint32_t>(base + 16); env->fix_list[n] = f; }
+        else atomicOr(&env->status->long_overflow, 1u);
         return 0u;
     }
-    const uint64_t pos = base + k;
+    if (!(a & A_CONTR)) return lo;
+    const uint64_t pos = base + k, total = env->total;
     uint64_t pe = pos + 3 < total ? pos + 3 : total;          // a contraction does not cross the end of its prompt
-    if (pos + 2 < total && bit_at(pstart_bits, pos + 2)) pe = pos + 2;
-    if (pos + 1 < total && bit_at(pstart_bits, pos + 1)) pe = pos + 1;
-    const uint32_t skip = contraction_bytes(s, pos, pe);
+    if (pos + 2 < total && bit_at(env->pstart_bits, pos + 2)) pe = pos + 2;
+    if (pos + 1 < total && bit_at(env->pstart_bits, pos + 1)) pe = pos + 1;
+    const uint32_t skip = contraction_bytes(env->s, pos, pe);
     if (!skip) return lo;
-    const uint32_t chars = (skip == 3 && s[pos + 1] < 0x80u) ? 2u : 1u;     // 'll 've 're: two characters follow the apostrophe; 's ... and U+017F: one
+    const uint32_t chars = (skip == 3 && env->s[pos + 1] < 0x80u) ? 2u : 1u;     // 'll 've 're: two characters follow the apostrophe; 's ... and U+017F: one
     if (a & A_CONTR_SUFFIX) lo &= ~PE_B_NOW;                  // the contraction belongs to the piece that just ended
-    return (lo & ~PE_NEXT_MASK) | (static_cast<uint32_t>(skip_tab[(chars - 1u) * kCtxMax + next_ctx]) << PE_NEXT_SHIFT);
+    const uint32_t next_ctx = env->info[pat * kProdMax + ((lo & PE_NEXT_MASK) >> PE_NEXT_SHIFT)].ctx;
+    return (lo & ~PE_NEXT_MASK) | (static_cast<uint32_t>(env->skip[(pat * 2 + chars - 1u) * kCtxMax + next_ctx]) << PE_NEXT_SHIFT);
 }
 
-// A prompt starts at byte k of the window (or the data ends there): the prompt before it ends.  Out of line (one lane in a
-// hundred meets one).  Returns {new state row, marks, new pattern}.
-__device__ __noinline__ uint4 split_prompt_start(uint32_t st, uint32_t pat, uint32_t k, uint32_t rem, uint64_t base, uint64_t total,
-                                                 const uint16_t* s_fsm, const ProdInfo* s_info, const uint8_t* s_start, const uint8_t* __restrict__ s,
-                                                 const uint32_t* __restrict__ pstart_bits, DeviceStatus* status, SplitFix* fix_list, uint32_t fix_cap,
-                                                 const uint64_t* __restrict__ offsets, const uint8_t* __restrict__ vocab_ids, uint32_t pats,
-                                                 const uint32_t* __restrict__ block_prompt) {
-    const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
-    bool stop = k >= 16 || base + k >= total;                    // (the owner of that block starts there)
+// Four bytes of the window with a prompt start (or the end of the data) among them, one byte at a time, everything handled:
+// the prompt before the start ends (its last state meets X_EOT), the walker stops there if that is the next block's affair, else
+// goes on in the new prompt with the new prompt's pattern.  Out of line: one group in five hundred.
+// Returns {state row, marks (window bits), remembered positions, pattern}.
+__device__ __noinline__ uint4 split_prompt_group(const SplitEnv* env, uint32_t word, uint32_t Pw, uint32_t kb, uint32_t st, uint32_t pat,
+                                                 uint32_t rem, uint64_t base, uint32_t sync_mask) {
     uint32_t marks = 0;
-    if (pi.q < S_COUNT) {
-        const uint32_t a = s_fsm[pat * kFsm16Size + pi.q * 16 + X_EOT];
-        if (a & A_EMIT_ALC) marks |= 1u << (rem & 31u);
-        if (a & A_EMIT_LAST) marks |= 1u << ((rem >> 8) & 31u);
-        if (a & A_EMIT_LBE) marks |= 1u << ((rem >> 16) & 31u);
-        if (a & A_RESOLVE) { split_rare(0, a, k, base, total, s, pstart_bits, status, fix_list, fix_cap, nullptr, 0); stop = true; }
+    for (uint32_t i = 0; i < 4; ++i, word >>= 8) {
+        const uint32_t k = kb + i;
+        if (((Pw >> i) & 1u) && st != 0u) {
+            const ProdInfo pi = env->info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
+            bool stop = k >= 16 || base + k >= env->total;                    // (the owner of that block starts there)
+            if (pi.q < S_COUNT) {
+                const uint32_t a = env->fsm[pat * kFsm16Size + pi.q * 16 + X_EOT];
+                if (a & A_EMIT_ALC) marks |= 1u << (rem & 31u);
+                if (a & A_EMIT_LAST) marks |= 1u << ((rem >> 8) & 31u);
+                if (a & A_EMIT_LBE) marks |= 1u << ((rem >> 16) & 31u);
+                if (a & A_RESOLVE) { split_rare(env, 0, st, X_EOT, k, pat, base); stop = true; }
+            }
+            if (env->vocab_ids && !stop) pat = pattern_at(env->offsets, env->vocab_ids, env->pats, env->block_prompt, base + k);
+            st = stop ? 0u : (static_cast<uint32_t>(env->start[pat]) << PE_NEXT_SHIFT);
+        }
+        const uint32_t cb = word & 0xFFu;
+        const uint8_t* tab = env->tabs + (env->n_tabs == 1 ? 0u : pat) * kProdTableBytes;
+        const uint2 e = *reinterpret_cast<const uint2*>(tab + st + ((cb & 15u) << 3));
+        uint32_t lo = e.x, hi = e.y;
+        if (lo & PE_EMIT_ALC) marks |= 1u << (rem & 31u);
+        if (lo & PE_EMIT_LAST) marks |= 1u << ((rem >> 8) & 31u);
+        if (lo & PE_EMIT_LBE) marks |= 1u << ((rem >> 16) & 31u);
+        if (lo & PE_RARE) { lo = split_rare(env, lo, st, cb, k, pat, base); if (lo == 0u) hi = 0u; }
+        if (lo & sync_mask) { lo = 0u; hi = 0u; }
+        marks |= (lo & PE_B_NOW) << k;
+        const uint32_t kk = k * 0x010101u + ((cb >> 4) + 1u) * 0x010001u;
+        rem = (rem & ~hi) | (kk & hi);
+        st = lo & PE_NEXT_MASK;
     }
-    if (vocab_ids && !stop) pat = pattern_at(offsets, vocab_ids, pats, block_prompt, base + k);
-    return make_uint4(stop ? 0u : (static_cast<uint32_t>(s_start[pat]) << PE_NEXT_SHIFT), marks, pat, 0u);
+    return make_uint4(st, marks, rem, pat);
 }
 
 // the per-character walker of the first form, out of line (it is large, and rare: long runs without a sync point)
@@ -192,7 +225,10 @@ constexpr uint32_t kSplitWarpOwned = 30;            // blocks of 16 bytes a WARP
                                                     // warp ever waits for another (a CTA-wide exchange spent 39 % of the time in barriers)
 
 // n_tabs: product tables in shared memory -- 1 (single-vocabulary batch: the table of pattern pat0) or kNumPatterns
-__global__ void __launch_bounds__(kSplitCta, 5)
+#ifndef CFBPE_SPLIT_CTAS
+#define CFBPE_SPLIT_CTAS 5
+#endif
+__global__ void __launch_bounds__(kSplitCta, CFBPE_SPLIT_CTAS)
 pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __restrict__ pstart_bits,
                       const uint32_t* __restrict__ block_prompt, uint32_t* __restrict__ piece_bits, DeviceStatus* status,
                       SplitFix* fix_list, uint32_t fix_cap, uint32_t n_tabs, uint32_t n_tiles) {
@@ -203,6 +239,7 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
     __shared__ ProdInfo s_info[kNumPatterns * kProdMax];
     __shared__ uint8_t s_skip[kNumPatterns * 2 * kCtxMax];
     __shared__ uint8_t s_start[kNumPatterns];
+    __shared__ SplitEnv s_env;
     const uint32_t t = threadIdx.x, lane = t & 31u;
     const bool multi = b.vocab_ids != nullptr;
     const uint32_t pat0 = vs.v[0].pattern_id;
@@ -217,13 +254,20 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
         if (t < kNumPatterns) s_start[t] = uc.prod_start[t];
         s_cls[t] = uc.cls256[t];
     }
+    uint32_t pats = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < kMaxVocabs; ++i) pats |= (vs.v[i].pattern_id & 15u) << (4u * i);
+    if (t == 0) {
+        SplitEnv e;
+        e.s = b.bytes; e.pstart_bits = pstart_bits; e.block_prompt = block_prompt; e.offsets = b.offsets; e.vocab_ids = b.vocab_ids;
+        e.status = status; e.fix_list = fix_list; e.total = b.total_bytes; e.fix_cap = fix_cap; e.pats = pats; e.n_tabs = n_tabs;
+        e.fsm = s_fsm; e.ctx = s_ctx; e.info = s_info; e.skip = s_skip; e.start = s_start; e.tabs = reinterpret_cast<const uint8_t*>(s_dyn);
+        s_env = e;
+    }
     __syncthreads();
     const uint8_t* __restrict__ s = b.bytes;
     const uint64_t total = b.total_bytes;
     const bool aligned = (reinterpret_cast<uintptr_t>(s) & 15u) == 0u;
-    uint32_t pats = 0;
-#pragma unroll
-    for (uint32_t i = 0; i < kMaxVocabs; ++i) pats |= (vs.v[i].pattern_id & 15u) << (4u * i);
     const uint8_t* const tabs = reinterpret_cast<const uint8_t*>(s_dyn);
     const uint32_t warps_total = gridDim.x * (kSplitCta / 32u);
 
@@ -255,7 +299,14 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
                                                    make_uint4(cw[0], cw[1], cw[2], cw[3]), P, status);
                 cw[0] = r.x; cw[1] = r.y; cw[2] = r.z; cw[3] = r.w;
             }
-            if (multi) pat = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, base);
+        }
+        if (multi) {    // the pattern at my block's first byte: one query per warp, repeated only by lanes behind a prompt start
+            const uint32_t starts_before = __ballot_sync(kFull, have && (P & 0xFFFFu)) & ((2u << lane) - 1u);
+            uint32_t p0 = 0;
+            if (lane == 0 && have) p0 = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, base);
+            else if (lane == 0 && blk < 0 && total) p0 = pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, 0);
+            p0 = __shfl_sync(kFull, p0, 0);
+            pat = (have && starts_before) ? pattern_at(b.offsets, b.vocab_ids, pats, block_prompt, base) : p0;
         }
         // ---- the exact context at the end of my block: the context automaton over its last three characters
         uint32_t endc = kCtxStart;
@@ -304,7 +355,8 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
         uint32_t rem = 0;               // remembered positions, relative to base: alc | last << 8 | lbe << 16
         uint32_t st = owner ? ((1u + left_ctx) << PE_NEXT_SHIFT) : 0u;     // row of my state in the product table; 0 = DONE; NOSYNC(context to my left)
         const uint8_t* tab = tabs + (n_tabs == 1 ? 0u : pat) * kProdTableBytes;
-        // one byte: ONE lookup in the product table.  kb = first byte index of the group of four, i = index in the group.
+        // one byte: ONE lookup in the product table.  kb = first byte index of the group of four, i = index in the group.  The
+        // hot loop is these ~20 instructions four times over, plus the three conditional marks; everything else is a call.
         auto step = [&](const uint32_t i, const uint32_t cb, const uint32_t kb, const uint32_t kb3, const uint32_t sync_mask, uint32_t& gm) {
             const uint2 e = *reinterpret_cast<const uint2*>(tab + st + ((cb & 15u) << 3));
             uint32_t lo = e.x, hi = e.y;
@@ -312,15 +364,7 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
                 if (lo & PE_EMIT_ALC) mine |= 1u << (rem & 31u);
                 if (lo & PE_EMIT_LAST) mine |= 1u << ((rem >> 8) & 31u);
                 if (lo & PE_EMIT_LBE) mine |= 1u << ((rem >> 16) & 31u);
-                if (lo & PE_RARE) {
-                    const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
-                    const uint32_t q = pi.q == PQ_NOSYNC ? (s_ctx[(pat & 1u) * kCtx16Size + (pi.ctx << 4) + (cb & 15u)] >> 8) : pi.q;   // (first sync point: the state the context names)
-                    const uint32_t a = s_fsm[pat * kFsm16Size + q * 16 + (cb & 15u)];
-                    const uint32_t nctx = s_info[pat * kProdMax + ((lo & PE_NEXT_MASK) >> PE_NEXT_SHIFT)].ctx;
-                    lo = split_rare(lo, a, kb + i, base, total, s, pstart_bits, status, fix_list, fix_cap, s_skip + pat * 2 * kCtxMax,
-                                    (a & A_RESOLVE) ? 0u : nctx);
-                    if (lo == 0u) hi = 0u;
-                }
+                if (lo & PE_RARE) { lo = split_rare(&s_env, lo, st, cb, kb + i, pat, base); if (lo == 0u) hi = 0u; }
             }
             if (lo & sync_mask) { lo = 0u; hi = 0u; }               // hand-over: the next block's owner started exactly here
             gm |= (lo & PE_B_NOW) << i;
@@ -337,25 +381,16 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
             const uint32_t kb = 4u * j, kb3 = kb * 0x010101u;
             const uint32_t Pw = (P >> kb) & 15u;
             const uint32_t sync_mask = j >= 4 ? static_cast<uint32_t>(PE_SYNC) : 0u;
-            uint32_t gm = 0;            // the group's A_B_NOW marks
-            if (Pw && st != 0u) {       // a prompt starts inside these four bytes (or the data ends): rare, one byte at a time
-#pragma unroll 1
-                for (uint32_t i = 0; i < 4; ++i) {
-                    if (((Pw >> i) & 1u) && st != 0u) {
-                        const uint4 r = split_prompt_start(st, pat, kb + i, rem, base, total, s_fsm, s_info, s_start, s, pstart_bits, status, fix_list, fix_cap,
-                                                           b.offsets, b.vocab_ids, pats, block_prompt);
-                        st = r.x; mine |= r.y; pat = r.z;
-                        tab = tabs + (n_tabs == 1 ? 0u : pat) * kProdTableBytes;
-                    }
-                    uint32_t g1 = 0;
-                    step(0, (word >> (8u * i)) & 0xFFu, kb + i, kb3 + i * 0x010101u, sync_mask, g1);
-                    gm |= g1 << i;
-                }
+            if (Pw && st != 0u) {       // a prompt starts inside these four bytes (or the data ends): rare
+                const uint4 r = split_prompt_group(&s_env, word, Pw, kb, st, pat, rem, base, sync_mask);
+                st = r.x; mine |= r.y; rem = r.z; pat = r.w;
+                tab = tabs + (n_tabs == 1 ? 0u : pat) * kProdTableBytes;
             } else {
+                uint32_t gm = 0;            // the group's A_B_NOW marks
 #pragma unroll
                 for (uint32_t i = 0; i < 4; ++i) step(i, (word >> (8u * i)) & 0xFFu, kb, kb3, sync_mask, gm);
+                mine |= gm << kb;
             }
-            mine |= gm << kb;
         }
         // ---- a walker that crossed the whole next block: the per-character walker goes on from its state
         if (st != 0u) {

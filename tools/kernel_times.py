@@ -31,7 +31,7 @@ for nm in names:
         acc = {k: 0.0 for k in N.KERNEL_NAMES}
         reps = 4
         for i in range(reps + 2):
-            nt = plug.ctx.encode_batch_device(n, d_bytes.data_ptr(), total, d_offs.data_ptr(), vid.data_ptr(), d_ids.data_ptr(), d_ids.numel(),
+            nt = plug.ctx.encode_batch_device(n, d_bytes.data_ptr(), total, d_offs.data_ptr(), vid.data_ptr() if slot else None, d_ids.data_ptr(), d_ids.numel(),   # slot 0: the single-vocabulary path (no vocab ids)
                                               d_off.data_ptr(), d_cnt.data_ptr(), s, sync=True)
             pr = plug.ctx.profile_read()
             if i >= 2:
