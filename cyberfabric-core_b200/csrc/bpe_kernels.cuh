@@ -1189,6 +1189,8 @@ __device__ __forceinline__ void flag_parts(const uint32_t* id, uint32_t* copy_to
 constexpr uint32_t kDeferMaxParts = 4096;   // K2c: parts whose merge state fits 64 KB of shared memory
 constexpr uint32_t kListSmemBytes = kDeferMaxParts * 16;
 constexpr uint32_t kListMaxRank = (1u << 20) - 1u;   // K2c packs rank << 12 | position into 32 bits
+// the big pieces bpe_list_kernel takes (from their bytes); bpe_long_kernel keeps the rest
+__device__ __forceinline__ bool list_kernel_takes(const TablesView& T, uint32_t n_bytes) { return n_bytes <= kDeferMaxParts && T.n_ranks < kListMaxRank; }
 
 #ifdef CUSIM_EMULATOR
 #define CFBPE_DYN_SMEM(name) uint32_t* const name = reinterpret_cast<uint32_t*>(cusim::dyn_smem())
@@ -1216,6 +1218,9 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
         const TablesView T = vs.v[lp.vocab];
         const uint8_t* __restrict__ p = b.bytes + lp.start;
         const uint32_t n = static_cast<uint32_t>(lp.end - lp.start);
+#ifndef CFBPE_NO_DEFER
+        if (item < n_big && list_kernel_takes(T, n)) continue;       // a big piece: bpe_list_kernel has it, from its bytes, at the same time
+#endif
         // state of the piece: shared memory for pieces of <= kMedSmem bytes (most of them), else its slice of scratch
         uint32_t* const gid = ids_by_pos + lp.start;
         const bool in_smem = n <= kMedSmem;
@@ -1263,13 +1268,6 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
                 m = array_compact<8>(id, rk, m, lane, rmin);
                 continue;
             }
-#ifndef CFBPE_NO_DEFER
-            if (m <= kDeferMaxParts && T.n_ranks < kListMaxRank) {   // bpe_list_kernel goes on from here, in shared memory
-                if (lane == 0) { long_list[slot].pad = m; atomicAdd(&status->defer_n, 1u); atomicAdd(&status->defer_parts, static_cast<unsigned long long>(m)); CFBPE_DBG_COUNT(0); }
-                deferred = true;
-                break;
-            }
-#endif
             if (lane == 0) CFBPE_DBG_COUNT(5);
             list_rounds_multi(T, id, rk, a0, a1, m, lane);
             __syncwarp();
@@ -1282,28 +1280,135 @@ bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* st
     }
 }
 
-// K2c: the list phase of the pieces K2b deferred (more than kMedSmem bytes, at most kDeferMaxParts parts left after the
-// batched rounds).  One CTA of kListWarps warps per piece with the whole merge state -- id | key | link | claim, 16 bytes
-// per part -- in 64 KB of dynamic shared memory, parallel-cut rounds (list_rounds_par): a round costs one table round trip
-// and a few hundred cycles of shared-memory work and takes ~20 merges.  Three such CTAs fit an SM.  Tickets run over the
-// big end of the long-piece list.
+// ---- batched rounds by a whole CTA (the warp forms above, array_round / array_compact, walk the array 32 parts at a time:
+//      on a 4 KiB piece that is 128 trips per pass, and it was the 0.45 ms head of the long-piece chain).  Thread t owns the
+//      contiguous parts [t * c, t * c + c), c = ceil(m / threads) <= kCtaChunk.
+constexpr uint32_t kCtaChunk = 16;        // parts per thread: kListWarps * 32 * kCtaChunk >= kDeferMaxParts
+
+// one batched round on the compact arrays id[] / rk[] of m parts (same result as array_round).
+// s_scan: blockDim.x + 2 words; s_sel: kDeferMaxParts / 32 words (which pairs merge this round).
+__device__ __forceinline__ void cta_array_round(const TablesView& T, uint32_t* id, uint32_t* rk, uint32_t* a0, uint32_t* a1,
+                                                uint32_t m, uint32_t rmin, uint32_t* s_scan, uint32_t* s_sel) {
+    const uint32_t P = blockDim.x, t = threadIdx.x;
+    const uint32_t c = (m + P - 1) / P;
+    const uint32_t lo = t * c < m ? t * c : m, hi = lo + c < m ? lo + c : m;
+    // -- candidates of my chunk: are they all candidates, and how many consecutive ones end the chunk
+    uint32_t tail = 0, all = 1;
+    for (uint32_t i = lo; i < hi; ++i) {
+        const bool cand = (i + 1 < m) && rk[i] == rmin;
+        if (cand) ++tail; else { tail = 0; all = 0; }
+    }
+    s_scan[t] = (all << 31) | tail;
+    if (t == 0) s_scan[P] = kNone;          // the cut
+    for (uint32_t w = t; w < kDeferMaxParts / 32; w += P) s_sel[w] = 0;
+    __syncthreads();
+    // -- consecutive candidates right before my chunk (walk back over the chunks that are candidates throughout); then select
+    //    every second pair of a run of candidates, counted from the run's start (overlapping pairs: leftmost first)
+    uint32_t cnt = 0;
+    for (uint32_t u = t; u > 0 && lo < m;) {
+        const uint32_t e = s_scan[--u];
+        cnt += e & 0x7FFFFFFFu;
+        if (!(e >> 31)) break;
+    }
+    uint32_t sel_bits = 0;
+    for (uint32_t i = lo; i < hi; ++i) {
+        const bool cand = (i + 1 < m) && rk[i] == rmin;
+        if (cand && !(cnt & 1u)) { sel_bits |= 1u << (i - lo); atomicOr(&s_sel[i >> 5], 1u << (i & 31)); }
+        cnt = cand ? cnt + 1 : 0;
+    }
+    __syncthreads();
+    // -- look up the pairs each merge creates, find the cut
+    uint32_t m2_bits = 0;
+    for (uint32_t bts = sel_bits; bts; bts &= bts - 1) {
+        const uint32_t k = static_cast<uint32_t>(__ffs(bts)) - 1u, i = lo + k;
+        const bool selm2 = i >= 2 && ((s_sel[(i - 2) >> 5] >> ((i - 2) & 31)) & 1u);     // the pair two to the left merges too: my left neighbour will be rmin
+        uint32_t L = kNone, R = kNone;
+        if (i > 0) L = pair_lookup(T, selm2 ? rmin : id[i - 1], rmin);
+        if (i + 2 < m) R = pair_lookup(T, rmin, id[i + 2]);
+        a0[i] = L; a1[i] = R;
+        if (selm2) m2_bits |= 1u << k;
+        if (L < rmin || R < rmin) atomicMin(&s_scan[P], i);               // the sequential loop would take that new pair next: cut after this merge
+    }
+    __syncthreads();
+    const uint32_t cut = s_scan[P];
+    // -- apply the merges up to the cut: right ranks first, then left ranks (a left write may replace a neighbour's right one)
+    for (uint32_t bts = sel_bits; bts; bts &= bts - 1) {
+        const uint32_t i = lo + static_cast<uint32_t>(__ffs(bts)) - 1u;
+        if (i > cut) break;
+        id[i] = rmin; id[i + 1] = kNone; rk[i] = a1[i];
+    }
+    __syncthreads();
+    for (uint32_t bts = sel_bits; bts; bts &= bts - 1) {
+        const uint32_t k = static_cast<uint32_t>(__ffs(bts)) - 1u, i = lo + k;
+        if (i > cut) break;
+        if (i > 0) rk[((m2_bits >> k) & 1u) ? i - 2 : i - 1] = a0[i];
+    }
+    __syncthreads();
+}
+
+// squeeze the dead slots out (whole CTA); kPosBits != 0: rk[] holds list-mode keys, turned back into ranks.  Returns the new part
+// count; rmin_out = the smallest rank left.  s_scan: blockDim.x + 2 words.
+template <uint32_t kPosBits>
+__device__ __forceinline__ uint32_t cta_array_compact(uint32_t* id, uint32_t* rk, uint32_t m, uint32_t& rmin_out, uint32_t* s_scan) {
+    const uint32_t P = blockDim.x, t = threadIdx.x, lane = t & 31u, wid = t >> 5;
+    const uint32_t c = (m + P - 1) / P;
+    const uint32_t lo = t * c < m ? t * c : m, hi = lo + c < m ? lo + c : m;
+    uint32_t vid[kCtaChunk], vrk[kCtaChunk];
+    uint32_t keep = 0, nmin = kNone;
+#pragma unroll
+    for (uint32_t k = 0; k < kCtaChunk; ++k) {
+        const uint32_t i = lo + k;
+        vid[k] = (k < c && i < hi) ? id[i] : kNone;
+        uint32_t r = (k < c && i < hi) ? rk[i] : kNone;
+        if (kPosBits && r != kNone) r >>= kPosBits;                      // kNoKey == kNone
+        vrk[k] = r;
+        if (vid[k] != kNone) { ++keep; nmin = r < nmin ? r : nmin; }
+    }
+    // exclusive scan of the keep counts over the CTA; minimum of the ranks kept
+    uint32_t x = keep;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(kFull, x, d); if (lane >= d) x += o; }
+    nmin = warp_min_u32(nmin);
+    if (lane == 31) s_scan[wid] = x;
+    if (lane == 0) s_scan[32 + wid] = nmin;
+    __syncthreads();                                                     // (also: everybody has read its chunk)
+    uint32_t woff = 0, total = 0, rmin = kNone;
+    for (uint32_t w = 0; w < (P >> 5); ++w) { const uint32_t v = s_scan[w]; if (w < wid) woff += v; total += v; const uint32_t r = s_scan[32 + w]; rmin = r < rmin ? r : rmin; }
+    uint32_t pos = woff + x - keep;
+#pragma unroll
+    for (uint32_t k = 0; k < kCtaChunk; ++k) if (vid[k] != kNone) { id[pos] = vid[k]; rk[pos] = vrk[k]; ++pos; }
+    __syncthreads();
+    rmin_out = rmin;
+    return total;
+}
+
+// K2c: the big pieces (more than kBigPiece bytes, at most kDeferMaxParts), one CTA of kListWarps warps per piece, FROM THEIR
+// BYTES -- batched rounds by the whole CTA while they merge a useful fraction, then parallel-cut rounds (list_rounds_par) -- with
+// the whole merge state (id | key | link | claim, 16 bytes per part) in 64 KB of dynamic shared memory.  It does not wait for
+// K2b any more (which keeps the pieces of 33..kBigPiece bytes and the rare giants): the long-piece chain was K2b's batched
+// rounds on global scratch (0.45 ms, one warp per piece) + this kernel (0.58 ms); now the two kernels run side by side.
+// A list round costs one table round trip and a few hundred cycles of shared-memory work and takes ~20 merges.
 #ifndef CFBPE_LIST_WARPS
 #define CFBPE_LIST_WARPS 8
 #endif
 constexpr uint32_t kListWarps = CFBPE_LIST_WARPS;
+static_assert(kListWarps * 32 * kCtaChunk >= kDeferMaxParts, "a thread's chunk of the batched rounds holds kCtaChunk parts");
+
 __global__ void __launch_bounds__(kListWarps * 32, 3)
 bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
     CFBPE_DYN_SMEM(s_dyn);
     __shared__ uint32_t s_red[3 * kListWarps + 2];
-    __shared__ uint32_t s_item, s_m, s_rmin;
+    __shared__ uint32_t s_item, s_tok;
     __shared__ uint32_t s_dirty[kListWarps * 32];
+    __shared__ uint32_t s_scan[kListWarps * 32 + 64];
+    __shared__ uint32_t s_sel[kDeferMaxParts / 32];
     const uint32_t n_big = status->long_overflow ? 0u : status->n_big;
     uint32_t* const id = s_dyn;
     uint32_t* const kk = s_dyn + kDeferMaxParts;
     uint32_t* const link = s_dyn + 2 * kDeferMaxParts;
     uint32_t* const claim = s_dyn + 3 * kDeferMaxParts;
-    (void)b;
+    (void)sc;
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(&status->defer_next, 1u);
         __syncthreads();
@@ -1311,33 +1416,52 @@ bpe_list_kernel(BatchView b, VocabSet vs, const LongPiece* __restrict__ long_lis
         __syncthreads();
         if (item >= n_big) break;
         const LongPiece lp = long_list[long_cap - 1 - item];
-        uint32_t m = lp.pad;
-        if (!m) continue;
         const TablesView T = vs.v[lp.vocab];
+        const uint32_t n = static_cast<uint32_t>(lp.end - lp.start);
+        if (!list_kernel_takes(T, n)) continue;                          // a giant: K2b's global-memory path
+        const uint8_t* __restrict__ p = b.bytes + lp.start;
         uint32_t* const gid = ids_by_pos + lp.start;
-        const uint32_t* const grk = sc.rank + lp.start;
-        for (uint32_t i = threadIdx.x; i < m; i += kListWarps * 32) { id[i] = gid[i]; kk[i] = grk[i]; }
+        // ---- whole-piece shortcut (CoreBPE: `if piece in ranks`)
+        if (n <= T.max_token_len) {
+            if (threadIdx.x == 0) s_tok = piece_lookup(T, p, n);
+            __syncthreads();
+            const uint32_t tok = s_tok;
+            __syncthreads();
+            if (tok != kNone) {
+                if (threadIdx.x == 0) { gid[0] = tok; atomicOr(&tok_bits[lp.start >> 5], 1u << (lp.start & 31)); atomicAdd(&status->long_tokens, 1ull); }
+                continue;
+            }
+        }
+        // ---- parts = bytes
+        uint32_t m = n, rmin = kNone;
+        for (uint32_t i = threadIdx.x; i < n; i += kListWarps * 32) {
+            const uint32_t c0 = p[i];
+            id[i] = T.byte2id[c0];
+            const uint32_t r = (i + 1 < n) ? T.bytepair[(c0 << 8) | p[i + 1]] : kNone;
+            kk[i] = r;
+            rmin = r < rmin ? r : rmin;
+        }
+        rmin = warp_min_u32(rmin);
+        if ((threadIdx.x & 31) == 0) s_scan[threadIdx.x >> 5] = rmin;
         __syncthreads();
-        for (;;) {
+        rmin = kNone;
+        for (uint32_t w = 0; w < kListWarps; ++w) { const uint32_t r = s_scan[w]; rmin = r < rmin ? r : rmin; }
+        __syncthreads();
+        // ---- rounds: batched rounds while they merge a useful fraction (runs, periods: O(log n) rounds), list rounds otherwise; a
+        //      list phase that meets many pairs of one rank comes back for a batched round
+        bool counted = false;
+        while (rmin != kNone) {
+            cta_array_round(T, id, kk, link, claim, m, rmin, s_scan, s_sel);
+            const uint32_t before = m;
+            m = cta_array_compact<0>(id, kk, m, rmin, s_scan);
+            if (rmin == kNone || (before - m) * 8u >= m || m <= 32u) continue;
+            if (!counted && threadIdx.x == 0) { atomicAdd(&status->defer_n, 1u); atomicAdd(&status->defer_parts, static_cast<unsigned long long>(m)); CFBPE_DBG_COUNT(0); }
+            counted = true;
             const bool done = list_rounds_par<kListWarps, 12>(T, id, kk, link, claim, m, s_red, s_dirty);
             __syncthreads();
             if (done) break;
-            // a stretch of same-rank pairs: batched rounds, by the first warp (their lookups are all the same few
-            // table slots, L1 hits; the passes over <= 4096 words of shared memory are a few microseconds)
             if (threadIdx.x == 0) CFBPE_DBG_COUNT(2);
-            if (threadIdx.x < 32) {
-                uint32_t rmin, mm = array_compact<12>(id, kk, m, threadIdx.x, rmin);
-                while (rmin != kNone) {
-                    array_round(T, id, kk, link, claim, mm, rmin, threadIdx.x);
-                    const uint32_t before = mm;
-                    mm = array_compact<0>(id, kk, mm, threadIdx.x, rmin);
-                    if ((before - mm) * 8u < mm && mm > 32u) break;
-                }
-                if (threadIdx.x == 0) { s_m = mm; s_rmin = rmin; }
-            }
-            __syncthreads();
-            m = s_m;
-            if (s_rmin == kNone) break;
+            m = cta_array_compact<12>(id, kk, m, rmin, s_scan);        // a stretch of same-rank pairs: back to batched rounds
         }
         __syncthreads();
         if (threadIdx.x < 32) flag_parts(id, gid, m, lp.start, tok_bits, status, threadIdx.x);

@@ -71,7 +71,10 @@ struct cfbpe_ctx {
     uint32_t* d_dec_sums = nullptr;      // decode: bytes per tile of kDecodeTile tokens ...
     uint64_t* d_dec_base = nullptr;      // ... and their exclusive scan
     cudaStream_t aux_stream = nullptr;   // the long-piece kernel runs here, next to the short-piece kernel
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t aux2_stream = nullptr;  // ... and the big-piece kernel here, next to both
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+    cudaStream_t side2[kSideStreams] = {};       // pipelined host calls: the big-piece kernel of sub-batch k
+    cudaEvent_t ev_list[kMaxPipeChunks] = {};
     cudaEvent_t ev_ws = nullptr;         // recorded at the end of an asynchronous device-path call: the workspace is busy until then
     bool ws_pending = false;             // ... and whether one is outstanding
     uint64_t dev_out_cap = 0;            // out_cap of the last device-path call (cfbpe_device_status reports ENOSPC against it)
@@ -254,12 +257,17 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         CK(cudaEventRecord(ctx->ev_scan[k], ss));
         if (trace) CK(cudaEventRecord(ctx->trace[k][1], ss));
         CK(cudaStreamWaitEvent(ck, ctx->ev_scan[k], 0));
+        cudaStream_t ss2 = ctx->side2[k % kSideStreams];
+        CK(cudaStreamWaitEvent(ss2, ctx->ev_scan[k], 0));
+        enqueue_list(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ss2, static_cast<ProfEvents*>(nullptr));   // the big pieces, beside everything else
+        CK(cudaEventRecord(ctx->ev_list[k], ss2));
         enqueue_long(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ss, static_cast<ProfEvents*>(nullptr));   // tail overlaps what follows on cs
         if (trace) CK(cudaEventRecord(ctx->trace[k][3], ss));
         enqueue_short(b, ctx->vs, w, static_cast<uint32_t>(ctx->sm_count * 4), ck, static_cast<ProfEvents*>(nullptr));
         CK(cudaEventRecord(ctx->ev_front[k], ck));
         if (trace) CK(cudaEventRecord(ctx->trace[k][2], ck));
         CK(cudaStreamWaitEvent(ss, ctx->ev_front[k], 0));
+        CK(cudaStreamWaitEvent(ss, ctx->ev_list[k], 0));
         enqueue_count(b, w, ss, static_cast<ProfEvents*>(nullptr));
         if (k) CK(cudaStreamWaitEvent(ss, ctx->ev_chain[k - 1], 0));    // token ranks chain through DeviceStatus::tok_end: only the scan waits
         enqueue_scan(b, w, ss, static_cast<ProfEvents*>(nullptr), k ? &ctx->d_status_arr[k - 1].tok_end : nullptr);
@@ -294,6 +302,7 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
     CK(cudaStreamSynchronize(cs));
     for (int k = 1; k < kFrontStreams; ++k) CK(cudaStreamSynchronize(ctx->front[k]));
     for (int k = 0; k < kSideStreams; ++k) CK(cudaStreamSynchronize(ctx->side[k]));
+    for (int k = 0; k < kSideStreams; ++k) CK(cudaStreamSynchronize(ctx->side2[k]));
     if (trace && !err) {
         fprintf(stderr, "pipe trace (ms since the first upload was enqueued): sub-batch bytes | h2d split short long_end back d2h\n");
         for (int k = 0; k < nc; ++k) {
@@ -335,7 +344,8 @@ int run_host(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const uint64_t* o
 
     BatchView b{ctx->d_bytes, ctx->d_offsets, vocab_ids ? ctx->d_vocab_ids : nullptr, n, total};
     enqueue_encode(b, ctx->vs, ctx->uc, ctx->ws, want_ids ? ctx->d_out_ids : nullptr, ctx->max_bytes, ctx->d_out_offsets,
-                   ctx->d_out_counts, static_cast<uint32_t>(ctx->sm_count * 4), s, prof ? s : ctx->aux_stream, ctx->ev_fork, ctx->ev_join, prof);
+                   ctx->d_out_counts, static_cast<uint32_t>(ctx->sm_count * 4), s, prof ? s : ctx->aux_stream, prof ? s : ctx->aux2_stream,
+                   ctx->ev_fork, ctx->ev_join, ctx->ev_join2, prof);
     CK(cudaGetLastError());
     if (prof) cudaEventRecord(prof->d2h[0], s);
     CK(cudaMemcpyAsync(ctx->h_status, ctx->ws.status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, s));
@@ -441,14 +451,18 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
         for (int k = 1; ok && k < kFrontStreams; ++k)
             ok = cudaStreamCreateWithPriority(&ctx->front[k], cudaStreamNonBlocking, prio_hi + (k < levels ? k : levels - 1)) == cudaSuccess;
         for (int k = 0; ok && k < kSideStreams; ++k) ok = cudaStreamCreateWithPriority(&ctx->side[k], cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        for (int k = 0; ok && k < kSideStreams; ++k) ok = cudaStreamCreateWithPriority(&ctx->side2[k], cudaStreamNonBlocking, prio_hi) == cudaSuccess;
     }
     {   // the long-piece kernels are latency-bound and small: their CTAs go first, the short-piece kernels fill the rest
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         ok = ok && cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&ctx->aux2_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
     }
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_ws, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; ok && k < kMaxPipeChunks; ++k) ok = cudaEventCreateWithFlags(&ctx->ev_list[k], cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; ok && k < kMaxPipeChunks; ++k) ok = cudaEventCreateWithFlags(&ctx->ev_scan[k], cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; ok && k < kMaxPipeChunks; ++k)
         ok = cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming) == cudaSuccess &&
@@ -522,6 +536,10 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     for (int k = 0; k < kSideStreams; ++k) if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
     for (int k = 0; k < kMaxPipeChunks; ++k) if (ctx->ev_scan[k]) cudaEventDestroy(ctx->ev_scan[k]);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->aux2_stream) cudaStreamDestroy(ctx->aux2_stream);
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
+    for (int k = 0; k < kSideStreams; ++k) if (ctx->side2[k]) cudaStreamDestroy(ctx->side2[k]);
+    for (int k = 0; k < kMaxPipeChunks; ++k) if (ctx->ev_list[k]) cudaEventDestroy(ctx->ev_list[k]);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_ws) cudaEventDestroy(ctx->ev_ws);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -676,7 +694,8 @@ int cfbpe_encode_batch_device(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t*
     if (prof) { std::memset(prof->launched, 0, sizeof prof->launched); cudaEventRecord(prof->total[0], s); cudaEventRecord(prof->h2d[0], s); cudaEventRecord(prof->h2d[1], s); }
     BatchView b{d_bytes, d_offsets, d_vocab_ids, n_prompts, total_bytes};
     enqueue_encode(b, ctx->vs, ctx->uc, ctx->ws, d_out_ids, out_cap, d_out_offsets, d_out_counts,
-                   static_cast<uint32_t>(ctx->sm_count * 4), s, prof ? s : ctx->aux_stream, ctx->ev_fork, ctx->ev_join, prof);   // profiling: one stream, so that the per-kernel times do not overlap
+                   static_cast<uint32_t>(ctx->sm_count * 4), s, prof ? s : ctx->aux_stream, prof ? s : ctx->aux2_stream,
+                   ctx->ev_fork, ctx->ev_join, ctx->ev_join2, prof);   // profiling: one stream, so that the per-kernel times do not overlap
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_ws, s));
     ctx->ws_pending = true;

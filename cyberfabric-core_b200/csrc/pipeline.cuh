@@ -124,16 +124,21 @@ inline void enqueue_short(const BatchView& b, const VocabSet& vs, const Workspac
 #endif
 }
 
+// K2b: the pieces of 33 .. kBigPiece bytes (and the rare giants the list kernel cannot hold), one warp each
 template <typename Stream, typename Prof>
 inline void enqueue_long(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
     if (!b.total_bytes) return;
     CFBPE_MARK(prof, K_LONG, stream, true);
     CFBPE_LAUNCH(bpe_long_kernel, (long_grid / 4) * kLongCtasPerSm, kLongWarps * 32, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
     CFBPE_MARK(prof, K_LONG, stream, false);
+}
+// K2c: the big pieces, one CTA each, from their bytes -- independent of K2b (its own stream where the caller has one): two 64 KB
+// CTAs per SM (long_grid = 4 x SM count), so that the short-piece kernels on the other stream keep ~100 KB of shared memory per SM
+template <typename Stream, typename Prof>
+inline void enqueue_list(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
+    if (!b.total_bytes) return;
 #ifndef CFBPE_NO_DEFER
     CFBPE_MARK(prof, K_LIST, stream, true);
-    // the list phase of the big pieces K2b deferred: two 64 KB CTAs per SM (long_grid = 4 x SM count), so that the short-piece
-    // kernels on the other stream keep ~100 KB of shared memory per SM
     CFBPE_LAUNCH_SMEM(bpe_list_kernel, (long_grid / 4) * kListCtasPerSm, kListWarps * 32, kListSmemBytes, stream, b, vs, w.long_list, w.status, w.long_cap, w.ids_by_pos, w.lscratch, w.tok_bits);
     CFBPE_MARK(prof, K_LIST, stream, false);
 #endif
@@ -177,18 +182,21 @@ inline void enqueue_back(const BatchView& b, const Workspace& w, uint32_t* out_i
     enqueue_emit(b, w, out_ids, out_cap, out_offsets, out_counts, stream, prof);
 }
 
-// The whole path.  `aux` is a second stream for the long-piece kernel (pass the same stream to run everything in order);
-// CFBPE_FORK / CFBPE_JOIN order the two.  out_ids may be nullptr (count only).  Everything is asynchronous.
+// The whole path.  `aux` / `aux2` are streams of their own for the two long-piece kernels (pass the main stream to run everything
+// in order); CFBPE_FORK / CFBPE_JOIN order them.  out_ids may be nullptr (count only).  Everything is asynchronous.
 template <typename Stream, typename Prof, typename Ev>
 inline void enqueue_encode(const BatchView& b, const VocabSet& vs, const UcTables& uc, const Workspace& w,
                            uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_counts,
-                           uint32_t long_grid, Stream stream, Stream aux, Ev ev_fork, Ev ev_join, Prof* prof,
+                           uint32_t long_grid, Stream stream, Stream aux, Stream aux2, Ev ev_fork, Ev ev_join, Ev ev_join2, Prof* prof,
                            const uint64_t* token_base = nullptr) {
     enqueue_split(b, vs, uc, w, stream, prof);
+    CFBPE_FORK(stream, aux2, ev_fork);
+    enqueue_list(b, vs, w, long_grid, aux2, prof);
     CFBPE_FORK(stream, aux, ev_fork);
     enqueue_long(b, vs, w, long_grid, aux, prof);
     enqueue_short(b, vs, w, long_grid, stream, prof);
     CFBPE_JOIN(stream, aux, ev_join);
+    CFBPE_JOIN(stream, aux2, ev_join2);
     enqueue_back(b, w, out_ids, out_cap, out_offsets, out_counts, stream, prof, token_base);
 }
 

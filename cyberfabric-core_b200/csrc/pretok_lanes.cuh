@@ -226,7 +226,10 @@ constexpr uint32_t kSplitWarpOwned = 30;            // blocks of 16 bytes a WARP
 
 // n_tabs: product tables in shared memory -- 1 (single-vocabulary batch: the table of pattern pat0) or kNumPatterns
 #ifndef CFBPE_SPLIT_CTAS
-#define CFBPE_SPLIT_CTAS 5
+#define CFBPE_SPLIT_CTAS 4
+#endif
+#ifndef CFBPE_SPLIT_UNROLL
+#define CFBPE_SPLIT_UNROLL 1       // copies of the step in the hot loop (1 | 2 | 4); measured: profiles/ab_variants_r02g.txt
 #endif
 __global__ void __launch_bounds__(kSplitCta, CFBPE_SPLIT_CTAS)
 pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __restrict__ pstart_bits,
@@ -387,8 +390,16 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
                 tab = tabs + (n_tabs == 1 ? 0u : pat) * kProdTableBytes;
             } else {
                 uint32_t gm = 0;            // the group's A_B_NOW marks
+#if CFBPE_SPLIT_UNROLL == 4
 #pragma unroll
                 for (uint32_t i = 0; i < 4; ++i) step(i, (word >> (8u * i)) & 0xFFu, kb, kb3, sync_mask, gm);
+#elif CFBPE_SPLIT_UNROLL == 2
+#pragma unroll 1
+                for (uint32_t i = 0; i < 4; i += 2) { step(i, (word >> (8u * i)) & 0xFFu, kb, kb3, sync_mask, gm); step(i + 1, (word >> (8u * i + 8u)) & 0xFFu, kb, kb3, sync_mask, gm); }
+#else
+#pragma unroll 1
+                for (uint32_t i = 0; i < 4; ++i) step(i, (word >> (8u * i)) & 0xFFu, kb, kb3, sync_mask, gm);
+#endif
                 mine |= gm << kb;
             }
         }

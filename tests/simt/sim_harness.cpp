@@ -155,7 +155,7 @@ __attribute__((visibility("default"))) int sim_encode_batch(void* const* vocabs,
                 pstart.data(), bprompt.data()};
     vs.loaded_mask = n_vocabs >= 32 ? 0xFFFFFFFFu : ((1u << n_vocabs) - 1u);
     int* prof = nullptr;
-    enqueue_encode(b, vs, uc_tables(), w, out_ids, out_cap, out_offsets, out_counts, 4u, 0, 0, 0, 0, prof);
+    enqueue_encode(b, vs, uc_tables(), w, out_ids, out_cap, out_offsets, out_counts, 4u, 0, 0, 0, 0, 0, 0, prof);
     if (n_long_out) *n_long_out = static_cast<uint64_t>(st.n_long) + st.n_big;
     if (st.bad_utf8) return CFBPE_EILSEQ;
     if (st.long_overflow || st.miss_overflow) return CFBPE_EIO;
