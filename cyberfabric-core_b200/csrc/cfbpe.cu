@@ -456,8 +456,12 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     {   // the long-piece kernels are latency-bound and small: their CTAs go first, the short-piece kernels fill the rest
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        ok = ok && cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
-        ok = ok && cudaStreamCreateWithPriority(&ctx->aux2_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+#ifndef CFBPE_AUX_PRIO_LOW
+#define CFBPE_AUX_PRIO_LOW 0      // A/B: 1 = the long-piece streams at the LOWEST priority (they take what the short-piece kernels leave)
+#endif
+        const int aux_prio = CFBPE_AUX_PRIO_LOW ? prio_lo : prio_hi;
+        ok = ok && cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, aux_prio) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&ctx->aux2_stream, cudaStreamNonBlocking, aux_prio) == cudaSuccess;
     }
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_ws, cudaEventDisableTiming) == cudaSuccess;
