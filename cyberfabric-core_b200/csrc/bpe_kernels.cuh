@@ -1,14 +1,13 @@
 // bpe_kernels.cuh -- the encode hot path as CUDA kernels for sm_100a.
 //
 //   K1  pretok_split_kernel (+ pretok_fixup_kernel)   packed prompt bytes -> piece-start bitmask      
-//   K2s bpe_encode_pieces_kernel<1>   finds the pieces longer than 32 bytes (work list of K2b / K2c)
+//   K2s long_scan_kernel              finds the pieces longer than 32 bytes (work list of K2b / K2c), counts pieces per 2 KiB tile
 //   K2a bpe_lookup_kernel             every short piece once: whole-piece lookup (CoreBPE's shortcut)       (a2)
 //   K2m bpe_merge_kernel              the misses: exact min-rank merge loop, one lane per piece              (a2)
 //   K2b bpe_long_kernel               pieces of 33.. bytes, one warp each: batched rounds + parallel-cut rounds (a2)
 //   K2c bpe_list_kernel               the list phase of big pieces, one CTA each, state in shared memory     (a2)
 //   K3  flag_count / tile_scan / emit_compact / prompt_offsets   token flags -> dense id stream + offsets + counts (a3, a4)
 //   decode_len / decode_copy / decode_offsets                    ids -> bytes
-//   (bpe_encode_pieces_kernel<2>, the fused predecessor of K2a + K2m, is kept as the CFBPE_K2_FUSED A/B build)
 //
 // Pure integer/indexing work: no tensor cores (north_star).  Bounds: HBM for the byte and id
 // streams, L2 latency for the rank-table lookups.
@@ -73,6 +72,8 @@ struct DeviceStatus {
     uint32_t miss_n[3];    // short pieces that are not one token, by length class: 13..32 | 7..12 | 2..6 bytes (K2a -> K2m)
     uint32_t miss_next[3]; // K2m work tickets
     uint32_t miss_overflow;
+    uint32_t extra_n;      // tokens of merged short pieces written to DenseIds::extras so far
+    uint32_t pad4;
     uint32_t fix_n;        // K1 threads that stopped in S_W_U (pretok_fixup_kernel finishes them)
     uint32_t bad_vocab;    // != 0: a prompt names a vocabulary id that is not loaded (device-path callers; the host paths check before)
     uint32_t defer_n;      // pieces K2b handed to K2c ...
@@ -82,7 +83,7 @@ struct DeviceStatus {
 // K2a's lists of the short pieces that need the merge loop, one per length class (worst-case capacities: a class with
 // pieces of >= L bytes holds at most total / L of them)
 struct MissLists {
-    uint32_t* list[3];
+    uint64_t* list[3];     // byte position | rank of the piece << 32
     uint32_t cap[3];
 };
 __host__ __device__ inline uint32_t miss_class_min_len(uint32_t c) { return c == 0 ? 13u : (c == 1 ? 7u : 1u); }
@@ -429,9 +430,8 @@ __device__ __forceinline__ uint32_t whole_piece_lookup(const TablesView& T, cons
 // the exact merge loop on one piece of 2..32 bytes.  Part k = the part that STARTS at byte k of the piece; `alive` has
 // one bit per live part, so a merge clears a bit instead of shifting arrays.  Shared-memory columns (stride 32 words):
 //   sid[k*32] = id of part k      srk[k*32] = rank of (part k, next live part)
-__device__ __forceinline__ void merge_piece_in_lane(const TablesView& T, const uint8_t* __restrict__ text, uint64_t pos, uint32_t len,
-                                                    uint32_t* sid, uint32_t* srk, uint32_t* __restrict__ ids_by_pos,
-                                                    uint32_t* __restrict__ tok_bits) {
+__device__ __forceinline__ uint32_t merge_piece_in_lane(const TablesView& T, const uint8_t* __restrict__ text, uint64_t pos, uint32_t len,
+                                                        uint32_t* sid, uint32_t* srk, uint32_t* __restrict__ tok_bits) {
     const uint8_t* __restrict__ p = text + pos;
     // the piece's bytes (<= 32) in eight registers; parts = bytes, ranks from the raw byte-pair table, four loads in flight
     uint32_t w[8];
@@ -478,13 +478,10 @@ __device__ __forceinline__ void merge_piece_in_lane(const TablesView& T, const u
         srk[bi * 32] = nr == kNone ? kNone : ((nr << 5) | bi);
         if (wl) srk[pv * 32] = nl == kNone ? kNone : ((nl << 5) | pv);
     }
-    for (uint32_t bits = alive; bits; bits &= bits - 1) {
-        const uint32_t k = static_cast<uint32_t>(__ffs(bits)) - 1u;
-        ids_by_pos[pos + k] = sid[k * 32];
-    }
     const uint64_t mask = static_cast<uint64_t>(alive) << (pos & 31);
     atomicOr(&tok_bits[pos >> 5], static_cast<uint32_t>(mask));
     if (mask >> 32) atomicOr(&tok_bits[(pos >> 5) + 1], static_cast<uint32_t>(mask >> 32));
+    return alive;      // the ids of the live parts are in sid[k * 32]
 }
 
 __device__ __forceinline__ uint32_t kth_set_bit(uint32_t mask, uint32_t k) {   // position of the k-th (0-based) set bit
@@ -492,25 +489,37 @@ __device__ __forceinline__ uint32_t kth_set_bit(uint32_t mask, uint32_t k) {   /
     return __ffs(mask) - 1;
 }
 
-// kMode 0: everything.  1: only find the pieces longer than 32 bytes and queue them (so that the long-piece kernel can
-// start on another stream while mode 2 runs).  2: everything except queueing.
-template <int kMode>
+// ---------------------------------------------------------------------------------------
+// Where the ids of the short pieces live between K2 and K3: DENSE, one word per PIECE (not per byte position: that array was
+// written one id per 32-byte sector and read back the same way -- 9x the algorithmic DRAM traffic over the step).
+//   by_piece[r]  r = rank of the piece (number of piece starts before it):  the id, when the piece is one token (9 in 10);
+//                kPieceMulti | slot, when the merge loop made several tokens of it: they are extras[slot ..], in order;
+//                kPieceLong, when the piece is longer than 32 bytes: the long-piece kernels keep its ids in ids_by_pos.
+//   extras[]     the tokens of the merged short pieces, allocated a warp at a time (one atomicAdd per 32 pieces).
+//   piece_base[t]  pieces before the 2 KiB tile t (K2s counts, tile_scan scans): a piece's rank is its tile's base + a popcount.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kPieceMulti = 0x80000000u;
+constexpr uint32_t kPieceLong = 0xFFFFFFFEu;
+constexpr uint32_t kPieceTileBytes = kPieceWarps * kPieceRange;      // 2 KiB: one CTA of K2s / K2a
+static_assert(kPieceTileBytes == 64 * 32, "K3 derives a word's piece tile as word >> 6");
+struct DenseIds {
+    uint32_t* by_piece;            // [pieces] <= [total + 1]
+    uint32_t* extras;              // [tokens of merged short pieces] <= [total + 1]
+    uint32_t extras_cap;
+    uint32_t* tile_pieces;         // [n_tiles2k] piece starts per 2 KiB tile
+    uint64_t* piece_base;          // [n_tiles2k] exclusive scan of tile_pieces
+};
+
+// K2s: one pass over the piece-start flags -- the pieces longer than 32 bytes go to the work list of K2b / K2c (so that the
+// long-piece kernels start early, on their own streams), and every 2 KiB tile counts its piece starts.
 __global__ void __launch_bounds__(kPieceWarps * 32)
-bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits,
-                         uint32_t* __restrict__ ids_by_pos, uint32_t* __restrict__ tok_bits,
-                         LongPiece* __restrict__ long_list, uint32_t long_cap, DeviceStatus* status) {
-    __shared__ uint32_t s_id[kPieceWarps][32][32];   // [warp][part][lane]
-    __shared__ uint32_t s_rk[kPieceWarps][32][32];
-    __shared__ uint16_t s_queue[kPieceWarps][kPieceRange];   // the warp's misses: offset in range | (len-1) << 9
-    __shared__ uint32_t s_head[kPieceWarps];
+long_scan_kernel(BatchView b, const uint32_t* __restrict__ piece_bits, LongPiece* __restrict__ long_list, uint32_t long_cap,
+                 DeviceStatus* status, uint32_t* __restrict__ tile_pieces) {
     const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const uint64_t warp = static_cast<uint64_t>(blockIdx.x) * kPieceWarps + wic;
     const uint64_t r0 = warp * kPieceRange;
-    if (kMode != 1 && r0 >= b.total_bytes) return;   // whole warp exits together (mode 1 has CTA barriers below: everybody stays)
     const uint64_t r1 = (r0 + kPieceRange < b.total_bytes) ? r0 + kPieceRange : b.total_bytes;
-    const uint8_t* __restrict__ text = b.bytes;
     const bool multi = b.vocab_ids != nullptr;
-
     // ---- my 16 piece-start bits, and the first piece start after them
     const uint64_t base = r0 + 16ull * lane;
     const uint32_t my = (base < b.total_bytes) ? ((piece_bits[base >> 5] >> (16u * (lane & 1u))) & 0xFFFFu) : 0u;
@@ -524,125 +533,38 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
     uint64_t beyond = b.total_bytes;
     if (any_open) beyond = next_set_bit(piece_bits, r1, b.total_bytes);
     const uint64_t nf = (nf_rel == 0xFFFFu) ? beyond : r0 + nf_rel;
-
-    if (kMode == 1) {
-        // the only piece of my 16 bytes that can be longer than 32 is the LAST one that starts there (the others end inside
-        // them).  The counters are bumped once per CTA, not once per piece: with half a million long pieces (CJK text) the
-        // kernel was bound by atomics on three addresses (1.0 ms; 0.24 ms on the bench mix).
-        __shared__ uint32_t s_n[2], s_at[2];
-        __shared__ unsigned long long s_bytes;
-        if (threadIdx.x < 2) s_n[threadIdx.x] = 0;
-        if (threadIdx.x == 0) s_bytes = 0;
-        __syncthreads();
-        bool is_long = false, big = false;
-        uint32_t k = 0, pv = 0;
-        uint64_t pos = 0;
-        if (my && r0 < b.total_bytes) {
-            pos = base + (31u - static_cast<uint32_t>(__clz(my)));
-            if (nf - pos > 32) {
-                is_long = true;
-                big = (nf - pos) > kBigPiece;
-                pv = multi ? b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)] : 0u;
-                k = atomicAdd(&s_n[big ? 1 : 0], 1u);
-                atomicAdd(&s_bytes, static_cast<unsigned long long>(nf - pos));
-            }
+    // the only piece of my 16 bytes that can be longer than 32 is the LAST one that starts there (the others end inside
+    // them).  The counters are bumped once per CTA, not once per piece: with half a million long pieces (CJK text) the
+    // kernel was bound by atomics on three addresses (1.0 ms; 0.24 ms on the bench mix).
+    __shared__ uint32_t s_n[2], s_at[2], s_pieces;
+    __shared__ unsigned long long s_bytes;
+    if (threadIdx.x < 2) s_n[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s_bytes = 0; s_pieces = 0; }
+    __syncthreads();
+    const uint32_t np = __reduce_add_sync(kFull, static_cast<uint32_t>(__popc(my)));
+    if (lane == 0 && np) atomicAdd(&s_pieces, np);
+    bool is_long = false, big = false;
+    uint32_t k = 0, pv = 0;
+    uint64_t pos = 0;
+    if (my && r0 < b.total_bytes) {
+        pos = base + (31u - static_cast<uint32_t>(__clz(my)));
+        if (nf - pos > 32) {
+            is_long = true;
+            big = (nf - pos) > kBigPiece;
+            pv = multi ? b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)] : 0u;
+            k = atomicAdd(&s_n[big ? 1 : 0], 1u);
+            atomicAdd(&s_bytes, static_cast<unsigned long long>(nf - pos));
         }
-        __syncthreads();
-        if (threadIdx.x < 2 && s_n[threadIdx.x]) s_at[threadIdx.x] = atomicAdd(threadIdx.x ? &status->n_big : &status->n_long, s_n[threadIdx.x]);
-        if (threadIdx.x == 2 && s_bytes) atomicAdd(&status->long_bytes, s_bytes);
-        __syncthreads();
-        if (is_long) {
-            const uint32_t idx = s_at[big ? 1 : 0] + k;
-            if (idx < long_cap) { LongPiece lp; lp.start = pos; lp.end = nf; lp.vocab = pv; lp.pad = 0; long_list[big ? long_cap - 1 - idx : idx] = lp; }
-            else atomicOr(&status->long_overflow, 1u);
-        }
-        return;
     }
-
-    // ---- vocabulary of my pieces (multi-tenant batches: one prompt lookup per lane, then walk)
-    uint32_t pidx = 0, vid = 0;
-    uint64_t pe = ~0ull;
-    if (multi && my) {
-        pidx = find_prompt(b.offsets, b.n_prompts, base + static_cast<uint32_t>(__ffs(my)) - 1u);
-        pe = b.offsets[pidx + 1];
-        vid = b.vocab_ids[pidx];
-    }
-    TablesView T = vs.v[vid];
-
-    // ---- pass 1: whole-piece lookups
-    uint32_t need_s = 0, need_m = 0, need_l = 0, done = 0;   // misses of <= 6, 7..12, 13..32 bytes
-    uint32_t bits = my;
-    while (bits) {
-        const uint32_t bpos = static_cast<uint32_t>(__ffs(bits)) - 1u;
-        bits &= bits - 1;
-        const uint64_t pos = base + bpos;
-        const uint64_t end = bits ? base + static_cast<uint32_t>(__ffs(bits)) - 1u : nf;
-        if (multi && pos >= pe) {
-            do { ++pidx; pe = b.offsets[pidx + 1]; } while (pos >= pe);
-            const uint32_t nv = b.vocab_ids[pidx];
-            if (nv != vid) { vid = nv; T = vs.v[vid]; }
-        }
-        if (end - pos > 32) {   // long piece: K2b
-            if (kMode == 2) continue;
-            const bool big = (end - pos) > kBigPiece;
-            atomicAdd(&status->long_bytes, static_cast<unsigned long long>(end - pos));
-            const uint32_t idx = atomicAdd(big ? &status->n_big : &status->n_long, 1u);
-            if (idx < long_cap) { LongPiece lp; lp.start = pos; lp.end = end; lp.vocab = vid; lp.pad = 0; long_list[big ? long_cap - 1 - idx : idx] = lp; }
-            else atomicOr(&status->long_overflow, 1u);
-            continue;
-        }
-        if (kMode == 1) continue;
-        const uint32_t len = static_cast<uint32_t>(end - pos);
-        const uint32_t tok = whole_piece_lookup(T, text + pos, len);
-        if (tok != kNone) { ids_by_pos[pos] = tok; done |= 1u << bpos; }
-        else if (len <= 6) need_s |= 1u << bpos;
-        else if (len <= 12) need_m |= 1u << bpos;
-        else need_l |= 1u << bpos;
-    }
-    if (kMode == 1) return;
-    {   // flags of the direct hits: two lanes share a 32-bit word
-        const uint32_t other = __shfl_xor_sync(kFull, done, 1);
-        if (!(lane & 1u) && base < b.total_bytes) { const uint32_t wbits = done | (other << 16); if (wbits) atomicOr(&tok_bits[base >> 5], wbits); }
-    }
-
-    // ---- pass 2: the misses.  They are written to a per-warp queue, longest class first, and every lane then takes the
-    //      next entry as soon as it is free (the merge loop of a 30-byte piece is ~10x that of a 4-byte one; with fixed
-    //      batches of 32 most lanes sat idle: 6.7 active lanes per instruction in profiles/ncu_summary_r01k.json)
-    uint16_t* queue = s_queue[wic];
-    uint32_t qbase = 0;
-#pragma unroll 1
-    for (uint32_t cls = 0; cls < 3; ++cls) {
-        const uint32_t need_c = cls == 0 ? need_l : (cls == 1 ? need_m : need_s);
-        const uint32_t cnt = __popc(need_c);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
-        uint32_t slot = qbase + incl - cnt;
-        for (uint32_t bits2 = need_c; bits2; bits2 &= bits2 - 1) {
-            const uint32_t bpos = static_cast<uint32_t>(__ffs(bits2)) - 1u;
-            const uint32_t rest = my & ~((2u << bpos) - 1u);
-            const uint64_t pos = base + bpos;
-            const uint64_t end = rest ? base + static_cast<uint32_t>(__ffs(rest)) - 1u : nf;
-            queue[slot++] = static_cast<uint16_t>((16u * lane + bpos) | ((static_cast<uint32_t>(end - pos) - 1u) << 9));   // offset in range | (len-1)
-        }
-        qbase += __shfl_sync(kFull, incl, 31);
-    }
-    if (lane == 0) s_head[wic] = 0;
-    __syncwarp();
-    if (qbase == 0) return;
-    uint32_t* sid = &s_id[wic][0][lane];
-    uint32_t* srk = &s_rk[wic][0][lane];
-    for (;;) {
-        const uint32_t g = atomicAdd(&s_head[wic], 1u);
-        if (g >= qbase) break;
-        const uint32_t e = queue[g];
-        const uint64_t pos = r0 + (e & 511u);
-        const uint32_t len = (e >> 9) + 1u;
-        if (multi) {
-            const uint32_t pv = b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)];
-            if (pv != vid) { vid = pv; T = vs.v[vid]; }
-        }
-        merge_piece_in_lane(T, text, pos, len, sid, srk, ids_by_pos, tok_bits);
+    __syncthreads();
+    if (threadIdx.x < 2 && s_n[threadIdx.x]) s_at[threadIdx.x] = atomicAdd(threadIdx.x ? &status->n_big : &status->n_long, s_n[threadIdx.x]);
+    if (threadIdx.x == 2 && s_bytes) atomicAdd(&status->long_bytes, s_bytes);
+    if (threadIdx.x == 3) tile_pieces[blockIdx.x] = s_pieces;
+    __syncthreads();
+    if (is_long) {
+        const uint32_t idx = s_at[big ? 1 : 0] + k;
+        if (idx < long_cap) { LongPiece lp; lp.start = pos; lp.end = nf; lp.vocab = pv; lp.pad = 0; long_list[big ? long_cap - 1 - idx : idx] = lp; }
+        else atomicOr(&status->long_overflow, 1u);
     }
 }
 
@@ -650,32 +572,35 @@ bpe_encode_pieces_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ 
 // K2a + K2m: the short pieces (<= 32 bytes), in two kernels so that both run with full warps.
 //   K2a  bpe_lookup_kernel   every piece once: CoreBPE's `if piece in ranks`.  A warp lists the piece starts of its 512
 //        bytes in shared memory and its lanes take them round-robin (a lane that owned 16 BYTES had between one and
-//        eight pieces to look up); a hit stores the id and its flag, a miss goes to the CTA's list of its length class,
-//        which the CTA appends to the global list with one atomic per class.
+//        eight pieces to look up); a hit stores the id at the piece's rank (consecutive lanes, consecutive words) and its
+//        flag, a miss goes to the CTA's list of its length class, which the CTA appends to the global list with one atomic
+//        per class.
 //   K2m  bpe_merge_kernel    the misses, one LANE per piece (merge_piece_in_lane), 32 pieces of one length class per
 //        warp ticket -- in the fused version the merge loops ran with 4-5 active lanes, because a warp only had the
 //        ~15 misses of its own 512 bytes to spread over its lanes (profiles/ncu_lines_bpe_encode_r01n.txt).
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kLookupWarps = 4;
+static_assert(kLookupWarps == kPieceWarps, "K2a's CTA is the 2 KiB tile K2s counted");
 __global__ void __launch_bounds__(kLookupWarps * 32)
-bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits, uint32_t* __restrict__ ids_by_pos,
+bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits, DenseIds dn,
                   uint32_t* __restrict__ tok_bits, MissLists ml, DeviceStatus* status) {
     __shared__ uint16_t s_pos[kLookupWarps][kPieceRange + 2];
     __shared__ uint32_t s_flags[kLookupWarps][kPieceRange / 32];
-    __shared__ uint32_t s_miss0[kLookupWarps * kPieceRange / 13 + 8];
-    __shared__ uint32_t s_miss1[kLookupWarps * kPieceRange / 7 + 8];
-    __shared__ uint32_t s_miss2[kLookupWarps * kPieceRange / 2 + 8];
-    __shared__ uint32_t s_cnt[3], s_base[3];
+    __shared__ uint64_t s_miss0[kLookupWarps * kPieceRange / 13 + 8];
+    __shared__ uint64_t s_miss1[kLookupWarps * kPieceRange / 7 + 8];
+    __shared__ uint64_t s_miss2[kLookupWarps * kPieceRange / 2 + 8];
+    __shared__ uint32_t s_cnt[3], s_base[3], s_nw[kLookupWarps];
     const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
     if (lane < kPieceRange / 32) s_flags[wic][lane] = 0;
-    __syncthreads();
     const uint64_t warp = static_cast<uint64_t>(blockIdx.x) * kLookupWarps + wic;
     const uint64_t r0 = warp * kPieceRange;
     const uint8_t* __restrict__ text = b.bytes;
     const bool multi = b.vocab_ids != nullptr;
-    if (r0 < b.total_bytes) {
-        const uint64_t r1 = (r0 + kPieceRange < b.total_bytes) ? r0 + kPieceRange : b.total_bytes;
+    const bool in_range = r0 < b.total_bytes;
+    const uint64_t r1 = (r0 + kPieceRange < b.total_bytes) ? r0 + kPieceRange : b.total_bytes;
+    uint32_t n_w = 0;
+    if (in_range) {
         // ---- the piece starts of my range, in order, as offsets
         const uint64_t base = r0 + 16ull * lane;
         const uint32_t my = (base < b.total_bytes) ? ((piece_bits[base >> 5] >> (16u * (lane & 1u))) & 0xFFFFu) : 0u;
@@ -683,10 +608,16 @@ bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
         uint32_t incl = cnt;
 #pragma unroll
         for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
-        const uint32_t n_w = __shfl_sync(kFull, incl, 31);
+        n_w = __shfl_sync(kFull, incl, 31);
         uint32_t slot = incl - cnt;
         for (uint32_t bits = my; bits; bits &= bits - 1) s_pos[wic][slot++] = static_cast<uint16_t>(16u * lane + static_cast<uint32_t>(__ffs(bits)) - 1u);
-        __syncwarp();
+    }
+    if (lane == 0) s_nw[wic] = n_w;
+    __syncthreads();
+    if (in_range) {
+        // rank of my first piece: the tile's base + the pieces of the warps before me
+        uint64_t rank0 = dn.piece_base[blockIdx.x];
+        for (uint32_t w = 0; w < wic; ++w) rank0 += s_nw[w];
         // the last piece ends at the next start beyond the range (or at the end of the data)
         uint64_t beyond = b.total_bytes;
         if (n_w) beyond = next_set_bit(piece_bits, r1, b.total_bytes);
@@ -696,7 +627,7 @@ bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
             const uint32_t off = s_pos[wic][i];
             const uint64_t pos = r0 + off;
             const uint64_t end = (i + 1 < n_w) ? r0 + s_pos[wic][i + 1] : beyond;
-            if (end - pos > 32) continue;                         // long piece: K2b
+            if (end - pos > 32) { dn.by_piece[rank0 + i] = kPieceLong; continue; }     // long piece: K2b / K2c
             const uint32_t len = static_cast<uint32_t>(end - pos);
             if (multi) {
                 const uint32_t pv = b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)];
@@ -704,12 +635,12 @@ bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
             }
             const uint32_t tok = (len == 1) ? T.byte2id[text[pos]] : whole_piece_lookup(T, text + pos, len);   // a byte is a token
             if (tok != kNone) {
-                ids_by_pos[pos] = tok;
+                dn.by_piece[rank0 + i] = tok;
                 atomicOr(&s_flags[wic][off >> 5], 1u << (off & 31));
             } else {
                 const uint32_t c = len >= 13 ? 0u : (len >= 7 ? 1u : 2u);
                 const uint32_t k = atomicAdd(&s_cnt[c], 1u);
-                (c == 0 ? s_miss0 : (c == 1 ? s_miss1 : s_miss2))[k] = static_cast<uint32_t>(pos);
+                (c == 0 ? s_miss0 : (c == 1 ? s_miss1 : s_miss2))[k] = pos | ((rank0 + i) << 32);
             }
         }
         __syncwarp();
@@ -730,13 +661,13 @@ bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
     for (uint32_t c = 0; c < 3; ++c) {
         const uint32_t n = s_cnt[c], g = s_base[c];
         if (g == 0xFFFFFFFFu) continue;
-        const uint32_t* src = c == 0 ? s_miss0 : (c == 1 ? s_miss1 : s_miss2);
+        const uint64_t* src = c == 0 ? s_miss0 : (c == 1 ? s_miss1 : s_miss2);
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) ml.list[c][g + i] = src[i];
     }
 }
 
 __global__ void __launch_bounds__(kPieceWarps * 32)
-bpe_merge_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits, uint32_t* __restrict__ ids_by_pos,
+bpe_merge_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits, DenseIds dn,
                  uint32_t* __restrict__ tok_bits, MissLists ml, DeviceStatus* status) {
     __shared__ uint32_t s_id[kPieceWarps][32][32];   // [warp][part][lane]
     __shared__ uint32_t s_rk[kPieceWarps][32][32];
@@ -751,21 +682,40 @@ bpe_merge_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bi
 #pragma unroll 1
     for (uint32_t c = 0; c < 3; ++c) {     // longest class first
         const uint32_t n = status->miss_n[c];
-        const uint32_t* __restrict__ list = ml.list[c];
+        const uint64_t* __restrict__ list = ml.list[c];
         for (;;) {
             uint32_t t0 = 0;
             if (lane == 0) t0 = atomicAdd(&status->miss_next[c], 32u);
             t0 = __shfl_sync(kFull, t0, 0);
             if (t0 >= n) break;
             const uint32_t i = t0 + lane;
+            uint32_t alive = 0, rank = 0;
             if (i < n) {
-                const uint64_t pos = list[i];
+                const uint64_t e = list[i];
+                const uint64_t pos = e & 0xFFFFFFFFull;
+                rank = static_cast<uint32_t>(e >> 32);
                 const uint64_t end = next_set_bit(piece_bits, pos + 1, b.total_bytes);
                 if (multi) {
                     const uint32_t pv = b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)];
                     if (pv != vid) { vid = pv; T = vs.v[vid]; }
                 }
-                merge_piece_in_lane(T, text, pos, static_cast<uint32_t>(end - pos), sid, srk, ids_by_pos, tok_bits);
+                alive = merge_piece_in_lane(T, text, pos, static_cast<uint32_t>(end - pos), sid, srk, tok_bits);
+            }
+            // the warp's tokens go to one contiguous stretch of `extras` (one atomic per 32 pieces); the piece's word names its slot
+            const uint32_t cnt = __popc(alive);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (uint32_t d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            uint32_t base = 0;
+            if (lane == 0 && total) base = atomicAdd(&status->extra_n, total);
+            base = __shfl_sync(kFull, base, 0);
+            if (cnt) {
+                uint32_t slot = base + incl - cnt;
+                if (slot + cnt <= dn.extras_cap) {
+                    dn.by_piece[rank] = kPieceMulti | slot;
+                    for (uint32_t bits = alive; bits; bits &= bits - 1) dn.extras[slot++] = sid[(static_cast<uint32_t>(__ffs(bits)) - 1u) * 32];
+                } else atomicOr(&status->miss_overflow, 1u);
             }
             __syncwarp();
         }
@@ -1529,34 +1479,56 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_counts, uint32_t n_tiles, uin
         if (threadIdx.x == blockDim.x - 1) s_carry = carry + woff + x;
         __syncthreads();
     }
-    if (threadIdx.x == 0) { status->n_tokens = s_carry - base0; status->tok_end = s_carry; }
+    if (threadIdx.x == 0 && status) { status->n_tokens = s_carry - base0; status->tok_end = s_carry; }
 }
 
 __global__ void __launch_bounds__(256)
-emit_compact_kernel(const uint32_t* __restrict__ tok_bits, uint64_t n_words, const uint64_t* __restrict__ tile_base,
-                    const uint32_t* __restrict__ ids_by_pos, uint32_t* __restrict__ out_ids, uint64_t out_cap) {
-    // one CTA per tile of kScanTileWords (= blockDim.x) flag words, one word per thread
-    __shared__ uint32_t s_warp[8];
+emit_compact_kernel(const uint32_t* __restrict__ tok_bits, const uint32_t* __restrict__ piece_bits, uint64_t n_words,
+                    const uint64_t* __restrict__ tile_base, DenseIds dn, const uint32_t* __restrict__ ids_by_pos,
+                    uint32_t* __restrict__ out_ids, uint64_t out_cap) {
+    // one CTA per tile of kScanTileWords (= blockDim.x) flag words, one word per thread.  A token's rank = prefix popcount of the
+    // token flags; its id is found through the rank of the PIECE it belongs to (prefix popcount of the piece flags, per 2 KiB tile)
+    __shared__ uint32_t s_warp[8], s_pw[8];
     const uint64_t w = static_cast<uint64_t>(blockIdx.x) * kScanTileWords + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t bits = (w < n_words) ? tok_bits[w] : 0u;
-    const uint32_t c = __popc(bits);
-    uint32_t x = c;
+    const uint32_t pb = (w < n_words) ? piece_bits[w] : 0u;
+    const uint32_t c = __popc(bits), pc = __popc(pb);
+    uint32_t x = c, px = pc;
 #pragma unroll
     for (uint32_t d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(kFull, x, d);
-        if (lane >= d) x += o;
+        const uint32_t o = __shfl_up_sync(kFull, x, d), po = __shfl_up_sync(kFull, px, d);
+        if (lane >= d) { x += o; px += po; }
     }
-    if (lane == 31) s_warp[wid] = x;
+    if (lane == 31) { s_warp[wid] = x; s_pw[wid] = px; }
+    // the word before mine (a token's piece may have started there): from my neighbour, or from memory for the first lane
+    uint32_t prev_bits = __shfl_up_sync(kFull, bits, 1), prev_pb = __shfl_up_sync(kFull, pb, 1);
+    if (lane == 0) { prev_bits = (w > 0 && w <= n_words) ? tok_bits[w - 1] : 0u; prev_pb = (w > 0 && w <= n_words) ? piece_bits[w - 1] : 0u; }
     __syncthreads();
+    if (!bits) return;
     uint32_t woff = 0;
     for (uint32_t k = 0; k < wid; ++k) woff += s_warp[k];
     uint64_t r = tile_base[blockIdx.x] + woff + (x - c);
+    // pieces that start before my word: the 2 KiB tile (64 words = two warps) has its base from the scan of K2s's counts
+    const uint64_t prank = dn.piece_base[w >> 6] + ((wid & 1u) ? s_pw[wid - 1] : 0u) + (px - pc);
     uint32_t rest = bits;
     while (rest) {
         const uint32_t bit = __ffs(rest) - 1;
         rest &= rest - 1;
-        if (r < out_cap) out_ids[r] = ids_by_pos[(w << 5) + bit];
+        const uint32_t below = pb & ((2u << bit) - 1u);                     // piece starts at or before this token, in my word
+        const uint32_t nb = __popc(below);
+        const uint32_t v = dn.by_piece[prank + nb - 1];                     // the piece this token belongs to
+        uint32_t id;
+        if (v == kPieceLong) id = ids_by_pos[(w << 5) + bit];               // a long piece: its kernel left the ids by position
+        else if (!(v & kPieceMulti)) id = v;                                // the piece is one token
+        else {                                                              // k-th token of a merged piece
+            uint32_t k;
+            const uint32_t before = bits & ((1u << bit) - 1u);              // tokens before me in my word
+            if (nb) { const uint32_t q = 31u - static_cast<uint32_t>(__clz(below)); k = __popc(before >> q); }
+            else { const uint32_t q = 31u - static_cast<uint32_t>(__clz(prev_pb)); k = __popc(prev_bits >> q) + __popc(before); }   // (a short piece starts at most one word back)
+            id = dn.extras[(v & ~kPieceMulti) + k];
+        }
+        if (r < out_cap) out_ids[r] = id;
         ++r;
     }
 }

@@ -239,6 +239,8 @@ int run_host_pipelined(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const u
         const uint64_t w0 = (o0 >> 5) + 4ull * k;
         w.piece_bits += w0; w.tok_bits += w0; w.pstart_bits += w0;
         w.block_prompt += (o0 >> kPromptBlockShift) + 2ull * k;
+        w.dense.by_piece += o0; w.dense.extras += o0; w.dense.extras_cap = static_cast<uint32_t>(len + 1);
+        w.dense.tile_pieces += (o0 >> 11) + 2ull * k; w.dense.piece_base += (o0 >> 11) + 2ull * k;
         w.ids_by_pos += o0; w.lscratch.rank += o0; w.lscratch.aux0 += o0; w.lscratch.aux1 += o0;
         w.long_list += (o0 >> 5) + k;
         w.long_cap = static_cast<uint32_t>(len / 32 + 1);
@@ -423,10 +425,15 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     ctx->ws.long_cap = static_cast<uint32_t>(mb / 32 + 1 + kMaxPipeChunks);   // a long piece holds more than 32 bytes
     ok = ok && dmalloc(&ctx->ws.long_list, ctx->ws.long_cap) == cudaSuccess;
     for (uint32_t c = 0; c < 3; ++c) {
-        const uint64_t words = miss_list_words(mb, c, kMaxPipeChunks);
+        const uint64_t words = miss_list_words(mb, c, kMaxPipeChunks);      // 64-bit entries
         ok = ok && dmalloc(&ctx->ws.miss.list[c], words) == cudaSuccess;
         ctx->ws.miss.cap[c] = static_cast<uint32_t>(words);
     }
+    ok = ok && dmalloc(&ctx->ws.dense.by_piece, mb + 1) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.dense.extras, mb + 1) == cudaSuccess;
+    ctx->ws.dense.extras_cap = static_cast<uint32_t>(mb + 1);
+    ok = ok && dmalloc(&ctx->ws.dense.tile_pieces, (mb >> 11) + 2 + 2 * kMaxPipeChunks) == cudaSuccess;
+    ok = ok && dmalloc(&ctx->ws.dense.piece_base, (mb >> 11) + 2 + 2 * kMaxPipeChunks) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.pstart_bits, nw) == cudaSuccess;
     ok = ok && dmalloc(&ctx->ws.block_prompt, (mb >> kPromptBlockShift) + 2 + 2 * kMaxPipeChunks) == cudaSuccess;
     ctx->ws.fix_cap = static_cast<uint32_t>(mb / 16 + 2 + 2 * kMaxPipeChunks);
@@ -528,6 +535,7 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     cudaFree(ctx->ws.lscratch.rank); cudaFree(ctx->ws.lscratch.aux0); cudaFree(ctx->ws.lscratch.aux1);
     for (uint32_t c = 0; c < 3; ++c) cudaFree(ctx->ws.miss.list[c]);
     cudaFree(ctx->d_dec_sums); cudaFree(ctx->d_dec_base);
+    cudaFree(ctx->ws.dense.by_piece); cudaFree(ctx->ws.dense.extras); cudaFree(ctx->ws.dense.tile_pieces); cudaFree(ctx->ws.dense.piece_base);
     cudaFree(ctx->ws.fix_list); cudaFree(ctx->ws.pstart_bits); cudaFree(ctx->ws.block_prompt); cudaFree(ctx->d_split_tables);
     cudaFree(ctx->ws.long_list); cudaFree(ctx->ws.tile_counts); cudaFree(ctx->ws.tile_base); cudaFree(ctx->ws.status);
     cudaFree(ctx->d_uc1); cudaFree(ctx->d_uc2); cudaFree(ctx->d_ascii); cudaFree(ctx->d_fsm);

@@ -25,6 +25,7 @@ struct Workspace {
     MissLists miss;         // K2a -> K2m: short pieces that need the merge loop, by length class
     SplitFix* fix_list;     // K1 -> fixup: walkers that stopped in an undecided state (at most one per 16-byte block)   [total / 16 + 2]
     uint32_t fix_cap;
+    DenseIds dense;         // ids of the short pieces, one word per piece; extras; piece counts / bases per 2 KiB tile
     uint32_t* pstart_bits;  // 1 bit per byte: a prompt starts here (and one at the end of the data)   [n_words + 2]
     uint32_t* block_prompt; // the prompt that holds the first byte of every 512-byte block           [total / 512 + 2]
 };
@@ -32,7 +33,7 @@ struct Workspace {
 // the slice of the miss lists that belongs to a sub-batch of `len` bytes starting at byte o0 (k-th sub-batch)
 inline MissLists slice_miss(const MissLists& all, uint64_t o0, uint64_t len, uint32_t k) {
     MissLists m;
-    for (uint32_t c = 0; c < 3; ++c) {
+    for (uint32_t c = 0; c < 3; ++c) {     // (entries are 64-bit: position | rank << 32)
         const uint32_t L = miss_class_min_len(c) < 2 ? 2u : miss_class_min_len(c);   // no one-byte piece is ever a miss
         m.list[c] = all.list[c] + o0 / L + 2ull * k;
         m.cap[c] = static_cast<uint32_t>(len / L + 2);
@@ -97,31 +98,25 @@ inline void enqueue_split(const BatchView& b, const VocabSet& vs, const UcTables
     CFBPE_MARK(prof, K_SPLIT, stream, false);
     const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
     CFBPE_MARK(prof, K_LONGSCAN, stream, true);
-    CFBPE_LAUNCH(bpe_encode_pieces_kernel<1>, static_cast<unsigned>((n_warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, stream,
-                 b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
+    CFBPE_LAUNCH(long_scan_kernel, static_cast<unsigned>((n_warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, stream,
+                 b, w.piece_bits, w.long_list, w.long_cap, w.status, w.dense.tile_pieces);
     CFBPE_MARK(prof, K_LONGSCAN, stream, false);
 }
 
 template <typename Stream, typename Prof>
 inline void enqueue_short(const BatchView& b, const VocabSet& vs, const Workspace& w, uint32_t long_grid, Stream stream, Prof* prof) {
     if (!b.total_bytes) return;
-#if defined(CFBPE_K2_FUSED)
-    CFBPE_MARK(prof, K_ENCODE, stream, true);
-    const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
-    CFBPE_LAUNCH(bpe_encode_pieces_kernel<2>, static_cast<unsigned>((n_warps + kPieceWarps - 1) / kPieceWarps), kPieceWarps * 32, stream,
-                 b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.long_list, w.long_cap, w.status);
-    CFBPE_MARK(prof, K_ENCODE, stream, false);
-#else
     const uint64_t n_warps = (b.total_bytes + kPieceRange - 1) / kPieceRange;
     CFBPE_MARK(prof, K_ENCODE, stream, true);
-    CFBPE_LAUNCH(bpe_lookup_kernel, static_cast<unsigned>((n_warps + kLookupWarps - 1) / kLookupWarps), kLookupWarps * 32, stream,
-                 b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.miss, w.status);
+    const uint32_t n_tiles2k = static_cast<uint32_t>((n_warps + kLookupWarps - 1) / kLookupWarps);
+    CFBPE_LAUNCH(tile_scan_kernel, 1u, 1024, stream, w.dense.tile_pieces, n_tiles2k, w.dense.piece_base, static_cast<DeviceStatus*>(nullptr),
+                 static_cast<const uint64_t*>(nullptr));      // piece ranks: exclusive scan of K2s's per-tile counts
+    CFBPE_LAUNCH(bpe_lookup_kernel, n_tiles2k, kLookupWarps * 32, stream, b, vs, w.piece_bits, w.dense, w.tok_bits, w.miss, w.status);
     CFBPE_MARK(prof, K_ENCODE, stream, false);
     CFBPE_MARK(prof, K_MERGE, stream, true);
     CFBPE_LAUNCH(bpe_merge_kernel, long_grid + long_grid / 2, kPieceWarps * 32, stream,      // 6 CTAs of 32 KB per SM
-                 b, vs, w.piece_bits, w.ids_by_pos, w.tok_bits, w.miss, w.status);
+                 b, vs, w.piece_bits, w.dense, w.tok_bits, w.miss, w.status);
     CFBPE_MARK(prof, K_MERGE, stream, false);
-#endif
 }
 
 // K2b: the pieces of 33 .. kBigPiece bytes (and the rare giants the list kernel cannot hold), one warp each
@@ -168,7 +163,8 @@ inline void enqueue_emit(const BatchView& b, const Workspace& w, uint32_t* out_i
                          uint32_t* out_counts, Stream stream, Prof* prof) {
     CFBPE_MARK(prof, K_EMIT, stream, true);
     if (b.total_bytes && out_ids) {
-        CFBPE_LAUNCH(emit_compact_kernel, n_scan_tiles(b.total_bytes), 256, stream, w.tok_bits, n_flag_words(b.total_bytes), w.tile_base, w.ids_by_pos, out_ids, out_cap);
+        CFBPE_LAUNCH(emit_compact_kernel, n_scan_tiles(b.total_bytes), 256, stream, w.tok_bits, w.piece_bits, n_flag_words(b.total_bytes), w.tile_base,
+                     w.dense, w.ids_by_pos, out_ids, out_cap);
     }
     CFBPE_LAUNCH(prompt_offsets_kernel, static_cast<unsigned>((static_cast<uint64_t>(b.n_prompts) + 1 + 255) / 256), 256, stream,
                  b, w.tok_bits, w.tile_base, out_offsets, out_counts, w.status);

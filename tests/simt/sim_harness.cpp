@@ -142,7 +142,7 @@ __attribute__((visibility("default"))) int sim_encode_batch(void* const* vocabs,
     std::vector<LongPiece> ll(total / 32 + 1);
     DeviceStatus st{};
     std::vector<SplitFix> fix(total / 16 + 2);
-    std::vector<uint32_t> miss[3];
+    std::vector<uint64_t> miss[3];
     MissLists ml;
     for (uint32_t c = 0; c < 3; ++c) {
         miss[c].resize(miss_list_words(total, c, 1));
@@ -150,8 +150,11 @@ __attribute__((visibility("default"))) int sim_encode_batch(void* const* vocabs,
         ml.cap[c] = static_cast<uint32_t>(miss[c].size());
     }
     std::vector<uint32_t> pstart(nw + 2), bprompt((total >> kPromptBlockShift) + 2);
+    std::vector<uint32_t> by_piece(total + 1, 0xDEADBEEF), extras(total + 1, 0xDEADBEEF), tile_pieces((total >> 11) + 2);
+    std::vector<uint64_t> piece_base((total >> 11) + 2);
     Workspace w{piece_bits.data(), tok_bits.data(), ids.data(), LongScratch{rk.data(), nx.data(), pv.data()},
                 ll.data(), static_cast<uint32_t>(ll.size()), tile_counts.data(), tile_base.data(), &st, ml, fix.data(), static_cast<uint32_t>(fix.size()),
+                DenseIds{by_piece.data(), extras.data(), static_cast<uint32_t>(extras.size()), tile_pieces.data(), piece_base.data()},
                 pstart.data(), bprompt.data()};
     vs.loaded_mask = n_vocabs >= 32 ? 0xFFFFFFFFu : ((1u << n_vocabs) - 1u);
     int* prof = nullptr;
