@@ -22,8 +22,15 @@
 #include "pretok_fsm.h"
 #include "pretok_sync.cuh"
 #include "tables.h"
+#include "tma.cuh"
 
 namespace cfbpe {
+
+#ifdef CUSIM_EMULATOR
+#define CFBPE_DYN_SMEM(name) uint32_t* const name = reinterpret_cast<uint32_t*>(cusim::dyn_smem())
+#else
+#define CFBPE_DYN_SMEM(name) extern __shared__ __align__(16) uint32_t name[]
+#endif
 
 constexpr uint32_t kMaxVocabs = 8;
 // path counters for the emulator tests (which path did a test actually exercise); nothing on the device
@@ -430,8 +437,9 @@ __device__ __forceinline__ uint32_t whole_piece_lookup(const TablesView& T, cons
 // the exact merge loop on one piece of 2..32 bytes.  Part k = the part that STARTS at byte k of the piece; `alive` has
 // one bit per live part, so a merge clears a bit instead of shifting arrays.  Shared-memory columns (stride 32 words):
 //   sid[k*32] = id of part k      srk[k*32] = rank of (part k, next live part)
+// hot: the hot slice of the pair table in shared memory (CFBPE_MERGE_HOT build), or nullptr
 __device__ __forceinline__ uint32_t merge_piece_in_lane(const TablesView& T, const uint8_t* __restrict__ text, uint64_t pos, uint32_t len,
-                                                        uint32_t* sid, uint32_t* srk, uint32_t* __restrict__ tok_bits) {
+                                                        uint32_t* sid, uint32_t* srk, uint32_t* __restrict__ tok_bits, const uint64_t* hot = nullptr) {
     const uint8_t* __restrict__ p = text + pos;
     // the piece's bytes (<= 32) in eight registers; parts = bytes, ranks from the raw byte-pair table, four loads in flight
     uint32_t w[8];
@@ -474,6 +482,12 @@ __device__ __forceinline__ uint32_t merge_piece_in_lane(const TablesView& T, con
         const uint32_t nn = wr ? static_cast<uint32_t>(__ffs(above2)) - 1u : 0u;
         const uint32_t pv = wl ? 31u - static_cast<uint32_t>(__clz(below)) : 0u;
         uint32_t nr, nl;
+        if (hot) {      // shared memory first: a hit there saves the trip to L2 (a miss there says nothing)
+            const uint32_t rid = wr ? sid[nn * 32] : 0u, lid = wl ? sid[pv * 32] : 0u;
+            const uint32_t hr = wr ? hot_lookup(hot, best, rid) : kNone, hl = wl ? hot_lookup(hot, lid, best) : kNone;
+            pair_lookup2(T, best, rid, wr && hr == kNone, lid, best, wl && hl == kNone, nr, nl);
+            nr = hr != kNone ? hr : nr; nl = hl != kNone ? hl : nl;
+        } else
         pair_lookup2(T, best, wr ? sid[nn * 32] : 0u, wr, wl ? sid[pv * 32] : 0u, best, wl, nr, nl);
         srk[bi * 32] = nr == kNone ? kNone : ((nr << 5) | bi);
         if (wl) srk[pv * 32] = nl == kNone ? kNone : ((nl << 5) | pv);
@@ -666,6 +680,9 @@ bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
     }
 }
 
+#ifndef CFBPE_MERGE_HOT
+#define CFBPE_MERGE_HOT 0      // A/B: 1 = probe a TMA-staged shared-memory slice of the pair table before the L2-resident table
+#endif
 __global__ void __launch_bounds__(kPieceWarps * 32)
 bpe_merge_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits, DenseIds dn,
                  uint32_t* __restrict__ tok_bits, MissLists ml, DeviceStatus* status) {
@@ -679,6 +696,20 @@ bpe_merge_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bi
     if (status->miss_overflow) return;
     TablesView T = vs.v[0];
     uint32_t vid = 0;
+    const uint64_t* hot = nullptr;
+#if CFBPE_MERGE_HOT && !defined(CUSIM_EMULATOR)
+    // A/B build: the hot slice of vocabulary 0's pair table (merged id < kHotRanks, 16 KB) staged into shared memory by ONE TMA
+    // bulk copy; single-vocabulary batches only
+    CFBPE_DYN_SMEM(s_hot);
+    __shared__ __align__(8) uint64_t s_bar;
+    if (!multi && T.hot) {
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, kHotCap * 8u); bulk_g2s(s_hot, T.hot, kHotCap * 8u, &s_bar); }
+        mbar_wait(&s_bar, 0);
+        hot = reinterpret_cast<const uint64_t*>(s_hot);
+    }
+#endif
 #pragma unroll 1
     for (uint32_t c = 0; c < 3; ++c) {     // longest class first
         const uint32_t n = status->miss_n[c];
@@ -699,7 +730,7 @@ bpe_merge_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bi
                     const uint32_t pv = b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)];
                     if (pv != vid) { vid = pv; T = vs.v[vid]; }
                 }
-                alive = merge_piece_in_lane(T, text, pos, static_cast<uint32_t>(end - pos), sid, srk, tok_bits);
+                alive = merge_piece_in_lane(T, text, pos, static_cast<uint32_t>(end - pos), sid, srk, tok_bits, hot);
             }
             // the warp's tokens go to one contiguous stretch of `extras` (one atomic per 32 pieces); the piece's word names its slot
             const uint32_t cnt = __popc(alive);
@@ -1142,11 +1173,6 @@ constexpr uint32_t kListMaxRank = (1u << 20) - 1u;   // K2c packs rank << 12 | p
 // the big pieces bpe_list_kernel takes (from their bytes); bpe_long_kernel keeps the rest
 __device__ __forceinline__ bool list_kernel_takes(const TablesView& T, uint32_t n_bytes) { return n_bytes <= kDeferMaxParts && T.n_ranks < kListMaxRank; }
 
-#ifdef CUSIM_EMULATOR
-#define CFBPE_DYN_SMEM(name) uint32_t* const name = reinterpret_cast<uint32_t*>(cusim::dyn_smem())
-#else
-#define CFBPE_DYN_SMEM(name) extern __shared__ __align__(16) uint32_t name[]
-#endif
 
 // One warp per CTA: a warp that is deep in the serial chain of a long piece then holds one warp's worth of registers and
 // 6 KB of shared memory, not a whole CTA's, so the tail of this kernel can share the SMs with whatever runs next.
@@ -1449,37 +1475,35 @@ flag_count_kernel(const uint32_t* __restrict__ tok_bits, uint64_t n_words, uint3
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = t;
 }
 
-// single CTA; n_tiles arbitrary (looped).  token_base (nullable) = ids produced by the sub-batches before this one
-// (a pipelined host call chains them on the device), so tile_base and out_offsets are global ranks.
+// single CTA; n_tiles arbitrary.  token_base (nullable) = ids produced by the sub-batches before this one (a pipelined host call
+// chains them on the device), so tile_base and out_offsets are global ranks.  status (nullable) gets the totals.
+// Every thread scans a CONTIGUOUS run of tiles (sum, block scan of the 1024 sums, write back): one pass over the counts and three
+// barriers, whatever n_tiles is -- the first form looped over the tiles 1024 at a time with three barriers a trip, 64 trips
+// (89 us) for the 65 536 two-KiB tiles of a 134 MB batch.
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(const uint32_t* __restrict__ tile_counts, uint32_t n_tiles, uint64_t* __restrict__ tile_base,
                  DeviceStatus* status, const uint64_t* __restrict__ token_base) {
     __shared__ uint64_t s_warp[32];
-    __shared__ uint64_t s_carry;
     const uint64_t base0 = token_base ? *token_base : 0;
-    if (threadIdx.x == 0) s_carry = base0;
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < n_tiles; base += blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        const uint64_t v = (i < n_tiles) ? tile_counts[i] : 0;
-        uint64_t x = v;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nthr = blockDim.x;
+    const uint32_t per = (n_tiles + nthr - 1) / nthr;
+    const uint32_t lo = threadIdx.x * per < n_tiles ? threadIdx.x * per : n_tiles;
+    const uint32_t hi = lo + per < n_tiles ? lo + per : n_tiles;
+    uint64_t sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += tile_counts[i];
+    uint64_t x = sum;
 #pragma unroll
-        for (uint32_t d = 1; d < 32; d <<= 1) {
-            const uint64_t o = __shfl_up_sync(kFull, x, d);
-            if (lane >= d) x += o;
-        }
-        if (lane == 31) s_warp[wid] = x;
-        __syncthreads();
-        uint64_t woff = 0;
-        for (uint32_t w = 0; w < wid; ++w) woff += s_warp[w];
-        const uint64_t carry = s_carry;
-        if (i < n_tiles) tile_base[i] = carry + woff + x - v;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = carry + woff + x;
-        __syncthreads();
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint64_t o = __shfl_up_sync(kFull, x, d);
+        if (lane >= d) x += o;
     }
-    if (threadIdx.x == 0 && status) { status->n_tokens = s_carry - base0; status->tok_end = s_carry; }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    uint64_t woff = 0, total = 0;
+    for (uint32_t w = 0; w < (nthr + 31) / 32; ++w) { const uint64_t v = s_warp[w]; if (w < wid) woff += v; total += v; }
+    uint64_t r = base0 + woff + x - sum;
+    for (uint32_t i = lo; i < hi; ++i) { tile_base[i] = r; r += tile_counts[i]; }
+    if (threadIdx.x == 0 && status) { status->n_tokens = total; status->tok_end = base0 + total; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1533,24 +1557,29 @@ emit_compact_kernel(const uint32_t* __restrict__ tok_bits, const uint32_t* __res
     }
 }
 
-// out_offsets[p] = number of flags before byte offsets[p]; counts[p] = difference.  One thread per prompt.
+// out_offsets[p] = number of flags before byte offsets[p]; counts[p] = difference.  One WARP per prompt boundary: the flags of
+// the tile before the position are counted eight words per lane (one thread per prompt walked up to 255 words: 38 us).
 __global__ void __launch_bounds__(256)
 prompt_offsets_kernel(BatchView b, const uint32_t* __restrict__ tok_bits, const uint64_t* __restrict__ tile_base,
                       uint64_t* __restrict__ out_offsets, uint32_t* __restrict__ out_counts, const DeviceStatus* status) {
-    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t i = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (i > b.n_prompts) return;
     auto rank_at = [&](uint64_t pos) -> uint64_t {
         if (pos >= b.total_bytes) return status->tok_end;
         const uint64_t w = pos >> 5;
-        const uint64_t tile = w / kScanTileWords;
-        uint64_t r = tile_base[tile];
-        for (uint64_t k = tile * kScanTileWords; k < w; ++k) r += __popc(tok_bits[k]);
-        r += __popc(tok_bits[w] & ((1u << (pos & 31)) - 1u));
-        return r;
+        const uint64_t w0 = (w / kScanTileWords) * kScanTileWords;
+        uint32_t c = 0;
+        for (uint64_t k = w0 + lane; k < w; k += 32) c += __popc(tok_bits[k]);
+        c = __reduce_add_sync(kFull, c);
+        return tile_base[w / kScanTileWords] + c + __popc(tok_bits[w] & ((1u << (pos & 31)) - 1u));
     };
     const uint64_t r = rank_at(b.offsets[i]);
-    out_offsets[i] = r;
-    if (i < b.n_prompts && out_counts) out_counts[i] = static_cast<uint32_t>(rank_at(b.offsets[i + 1]) - r);
+    const uint64_t r1 = (i < b.n_prompts && out_counts) ? rank_at(b.offsets[i + 1]) : r;
+    if (lane == 0) {
+        out_offsets[i] = r;
+        if (i < b.n_prompts && out_counts) out_counts[i] = static_cast<uint32_t>(r1 - r);
+    }
 }
 
 // ---------------------------------------------------------------------------------------

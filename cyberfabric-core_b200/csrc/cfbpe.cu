@@ -55,6 +55,7 @@ constexpr uint64_t kPipeMinBytes = 16ull << 20;     // smaller calls run as one 
 struct VocabSlot {
     bool loaded = false;
     uint8_t* d_blob = nullptr;
+    uint64_t* d_hot = nullptr;       // the hot slice of the pair table (tables.h kHotRanks / kHotCap)
     std::vector<uint8_t> h_blob;
     TablesHeader hdr{};
 };
@@ -156,12 +157,34 @@ int install_blob(cfbpe_ctx* ctx, uint32_t vocab_id, std::vector<uint8_t>&& blob)
     CK(cudaMalloc(reinterpret_cast<void**>(&d), blob.size()));
     cudaError_t e = cudaMemcpy(d, blob.data(), blob.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(d); return fail(ctx, CFBPE_EIO, std::string("table upload: ") + cudaGetErrorString(e)); }
-    if (v.d_blob) { cudaDeviceSynchronize(); cudaFree(v.d_blob); }   // kernels of a device-path call on any stream may still read the old tables
+    // the hot slice: the pair entries with a low merged id, re-hashed into a table small enough for shared memory
+    uint64_t* d_hot = nullptr;
+    {
+        TablesHeader h;
+        std::memcpy(&h, blob.data(), sizeof h);
+        const uint64_t* pairs = reinterpret_cast<const uint64_t*>(blob.data() + h.off_pair);
+        std::vector<uint64_t> hot(kHotCap, kPairEmpty);
+        uint32_t n_hot = 0;
+        for (uint32_t i = 0; i < h.cap_pair; ++i) {
+            const uint64_t sl = pairs[i];
+            if (sl == kPairEmpty || (static_cast<uint32_t>(sl) & kIdMask) >= kHotRanks || n_hot >= kHotCap * 3 / 4) continue;
+            uint32_t hh = pair_hash(static_cast<uint32_t>(sl >> (2 * kIdBits)), static_cast<uint32_t>(sl >> kIdBits) & kIdMask) & (kHotCap - 1);
+            while (hot[hh] != kPairEmpty) hh = (hh + 1) & (kHotCap - 1);
+            hot[hh] = sl; ++n_hot;
+        }
+        if (cudaMalloc(reinterpret_cast<void**>(&d_hot), kHotCap * sizeof(uint64_t)) != cudaSuccess ||
+            cudaMemcpy(d_hot, hot.data(), kHotCap * sizeof(uint64_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(d); cudaFree(d_hot); return fail(ctx, CFBPE_EIO, "hot pair table upload failed");
+        }
+    }
+    if (v.d_blob) { cudaDeviceSynchronize(); cudaFree(v.d_blob); cudaFree(v.d_hot); }   // kernels of a device-path call on any stream may still read the old tables
     v.d_blob = d;
+    v.d_hot = d_hot;
     v.h_blob = std::move(blob);
     std::memcpy(&v.hdr, v.h_blob.data(), sizeof(TablesHeader));
     v.loaded = true;
     ctx->vs.v[vocab_id] = make_view(v.d_blob, v.hdr);
+    ctx->vs.v[vocab_id].hot = v.d_hot;
     ctx->vs.loaded_mask |= 1u << vocab_id;
     // slots that are not loaded alias a loaded one: a bad vocabulary id handed in by a device-path caller is reported
     // (DeviceStatus::bad_vocab -> CFBPE_ENOENT) instead of dereferencing a null table
@@ -409,6 +432,7 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
     cudaDeviceGetStreamPriorityRange(&prio_lo0, &prio_hi0);
     bool ok = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi0) == cudaSuccess;   // front stream of sub-batch 0
     ok = ok && cudaFuncSetAttribute(bpe_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kListSmemBytes)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(bpe_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHotCap * 8)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pretok_split16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kNumPatterns * kProdTableBytes)) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_bytes, mb + 256 + 16 * (kMaxPipeChunks + 1)) == cudaSuccess;
     ok = ok && dmalloc(&ctx->d_offsets, mp + 1 + kMaxPipeChunks) == cudaSuccess;
@@ -557,7 +581,7 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
-    for (auto& v : ctx->vocabs) if (v.d_blob) cudaFree(v.d_blob);
+    for (auto& v : ctx->vocabs) { if (v.d_blob) cudaFree(v.d_blob); if (v.d_hot) cudaFree(v.d_hot); }
     for (int k = 0; k < CFBPE_NUM_KERNELS; ++k) for (int j = 0; j < 2; ++j) if (ctx->prof.ev[k][j]) cudaEventDestroy(ctx->prof.ev[k][j]);
     for (int j = 0; j < 2; ++j) {
         if (ctx->prof.h2d[j]) cudaEventDestroy(ctx->prof.h2d[j]);

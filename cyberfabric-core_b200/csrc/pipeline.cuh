@@ -114,7 +114,7 @@ inline void enqueue_short(const BatchView& b, const VocabSet& vs, const Workspac
     CFBPE_LAUNCH(bpe_lookup_kernel, n_tiles2k, kLookupWarps * 32, stream, b, vs, w.piece_bits, w.dense, w.tok_bits, w.miss, w.status);
     CFBPE_MARK(prof, K_ENCODE, stream, false);
     CFBPE_MARK(prof, K_MERGE, stream, true);
-    CFBPE_LAUNCH(bpe_merge_kernel, long_grid + long_grid / 2, kPieceWarps * 32, stream,      // 6 CTAs of 32 KB per SM
+    CFBPE_LAUNCH_SMEM(bpe_merge_kernel, long_grid + long_grid / 2, kPieceWarps * 32, CFBPE_MERGE_HOT ? kHotCap * 8u : 0u, stream,      // 6 CTAs of 32 KB per SM
                  b, vs, w.piece_bits, w.dense, w.tok_bits, w.miss, w.status);
     CFBPE_MARK(prof, K_MERGE, stream, false);
 }
@@ -166,7 +166,7 @@ inline void enqueue_emit(const BatchView& b, const Workspace& w, uint32_t* out_i
         CFBPE_LAUNCH(emit_compact_kernel, n_scan_tiles(b.total_bytes), 256, stream, w.tok_bits, w.piece_bits, n_flag_words(b.total_bytes), w.tile_base,
                      w.dense, w.ids_by_pos, out_ids, out_cap);
     }
-    CFBPE_LAUNCH(prompt_offsets_kernel, static_cast<unsigned>((static_cast<uint64_t>(b.n_prompts) + 1 + 255) / 256), 256, stream,
+    CFBPE_LAUNCH(prompt_offsets_kernel, static_cast<unsigned>((static_cast<uint64_t>(b.n_prompts) + 1 + 7) / 8), 256, stream,      // a warp per prompt boundary
                  b, w.tok_bits, w.tile_base, out_offsets, out_counts, w.status);
     CFBPE_MARK(prof, K_EMIT, stream, false);
 }

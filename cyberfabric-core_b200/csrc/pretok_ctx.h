@@ -52,18 +52,22 @@ enum : uint32_t {
 enum : uint32_t { PQ_DONE = 0xFF, PQ_NOSYNC = 0xFE, PQ_SKIP1 = 0xFD, PQ_SKIP2 = 0xFC };    // pseudo split states in ProdInfo::q
 struct ProdInfo { uint8_t q, ctx; };                 // what a product state is made of
 
+// Every array starts on a 16-byte boundary and is a multiple of 16 bytes long: K1 stages them into shared memory with TMA bulk
+// copies (cp.async.bulk: 16-byte granularity on both sides).
 struct SplitTablesHost {
-    uint8_t cls256[256];
-    uint16_t fsm16[kNumPatterns * kFsm16Size];
-    uint16_t ctx16[2 * kCtx16Size];
-    uint16_t ctxinfo[2 * kCtxMax];
-    uint32_t n_ctx[2];
-    uint64_t prod[kNumPatterns * kProdMax * 16];     // [pattern][state * 16 + class]
-    ProdInfo prod_info[kNumPatterns * kProdMax];
-    uint8_t prod_skip[kNumPatterns * 2 * kCtxMax];   // [pattern][n - 1][context] -> state SKIPn(context)
-    uint8_t prod_start[kNumPatterns];                // the state (S_START, kCtxStart): where a prompt begins
-    uint32_t n_prod[kNumPatterns];
+    alignas(16) uint8_t cls256[256];
+    alignas(16) uint16_t fsm16[kNumPatterns * kFsm16Size];
+    alignas(16) uint16_t ctx16[2 * kCtx16Size];
+    alignas(16) uint16_t ctxinfo[2 * kCtxMax];
+    alignas(16) uint32_t n_ctx[4];
+    alignas(16) uint64_t prod[kNumPatterns * kProdMax * 16];     // [pattern][state * 16 + class]
+    alignas(16) ProdInfo prod_info[kNumPatterns * kProdMax];
+    alignas(16) uint8_t prod_skip[kNumPatterns * 2 * kCtxMax];   // [pattern][n - 1][context] -> state SKIPn(context)
+    alignas(16) uint8_t prod_start[16];                          // the state (S_START, kCtxStart): where a prompt begins (kNumPatterns used)
+    alignas(16) uint32_t n_prod[kNumPatterns];
 };
+static_assert(sizeof(uint16_t) * kNumPatterns * kFsm16Size % 16 == 0 && kProdTableBytes % 16 == 0 && sizeof(ProdInfo) * kNumPatterns * kProdMax % 16 == 0,
+              "table sizes are multiples of 16 bytes (bulk copies)");
 
 inline void build_split_tables(SplitTablesHost* t) {
     memset(t, 0, sizeof *t);

@@ -220,6 +220,12 @@ __device__ __noinline__ void split_resume(const BatchView b, uint32_t pats, cons
     split_thread<2, 16, kFsm16Size>(b, *none, uc, s_fsm, s_cls, piece_bits, status, fix_list, fix_cap, 0, pos, pos, pidx, q, alc, last, lbe, pats);
 }
 
+// ---- TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier): how K1 stages its tables.  One thread arms the
+//      barrier with the byte count and issues the copies; everybody waits on the barrier's phase.  (The emulator copies in a loop.)
+#ifndef CFBPE_SPLIT_TMA
+#define CFBPE_SPLIT_TMA 1          // A/B: 0 = cooperative load loop (ld.global + st.shared by all threads)
+#endif
+
 constexpr uint32_t kSplitWarpOwned = 30;            // blocks of 16 bytes a WARP owns: lanes 1..30; lanes 0 and 31 classify the blocks on
                                                     // either side and do not walk (ghosts), so neighbours are one shuffle away and no
                                                     // warp ever waits for another (a CTA-wide exchange spent 39 % of the time in barriers)
@@ -236,18 +242,36 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
                       const uint32_t* __restrict__ block_prompt, uint32_t* __restrict__ piece_bits, DeviceStatus* status,
                       SplitFix* fix_list, uint32_t fix_cap, uint32_t n_tabs, uint32_t n_tiles) {
     CFBPE_DYN_SMEM(s_dyn);                                   // n_tabs product tables of kProdTableBytes
-    __shared__ uint16_t s_fsm[kNumPatterns * kFsm16Size];    // for the end-of-prompt transition and the per-character walker
-    __shared__ uint16_t s_ctx[2 * kCtx16Size];
-    __shared__ uint8_t s_cls[256];
-    __shared__ ProdInfo s_info[kNumPatterns * kProdMax];
-    __shared__ uint8_t s_skip[kNumPatterns * 2 * kCtxMax];
-    __shared__ uint8_t s_start[kNumPatterns];
+    __shared__ __align__(16) uint16_t s_fsm[kNumPatterns * kFsm16Size];    // for the end-of-prompt transition and the per-character walker
+    __shared__ __align__(16) uint16_t s_ctx[2 * kCtx16Size];
+    __shared__ __align__(16) uint8_t s_cls[256];
+    __shared__ __align__(16) ProdInfo s_info[kNumPatterns * kProdMax];
+    __shared__ __align__(16) uint8_t s_skip[kNumPatterns * 2 * kCtxMax];
+    __shared__ __align__(16) uint8_t s_start[16];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ SplitEnv s_env;
     const uint32_t t = threadIdx.x, lane = t & 31u;
     const bool multi = b.vocab_ids != nullptr;
     const uint32_t pat0 = vs.v[0].pattern_id;
-    {   // tables: once per CTA (its warps walk many tiles)
+    {   // tables: once per CTA (its warps walk many tiles) -- staged by TMA: seven bulk copies, one mbarrier
         const uint64_t* src = uc.prod + (n_tabs == 1 ? static_cast<uint64_t>(pat0) * kProdMax * 16 : 0);
+#if CFBPE_SPLIT_TMA && !defined(CUSIM_EMULATOR)
+        if (t == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (t == 0) {
+            const uint32_t b_prod = n_tabs * kProdTableBytes, b_fsm = sizeof(uint16_t) * kNumPatterns * kFsm16Size, b_ctx = sizeof(uint16_t) * 2 * kCtx16Size,
+                           b_info = sizeof(ProdInfo) * kNumPatterns * kProdMax, b_skip = kNumPatterns * 2 * kCtxMax;
+            mbar_expect_tx(&s_bar, b_prod + b_fsm + b_ctx + b_info + b_skip + 16u + 256u);
+            bulk_g2s(s_dyn, src, b_prod, &s_bar);
+            bulk_g2s(s_fsm, uc.fsm16, b_fsm, &s_bar);
+            bulk_g2s(s_ctx, uc.ctx16, b_ctx, &s_bar);
+            bulk_g2s(s_info, uc.prod_info, b_info, &s_bar);
+            bulk_g2s(s_skip, uc.prod_skip, b_skip, &s_bar);
+            bulk_g2s(s_start, uc.prod_start, 16u, &s_bar);
+            bulk_g2s(s_cls, uc.cls256, 256u, &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+#else
         uint64_t* dst = reinterpret_cast<uint64_t*>(s_dyn);
         for (uint32_t i = t; i < n_tabs * kProdMax * 16; i += kSplitCta) dst[i] = src[i];
         for (uint32_t i = t; i < kNumPatterns * kFsm16Size; i += kSplitCta) s_fsm[i] = uc.fsm16[i];
@@ -256,6 +280,8 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
         for (uint32_t i = t; i < kNumPatterns * 2 * kCtxMax; i += kSplitCta) s_skip[i] = uc.prod_skip[i];
         if (t < kNumPatterns) s_start[t] = uc.prod_start[t];
         s_cls[t] = uc.cls256[t];
+        (void)s_bar;
+#endif
     }
     uint32_t pats = 0;
 #pragma unroll
