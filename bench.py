@@ -121,6 +121,30 @@ def cpu_encode_rate(data, offs, rv, threads, target_s=12.0):
     return b / t, "first %d prompts (%d bytes) of the same batch, %.1f s wall" % (k, b, t), t, b
 
 
+def pin_to_gpu_numa_node(local_rank):
+    """Run this rank -- and allocate its pinned buffers, which follow the allocating thread's node -- on the CPUs next to its GPU.
+    With eight ranks the host leg is bound by the box's PCIe roots and memory: a rank whose buffers sit on the other socket pays
+    the inter-socket link on every copy (SCALE_r01: e2e efficiency 0.87 at N = 8 without pinning).  Returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1 and 64 * i + b < n_cpu]
+        node = None
+        try:
+            node = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            pass
+        if cpus and len(cpus) < n_cpu:
+            os.sched_setaffinity(0, cpus)
+            return {"pinned": True, "cpus": len(cpus), "first_cpu": cpus[0], "numa_node": node, "how": "nvml cpu affinity of the GPU"}
+        return {"pinned": False, "why": "the GPU's affinity covers every CPU (one node, or not exposed here)", "numa_node": node}
+    except Exception as e:   # noqa: BLE001
+        return {"pinned": False, "why": "nvml affinity query failed: %s" % type(e).__name__}
+
+
 def tiktoken_context_rate(data, offs, rv, threads, target_s=6.0):
     """context only (not the baseline of record): tiktoken 0.12.0 `encode_ordinary_batch(num_threads=threads)` on a prefix of the
     same batch, with the same ranks and pattern.  Returns a dict, or None when tiktoken is not importable."""
@@ -198,6 +222,7 @@ def main():
     ap.add_argument("--impl", default="cfbpe", choices=["cfbpe", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the batch (debug only; a scaled run is not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the extra config-5 record")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cfbpe" else args.warmup
     if args.impl == "reference":
@@ -217,6 +242,7 @@ def main():
         if world == 1 and args.gpus > 1:
             sys.stderr.write("bench.py: --gpus %d needs torchrun (one process per GPU)\n" % args.gpus)
             return 2
+    numa = pin_to_gpu_numa_node(local_rank)      # before any pinned allocation
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -333,6 +359,68 @@ def main():
     e2e_ms = max_over_ranks(max(c0.elapsed_time(c1), (time.perf_counter() - t0) * 1e3))
     e2e_value = total_all * args.steps / (e2e_ms * 1e-3)
     assert int(r.offsets[n]) == n_tokens
+    # ---- the two multi-GPU workloads BASELINE.json names, as extra records (the headline stays the weak-scaled config 3):
+    #   strong   configs[2] as ONE 65 536-prompt batch sharded by bytes over the N ranks (cfbpe.dist.shard_by_bytes); timed end to
+    #            end from host buffers, the host-side sharding and the gather of the per-prompt counts inside the timed region
+    #   config5  configs[4]: 256 tenants x 256 prompts, vocabulary = tenant mod 3 (cl100k / o200k / llama3 patterns), sharded likewise
+    def sharded_leg(g_data, g_offs, g_vid, names):
+        refs_all = None if g_vid is None else [P.VocabRef(names[int(v)]) for v in g_vid]
+        stage = {}
+
+        def once():
+            sh_bytes, sh_offs, sh_vid, (lo, hi) = D.shard_batch(g_data, g_offs, g_vid, rank, world)     # host-side sharding: inside the timed region
+            nb, nn = int(sh_offs[-1]), len(sh_offs) - 1
+            if "hb" not in stage:                                           # pinned staging of this rank's shard, allocated once
+                stage["hb"] = plug.ctx.pinned(nb + 64, np.uint8); stage["ho"] = plug.ctx.pinned(nn + 1, np.uint64)
+                stage["hi"] = plug.ctx.pinned(nb + 1, np.uint32); stage["hoo"] = plug.ctx.pinned(nn + 1, np.uint64); stage["hc"] = plug.ctx.pinned(max(nn, 1), np.uint32)
+            stage["hb"].array[:nb] = sh_bytes; stage["ho"].array[:] = sh_offs
+            req = P.EncodeBatchRequest(P.VocabRef(names[0]), stage["hb"].array[:nb], stage["ho"].array, None if refs_all is None else refs_all[lo:hi])
+            res = plug.encode_batch(ctx, req, out=P.EncodeBatchResponse(stage["hi"].array, stage["hoo"].array, stage["hc"].array))
+            counts = D.gather_counts(res.counts, dev) if world > 1 else res.counts      # the path's exchange: per-prompt counts of every shard
+            return res, counts, (lo, hi), nb
+        for _ in range(args.warmup):
+            once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res, counts, span, nb = once()
+        barrier()
+        ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        return res, counts, span, nb, ms
+
+    strong = None
+    s_data, s_offs, _, s_meta = (data, offs, None, None) if rank == 0 and args.scale == 1.0 else W.make_config(CONFIG_ID, args.scale)[:4]
+    res, counts, span, nb, ms = sharded_leg(s_data, s_offs, None, ["cl100k_base"])
+    strong = {"workload": "configs[2] as ONE batch of %d prompts (%d bytes) sharded by bytes over %d GPU(s)" % (len(s_offs) - 1, int(s_offs[-1]), world),
+              "value": int(s_offs[-1]) * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps, "shard_bytes_rank0": nb,
+              "tokens_total": int(np.asarray(counts, dtype=np.int64).sum()),
+              "timed": "host sharding + H2D + kernels + D2H + gather of per-prompt counts (wall clock, max over ranks)"}
+    config5 = None
+    if not args.no_config5:
+        c_data, c_offs, c_vid, c_meta = W.make_config(5, args.scale)
+        for nm in c_meta["vocabs"]:
+            if nm not in plug._slot:      # rank 0 parses, the packed tables travel by NCCL broadcast (cfbpe.dist)
+                if world == 1:
+                    plug.load_vocab(nm)
+                elif rank == 0:
+                    plug.load_vocab(nm); D.broadcast_blob(plug.export_vocab(nm), 0, dev)
+                else:
+                    plug.load_vocab(nm, D.broadcast_blob(None, 0, dev))
+        res5, counts5, span5, nb5, ms5 = sharded_leg(c_data, c_offs, c_vid, c_meta["vocabs"])
+        ok5 = True
+        if rank == 0:      # a sample of rank 0's shard against the oracle (checker only, untimed)
+            from oracle import oracle as _o
+            ovs = [_o.OracleVocab(plug.resolved[nm].file_bytes, plug.resolved[nm].max_ranks) for nm in c_meta["vocabs"]]
+            pats = [plug.resolved[nm].pattern_id for nm in c_meta["vocabs"]]
+            for i in np.random.default_rng(5).choice(span5[1] - span5[0], size=min(256, span5[1] - span5[0]), replace=False):
+                g = span5[0] + int(i); v = int(c_vid[g])
+                want = ovs[v].encode(pats[v], bytes(c_data[int(c_offs[g]):int(c_offs[g + 1])]))
+                ok5 = ok5 and np.array_equal(res5.ids[int(res5.offsets[i]):int(res5.offsets[i + 1])], want)
+        config5 = {"workload": "configs[4]: %d tenants x %d prompts, vocabulary = tenant mod 3 (%s), %d bytes, sharded by bytes over %d GPU(s)"
+                               % (256, (len(c_offs) - 1) // 256, "/".join(c_meta["vocabs"]), int(c_offs[-1]), world),
+                   "value": int(c_offs[-1]) * args.steps / (ms5 * 1e-3), "unit": UNIT, "ms_per_step": ms5 / args.steps,
+                   "tokens_total": int(np.asarray(counts5, dtype=np.int64).sum()), "parity_sample_rank0_ok": bool(ok5),
+                   "vocab_stand_in": True}
     clocks = sampler.stop() if rank == 0 else None
     # ---- parity of what was just timed, on EVERY rank (ranks != 0 run on NCCL-broadcast tables): each rank hashes its id stream and
     #      hands rank 0 a seeded sample of its prompts with the ids the e2e leg produced and the ids the device leg left in HBM;
@@ -428,6 +516,9 @@ def main():
                      "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
                      "path_algorithmic_bytes": path_alg,
                      "path_achieved_gbs": path_alg / (kernels_ms * 1e-3) / 1e9 if kernels_ms > 0 else 0.0},
+        "strong": strong,
+        "config5": config5,
+        "numa": numa,
         "cpu_baseline": cpu,
         "cpu_baseline_context": cpu_ctx,
         "clocks": clocks,

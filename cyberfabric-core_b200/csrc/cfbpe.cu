@@ -50,7 +50,7 @@ constexpr int kSideStreams = 16;
 #endif
 constexpr int kFrontStreams = CFBPE_FRONT_STREAMS;
 constexpr uint64_t kPipeChunkBytes = 12ull << 20;   // largest sub-batch of a pipelined host call (the sizes ramp up to it and down again); measured: profiles/e2e_subbatch_sizes_r01t.jsonl
-constexpr uint64_t kPipeMinBytes = 16ull << 20;     // smaller calls run as one shot
+constexpr uint64_t kPipeMinBytes = 4ull << 20;      // smaller calls run as one shot (a 134 MB batch sharded over 8 GPUs is 16.8 MB a rank: it must still pipeline)
 
 struct VocabSlot {
     bool loaded = false;
