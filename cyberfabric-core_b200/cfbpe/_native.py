@@ -26,9 +26,13 @@ EXPORTS = [
 ]
 
 
+MAX_DEVICES = 8
+
+
 class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("max_batch_bytes", C.c_uint64),
-                ("max_prompts", C.c_uint32), ("flags", C.c_uint32)]
+                ("max_prompts", C.c_uint32), ("flags", C.c_uint32),
+                ("devices", C.c_int32 * MAX_DEVICES), ("n_devices", C.c_uint32), ("n_workspaces", C.c_uint32)]
 
 
 class VocabInfo(C.Structure):
@@ -135,16 +139,28 @@ class PinnedArray:
 
 
 class Context:
-    """One device context (one per process / GPU)."""
+    """One context: one device (`device`) or several (`devices`: a host batch is sharded over them, NCCL inside the library),
+    `n_workspaces` independent workspaces per device (that many calls run concurrently).  max_batch_bytes is per device."""
 
-    def __init__(self, device=0, max_batch_bytes=0, max_prompts=0):
+    def __init__(self, device=0, max_batch_bytes=0, max_prompts=0, devices=None, n_workspaces=1):
         self._h = None
         L = load()
         cfg = Config(C.sizeof(Config), device, max_batch_bytes, max_prompts, 0)
+        if devices:
+            if len(devices) > MAX_DEVICES:
+                raise NativeError(EINVAL, "at most %d devices" % MAX_DEVICES)
+            for i, d in enumerate(devices):
+                cfg.devices[i] = int(d)
+            cfg.n_devices = len(devices)
+            device = int(devices[0])
+        cfg.n_workspaces = int(n_workspaces)
+        self.devices = list(devices) if devices else [device]
+        self.n_workspaces = int(n_workspaces)
         h = C.c_void_p()
         rc = L.cfbpe_create(C.byref(cfg), C.byref(h))
         if rc != OK:
-            raise NativeError(rc, "cfbpe_create failed (no sm_100 device visible?)" if rc == ENODEV else "cfbpe_create failed")
+            raise NativeError(rc, "cfbpe_create failed (no sm_100 device visible?)" if rc == ENODEV else
+                              ("cfbpe_create failed: " + L.cfbpe_last_error(None).decode("utf-8", "replace")))
         self._h = h
         self.device = device
 

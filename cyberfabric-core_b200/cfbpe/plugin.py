@@ -205,14 +205,14 @@ class GpuBpeTokenizerPlugin(TokenizerPluginClient):
 
     def __init__(self, device: int = 0, vocab_names: Sequence[str] = ("cl100k_base",), max_batch_bytes: int = 0,
                  max_prompts: int = 0, priority: int = 10, import_blobs: Optional[Dict[str, np.ndarray]] = None,
-                 allow_stand_in: bool = False):
+                 allow_stand_in: bool = False, devices: Optional[Sequence[int]] = None, n_workspaces: int = 1):
         """allow_stand_in: see cfbpe.vocabs.resolve -- benchmarks and tests only; a production plugin fails with VocabNotFound
         when a real rank file is missing instead of counting tokens with another vocabulary"""
         self.allow_stand_in = allow_stand_in
         self.max_batch_bytes = int(max_batch_bytes) if max_batch_bytes else 256 << 20     # cfbpe_create's defaults
         self.max_prompts = int(max_prompts) if max_prompts else 1 << 20
         try:
-            self.ctx = N.Context(device, max_batch_bytes, max_prompts)
+            self.ctx = N.Context(device, max_batch_bytes, max_prompts, devices=devices, n_workspaces=n_workspaces)
         except N.NativeError as e:
             raise _map_native(e) from e
         self._slot: Dict[str, int] = {}
@@ -220,7 +220,7 @@ class GpuBpeTokenizerPlugin(TokenizerPluginClient):
         self._lock = threading.Lock()
         self.instance = PluginInstance(
             id=GTS_PLUGIN_SCHEMA + "cyberfabric.gpu_bpe.b200.v1", vendor=self.VENDOR, priority=priority,
-            properties={"device": device, "vocabs": {}})
+            properties={"devices": list(devices) if devices else [device], "workspaces": n_workspaces, "vocabs": {}})
         for name in vocab_names:
             self.load_vocab(name, None if import_blobs is None else import_blobs.get(name))
 

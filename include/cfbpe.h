@@ -79,12 +79,22 @@ extern "C" {
 
 typedef struct cfbpe_ctx cfbpe_ctx; /* opaque */
 
+#define CFBPE_MAX_DEVICES 8
+
 typedef struct cfbpe_config {
-    uint32_t struct_size;     /* sizeof(cfbpe_config), for forward compatibility */
-    int32_t device;           /* CUDA device ordinal */
-    uint64_t max_batch_bytes; /* largest packed prompt buffer one call may carry (0 = 256 MiB) */
+    uint32_t struct_size;     /* sizeof(cfbpe_config), for forward compatibility: a caller built against the five-field struct of
+                                 ABI version 1 (24 bytes) still works, and gets one device and one workspace */
+    int32_t device;           /* CUDA device ordinal (used when n_devices == 0) */
+    uint64_t max_batch_bytes; /* largest packed prompt buffer one DEVICE takes in one call (0 = 256 MiB) */
     uint32_t max_prompts;     /* largest n_prompts of one call (0 = 1 Mi) */
     uint32_t flags;           /* reserved, 0 */
+    /* cfbpe_create(cfg: devices[], n_devices, ...) */
+    int32_t devices[CFBPE_MAX_DEVICES]; /* CUDA ordinals of a multi-device context */
+    uint32_t n_devices;       /* 0 = single device (`device`); > 1: a host batch is sharded by bytes on prompt boundaries over the
+                                 devices, the packed tables are broadcast and the per-shard token totals gathered with NCCL
+                                 (libnccl.so.2 is dlopen'ed; without it cfbpe_create fails with CFBPE_EIO) */
+    uint32_t n_workspaces;    /* independent workspaces per device (0 = 1, at most 16): that many calls run concurrently on the
+                                 context; each costs ~33 bytes of device memory per byte of max_batch_bytes */
 } cfbpe_config;
 
 typedef struct cfbpe_vocab_info {
@@ -113,7 +123,8 @@ CFBPE_API const char *cfbpe_build_id(void);
 
 CFBPE_API int cfbpe_create(const cfbpe_config *cfg, cfbpe_ctx **out);
 CFBPE_API void cfbpe_destroy(cfbpe_ctx *ctx);
-/* NUL-terminated description of the last failure on this ctx (valid until the next call) */
+/* NUL-terminated description of the last failure of the CALLING THREAD (valid until its next call): entry points run
+ * concurrently on one context, so the message is kept per thread, not per context */
 CFBPE_API const char *cfbpe_last_error(const cfbpe_ctx *ctx);
 
 /* Parse a rank file, build the lookup tables on the host and upload them.

@@ -44,7 +44,8 @@ def test_no_torch_types_in_the_abi():
 
 def test_struct_layouts_match_the_header():
     from cfbpe import _native as N
-    assert ctypes.sizeof(N.Config) == 24
+    assert ctypes.sizeof(N.Config) == 24 + 4 * 8 + 4 + 4          # the ABI-1 fields, then devices[8], n_devices, n_workspaces
+    assert N.Config.devices.offset == 24 and N.Config.n_devices.offset == 56 and N.Config.n_workspaces.offset == 60
     assert ctypes.sizeof(N.VocabInfo) == 24
     assert ctypes.sizeof(N.Profile) == 4 * 10 + 4 * 10 + 12 + 4 + 64
 
@@ -57,6 +58,15 @@ def test_create_fails_without_a_device(lib):
     with pytest.raises(N.NativeError) as ei:
         N.Context(0, 1 << 20, 16)
     assert ei.value.code == N.ENODEV       # no CPU fallback
+
+
+def test_old_and_bad_configs(lib):
+    """struct_size versions the config: too small a struct is refused before any CUDA call; so are duplicate devices"""
+    from cfbpe import _native as N
+    h = ctypes.c_void_p()
+    cfg = N.Config(8, 0, 1 << 20, 16, 0)
+    assert lib.cfbpe_create(ctypes.byref(cfg), ctypes.byref(h)) == N.EINVAL
+    assert lib.cfbpe_create(None, ctypes.byref(h)) == N.EINVAL
 
 
 def test_product_never_imports_the_oracle():

@@ -473,3 +473,100 @@ def test_async_device_calls_and_buffer_reuse(plug, ctx, oracle_vocabs):
             off = b["d_out"].cpu().numpy().astype(np.uint64)
             assert np.array_equal(off, want_off)
             assert np.array_equal(b["d_ids"][:int(off[-1])].cpu().numpy().view(np.uint32), want_ids)
+
+
+def test_concurrent_calls_on_one_context(oracle_vocabs, tekken_bytes):
+    """"safe to call concurrently from several host threads (internal stream pool ...)".  A context with
+    two workspaces: two threads encode different batches at the same time, both bit-exact, and the pair takes less than
+    1.3x one call (they would take 2x behind one mutex); a context with ONE workspace stays correct (calls queue)."""
+    import threading, time
+    from cfbpe import _native as N
+    from oracle import oracle
+    batches = []
+    for seed in (11, 12):
+        prompts = [s.encode() for s in fuzzgen.fuzz_strings(seed, 30000, max_atoms=60)]
+        data, offs = pack(prompts)
+        want = oracle.encode_batch([oracle_vocabs[0]], [0], data, offs, nthreads=os.cpu_count())
+        batches.append((data, offs, want))
+    for n_ws in (2, 1):
+        c = N.Context(0, 32 << 20, 1 << 16, n_workspaces=n_ws)
+        c.vocab_load(0, tekken_bytes, N.FORMAT_TIKTOKEN, 0, 100256)
+        pinned = []
+        for data, offs, _ in batches:      # pinned buffers: the copies of the two calls overlap too
+            hb = c.pinned(len(data), np.uint8); hb.array[:] = data
+            pinned.append((hb, c.pinned(len(data) + 1, np.uint32), c.pinned(len(offs), np.uint64), c.pinned(len(offs), np.uint32)))
+        out, errs = {}, []
+
+        def call(i):
+            try:
+                hb, hi, ho, hc = pinned[i]
+                out[i] = c.encode_batch(hb.array, batches[i][1], None, hi.array, ho.array, hc.array)
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+        for i in (0, 1):
+            call(i)                                   # warm-up, one after the other
+        t0 = time.perf_counter(); call(0); t_one = time.perf_counter() - t0
+        t0 = time.perf_counter(); call(1); t_one = max(t_one, time.perf_counter() - t0)
+        th = [threading.Thread(target=call, args=(i,)) for i in (0, 1)]
+        t0 = time.perf_counter()
+        for t in th: t.start()
+        for t in th: t.join()
+        t_both = time.perf_counter() - t0
+        assert not errs, errs
+        for i in (0, 1):
+            ids, off, counts = out[i]
+            assert np.array_equal(off, batches[i][2][1]) and np.array_equal(ids, batches[i][2][0]) and np.array_equal(counts, batches[i][2][2])
+        if n_ws == 2:
+            assert t_both < 1.6 * t_one, (t_both, t_one)     # measured ~1.1x; 2x would be serialisation
+        for p4 in pinned:
+            for p in p4: p.free()
+        c.close()
+
+
+def test_error_message_is_per_thread(plug, ctx):
+    """the last error is kept per calling thread: a failing call on one thread does not clobber another thread's message"""
+    import threading
+    from cfbpe import _native as N
+    msgs = {}
+
+    def bad():
+        try:
+            plug.ctx.encode_batch(*pack([b"bad \xff"]))
+        except N.NativeError as e:
+            msgs["bad"] = str(e)
+    t = threading.Thread(target=bad); t.start(); t.join()
+    assert "UTF-8" in msgs["bad"]
+    ids, off, counts = plug.ctx.encode_batch(*pack([b"fine"]))
+    assert len(ids) > 0
+
+
+@pytest.mark.skipif("__import__('torch').cuda.device_count() < 2")
+def test_multi_device_context_shards_a_batch(oracle_vocabs, tekken_bytes):
+    """cfbpe_create(cfg: devices[], n_devices): one context over two GPUs -- tables by ncclBroadcast, the batch sharded by bytes,
+    token totals by ncclAllGather, offsets rebased on the devices -- returns exactly what one device returns"""
+    import torch
+    from cfbpe import _native as N
+    from oracle import oracle
+    ndev = min(torch.cuda.device_count(), 8)
+    prompts = [s.encode() for s in fuzzgen.fuzz_strings(77, 40000, max_atoms=60) + fuzzgen.long_runs(5)] + [b"", b"x", b""]
+    data, offs = pack(prompts)
+    vid = (np.arange(len(prompts)) % 2).astype(np.uint8)
+    want_ids, want_off, want_counts = oracle.encode_batch([oracle_vocabs[0], oracle_vocabs[3]], [0, 3], data, offs, vocab_ids=vid, nthreads=os.cpu_count())
+    c = N.Context(0, 64 << 20, 1 << 17, devices=list(range(ndev)))
+    c.vocab_load(0, tekken_bytes, N.FORMAT_TIKTOKEN, 0, 100256)
+    c.vocab_load(1, tekken_bytes, N.FORMAT_TIKTOKEN, 3, 130072)
+    for _ in range(2):
+        ids, off, counts = c.encode_batch(data, offs, vid)
+        assert np.array_equal(off, want_off) and np.array_equal(ids, want_ids) and np.array_equal(counts, want_counts)
+        assert np.array_equal(c.count_batch(data, offs, vid), want_counts)
+    small = np.zeros(10, dtype=np.uint32)
+    with pytest.raises(N.NativeError) as ei:
+        c.encode_batch(data, offs, vid, small)
+    assert ei.value.code == N.ENOSPC
+    bad = prompts[:1000] + [b"\xff\xfe"] + prompts[1000:]
+    with pytest.raises(N.NativeError) as ei:
+        c.encode_batch(*pack(bad))
+    assert ei.value.code == N.EILSEQ
+    ids, off, counts = c.encode_batch(*pack([b"one prompt only"]))        # fewer prompts than devices: one device does it
+    assert np.array_equal(ids, oracle_vocabs[0].encode(0, b"one prompt only"))
+    c.close()
