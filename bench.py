@@ -463,16 +463,18 @@ def main():
     # ---- roofline of the dominant kernel
     hbm_gbs, peak_src = peaks()
     n_miss, n_list, list_parts = pr["n_miss_pieces"], pr["n_list_pieces"], pr["n_list_parts"]
+    n_extra = pr["n_extra_tokens"]
+    n_pieces = (n_tokens - long_tokens) - n_extra + n_miss + n_long        # every short piece is one token or a miss; long pieces once
     alg = {  # algorithmic bytes per launch
-        "pretok_split": total * (1 + 1 / 8) + 8 * (n + 1),                       # text in, piece-start flags out, offsets
-        "long_scan": total / 8 + 24.0 * n_long,                                   # flags in, work-list entries out
-        "bpe_encode": total * (1 + 1 / 8) + 4 * (n_tokens - long_tokens) + total / 8 + 4.0 * n_miss,   # text + flags in; ids, id flags, miss lists out
-        "bpe_merge": n_miss * (4 + 8 + 8),                                        # list entry, ~8 piece bytes, ~2 ids (estimate)
-        "bpe_long": long_bytes + 4.0 * (long_tokens + list_parts) + 24.0 * n_long,   # piece bytes in, ids (or hand-over state) out, work-list entries
-        "bpe_list": 12.0 * list_parts,                                            # id + rank of every part in, ids out
+        "pretok_split": total * (1 + 1 / 8 + 1 / 8) + 12 * (n + 1),              # text in, prompt-start flags in, piece-start flags out; offsets
+        "long_scan": total / 8 + 24.0 * n_long + 4 * total / 2048,                # flags in; work-list entries and per-tile piece counts out
+        "bpe_encode": total * (1 + 1 / 8) + 4.0 * n_pieces + total / 8 + 8.0 * n_miss + 12 * total / 2048,   # text + flags in; one word per piece, id flags, miss lists out
+        "bpe_merge": n_miss * (8 + 8 + 4) + 4.0 * n_extra,                        # list entry, ~8 piece bytes, the piece's word; its tokens
+        "bpe_long": long_bytes + 4.0 * long_tokens + 24.0 * n_long,               # piece bytes in, ids out, work-list entries
+        "bpe_list": 0.0,                                                          # (its bytes and ids are counted under bpe_long: the two share the long pieces)
         "flag_count": total / 8,
         "tile_scan": 0.0,
-        "emit_compact": total / 8 + 8 * n_tokens + 12 * (n + 1),
+        "emit_compact": 2 * total / 8 + 4.0 * n_pieces + 4.0 * n_extra + 4.0 * long_tokens + 4.0 * n_tokens + 12 * (n + 1),   # both flag arrays, ids by piece, extras, long ids; ids out
         "reserved": 0.0,
     }
     dom = max(kms, key=lambda k: kms[k])
@@ -510,7 +512,7 @@ def main():
                            "list_pieces_per_gpu": int(n_list), "list_parts_per_gpu": int(list_parts)},
         "parity": parity,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": 11 * args.steps,   # split, split fix-up, long-piece scan, piece lookup, short-piece merges, long pieces, long-piece lists, flag_count, tile_scan, emit, offsets
+        "gpu_launches": 13 * args.steps,   # prompt map, split, split fix-up, long-piece scan, big pieces (list), long pieces, piece-rank scan, piece lookup, short-piece merges, flag_count, tile_scan, emit, offsets
         "kernel_ms": kms,   # CUDA-event durations; bpe_long runs on a second stream next to bpe_encode, so they overlap
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                      "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],

@@ -45,7 +45,7 @@ class Profile(C.Structure):
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("n_tokens", C.c_uint64), ("n_bytes", C.c_uint64), ("n_long_pieces", C.c_uint64),
                 ("n_long_bytes", C.c_uint64), ("n_long_tokens", C.c_uint64),
-                ("n_miss_pieces", C.c_uint64), ("n_list_pieces", C.c_uint64), ("n_list_parts", C.c_uint64)]
+                ("n_miss_pieces", C.c_uint64), ("n_list_pieces", C.c_uint64), ("n_list_parts", C.c_uint64), ("n_extra_tokens", C.c_uint64)]
 
 
 _lib = None
@@ -294,4 +294,4 @@ class Context:
                 "h2d_ms": p.h2d_ms, "d2h_ms": p.d2h_ms, "total_ms": p.total_ms, "n_tokens": p.n_tokens,
                 "n_bytes": p.n_bytes, "n_long_pieces": p.n_long_pieces, "n_long_bytes": p.n_long_bytes,
                 "n_long_tokens": p.n_long_tokens, "n_miss_pieces": p.n_miss_pieces, "n_list_pieces": p.n_list_pieces,
-                "n_list_parts": p.n_list_parts}
+                "n_list_parts": p.n_list_parts, "n_extra_tokens": p.n_extra_tokens}

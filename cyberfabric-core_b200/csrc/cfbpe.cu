@@ -308,6 +308,7 @@ void fill_profile(Lane* ln, uint64_t n_bytes) {
     p.n_miss_pieces = static_cast<uint64_t>(ln->h_status->miss_n[0]) + ln->h_status->miss_n[1] + ln->h_status->miss_n[2];
     p.n_list_pieces = ln->h_status->defer_n;
     p.n_list_parts = ln->h_status->defer_parts;
+    p.n_extra_tokens = ln->h_status->extra_n;
     tl_profile_ready = true;
 }
 

@@ -114,7 +114,8 @@ typedef struct cfbpe_profile {
     uint64_t n_tokens, n_bytes, n_long_pieces;
     uint64_t n_long_bytes, n_long_tokens; /* bytes in / ids out of the long-piece kernels */
     uint64_t n_miss_pieces;               /* short pieces that were not one token (merged by bpe_merge) */
-    uint64_t n_list_pieces, n_list_parts; /* long pieces whose list phase ran in bpe_list, and their parts at hand-over */
+    uint64_t n_list_pieces, n_list_parts; /* big pieces whose list phase ran in bpe_list, and their parts when it began */
+    uint64_t n_extra_tokens;              /* tokens of the merged short pieces (the dense `extras` list of bpe_merge) */
 } cfbpe_profile;
 
 CFBPE_API int cfbpe_abi_version(void);

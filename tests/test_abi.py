@@ -47,7 +47,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(N.Config) == 24 + 4 * 8 + 4 + 4          # the ABI-1 fields, then devices[8], n_devices, n_workspaces
     assert N.Config.devices.offset == 24 and N.Config.n_devices.offset == 56 and N.Config.n_workspaces.offset == 60
     assert ctypes.sizeof(N.VocabInfo) == 24
-    assert ctypes.sizeof(N.Profile) == 4 * 10 + 4 * 10 + 12 + 4 + 64
+    assert ctypes.sizeof(N.Profile) == 4 * 10 + 4 * 10 + 12 + 4 + 72
 
 
 def test_create_fails_without_a_device(lib):

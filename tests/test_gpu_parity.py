@@ -505,19 +505,23 @@ def test_concurrent_calls_on_one_context(oracle_vocabs, tekken_bytes):
                 errs.append(e)
         for i in (0, 1):
             call(i)                                   # warm-up, one after the other
-        t0 = time.perf_counter(); call(0); t_one = time.perf_counter() - t0
-        t0 = time.perf_counter(); call(1); t_one = max(t_one, time.perf_counter() - t0)
-        th = [threading.Thread(target=call, args=(i,)) for i in (0, 1)]
-        t0 = time.perf_counter()
-        for t in th: t.start()
-        for t in th: t.join()
-        t_both = time.perf_counter() - t0
+        t_one, t_both = 1e9, 1e9
+        for _ in range(5):
+            for i in (0, 1):
+                t0 = time.perf_counter(); call(i); t_one = min(t_one, time.perf_counter() - t0)
+        for _ in range(5):
+            th = [threading.Thread(target=call, args=(i,)) for i in (0, 1)]
+            t0 = time.perf_counter()
+            for t in th: t.start()
+            for t in th: t.join()
+            t_both = min(t_both, time.perf_counter() - t0)
+        print("concurrent calls, %d workspace(s): one call %.3f ms, two at once %.3f ms (%.2fx), %d bytes each" % (n_ws, 1e3 * t_one, 1e3 * t_both, t_both / t_one, len(batches[0][0])))
         assert not errs, errs
         for i in (0, 1):
             ids, off, counts = out[i]
             assert np.array_equal(off, batches[i][2][1]) and np.array_equal(ids, batches[i][2][0]) and np.array_equal(counts, batches[i][2][2])
         if n_ws == 2:
-            assert t_both < 1.6 * t_one, (t_both, t_one)     # measured ~1.1x; 2x would be serialisation
+            assert t_both < 1.5 * t_one, (t_both, t_one, n_ws)     # two calls behind one mutex would take 2x
         for p4 in pinned:
             for p in p4: p.free()
         c.close()
