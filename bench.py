@@ -121,6 +121,39 @@ def cpu_encode_rate(data, offs, rv, threads, target_s=12.0):
     return b / t, "first %d prompts (%d bytes) of the same batch, %.1f s wall" % (k, b, t), t, b
 
 
+try:
+    ALL_CPUS = os.sched_getaffinity(0)          # before any NUMA pinning
+except Exception:
+    ALL_CPUS = None
+
+
+def host_cpu_budget():
+    """How many host threads can really run: the CPUs of the affinity mask, capped by the cgroup CPU quota when there is one
+    (a container that SEES 128 CPUs may be allowed far fewer; threads beyond the quota only get throttled).  -> (threads, facts)"""
+    visible = os.cpu_count() or 1
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = visible
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            q, per = open(path).read().split()[:2]
+            if q != "max":
+                quota = float(q) / float(per)
+        except Exception:
+            pass
+    if quota is None:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    n = aff if quota is None else max(1, min(aff, int(quota + 0.999)))
+    return n, {"visible_cpus": visible, "affinity_cpus": aff, "cgroup_quota_cpus": quota}
+
+
 def pin_to_gpu_numa_node(local_rank):
     """Run this rank -- and allocate its pinned buffers, which follow the allocating thread's node -- on the CPUs next to its GPU.
     With eight ranks the host leg is bound by the box's PCIe roots and memory: a rank whose buffers sit on the other socket pays
@@ -183,7 +216,7 @@ def run_reference(args):
     from cfbpe import workload as W
     data, offs, vid, meta = W.make_config(CONFIG_ID, 1.0)
     rv = V.resolve("cl100k_base", allow_stand_in=True)
-    threads = os.cpu_count() or 1
+    threads, cpu_facts = host_cpu_budget()
     per_step = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
     for _ in range(args.warmup):
         cpu_encode_rate(data, offs, rv, threads, target_s=per_step / 2)
@@ -198,7 +231,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": workload_config(rv, len(offs) - 1, meta["total_bytes"], W.CONFIGS[CONFIG_ID]["seed"], 1.0),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "each step: " + sample},
+                             "sample": "each step: " + sample, "host": cpu_facts},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit_line(json.dumps(line))
@@ -364,17 +397,20 @@ def main():
     #            end from host buffers, the host-side sharding and the gather of the per-prompt counts inside the timed region
     #   config5  configs[4]: 256 tenants x 256 prompts, vocabulary = tenant mod 3 (cl100k / o200k / llama3 patterns), sharded likewise
     def sharded_leg(g_data, g_offs, g_vid, names):
-        refs_all = None if g_vid is None else [P.VocabRef(names[int(v)]) for v in g_vid]
-        stage = {}
+        # The request buffers are pinned host memory, as in the e2e leg (set-up, untimed): the whole batch once; a shard is a
+        # VIEW of it (no copy), its offsets rebased on the host inside the timed region.
+        table = [P.VocabRef(nm) for nm in names]
+        g_pin = plug.ctx.pinned(len(g_data) + 64, np.uint8)
+        g_pin.array[:len(g_data)] = g_data
+        g_view = g_pin.array[:len(g_data)]
+        stage = {"g": g_pin}
 
         def once():
-            sh_bytes, sh_offs, sh_vid, (lo, hi) = D.shard_batch(g_data, g_offs, g_vid, rank, world)     # host-side sharding: inside the timed region
+            sh_bytes, sh_offs, sh_vid, (lo, hi) = D.shard_batch(g_view, g_offs, g_vid, rank, world)     # host-side sharding: inside the timed region
             nb, nn = int(sh_offs[-1]), len(sh_offs) - 1
-            if "hb" not in stage:                                           # pinned staging of this rank's shard, allocated once
-                stage["hb"] = plug.ctx.pinned(nb + 64, np.uint8); stage["ho"] = plug.ctx.pinned(nn + 1, np.uint64)
+            if "hi" not in stage:                                           # pinned output buffers of this rank's shard, allocated once
                 stage["hi"] = plug.ctx.pinned(nb + 1, np.uint32); stage["hoo"] = plug.ctx.pinned(nn + 1, np.uint64); stage["hc"] = plug.ctx.pinned(max(nn, 1), np.uint32)
-            stage["hb"].array[:nb] = sh_bytes; stage["ho"].array[:] = sh_offs
-            req = P.EncodeBatchRequest(P.VocabRef(names[0]), stage["hb"].array[:nb], stage["ho"].array, None if refs_all is None else refs_all[lo:hi])
+            req = P.EncodeBatchRequest(table[0], sh_bytes, sh_offs, None if sh_vid is None else table, None if sh_vid is None else sh_vid)
             res = plug.encode_batch(ctx, req, out=P.EncodeBatchResponse(stage["hi"].array, stage["hoo"].array, stage["hc"].array))
             counts = D.gather_counts(res.counts, dev) if world > 1 else res.counts      # the path's exchange: per-prompt counts of every shard
             return res, counts, (lo, hi), nb
@@ -496,10 +532,16 @@ def main():
 
     cpu, cpu_ctx = None, None
     if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        mask = os.sched_getaffinity(0)
+        try:                                      # the CPU legs get every host CPU, not only the ones next to the GPU
+            os.sched_setaffinity(0, ALL_CPUS or mask)
+        except Exception:
+            pass
+        threads, cpu_facts = host_cpu_budget()
         rate, sample, _, _ = cpu_encode_rate(data, offs, rv, threads)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "host": cpu_facts}
         cpu_ctx = tiktoken_context_rate(data, offs, rv, threads)
+        os.sched_setaffinity(0, mask)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

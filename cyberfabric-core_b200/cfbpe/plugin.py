@@ -96,6 +96,8 @@ class EncodeBatchRequest:
     bytes: np.ndarray            # uint8, packed UTF-8 of all prompts
     offsets: np.ndarray          # uint64, n+1, offsets[0] == 0
     vocabs_per_prompt: Optional[Sequence[VocabRef]] = None   # multi-tenant batches: one vocab per prompt
+    vocab_index: Optional[np.ndarray] = None   # uint8, n: with it, vocabs_per_prompt lists the DISTINCT vocabularies and
+                                               # vocab_index[i] picks prompt i's (large batches: no per-prompt objects)
 
 
 @dataclass
@@ -111,6 +113,7 @@ class CountTokensRequest:
     bytes: np.ndarray
     offsets: np.ndarray
     vocabs_per_prompt: Optional[Sequence[VocabRef]] = None
+    vocab_index: Optional[np.ndarray] = None
 
 
 @dataclass
@@ -119,6 +122,7 @@ class DecodeBatchRequest:
     ids: np.ndarray              # uint32, packed ids of all sequences
     offsets: np.ndarray          # uint64, n+1 (in ids)
     vocabs_per_prompt: Optional[Sequence[VocabRef]] = None
+    vocab_index: Optional[np.ndarray] = None
 
 
 @dataclass
@@ -265,9 +269,25 @@ class GpuBpeTokenizerPlugin(TokenizerPluginClient):
         if req.vocabs_per_prompt is None:
             slot = self._resolve_slot(req.vocab)
             return None if slot == 0 else np.full(max(n, 1), slot, dtype=np.uint8)
+        idx = getattr(req, "vocab_index", None)
+        if idx is not None:         # a table of distinct vocabularies + one index per prompt
+            if not isinstance(idx, np.ndarray) or idx.dtype != np.uint8 or idx.ndim != 1 or len(idx) != n:
+                raise InvalidInput("vocab_index must be a uint8 array with one entry per prompt")
+            lut = np.fromiter((self._resolve_slot(r) for r in req.vocabs_per_prompt), dtype=np.uint8, count=len(req.vocabs_per_prompt))
+            if n and int(idx.max()) >= len(lut):
+                raise InvalidInput("vocab_index names entry %d of %d vocabularies" % (int(idx.max()), len(lut)))
+            return lut[idx] if n else np.zeros(1, dtype=np.uint8)
         if len(req.vocabs_per_prompt) != n:
             raise InvalidInput("vocabs_per_prompt must name one vocab per prompt")
-        return np.fromiter((self._resolve_slot(r) for r in req.vocabs_per_prompt), dtype=np.uint8, count=n)
+        memo = {}
+        out = np.empty(max(n, 1), dtype=np.uint8)
+        for i, r in enumerate(req.vocabs_per_prompt):
+            k = r.name
+            v = memo.get(k)
+            if v is None:
+                v = memo[k] = self._resolve_slot(r)
+            out[i] = v
+        return out
 
     @staticmethod
     def _check_arrays(req):

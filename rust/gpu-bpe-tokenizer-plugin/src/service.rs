@@ -75,7 +75,19 @@ impl Service {
     }
 
     /// one vocabulary id per prompt, or `None` when the whole batch uses slot 0
-    fn vocab_ids(&self, vocab: &VocabRef, per_prompt: Option<&[VocabRef]>, n: usize) -> Result<Option<Vec<u8>>, TokenizerError> {
+    fn vocab_ids(&self, vocab: &VocabRef, per_prompt: Option<&[VocabRef]>, index: Option<&[u8]>, n: usize) -> Result<Option<Vec<u8>>, TokenizerError> {
+        if let (Some(table), Some(idx)) = (per_prompt, index) {
+            // a table of distinct vocabularies + one index per prompt
+            if idx.len() != n {
+                return Err(TokenizerError::InvalidInput("vocab_index must hold one entry per prompt".to_owned()));
+            }
+            let lut = table.iter().map(|r| self.slot(r)).collect::<Result<Vec<_>, _>>()?;
+            return idx
+                .iter()
+                .map(|&i| lut.get(i as usize).copied().ok_or_else(|| TokenizerError::InvalidInput(format!("vocab_index names entry {i} of {} vocabularies", lut.len()))))
+                .collect::<Result<Vec<_>, _>>()
+                .map(Some);
+        }
         match per_prompt {
             Some(v) if v.len() != n => Err(TokenizerError::InvalidInput("vocabs_per_prompt must name one vocabulary per prompt".to_owned())),
             Some(v) => v.iter().map(|r| self.slot(r)).collect::<Result<Vec<_>, _>>().map(Some),
@@ -91,7 +103,7 @@ impl Service {
 impl TokenizerPluginClient for Service {
     async fn encode_batch(&self, _ctx: &SecurityContext, req: EncodeBatchRequest) -> Result<EncodeBatchResponse, TokenizerError> {
         let n = req.offsets.len().saturating_sub(1);
-        let vid = self.vocab_ids(&req.vocab, req.vocabs_per_prompt.as_deref(), n)?;
+        let vid = self.vocab_ids(&req.vocab, req.vocabs_per_prompt.as_deref(), req.vocab_index.as_deref(), n)?;
         let native = self.native.clone();
         // never block a tokio worker on a CUDA synchronisation (precedent: modules/file-parser/src/infra/parsers/html_parser.rs:47)
         let out = tokio::task::spawn_blocking(move || native.encode_batch(&req.bytes, &req.offsets, vid.as_deref()))
@@ -103,7 +115,7 @@ impl TokenizerPluginClient for Service {
 
     async fn count_tokens(&self, _ctx: &SecurityContext, req: CountTokensRequest) -> Result<Vec<u32>, TokenizerError> {
         let n = req.offsets.len().saturating_sub(1);
-        let vid = self.vocab_ids(&req.vocab, req.vocabs_per_prompt.as_deref(), n)?;
+        let vid = self.vocab_ids(&req.vocab, req.vocabs_per_prompt.as_deref(), req.vocab_index.as_deref(), n)?;
         // small requests (a chat message is a few KB) ride in a shared device batch; large ones go straight through
         if (req.bytes.len() as u64) < self.batcher.direct_threshold() {
             return self.batcher.count(req.bytes, req.offsets, vid).await;
@@ -117,7 +129,7 @@ impl TokenizerPluginClient for Service {
 
     async fn decode_batch(&self, _ctx: &SecurityContext, req: DecodeBatchRequest) -> Result<DecodeBatchResponse, TokenizerError> {
         let n = req.offsets.len().saturating_sub(1);
-        let vid = self.vocab_ids(&req.vocab, req.vocabs_per_prompt.as_deref(), n)?;
+        let vid = self.vocab_ids(&req.vocab, req.vocabs_per_prompt.as_deref(), req.vocab_index.as_deref(), n)?;
         let native = self.native.clone();
         let (bytes, offsets) = tokio::task::spawn_blocking(move || native.decode_batch(&req.ids, &req.offsets, vid.as_deref()))
             .await

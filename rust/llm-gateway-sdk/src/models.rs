@@ -22,6 +22,9 @@ pub struct EncodeBatchRequest {
     pub offsets: Vec<u64>,
     /// multi-tenant batches: one vocabulary per prompt (overrides `vocab`)
     pub vocabs_per_prompt: Option<Vec<VocabRef>>,
+    /// with it, `vocabs_per_prompt` lists the DISTINCT vocabularies and `vocab_index[i]` picks prompt i's
+    /// (a 65 536-prompt batch carries three names and 64 KiB of indices, not 65 536 strings)
+    pub vocab_index: Option<Vec<u8>>,
 }
 
 #[derive(Debug, Clone, Default)]
@@ -39,6 +42,7 @@ pub struct CountTokensRequest {
     pub bytes: Bytes,
     pub offsets: Vec<u64>,
     pub vocabs_per_prompt: Option<Vec<VocabRef>>,
+    pub vocab_index: Option<Vec<u8>>,
 }
 
 #[derive(Debug, Clone)]
@@ -47,6 +51,7 @@ pub struct DecodeBatchRequest {
     pub ids: Vec<u32>,
     pub offsets: Vec<u64>,
     pub vocabs_per_prompt: Option<Vec<VocabRef>>,
+    pub vocab_index: Option<Vec<u8>>,
 }
 
 #[derive(Debug, Clone, Default)]
