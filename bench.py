@@ -412,7 +412,8 @@ def main():
                 stage["hi"] = plug.ctx.pinned(nb + 1, np.uint32); stage["hoo"] = plug.ctx.pinned(nn + 1, np.uint64); stage["hc"] = plug.ctx.pinned(max(nn, 1), np.uint32)
             req = P.EncodeBatchRequest(table[0], sh_bytes, sh_offs, None if sh_vid is None else table, None if sh_vid is None else sh_vid)
             res = plug.encode_batch(ctx, req, out=P.EncodeBatchResponse(stage["hi"].array, stage["hoo"].array, stage["hc"].array))
-            counts = D.gather_counts(res.counts, dev) if world > 1 else res.counts      # the path's exchange: per-prompt counts of every shard
+            # the path's exchange: per-prompt counts of every shard (every rank cut the batch the same way and knows the sizes)
+            counts = D.gather_counts(res.counts, dev, sizes=[h - l for l, h in D.shard_by_bytes(g_offs, world)]) if world > 1 else res.counts
             return res, counts, (lo, hi), nb
         for _ in range(args.warmup):
             once()
@@ -431,6 +432,33 @@ def main():
               "value": int(s_offs[-1]) * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps, "shard_bytes_rank0": nb,
               "tokens_total": int(np.asarray(counts, dtype=np.int64).sum()),
               "timed": "host sharding + H2D + kernels + D2H + gather of per-prompt counts (wall clock, max over ranks)"}
+    # the same batch through ONE context over all the GPUs of the run (cfbpe_config.devices[]): sharding, the NCCL gather of
+    # the totals and the rebasing of the offsets happen inside the library; rank 0 makes the call, the other ranks wait
+    strong_lib = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            try:
+                from cfbpe import _native as NN
+                cN = NN.Context(0, int(s_offs[-1]) // world + (16 << 20), len(s_offs), devices=list(range(world)))
+                cN.vocab_load(0, rv.file_bytes, rv.fmt, rv.pattern_id, rv.max_ranks or 0)
+                hb = cN.pinned(len(s_data) + 64, np.uint8); hb.array[:len(s_data)] = s_data
+                ho = (cN.pinned(int(s_offs[-1]) + 1, np.uint32), cN.pinned(len(s_offs), np.uint64), cN.pinned(len(s_offs), np.uint32))
+                for _ in range(args.warmup):
+                    rN = cN.encode_batch(hb.array[:len(s_data)], s_offs, None, *[x.array for x in ho])
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    rN = cN.encode_batch(hb.array[:len(s_data)], s_offs, None, *[x.array for x in ho])
+                msN = (time.perf_counter() - t0) * 1e3
+                same = bool(int(rN[1][-1]) == int(np.asarray(counts, dtype=np.int64).sum()) and np.array_equal(rN[2], np.asarray(counts, dtype=np.uint32)))
+                strong_lib = {"workload": "the same batch through ONE context over %d devices (cfbpe_config.devices[]): sharding, NCCL gather of the shard "
+                                          "totals and offset rebasing inside the library; one host process" % world,
+                              "value": int(s_offs[-1]) * args.steps / (msN * 1e-3), "unit": UNIT, "ms_per_step": msN / args.steps,
+                              "counts_equal_to_the_sharded_leg": same}
+                cN.close()
+            except Exception as e:   # noqa: BLE001
+                strong_lib = {"error": "%s: %s" % (type(e).__name__, e)}
+        barrier()
     config5 = None
     if not args.no_config5:
         c_data, c_offs, c_vid, c_meta = W.make_config(5, args.scale)
@@ -560,7 +588,7 @@ def main():
                      "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
                      "path_algorithmic_bytes": path_alg,
                      "path_achieved_gbs": path_alg / (kernels_ms * 1e-3) / 1e9 if kernels_ms > 0 else 0.0},
-        "strong": strong,
+        "strong": strong, "strong_one_context": strong_lib,
         "config5": config5,
         "numa": numa,
         "cpu_baseline": cpu,

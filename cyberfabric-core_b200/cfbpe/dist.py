@@ -83,17 +83,20 @@ def gather_totals(local_total, device=None) -> np.ndarray:
     return torch.cat(out).cpu().numpy()
 
 
-def gather_counts(local_counts: np.ndarray, device=None) -> np.ndarray:
+def gather_counts(local_counts: np.ndarray, device=None, sizes=None) -> np.ndarray:
     """all_gather of the per-prompt counts of every shard (variable length), in rank order: a dense global
-    counts vector from which out_offsets follows by one exclusive scan."""
+    counts vector from which out_offsets follows by one exclusive scan.  `sizes`: the shards' prompt counts when every rank
+    already knows them (they all cut the batch with shard_by_bytes) -- saves the first collective and its synchronisation."""
     import torch
     import torch.distributed as dist
     dev = torch.device("cpu") if device is None else device
     world = dist.get_world_size()
-    sizes = gather_totals(len(local_counts), device)
-    m = int(sizes.max()) if world else 0
+    if sizes is None:
+        sizes = gather_totals(len(local_counts), device)
+    m = int(max(sizes)) if world else 0
     pad = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
-    pad[:len(local_counts)] = torch.from_numpy(local_counts.astype(np.int32)).to(dev)
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad)
-    return np.concatenate([o.cpu().numpy()[:int(s)] for o, s in zip(out, sizes)]).astype(np.uint32)
+    pad[:len(local_counts)] = torch.from_numpy(local_counts.view(np.int32) if local_counts.dtype == np.uint32 else local_counts.astype(np.int32)).to(dev, non_blocking=True)
+    out = torch.empty(world * max(m, 1), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(out, pad)
+    host = out.cpu().numpy().view(np.uint32).reshape(world, max(m, 1))
+    return np.concatenate([host[r, :int(s)] for r, s in enumerate(sizes)])
