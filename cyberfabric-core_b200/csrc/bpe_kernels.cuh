@@ -35,7 +35,7 @@ namespace cfbpe {
 constexpr uint32_t kMaxVocabs = 8;
 // path counters for the emulator tests (which path did a test actually exercise); nothing on the device
 #ifdef CUSIM_EMULATOR
-inline unsigned long long* dbg_counters() { static unsigned long long c[8]; return c; }
+inline unsigned long long* dbg_counters() { static unsigned long long c[16]; return c; }
 #define CFBPE_DBG_COUNT(i) (++dbg_counters()[i])
 #else
 #define CFBPE_DBG_COUNT(i) ((void)0)
@@ -43,6 +43,7 @@ inline unsigned long long* dbg_counters() { static unsigned long long c[8]; retu
 // 0: pieces deferred to bpe_list_kernel  1: list -> batched switches (medium pieces)  2: the same in bpe_list_kernel
 // 3: K1 bulk whitespace runs  4: K1 bulk digit runs  5: pieces on the global-memory list path
 // 6: rounds of bpe_list_kernel  7: merges taken in them
+// 8: K1 calls of the per-character walker (a lane crossed its 32-byte window)  9: characters it walked  10: K1 warp tiles
 
 #ifndef CFBPE_SPLIT_CHUNK
 #define CFBPE_SPLIT_CHUNK 64
@@ -80,7 +81,7 @@ struct DeviceStatus {
     uint32_t miss_next[3]; // K2m work tickets
     uint32_t miss_overflow;
     uint32_t extra_n;      // tokens of merged short pieces written to DenseIds::extras so far
-    uint32_t pad4;
+    uint32_t split_next;   // K1 work ticket: the next warp tile (tiles differ widely in cost: a tile that enters a 4 KiB run costs ten average ones)
     uint32_t fix_n;        // K1 threads that stopped in S_W_U (pretok_fixup_kernel finishes them)
     uint32_t bad_vocab;    // != 0: a prompt names a vocabulary id that is not loaded (device-path callers; the host paths check before)
     uint32_t defer_n;      // pieces K2b handed to K2c ...
@@ -114,12 +115,33 @@ __device__ __forceinline__ void or_bits(uint32_t* __restrict__ words, uint64_t w
     if (bits) atomicOr(&words[word], bits);
 }
 
+// L2 prefetch of the line at p (a long run is scanned by ONE lane: without it every iteration is a DRAM round trip)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#if !defined(CUSIM_EMULATOR)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // end of the run of bytes equal to c that starts at pos (pos < pe, s[pos] == c need not hold): first position in
 // [pos, pe) whose byte differs, 16 bytes per load once aligned
 __device__ __forceinline__ uint64_t same_byte_run_end(const uint8_t* __restrict__ s, uint64_t pos, uint64_t pe, uint32_t c) {
     uint64_t e = pos;
     while (e < pe && (reinterpret_cast<uintptr_t>(s + e) & 15u)) { if (s[e] != c) return e; ++e; }
     const uint32_t w = c * 0x01010101u;
+    for (uint64_t a = e; a < pe && a < e + 1024; a += 128) prefetch_l2(s + a);
+    while (e + 128 <= pe) {     // eight loads in flight: the loop is one dependent memory round trip per iteration
+        if (e + 1024 < pe) prefetch_l2(s + e + 1024);
+        uint4 v[8];
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const uint4*>(s + e + 16 * k);
+        uint32_t d = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) d |= (v[k].x ^ w) | (v[k].y ^ w) | (v[k].z ^ w) | (v[k].w ^ w);
+        if (d) break;
+        e += 128;
+    }
     while (e + 16 <= pe) {
         const uint4 v = *reinterpret_cast<const uint4*>(s + e);
         if (v.x != w || v.y != w || v.z != w || v.w != w) break;
@@ -135,6 +157,18 @@ __device__ __forceinline__ bool four_ascii_digits(uint32_t w) {
 __device__ __forceinline__ uint64_t ascii_digit_run_end(const uint8_t* __restrict__ s, uint64_t pos, uint64_t pe) {
     uint64_t e = pos;
     while (e < pe && (reinterpret_cast<uintptr_t>(s + e) & 15u)) { if ((s[e] - '0') >= 10u) return e; ++e; }
+    for (uint64_t a = e; a < pe && a < e + 1024; a += 128) prefetch_l2(s + a);
+    while (e + 128 <= pe) {      // eight loads in flight (see same_byte_run_end)
+        if (e + 1024 < pe) prefetch_l2(s + e + 1024);
+        uint4 v[8];
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const uint4*>(s + e + 16 * k);
+        bool ok = true;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) ok = ok && four_ascii_digits(v[k].x) && four_ascii_digits(v[k].y) && four_ascii_digits(v[k].z) && four_ascii_digits(v[k].w);
+        if (!ok) break;
+        e += 128;
+    }
     while (e + 16 <= pe) {
         const uint4 v = *reinterpret_cast<const uint4*>(s + e);
         if (!(four_ascii_digits(v.x) && four_ascii_digits(v.y) && four_ascii_digits(v.z) && four_ascii_digits(v.w))) break;
@@ -224,7 +258,24 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
         if (!kFix && p - cs < kSplitChunk) mine |= 1ull << (p - cs);
         else atomicOr(&piece_bits[p >> 5], 1u << (p & 31));
     };
+#ifdef CUSIM_EMULATOR
+    const uint64_t dbg_pos0 = pos; uint64_t dbg_iters = 0;
+    struct DbgWalk { uint64_t p0, *it, *pp; const uint8_t* s; int mode; ~DbgWalk() { if (getenv("CFBPE_DBG_WALK") && *it > (uint64_t)atoi(getenv("CFBPE_DBG_WALK"))) { fprintf(stderr, "walk mode %d: %llu iterations from %llu to %llu: ", mode, (unsigned long long)*it, (unsigned long long)p0, (unsigned long long)*pp); for (int i = 0; i < 40; ++i) fputc(s[p0 + i] >= 32 && s[p0 + i] < 127 ? s[p0 + i] : '.', stderr); fputc('\n', stderr); } } } dbg_walk{dbg_pos0, &dbg_iters, &pos, s, kMode};
+#endif
+    if (kMode == 2) CFBPE_DBG_COUNT(8);
+#if defined(CFBPE_TILE_CLOCK) && !defined(CUSIM_EMULATOR)
+    const long long rs_t0 = clock64(); long long rs_bulk = 0, rs_scan = 0; unsigned rs_iters = 0; const uint64_t rs_pos0 = pos;
+    struct RsPrint { const long long* t0; long long* bulk; long long* scan; unsigned* it; const uint64_t* p0; const uint64_t* p1; int mode;
+        __device__ ~RsPrint() { const long long dt = clock64() - *t0; if (mode == 2 && dt > 40000) printf("  resume: %lld cycles, %u iterations, bulk %lld (scan %lld), %llu bytes from %llu\n", dt, *it, *bulk, *scan, (unsigned long long)(*p1 - *p0), (unsigned long long)*p0); } } rs_print{&rs_t0, &rs_bulk, &rs_scan, &rs_iters, &rs_pos0, &pos, kMode};
+#endif
     for (;;) {
+#if defined(CFBPE_TILE_CLOCK) && !defined(CUSIM_EMULATOR)
+        ++rs_iters;
+#endif
+#ifdef CUSIM_EMULATOR
+        ++dbg_iters;
+        if (kMode == 2) CFBPE_DBG_COUNT(9);
+#endif
         uint32_t x, len, b0 = 0x100u;
         if (pos == pe) { x = X_EOT; len = 0; }
         else {
@@ -290,6 +341,9 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
             //      thread that entered such a run would otherwise walk it a character per iteration (~200 cycles each,
             //      nothing else to hide the latency) while the rest of the grid has long finished.  Only beyond the end of
             //      my chunk: inside it the walk is bounded anyway, and short runs (indentation, years) are cheaper per character
+#if defined(CFBPE_TILE_CLOCK) && !defined(CUSIM_EMULATOR)
+            const long long rs_b0 = clock64();
+#endif
             if (pos >= ce && b0 < 0x80u && pos < pe) {
                 if ((x == X_SPACE || x == X_CRLF || x == X_WS) && s[pos] == b0) {
                     const uint32_t a2 = tab[state * kRow + x];
@@ -306,20 +360,33 @@ __device__ __forceinline__ void split_thread(const BatchView& b, const VocabSet&
                     const uint32_t md = (tab[S_D1 * kRow + X_N] & A_B_NOW) ? 1u : ((tab[S_D2 * kRow + X_N] & A_B_NOW) ? 2u : 3u);
                     CFBPE_DBG_COUNT(4);
                     const uint64_t e = ascii_digit_run_end(s, pos, pe);
+#if defined(CFBPE_TILE_CLOCK) && !defined(CUSIM_EMULATOR)
+                    rs_scan += clock64() - rs_b0;
+#endif
                     const uint32_t d = state - S_D1 + 1u;                        // digits in the current piece so far
-                    {   // only beyond my chunk (pos >= ce): word-wise
-                        uint64_t cw = ~0ull; uint32_t cb = 0;
-                        for (uint64_t p = pos + (md - d); p < e; p += md) {
-                            const uint64_t w = p >> 5;
-                            if (w != cw) { if (cb) atomicOr(&piece_bits[cw], cb); cw = w; cb = 0; }
-                            cb |= 1u << (p & 31);
+                    {   // a boundary every md digits from `first` on: one flag word at a time (the pattern repeats: a loop over
+                        // the boundaries took 200 cycles each, 100 000 for a run of 1.4 KiB -- profiles/k1_tiles_r02.txt)
+                        const uint64_t first = pos + (md - d);
+                        const uint32_t pat_bits = md == 1u ? 0xFFFFFFFFu : (md == 2u ? 0x55555555u : 0x49249249u);
+                        if (first < e) {
+                            uint32_t off = static_cast<uint32_t>(first & 31u);          // first boundary of the word, as a bit index
+                            const uint32_t adv = 4u % md;                               // 36 = 0 (mod 1, 2, 3): the offset moves by (36 - 32) mod md a word
+                            for (uint64_t w = first >> 5; w <= (e - 1) >> 5; ++w) {
+                                const uint64_t w0 = w << 5;
+                                uint32_t m = pat_bits << off;
+                                if (e < w0 + 32u) m &= (1u << static_cast<uint32_t>(e - w0)) - 1u;
+                                if (m) atomicOr(&piece_bits[w], m);
+                                off = off % md + adv; if (off >= md) off -= md;
+                            }
                         }
-                        if (cb) atomicOr(&piece_bits[cw], cb);
                     }
                     state = S_D1 + static_cast<uint32_t>((d - 1u + (e - pos)) % md);
                     pos = e; prevx = X_N; nlet = 0; npun = 0;
                 }
             }
+#if defined(CFBPE_TILE_CLOCK) && !defined(CUSIM_EMULATOR)
+            rs_bulk += clock64() - rs_b0;
+#endif
         }
     }
     if (!kFix) {

@@ -52,6 +52,8 @@ static inline void prof_mark(ProfEvents* p, int idx, cudaStream_t s, bool begin)
 
 constexpr int kMaxPipeChunks = 64;
 constexpr int kSideStreams = 16;
+constexpr int kPrioLevels = 8, kPoolSlots = 9;
+constexpr int kTracePoints = 8;     // CFBPE_PIPE_TRACE: events per sub-batch
 #ifndef CFBPE_FRONT_STREAMS
 #define CFBPE_FRONT_STREAMS 6
 #endif
@@ -91,12 +93,14 @@ struct Lane {
     bool dev_want_ids = false;
     cudaEvent_t ev_scan[kMaxPipeChunks] = {};
     cudaStream_t front[kFrontStreams] = {};   // front streams 1.. of a pipelined host call (0 = stream)
+    cudaStream_t pool[kPrioLevels][kPoolSlots] = {};   // CFBPE_PIPE_PRIO=1|2 (experiment): streams by priority level
+    int prio_mode = 0, prio_levels = 1;
     cudaStream_t side[kSideStreams] = {};  // long-piece tails + emit of sub-batch k overlap the front of k+1
     cudaEvent_t ev_front[kMaxPipeChunks] = {};
     cudaEvent_t ev_h2d[kMaxPipeChunks] = {};
     cudaEvent_t ev_done[kMaxPipeChunks] = {};
     cudaEvent_t ev_chain[kMaxPipeChunks] = {};   // tile_scan of sub-batch k done: the next sub-batch's scan may read tok_end
-    cudaEvent_t (*trace)[6] = nullptr;           // CFBPE_PIPE_TRACE=1: timed events per sub-batch (h2d, split, short, long, back, d2h) + [nc][0] = start
+    cudaEvent_t (*trace)[kTracePoints] = nullptr;           // CFBPE_PIPE_TRACE=1: timed events per sub-batch (h2d, split, short, long, back, d2h) + [nc][0] = start
     DeviceStatus* d_status_arr = nullptr; // one status per sub-batch
     DeviceStatus* h_status_arr = nullptr; // pinned
     uint64_t* h_offs_stage = nullptr;     // pinned: sub-batch-local offsets
@@ -335,9 +339,10 @@ int run_host_pipelined(cfbpe_ctx* ctx, DeviceCtx* dv, Lane* ln, uint32_t n, cons
     }
     // ---- enqueue everything that does not depend on the host knowing a result
     const bool trace = getenv("CFBPE_PIPE_TRACE") != nullptr;
+    const bool no_copy = trace && getenv("CFBPE_PIPE_NO_COPY") != nullptr;   // measurement aid: the kernels of a pipelined call without its copies (the device buffers still hold the previous call's data)
     if (trace && !ln->trace) {
-        ln->trace = new cudaEvent_t[kMaxPipeChunks + 1][6];
-        for (int k = 0; k <= kMaxPipeChunks; ++k) for (int j = 0; j < 6; ++j) cudaEventCreate(&ln->trace[k][j]);
+        ln->trace = new cudaEvent_t[kMaxPipeChunks + 1][kTracePoints];
+        for (int k = 0; k <= kMaxPipeChunks; ++k) for (int j = 0; j < kTracePoints; ++j) cudaEventCreate(&ln->trace[k][j]);
     }
     if (trace) CK(cudaEventRecord(ln->trace[nc][0], hs));
     const auto host_t0 = std::chrono::steady_clock::now();
@@ -348,13 +353,15 @@ int run_host_pipelined(cfbpe_ctx* ctx, DeviceCtx* dv, Lane* ln, uint32_t n, cons
         const uint64_t o0 = offsets[p0], len = offsets[p1] - o0;
         // every sub-batch lands on a 16-byte boundary of the device buffer (K1 reads 16 bytes per lane with one load)
         uint8_t* const d_sub = ln->d_bytes + ((o0 + 15) & ~15ull) + 16ull * k;
-        if (len) CK(cudaMemcpyAsync(d_sub, bytes + o0, len, cudaMemcpyHostToDevice, hs));
+        if (len && !no_copy) CK(cudaMemcpyAsync(d_sub, bytes + o0, len, cudaMemcpyHostToDevice, hs));
         CK(cudaMemcpyAsync(ln->d_offsets + p0 + k, ln->h_offs_stage + p0 + k, (static_cast<uint64_t>(nk) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, hs));
         if (vocab_ids && nk) CK(cudaMemcpyAsync(ln->d_vocab_ids + p0, vocab_ids + p0, nk, cudaMemcpyHostToDevice, hs));
         CK(cudaEventRecord(ln->ev_h2d[k], hs));
         if (trace) CK(cudaEventRecord(ln->trace[k][0], hs));
         const int fk = k < kFrontStreams ? k : kFrontStreams - 1;
-        cudaStream_t ck = fk ? ln->front[fk] : cs;   // the short-piece kernels of sub-batch k: priority falls with k (earlier sub-batches finish, and download, first)
+        cudaStream_t ck = fk ? ln->front[fk] : cs;
+        const int lv = ln->prio_mode == 2 ? (k * ln->prio_levels) / nc : 0;
+        if (ln->prio_mode) ck = ln->pool[lv][(3 * k + 2) % kPoolSlots];   // the short-piece kernels of sub-batch k: priority falls with k (earlier sub-batches finish, and download, first)
         Workspace w = ln->ws;
         const uint64_t w0 = (o0 >> 5) + 4ull * k;
         w.piece_bits += w0; w.tok_bits += w0; w.pstart_bits += w0;
@@ -373,16 +380,17 @@ int run_host_pipelined(cfbpe_ctx* ctx, DeviceCtx* dv, Lane* ln, uint32_t n, cons
         BatchView b{d_sub, ln->d_offsets + p0 + k, vocab_ids ? ln->d_vocab_ids + p0 : nullptr, nk, len};
         // split, long pieces and the back stage run on a top-priority stream of their own: the long-piece kernels are a latency
         // chain that uses little of the machine, so they start as early as possible and the short-piece kernels fill the rest
-        cudaStream_t ss = ln->side[k % kSideStreams];
+        cudaStream_t ss = ln->prio_mode ? ln->pool[lv][(3 * k) % kPoolSlots] : ln->side[k % kSideStreams];
         CK(cudaStreamWaitEvent(ss, ln->ev_h2d[k], 0));
         enqueue_split(b, dv->vs, dv->uc, w, ss, static_cast<ProfEvents*>(nullptr));
         CK(cudaEventRecord(ln->ev_scan[k], ss));
         if (trace) CK(cudaEventRecord(ln->trace[k][1], ss));
         CK(cudaStreamWaitEvent(ck, ln->ev_scan[k], 0));
-        cudaStream_t ss2 = ln->side2[k % kSideStreams];
+        cudaStream_t ss2 = ln->prio_mode ? ln->pool[lv][(3 * k + 1) % kPoolSlots] : ln->side2[k % kSideStreams];
         CK(cudaStreamWaitEvent(ss2, ln->ev_scan[k], 0));
         enqueue_list(b, dv->vs, w, static_cast<uint32_t>(dv->sm_count * 4), ss2, static_cast<ProfEvents*>(nullptr));   // the big pieces, beside everything else
         CK(cudaEventRecord(ln->ev_list[k], ss2));
+        if (trace) CK(cudaEventRecord(ln->trace[k][6], ss2));
         enqueue_long(b, dv->vs, w, static_cast<uint32_t>(dv->sm_count * 4), ss, static_cast<ProfEvents*>(nullptr));   // tail overlaps what follows on cs
         if (trace) CK(cudaEventRecord(ln->trace[k][3], ss));
         enqueue_short(b, dv->vs, w, static_cast<uint32_t>(dv->sm_count * 4), ck, static_cast<ProfEvents*>(nullptr));
@@ -391,6 +399,7 @@ int run_host_pipelined(cfbpe_ctx* ctx, DeviceCtx* dv, Lane* ln, uint32_t n, cons
         CK(cudaStreamWaitEvent(ss, ln->ev_front[k], 0));
         CK(cudaStreamWaitEvent(ss, ln->ev_list[k], 0));
         enqueue_count(b, w, ss, static_cast<ProfEvents*>(nullptr));
+        if (trace) CK(cudaEventRecord(ln->trace[k][7], ss));
         if (k) CK(cudaStreamWaitEvent(ss, ln->ev_chain[k - 1], 0));    // token ranks chain through DeviceStatus::tok_end: only the scan waits
         enqueue_scan(b, w, ss, static_cast<ProfEvents*>(nullptr), k ? &ln->d_status_arr[k - 1].tok_end : nullptr);
         CK(cudaEventRecord(ln->ev_chain[k], ss));
@@ -414,6 +423,7 @@ int run_host_pipelined(cfbpe_ctx* ctx, DeviceCtx* dv, Lane* ln, uint32_t n, cons
         const uint64_t base = st.tok_end - st.n_tokens;
         tok_total = st.tok_end;
         if (err || defer) continue;
+        if (no_copy) continue;
         if (want_ids && st.tok_end <= out_cap && st.n_tokens)
             CK(cudaMemcpyAsync(out_ids + base, ln->d_out_ids + base, st.n_tokens * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds));
         if (out_offsets) CK(cudaMemcpyAsync(out_offsets + p0, ln->d_out_offsets + p0 + k, (static_cast<uint64_t>(nk) + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ds));
@@ -425,13 +435,14 @@ int run_host_pipelined(cfbpe_ctx* ctx, DeviceCtx* dv, Lane* ln, uint32_t n, cons
     for (int k = 1; k < kFrontStreams; ++k) CK(cudaStreamSynchronize(ln->front[k]));
     for (int k = 0; k < kSideStreams; ++k) CK(cudaStreamSynchronize(ln->side[k]));
     for (int k = 0; k < kSideStreams; ++k) CK(cudaStreamSynchronize(ln->side2[k]));
+    if (ln->prio_mode) for (int l = 0; l < kPrioLevels; ++l) for (int j = 0; j < kPoolSlots; ++j) if (ln->pool[l][j]) CK(cudaStreamSynchronize(ln->pool[l][j]));
     if (trace && !err) {
-        fprintf(stderr, "pipe trace (ms since the first upload was enqueued): sub-batch bytes | h2d split short long_end back d2h\n");
+        fprintf(stderr, "pipe trace (ms since the first upload was enqueued): sub-batch bytes | h2d split long_end list_end short count back d2h\n");
         for (int k = 0; k < nc; ++k) {
-            float t[6];
-            for (int j = 0; j < 6; ++j) cudaEventElapsedTime(&t[j], ln->trace[nc][0], ln->trace[k][j]);
-            fprintf(stderr, "  %2d %9llu | %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f | host: enqueued %.2f download issued %.2f\n", k,
-                    static_cast<unsigned long long>(offsets[cut[k + 1]] - offsets[cut[k]]), t[0], t[1], t[2], t[3], t[4], t[5], host_enq[k], host_dl[k]);
+            float t[kTracePoints] = {};
+            for (int j = 0; j < kTracePoints; ++j) if (!(no_copy && j == 5)) cudaEventElapsedTime(&t[j], ln->trace[nc][0], ln->trace[k][j]);
+            fprintf(stderr, "  %2d %9llu | %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f | host: enqueued %.2f download issued %.2f\n", k,
+                    static_cast<unsigned long long>(offsets[cut[k + 1]] - offsets[cut[k]]), t[0], t[1], t[3], t[6], t[2], t[7], t[4], t[5], host_enq[k], host_dl[k]);
         }
     }
     if (err) return err;
@@ -633,6 +644,7 @@ void destroy_lane(Lane* ln) {
         if (ln->ev_scan[k]) cudaEventDestroy(ln->ev_scan[k]); if (ln->ev_list[k]) cudaEventDestroy(ln->ev_list[k]);
     }
     for (int k = 1; k < kFrontStreams; ++k) if (ln->front[k]) cudaStreamDestroy(ln->front[k]);
+    for (int l = 0; l < kPrioLevels; ++l) for (int j = 0; j < kPoolSlots; ++j) if (ln->pool[l][j]) cudaStreamDestroy(ln->pool[l][j]);
     for (int k = 0; k < kSideStreams; ++k) { if (ln->side[k]) cudaStreamDestroy(ln->side[k]); if (ln->side2[k]) cudaStreamDestroy(ln->side2[k]); }
     if (ln->aux_stream) cudaStreamDestroy(ln->aux_stream);
     if (ln->aux2_stream) cudaStreamDestroy(ln->aux2_stream);
@@ -709,6 +721,12 @@ bool create_lane(Lane* ln, int device, uint64_t mb, uint64_t mp) {
             ok = cudaStreamCreateWithPriority(&ln->front[k], cudaStreamNonBlocking, prio_hi + (k < levels ? k : levels - 1)) == cudaSuccess;
         for (int k = 0; ok && k < kSideStreams; ++k) ok = cudaStreamCreateWithPriority(&ln->side[k], cudaStreamNonBlocking, prio_hi) == cudaSuccess;
         for (int k = 0; ok && k < kSideStreams; ++k) ok = cudaStreamCreateWithPriority(&ln->side2[k], cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        if (const char* e = std::getenv("CFBPE_PIPE_PRIO")) {      // experiment: 1 = every kernel at one priority, 2 = priority by the sub-batch's age
+            ln->prio_mode = std::atoi(e);
+            ln->prio_levels = ln->prio_mode == 2 ? (levels < kPrioLevels ? levels : kPrioLevels) : 1;
+            for (int l = 0; ok && ln->prio_mode && l < ln->prio_levels; ++l)
+                for (int j = 0; ok && j < kPoolSlots; ++j) ok = cudaStreamCreateWithPriority(&ln->pool[l][j], cudaStreamNonBlocking, prio_hi + l) == cudaSuccess;
+        }
     }
     // the long-piece kernels are latency-bound and small: their CTAs go first, the short-piece kernels fill the rest
     // (A/B of lower priorities and of CTA caps: no gain, profiles/ab_bench_r02h.txt)

@@ -142,6 +142,7 @@ struct SplitEnv {
     DeviceStatus* status; SplitFix* fix_list;
     uint64_t total; uint32_t fix_cap, pats, n_tabs;
     const uint16_t* fsm; const uint16_t* ctx; const ProdInfo* info; const uint8_t* skip; const uint8_t* start; const uint8_t* tabs;
+    const uint8_t* cls; uint32_t* piece_bits;
 };
 
 // The rare actions of a step: an undecided state that has to be resolved (the fix-up kernel goes on from here: the walker
@@ -212,6 +213,53 @@ __device__ __noinline__ uint4 split_prompt_group(const SplitEnv* env, uint32_t w
     return make_uint4(st, marks, rem, pat);
 }
 
+// A walker that crossed its whole 32-byte window (every second tile has one: sixteen spaces of indentation, a nine-digit number) and
+// needs, on average, three or four characters more.  It goes on with the product automaton over the next blocks of 16 bytes, loaded
+// here -- ASCII only, no prompt start inside: anything else is left to the per-character walker, whose set-up alone (prompt
+// search, the classes of the last three characters from memory) costs ~10 000 cycles (profiles/k1_tiles_r02.txt).
+// Marks at window positions >= 32 go to the flag words directly.  Returns {state row, marks at window positions < 32,
+// remembered positions, blocks done}; state row != 0: the per-character walker goes on at base + 32 + 16 * blocks.
+constexpr uint32_t kSplitExtBlocks = 8;      // window positions stay below 160 (the remembered positions are bytes)
+__device__ __noinline__ uint4 split_extend(const SplitEnv* env, uint32_t st, uint32_t rem, uint32_t pat, uint64_t base) {
+    const uint8_t* tab = env->tabs + (env->n_tabs == 1 ? 0u : pat) * kProdTableBytes;
+    uint32_t marks_lo = 0, blocks = 0;
+    while (st != 0u && blocks < kSplitExtBlocks) {
+        const uint64_t p0 = base + 32u + 16u * blocks;
+        if (p0 + 16u > env->total) break;
+        uint32_t ww[4];
+        load16(env->s + p0, ww[0], ww[1], ww[2], ww[3]);
+        if ((ww[0] | ww[1] | ww[2] | ww[3]) & 0x80808080u) break;                                  // a character of several bytes
+        if ((env->pstart_bits[p0 >> 5] >> (p0 & 31u)) & 0xFFFFu) break;                            // a prompt starts in these 16 bytes
+        uint32_t out = 0;                                                                          // marks of this block (bit = byte in it) ...
+        auto mark_at = [&](uint32_t k) {                                                           // ... and at remembered positions (anywhere before)
+            if (k < 32u) marks_lo |= 1u << k;
+            else if (k >= 32u + 16u * blocks) out |= 1u << (k - 32u - 16u * blocks);
+            else atomicOr(&env->piece_bits[(base + k) >> 5], 1u << ((base + k) & 31u));
+        };
+#pragma unroll 1
+        for (uint32_t i = 0; i < 16u && st != 0u; ++i) {
+            const uint32_t k = 32u + 16u * blocks + i;
+            const uint32_t cb = env->cls[(ww[i >> 2] >> (8u * (i & 3u))) & 0xFFu];
+            const uint2 e = *reinterpret_cast<const uint2*>(tab + st + ((cb & 15u) << 3));
+            uint32_t lo = e.x, hi = e.y;
+            if (lo & (PE_EMIT_ANY | PE_RARE)) {
+                if (lo & PE_EMIT_ALC) mark_at(rem & 0xFFu);
+                if (lo & PE_EMIT_LAST) mark_at((rem >> 8) & 0xFFu);
+                if (lo & PE_EMIT_LBE) mark_at((rem >> 16) & 0xFFu);
+                if (lo & PE_RARE) { lo = split_rare(env, lo, st, cb, k, pat, base); if (lo == 0u) hi = 0u; }
+            }
+            if (lo & PE_SYNC) { lo = 0u; hi = 0u; }           // the owner of this block started exactly here
+            if (lo & PE_B_NOW) out |= 1u << i;
+            const uint32_t kk = k * 0x010101u + 0x010001u;     // (ASCII: every character is one byte)
+            rem = (rem & ~hi) | (kk & hi);
+            st = lo & PE_NEXT_MASK;
+        }
+        if (out) atomicOr(&env->piece_bits[p0 >> 5], out << (p0 & 31u));
+        ++blocks;
+    }
+    return make_uint4(st, marks_lo, rem, blocks);
+}
+
 // the per-character walker of the first form, out of line (it is large, and rare: long runs without a sync point)
 __device__ __noinline__ void split_resume(const BatchView b, uint32_t pats, const UcTables uc, const uint16_t* s_fsm, const uint8_t* s_cls,
                                          uint32_t* __restrict__ piece_bits, DeviceStatus* status, SplitFix* fix_list, uint32_t fix_cap,
@@ -233,6 +281,9 @@ constexpr uint32_t kSplitWarpOwned = 30;            // blocks of 16 bytes a WARP
 // n_tabs: product tables in shared memory -- 1 (single-vocabulary batch: the table of pattern pat0) or kNumPatterns
 #ifndef CFBPE_SPLIT_CTAS
 #define CFBPE_SPLIT_CTAS 4
+#endif
+#ifndef CFBPE_SPLIT_TICKETS
+#define CFBPE_SPLIT_TICKETS 1      // 1: warps draw tiles from a counter; 0: fixed stride (A/B: profiles/ab_variants_r02u.txt, 0.846 -> 0.787 ms)
 #endif
 #ifndef CFBPE_SPLIT_UNROLL
 #define CFBPE_SPLIT_UNROLL 1       // copies of the step in the hot loop (1 | 2 | 4); measured: profiles/ab_variants_r02g.txt
@@ -291,6 +342,7 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
         e.s = b.bytes; e.pstart_bits = pstart_bits; e.block_prompt = block_prompt; e.offsets = b.offsets; e.vocab_ids = b.vocab_ids;
         e.status = status; e.fix_list = fix_list; e.total = b.total_bytes; e.fix_cap = fix_cap; e.pats = pats; e.n_tabs = n_tabs;
         e.fsm = s_fsm; e.ctx = s_ctx; e.info = s_info; e.skip = s_skip; e.start = s_start; e.tabs = reinterpret_cast<const uint8_t*>(s_dyn);
+        e.cls = s_cls; e.piece_bits = piece_bits;
         s_env = e;
     }
     __syncthreads();
@@ -298,10 +350,30 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
     const uint64_t total = b.total_bytes;
     const bool aligned = (reinterpret_cast<uintptr_t>(s) & 15u) == 0u;
     const uint8_t* const tabs = reinterpret_cast<const uint8_t*>(s_dyn);
-    const uint32_t warps_total = gridDim.x * (kSplitCta / 32u);
 
+    // tiles by ticket (CFBPE_SPLIT_TICKETS, A/B) or by stride: a tile that enters a long run (the per-character walker, one lane)
+    // costs ten average tiles.  The next ticket is drawn while the current tile is worked on.
+#if CFBPE_SPLIT_TICKETS
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(&status->split_next, 1u);
+    tile = __shfl_sync(kFull, tile, 0);
+#else
+    const uint32_t warps_total = gridDim.x * (kSplitCta / 32u);
+    uint32_t tile = blockIdx.x * (kSplitCta / 32u) + (t >> 5);
+#endif
 #pragma unroll 1
-    for (uint32_t tile = blockIdx.x * (kSplitCta / 32u) + (t >> 5); tile < n_tiles; tile += warps_total) {
+    while (tile < n_tiles) {
+#if CFBPE_SPLIT_TICKETS
+        uint32_t next_tile = 0;
+        if (lane == 0) next_tile = atomicAdd(&status->split_next, 1u);
+#else
+        const uint32_t next_tile = tile + warps_total;
+#endif
+        CFBPE_DBG_COUNT(10);
+#if defined(CFBPE_TILE_CLOCK) && !defined(CUSIM_EMULATOR)
+        const long long tile_t0 = clock64();         // measurement build: which tiles take long (printf from the device)
+        const uint32_t tile_dbg = tile;
+#endif
         const int64_t blk = static_cast<int64_t>(tile) * kSplitWarpOwned + static_cast<int64_t>(lane) - 1;
         const uint64_t base = blk > 0 ? static_cast<uint64_t>(blk) * 16u : 0u;
         const bool have = blk >= 0 && base < total;
@@ -371,6 +443,9 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
                 for (uint32_t k = 4; k < 16; ++k) ctx_step(k);
             }
         }
+#if defined(CFBPE_TILE_CLOCK) && !defined(CUSIM_EMULATOR)
+        __syncwarp(); const long long tile_t1 = clock64();
+#endif
         // ---- neighbours: the class bytes of the block to my right, the context at the end of the block to my left
         const uint32_t left_ctx = __shfl_up_sync(kFull, endc, 1);
         uint32_t w0 = cw[0], w1 = cw[1], w2 = cw[2], w3 = cw[3];
@@ -429,10 +504,18 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
                 mine |= gm << kb;
             }
         }
+#if defined(CFBPE_TILE_CLOCK) && !defined(CUSIM_EMULATOR)
+        __syncwarp(); const long long tile_t2 = clock64(); const uint32_t n_resume = __popc(__ballot_sync(kFull, st != 0u));
+#endif
         // ---- a walker that crossed the whole next block: the per-character walker goes on from its state
+        uint32_t ext_blocks = 0;
+        if (st != 0u) {         // a few characters more, mostly: go on with the product automaton (split_extend)
+            const uint4 r = split_extend(&s_env, st, rem, pat, base);
+            st = r.x; mine |= r.y; rem = r.z; ext_blocks = r.w;
+        }
         if (st != 0u) {
             const ProdInfo pi = s_info[pat * kProdMax + (st >> PE_NEXT_SHIFT)];
-            uint64_t pos = base + 32u;
+            uint64_t pos = base + 32u + 16u * ext_blocks;
             while (pos < total && (s[pos] & 0xC0u) == 0x80u) ++pos;          // byte 32 may lie inside the character that began at byte 29..31
             uint32_t q = pi.q;
             if (q == PQ_SKIP1 || q == PQ_SKIP2) {                            // inside a contraction: step over what is left of it
@@ -443,6 +526,9 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
                          q, base + (rem & 0xFFu), base + ((rem >> 8) & 0xFFu), base + ((rem >> 16) & 0xFFu));
         }
 
+#if defined(CFBPE_TILE_CLOCK) && !defined(CUSIM_EMULATOR)
+        __syncwarp(); const long long tile_t3 = clock64();
+#endif
         // ---- flags out: my 16 bits + what the lane to my left marked in my block; two lanes share a 32-bit word
         //      (30 blocks a warp: odd lanes hold even blocks)
         uint32_t v = mine & 0xFFFFu;
@@ -458,6 +544,15 @@ pretok_split16_kernel(BatchView b, VocabSet vs, UcTables uc, const uint32_t* __r
             } else if (lane == 0u) {    // the ghost to the left owns nothing here
             }
         }
+#if CFBPE_SPLIT_TICKETS
+        tile = __shfl_sync(kFull, next_tile, 0);
+#else
+        tile = next_tile;
+#endif
+#if defined(CFBPE_TILE_CLOCK) && !defined(CUSIM_EMULATOR)
+        __syncwarp();
+        { const long long dt = clock64() - tile_t0; if (lane == 0 && dt > CFBPE_TILE_CLOCK) printf("slow tile %u: %lld cycles (classify %lld walk %lld resume %lld [%u lanes] out %lld)\n", tile_dbg, dt, tile_t1 - tile_t0, tile_t2 - tile_t1, tile_t3 - tile_t2, n_resume, clock64() - tile_t3); }
+#endif
     }   // tiles
 }
 

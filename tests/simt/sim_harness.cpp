@@ -60,8 +60,8 @@ __attribute__((visibility("default"))) void* sim_vocab_build(const uint8_t* file
 }
 __attribute__((visibility("default"))) unsigned long long sim_dbg_counter(uint32_t i, int reset) {
     unsigned long long* c = cfbpe::dbg_counters();
-    const unsigned long long v = c[i & 7];
-    if (reset) c[i & 7] = 0;
+    const unsigned long long v = c[i & 15];
+    if (reset) c[i & 15] = 0;
     return v;
 }
 __attribute__((visibility("default"))) void sim_vocab_free(void* v) { delete static_cast<SimVocab*>(v); }

@@ -18,8 +18,9 @@ hb = c.pinned(total + 64, np.uint8); hb.array[:total] = data
 ho = c.pinned(n + 1, np.uint64); ho.array[:] = offs
 hi = c.pinned(total + 1, np.uint32); hoo = c.pinned(n + 1, np.uint64); hc = c.pinned(n, np.uint32)
 import time
-for it in range(4):
+for it in range(6):
     if it == 3: os.environ["CFBPE_PIPE_TRACE"] = "1"
+    if it == 4: os.environ["CFBPE_PIPE_NO_COPY"] = "1"; print("-- the same call without its copies (kernels only):", flush=True)
     t0 = time.perf_counter()
     c.encode_batch(hb.array[:total], ho.array, None, hi.array, hoo.array, hc.array)
     print("call %d: %.2f ms" % (it, (time.perf_counter() - t0) * 1e3), flush=True)
