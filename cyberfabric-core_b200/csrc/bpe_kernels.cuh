@@ -491,6 +491,16 @@ __device__ __forceinline__ void load16(const uint8_t* __restrict__ p, uint32_t& 
 // CoreBPE's `if piece in ranks` for a piece of 1..32 bytes at p
 __device__ __forceinline__ uint32_t whole_piece_lookup(const TablesView& T, const uint8_t* __restrict__ p, uint32_t len) {
     if (len > T.max_token_len) return kNone;
+    if (len <= 4) {       // half of all pieces: two aligned words instead of five, and a two-byte piece is a direct table index
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(addr & ~static_cast<uintptr_t>(3));
+        const uint32_t sh = static_cast<uint32_t>(addr & 3) * 8;
+        uint32_t w = q[0];
+        if (sh + 8 * len > 32) w = __funnelshift_r(w, q[1], sh); else w >>= sh;
+        if (len == 2) return T.bytepair[((w & 0xFFu) << 8) | ((w >> 8) & 0xFFu)];
+        if (len < 4) w &= (1u << (8 * len)) - 1u;
+        return short_lookup(T, w, 0u, len);
+    }
     uint32_t w0, w1, w2, w3;
     load16(p, w0, w1, w2, w3);
     uint64_t k0 = static_cast<uint64_t>(w0) | (static_cast<uint64_t>(w1) << 32);
@@ -504,9 +514,8 @@ __device__ __forceinline__ uint32_t whole_piece_lookup(const TablesView& T, cons
 // the exact merge loop on one piece of 2..32 bytes.  Part k = the part that STARTS at byte k of the piece; `alive` has
 // one bit per live part, so a merge clears a bit instead of shifting arrays.  Shared-memory columns (stride 32 words):
 //   sid[k*32] = id of part k      srk[k*32] = rank of (part k, next live part)
-// hot: the hot slice of the pair table in shared memory (CFBPE_MERGE_HOT build), or nullptr
 __device__ __forceinline__ uint32_t merge_piece_in_lane(const TablesView& T, const uint8_t* __restrict__ text, uint64_t pos, uint32_t len,
-                                                        uint32_t* sid, uint32_t* srk, uint32_t* __restrict__ tok_bits, const uint64_t* hot = nullptr) {
+                                                        uint32_t* sid, uint32_t* srk, uint32_t* __restrict__ tok_bits) {
     const uint8_t* __restrict__ p = text + pos;
     // the piece's bytes (<= 32) in eight registers; parts = bytes, ranks from the raw byte-pair table, four loads in flight
     uint32_t w[8];
@@ -549,12 +558,6 @@ __device__ __forceinline__ uint32_t merge_piece_in_lane(const TablesView& T, con
         const uint32_t nn = wr ? static_cast<uint32_t>(__ffs(above2)) - 1u : 0u;
         const uint32_t pv = wl ? 31u - static_cast<uint32_t>(__clz(below)) : 0u;
         uint32_t nr, nl;
-        if (hot) {      // shared memory first: a hit there saves the trip to L2 (a miss there says nothing)
-            const uint32_t rid = wr ? sid[nn * 32] : 0u, lid = wl ? sid[pv * 32] : 0u;
-            const uint32_t hr = wr ? hot_lookup(hot, best, rid) : kNone, hl = wl ? hot_lookup(hot, lid, best) : kNone;
-            pair_lookup2(T, best, rid, wr && hr == kNone, lid, best, wl && hl == kNone, nr, nl);
-            nr = hr != kNone ? hr : nr; nl = hl != kNone ? hl : nl;
-        } else
         pair_lookup2(T, best, wr ? sid[nn * 32] : 0u, wr, wl ? sid[pv * 32] : 0u, best, wl, nr, nl);
         srk[bi * 32] = nr == kNone ? kNone : ((nr << 5) | bi);
         if (wl) srk[pv * 32] = nl == kNone ? kNone : ((nl << 5) | pv);
@@ -663,17 +666,14 @@ long_scan_kernel(BatchView b, const uint32_t* __restrict__ piece_bits, LongPiece
 constexpr uint32_t kLookupWarps = 4;
 static_assert(kLookupWarps == kPieceWarps, "K2a's CTA is the 2 KiB tile K2s counted");
 __global__ void __launch_bounds__(kLookupWarps * 32)
-bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits, DenseIds dn,
-                  uint32_t* __restrict__ tok_bits, MissLists ml, DeviceStatus* status) {
+bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits, DenseIds dn, MissLists ml, DeviceStatus* status) {
     __shared__ uint16_t s_pos[kLookupWarps][kPieceRange + 2];
-    __shared__ uint32_t s_flags[kLookupWarps][kPieceRange / 32];
     __shared__ uint64_t s_miss0[kLookupWarps * kPieceRange / 13 + 8];
     __shared__ uint64_t s_miss1[kLookupWarps * kPieceRange / 7 + 8];
     __shared__ uint64_t s_miss2[kLookupWarps * kPieceRange / 2 + 8];
     __shared__ uint32_t s_cnt[3], s_base[3], s_nw[kLookupWarps];
     const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
-    if (lane < kPieceRange / 32) s_flags[wic][lane] = 0;
     const uint64_t warp = static_cast<uint64_t>(blockIdx.x) * kLookupWarps + wic;
     const uint64_t r0 = warp * kPieceRange;
     const uint8_t* __restrict__ text = b.bytes;
@@ -716,18 +716,12 @@ bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
             }
             const uint32_t tok = (len == 1) ? T.byte2id[text[pos]] : whole_piece_lookup(T, text + pos, len);   // a byte is a token
             if (tok != kNone) {
-                dn.by_piece[rank0 + i] = tok;
-                atomicOr(&s_flags[wic][off >> 5], 1u << (off & 31));
+                dn.by_piece[rank0 + i] = tok;          // (its token flag is its piece flag: flag_count_kernel ORs the piece flags in)
             } else {
                 const uint32_t c = len >= 13 ? 0u : (len >= 7 ? 1u : 2u);
                 const uint32_t k = atomicAdd(&s_cnt[c], 1u);
                 (c == 0 ? s_miss0 : (c == 1 ? s_miss1 : s_miss2))[k] = pos | ((rank0 + i) << 32);
             }
-        }
-        __syncwarp();
-        if (lane < kPieceRange / 32) {
-            const uint32_t f = s_flags[wic][lane];
-            if (f) atomicOr(&tok_bits[(r0 >> 5) + lane], f);
         }
     }
     __syncthreads();
@@ -747,38 +741,25 @@ bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
     }
 }
 
-#ifndef CFBPE_MERGE_HOT
-#define CFBPE_MERGE_HOT 0      // A/B: 1 = probe a TMA-staged shared-memory slice of the pair table before the L2-resident table
-#endif
 __global__ void __launch_bounds__(kPieceWarps * 32)
 bpe_merge_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits, DenseIds dn,
-                 uint32_t* __restrict__ tok_bits, MissLists ml, DeviceStatus* status) {
-    __shared__ uint32_t s_id[kPieceWarps][32][32];   // [warp][part][lane]
-    __shared__ uint32_t s_rk[kPieceWarps][32][32];
+                 uint32_t* __restrict__ tok_bits, MissLists ml, DeviceStatus* status, uint32_t c_lo, uint32_t c_hi, uint32_t max_parts) {
+    // ids and pair ranks of the parts, [warp][part][lane]: 8 bytes a part and lane.  The CTA's shared memory is sized by the
+    // longest piece of the classes it serves (max_parts): 32 KB for the class of 13..32 bytes, 12 KB for the two classes of
+    // 2..12 bytes, which hold most of the misses -- eight CTAs a SM instead of six (the kernel waits on L2 round trips)
+    CFBPE_DYN_SMEM(s_parts);
     const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const uint8_t* __restrict__ text = b.bytes;
     const bool multi = b.vocab_ids != nullptr;
-    uint32_t* sid = &s_id[wic][0][lane];
-    uint32_t* srk = &s_rk[wic][0][lane];
+    uint32_t* sid = s_parts + (wic * 2u) * max_parts * 32u + lane;
+    uint32_t* srk = s_parts + (wic * 2u + 1u) * max_parts * 32u + lane;
     if (status->miss_overflow) return;
     TablesView T = vs.v[0];
     uint32_t vid = 0;
-    const uint64_t* hot = nullptr;
-#if CFBPE_MERGE_HOT && !defined(CUSIM_EMULATOR)
-    // A/B build: the hot slice of vocabulary 0's pair table (merged id < kHotRanks, 16 KB) staged into shared memory by ONE TMA
-    // bulk copy; single-vocabulary batches only
-    CFBPE_DYN_SMEM(s_hot);
-    __shared__ __align__(8) uint64_t s_bar;
-    if (!multi && T.hot) {
-        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-        __syncthreads();
-        if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, kHotCap * 8u); bulk_g2s(s_hot, T.hot, kHotCap * 8u, &s_bar); }
-        mbar_wait(&s_bar, 0);
-        hot = reinterpret_cast<const uint64_t*>(s_hot);
-    }
-#endif
+    // (a TMA-staged hot slice of the pair table, probed before the L2-resident table, made this kernel 2x slower:
+    //  profiles/ab_variants_r02k.txt)
 #pragma unroll 1
-    for (uint32_t c = 0; c < 3; ++c) {     // longest class first
+    for (uint32_t c = c_lo; c <= c_hi; ++c) {     // longest class first
         const uint32_t n = status->miss_n[c];
         const uint64_t* __restrict__ list = ml.list[c];
         for (;;) {
@@ -797,7 +778,7 @@ bpe_merge_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bi
                     const uint32_t pv = b.vocab_ids[find_prompt(b.offsets, b.n_prompts, pos)];
                     if (pv != vid) { vid = pv; T = vs.v[vid]; }
                 }
-                alive = merge_piece_in_lane(T, text, pos, static_cast<uint32_t>(end - pos), sid, srk, tok_bits, hot);
+                alive = merge_piece_in_lane(T, text, pos, static_cast<uint32_t>(end - pos), sid, srk, tok_bits);
             }
             // the warp's tokens go to one contiguous stretch of `extras` (one atomic per 32 pieces); the piece's word names its slot
             const uint32_t cnt = __popc(alive);
@@ -1530,13 +1511,16 @@ __device__ __forceinline__ uint32_t block_reduce_add_256(uint32_t v, uint32_t* s
 }
 
 __global__ void __launch_bounds__(256)
-flag_count_kernel(const uint32_t* __restrict__ tok_bits, uint64_t n_words, uint32_t* __restrict__ tile_counts) {
+flag_count_kernel(uint32_t* __restrict__ tok_bits, const uint32_t* __restrict__ piece_bits, uint64_t n_words, uint32_t* __restrict__ tile_counts) {
+    // Every piece starts with a token: the piece flags are token flags.  The K2 kernels only flag the tokens INSIDE pieces (the
+    // merged short ones, the long ones); the piece flags are ORed in here, once, word by word -- K2a used to set them one
+    // atomic a piece.  All K2 kernels of the (sub-)batch are done: plain stores.
     __shared__ uint32_t s_tmp[8];
     const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanTileWords;
     uint32_t c = 0;
     for (uint32_t i = threadIdx.x; i < kScanTileWords; i += blockDim.x) {
         const uint64_t w = base + i;
-        if (w < n_words) c += __popc(tok_bits[w]);
+        if (w < n_words) { const uint32_t t = tok_bits[w], f = t | piece_bits[w]; if (f != t) tok_bits[w] = f; c += __popc(f); }
     }
     const uint32_t t = block_reduce_add_256(c, s_tmp);
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = t;

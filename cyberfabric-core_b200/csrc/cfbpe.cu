@@ -118,7 +118,7 @@ struct Lane {
     ProfEvents prof{};
 };
 
-struct DeviceVocab { uint8_t* d_blob = nullptr; uint64_t* d_hot = nullptr; };   // (d_hot: the hot slice of the pair table, tables.h kHotRanks / kHotCap)
+struct DeviceVocab { uint8_t* d_blob = nullptr; };
 
 struct DeviceCtx {
     int device = 0;
@@ -219,42 +219,22 @@ int validate_batch(cfbpe_ctx* ctx, uint32_t n, const uint64_t* offsets, const ui
     return CFBPE_OK;
 }
 
-// the hot slice of a blob's pair table (tables.h): the entries with a low merged id, re-hashed into a table small enough for shared memory
-std::vector<uint64_t> build_hot_slice(const std::vector<uint8_t>& blob) {
-    TablesHeader h;
-    std::memcpy(&h, blob.data(), sizeof h);
-    const uint64_t* pairs = reinterpret_cast<const uint64_t*>(blob.data() + h.off_pair);
-    std::vector<uint64_t> hot(kHotCap, kPairEmpty);
-    uint32_t n_hot = 0;
-    for (uint32_t i = 0; i < h.cap_pair; ++i) {
-        const uint64_t sl = pairs[i];
-        if (sl == kPairEmpty || (static_cast<uint32_t>(sl) & kIdMask) >= kHotRanks || n_hot >= kHotCap * 3 / 4) continue;
-        uint32_t hh = pair_hash(static_cast<uint32_t>(sl >> (2 * kIdBits)), static_cast<uint32_t>(sl >> kIdBits) & kIdMask) & (kHotCap - 1);
-        while (hot[hh] != kPairEmpty) hh = (hh + 1) & (kHotCap - 1);
-        hot[hh] = sl; ++n_hot;
-    }
-    return hot;
-}
-
 // Install a packed table blob as vocabulary vocab_id on EVERY device of the context (caller holds vocab_mu exclusively).
 // Device 0 gets it from the host; with several devices the others get it from device 0 by ncclBroadcast over NVLink -- the rank
 // file was parsed once, the tables crossed PCIe once.
 int install_blob(cfbpe_ctx* ctx, uint32_t vocab_id, std::vector<uint8_t>&& blob) {
-    const std::vector<uint64_t> hot = build_hot_slice(blob);
     const size_t G = ctx->devs.size();
     std::vector<uint8_t*> nb(G, nullptr);
-    std::vector<uint64_t*> nh(G, nullptr);
-    auto cleanup = [&]() { for (size_t d = 0; d < G; ++d) { cudaSetDevice(ctx->devs[d]->device); cudaFree(nb[d]); cudaFree(nh[d]); } };
+    auto cleanup = [&]() { for (size_t d = 0; d < G; ++d) { cudaSetDevice(ctx->devs[d]->device); cudaFree(nb[d]); } };
     for (size_t d = 0; d < G; ++d) {
         cudaSetDevice(ctx->devs[d]->device);
-        if (cudaMalloc(reinterpret_cast<void**>(&nb[d]), blob.size()) != cudaSuccess || cudaMalloc(reinterpret_cast<void**>(&nh[d]), kHotCap * sizeof(uint64_t)) != cudaSuccess) {
+        if (cudaMalloc(reinterpret_cast<void**>(&nb[d]), blob.size()) != cudaSuccess) {
             cleanup(); cudaGetLastError();
             return fail(ctx, CFBPE_ENOMEM, "no device memory for the vocabulary tables");
         }
     }
     cudaSetDevice(ctx->devs[0]->device);
     cudaError_t e = cudaMemcpy(nb[0], blob.data(), blob.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(nh[0], hot.data(), kHotCap * sizeof(uint64_t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cleanup(); return fail(ctx, CFBPE_EIO, std::string("table upload: ") + cudaGetErrorString(e)); }
     if (G > 1) {
         const NcclApi& nc = ctx->nccl;
@@ -263,7 +243,6 @@ int install_blob(cfbpe_ctx* ctx, uint32_t vocab_id, std::vector<uint8_t>&& blob)
             cudaSetDevice(ctx->devs[d]->device);
             cudaStream_t st = ctx->devs[d]->lanes[0]->stream;
             rc = nc.Broadcast(nb[0], nb[d], blob.size(), kNcclChar, 0, ctx->devs[d]->comm, st);
-            if (rc == 0) rc = nc.Broadcast(nh[0], nh[d], kHotCap * sizeof(uint64_t), kNcclChar, 0, ctx->devs[d]->comm, st);
         }
         const int rc2 = nc.GroupEnd();
         if (rc == 0) rc = rc2;
@@ -279,10 +258,9 @@ int install_blob(cfbpe_ctx* ctx, uint32_t vocab_id, std::vector<uint8_t>&& blob)
         DeviceCtx* dv = ctx->devs[d].get();
         cudaSetDevice(dv->device);
         DeviceVocab& v = dv->vocabs[vocab_id];
-        if (v.d_blob) { cudaDeviceSynchronize(); cudaFree(v.d_blob); cudaFree(v.d_hot); }   // kernels of a device-path call on any stream may still read the old tables
-        v.d_blob = nb[d]; v.d_hot = nh[d];
+        if (v.d_blob) { cudaDeviceSynchronize(); cudaFree(v.d_blob); }   // kernels of a device-path call on any stream may still read the old tables
+        v.d_blob = nb[d];
         dv->vs.v[vocab_id] = make_view(v.d_blob, hv.hdr);
-        dv->vs.v[vocab_id].hot = v.d_hot;
         dv->vs.loaded_mask = ctx->loaded_mask;
         // slots that are not loaded alias a loaded one: a bad vocabulary id handed in by a device-path caller is reported
         // (DeviceStatus::bad_vocab -> CFBPE_ENOENT) instead of dereferencing a null table
@@ -758,7 +736,7 @@ bool create_device(DeviceCtx* dv, int device, int index, uint32_t n_lanes, uint6
     if (cudaSetDevice(device) != cudaSuccess) return false;
     dv->sm_count = prop.multiProcessorCount;
     bool ok = cudaFuncSetAttribute(bpe_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kListSmemBytes)) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(bpe_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHotCap * 8)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(bpe_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(pretok_split16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kNumPatterns * kProdTableBytes)) == cudaSuccess;
     ok = ok && dmalloc(&dv->d_uc1, sizeof cfbpe_uc_stage1) == cudaSuccess;
     ok = ok && dmalloc(&dv->d_uc2, sizeof cfbpe_uc_stage2) == cudaSuccess;
@@ -875,7 +853,7 @@ void cfbpe_destroy(cfbpe_ctx* ctx) {
         for (auto& ln : dv->lanes) destroy_lane(ln.get());
         cudaSetDevice(dv->device);
         cudaFree(dv->d_uc1); cudaFree(dv->d_uc2); cudaFree(dv->d_ascii); cudaFree(dv->d_fsm); cudaFree(dv->d_split_tables);
-        for (auto& v : dv->vocabs) { if (v.d_blob) cudaFree(v.d_blob); if (v.d_hot) cudaFree(v.d_hot); }
+        for (auto& v : dv->vocabs) { if (v.d_blob) cudaFree(v.d_blob); }
     }
     delete ctx;
 }

@@ -111,11 +111,14 @@ inline void enqueue_short(const BatchView& b, const VocabSet& vs, const Workspac
     const uint32_t n_tiles2k = static_cast<uint32_t>((n_warps + kLookupWarps - 1) / kLookupWarps);
     CFBPE_LAUNCH(tile_scan_kernel, 1u, 1024, stream, w.dense.tile_pieces, n_tiles2k, w.dense.piece_base, static_cast<DeviceStatus*>(nullptr),
                  static_cast<const uint64_t*>(nullptr));      // piece ranks: exclusive scan of K2s's per-tile counts
-    CFBPE_LAUNCH(bpe_lookup_kernel, n_tiles2k, kLookupWarps * 32, stream, b, vs, w.piece_bits, w.dense, w.tok_bits, w.miss, w.status);
+    CFBPE_LAUNCH(bpe_lookup_kernel, n_tiles2k, kLookupWarps * 32, stream, b, vs, w.piece_bits, w.dense, w.miss, w.status);
     CFBPE_MARK(prof, K_ENCODE, stream, false);
     CFBPE_MARK(prof, K_MERGE, stream, true);
-    CFBPE_LAUNCH_SMEM(bpe_merge_kernel, long_grid + long_grid / 2, kPieceWarps * 32, CFBPE_MERGE_HOT ? kHotCap * 8u : 0u, stream,      // 6 CTAs of 32 KB per SM
-                 b, vs, w.piece_bits, w.dense, w.tok_bits, w.miss, w.status);
+    // two launches: the class of 13..32 bytes with 32 parts a lane (32 KB a CTA), the classes of 2..12 bytes with 12 (12 KB a CTA)
+    CFBPE_LAUNCH_SMEM(bpe_merge_kernel, long_grid + long_grid / 2, kPieceWarps * 32, kPieceWarps * 2u * 32u * 32u * 4u, stream,
+                 b, vs, w.piece_bits, w.dense, w.tok_bits, w.miss, w.status, 0u, 0u, 32u);
+    CFBPE_LAUNCH_SMEM(bpe_merge_kernel, 2u * long_grid, kPieceWarps * 32, kPieceWarps * 2u * 12u * 32u * 4u, stream,
+                 b, vs, w.piece_bits, w.dense, w.tok_bits, w.miss, w.status, 1u, 2u, 12u);
     CFBPE_MARK(prof, K_MERGE, stream, false);
 }
 
@@ -145,7 +148,7 @@ template <typename Stream, typename Prof>
 inline void enqueue_count(const BatchView& b, const Workspace& w, Stream stream, Prof* prof) {
     if (!b.total_bytes) return;
     CFBPE_MARK(prof, K_COUNT, stream, true);
-    CFBPE_LAUNCH(flag_count_kernel, n_scan_tiles(b.total_bytes), 256, stream, w.tok_bits, n_flag_words(b.total_bytes), w.tile_counts);
+    CFBPE_LAUNCH(flag_count_kernel, n_scan_tiles(b.total_bytes), 256, stream, w.tok_bits, w.piece_bits, n_flag_words(b.total_bytes), w.tile_counts);
     CFBPE_MARK(prof, K_COUNT, stream, false);
 }
 template <typename Stream, typename Prof>

@@ -57,13 +57,7 @@ struct TablesView {
     const uint8_t* blob;
     uint32_t pair_mask, short_mask, long_mask;
     uint32_t n_ranks, pattern_id, max_token_len;
-    const uint64_t* hot;     // [kHotCap] the pair entries whose merged id is below kHotRanks, same slot format (device only: built at install)
 };
-
-// the hot slice of the pair table (most merges that happen yield a low rank): small enough to be staged into shared
-// memory by TMA and probed there before the L2-resident table.  A/B build CFBPE_MERGE_HOT of bpe_merge_kernel.
-constexpr uint32_t kHotRanks = 1024;
-constexpr uint32_t kHotCap = 2048;       // slots (16 KB)
 
 static inline TablesView make_view(const uint8_t* base, const TablesHeader& h) {
     TablesView v;
@@ -80,7 +74,6 @@ static inline TablesView make_view(const uint8_t* base, const TablesHeader& h) {
     v.n_ranks = h.n_ranks;
     v.pattern_id = h.pattern_id;
     v.max_token_len = h.max_token_len;
-    v.hot = nullptr;
     return v;
 }
 
@@ -142,17 +135,6 @@ CFBPE_HD void pair_lookup2(const TablesView& t, uint32_t l0, uint32_t r0, bool w
         if ((s1 >> kIdBits) == key1) { out1 = static_cast<uint32_t>(s1) & kIdMask; break; }
         if (s1 == kPairEmpty) break;
         h1 = (h1 + 1) & t.pair_mask; s1 = t.pair[h1];
-    }
-}
-// probe of the hot slice (shared memory): merged id or kNone ("not among the hot pairs": says nothing about the full table)
-CFBPE_HD uint32_t hot_lookup(const uint64_t* hot, uint32_t left, uint32_t right) {
-    const uint64_t key = (static_cast<uint64_t>(left) << kIdBits) | right;
-    uint32_t h = pair_hash(left, right) & (kHotCap - 1);
-    for (;;) {
-        const uint64_t s = hot[h];
-        if ((s >> kIdBits) == key) return static_cast<uint32_t>(s) & kIdMask;
-        if (s == kPairEmpty) return kNone;
-        h = (h + 1) & (kHotCap - 1);
     }
 }
 // id of a token of len <= 12 whose bytes are packed little-endian in (k0,k1), or kNone
