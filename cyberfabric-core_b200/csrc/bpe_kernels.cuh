@@ -491,16 +491,8 @@ __device__ __forceinline__ void load16(const uint8_t* __restrict__ p, uint32_t& 
 // CoreBPE's `if piece in ranks` for a piece of 1..32 bytes at p
 __device__ __forceinline__ uint32_t whole_piece_lookup(const TablesView& T, const uint8_t* __restrict__ p, uint32_t len) {
     if (len > T.max_token_len) return kNone;
-    if (len <= 4) {       // half of all pieces: two aligned words instead of five, and a two-byte piece is a direct table index
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(addr & ~static_cast<uintptr_t>(3));
-        const uint32_t sh = static_cast<uint32_t>(addr & 3) * 8;
-        uint32_t w = q[0];
-        if (sh + 8 * len > 32) w = __funnelshift_r(w, q[1], sh); else w >>= sh;
-        if (len == 2) return T.bytepair[((w & 0xFFu) << 8) | ((w >> 8) & 0xFFu)];
-        if (len < 4) w &= (1u << (8 * len)) - 1u;
-        return short_lookup(T, w, 0u, len);
-    }
+    // (a separate path for pieces of <= 4 bytes -- two words loaded instead of five, a two-byte piece as a direct index into the
+    //  byte-pair table -- made K2a 13 % SLOWER: the lanes of a warp then run two paths one after the other; profiles/bench_r02w.json)
     uint32_t w0, w1, w2, w3;
     load16(p, w0, w1, w2, w3);
     uint64_t k0 = static_cast<uint64_t>(w0) | (static_cast<uint64_t>(w1) << 32);
@@ -715,6 +707,8 @@ bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
                 if (pv != vid) { vid = pv; T = vs.v[vid]; }
             }
             const uint32_t tok = (len == 1) ? T.byte2id[text[pos]] : whole_piece_lookup(T, text + pos, len);   // a byte is a token
+            // (leaving the pieces of 13..32 bytes -- hash over the whole piece, byte-wise verify, one or two lanes active here -- to
+            //  K2m, where 32 of them fill a warp, took 0.15 ms off this kernel and put 0.35 ms on that one: profiles/ab_variants_r02x.txt)
             if (tok != kNone) {
                 dn.by_piece[rank0 + i] = tok;          // (its token flag is its piece flag: flag_count_kernel ORs the piece flags in)
             } else {
@@ -743,23 +737,23 @@ bpe_lookup_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_b
 
 __global__ void __launch_bounds__(kPieceWarps * 32)
 bpe_merge_kernel(BatchView b, VocabSet vs, const uint32_t* __restrict__ piece_bits, DenseIds dn,
-                 uint32_t* __restrict__ tok_bits, MissLists ml, DeviceStatus* status, uint32_t c_lo, uint32_t c_hi, uint32_t max_parts) {
-    // ids and pair ranks of the parts, [warp][part][lane]: 8 bytes a part and lane.  The CTA's shared memory is sized by the
-    // longest piece of the classes it serves (max_parts): 32 KB for the class of 13..32 bytes, 12 KB for the two classes of
-    // 2..12 bytes, which hold most of the misses -- eight CTAs a SM instead of six (the kernel waits on L2 round trips)
-    CFBPE_DYN_SMEM(s_parts);
+                 uint32_t* __restrict__ tok_bits, MissLists ml, DeviceStatus* status) {
+    // (one launch per length class with the shared memory sized by the class -- 12 KB instead of 32 KB for the pieces of 2..12
+    //  bytes, eight CTAs a SM instead of six -- gained 3 % at full size and cost a launch per sub-batch: not kept)
+    __shared__ uint32_t s_id[kPieceWarps][32][32];   // [warp][part][lane]
+    __shared__ uint32_t s_rk[kPieceWarps][32][32];
     const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const uint8_t* __restrict__ text = b.bytes;
     const bool multi = b.vocab_ids != nullptr;
-    uint32_t* sid = s_parts + (wic * 2u) * max_parts * 32u + lane;
-    uint32_t* srk = s_parts + (wic * 2u + 1u) * max_parts * 32u + lane;
+    uint32_t* sid = &s_id[wic][0][lane];
+    uint32_t* srk = &s_rk[wic][0][lane];
     if (status->miss_overflow) return;
     TablesView T = vs.v[0];
     uint32_t vid = 0;
     // (a TMA-staged hot slice of the pair table, probed before the L2-resident table, made this kernel 2x slower:
     //  profiles/ab_variants_r02k.txt)
 #pragma unroll 1
-    for (uint32_t c = c_lo; c <= c_hi; ++c) {     // longest class first
+    for (uint32_t c = 0; c < 3; ++c) {     // longest class first
         const uint32_t n = status->miss_n[c];
         const uint64_t* __restrict__ list = ml.list[c];
         for (;;) {
@@ -1225,7 +1219,10 @@ __device__ __forceinline__ bool list_kernel_takes(const TablesView& T, uint32_t 
 // One warp per CTA: a warp that is deep in the serial chain of a long piece then holds one warp's worth of registers and
 // 6 KB of shared memory, not a whole CTA's, so the tail of this kernel can share the SMs with whatever runs next.
 constexpr uint32_t kLongWarps = 4;
-__global__ void __launch_bounds__(kLongWarps * 32, 32 / kLongWarps)
+#ifndef CFBPE_LONG_MIN_CTAS
+#define CFBPE_LONG_MIN_CTAS (32 / kLongWarps)     // launch bound: CTAs per SM the register allocation must allow (A/B: 10, 12)
+#endif
+__global__ void __launch_bounds__(kLongWarps * 32, CFBPE_LONG_MIN_CTAS)
 bpe_long_kernel(BatchView b, VocabSet vs, LongPiece* long_list, DeviceStatus* status,
                 uint32_t long_cap, uint32_t* __restrict__ ids_by_pos, LongScratch sc, uint32_t* __restrict__ tok_bits) {
     __shared__ uint32_t s_med[kLongWarps][4][kMedSmem];   // [warp][id | rank | aux0 | aux1] of a piece of <= kMedSmem bytes

@@ -114,11 +114,8 @@ inline void enqueue_short(const BatchView& b, const VocabSet& vs, const Workspac
     CFBPE_LAUNCH(bpe_lookup_kernel, n_tiles2k, kLookupWarps * 32, stream, b, vs, w.piece_bits, w.dense, w.miss, w.status);
     CFBPE_MARK(prof, K_ENCODE, stream, false);
     CFBPE_MARK(prof, K_MERGE, stream, true);
-    // two launches: the class of 13..32 bytes with 32 parts a lane (32 KB a CTA), the classes of 2..12 bytes with 12 (12 KB a CTA)
-    CFBPE_LAUNCH_SMEM(bpe_merge_kernel, long_grid + long_grid / 2, kPieceWarps * 32, kPieceWarps * 2u * 32u * 32u * 4u, stream,
-                 b, vs, w.piece_bits, w.dense, w.tok_bits, w.miss, w.status, 0u, 0u, 32u);
-    CFBPE_LAUNCH_SMEM(bpe_merge_kernel, 2u * long_grid, kPieceWarps * 32, kPieceWarps * 2u * 12u * 32u * 4u, stream,
-                 b, vs, w.piece_bits, w.dense, w.tok_bits, w.miss, w.status, 1u, 2u, 12u);
+    CFBPE_LAUNCH(bpe_merge_kernel, long_grid + long_grid / 2, kPieceWarps * 32, stream,      // 6 CTAs of 32 KB per SM
+                 b, vs, w.piece_bits, w.dense, w.tok_bits, w.miss, w.status);
     CFBPE_MARK(prof, K_MERGE, stream, false);
 }
 

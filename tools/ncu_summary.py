@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (one `ncu --set full` capture) into JSON: per kernel duration, DRAM traffic, cache hit rates,
-issue utilisation, occupancy.  usage: ncu_summary.py REPORT OUT.json [TRAFFIC.json]
-TRAFFIC.json (kernel short name -> dram bytes read+written per launch) is what bench.py reports as roofline.traffic."""
+issue utilisation, occupancy.  usage: ncu_summary.py REPORT OUT.json [TRAFFIC.json [BUILD_ID]]
+TRAFFIC.json (kernel short name -> dram bytes read+written per launch, + build_id of the library that was profiled) is what
+bench.py reports as roofline.traffic -- only when the library it runs has that build id."""
 import csv, io, json, subprocess, sys
 
 rep, out = sys.argv[1], sys.argv[2]
@@ -38,6 +39,8 @@ for r in rows[2:]:
         traffic[short] = d["dram_read"] + d.get("dram_write", 0)
 json.dump(res, open(out, "w"), indent=1)
 if len(sys.argv) > 3:
+    if len(sys.argv) > 4:
+        traffic["build_id"] = sys.argv[4]
     json.dump(traffic, open(sys.argv[3], "w"), indent=1)
 for d in res:
     print(d)
