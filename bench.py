@@ -527,6 +527,7 @@ def main():
     # ---- roofline of the dominant kernel
     hbm_gbs, peak_src = peaks()
     n_miss, n_list, list_parts = pr["n_miss_pieces"], pr["n_list_pieces"], pr["n_list_parts"]
+    list_bytes = min(list_parts, long_bytes)      # bpe_list starts from the bytes: its parts at the start are its bytes
     n_extra = pr["n_extra_tokens"]
     n_pieces = (n_tokens - long_tokens) - n_extra + n_miss + n_long        # every short piece is one token or a miss; long pieces once
     alg = {  # algorithmic bytes per launch
@@ -534,9 +535,11 @@ def main():
         "long_scan": total / 8 + 24.0 * n_long + 4 * total / 2048,                # flags in; work-list entries and per-tile piece counts out
         "bpe_encode": total * (1 + 1 / 8) + 4.0 * n_pieces + total / 8 + 8.0 * n_miss + 12 * total / 2048,   # text + flags in; one word per piece, id flags, miss lists out
         "bpe_merge": n_miss * (8 + 8 + 4) + 4.0 * n_extra,                        # list entry, ~8 piece bytes, the piece's word; its tokens
-        "bpe_long": long_bytes + 4.0 * long_tokens + 24.0 * n_long,               # piece bytes in, ids out, work-list entries
-        "bpe_list": 0.0,                                                          # (its bytes and ids are counted under bpe_long: the two share the long pieces)
-        "flag_count": total / 8,
+        # the long pieces are shared by two kernels: bpe_list takes the ones above 256 bytes FROM THEIR BYTES (list_bytes of them;
+        # their ids are apportioned by bytes: the status block counts the ids of both kernels together), bpe_long the rest
+        "bpe_long": (long_bytes - list_bytes) * (1 + 4.0 * long_tokens / max(long_bytes, 1)) + 24.0 * (n_long - n_list),
+        "bpe_list": list_bytes * (1 + 4.0 * long_tokens / max(long_bytes, 1)) + 24.0 * n_list,
+        "flag_count": 3 * total / 8,                                             # token flags in, piece flags in, token flags out (ORed)
         "tile_scan": 0.0,
         "emit_compact": 2 * total / 8 + 4.0 * n_pieces + 4.0 * n_extra + 4.0 * long_tokens + 4.0 * n_tokens + 12 * (n + 1),   # both flag arrays, ids by piece, extras, long ids; ids out
         "reserved": 0.0,

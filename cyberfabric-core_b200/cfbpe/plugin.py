@@ -26,7 +26,7 @@ from __future__ import annotations
 import threading
 import uuid
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence
+from typing import Tuple, Dict, List, Optional, Sequence
 
 import numpy as np
 
@@ -136,6 +136,44 @@ class Usage:
     """gts.x.llmgw.core.usage.v1~"""
     input_tokens: int
     output_tokens: int = 0
+
+
+@dataclass(frozen=True)
+class ChatTemplate:
+    """How a provider frames a list of chat messages into the token stream it bills as `Usage.input_tokens`
+    ("chat-template overhead accounting").  Two kinds:
+
+    "overhead"  a fixed number of framing tokens a message (OpenAI's ChatML accounting: every message is
+                <|start|>{role/name}\n{content}<|end|>\n = `tokens_per_message` tokens beside role and content, a `name` costs
+                `tokens_per_name` more, the reply is primed with `reply_priming` tokens);
+    "rendered"  the conversation is rendered to text around control tokens (Llama 3, Mistral): `bos`, then per message
+                `message_prefix.format(role=...)` + content + `message_suffix`, then `generation_prompt`; the strings in
+                `special_tokens` count one token each, the text between them is tokenised as ordinary text.
+
+    Message CONTENT is always ordinary text: a message that spells a control token gets the pieces of that spelling, never the
+    control token (the gateway does not let user text forge framing)."""
+    kind: str = "overhead"
+    tokens_per_message: int = 3
+    tokens_per_name: int = 1
+    reply_priming: int = 3
+    bos: str = ""
+    message_prefix: str = ""
+    message_suffix: str = ""
+    generation_prompt: str = ""
+    special_tokens: Tuple[str, ...] = ()
+
+
+# templates of the model families the stand-in vocabularies cover; a deployment lists its own next to the model's tokenizer
+# (docs/model-registry-tokenizer-proposal.md)
+CHAT_TEMPLATES = {
+    # https://cookbook.openai.com "How to count tokens with tiktoken": gpt-3.5-turbo-0613 / gpt-4 and later
+    "openai-chatml": ChatTemplate("overhead", tokens_per_message=3, tokens_per_name=1, reply_priming=3),
+    # Meta Llama 3 instruct
+    "llama3-instruct": ChatTemplate("rendered", bos="<|begin_of_text|>",
+                                    message_prefix="<|start_header_id|>{role}<|end_header_id|>\n\n", message_suffix="<|eot_id|>",
+                                    generation_prompt="<|start_header_id|>assistant<|end_header_id|>\n\n",
+                                    special_tokens=("<|begin_of_text|>", "<|start_header_id|>", "<|end_header_id|>", "<|eot_id|>")),
+}
 
 
 # --------------------------------------------------------------------------- plugin trait
@@ -374,13 +412,64 @@ class LlmGatewayTokenizerService:
 
     def count_tokens(self, ctx: SecurityContext, model: str, messages: Sequence[dict]) -> Usage:
         """Usage.input_tokens of one chat request = sum of len(encode_ordinary(text)) over its
-        TextContent parts; chat-template overheads are provider specific and out of scope."""
+        TextContent parts; the provider's framing on top of that: count_chat_tokens."""
         texts = [part["text"] for m in messages for part in m.get("content", []) if part.get("type") == "text"]
         if not texts:
             return Usage(0)
         data, offs = pack_texts(texts)
         counts = self._plugin().count_tokens(ctx, CountTokensRequest(VocabRef(model), data, offs))
         return Usage(int(counts.sum()))
+
+    def count_chat_tokens(self, ctx: SecurityContext, model: str, messages: Sequence[dict], template: ChatTemplate) -> Usage:
+        """`Usage.input_tokens` of one chat request as the provider counts it: content AND framing (ChatTemplate).
+        messages: [{"role": "user", "name": optional, "content": [{"type": "text", "text": ...}, ...]}, ...]; parts that are
+        not text (images ...) are priced elsewhere.  Every stretch of text of the whole request goes to the device in ONE batch."""
+        import re
+        texts: List[str] = []
+        fixed = 0
+        if template.kind == "overhead":
+            for m in messages:
+                fixed += template.tokens_per_message
+                texts.append(str(m.get("role", "")))
+                if m.get("name"):
+                    fixed += template.tokens_per_name
+                    texts.append(str(m["name"]))
+                texts.extend(part["text"] for part in m.get("content", []) if part.get("type") == "text")
+            fixed += template.reply_priming
+        elif template.kind == "rendered":
+            cut = re.compile("|".join(re.escape(t) for t in sorted(template.special_tokens, key=len, reverse=True))) if template.special_tokens else None
+
+            def framing(text, into):          # control tokens count one each; the text between them is returned in pieces
+                n, last = 0, 0
+                for mt in (cut.finditer(text) if cut else ()):
+                    into.append(text[last:mt.start()]); last = mt.end(); n += 1
+                into.append(text[last:])
+                return n
+            # a stretch of ordinary text runs from one control token to the next: framing text and content are tokenised TOGETHER
+            # (the pre-tokenizer may join the framing's trailing line breaks with the content's leading spaces)
+            run: List[str] = [""]
+            def feed_framing(text):
+                nonlocal fixed
+                pieces: List[str] = []
+                fixed += framing(text, pieces)
+                run[-1] += pieces[0]
+                for p in pieces[1:]:
+                    run.append(p)
+            feed_framing(template.bos)
+            for m in messages:
+                feed_framing(template.message_prefix.format(role=m.get("role", "")))
+                run[-1] += "".join(part["text"] for part in m.get("content", []) if part.get("type") == "text")
+                feed_framing(template.message_suffix)
+            feed_framing(template.generation_prompt)
+            texts = [t for t in run if t]
+        else:
+            raise InvalidInput("unknown chat template kind %r" % template.kind)
+        texts = [t for t in texts if t]
+        if not texts:
+            return Usage(fixed)
+        data, offs = pack_texts(texts)
+        counts = self._plugin().count_tokens(ctx, CountTokensRequest(VocabRef(model), data, offs))
+        return Usage(fixed + int(counts.sum()))
 
     def encode_with_special(self, ctx: SecurityContext, model: str, texts: Sequence[str], special_tokens: dict,
                             allowed_special=(), disallowed_special="all") -> List[np.ndarray]:

@@ -52,7 +52,7 @@ inline uint64_t miss_list_words(uint64_t max_bytes, uint32_t c, uint32_t max_chu
 #endif
 constexpr uint32_t kLongCtasPerSm = CFBPE_LONG_CTAS;
 #ifndef CFBPE_LIST_CTAS
-#define CFBPE_LIST_CTAS 2
+#define CFBPE_LIST_CTAS 3      // (2 -> 3: the kernel alone 0.72 -> 0.57 ms, the step unchanged: profiles/ab_bench_r02z.txt)
 #endif
 constexpr uint32_t kListCtasPerSm = CFBPE_LIST_CTAS;   // K2c CTAs (64 KB of shared memory each) per SM
 

@@ -5,7 +5,7 @@ use modkit_security::SecurityContext;
 use serde_json::Value;
 
 use crate::error::TokenizerError;
-use crate::models::{SpecialTokens, Usage};
+use crate::models::{ChatTemplate, SpecialTokens, Usage};
 
 #[async_trait]
 pub trait TokenizerClient: Send + Sync {
@@ -22,5 +22,7 @@ pub trait TokenizerClient: Send + Sync {
     async fn count_tokens(&self, ctx: &SecurityContext, model: &str, messages: &[Value]) -> Result<Usage, TokenizerError>;
 
     /// Pre-call estimate against a remaining budget (`docs/DESIGN.md:833-855`).
+    /// `Usage.input_tokens` as the provider counts it: content AND the framing of `template`
+    async fn count_chat_tokens(&self, ctx: &SecurityContext, model: &str, messages: &[Value], template: &ChatTemplate) -> Result<Usage, TokenizerError>;
     async fn check_budget(&self, ctx: &SecurityContext, model: &str, messages: &[Value], remaining_tokens: u64) -> Result<bool, TokenizerError>;
 }

@@ -70,6 +70,19 @@ pub struct SpecialTokens {
     pub disallow_all_others: bool,
 }
 
+/// How a provider frames a list of chat messages into the token stream it bills as `Usage.input_tokens`
+/// (Python mirror: `cfbpe/plugin.py:ChatTemplate`).  Message content is always ordinary text: a message that spells a control
+/// token costs the pieces of that spelling and never becomes the control token.
+#[derive(Debug, Clone, PartialEq, Eq)]
+pub enum ChatTemplate {
+    /// a fixed number of framing tokens a message (OpenAI ChatML accounting: 3 a message, 1 a name, 3 to prime the reply)
+    Overhead { tokens_per_message: u32, tokens_per_name: u32, reply_priming: u32 },
+    /// the conversation rendered to text around control tokens (Llama 3, Mistral): `bos`, then per message
+    /// `message_prefix` (with `{role}`) + content + `message_suffix`, then `generation_prompt`; every string of
+    /// `special_tokens` counts one token, the text between two of them is tokenised as ONE stretch of ordinary text
+    Rendered { bos: String, message_prefix: String, message_suffix: String, generation_prompt: String, special_tokens: Vec<String> },
+}
+
 /// `gts.x.llmgw.core.usage.v1~` (`llm-gateway-sdk/schemas/core/usage.v1.schema.json:8-12`)
 #[derive(Debug, Clone, Copy, Default, PartialEq, Eq, Serialize, Deserialize)]
 pub struct Usage {

@@ -7,7 +7,8 @@ use std::sync::Arc;
 use async_trait::async_trait;
 use bytes::Bytes;
 use llm_gateway_sdk::{
-    CountTokensRequest, EncodeBatchRequest, SpecialTokens, TokenizerClient, TokenizerError, TokenizerPluginClient, TokenizerPluginSpecV1, Usage, VocabRef,
+    ChatTemplate, CountTokensRequest, EncodeBatchRequest, SpecialTokens, TokenizerClient, TokenizerError, TokenizerPluginClient, TokenizerPluginSpecV1, Usage,
+    VocabRef,
 };
 use modkit::client_hub::{ClientHub, ClientScope};
 use modkit::plugins::{choose_plugin_instance, GtsPluginSelector};
@@ -122,6 +123,60 @@ impl TokenizerClient for TokenizerService {
         let (bytes, offsets) = pack_texts(&texts);
         let counts = self.plugin().await?.count_tokens(ctx, CountTokensRequest { vocab: VocabRef(model.to_owned()), bytes, offsets, vocabs_per_prompt: None, vocab_index: None }).await?;
         Ok(Usage { input_tokens: counts.iter().map(|c| u64::from(*c)).sum(), output_tokens: 0 })
+    }
+
+    async fn count_chat_tokens(&self, ctx: &SecurityContext, model: &str, messages: &[Value], template: &ChatTemplate) -> Result<Usage, TokenizerError> {
+        // every stretch of ordinary text of the whole request goes to the device in ONE batch; control tokens count one each
+        let content = |m: &Value| -> String {
+            m.get("content").and_then(Value::as_array).map(|parts| {
+                parts.iter().filter(|p| p.get("type").and_then(Value::as_str) == Some("text")).filter_map(|p| p.get("text").and_then(Value::as_str)).collect::<String>()
+            }).unwrap_or_default()
+        };
+        let role = |m: &Value| m.get("role").and_then(Value::as_str).unwrap_or("").to_owned();
+        let (mut fixed, mut texts): (u64, Vec<String>) = (0, Vec::new());
+        match template {
+            ChatTemplate::Overhead { tokens_per_message, tokens_per_name, reply_priming } => {
+                for m in messages {
+                    fixed += u64::from(*tokens_per_message);
+                    texts.push(role(m));
+                    if let Some(name) = m.get("name").and_then(Value::as_str) {
+                        fixed += u64::from(*tokens_per_name);
+                        texts.push(name.to_owned());
+                    }
+                    texts.extend(Self::text_parts(std::slice::from_ref(m)));
+                }
+                fixed += u64::from(*reply_priming);
+            }
+            ChatTemplate::Rendered { bos, message_prefix, message_suffix, generation_prompt, special_tokens } => {
+                // framing text and content between two control tokens form one stretch (the pre-tokenizer may join them)
+                let mut run = vec![String::new()];
+                let mut feed = |framing: &str, fixed: &mut u64, run: &mut Vec<String>| {
+                    let mut rest = framing;
+                    loop {
+                        let next = special_tokens.iter().filter_map(|t| rest.find(t.as_str()).map(|i| (i, t.len()))).min_by_key(|(i, l)| (*i, std::cmp::Reverse(*l)));
+                        match next {
+                            Some((i, l)) => { run.last_mut().expect("never empty").push_str(&rest[..i]); run.push(String::new()); *fixed += 1; rest = &rest[i + l..]; }
+                            None => { run.last_mut().expect("never empty").push_str(rest); break; }
+                        }
+                    }
+                };
+                feed(bos, &mut fixed, &mut run);
+                for m in messages {
+                    feed(&message_prefix.replace("{role}", &role(m)), &mut fixed, &mut run);
+                    run.last_mut().expect("never empty").push_str(&content(m));
+                    feed(message_suffix, &mut fixed, &mut run);
+                }
+                feed(generation_prompt, &mut fixed, &mut run);
+                texts = run;
+            }
+        }
+        texts.retain(|t| !t.is_empty());
+        if texts.is_empty() {
+            return Ok(Usage { input_tokens: fixed, output_tokens: 0 });
+        }
+        let (bytes, offsets) = pack_texts(&texts);
+        let counts = self.plugin().await?.count_tokens(ctx, CountTokensRequest { vocab: VocabRef(model.to_owned()), bytes, offsets, vocabs_per_prompt: None, vocab_index: None }).await?;
+        Ok(Usage { input_tokens: fixed + counts.iter().map(|c| u64::from(*c)).sum::<u64>(), output_tokens: 0 })
     }
 
     async fn check_budget(&self, ctx: &SecurityContext, model: &str, messages: &[Value], remaining_tokens: u64) -> Result<bool, TokenizerError> {

@@ -157,6 +157,23 @@ def test_encode_with_special_on_device_against_tiktoken(plug, ctx, tekken_bytes)
     assert got[0].tolist() == enc.encode("a <|endoftext|> b", allowed_special=set(), disallowed_special=())
 
 
+def test_chat_template_accounting_on_device_against_tiktoken(plug, ctx, tekken_bytes):
+    """Usage.input_tokens with the provider's framing: the Llama 3 template over the CUDA path vs tiktoken on
+    the rendered conversation with the template's control tokens as special tokens; 300 conversations in the fuzz alphabet"""
+    from cfbpe import plugin as P
+    tpl = P.CHAT_TEMPLATES["llama3-instruct"]
+    enc = _tiktoken_encoding(tekken_bytes, 2, 128000, {t: 128000 + i for i, t in enumerate(tpl.special_tokens)})
+    hub = P.ClientHub()
+    hub.register_scoped(P.TokenizerPluginClient, plug.instance.id, plug)
+    svc = P.LlmGatewayTokenizerService(hub, [plug.instance])
+    texts = [t for t in fuzzgen.fuzz_strings(4711, 1200, max_atoms=24) if "<|" not in t]
+    roles = ["system", "user", "assistant", "tool"]
+    for c in range(300):
+        conv = [{"role": roles[(c + i) % 4], "content": [{"type": "text", "text": texts[(4 * c + i) % len(texts)]}]} for i in range(1 + c % 4)]
+        rendered = tpl.bos + "".join(tpl.message_prefix.format(role=m["role"]) + m["content"][0]["text"] + tpl.message_suffix for m in conv) + tpl.generation_prompt
+        assert svc.count_chat_tokens(ctx, "llama3", conv, tpl).input_tokens == len(enc.encode(rendered, allowed_special="all")), rendered
+
+
 def test_micro_batcher_on_device_from_64_threads(plug, ctx, oracle_vocabs):
     """SURVEY.md 8(f) item 4 on the real plugin: 64 request threads, two vocabularies, every caller gets its own counts;
     one bad request fails alone"""

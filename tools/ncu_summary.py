@@ -35,7 +35,7 @@ for r in rows[2:]:
     res.append(d)
     if "dram_read" in d:
         short = name.replace("_kernel", "").replace("void ", "")
-        short = {"bpe_lookup": "bpe_encode", "bpe_encode_pieces<1>": "long_scan", "bpe_encode_pieces<2>": "bpe_encode_fused"}.get(short, short)   # bench.py's names
+        short = {"bpe_lookup": "bpe_encode", "pretok_split16": "pretok_split", "bpe_encode_pieces<1>": "long_scan", "bpe_encode_pieces<2>": "bpe_encode_fused"}.get(short, short)   # bench.py's names
         traffic[short] = d["dram_read"] + d.get("dram_write", 0)
 json.dump(res, open(out, "w"), indent=1)
 if len(sys.argv) > 3:
