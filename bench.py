@@ -154,6 +154,15 @@ def host_cpu_budget():
     return n, {"visible_cpus": visible, "affinity_cpus": aff, "cgroup_quota_cpus": quota}
 
 
+def cgroup_throttle():
+    """(nr_throttled, throttled_usec, usage_usec) of this container's CPU controller, or None"""
+    try:
+        kv = dict(l.split() for l in open("/sys/fs/cgroup/cpu.stat").read().splitlines())
+        return int(kv.get("nr_throttled", 0)), int(kv.get("throttled_usec", 0)), int(kv.get("usage_usec", 0))
+    except Exception:
+        return None
+
+
 def pin_to_gpu_numa_node(local_rank):
     """Run this rank -- and allocate its pinned buffers, which follow the allocating thread's node -- on the CPUs next to its GPU.
     With eight ranks the host leg is bound by the box's PCIe roots and memory: a rank whose buffers sit on the other socket pays
@@ -382,6 +391,7 @@ def main():
     for _ in range(args.warmup):
         r = step_e2e()
     barrier()
+    thr0 = cgroup_throttle()
     t0 = time.perf_counter()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record()
@@ -391,6 +401,12 @@ def main():
     barrier()
     e2e_ms = max_over_ranks(max(c0.elapsed_time(c1), (time.perf_counter() - t0) * 1e3))
     e2e_value = total_all * args.steps / (e2e_ms * 1e-3)
+    thr1 = cgroup_throttle()
+    # was the container's CPU quota hit while the host legs of all ranks ran?  (each rank enqueues ~350 launches a step and waits
+    # on events; a throttled rank stalls its pipeline.)  Container-wide counters, read by rank 0.
+    host_cpu = None if thr0 is None or thr1 is None else {
+        "cgroup_quota_cpus": host_cpu_budget()[1]["cgroup_quota_cpus"], "throttled_periods_during_e2e": thr1[0] - thr0[0],
+        "throttled_ms_during_e2e": (thr1[1] - thr0[1]) / 1e3, "cpu_ms_used_during_e2e": (thr1[2] - thr0[2]) / 1e3, "wall_ms": e2e_ms}
     assert int(r.offsets[n]) == n_tokens
     # ---- the two multi-GPU workloads BASELINE.json names, as extra records (the headline stays the weak-scaled config 3):
     #   strong   configs[2] as ONE 65 536-prompt batch sharded by bytes over the N ranks (cfbpe.dist.shard_by_bytes); timed end to
@@ -441,7 +457,7 @@ def main():
             try:
                 from cfbpe import _native as NN
                 cN = NN.Context(0, int(s_offs[-1]) // world + (16 << 20), len(s_offs), devices=list(range(world)))
-                cN.vocab_load(0, rv.file_bytes, rv.fmt, rv.pattern_id, rv.max_ranks or 0)
+                cN.vocab_load(0, rv.file_bytes, rv.spec.fmt, rv.pattern_id, rv.max_ranks or 0)
                 hb = cN.pinned(len(s_data) + 64, np.uint8); hb.array[:len(s_data)] = s_data
                 ho = (cN.pinned(int(s_offs[-1]) + 1, np.uint32), cN.pinned(len(s_offs), np.uint64), cN.pinned(len(s_offs), np.uint32))
                 for _ in range(args.warmup):
@@ -591,7 +607,7 @@ def main():
                      "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
                      "path_algorithmic_bytes": path_alg,
                      "path_achieved_gbs": path_alg / (kernels_ms * 1e-3) / 1e9 if kernels_ms > 0 else 0.0},
-        "strong": strong, "strong_one_context": strong_lib,
+        "strong": strong, "strong_one_context": strong_lib, "host_cpu": host_cpu,
         "config5": config5,
         "numa": numa,
         "cpu_baseline": cpu,
