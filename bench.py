@@ -452,6 +452,8 @@ def main():
     # the totals and the rebasing of the offsets happen inside the library; rank 0 makes the call, the other ranks wait
     strong_lib = None
     if world > 1:
+        # the other ranks wait on the CPU (a gloo barrier): an NCCL barrier would keep a spinning kernel on every GPU this context uses
+        cpu_group = dist.new_group(backend="gloo")
         barrier()
         if rank == 0:
             try:
@@ -474,6 +476,8 @@ def main():
                 cN.close()
             except Exception as e:   # noqa: BLE001
                 strong_lib = {"error": "%s: %s" % (type(e).__name__, e)}
+        dist.barrier(group=cpu_group)
+        torch.cuda.set_device(dev)
         barrier()
     config5 = None
     if not args.no_config5:

@@ -787,6 +787,14 @@ bool load_nccl(NcclApi* n) {
 
 }  // namespace
 
+// Every entry point that selects a device puts the caller's current device back on return: the library is a guest in the host
+// process (a model runtime next door expects its own device to stay current on its thread).
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 extern "C" {
 
 int cfbpe_abi_version(void) { return static_cast<int>(CFBPE_ABI_VERSION); }
@@ -797,6 +805,7 @@ int cfbpe_abi_version(void) { return static_cast<int>(CFBPE_ABI_VERSION); }
 const char* cfbpe_build_id(void) { return CFBPE_SRC_HASH; }
 
 int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
+    DeviceGuard restore_device;
     if (!cfg || !out || cfg->struct_size < offsetof(cfbpe_config, devices)) return CFBPE_EINVAL;
     *out = nullptr;
     // (a pipelined host call keeps ~20 streams busy: hosts should export CUDA_DEVICE_MAX_CONNECTIONS=32 before CUDA
@@ -843,6 +852,7 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
 }
 
 void cfbpe_destroy(cfbpe_ctx* ctx) {
+    DeviceGuard restore_device;
     if (!ctx) return;
     for (auto& dvp : ctx->devs) {
         DeviceCtx* dv = dvp.get();
@@ -861,6 +871,7 @@ const char* cfbpe_last_error(const cfbpe_ctx*) { return tl_err.c_str(); }
 
 int cfbpe_vocab_load(cfbpe_ctx* ctx, uint32_t vocab_id, const uint8_t* ranks_file, size_t len, uint32_t format,
                      uint32_t pattern_id, uint32_t max_ranks) {
+    DeviceGuard restore_device;
     if (!ctx) return CFBPE_EINVAL;
     tl_err.clear();
     if (vocab_id >= CFBPE_MAX_VOCABS) return fail(ctx, CFBPE_EINVAL, "vocab_id out of range");
@@ -904,6 +915,7 @@ int cfbpe_vocab_export(const cfbpe_ctx* ctx, uint32_t vocab_id, uint8_t* buf, ui
 }
 
 int cfbpe_vocab_import(cfbpe_ctx* ctx, uint32_t vocab_id, const uint8_t* buf, uint64_t size) {
+    DeviceGuard restore_device;
     if (!ctx) return CFBPE_EINVAL;
     tl_err.clear();
     if (vocab_id >= CFBPE_MAX_VOCABS || !buf) return fail(ctx, CFBPE_EINVAL, "bad argument");
@@ -917,12 +929,14 @@ int cfbpe_vocab_import(cfbpe_ctx* ctx, uint32_t vocab_id, const uint8_t* buf, ui
 int cfbpe_encode_batch(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t* bytes, const uint64_t* offsets,
                        const uint8_t* vocab_ids, uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets,
                        uint32_t* out_counts) {
+    DeviceGuard restore_device;
     if (!ctx) return CFBPE_EINVAL;
     return run_host(ctx, n_prompts, bytes, offsets, vocab_ids, out_ids, out_cap, out_offsets, out_counts, true);
 }
 
 int cfbpe_count_batch(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t* bytes, const uint64_t* offsets,
                       const uint8_t* vocab_ids, uint32_t* out_counts) {
+    DeviceGuard restore_device;
     if (!ctx) return CFBPE_EINVAL;
     if (!out_counts && n_prompts) return fail(ctx, CFBPE_EINVAL, "out_counts is NULL");
     return run_host(ctx, n_prompts, bytes, offsets, vocab_ids, nullptr, 0, nullptr, out_counts, false);
@@ -930,6 +944,7 @@ int cfbpe_count_batch(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t* bytes, 
 
 int cfbpe_decode_batch(cfbpe_ctx* ctx, uint32_t n_seqs, const uint32_t* ids, const uint64_t* id_offsets,
                        const uint8_t* vocab_ids, uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offsets) {
+    DeviceGuard restore_device;
     if (!ctx) return CFBPE_EINVAL;
     tl_err.clear();
     std::shared_lock<std::shared_mutex> vocabs(ctx->vocab_mu);
@@ -981,6 +996,7 @@ int cfbpe_encode_batch_device(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t*
                               const uint64_t* d_offsets, const uint8_t* d_vocab_ids, uint32_t* d_out_ids,
                               uint64_t out_cap, uint64_t* d_out_offsets, uint32_t* d_out_counts, uint64_t* n_tokens,
                               void* stream) {
+    DeviceGuard restore_device;
     if (!ctx) return CFBPE_EINVAL;
     tl_err.clear();
     std::shared_lock<std::shared_mutex> vocabs(ctx->vocab_mu);
@@ -1027,6 +1043,7 @@ int cfbpe_encode_batch_device(cfbpe_ctx* ctx, uint32_t n_prompts, const uint8_t*
 }
 
 int cfbpe_device_status(cfbpe_ctx* ctx, void* stream) {
+    DeviceGuard restore_device;
     if (!ctx) return CFBPE_EINVAL;
     Lane* ln = tl_device_lane;      // the lane of this thread's last device-path call
     if (!ln) return CFBPE_OK;
@@ -1044,6 +1061,7 @@ int cfbpe_device_status(cfbpe_ctx* ctx, void* stream) {
 }
 
 void* cfbpe_host_alloc(cfbpe_ctx* ctx, size_t size) {
+    DeviceGuard restore_device;
     if (!ctx) return nullptr;
     void* p = nullptr;
     cudaSetDevice(ctx->devs[0]->device);
@@ -1051,6 +1069,7 @@ void* cfbpe_host_alloc(cfbpe_ctx* ctx, size_t size) {
     return p;
 }
 void cfbpe_host_free(cfbpe_ctx* ctx, void* ptr) {
+    DeviceGuard restore_device;
     if (!ctx || !ptr) return;
     cudaFreeHost(ptr);
 }
@@ -1062,6 +1081,7 @@ int cfbpe_profile_enable(cfbpe_ctx* ctx, int on) {
     return CFBPE_OK;
 }
 int cfbpe_profile_read(cfbpe_ctx* ctx, cfbpe_profile* out) {
+    DeviceGuard restore_device;
     if (!ctx || !out) return CFBPE_EINVAL;
     if (!tl_profile_ready) return CFBPE_ENOENT;
     *out = tl_profile;

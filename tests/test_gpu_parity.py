@@ -613,9 +613,11 @@ def test_multi_device_context_shards_a_batch(oracle_vocabs, tekken_bytes):
     data, offs = pack(prompts)
     vid = (np.arange(len(prompts)) % 2).astype(np.uint8)
     want_ids, want_off, want_counts = oracle.encode_batch([oracle_vocabs[0], oracle_vocabs[3]], [0, 3], data, offs, vocab_ids=vid, nthreads=os.cpu_count())
+    torch.cuda.set_device(0)
     c = N.Context(0, 64 << 20, 1 << 17, devices=list(range(ndev)))
     c.vocab_load(0, tekken_bytes, N.FORMAT_TIKTOKEN, 0, 100256)
     c.vocab_load(1, tekken_bytes, N.FORMAT_TIKTOKEN, 3, 130072)
+    assert torch.cuda.current_device() == 0        # the library leaves the caller's current device alone
     for _ in range(2):
         ids, off, counts = c.encode_batch(data, offs, vid)
         assert np.array_equal(off, want_off) and np.array_equal(ids, want_ids) and np.array_equal(counts, want_counts)
@@ -631,3 +633,4 @@ def test_multi_device_context_shards_a_batch(oracle_vocabs, tekken_bytes):
     ids, off, counts = c.encode_batch(*pack([b"one prompt only"]))        # fewer prompts than devices: one device does it
     assert np.array_equal(ids, oracle_vocabs[0].encode(0, b"one prompt only"))
     c.close()
+    assert torch.cuda.current_device() == 0
