@@ -458,7 +458,7 @@ def main():
         if rank == 0:
             try:
                 from cfbpe import _native as NN
-                cN = NN.Context(0, int(s_offs[-1]) // world + (16 << 20), len(s_offs), devices=list(range(world)))
+                cN = NN.Context(0, int(s_offs[-1]) + 4096, len(s_offs), devices=list(range(world)))     # every device can hold the batch: sub-batches go round-robin
                 cN.vocab_load(0, rv.file_bytes, rv.spec.fmt, rv.pattern_id, rv.max_ranks or 0)
                 hb = cN.pinned(len(s_data) + 64, np.uint8); hb.array[:len(s_data)] = s_data
                 ho = (cN.pinned(int(s_offs[-1]) + 1, np.uint32), cN.pinned(len(s_offs), np.uint64), cN.pinned(len(s_offs), np.uint32))
@@ -469,8 +469,8 @@ def main():
                     rN = cN.encode_batch(hb.array[:len(s_data)], s_offs, None, *[x.array for x in ho])
                 msN = (time.perf_counter() - t0) * 1e3
                 same = bool(int(rN[1][-1]) == int(np.asarray(counts, dtype=np.int64).sum()) and np.array_equal(rN[2], np.asarray(counts, dtype=np.uint32)))
-                strong_lib = {"workload": "the same batch through ONE context over %d devices (cfbpe_config.devices[]): sharding, NCCL gather of the shard "
-                                          "totals and offset rebasing inside the library; one host process" % world,
+                strong_lib = {"workload": "the same batch through ONE context over %d devices (cfbpe_config.devices[]), one host process: the sub-batches of "
+                                          "the pipelined call go round-robin over the devices, token ranks chained over NVLink peer memory" % world,
                               "value": int(s_offs[-1]) * args.steps / (msN * 1e-3), "unit": UNIT, "ms_per_step": msN / args.steps,
                               "counts_equal_to_the_sharded_leg": same}
                 cN.close()

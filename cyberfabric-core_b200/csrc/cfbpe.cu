@@ -163,6 +163,7 @@ struct cfbpe_ctx {
     uint64_t pipe_chunk = kPipeChunkBytes, pipe_min = kPipeMinBytes;   // CFBPE_PIPE_CHUNK_BYTES / CFBPE_PIPE_MIN_BYTES override (tests)
     std::atomic<bool> profiling{false};
     NcclApi nccl;
+    bool peer_ok = false;      // several devices, each maps the memory of all the others (NVLink): sub-batches may go round-robin
 };
 
 namespace {
@@ -301,13 +302,17 @@ void fill_profile(Lane* ln, uint64_t n_bytes) {
 // ids to fetch.
 // defer != nullptr (a shard of a multi-device call): nothing is downloaded here -- ids, offsets and counts stay in the lane's device
 // buffers (dense, shard-local ranks: sub-batch k's offsets at d_out_offsets + p_k + k) and *defer gets the shard's token total.
-int run_host_pipelined(cfbpe_ctx* ctx, DeviceCtx* dv, Lane* ln, uint32_t n, const uint8_t* bytes, const uint64_t* offsets, const uint8_t* vocab_ids,
-                       uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_counts, bool want_ids,
+int run_host_pipelined(cfbpe_ctx* ctx, DeviceCtx* const* dvs, Lane* const* lns, int G, uint32_t n, const uint8_t* bytes, const uint64_t* offsets,
+                       const uint8_t* vocab_ids, uint32_t* out_ids, uint64_t out_cap, uint64_t* out_offsets, uint32_t* out_counts, bool want_ids,
                        uint64_t total, uint64_t* defer, uint32_t* cut_out, int* nc_out) {
     // ---- cut
     uint32_t cut[kMaxPipeChunks + 1];
     const int nc = plan_sub_batches(offsets, n, total, ctx->pipe_chunk, kMaxPipeChunks, cut);
-    cudaStream_t cs = ln->stream, hs = ln->h2d_stream, ds = ln->d2h_stream;
+    // Sub-batch k runs on device k mod G (G = 1: the single-device call).  Every device keeps the layout of the whole batch
+    // (same slices of its own workspace), so the devices differ only in WHICH sub-batches they fill in; the one thing a sub-batch
+    // needs from its predecessor -- the token rank it starts at -- is read from the predecessor's device over NVLink (peer
+    // memory), behind a cross-device event.  Uploads and downloads of the devices run side by side on their own PCIe links.
+    Lane* ln = lns[0];                       // (host-side staging of the offsets and the trace live in the first lane)
     // local offsets of every sub-batch, staged in pinned memory (sub-batch k occupies [p_k + k, p_{k+1} + k])
     for (int k = 0; k < nc; ++k) {
         const uint32_t p0 = cut[k], p1 = cut[k + 1];
@@ -316,23 +321,28 @@ int run_host_pipelined(cfbpe_ctx* ctx, DeviceCtx* dv, Lane* ln, uint32_t n, cons
         for (uint32_t i = p0; i <= p1; ++i) dst[i - p0] = offsets[i] - o0;
     }
     // ---- enqueue everything that does not depend on the host knowing a result
-    const bool trace = getenv("CFBPE_PIPE_TRACE") != nullptr;
+    const bool trace = G == 1 && getenv("CFBPE_PIPE_TRACE") != nullptr;
     const bool no_copy = trace && getenv("CFBPE_PIPE_NO_COPY") != nullptr;   // measurement aid: the kernels of a pipelined call without its copies (the device buffers still hold the previous call's data)
     if (trace && !ln->trace) {
         ln->trace = new cudaEvent_t[kMaxPipeChunks + 1][kTracePoints];
         for (int k = 0; k <= kMaxPipeChunks; ++k) for (int j = 0; j < kTracePoints; ++j) cudaEventCreate(&ln->trace[k][j]);
     }
-    if (trace) CK(cudaEventRecord(ln->trace[nc][0], hs));
+    if (trace) CK(cudaEventRecord(ln->trace[nc][0], ln->h2d_stream));
     const auto host_t0 = std::chrono::steady_clock::now();
     auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
     double host_enq[kMaxPipeChunks] = {}, host_dl[kMaxPipeChunks] = {};
     for (int k = 0; k < nc; ++k) {
+        DeviceCtx* const dv = dvs[k % G];
+        Lane* const ln = lns[k % G];
+        Lane* const prev = k ? lns[(k - 1) % G] : nullptr;
+        if (G > 1) CK(cudaSetDevice(dv->device));
+        cudaStream_t cs = ln->stream, hs = ln->h2d_stream;
         const uint32_t p0 = cut[k], p1 = cut[k + 1], nk = p1 - p0;
         const uint64_t o0 = offsets[p0], len = offsets[p1] - o0;
         // every sub-batch lands on a 16-byte boundary of the device buffer (K1 reads 16 bytes per lane with one load)
         uint8_t* const d_sub = ln->d_bytes + ((o0 + 15) & ~15ull) + 16ull * k;
         if (len && !no_copy) CK(cudaMemcpyAsync(d_sub, bytes + o0, len, cudaMemcpyHostToDevice, hs));
-        CK(cudaMemcpyAsync(ln->d_offsets + p0 + k, ln->h_offs_stage + p0 + k, (static_cast<uint64_t>(nk) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, hs));
+        CK(cudaMemcpyAsync(ln->d_offsets + p0 + k, lns[0]->h_offs_stage + p0 + k, (static_cast<uint64_t>(nk) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, hs));
         if (vocab_ids && nk) CK(cudaMemcpyAsync(ln->d_vocab_ids + p0, vocab_ids + p0, nk, cudaMemcpyHostToDevice, hs));
         CK(cudaEventRecord(ln->ev_h2d[k], hs));
         if (trace) CK(cudaEventRecord(ln->trace[k][0], hs));
@@ -378,8 +388,8 @@ int run_host_pipelined(cfbpe_ctx* ctx, DeviceCtx* dv, Lane* ln, uint32_t n, cons
         CK(cudaStreamWaitEvent(ss, ln->ev_list[k], 0));
         enqueue_count(b, w, ss, static_cast<ProfEvents*>(nullptr));
         if (trace) CK(cudaEventRecord(ln->trace[k][7], ss));
-        if (k) CK(cudaStreamWaitEvent(ss, ln->ev_chain[k - 1], 0));    // token ranks chain through DeviceStatus::tok_end: only the scan waits
-        enqueue_scan(b, w, ss, static_cast<ProfEvents*>(nullptr), k ? &ln->d_status_arr[k - 1].tok_end : nullptr);
+        if (k) CK(cudaStreamWaitEvent(ss, prev->ev_chain[k - 1], 0));    // token ranks chain through DeviceStatus::tok_end: only the scan waits
+        enqueue_scan(b, w, ss, static_cast<ProfEvents*>(nullptr), k ? &prev->d_status_arr[k - 1].tok_end : nullptr);   // (G > 1: a peer pointer)
         CK(cudaEventRecord(ln->ev_chain[k], ss));
         enqueue_emit(b, w, want_ids ? ln->d_out_ids : nullptr, ctx->max_bytes, ln->d_out_offsets + p0 + k, ln->d_out_counts + p0,
                      ss, static_cast<ProfEvents*>(nullptr));
@@ -392,6 +402,9 @@ int run_host_pipelined(cfbpe_ctx* ctx, DeviceCtx* dv, Lane* ln, uint32_t n, cons
     int err = CFBPE_OK;
     uint64_t tok_total = 0;
     for (int k = 0; k < nc; ++k) {
+        Lane* const ln = lns[k % G];
+        if (G > 1) CK(cudaSetDevice(dvs[k % G]->device));
+        cudaStream_t ds = ln->d2h_stream;
         CK(cudaEventSynchronize(ln->ev_done[k]));
         const DeviceStatus st = ln->h_status_arr[k];
         const uint32_t p0 = cut[k], p1 = cut[k + 1], nk = p1 - p0;
@@ -408,12 +421,16 @@ int run_host_pipelined(cfbpe_ctx* ctx, DeviceCtx* dv, Lane* ln, uint32_t n, cons
         if (out_counts && nk) CK(cudaMemcpyAsync(out_counts + p0, ln->d_out_counts + p0, static_cast<uint64_t>(nk) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds));
         if (trace) { CK(cudaEventRecord(ln->trace[k][5], ds)); host_dl[k] = host_ms(); }
     }
-    CK(cudaStreamSynchronize(ds));
-    CK(cudaStreamSynchronize(cs));
-    for (int k = 1; k < kFrontStreams; ++k) CK(cudaStreamSynchronize(ln->front[k]));
-    for (int k = 0; k < kSideStreams; ++k) CK(cudaStreamSynchronize(ln->side[k]));
-    for (int k = 0; k < kSideStreams; ++k) CK(cudaStreamSynchronize(ln->side2[k]));
-    if (ln->prio_mode) for (int l = 0; l < kPrioLevels; ++l) for (int j = 0; j < kPoolSlots; ++j) if (ln->pool[l][j]) CK(cudaStreamSynchronize(ln->pool[l][j]));
+    for (int g = 0; g < G; ++g) {
+        Lane* const lg = lns[g];
+        if (G > 1) CK(cudaSetDevice(dvs[g]->device));
+        CK(cudaStreamSynchronize(lg->d2h_stream));
+        CK(cudaStreamSynchronize(lg->stream));
+        for (int k = 1; k < kFrontStreams; ++k) CK(cudaStreamSynchronize(lg->front[k]));
+        for (int k = 0; k < kSideStreams; ++k) CK(cudaStreamSynchronize(lg->side[k]));
+        for (int k = 0; k < kSideStreams; ++k) CK(cudaStreamSynchronize(lg->side2[k]));
+        if (lg->prio_mode) for (int l = 0; l < kPrioLevels; ++l) for (int j = 0; j < kPoolSlots; ++j) if (lg->pool[l][j]) CK(cudaStreamSynchronize(lg->pool[l][j]));
+    }
     if (trace && !err) {
         fprintf(stderr, "pipe trace (ms since the first upload was enqueued): sub-batch bytes | h2d split long_end list_end short count back d2h\n");
         for (int k = 0; k < nc; ++k) {
@@ -441,7 +458,7 @@ int run_lane(cfbpe_ctx* ctx, DeviceCtx* dv, Lane* ln, uint32_t n, const uint8_t*
     if (ln->ws_pending) { CK(cudaEventSynchronize(ln->ev_ws)); ln->ws_pending = false; }   // an asynchronous device-path call still owns the workspace
     const bool profiling = ctx->profiling.load();
     if (!profiling && total >= ctx->pipe_min && n >= 2)
-        return run_host_pipelined(ctx, dv, ln, n, bytes, offsets, vocab_ids, out_ids, out_cap, out_offsets, out_counts, want_ids, total, defer, cut_out, nc_out);
+        return run_host_pipelined(ctx, &dv, &ln, 1, n, bytes, offsets, vocab_ids, out_ids, out_cap, out_offsets, out_counts, want_ids, total, defer, cut_out, nc_out);
     cudaStream_t s = ln->stream;
     ProfEvents* prof = profiling ? &ln->prof : nullptr;
     if (prof) { std::memset(prof->launched, 0, sizeof prof->launched); cudaEventRecord(prof->total[0], s); cudaEventRecord(prof->h2d[0], s); }
@@ -588,8 +605,24 @@ int run_host(cfbpe_ctx* ctx, uint32_t n, const uint8_t* bytes, const uint64_t* o
     if (rc) return rc;
     if (total && !bytes) return fail(ctx, CFBPE_EINVAL, "bytes is NULL");
     if (want_ids && (!out_offsets || (!out_ids && out_cap))) return fail(ctx, CFBPE_EINVAL, "output pointer is NULL");
-    if (ctx->devs.size() > 1 && n >= ctx->devs.size() && !ctx->profiling.load())
+    if (ctx->devs.size() > 1 && n >= ctx->devs.size() && !ctx->profiling.load()) {
+        // Two ways over several devices.  When every device can hold the whole batch (and the devices see each other's memory):
+        // the sub-batches of ONE pipelined call go round-robin over the devices -- uploads, kernels and downloads of all devices
+        // overlap, the token-rank chain crosses NVLink.  Else: one contiguous shard a device, totals by ncclAllGather.
+        if (ctx->peer_ok && total <= ctx->max_bytes && total >= ctx->pipe_min) {
+            const int G = static_cast<int>(ctx->devs.size());
+            std::vector<std::unique_ptr<LaneLock>> locks(G);
+            DeviceCtx* dvs[CFBPE_MAX_DEVICES]; Lane* lns[CFBPE_MAX_DEVICES];
+            for (int g = 0; g < G; ++g) {
+                dvs[g] = ctx->devs[g].get();
+                locks[g].reset(new LaneLock(dvs[g]));
+                lns[g] = locks[g]->ln;
+                if (lns[g]->ws_pending) { CK(cudaSetDevice(dvs[g]->device)); CK(cudaEventSynchronize(lns[g]->ev_ws)); lns[g]->ws_pending = false; }
+            }
+            return run_host_pipelined(ctx, dvs, lns, G, n, bytes, offsets, vocab_ids, out_ids, out_cap, out_offsets, out_counts, want_ids, total, nullptr, nullptr, nullptr);
+        }
         return run_multi_device(ctx, n, bytes, offsets, vocab_ids, out_ids, out_cap, out_offsets, out_counts, want_ids, total);
+    }
     if (total > ctx->max_bytes) return fail(ctx, CFBPE_EINVAL, "batch exceeds max_batch_bytes of this context");
     DeviceCtx* dv = ctx->devs[0].get();
     LaneLock lk(dv);
@@ -844,6 +877,20 @@ int cfbpe_create(const cfbpe_config* cfg, cfbpe_ctx** out) {
         const int rc = ctx->nccl.CommInitAll(comms.data(), static_cast<int>(devices.size()), devices.data());
         if (rc != 0) { tl_err = std::string("ncclCommInitAll: ") + ctx->nccl.GetErrorString(rc); cfbpe_destroy(ctx); return CFBPE_EIO; }
         for (size_t i = 0; i < devices.size(); ++i) ctx->devs[i]->comm = comms[i];
+        // peer mappings: a sub-batch on one device reads the token rank its predecessor on another device ended at
+        bool peers = std::getenv("CFBPE_NO_PEER") == nullptr;
+        for (size_t a = 0; a < devices.size() && peers; ++a) {
+            cudaSetDevice(devices[a]);
+            for (size_t b2 = 0; b2 < devices.size() && peers; ++b2) {
+                if (a == b2) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b2]) != cudaSuccess || !can) { peers = false; break; }
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b2], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) peers = false;
+                cudaGetLastError();
+            }
+        }
+        ctx->peer_ok = peers;
     }
     if (const char* e = std::getenv("CFBPE_PIPE_CHUNK_BYTES")) { const uint64_t v = std::strtoull(e, nullptr, 10); if (v >= 1024) ctx->pipe_chunk = v; }
     if (const char* e = std::getenv("CFBPE_PIPE_MIN_BYTES")) { const uint64_t v = std::strtoull(e, nullptr, 10); if (v >= 1) ctx->pipe_min = v; }

@@ -602,13 +602,22 @@ def test_error_message_is_per_thread(plug, ctx):
 
 
 @pytest.mark.skipif("__import__('torch').cuda.device_count() < 2")
-def test_multi_device_context_shards_a_batch(oracle_vocabs, tekken_bytes):
-    """cfbpe_create(cfg: devices[], n_devices): one context over two GPUs -- tables by ncclBroadcast, the batch sharded by bytes,
-    token totals by ncclAllGather, offsets rebased on the devices -- returns exactly what one device returns"""
+@pytest.mark.parametrize("mode", ["shards", "round_robin"])
+def test_multi_device_context_shards_a_batch(oracle_vocabs, tekken_bytes, mode, monkeypatch):
+    """cfbpe_create(cfg: devices[], n_devices): one context over the GPUs of the box returns exactly what one device returns.
+    "shards": one contiguous range of prompts a device, tables by ncclBroadcast, token totals by ncclAllGather, offsets rebased
+    on the devices (batches a device cannot hold whole, or devices without peer access).  "round_robin": the sub-batches of ONE
+    pipelined call go round the devices, the token-rank chain crosses NVLink peer memory (here forced onto a small batch: 40
+    sub-batches of 64 KiB)."""
     import torch
     from cfbpe import _native as N
     from oracle import oracle
     ndev = min(torch.cuda.device_count(), 8)
+    if mode == "round_robin":
+        monkeypatch.setenv("CFBPE_PIPE_MIN_BYTES", "1")
+        monkeypatch.setenv("CFBPE_PIPE_CHUNK_BYTES", str(64 << 10))
+    else:
+        monkeypatch.setenv("CFBPE_NO_PEER", "1")
     prompts = [s.encode() for s in fuzzgen.fuzz_strings(77, 40000, max_atoms=60) + fuzzgen.long_runs(5)] + [b"", b"x", b""]
     data, offs = pack(prompts)
     vid = (np.arange(len(prompts)) % 2).astype(np.uint8)
@@ -632,5 +641,7 @@ def test_multi_device_context_shards_a_batch(oracle_vocabs, tekken_bytes):
     assert ei.value.code == N.EILSEQ
     ids, off, counts = c.encode_batch(*pack([b"one prompt only"]))        # fewer prompts than devices: one device does it
     assert np.array_equal(ids, oracle_vocabs[0].encode(0, b"one prompt only"))
+    ids, off, counts = c.encode_batch(data, offs, vid)                    # and the context still works after the failures
+    assert np.array_equal(ids, want_ids)
     c.close()
     assert torch.cuda.current_device() == 0
