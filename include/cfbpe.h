@@ -29,8 +29,10 @@
  * Conventions: 0 = ok, negative errno-style code = error; the caller
  * owns every buffer it passes and the library never retains a caller pointer past return;
  * the library owns device memory, pinned staging and streams; nothing throws across the
- * ABI; entry points taking a ctx may be called from several host threads (calls on one ctx
- * are serialised internally).  There is NO CPU fallback: cfbpe_create fails with
+ * ABI; entry points taking a ctx may be called from several host threads: a context holds
+ * cfbpe_config.n_workspaces independent call lanes per device (calls wait only when all are
+ * busy; vocabulary loads exclude running calls), the last error is kept per thread, and every
+ * entry point leaves the caller's current CUDA device as it found it.  There is NO CPU fallback: cfbpe_create fails with
  * CFBPE_ENODEV when no sm_100 device is present.
  *
  * Results are bit-exact with tiktoken 0.12.0 CoreBPE.encode_ordinary for the same rank
@@ -90,9 +92,11 @@ typedef struct cfbpe_config {
     uint32_t flags;           /* reserved, 0 */
     /* cfbpe_create(cfg: devices[], n_devices, ...) */
     int32_t devices[CFBPE_MAX_DEVICES]; /* CUDA ordinals of a multi-device context */
-    uint32_t n_devices;       /* 0 = single device (`device`); > 1: a host batch is sharded by bytes on prompt boundaries over the
-                                 devices, the packed tables are broadcast and the per-shard token totals gathered with NCCL
-                                 (libnccl.so.2 is dlopen'ed; without it cfbpe_create fails with CFBPE_EIO) */
+    uint32_t n_devices;       /* 0 = single device (`device`); > 1: the packed tables are broadcast with NCCL (libnccl.so.2 is
+                                 dlopen'ed; without it cfbpe_create fails with CFBPE_EIO) and a host batch is spread over the
+                                 devices -- its sub-batches round-robin, token ranks chained over NVLink peer memory, when
+                                 every device can hold the whole batch (<= max_batch_bytes); else one contiguous shard of
+                                 whole prompts a device, the shard totals gathered with NCCL */
     uint32_t n_workspaces;    /* independent workspaces per device (0 = 1, at most 16): that many calls run concurrently on the
                                  context; each costs ~33 bytes of device memory per byte of max_batch_bytes */
 } cfbpe_config;
