@@ -320,6 +320,49 @@ int validate_tables(const uint8_t* blob, uint64_t size, std::string& err) {
         !inside(h.off_long, static_cast<uint64_t>(h.cap_long) * sizeof(LongSlot)) ||
         !inside(h.off_tokoff, (static_cast<uint64_t>(h.n_ranks) + 1) * 4) ||
         !inside(h.off_blob, static_cast<uint64_t>(h.blob_bytes) + 16)) { err = "table blob: section out of bounds"; return CFBPE_EINVAL; }
+    // The CONTENT, not only the header: an imported blob comes from another process.  The device probes walk a table until
+    // they meet a free slot, read token bytes at stored offsets and index arrays with stored ids -- a table without free slots
+    // would spin a kernel forever, a wild offset or id would read outside the blob.
+    const uint64_t* pairs = reinterpret_cast<const uint64_t*>(blob + h.off_pair);
+    uint64_t free_pairs = 0;
+    for (uint32_t i = 0; i < h.cap_pair; ++i) {
+        const uint64_t sl = pairs[i];
+        if (sl == kPairEmpty) { ++free_pairs; continue; }
+        const uint32_t l = static_cast<uint32_t>(sl >> (2 * kIdBits)), r = static_cast<uint32_t>(sl >> kIdBits) & kIdMask, m = static_cast<uint32_t>(sl) & kIdMask;
+        if (l >= h.n_ranks || r >= h.n_ranks || m >= h.n_ranks) { err = "table blob: pair entry names an id outside the vocabulary"; return CFBPE_EINVAL; }
+    }
+    if (free_pairs * 2 < h.cap_pair) { err = "table blob: pair table more than half full"; return CFBPE_EINVAL; }
+    const ShortSlot* st = reinterpret_cast<const ShortSlot*>(blob + h.off_short);
+    uint64_t free_short = 0;
+    for (uint32_t i = 0; i < h.cap_short; ++i) {
+        if (st[i].meta == kMetaEmpty) { ++free_short; continue; }
+        if ((st[i].meta & 0x00FFFFFFu) >= h.n_ranks || (st[i].meta >> 24) > kShortMaxLen) { err = "table blob: short-token entry out of range"; return CFBPE_EINVAL; }
+    }
+    const LongSlot* lt = reinterpret_cast<const LongSlot*>(blob + h.off_long);
+    uint64_t free_long = 0;
+    for (uint32_t i = 0; i < h.cap_long; ++i) {
+        if (lt[i].meta == kMetaEmpty) { ++free_long; continue; }
+        const uint32_t len = lt[i].meta >> 24;
+        if ((lt[i].meta & 0x00FFFFFFu) >= h.n_ranks || static_cast<uint64_t>(lt[i].blob_off) + len > h.blob_bytes) { err = "table blob: long-token entry out of range"; return CFBPE_EINVAL; }
+    }
+    if (!free_short || !free_long) { err = "table blob: a token table has no free slot"; return CFBPE_EINVAL; }
+    const uint32_t* tokoff = reinterpret_cast<const uint32_t*>(blob + h.off_tokoff);
+    const uint32_t* byte2id = reinterpret_cast<const uint32_t*>(blob + h.off_byte2id);
+    const uint32_t* bytepair = reinterpret_cast<const uint32_t*>(blob + h.off_bytepair);
+    for (uint32_t i = 0; i < h.n_ranks; ++i)
+        if (tokoff[i] > tokoff[i + 1] || tokoff[i + 1] - tokoff[i] > 255) { err = "table blob: token offsets"; return CFBPE_EINVAL; }
+    if (tokoff[0] != 0 || tokoff[h.n_ranks] != h.blob_bytes) { err = "table blob: token offsets do not cover the byte blob"; return CFBPE_EINVAL; }
+    for (uint32_t i = 0; i < 256; ++i) if (byte2id[i] != kNone && byte2id[i] >= h.n_ranks) { err = "table blob: byte table"; return CFBPE_EINVAL; }
+    for (uint32_t i = 0; i < 65536; ++i) if (bytepair[i] != kNone && bytepair[i] >= h.n_ranks) { err = "table blob: byte-pair table"; return CFBPE_EINVAL; }
+    // the hash the builder left over (length, bytes) of every token in rank order: a blob that was altered after it was built fails here
+    const uint8_t* bytes = blob + h.off_blob;
+    uint64_t ch = 1469598103934665603ull;
+    for (uint32_t id = 0; id < h.n_ranks; ++id) {
+        const uint32_t len = tokoff[id + 1] - tokoff[id];
+        ch = (ch ^ len) * 1099511628211ull;
+        for (uint32_t i = 0; i < len; ++i) ch = (ch ^ bytes[tokoff[id] + i]) * 1099511628211ull;
+    }
+    if (ch != h.content_hash) { err = "table blob: content hash mismatch"; return CFBPE_EINVAL; }
     return CFBPE_OK;
 }
 

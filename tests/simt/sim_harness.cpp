@@ -58,6 +58,18 @@ __attribute__((visibility("default"))) void* sim_vocab_build(const uint8_t* file
     if (!v && err && errcap) { std::snprintf(err, errcap, "%s", e.c_str()); }
     return v;
 }
+// the packed tables of a built vocabulary (what cfbpe_vocab_export hands out) and the check cfbpe_vocab_import runs on a blob
+__attribute__((visibility("default"))) uint64_t sim_vocab_blob(void* vp, uint8_t* out, uint64_t cap) {
+    SimVocab* v = static_cast<SimVocab*>(vp);
+    if (out && cap >= v->blob.size()) std::memcpy(out, v->blob.data(), v->blob.size());
+    return v->blob.size();
+}
+__attribute__((visibility("default"))) int sim_validate_blob(const uint8_t* blob, uint64_t size, char* err, size_t errcap) {
+    std::string e;
+    const int rc = validate_tables(blob, size, e);
+    if (err && errcap) std::snprintf(err, errcap, "%s", e.c_str());
+    return rc;
+}
 __attribute__((visibility("default"))) unsigned long long sim_dbg_counter(uint32_t i, int reset) {
     unsigned long long* c = cfbpe::dbg_counters();
     const unsigned long long v = c[i & 15];

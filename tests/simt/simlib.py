@@ -34,10 +34,22 @@ def lib():
         L.sim_plan_sub_batches.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]
         L.sim_split_fixups.restype = C.c_ulonglong
         L.sim_split_fixups.argtypes = [C.c_int]
+        L.sim_vocab_blob.restype = C.c_uint64
+        L.sim_vocab_blob.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.sim_validate_blob.restype = C.c_int
+        L.sim_validate_blob.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_size_t]
         L.sim_dbg_counter.restype = C.c_ulonglong
         L.sim_dbg_counter.argtypes = [C.c_uint32, C.c_int]
         _lib = L
     return _lib
+
+
+def validate_blob(blob: np.ndarray):
+    """(rc, message) of the check cfbpe_vocab_import runs on a packed table blob"""
+    err = C.create_string_buffer(256)
+    b = np.ascontiguousarray(blob, dtype=np.uint8)
+    rc = lib().sim_validate_blob(b.ctypes.data, b.size, err, 256)
+    return rc, err.value.decode()
 
 
 def split_fixups(reset=False):
@@ -65,6 +77,13 @@ class SimVocab:
         if getattr(self, "_h", None):
             lib().sim_vocab_free(self._h)
             self._h = None
+
+    def blob(self) -> np.ndarray:
+        """the packed tables (what cfbpe_vocab_export hands out)"""
+        n = int(lib().sim_vocab_blob(self._h, None, 0))
+        out = np.empty(n, dtype=np.uint8)
+        lib().sim_vocab_blob(self._h, out.ctypes.data, n)
+        return out
 
     def piece_lookup(self, b: bytes):
         return lib().sim_piece_lookup(self._h, b, len(b))

@@ -66,3 +66,40 @@ def test_tekken_json_parser(toks):
 def test_bad_rank_files_are_rejected(bad):
     with pytest.raises(ValueError):
         simlib.SimVocab(bad, 0, 0, 0)
+
+
+def test_imported_blob_is_checked_by_content_not_only_by_header():
+    """cfbpe_vocab_import takes a blob from another process: the check walks the tables.  A table without free slots
+    would spin the device probes forever, a wild offset or id would read outside the blob, an altered token byte changes ids."""
+    import struct
+    ranks = b"".join(base64.b64encode(bytes([i])) + b" %d\n" % i for i in range(256))
+    ranks += b"".join(base64.b64encode(t) + b" %d\n" % (256 + i) for i, t in enumerate([b"ab", b"abc", b"th", b"the", b"a very long token indeed"]))
+    v = simlib.SimVocab(ranks, 0, 0)
+    good = v.blob()
+    assert simlib.validate_blob(good) == (0, "")
+    hdr = struct.unpack_from("<6I Q 7Q 4I Q", good, 0)
+    off_pair, off_short, off_long, off_tokoff, off_blob = hdr[9], hdr[10], hdr[11], hdr[12], hdr[13]
+    cap_pair, cap_long = hdr[14], hdr[16]
+
+    def broken(mut):
+        b = good.copy(); mut(b); rc, msg = simlib.validate_blob(b); assert rc != 0, msg; return msg
+
+    assert simlib.validate_blob(good[:40])[0] != 0                                        # truncated
+    assert "size" in simlib.validate_blob(np.concatenate([good, np.zeros(16, np.uint8)]))[1]
+    def fill_pairs(b):
+        b[off_pair:off_pair + 8 * cap_pair].view(np.uint64)[:] = (1 << 42) | (2 << 21) | 3
+    assert "half full" in broken(fill_pairs)
+    def wild_pair(b):
+        b[off_pair:off_pair + 8].view(np.uint64)[0] = (0x1FFFF0 << 42) | (2 << 21) | 3
+    assert "outside the vocabulary" in broken(wild_pair)
+    def wild_long(b):
+        slots = b[off_long:off_long + 16 * cap_long].view(np.uint32).reshape(-1, 4)
+        used = np.nonzero(slots[:, 2] != 0xFFFFFFFF)[0]
+        slots[used[0], 3] = 0x7FFFFFF0
+    assert "long-token" in broken(wild_long)
+    def altered_byte(b):
+        b[off_blob + 100] ^= 1
+    assert "content hash" in broken(altered_byte)
+    def bad_tokoff(b):
+        b[off_tokoff + 40:off_tokoff + 44].view(np.uint32)[0] = 0xFFFFFF
+    assert "token offsets" in broken(bad_tokoff)
