@@ -13,7 +13,10 @@ the per-shard token totals are all_gathered every step (the path's only exchange
   value     whole-job prompt-bytes/s, inputs resident in HBM (cfbpe_encode_batch_device on torch's stream)
   e2e       the same metric through the plugin / C ABI with pinned HOST buffers, H2D + D2H inside the timed region
   roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs the measured HBM copy peak
-  cpu_baseline  the oracle port on the host cores, bounded sample, rank 0 only
+  cpu_baseline  the oracle port on the host CPUs the container may use (cgroup quota), bounded sample, rank 0 only
+  + extra records (the headline is unchanged by them): kernel_ms (CUDA events inside the library), parity (every rank's ids against
+    the oracle), sustained (the device leg held ~2 s), strong / strong_one_context / config5 (the multi-GPU workloads BASELINE.json
+    names), host_cpu (was the container's CPU quota hit during the e2e leg), numa, cpu_baseline_context (tiktoken's own batch call)
 """
 import os
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initialises: the pipelined host path keeps ~20 streams busy (DESIGN.md section 4)
@@ -265,6 +268,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the batch (debug only; a scaled run is not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="skip the extra config-5 record")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0, help="extra record: the device leg held this long (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cfbpe" else args.warmup
     if args.impl == "reference":
@@ -373,6 +377,21 @@ def main():
     total_all = sum_over_ranks(float(total))
     tokens_all = sum_over_ranks(float(n_tokens))
     value = total_all * args.steps / (dev_ms * 1e-3)
+
+    # ---- the same leg held for ~2 s (the K timed steps above are tens of milliseconds): a sustained rate under sustained clocks
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / max(dev_ms / args.steps, 1e-3)))
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n_sus):
+            step_device()
+        s1.record()
+        barrier()
+        sus_ms = max_over_ranks(s0.elapsed_time(s1))
+        plug.ctx.device_status(stream)
+        sustained = {"steps": n_sus, "seconds": sus_ms / 1e3, "ms_per_step": sus_ms / n_sus, "value": total_all * n_sus / (sus_ms * 1e-3), "unit": UNIT}
 
     # ---- per-kernel device times (CUDA events inside the library, same stream), averaged over the steps
     plug.ctx.profile_enable(True)
@@ -611,7 +630,7 @@ def main():
                      "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
                      "path_algorithmic_bytes": path_alg,
                      "path_achieved_gbs": path_alg / (kernels_ms * 1e-3) / 1e9 if kernels_ms > 0 else 0.0},
-        "strong": strong, "strong_one_context": strong_lib, "host_cpu": host_cpu,
+        "strong": strong, "strong_one_context": strong_lib, "host_cpu": host_cpu, "sustained": sustained,
         "config5": config5,
         "numa": numa,
         "cpu_baseline": cpu,
