@@ -150,7 +150,7 @@ impl TokenizerClient for TokenizerService {
             ChatTemplate::Rendered { bos, message_prefix, message_suffix, generation_prompt, special_tokens } => {
                 // framing text and content between two control tokens form one stretch (the pre-tokenizer may join them)
                 let mut run = vec![String::new()];
-                let mut feed = |framing: &str, fixed: &mut u64, run: &mut Vec<String>| {
+                let feed = |framing: &str, fixed: &mut u64, run: &mut Vec<String>| {
                     let mut rest = framing;
                     loop {
                         let next = special_tokens.iter().filter_map(|t| rest.find(t.as_str()).map(|i| (i, t.len()))).min_by_key(|(i, l)| (*i, std::cmp::Reverse(*l)));
