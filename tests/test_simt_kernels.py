@@ -323,3 +323,54 @@ def test_utf8_validation_at_every_alignment():
     assert rc == -84
     rc, _ = simlib.split([0], [b"x" * 14 + b"\xe4\xb8", b"\xad def"])
     assert rc == -84
+
+
+@pytest.mark.parametrize("pat", [0, 1, 2, 3])
+def test_split_window_overruns(pat):
+    """A walker that has met no sync point by the end of its 32-byte window goes on with the product automaton over the next
+    blocks (split_extend, up to eight of them), then with the per-character walker.  Runs of 17 .. 200 bytes without a sync point
+    (spaces, mixed white space, digits, digits and white space alternating) at every alignment of the run's start, followed by
+    everything that can stop them: a letter, a contraction, a character of several bytes, punctuation, the end of the prompt --
+    and the same runs with prompt boundaries falling inside them (every prompt restarts the automaton)."""
+    import random
+    rng = random.Random(900 + pat)
+    runs = lambda n: [" " * n, "\t " * (n // 2), "7" * n, "0123456789" * (n // 10 + 1), " \n" * (n // 2), "\n" * n, "12 " * (n // 3), "　" * (n // 3)]
+    stops = ["a", "Zebra", "'s", "'ll x", "é", "中文", "!", "?!", "", "\n", "x1", "٣"]
+    strs = []
+    for n in (17, 24, 31, 32, 33, 47, 48, 49, 64, 100, 159, 160, 161, 200):
+        for r in runs(n):
+            for lead in range(0, 33, 3):
+                strs.append(("w" * lead + "." + r + rng.choice(stops) + " tail").encode())
+    rc, ends = simlib.split([pat], strs)
+    assert rc == 0
+    bad = [(p, e) for p, e in zip(strs, ends) if oracle.split(pat, p).tolist() != e]
+    assert not bad, bad[:3]
+    assert simlib.dbg_counter(8) >= 0
+    # prompt boundaries inside the runs: cut each string at a random byte (on a character boundary) into two prompts
+    cut_strs = []
+    for s in strs[::3]:
+        t = s.decode()
+        k = rng.randint(1, max(1, len(t) - 1))
+        cut_strs += [t[:k].encode(), t[k:].encode()]
+    rc, ends = simlib.split([pat], cut_strs)
+    assert rc == 0
+    bad = [(p, e) for p, e in zip(cut_strs, ends) if oracle.split(pat, p).tolist() != e]
+    assert not bad, bad[:3]
+
+
+def test_split_window_overruns_across_vocabularies():
+    """the same overruns in a multi-vocabulary batch: the prompt after a boundary inside a run may use another pattern"""
+    import random
+    rng = random.Random(77)
+    strs, vids = [], []
+    for n in (20, 33, 50, 90, 170):
+        for r in (" " * n, "7" * n, " \n" * (n // 2), "12 " * (n // 3)):
+            for lead in (0, 5, 14, 15, 16, 27):
+                t = "w" * lead + "," + r + rng.choice(["a", "'s", "é", "", "!"]) + " z"
+                k = rng.randint(1, len(t) - 1)
+                strs += [t[:k].encode(), t[k:].encode()]
+                vids += [rng.randrange(4), rng.randrange(4)]
+    rc, ends = simlib.split([0, 1, 2, 3], strs, vocab_ids=vids)
+    assert rc == 0
+    bad = [(v, p, e) for v, p, e in zip(vids, strs, ends) if oracle.split(v, p).tolist() != e]
+    assert not bad, bad[:3]
