@@ -3,11 +3,11 @@
 use std::sync::Arc;
 
 use axum::{Extension, Json};
-use llm_gateway_sdk::{TokenizerClient, TokenizerError};
+use llm_gateway_sdk::{ChatTemplate, TokenizerClient, TokenizerError};
 use modkit_errors::Problem;
 use modkit_security::SecurityContext;
 
-use crate::api::rest::dto::{TokenizeRequest, TokenizeResponse};
+use crate::api::rest::dto::{ChatTemplateDto, CountTokensRequest, CountTokensResponse, TokenizeRequest, TokenizeResponse};
 use crate::domain::service::TokenizerService;
 
 fn problem(e: TokenizerError) -> Problem {
@@ -31,4 +31,26 @@ pub async fn tokenize(
     let counts: Vec<u32> = ids.iter().map(|v| v.len() as u32).collect();
     let input_tokens = counts.iter().map(|c| u64::from(*c)).sum();
     Ok(Json(TokenizeResponse { counts, input_tokens, ids: req.return_ids.then_some(ids) }))
+}
+
+pub async fn count_tokens(
+    Extension(ctx): Extension<SecurityContext>,
+    Extension(service): Extension<Arc<TokenizerService>>,
+    Json(req): Json<CountTokensRequest>,
+) -> Result<Json<CountTokensResponse>, Problem> {
+    tracing::debug!(model = %req.model, messages = req.messages.len(), "count_tokens");
+    let usage = match req.template {
+        None => service.count_tokens(&ctx, &req.model, &req.messages).await,
+        Some(t) => {
+            let template = match t {
+                ChatTemplateDto::Overhead { tokens_per_message, tokens_per_name, reply_priming } => ChatTemplate::Overhead { tokens_per_message, tokens_per_name, reply_priming },
+                ChatTemplateDto::Rendered { bos, message_prefix, message_suffix, generation_prompt, special_tokens } => {
+                    ChatTemplate::Rendered { bos, message_prefix, message_suffix, generation_prompt, special_tokens }
+                }
+            };
+            service.count_chat_tokens(&ctx, &req.model, &req.messages, &template).await
+        }
+    }
+    .map_err(problem)?;
+    Ok(Json(CountTokensResponse { input_tokens: usage.input_tokens }))
 }

@@ -34,5 +34,19 @@ pub fn register_routes(mut router: Router, openapi: &dyn OpenApiRegistry, servic
         .standard_errors(openapi)
         .error_415(openapi)
         .register(router, openapi);
+    // POST /llm-gateway/v1/count-tokens - Usage.input_tokens of a chat request before it is sent (budget / context-window checks)
+    router = OperationBuilder::post("/llm-gateway/v1/count-tokens")
+        .operation_id("llm_gateway.count_tokens")
+        .summary("Count the input tokens of a chat request, with the provider's framing if a template is given")
+        .tag("LLM Gateway")
+        .authenticated()
+        .require_license_features::<License>([])
+        .json_request::<dto::CountTokensRequest>(openapi, "Messages, the model whose vocabulary applies, and optionally its chat template")
+        .allow_content_types(&["application/json"])
+        .handler(handlers::count_tokens)
+        .json_response_with_schema::<dto::CountTokensResponse>(openapi, http::StatusCode::OK, "Usage.input_tokens")
+        .standard_errors(openapi)
+        .error_415(openapi)
+        .register(router, openapi);
     router.layer(Extension(service))
 }
